@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py — photon primaries/s of the GPU dose engine on BASELINE.json's configs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3|c2|c1|c4] [--histories H]
+    python bench.py --impl reference ...      # the CPU arm (oracle port on all host cores)
+
+A "step" is one batch of H photon histories through the hot path on an already configured
+engine (label volume, tables and accumulators resident in HBM).  N > 1 (torchrun): one process
+per GPU, histories sharded by global history id (weak scaling: H per GPU per step), one NCCL
+reduce of every accumulator grid at the end of the run, inside the timed region.
+Prints ONE JSON line (see the field list in DESIGN.md section "Measurement").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "photon primaries/sec"
+UNIT = "primaries/s"
+
+
+def build_setup(name, histories):
+    from opengate_b200 import setups
+    if name == "c3":
+        return setups.make_c3(n_primaries=histories)
+    if name == "c2":
+        return setups.make_c2(n_primaries=histories)
+    if name == "c1":
+        return setups.make_c1(n_primaries=histories)
+    if name == "c4":
+        return setups.make_c4(n_primaries=histories)
+    if name == "c3small":  # CPU-container debugging only
+        return setups.make_c3(nx=128, ny=128, nz=75, spacing=(3.9, 3.9, 4.0), n_primaries=histories)
+    raise SystemExit(f"unknown config {name}")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for ln in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in ln.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._loop, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes_per_history(st, label_bytes, n_grids, phsp_row_bytes=0):
+    """B_hist = N_tent*s_label + N_flush*G*2*8 + f_out*s_rec  (SURVEY.md section 8d)."""
+    n = max(st["histories"], 1)
+    n_tent = st["tentative_collisions"] / n
+    n_dep = st["flushed_entries"] / n
+    f_out = st["phsp_rows"] / n
+    return n_tent * label_bytes + n_dep * n_grids * 2 * 8 + f_out * phsp_row_bytes, n_tent, n_dep, f_out
+
+
+def n_active_grids(S):
+    from opengate_b200 import abi
+    f = S.dose[0].score_flags | abi.SCORE_EDEP if S.dose else 0
+    return bin(f & 31).count("1")
+
+
+def cpu_baseline(S, seconds_target=15.0, threads=None):
+    """The oracle port on all host cores over a bounded sample of the same workload."""
+    from oracle.oracle import TransportOracle
+    threads = threads or os.cpu_count() or 1
+    orc = TransportOracle(S.seed)
+    sids, _, _ = S.apply(orc)
+    orc.begin_run()
+    probe = 20000 * threads
+    t0 = time.perf_counter()
+    orc.run_source(sids[0], 0, probe, threads)
+    dt = time.perf_counter() - t0
+    rate = probe / dt
+    n = int(min(max(rate * seconds_target, probe), 5e8))
+    t0 = time.perf_counter()
+    orc.run_source(sids[0], probe, n, threads)
+    dt = time.perf_counter() - t0
+    orc.close()
+    return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} histories of the same workload in {dt:.1f} s (CPU oracle, not Geant4)"}
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on the host cores. The reference's
+    own implementation is Geant4-MT, which is not in the reference tree and cannot be built
+    here, so this arm times the oracle port with every host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.oracle import TransportOracle
+    S = build_setup(args.config, args.histories)
+    threads = os.cpu_count() or 1
+    orc = TransportOracle(S.seed)
+    sids, _, _ = S.apply(orc)
+    orc.begin_run()
+    probe = 10000 * threads
+    t0 = time.perf_counter()
+    orc.run_source(sids[0], 0, probe, threads)
+    rate = probe / (time.perf_counter() - t0)
+    per_step = int(max(rate * args.ref_seconds_per_step, probe))
+    first = probe
+    for _ in range(args.warmup):
+        orc.run_source(sids[0], first, per_step // 4 + 1, threads)
+        first += per_step // 4 + 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.run_source(sids[0], first, per_step, threads)
+        first += per_step
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": S.name, "histories_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{per_step} histories per step x {args.steps} steps (CPU oracle on {threads} threads; Geant4 not available)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c3")
+    ap.add_argument("--histories", type=int, default=100_000_000, help="histories per step per GPU")
+    ap.add_argument("--e2e-histories", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-seconds-per-step", type=float, default=8.0)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = max(args.warmup, 1)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback on the product path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from opengate_b200 import abi, multigpu
+    from opengate_b200.core import Engine
+
+    H = args.histories
+    S = build_setup(args.config, H)
+    eng = Engine(local, S.seed)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    sids, dids, pids = S.apply(eng)
+    sid = sids[0]
+    G = n_active_grids(S)
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng.begin_run()
+    next_first = [rank * H]
+
+    def step():
+        flush_buf.fill_(1)  # evict L2 between steps (the timing rule); ~0.1 ms
+        eng.run_source(sid, next_first[0], H)
+        next_first[0] += world * H
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.begin_run()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    if world > 1:
+        multigpu.reduce_dose_grids(eng, dids, S, dst=0)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    st = eng.stats()
+    total_hist = world * H * args.steps
+    value = total_hist / (ms * 1e-3)
+
+    # roofline of the dominant (only) kernel: algorithmic bytes / kernel time on this rank
+    label_bytes = S.labels.dtype.itemsize
+    row_bytes = 76 if S.phsp else 0
+    b_hist, n_tent, n_dep, f_out = algorithmic_bytes_per_history(st, label_bytes, G, row_bytes)
+    kernel_ms = st["kernel_ms"] / max(args.steps, 1)
+    achieved = b_hist * H / (kernel_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": S.name, "histories_per_step_per_gpu": H, "seed": S.seed,
+                       "label_dtype": str(S.labels.dtype), "n_materials": len(S.tables.names),
+                       "l2": "256 MB L2 flush before every step; accumulator grids "
+                             f"({G} x {S.dose[0].size[0] * S.dose[0].size[1] * S.dose[0].size[2] * 8 / 1e6:.0f} MB) exceed L2",
+                       "parallelism": f"histories sharded over {world} GPU(s), NCCL reduce of {G} grids at end of run" if world > 1 else "1 GPU"},
+            "clocks": clocks,
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "kernel": "gb2::transport_kernel", "kernel_ms_per_launch": kernel_ms,
+                         "bytes_per_history": b_hist, "tentative_collisions_per_history": n_tent,
+                         "deposit_entries_per_history": n_dep, "phsp_rows_per_history": f_out,
+                         "label_bytes": label_bytes, "grids_per_deposit": G},
+            "stats": {k: st[k] for k in ("histories", "tentative_collisions", "n_phot", "n_compt", "n_rayl", "n_conv",
+                                         "flushed_entries", "buffer_overflows", "escaped", "edep_total_MeV")},
+        }
+    eng.close()
+    del flush_buf
+    torch.cuda.empty_cache()
+
+    # e2e: the same metric through the C-ABI with HOST buffers: every step uploads tables +
+    # label volume, runs, and reads the accumulator grids back to host memory.
+    He = args.e2e_histories or H
+    e2e = measure_e2e(S, He, local, rank, world, torch, dist, steps=max(2, min(args.steps, 3)))
+    if rank == 0:
+        line["e2e"] = e2e
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(S, args.cpu_seconds)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def measure_e2e(S, H, local, rank, world, torch, dist, steps=2):
+    from opengate_b200 import abi
+    from opengate_b200.core import Engine
+    G = n_active_grids(S)
+    nvox = S.dose[0].size[0] * S.dose[0].size[1] * S.dose[0].size[2]
+    host_out = [np.empty((S.dose[0].size[2], S.dose[0].size[1], S.dose[0].size[0]), dtype=np.float64) for _ in range(G)]
+    which = [w for w, f in ((abi.GRID_EDEP, abi.SCORE_EDEP), (abi.GRID_EDEP_SQ, abi.SCORE_EDEP_SQ),
+                            (abi.GRID_DOSE, abi.SCORE_DOSE), (abi.GRID_DOSE_SQ, abi.SCORE_DOSE_SQ),
+                            (abi.GRID_COUNTS, abi.SCORE_COUNTS)) if (S.dose[0].score_flags | abi.SCORE_EDEP) & f]
+    t = S.tables
+    h2d = S.labels.nbytes + sum(a.nbytes for a in (t.density, t.mu_total, t.cum_phot, t.cum_compt, t.cum_rayl,
+                                                   t.rayl_cum_ff2, t.compt_sf))
+    d2h = G * nvox * 8
+
+    def one(first):
+        eng = Engine(local, S.seed)
+        sids, dids, pids = S.apply(eng)       # H2D: tables + label volume (+ source CDFs)
+        eng.begin_run()
+        eng.run_source(sids[0], first, H)
+        for w, out in zip(which, host_out):   # D2H: every active accumulator grid
+            eng.dose_grid(dids[0], w, out)
+        eng.close()
+
+    one(rank * H)  # warm-up (page-in, allocator)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one((1 + i) * world * H + rank * H)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    return {"value": world * H * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "histories_per_step_per_gpu": H, "steps": steps,
+            "what": "gate_b200 C-ABI from host buffers: create + set_tables + set_image_volume (H2D) + run + get_dose_grid of every grid (D2H) per step"}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,225 @@
+/* gate_b200.h — C-ABI of the B200-native photon-in-voxel-volume dose engine.
+ *
+ * Plain C: pointers + sizes, no C++/torch/pybind types.  One engine handle is bound to one
+ * CUDA device and is driven by one host thread.  All functions return 0 on success and a
+ * non-zero GATE_B200_E* code on failure; gate_b200_last_error(h) gives the message.
+ * The caller owns every host buffer it passes; the library owns device memory.
+ *
+ * The reference (OpenGATE/opengate @ 9b07951) has NO engine plug-in ABI: the
+ * run phase is the pybind11 module `opengate_core` called from `opengate/engines.py`.
+ * Each entry point below cites the reference interface whose job it takes over for the
+ * photon-in-image-volume path; INTEGRATION.md shows the ctypes/pybind stub a maintainer
+ * would add to `core/opengate_core`.
+ *
+ * Units: Geant4 internal (mm, MeV, ns); densities in g/cm3; cross-section tables in 1/mm.
+ * Array layout: itk order, x fastest: flat = x + nx*(y + ny*z)
+ * (reference core/opengate_core/opengate_lib/GateDoseActor.cpp:332-334).
+ */
+#ifndef GATE_B200_H
+#define GATE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GATE_B200_ABI_VERSION 1
+
+enum {
+  GATE_B200_OK = 0,
+  GATE_B200_EINVAL = 1,   /* bad argument / unsupported configuration */
+  GATE_B200_ECUDA = 2,    /* CUDA runtime error (message has the cudaError string) */
+  GATE_B200_ESTATE = 3,   /* call order violated (e.g. run before tables are set) */
+  GATE_B200_ENOMEM = 4
+};
+
+typedef struct gate_b200_engine gate_b200_engine;
+
+/* ---- physics tables -------------------------------------------------------------------
+ * Replaces: Geant4 EM physics initialisation driven by opengate/engines.py:366-402
+ * (PhysicsEngine.initialize_before/after_runmanager) and opengate/physics.py:300-337; the
+ * table content follows the per-material export pattern of
+ * GateMaterialMuHandler::SimulateMaterialTable (GateMaterialMuHandler.cpp:296-549).
+ * Energy grid: n_energy nodes, log-uniform between e_min and e_max (inclusive).
+ * Momentum-transfer grid: n_q nodes, log-uniform in q^2 (1/bohr^2) between q2_min, q2_max. */
+typedef struct {
+  int32_t n_materials;
+  int32_t n_energy;
+  double e_min_MeV, e_max_MeV;
+  double e_cut_MeV;               /* photons below this are absorbed on the spot        */
+  const float *density_g_cm3;     /* [n_materials]                                       */
+  const float *mu_total_per_mm;   /* [n_materials][n_energy] total attenuation           */
+  const float *cum_phot;          /* [n_materials][n_energy] P(phot)                     */
+  const float *cum_compt;         /* [n_materials][n_energy] P(phot)+P(compt)            */
+  const float *cum_rayl;          /* [n_materials][n_energy] ...+P(Rayl); rest = conv    */
+  int32_t n_q;
+  double q2_min, q2_max;
+  const float *rayl_cum_ff2;      /* [n_materials][n_q] int_0^{q2} F_mol^2 d(q2)         */
+  const float *compt_sf;          /* [n_materials][n_q] S_mol(q2)/S_mol(inf) in [0,1]    */
+  int32_t pair_mode;              /* 0: whole E deposited locally (production-cut kerma
+                                        configuration of the reference, apply_cuts=True),
+                                     1: deposit E-2mc2 and emit two 511 keV photons      */
+} gate_b200_tables;
+
+/* ---- sources ----------------------------------------------------------------------------
+ * Replaces: GateGenericSource::InitializePosition/Direction/Energy
+ * (GateGenericSource.cpp:312-664), GateSPSEneDistribution.cpp:16-157,
+ * GateSPSVoxelsPosDistribution.cpp:29-72, GateVSource.cpp:95-107 (attached-volume frame).
+ * All frames are already composed to WORLD by the caller. */
+enum { GATE_B200_POS_POINT = 0, GATE_B200_POS_BOX = 1, GATE_B200_POS_SPHERE = 2,
+       GATE_B200_POS_DISC = 3, GATE_B200_POS_CYLINDER = 4, GATE_B200_POS_VOXELS = 5 };
+enum { GATE_B200_DIR_ISO = 0, GATE_B200_DIR_MOMENTUM = 1, GATE_B200_DIR_FOCUSED = 2 };
+enum { GATE_B200_ENE_MONO = 0, GATE_B200_ENE_GAUSS = 1, GATE_B200_ENE_RANGE = 2,
+       GATE_B200_ENE_SPECTRUM_DISCRETE = 3, GATE_B200_ENE_SPECTRUM_HISTOGRAM = 4,
+       GATE_B200_ENE_SPECTRUM_HISTOGRAM_LINEAR = 5, GATE_B200_ENE_CDF = 6 };
+
+typedef struct {
+  int32_t pos_type;
+  double half_size[3];            /* box half sizes; cylinder: half_size[2] = dz         */
+  double radius, sigma_x, sigma_y;
+  double pos_rotation[9];         /* row-major, local -> world                            */
+  double pos_translation[3];
+  int32_t dir_type;
+  double theta[2], phi[2];        /* iso: [min,max] in rad                                */
+  double momentum[3];             /* world frame                                          */
+  double focus_point[3];          /* world frame                                          */
+  int32_t dir_relative;           /* 1: rotate sampled direction by dir_rotation          */
+  double dir_rotation[9];
+  int32_t ene_type;
+  double mono_MeV, sigma_MeV, e_min_MeV, e_max_MeV;
+  int32_t n_spectrum;             /* entries in spectrum_cdf                              */
+  const double *spectrum_energy;  /* discrete: [n]; histogram: [n+1] edges; cdf: [n]      */
+  const double *spectrum_cdf;     /* normalised cumulative weights, last == 1             */
+  double weight;
+  /* voxelised activity (pos_type == VOXELS): numpy (z,y,x) CDFs as built by
+   * opengate/image.py:313-358 */
+  int32_t vox_size[3];            /* nx, ny, nz                                           */
+  double vox_spacing[3];
+  double vox_origin[3];           /* centre of voxel (0,0,0) in the source frame          */
+  const float *cdf_z;             /* [nz]                                                  */
+  const float *cdf_y;             /* [nz][ny]                                              */
+  const float *cdf_x;             /* [nz][ny][nx]                                          */
+} gate_b200_source;
+
+/* ---- dose actor -------------------------------------------------------------------------
+ * Replaces: GateDoseActor (GateDoseActor.cpp:144-243, 359-397) + AttachImageToVolume
+ * (GateHelpersImage.txx:20-58). world_to_index maps a WORLD point p to the continuous
+ * index c = A*p + b (row-major 3x4); the voxel is round-half-up(c) as itk's
+ * TransformPhysicalPointToIndex does. */
+enum { GATE_B200_HIT_RANDOM = 0, GATE_B200_HIT_PRE = 1, GATE_B200_HIT_POST = 2,
+       GATE_B200_HIT_MIDDLE = 3 };
+enum { GATE_B200_SCORE_EDEP = 1, GATE_B200_SCORE_EDEP_SQ = 2, GATE_B200_SCORE_DOSE = 4,
+       GATE_B200_SCORE_DOSE_SQ = 8, GATE_B200_SCORE_COUNTS = 16 };
+enum { GATE_B200_GRID_EDEP = 0, GATE_B200_GRID_EDEP_SQ = 1, GATE_B200_GRID_DOSE = 2,
+       GATE_B200_GRID_DOSE_SQ = 3, GATE_B200_GRID_COUNTS = 4 };
+
+typedef struct {
+  int32_t size[3];
+  double world_to_index[12];
+  int32_t score_flags;            /* OR of GATE_B200_SCORE_*                              */
+  int32_t hit_type;
+} gate_b200_dose_desc;
+
+/* ---- phase-space actor --------------------------------------------------------------------
+ * Replaces: GatePhaseSpaceActor::SteppingAction (GatePhaseSpaceActor.cpp:119-201) for a Box
+ * volume placed in the world, steps_to_store entering/exiting, and the digi attributes
+ * KineticEnergy, PrePosition/Position, PreDirection/Direction, Weight, EventID,
+ * GlobalTime/TimeFromBeginOfEvent (GateDigiAttributeList.cpp:42-279). */
+enum { GATE_B200_PHSP_ENTERING = 1, GATE_B200_PHSP_EXITING = 2 };
+
+typedef struct {
+  double half_size[3];            /* of the Box the actor is attached to                  */
+  double world_to_box[12];        /* row-major 3x4: p_box = A*p_world + b                 */
+  int32_t steps_to_store;         /* OR of GATE_B200_PHSP_*                               */
+  uint64_t capacity;              /* rows reserved on the device                          */
+} gate_b200_phsp_desc;
+
+/* One stored row (structure of arrays on the device, gathered by gate_b200_get_phsp). */
+typedef struct {
+  float *kinetic_energy;          /* [n] MeV                                              */
+  float *position;                /* [n][3] world, mm (PrePosition if entering)           */
+  float *direction;               /* [n][3]                                               */
+  float *weight;                  /* [n]                                                  */
+  float *time_ns;                 /* [n] time from begin of event                         */
+  int64_t *event_id;              /* [n]                                                  */
+  int32_t *flags;                 /* [n] GATE_B200_PHSP_ENTERING / EXITING                */
+} gate_b200_phsp_columns;
+
+/* ---- run statistics -----------------------------------------------------------------------
+ * Replaces: GateSimulationStatisticsActor counters (GateSimulationStatisticsActor.cpp:42-226)
+ * plus the device counters the roofline figure is built from. */
+typedef struct {
+  uint64_t histories;             /* events                                               */
+  uint64_t tracks;
+  uint64_t steps;                 /* real interactions + boundary crossings              */
+  uint64_t tentative_collisions;  /* Woodcock candidates = label gathers                  */
+  uint64_t n_phot, n_compt, n_rayl, n_conv;
+  uint64_t deposits;              /* deposit events before per-history coalescing        */
+  uint64_t flushed_entries;       /* (voxel, history) pairs written to the grids         */
+  uint64_t buffer_overflows;      /* per-history coalescing buffer evictions             */
+  uint64_t escaped;               /* histories whose photon left the world               */
+  uint64_t phsp_rows, phsp_dropped;
+  uint64_t absorbed_events;       /* histories that never reached any phase-space plane  */
+  double edep_total_MeV;          /* everything deposited (also outside scoring grids)   */
+  double kernel_ms;               /* device time of the transport launches of this run   */
+} gate_b200_stats;
+
+/* ---- life cycle --------------------------------------------------------------------------- */
+int gate_b200_abi_version(void);
+/* Replaces: SimulationEngine.__init__/initialize_random_engine (engines.py:1414,1669-1698).
+ * seed is the Philox key; history h uses counter (h, block) so results do not depend on the
+ * number of GPUs or on scheduling. */
+int gate_b200_create(int device_id, uint64_t seed, gate_b200_engine **out);
+void gate_b200_destroy(gate_b200_engine *h);
+const char *gate_b200_last_error(const gate_b200_engine *h);
+/* Launch on the caller's stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = own. */
+int gate_b200_set_stream(gate_b200_engine *h, void *cuda_stream);
+
+int gate_b200_set_tables(gate_b200_engine *h, const gate_b200_tables *t);
+/* Replaces: VolumeEngine.Construct for the world box (engines.py:1166-1181). */
+int gate_b200_set_world(gate_b200_engine *h, const double half_size[3], int32_t material);
+/* Replaces: ImageVolume.construct + GateImageNestedParameterisation
+ * (volumes.py:1049-1125, GateImageNestedParameterisation.cpp:19-75). labels: nx*ny*nz,
+ * x fastest, label_bytes 1 or 2 (the reference uses unsigned short). world_to_volume maps a
+ * world point to the volume frame whose origin is the volume centre. */
+int gate_b200_set_image_volume(gate_b200_engine *h, const void *labels, int32_t label_bytes,
+                               const int32_t size[3], const double spacing[3],
+                               const double world_to_volume[12]);
+int gate_b200_add_source(gate_b200_engine *h, const gate_b200_source *s, int32_t *source_id);
+int gate_b200_add_dose_actor(gate_b200_engine *h, const gate_b200_dose_desc *d, int32_t *actor_id);
+int gate_b200_add_phsp_actor(gate_b200_engine *h, const gate_b200_phsp_desc *d, int32_t *actor_id);
+
+/* Replaces: GateSourceManager::StartMasterThread run loop (GateSourceManager.cpp:198-244):
+ * begin_run zeroes the accumulators (BeginOfRunActionMasterThread), run_source enqueues
+ * n histories of one source whose global ids are first_history.. (EventID), sync waits. */
+int gate_b200_begin_run(gate_b200_engine *h, int32_t run_id);
+int gate_b200_run_source(gate_b200_engine *h, int32_t source_id, uint64_t first_history,
+                         uint64_t n_histories);
+int gate_b200_sync(gate_b200_engine *h);
+
+/* Replaces: fetch_from_cpp_image (doseactors.py:255-270): copy one accumulator grid
+ * (double, nx*ny*nz) to the host. */
+int gate_b200_get_dose_grid(gate_b200_engine *h, int32_t actor_id, int32_t which, double *out);
+/* Device pointer of an accumulator grid (for the NCCL reduce done by the host plumbing). */
+int gate_b200_dose_grid_device_ptr(gate_b200_engine *h, int32_t actor_id, int32_t which,
+                                   void **ptr, uint64_t *n_elements);
+/* Host -> device overwrite of an accumulator (used after a reduce / for merging runs). */
+int gate_b200_set_dose_grid(gate_b200_engine *h, int32_t actor_id, int32_t which, const double *in);
+/* Replaces: GateDoseActor::ComputeMeanUncertainty (GateDoseActor.cpp:280-330). */
+int gate_b200_mean_uncertainty(gate_b200_engine *h, int32_t actor_id, uint64_t n_events,
+                               int32_t top_voxels, double threshold, double *out);
+int gate_b200_phsp_count(gate_b200_engine *h, int32_t actor_id, uint64_t *n_rows);
+int gate_b200_get_phsp(gate_b200_engine *h, int32_t actor_id, uint64_t max_rows,
+                       const gate_b200_phsp_columns *out, uint64_t *n_rows);
+int gate_b200_get_stats(gate_b200_engine *h, gate_b200_stats *out);
+
+/* One-call convenience used by benchmarks: upload nothing, just time `n` histories of an
+ * already configured source (same as run_source + sync) and return device milliseconds. */
+int gate_b200_timed_run(gate_b200_engine *h, int32_t source_id, uint64_t first_history,
+                        uint64_t n_histories, double *device_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GATE_B200_H */

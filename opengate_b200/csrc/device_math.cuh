@@ -1,0 +1,120 @@
+// device_math.cuh — the arithmetic contract of the transport kernel.
+//
+// Only IEEE single-precision +,-,*,/ and sqrt are used (the file is compiled with
+// -fmad=false, so nvcc never contracts a*b+c into an FMA); logarithm, exponential and
+// sin/cos are the polynomials below, not the CUDA math library, so that a scalar CPU
+// implementation of the same formulas (oracle/transport_oracle.c) reproduces every history
+// bit for bit.
+#pragma once
+#include <cstdint>
+
+namespace gb2 {
+
+__device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
+__device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }
+
+// natural logarithm: x = m 2^k, m in [sqrt(1/2), sqrt(2)); log(m) by the classic
+// s = f/(2+f) series with a degree-4 minimax polynomial in s^2 (FreeBSD msun e_logf.c).
+__device__ __forceinline__ float d_logf(float x) {
+  const float ln2_hi = 6.9313812256e-01f, ln2_lo = 9.0580006145e-06f;
+  const float Lg1 = 0.66666662693f, Lg2 = 0.40000972152f, Lg3 = 0.28498786688f,
+              Lg4 = 0.24279078841f;
+  uint32_t ix = f2u(x);
+  ix += 0x3f800000u - 0x3f3504f3u;
+  int k = (int)(ix >> 23) - 0x7f;
+  ix = (ix & 0x007fffffu) + 0x3f3504f3u;
+  float m = u2f(ix);
+  float f = m - 1.0f;
+  float s = f / (2.0f + f);
+  float z = s * s;
+  float w = z * z;
+  float t1 = w * (Lg2 + w * Lg4);
+  float t2 = z * (Lg1 + w * Lg3);
+  float R = t2 + t1;
+  float hfsq = 0.5f * f * f;
+  float dk = (float)k;
+  return s * (hfsq + R) + dk * ln2_lo - hfsq + f + dk * ln2_hi;
+}
+
+// exp(x) for moderate |x|: x = n ln2 + r, degree-6 Taylor polynomial in r, scale by 2^n.
+__device__ __forceinline__ float d_expf(float x) {
+  const float log2e = 1.44269504089f, ln2_hi = 6.9313812256e-01f, ln2_lo = 9.0580006145e-06f;
+  float fn = floorf(x * log2e + 0.5f);
+  float r = x - fn * ln2_hi;
+  r = r - fn * ln2_lo;
+  float p = 1.0f / 720.0f;
+  p = p * r + 1.0f / 120.0f;
+  p = p * r + 1.0f / 24.0f;
+  p = p * r + 1.0f / 6.0f;
+  p = p * r + 0.5f;
+  p = p * r + 1.0f;
+  p = p * r + 1.0f;
+  int n = (int)fn;
+  if (n < -126) return 0.0f;
+  return p * u2f((uint32_t)(n + 127) << 23);
+}
+
+// sin and cos of 2*pi*t, t in [0,1): quadrant reduction, |a| <= pi/4 polynomials.
+__device__ __forceinline__ void d_sincos2pi(float t, float &s, float &c) {
+  float y = t * 4.0f;
+  float fk = floorf(y + 0.5f);
+  float r = y - fk;
+  float a = r * 1.57079632679f;
+  float a2 = a * a;
+  float sp = a2 * 2.75573192e-6f + -1.98412698e-4f;
+  sp = sp * a2 + 8.33333333e-3f;
+  sp = sp * a2 + -1.66666667e-1f;
+  float sn = a + a * a2 * sp;
+  float cp = a2 * 2.48015873e-5f + -1.38888889e-3f;
+  cp = cp * a2 + 4.16666667e-2f;
+  cp = cp * a2 + -0.5f;
+  float cs = 1.0f + a2 * cp;
+  int q = ((int)fk) & 3;
+  if (q == 0) { s = sn; c = cs; }
+  else if (q == 1) { s = cs; c = -sn; }
+  else if (q == 2) { s = -sn; c = -cs; }
+  else { s = -cs; c = sn; }
+}
+
+// Philox4x32-10 counter-based generator (Salmon et al., SC'11). key = run seed,
+// counter = (history id lo, hi, block number, 0).
+struct Rng {
+  uint32_t k0, k1, h0, h1, blk;
+  uint32_t o0, o1, o2, o3;
+  int pos;
+};
+
+__device__ __forceinline__ void philox_block(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
+                                             uint32_t c2, uint32_t c3, uint32_t &r0, uint32_t &r1,
+                                             uint32_t &r2, uint32_t &r3) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0;
+    uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  r0 = c0; r1 = c1; r2 = c2; r3 = c3;
+}
+
+__device__ __forceinline__ void rng_init(Rng &r, uint64_t seed, uint64_t hist) {
+  r.k0 = (uint32_t)seed; r.k1 = (uint32_t)(seed >> 32);
+  r.h0 = (uint32_t)hist; r.h1 = (uint32_t)(hist >> 32);
+  r.blk = 0; r.pos = 4;
+}
+
+// uniform in (0,1): the top 24 bits, centred in their bin
+__device__ __forceinline__ float rng_uniform(Rng &r) {
+  if (r.pos == 4) {
+    philox_block(r.k0, r.k1, r.h0, r.h1, r.blk, 0u, r.o0, r.o1, r.o2, r.o3);
+    r.blk += 1u;
+    r.pos = 0;
+  }
+  uint32_t x = r.pos == 0 ? r.o0 : (r.pos == 1 ? r.o1 : (r.pos == 2 ? r.o2 : r.o3));
+  r.pos += 1;
+  return (float)(x >> 8) * 5.9604644775390625e-8f + 2.98023223876953125e-8f;
+}
+
+}  // namespace gb2

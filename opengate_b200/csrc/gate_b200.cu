@@ -1,0 +1,604 @@
+// gate_b200.cu — host side of the C-ABI declared in include/gate_b200.h.
+//
+// Owns all device memory of one engine (tables, label volume, accumulator grids, phase-space
+// columns, statistics), converts the double-precision descriptors of the ABI to the float
+// device model exactly once (same expressions as the oracle so both sides see identical
+// constants), and launches gb2::transport_kernel as a persistent grid sized from the SM
+// count.  No torch, no pybind: plain CUDA runtime.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "transport.cuh"
+
+using namespace gb2;
+
+namespace {
+
+struct DeviceBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+};
+
+struct DoseActor {
+  gate_b200_dose_desc desc;
+  DDose dev;
+  size_t nvox = 0;
+};
+
+struct PhspActor {
+  gate_b200_phsp_desc desc;
+  DPhsp dev;
+};
+
+struct SourceRec {
+  DSource dev;
+};
+
+}  // namespace
+
+struct gate_b200_engine {
+  int device = 0;
+  uint64_t seed = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  bool have_tables = false, have_volume = false;
+  Params P;
+  std::vector<void *> allocs;           // everything to cudaFree
+  std::vector<float> h_mu;              // host copy for the majorant
+  std::vector<DoseActor> dose;
+  std::vector<PhspActor> phsp;
+  std::vector<SourceRec> src;
+  float *d_maj = nullptr;
+  void *d_labels = nullptr;
+  unsigned long long *d_next = nullptr;
+  unsigned long long *d_stats = nullptr;
+  double *d_edep = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_events;
+  double kernel_ms = 0.0;
+  int sm_count = 148;
+  int block = 256, blocks_per_sm = 0;
+  int label_bytes = 0;
+};
+
+namespace {
+
+int fail(gate_b200_engine *h, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  return code;
+}
+
+#define CU(call)                                                                             \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess)                                                                   \
+      return fail(h, GATE_B200_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                       \
+  } while (0)
+
+template <typename T>
+int dev_alloc(gate_b200_engine *h, T **out, size_t n, bool zero = false) {
+  void *p = nullptr;
+  CU(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+  if (zero) CU(cudaMemsetAsync(p, 0, std::max<size_t>(n, 1) * sizeof(T), h->stream));
+  h->allocs.push_back(p);
+  *out = static_cast<T *>(p);
+  return 0;
+}
+
+template <typename T>
+int dev_upload(gate_b200_engine *h, const T **out, const T *src, size_t n) {
+  T *p = nullptr;
+  int rc = dev_alloc(h, &p, n);
+  if (rc) return rc;
+  CU(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  *out = p;
+  return 0;
+}
+
+void affine_from_double(Affine &a, const double m12[12]) {
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) a.m[3 * r + c] = (float)m12[4 * r + c];
+    a.t[r] = (float)m12[4 * r + 3];
+  }
+}
+
+int collect_kernel_time(gate_b200_engine *h) {
+  for (auto &pr : h->pending_events) {
+    float ms = 0.f;
+    CU(cudaEventSynchronize(pr.second));
+    CU(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    h->kernel_ms += ms;
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  h->pending_events.clear();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gate_b200_abi_version(void) { return GATE_B200_ABI_VERSION; }
+
+int gate_b200_create(int device_id, uint64_t seed, gate_b200_engine **out) {
+  if (!out) return GATE_B200_EINVAL;
+  *out = nullptr;
+  gate_b200_engine *h = new (std::nothrow) gate_b200_engine();
+  if (!h) return GATE_B200_ENOMEM;
+  *out = h;  // returned even on failure so that the caller can read last_error
+  h->device = device_id;
+  h->seed = seed;
+  memset(&h->P, 0, sizeof h->P);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(h, GATE_B200_ECUDA, "no CUDA device available: %s (the engine has no CPU fallback)",
+                cudaGetErrorString(e));
+  if (device_id < 0 || device_id >= ndev)
+    return fail(h, GATE_B200_EINVAL, "device %d out of range (%d devices)", device_id, ndev);
+  CU(cudaSetDevice(device_id));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device_id));
+  h->sm_count = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->own_stream = true;
+  if (int rc = dev_alloc(h, &h->d_next, 1, true)) return rc;
+  if (int rc = dev_alloc(h, &h->d_stats, (size_t)S_COUNT, true)) return rc;
+  if (int rc = dev_alloc(h, &h->d_edep, 1, true)) return rc;
+  h->P.seed = seed;
+  h->P.next = h->d_next;
+  h->P.stats = h->d_stats;
+  h->P.edep_total = h->d_edep;
+  h->P.wh[0] = h->P.wh[1] = h->P.wh[2] = 1.0e6f;
+  if (const char *s = getenv("GATE_B200_BLOCK")) h->block = std::max(32, atoi(s) / 32 * 32);
+  if (const char *s = getenv("GATE_B200_BLOCKS_PER_SM")) h->blocks_per_sm = atoi(s);
+  return GATE_B200_OK;
+}
+
+void gate_b200_destroy(gate_b200_engine *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto &pr : h->pending_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  for (void *p : h->allocs) cudaFree(p);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char *gate_b200_last_error(const gate_b200_engine *h) { return h ? h->err.c_str() : "null engine"; }
+
+int gate_b200_set_stream(gate_b200_engine *h, void *cuda_stream) {
+  if (!h) return GATE_B200_EINVAL;
+  CU(cudaSetDevice(h->device));
+  if (h->stream) CU(cudaStreamSynchronize(h->stream));
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  if (cuda_stream == nullptr) {
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+  } else {
+    h->stream = static_cast<cudaStream_t>(cuda_stream);
+    h->own_stream = false;
+  }
+  return GATE_B200_OK;
+}
+
+int gate_b200_set_tables(gate_b200_engine *h, const gate_b200_tables *t) {
+  if (!h || !t) return GATE_B200_EINVAL;
+  if (t->n_materials < 1 || t->n_energy < 2 || t->n_q < 2)
+    return fail(h, GATE_B200_EINVAL, "tables: need >=1 material, >=2 energy and q nodes");
+  if (!(t->e_min_MeV > 0) || !(t->e_max_MeV > t->e_min_MeV) || !(t->q2_max > t->q2_min) || !(t->q2_min > 0))
+    return fail(h, GATE_B200_EINVAL, "tables: bad grid limits");
+  CU(cudaSetDevice(h->device));
+  Params &P = h->P;
+  P.nmat = t->n_materials; P.ne = t->n_energy; P.nq = t->n_q; P.pair_mode = t->pair_mode;
+  const size_t n = (size_t)P.nmat * P.ne, nqq = (size_t)P.nmat * P.nq;
+  if (int rc = dev_upload(h, &P.dens, t->density_g_cm3, (size_t)P.nmat)) return rc;
+  if (int rc = dev_upload(h, &P.mu, t->mu_total_per_mm, n)) return rc;
+  if (int rc = dev_upload(h, &P.cph, t->cum_phot, n)) return rc;
+  if (int rc = dev_upload(h, &P.cco, t->cum_compt, n)) return rc;
+  if (int rc = dev_upload(h, &P.cra, t->cum_rayl, n)) return rc;
+  if (int rc = dev_upload(h, &P.ray, t->rayl_cum_ff2, nqq)) return rc;
+  if (int rc = dev_upload(h, &P.sf, t->compt_sf, nqq)) return rc;
+  h->h_mu.assign(t->mu_total_per_mm, t->mu_total_per_mm + n);
+  const double le0 = log(t->e_min_MeV), le1 = log(t->e_max_MeV);
+  P.ln_emin = (float)le0;
+  P.inv_dlne = (float)((double)(P.ne - 1) / (le1 - le0));
+  P.e_cut = (float)t->e_cut_MeV;
+  const double lq0 = log(t->q2_min), lq1 = log(t->q2_max);
+  P.ln_q2min = (float)lq0;
+  P.inv_dlnq2 = (float)((double)(P.nq - 1) / (lq1 - lq0));
+  std::vector<float> q2n(P.nq);
+  for (int j = 0; j < P.nq; ++j)
+    q2n[j] = (float)exp(lq0 + (lq1 - lq0) * (double)j / (double)(P.nq - 1));
+  if (int rc = dev_upload(h, &P.q2n, q2n.data(), q2n.size())) return rc;
+  if (int rc = dev_alloc(h, &h->d_maj, (size_t)P.ne, true)) return rc;
+  P.maj = h->d_maj;
+  h->have_tables = true;
+  return GATE_B200_OK;
+}
+
+int gate_b200_set_world(gate_b200_engine *h, const double half_size[3], int32_t material) {
+  if (!h || !half_size) return GATE_B200_EINVAL;
+  if (!h->have_tables) return fail(h, GATE_B200_ESTATE, "set_world before set_tables");
+  if (material < 0 || material >= h->P.nmat) return fail(h, GATE_B200_EINVAL, "world material %d out of range", material);
+  for (int a = 0; a < 3; ++a) h->P.wh[a] = (float)half_size[a];
+  h->P.world_mat = material;
+  return GATE_B200_OK;
+}
+
+int gate_b200_set_image_volume(gate_b200_engine *h, const void *labels, int32_t label_bytes,
+                               const int32_t size[3], const double spacing[3],
+                               const double world_to_volume[12]) {
+  if (!h || !labels || !size || !spacing || !world_to_volume) return GATE_B200_EINVAL;
+  if (!h->have_tables) return fail(h, GATE_B200_ESTATE, "set_image_volume before set_tables");
+  if (label_bytes != 1 && label_bytes != 2) return fail(h, GATE_B200_EINVAL, "label_bytes must be 1 or 2");
+  if (!h->dose.empty()) return fail(h, GATE_B200_ESTATE, "set_image_volume after add_dose_actor");
+  CU(cudaSetDevice(h->device));
+  Params &P = h->P;
+  const size_t nv = (size_t)size[0] * size[1] * size[2];
+  if (nv == 0) return fail(h, GATE_B200_EINVAL, "empty image volume");
+  // materials present -> majorant (same rule as the oracle's build_majorant)
+  std::vector<char> present(P.nmat, 0);
+  if (label_bytes == 1) {
+    const uint8_t *l = static_cast<const uint8_t *>(labels);
+    for (size_t i = 0; i < nv; ++i) {
+      if (l[i] >= P.nmat) return fail(h, GATE_B200_EINVAL, "label %d at voxel %zu has no material", (int)l[i], i);
+      present[l[i]] = 1;
+    }
+  } else {
+    const uint16_t *l = static_cast<const uint16_t *>(labels);
+    for (size_t i = 0; i < nv; ++i) {
+      if (l[i] >= P.nmat) return fail(h, GATE_B200_EINVAL, "label %d at voxel %zu has no material", (int)l[i], i);
+      present[l[i]] = 1;
+    }
+  }
+  std::vector<float> maj(P.ne, 0.f);
+  for (int i = 0; i < P.ne; ++i) {
+    float mx = 0.f;
+    for (int m = 0; m < P.nmat; ++m)
+      if (present[m] && h->h_mu[(size_t)m * P.ne + i] > mx) mx = h->h_mu[(size_t)m * P.ne + i];
+    maj[i] = mx;
+  }
+  CU(cudaMemcpy(h->d_maj, maj.data(), maj.size() * sizeof(float), cudaMemcpyHostToDevice));
+  uint8_t *dl = nullptr;
+  if (int rc = dev_alloc(h, &dl, nv * label_bytes)) return rc;
+  CU(cudaMemcpy(dl, labels, nv * label_bytes, cudaMemcpyHostToDevice));
+  h->d_labels = dl;
+  P.labels = dl;
+  for (int a = 0; a < 3; ++a) {
+    P.n[a] = size[a];
+    P.sp[a] = (float)spacing[a];
+    P.inv_sp[a] = (float)(1.0 / spacing[a]);
+    P.half[a] = (float)(0.5 * size[a] * spacing[a]);
+  }
+  affine_from_double(P.w2v, world_to_volume);
+  P.has_vol = 1;
+  h->have_volume = true;
+  h->label_bytes = label_bytes;
+  return GATE_B200_OK;
+}
+
+int gate_b200_add_source(gate_b200_engine *h, const gate_b200_source *s, int32_t *source_id) {
+  if (!h || !s) return GATE_B200_EINVAL;
+  CU(cudaSetDevice(h->device));
+  SourceRec rec;
+  DSource &d = rec.dev;
+  memset(&d, 0, sizeof d);
+  d.pos_type = s->pos_type; d.dir_type = s->dir_type; d.ene_type = s->ene_type;
+  d.dir_relative = s->dir_relative;
+  if (d.pos_type < 0 || d.pos_type > GATE_B200_POS_VOXELS) return fail(h, GATE_B200_EINVAL, "bad pos_type %d", d.pos_type);
+  if (d.dir_type < 0 || d.dir_type > GATE_B200_DIR_FOCUSED) return fail(h, GATE_B200_EINVAL, "bad dir_type %d", d.dir_type);
+  if (d.ene_type < 0 || d.ene_type > GATE_B200_ENE_CDF) return fail(h, GATE_B200_EINVAL, "bad ene_type %d", d.ene_type);
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) {
+      d.pos.m[3 * r + c] = (float)s->pos_rotation[3 * r + c];
+      d.dir_rot[3 * r + c] = (float)s->dir_rotation[3 * r + c];
+    }
+    d.pos.t[r] = (float)s->pos_translation[r];
+    d.mom[r] = (float)s->momentum[r];
+    d.focus[r] = (float)s->focus_point[r];
+    d.half[r] = (float)s->half_size[r];
+    d.vox_n[r] = s->vox_size[r];
+    d.vox_sp[r] = (float)s->vox_spacing[r];
+    d.vox_org[r] = (float)s->vox_origin[r];
+  }
+  d.radius = (float)s->radius; d.sigma_x = (float)s->sigma_x; d.sigma_y = (float)s->sigma_y;
+  d.cos_tmin = (float)cos(s->theta[0]); d.cos_tmax = (float)cos(s->theta[1]);
+  d.phi0_turn = (float)(s->phi[0] / 6.283185307179586);
+  d.dphi_turn = (float)((s->phi[1] - s->phi[0]) / 6.283185307179586);
+  d.mono = (float)s->mono_MeV; d.sigma = (float)s->sigma_MeV;
+  d.emin = (float)s->e_min_MeV; d.emax = (float)s->e_max_MeV;
+  d.weight = (float)s->weight;
+  d.n_spec = s->n_spectrum;
+  int ne = 0;
+  if (s->ene_type == GATE_B200_ENE_SPECTRUM_DISCRETE || s->ene_type == GATE_B200_ENE_CDF) ne = s->n_spectrum;
+  if (s->ene_type == GATE_B200_ENE_SPECTRUM_HISTOGRAM || s->ene_type == GATE_B200_ENE_SPECTRUM_HISTOGRAM_LINEAR)
+    ne = s->n_spectrum + 1;
+  if (ne > 0) {
+    if (!s->spectrum_energy || !s->spectrum_cdf || s->n_spectrum < 1)
+      return fail(h, GATE_B200_EINVAL, "spectrum arrays missing");
+    std::vector<float> e(ne), c(s->n_spectrum);
+    for (int i = 0; i < ne; ++i) e[i] = (float)s->spectrum_energy[i];
+    for (int i = 0; i < s->n_spectrum; ++i) c[i] = (float)s->spectrum_cdf[i];
+    if (int rc = dev_upload(h, &d.spec_e, e.data(), e.size())) return rc;
+    if (int rc = dev_upload(h, &d.spec_cdf, c.data(), c.size())) return rc;
+  }
+  if (s->pos_type == GATE_B200_POS_VOXELS) {
+    const size_t nx = s->vox_size[0], ny = s->vox_size[1], nz = s->vox_size[2];
+    if (!s->cdf_x || !s->cdf_y || !s->cdf_z || nx * ny * nz == 0)
+      return fail(h, GATE_B200_EINVAL, "voxel source needs cdf_x/y/z");
+    if (int rc = dev_upload(h, &d.cdf_z, s->cdf_z, nz)) return rc;
+    if (int rc = dev_upload(h, &d.cdf_y, s->cdf_y, nz * ny)) return rc;
+    if (int rc = dev_upload(h, &d.cdf_x, s->cdf_x, nz * ny * nx)) return rc;
+  }
+  h->src.push_back(rec);
+  if (source_id) *source_id = (int32_t)h->src.size() - 1;
+  return GATE_B200_OK;
+}
+
+int gate_b200_add_dose_actor(gate_b200_engine *h, const gate_b200_dose_desc *d, int32_t *actor_id) {
+  if (!h || !d) return GATE_B200_EINVAL;
+  if (!h->have_volume) return fail(h, GATE_B200_ESTATE, "add_dose_actor needs the image volume first");
+  if ((int)h->dose.size() >= kMaxDose) return fail(h, GATE_B200_EINVAL, "at most %d dose actors", kMaxDose);
+  const size_t nv = (size_t)d->size[0] * d->size[1] * d->size[2];
+  if (nv == 0 || nv >= (1u << 28)) return fail(h, GATE_B200_EINVAL, "dose grid must have 1..2^28-1 voxels");
+  if (d->hit_type < 0 || d->hit_type > GATE_B200_HIT_MIDDLE) return fail(h, GATE_B200_EINVAL, "bad hit_type");
+  CU(cudaSetDevice(h->device));
+  DoseActor A;
+  A.desc = *d;
+  A.nvox = nv;
+  DDose &D = A.dev;
+  memset(&D, 0, sizeof D);
+  for (int a = 0; a < 3; ++a) D.size[a] = d->size[a];
+  D.flags = d->score_flags | GATE_B200_SCORE_EDEP;
+  D.hit_type = d->hit_type;
+  // volume -> index = (world -> index) o (volume -> world); composed in double from the float
+  // world->volume transform (identical to the oracle's oracle_add_dose_actor)
+  const Affine &w = h->P.w2v;
+  double w2v[12];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) w2v[4 * r + c] = (double)w.m[3 * r + c];
+    w2v[4 * r + 3] = (double)w.t[r];
+  }
+  double v2w[12];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) v2w[4 * r + c] = w2v[4 * c + r];
+    v2w[4 * r + 3] = -(w2v[0 * 4 + r] * w2v[3] + w2v[1 * 4 + r] * w2v[7] + w2v[2 * 4 + r] * w2v[11]);
+  }
+  double comp[12];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 4; ++c) {
+      double acc = 0.0;
+      for (int k = 0; k < 3; ++k) acc += d->world_to_index[4 * r + k] * v2w[4 * k + c];
+      if (c == 3) acc += d->world_to_index[4 * r + 3];
+      comp[4 * r + c] = acc;
+    }
+  }
+  affine_from_double(D.v2i, comp);
+  const int want[5] = {GATE_B200_SCORE_EDEP, GATE_B200_SCORE_EDEP_SQ, GATE_B200_SCORE_DOSE,
+                       GATE_B200_SCORE_DOSE_SQ, GATE_B200_SCORE_COUNTS};
+  for (int k = 0; k < 5; ++k) {
+    if (D.flags & want[k]) {
+      if (int rc = dev_alloc(h, &D.grid[k], nv, true)) return rc;
+    }
+  }
+  h->dose.push_back(A);
+  h->P.dose[h->dose.size() - 1] = D;
+  h->P.ndose = (int)h->dose.size();
+  if (actor_id) *actor_id = (int32_t)h->dose.size() - 1;
+  return GATE_B200_OK;
+}
+
+int gate_b200_add_phsp_actor(gate_b200_engine *h, const gate_b200_phsp_desc *d, int32_t *actor_id) {
+  if (!h || !d) return GATE_B200_EINVAL;
+  if ((int)h->phsp.size() >= kMaxPhsp) return fail(h, GATE_B200_EINVAL, "at most %d phase-space actors", kMaxPhsp);
+  CU(cudaSetDevice(h->device));
+  PhspActor A;
+  A.desc = *d;
+  DPhsp &Q = A.dev;
+  memset(&Q, 0, sizeof Q);
+  for (int a = 0; a < 3; ++a) Q.half[a] = (float)d->half_size[a];
+  affine_from_double(Q.w2b, d->world_to_box);
+  Q.steps = d->steps_to_store;
+  Q.capacity = d->capacity;
+  const size_t cap = (size_t)d->capacity;
+  if (int rc = dev_alloc(h, &Q.ke, cap)) return rc;
+  if (int rc = dev_alloc(h, &Q.pos, 3 * cap)) return rc;
+  if (int rc = dev_alloc(h, &Q.dir, 3 * cap)) return rc;
+  if (int rc = dev_alloc(h, &Q.w, cap)) return rc;
+  if (int rc = dev_alloc(h, &Q.t, cap)) return rc;
+  if (int rc = dev_alloc(h, &Q.ev, cap)) return rc;
+  if (int rc = dev_alloc(h, &Q.fl, cap)) return rc;
+  if (int rc = dev_alloc(h, &Q.n_rows, 1, true)) return rc;
+  if (int rc = dev_alloc(h, &Q.n_dropped, 1, true)) return rc;
+  h->phsp.push_back(A);
+  h->P.phsp[h->phsp.size() - 1] = Q;
+  h->P.nphsp = (int)h->phsp.size();
+  if (actor_id) *actor_id = (int32_t)h->phsp.size() - 1;
+  return GATE_B200_OK;
+}
+
+int gate_b200_begin_run(gate_b200_engine *h, int32_t /*run_id*/) {
+  if (!h) return GATE_B200_EINVAL;
+  CU(cudaSetDevice(h->device));
+  for (auto &A : h->dose)
+    for (int k = 0; k < 5; ++k)
+      if (A.dev.grid[k]) CU(cudaMemsetAsync(A.dev.grid[k], 0, A.nvox * sizeof(double), h->stream));
+  for (auto &A : h->phsp) {
+    CU(cudaMemsetAsync(A.dev.n_rows, 0, sizeof(unsigned long long), h->stream));
+    CU(cudaMemsetAsync(A.dev.n_dropped, 0, sizeof(unsigned long long), h->stream));
+  }
+  CU(cudaMemsetAsync(h->d_stats, 0, S_COUNT * sizeof(unsigned long long), h->stream));
+  CU(cudaMemsetAsync(h->d_edep, 0, sizeof(double), h->stream));
+  if (int rc = collect_kernel_time(h)) return rc;
+  h->kernel_ms = 0.0;
+  return GATE_B200_OK;
+}
+
+int gate_b200_run_source(gate_b200_engine *h, int32_t source_id, uint64_t first_history, uint64_t n_histories) {
+  if (!h) return GATE_B200_EINVAL;
+  if (!h->have_tables) return fail(h, GATE_B200_ESTATE, "run_source before set_tables");
+  if (source_id < 0 || source_id >= (int)h->src.size()) return fail(h, GATE_B200_EINVAL, "unknown source %d", source_id);
+  if (n_histories == 0) return GATE_B200_OK;
+  CU(cudaSetDevice(h->device));
+  Params P = h->P;
+  const int label_bytes = h->label_bytes;
+  P.src = h->src[source_id].dev;
+  P.first = first_history;
+  P.count = n_histories;
+  CU(cudaMemsetAsync(h->d_next, 0, sizeof(unsigned long long), h->stream));
+  const size_t smem = (size_t)P.ne * sizeof(float);
+  auto kern = (label_bytes == 2) ? transport_kernel<uint16_t> : transport_kernel<uint8_t>;
+  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int bps = h->blocks_per_sm;
+  if (bps <= 0) {
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, h->block, smem));
+    if (bps < 1) bps = 1;
+  }
+  unsigned long long want = (n_histories + h->block - 1) / h->block;
+  unsigned long long grid = std::min<unsigned long long>((unsigned long long)h->sm_count * bps, want);
+  if (grid < 1) grid = 1;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, h->stream));
+  kern<<<(unsigned)grid, h->block, smem, h->stream>>>(P);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(e1, h->stream));
+  h->pending_events.emplace_back(e0, e1);
+  return GATE_B200_OK;
+}
+
+int gate_b200_sync(gate_b200_engine *h) {
+  if (!h) return GATE_B200_EINVAL;
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  return collect_kernel_time(h);
+}
+
+int gate_b200_timed_run(gate_b200_engine *h, int32_t source_id, uint64_t first_history,
+                        uint64_t n_histories, double *device_ms) {
+  if (!h) return GATE_B200_EINVAL;
+  if (int rc = gate_b200_sync(h)) return rc;
+  const double before = h->kernel_ms;
+  if (int rc = gate_b200_run_source(h, source_id, first_history, n_histories)) return rc;
+  if (int rc = gate_b200_sync(h)) return rc;
+  if (device_ms) *device_ms = h->kernel_ms - before;
+  return GATE_B200_OK;
+}
+
+static int check_grid(gate_b200_engine *h, int32_t actor_id, int32_t which, double **p, size_t *n) {
+  if (actor_id < 0 || actor_id >= (int)h->dose.size()) return fail(h, GATE_B200_EINVAL, "unknown dose actor %d", actor_id);
+  if (which < 0 || which > 4) return fail(h, GATE_B200_EINVAL, "unknown grid %d", which);
+  DoseActor &A = h->dose[actor_id];
+  if (!A.dev.grid[which]) return fail(h, GATE_B200_EINVAL, "grid %d of actor %d is not scored", which, actor_id);
+  *p = A.dev.grid[which];
+  *n = A.nvox;
+  return 0;
+}
+
+int gate_b200_get_dose_grid(gate_b200_engine *h, int32_t actor_id, int32_t which, double *out) {
+  if (!h || !out) return GATE_B200_EINVAL;
+  double *p; size_t n;
+  if (int rc = check_grid(h, actor_id, which, &p, &n)) return rc;
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpy(out, p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  return GATE_B200_OK;
+}
+
+int gate_b200_set_dose_grid(gate_b200_engine *h, int32_t actor_id, int32_t which, const double *in) {
+  if (!h || !in) return GATE_B200_EINVAL;
+  double *p; size_t n;
+  if (int rc = check_grid(h, actor_id, which, &p, &n)) return rc;
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpy(p, in, n * sizeof(double), cudaMemcpyHostToDevice));
+  return GATE_B200_OK;
+}
+
+int gate_b200_dose_grid_device_ptr(gate_b200_engine *h, int32_t actor_id, int32_t which, void **ptr,
+                                   uint64_t *n_elements) {
+  if (!h || !ptr) return GATE_B200_EINVAL;
+  double *p; size_t n;
+  if (int rc = check_grid(h, actor_id, which, &p, &n)) return rc;
+  *ptr = p;
+  if (n_elements) *n_elements = n;
+  return GATE_B200_OK;
+}
+
+int gate_b200_phsp_count(gate_b200_engine *h, int32_t actor_id, uint64_t *n_rows) {
+  if (!h || !n_rows) return GATE_B200_EINVAL;
+  if (actor_id < 0 || actor_id >= (int)h->phsp.size()) return fail(h, GATE_B200_EINVAL, "unknown phsp actor %d", actor_id);
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  unsigned long long n = 0;
+  CU(cudaMemcpy(&n, h->phsp[actor_id].dev.n_rows, sizeof n, cudaMemcpyDeviceToHost));
+  *n_rows = std::min<unsigned long long>(n, h->phsp[actor_id].dev.capacity);
+  return GATE_B200_OK;
+}
+
+int gate_b200_get_phsp(gate_b200_engine *h, int32_t actor_id, uint64_t max_rows,
+                       const gate_b200_phsp_columns *out, uint64_t *n_rows) {
+  if (!h || !out) return GATE_B200_EINVAL;
+  uint64_t n = 0;
+  if (int rc = gate_b200_phsp_count(h, actor_id, &n)) return rc;
+  n = std::min<uint64_t>(n, max_rows);
+  const DPhsp &Q = h->phsp[actor_id].dev;
+  if (n) {
+    if (out->kinetic_energy) CU(cudaMemcpy(out->kinetic_energy, Q.ke, n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (out->position) CU(cudaMemcpy(out->position, Q.pos, 3 * n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (out->direction) CU(cudaMemcpy(out->direction, Q.dir, 3 * n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (out->weight) CU(cudaMemcpy(out->weight, Q.w, n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (out->time_ns) CU(cudaMemcpy(out->time_ns, Q.t, n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (out->event_id) CU(cudaMemcpy(out->event_id, Q.ev, n * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (out->flags) CU(cudaMemcpy(out->flags, Q.fl, n * sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  if (n_rows) *n_rows = n;
+  return GATE_B200_OK;
+}
+
+int gate_b200_get_stats(gate_b200_engine *h, gate_b200_stats *out) {
+  if (!h || !out) return GATE_B200_EINVAL;
+  if (int rc = gate_b200_sync(h)) return rc;
+  unsigned long long s[S_COUNT];
+  CU(cudaMemcpy(s, h->d_stats, sizeof s, cudaMemcpyDeviceToHost));
+  memset(out, 0, sizeof *out);
+  out->histories = s[S_HIST]; out->tracks = s[S_TRACKS]; out->steps = s[S_STEPS];
+  out->tentative_collisions = s[S_TENT];
+  out->n_phot = s[S_PHOT]; out->n_compt = s[S_COMPT]; out->n_rayl = s[S_RAYL]; out->n_conv = s[S_CONV];
+  out->deposits = s[S_DEP]; out->flushed_entries = s[S_FLUSH]; out->buffer_overflows = s[S_OVER];
+  out->escaped = s[S_ESC]; out->absorbed_events = s[S_ABSORBED];
+  CU(cudaMemcpy(&out->edep_total_MeV, h->d_edep, sizeof(double), cudaMemcpyDeviceToHost));
+  for (auto &A : h->phsp) {
+    unsigned long long n = 0, d = 0;
+    CU(cudaMemcpy(&n, A.dev.n_rows, sizeof n, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&d, A.dev.n_dropped, sizeof d, cudaMemcpyDeviceToHost));
+    out->phsp_rows += std::min<unsigned long long>(n, A.dev.capacity);
+    out->phsp_dropped += d;
+  }
+  out->kernel_ms = h->kernel_ms;
+  return GATE_B200_OK;
+}
+
+int gate_b200_mean_uncertainty(gate_b200_engine *h, int32_t actor_id, uint64_t n_events,
+                               int32_t top_voxels, double threshold, double *out);
+
+}  // extern "C"
+
+#include "uncertainty.cuh"

@@ -1,0 +1,1161 @@
+/* transport_oracle.c — CPU ORACLE (test infrastructure, NOT a product path).
+ *
+ * A scalar, single-precision restatement of the photon-in-image-volume dose path, written
+ * independently of opengate_b200/csrc/ but to the same arithmetic specification
+ * (DESIGN.md section "Arithmetic contract"): IEEE float +,-,*,/ ,sqrt only, no FMA
+ * contraction (compile with -ffp-contract=off), own log/exp/sincos polynomials, Philox4x32-10
+ * keyed by (seed, history id).  Under that contract the CUDA engine must reproduce every
+ * history bit for bit; the accumulated grids then differ only by the order of the double
+ * additions.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * call this file.
+ *
+ * What it restates (reference = OpenGATE/opengate @ 9b07951, paths under /root/reference):
+ *   - voxel -> material lookup: core/opengate_core/opengate_lib/GateImageNestedParameterisation.cpp:47-75
+ *   - dose scoring + event-wise squares: GateDoseActor.cpp:144-243, 359-397
+ *   - dose-grid index (itk TransformPhysicalPointToIndex on the attached image):
+ *     GateHelpersImage.txx:20-58
+ *   - primary generation: GateGenericSource.cpp:312-664, GateSPSEneDistribution.cpp:16-157,
+ *     GateSPSVoxelsPosDistribution.cpp:29-72, GateSingleParticleSource.cpp:89-137
+ *     (position, then direction, then energy)
+ *   - phase-space entering/exiting rows: GatePhaseSpaceActor.cpp:119-201
+ *   - photon physics: Geant4 11.4.2 is NOT in the reference tree; the
+ *     interaction sampling follows the published algorithms (Klein-Nishina composition-
+ *     rejection of the Geant4 Physics Reference Manual "Compton scattering", scattering-
+ *     function rejection and form-factor sampling as in the Livermore models, Woodcock
+ *     delta tracking).  PARITY UNPINNED against Geant4 for this part: no golden vector of
+ *     the reference's transport is available in this container (tests/data submodule absent).
+ */
+#include "transport_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------ arithmetic contract */
+
+static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+/* natural logarithm, msun/musl style argument reduction + degree-4 even polynomial */
+static float o_logf(float x) {
+  const float ln2_hi = 6.9313812256e-01f, ln2_lo = 9.0580006145e-06f;
+  const float Lg1 = 0.66666662693f, Lg2 = 0.40000972152f, Lg3 = 0.28498786688f,
+              Lg4 = 0.24279078841f;
+  uint32_t ix = f2u(x);
+  ix += 0x3f800000u - 0x3f3504f3u;
+  int k = (int)(ix >> 23) - 0x7f;
+  ix = (ix & 0x007fffffu) + 0x3f3504f3u;
+  float m = u2f(ix);
+  float f = m - 1.0f;
+  float s = f / (2.0f + f);
+  float z = s * s;
+  float w = z * z;
+  float t1 = w * (Lg2 + w * Lg4);
+  float t2 = z * (Lg1 + w * Lg3);
+  float R = t2 + t1;
+  float hfsq = 0.5f * f * f;
+  float dk = (float)k;
+  return s * (hfsq + R) + dk * ln2_lo - hfsq + f + dk * ln2_hi;
+}
+
+/* exp(x) for moderate |x| (used on [-6,0]) */
+static float o_expf(float x) {
+  const float log2e = 1.44269504089f, ln2_hi = 6.9313812256e-01f, ln2_lo = 9.0580006145e-06f;
+  float fn = floorf(x * log2e + 0.5f);
+  float r = x - fn * ln2_hi;
+  r = r - fn * ln2_lo;
+  float p = 1.0f / 720.0f;
+  p = p * r + 1.0f / 120.0f;
+  p = p * r + 1.0f / 24.0f;
+  p = p * r + 1.0f / 6.0f;
+  p = p * r + 0.5f;
+  p = p * r + 1.0f;
+  p = p * r + 1.0f;
+  int n = (int)fn;
+  if (n < -126) return 0.0f;
+  return p * u2f((uint32_t)(n + 127) << 23);
+}
+
+/* sin and cos of 2*pi*t for t in [0,1) */
+static void o_sincos2pi(float t, float *s, float *c) {
+  float y = t * 4.0f;
+  float fk = floorf(y + 0.5f);
+  float r = y - fk;
+  float a = r * 1.57079632679f;
+  float a2 = a * a;
+  float sp = a2 * 2.75573192e-6f + -1.98412698e-4f;
+  sp = sp * a2 + 8.33333333e-3f;
+  sp = sp * a2 + -1.66666667e-1f;
+  float sn = a + a * a2 * sp;
+  float cp = a2 * 2.48015873e-5f + -1.38888889e-3f;
+  cp = cp * a2 + 4.16666667e-2f;
+  cp = cp * a2 + -0.5f;
+  float cs = 1.0f + a2 * cp;
+  int q = ((int)fk) & 3;
+  if (q == 0) { *s = sn; *c = cs; }
+  else if (q == 1) { *s = cs; *c = -sn; }
+  else if (q == 2) { *s = -sn; *c = -cs; }
+  else { *s = -cs; *c = sn; }
+}
+
+/* ------------------------------------------------------------------ Philox4x32-10 */
+
+typedef struct {
+  uint32_t key[2];
+  uint32_t ctr[4];
+  uint32_t out[4];
+  int pos;
+} rng_t;
+
+static void philox_block(const uint32_t key[2], const uint32_t ctr[4], uint32_t out[4]) {
+  uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+  uint32_t k0 = key[0], k1 = key[1];
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+static void rng_init(rng_t *r, uint64_t seed, uint64_t history) {
+  r->key[0] = (uint32_t)seed; r->key[1] = (uint32_t)(seed >> 32);
+  r->ctr[0] = (uint32_t)history; r->ctr[1] = (uint32_t)(history >> 32);
+  r->ctr[2] = 0; r->ctr[3] = 0;
+  r->pos = 4;
+}
+
+/* uniform in (0,1): 24 random bits, centred in their bin */
+static float rng_uniform(rng_t *r) {
+  if (r->pos == 4) {
+    philox_block(r->key, r->ctr, r->out);
+    r->ctr[2] += 1u;
+    r->pos = 0;
+  }
+  uint32_t x = r->out[r->pos++];
+  return (float)(x >> 8) * 5.9604644775390625e-8f + 2.98023223876953125e-8f;
+}
+
+/* ------------------------------------------------------------------ model (float copies) */
+
+#define ORACLE_MAX_PHSP 4
+#define ORACLE_MAX_DOSE 4
+#define DEP_BUF 32
+#define NUDGE 1.0e-3f
+#define BIG 3.0e38f
+#define MC2 0.51099891f
+#define K_PER_MEV 268.17264f /* photon wave number (1/bohr) per MeV */
+#define C_MM_PER_NS 299.792458f
+
+typedef struct { float m[9]; float t[3]; } affine_t; /* y = m x + t */
+
+typedef struct {
+  gate_b200_source d;
+  affine_t pos;      /* local -> world */
+  float dir_rot[9];
+  float cos_tmin, cos_tmax, phi0_turn, dphi_turn;
+  float mom[3], focus[3];
+  float *spec_e, *spec_cdf;
+} osource_t;
+
+typedef struct {
+  int size[3];
+  affine_t v2i;      /* phantom-local point -> continuous index */
+  int flags, hit_type;
+  double *grid[5];
+} odose_t;
+
+typedef struct {
+  float half[3];
+  affine_t w2b;
+  int steps;
+  uint64_t capacity;
+  oracle_phsp_row *rows;
+  uint64_t n_rows, n_dropped;
+} ophsp_t;
+
+struct oracle_engine {
+  uint64_t seed;
+  /* tables */
+  int nmat, ne, nq, pair_mode;
+  float ln_emin, inv_dlne, e_cut, e_min, e_max;
+  float ln_q2min, inv_dlnq2;
+  float *dens, *mu, *cph, *cco, *cra, *maj, *q2n, *ray, *sf;
+  /* geometry */
+  float wh[3];
+  int world_mat;
+  int has_vol, n[3], label_bytes;
+  float half[3], inv_sp[3], sp[3];
+  affine_t w2v;
+  void *labels;
+  /* actors, sources */
+  int nsrc; osource_t *src;
+  int ndose; odose_t dose[ORACLE_MAX_DOSE];
+  int nphsp; ophsp_t phsp[ORACLE_MAX_PHSP];
+  gate_b200_stats stats;
+  char err[256];
+};
+
+typedef struct { int key; float e; float d; int n; } dep_t;
+
+typedef struct {
+  oracle_engine *g;
+  rng_t rng;
+  float p[3], d[3];  /* world frame in WORLD, phantom frame in PHANTOM */
+  float E, w, path;
+  int in_phantom;
+  int ie; float fe;  /* energy bin + fraction */
+  float seg;         /* path since last step point inside the phantom */
+  int inside_plane[ORACLE_MAX_PHSP];
+  int stored;
+  uint64_t hist;
+  dep_t buf[DEP_BUF]; int nbuf;
+  gate_b200_stats st;
+  oracle_trace *trace;
+} hist_t;
+
+static void aff_from_d(affine_t *a, const double m12[12]) {
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) a->m[3 * r + c] = (float)m12[4 * r + c];
+    a->t[r] = (float)m12[4 * r + 3];
+  }
+}
+static void aff_apply(const affine_t *a, const float x[3], float y[3]) {
+  for (int r = 0; r < 3; ++r)
+    y[r] = a->m[3 * r] * x[0] + a->m[3 * r + 1] * x[1] + a->m[3 * r + 2] * x[2] + a->t[r];
+}
+static void rot_apply(const float m[9], const float x[3], float y[3]) {
+  for (int r = 0; r < 3; ++r) y[r] = m[3 * r] * x[0] + m[3 * r + 1] * x[1] + m[3 * r + 2] * x[2];
+}
+/* inverse of a rigid transform y = m x + t :  x = m^T (y - t) */
+static void aff_apply_inv(const affine_t *a, const float y[3], float x[3]) {
+  float v[3] = {y[0] - a->t[0], y[1] - a->t[1], y[2] - a->t[2]};
+  for (int c = 0; c < 3; ++c) x[c] = a->m[c] * v[0] + a->m[3 + c] * v[1] + a->m[6 + c] * v[2];
+}
+static void rot_apply_inv(const float m[9], const float y[3], float x[3]) {
+  for (int c = 0; c < 3; ++c) x[c] = m[c] * y[0] + m[3 + c] * y[1] + m[6 + c] * y[2];
+}
+
+/* slab test against an origin-centred box; returns 1 on hit with entry (>=0) and exit */
+static int ray_box(const float p[3], const float d[3], const float h[3], float *t_in, float *t_out) {
+  float tmin = -BIG, tmax = BIG;
+  for (int a = 0; a < 3; ++a) {
+    if (d[a] != 0.0f) {
+      float inv = 1.0f / d[a];
+      float t1 = (-h[a] - p[a]) * inv;
+      float t2 = (h[a] - p[a]) * inv;
+      if (t1 > t2) { float s = t1; t1 = t2; t2 = s; }
+      if (t1 > tmin) tmin = t1;
+      if (t2 < tmax) tmax = t2;
+    } else if (p[a] < -h[a] || p[a] > h[a]) {
+      return 0;
+    }
+  }
+  float t0 = tmin > 0.0f ? tmin : 0.0f;
+  if (tmax < t0) return 0;
+  *t_in = t0; *t_out = tmax;
+  return 1;
+}
+
+static int inside_box(const float p[3], const float h[3]) {
+  return p[0] > -h[0] && p[0] < h[0] && p[1] > -h[1] && p[1] < h[1] && p[2] > -h[2] && p[2] < h[2];
+}
+
+/* ------------------------------------------------------------------ table access */
+
+static void energy_bin(const oracle_engine *g, float E, int *ie, float *fe) {
+  float t = (o_logf(E) - g->ln_emin) * g->inv_dlne;
+  if (t < 0.0f) t = 0.0f;
+  int i = (int)t;
+  if (i > g->ne - 2) i = g->ne - 2;
+  float f = t - (float)i;
+  if (f > 1.0f) f = 1.0f;
+  *ie = i; *fe = f;
+}
+static float tab(const float *t, int ne, int m, int ie, float fe) {
+  const float *r = t + (size_t)m * ne + ie;
+  return r[0] + fe * (r[1] - r[0]);
+}
+
+/* ------------------------------------------------------------------ scoring */
+
+static void flush_buffer(hist_t *h) {
+  oracle_engine *g = h->g;
+  for (int j = 0; j < h->nbuf; ++j) {
+    dep_t *b = &h->buf[j];
+    int a = (int)((uint32_t)b->key >> 28);
+    int v = b->key & 0x0fffffff;
+    odose_t *D = &g->dose[a];
+    double e = (double)b->e, d = (double)b->d;
+    /* GateDoseActor.cpp:219-229 (sums) and :359-381 (one square per event and voxel) */
+#pragma omp atomic
+    D->grid[GATE_B200_GRID_EDEP][v] += e;
+    if (D->flags & GATE_B200_SCORE_EDEP_SQ) {
+#pragma omp atomic
+      D->grid[GATE_B200_GRID_EDEP_SQ][v] += e * e;
+    }
+    if (D->flags & GATE_B200_SCORE_DOSE) {
+#pragma omp atomic
+      D->grid[GATE_B200_GRID_DOSE][v] += d;
+    }
+    if (D->flags & GATE_B200_SCORE_DOSE_SQ) {
+#pragma omp atomic
+      D->grid[GATE_B200_GRID_DOSE_SQ][v] += d * d;
+    }
+    if (D->flags & GATE_B200_SCORE_COUNTS) {
+#pragma omp atomic
+      D->grid[GATE_B200_GRID_COUNTS][v] += (double)b->n;
+    }
+    h->st.flushed_entries++;
+  }
+  h->nbuf = 0;
+}
+
+/* deposit e (already weighted) at the current phantom-frame point, material m */
+static void deposit(hist_t *h, float e, int m, int vix, int viy, int viz) {
+  oracle_engine *g = h->g;
+  h->st.edep_total_MeV += (double)e;
+  h->st.deposits++;
+  if (h->trace && h->trace->n_dep < ORACLE_TRACE_MAX) {
+    h->trace->dep_e[h->trace->n_dep] = e;
+    h->trace->n_dep++;
+  }
+  if (!h->in_phantom) return; /* dose actors are attached to the image volume */
+  for (int a = 0; a < g->ndose; ++a) {
+    odose_t *D = &g->dose[a];
+    float pos[3] = {h->p[0], h->p[1], h->p[2]};
+    if (D->hit_type != GATE_B200_HIT_POST) {
+      /* GateDoseActor.cpp:144-178: pre/random/middle between the Geant4 pre and post step
+       * points; the Geant4 step starts at the voxel entry or at the previous interaction */
+      float back = h->seg;
+      const int vi[3] = {vix, viy, viz};
+      for (int ax = 0; ax < 3; ++ax) {
+        float dd = h->d[ax];
+        if (dd > 0.0f) {
+          float lo = -g->half[ax] + (float)vi[ax] * g->sp[ax];
+          float tb = (h->p[ax] - lo) / dd;
+          if (tb < back) back = tb;
+        } else if (dd < 0.0f) {
+          float hi = -g->half[ax] + (float)(vi[ax] + 1) * g->sp[ax];
+          float tb = (h->p[ax] - hi) / dd;
+          if (tb < back) back = tb;
+        }
+      }
+      if (back < 0.0f) back = 0.0f;
+      float fr = 1.0f;
+      if (D->hit_type == GATE_B200_HIT_RANDOM) fr = 1.0f - rng_uniform(&h->rng);
+      else if (D->hit_type == GATE_B200_HIT_MIDDLE) fr = 0.5f;
+      float bk = back * fr;
+      for (int ax = 0; ax < 3; ++ax) pos[ax] = h->p[ax] - h->d[ax] * bk;
+    }
+    float c[3];
+    aff_apply(&D->v2i, pos, c);
+    /* itk::ImageBase::TransformPhysicalPointToIndex: round half up, then region test */
+    float fx = floorf(c[0] + 0.5f), fy = floorf(c[1] + 0.5f), fz = floorf(c[2] + 0.5f);
+    if (fx < 0.0f || fy < 0.0f || fz < 0.0f || fx >= (float)D->size[0] || fy >= (float)D->size[1] ||
+        fz >= (float)D->size[2])
+      continue;
+    int v = (int)fx + D->size[0] * ((int)fy + D->size[1] * (int)fz);
+    int key = (int)(((uint32_t)a << 28) | (uint32_t)v);
+    float dd = e / g->dens[m];
+    int j;
+    for (j = 0; j < h->nbuf; ++j)
+      if (h->buf[j].key == key) break;
+    if (j == h->nbuf) {
+      if (h->nbuf == DEP_BUF) { /* coalescing buffer full: write it out, start again */
+        flush_buffer(h);
+        h->st.buffer_overflows++;
+        j = 0;
+      }
+      h->buf[j].key = key; h->buf[j].e = 0.0f; h->buf[j].d = 0.0f; h->buf[j].n = 0;
+      h->nbuf++;
+    }
+    h->buf[j].e += e; h->buf[j].d += dd; h->buf[j].n += 1;
+  }
+}
+
+/* ------------------------------------------------------------------ direction change */
+
+static void rotate_dir(float d[3], float cost, float sint, float sphi, float cphi) {
+  float u = d[0], v = d[1], w = d[2];
+  float nu, nv, nw;
+  float aw = w < 0.0f ? -w : w;
+  if (aw < 0.99999f) {
+    float sz = sqrtf(1.0f - w * w);
+    float a = sint / sz;
+    nu = u * cost + a * (u * w * cphi - v * sphi);
+    nv = v * cost + a * (v * w * cphi + u * sphi);
+    nw = w * cost - sint * sz * cphi;
+  } else {
+    float sg = w < 0.0f ? -1.0f : 1.0f;
+    nu = sint * cphi; nv = sint * sphi; nw = sg * cost;
+  }
+  float inv = 1.0f / sqrtf(nu * nu + nv * nv + nw * nw);
+  d[0] = nu * inv; d[1] = nv * inv; d[2] = nw * inv;
+}
+
+/* ------------------------------------------------------------------ momentum-transfer tables */
+
+static int q2_segment(const oracle_engine *g, float q2) {
+  /* largest j with q2n[j] <= q2, -1 if below the first node, nq-1 if above the last */
+  if (q2 < g->q2n[0]) return -1;
+  if (q2 >= g->q2n[g->nq - 1]) return g->nq - 1;
+  float t = (o_logf(q2) - g->ln_q2min) * g->inv_dlnq2;
+  int j = (int)t;
+  if (j < 0) j = 0;
+  if (j > g->nq - 2) j = g->nq - 2;
+  while (j < g->nq - 2 && g->q2n[j + 1] <= q2) ++j;
+  while (j > 0 && g->q2n[j] > q2) --j;
+  return j;
+}
+static float interp_q2(const oracle_engine *g, const float *row, float q2) {
+  int j = q2_segment(g, q2);
+  if (j < 0) return row[0] * (q2 / g->q2n[0]);
+  if (j >= g->nq - 1) return row[g->nq - 1];
+  float f = (q2 - g->q2n[j]) / (g->q2n[j + 1] - g->q2n[j]);
+  return row[j] + f * (row[j + 1] - row[j]);
+}
+
+/* ------------------------------------------------------------------ interactions */
+
+static void update_energy(hist_t *h) { energy_bin(h->g, h->E, &h->ie, &h->fe); }
+
+/* returns 1 if the photon survives */
+static int interact(hist_t *h, int m, int vix, int viy, int viz, float pend_p[3], float pend_d[3],
+                    int *pend) {
+  oracle_engine *g = h->g;
+  float u = rng_uniform(&h->rng);
+  float pph = tab(g->cph, g->ne, m, h->ie, h->fe);
+  float pco = tab(g->cco, g->ne, m, h->ie, h->fe);
+  float pra = tab(g->cra, g->ne, m, h->ie, h->fe);
+  h->st.steps++;
+  if (u < pph) { /* photoelectric: everything stays here (kerma, fluorescence not tracked) */
+    h->st.n_phot++;
+    deposit(h, h->E * h->w, m, vix, viy, viz);
+    return 0;
+  }
+  if (u < pco) { /* Compton: Klein-Nishina composition-rejection x scattering function */
+    h->st.n_compt++;
+    float E = h->E;
+    float k = E / MC2;
+    float eps0 = 1.0f / (1.0f + 2.0f * k);
+    float eps0sq = eps0 * eps0;
+    float alpha1 = -o_logf(eps0);
+    float alpha2 = alpha1 + 0.5f * (1.0f - eps0sq);
+    float kq = K_PER_MEV * E;
+    float two_kq2 = 2.0f * kq * kq;
+    const float *sfrow = g->sf + (size_t)m * g->nq;
+    float eps = 1.0f, onecost = 0.0f, sint2 = 0.0f;
+    for (int it = 0; it < 1000; ++it) {
+      float u1 = rng_uniform(&h->rng), u2 = rng_uniform(&h->rng), u3 = rng_uniform(&h->rng);
+      float epssq;
+      if (alpha1 > alpha2 * u1) {
+        eps = o_expf(-alpha1 * u2);
+        epssq = eps * eps;
+      } else {
+        epssq = eps0sq + (1.0f - eps0sq) * u2;
+        eps = sqrtf(epssq);
+      }
+      onecost = (1.0f - eps) / (eps * k);
+      sint2 = onecost * (2.0f - onecost);
+      float grej = 1.0f - eps * sint2 / (1.0f + epssq);
+      if (grej < u3) continue;
+      float sfv = interp_q2(g, sfrow, two_kq2 * onecost);
+      float u4 = rng_uniform(&h->rng);
+      if (u4 > sfv) continue;
+      break;
+    }
+    float cost = 1.0f - onecost;
+    float sint = sqrtf(sint2 > 0.0f ? sint2 : 0.0f);
+    float sphi, cphi;
+    o_sincos2pi(rng_uniform(&h->rng), &sphi, &cphi);
+    float E1 = eps * E;
+    deposit(h, (E - E1) * h->w, m, vix, viy, viz);
+    rotate_dir(h->d, cost, sint, sphi, cphi);
+    h->E = E1;
+    h->seg = 0.0f;
+    if (E1 < g->e_cut) {
+      deposit(h, E1 * h->w, m, vix, viy, viz);
+      return 0;
+    }
+    update_energy(h);
+    return 1;
+  }
+  if (u < pra) { /* Rayleigh: q2 from the cumulative squared form factor, (1+cos^2)/2 test */
+    h->st.n_rayl++;
+    float kq = K_PER_MEV * h->E;
+    float kq2 = kq * kq;
+    const float *A = g->ray + (size_t)m * g->nq;
+    float q2max = 4.0f * kq2;
+    int jmax = q2_segment(g, q2max);
+    float amax = interp_q2(g, A, q2max);
+    float cost = 1.0f;
+    for (int it = 0; it < 1000; ++it) {
+      float target = rng_uniform(&h->rng) * amax;
+      float q2;
+      if (target < A[0]) {
+        q2 = g->q2n[0] * (target / A[0]);
+      } else {
+        int lo = 0, hi = jmax < g->nq - 1 ? jmax + 1 : g->nq - 1; /* A[lo] <= target < A[hi] */
+        if (target >= A[hi]) lo = hi > 0 ? hi - 1 : 0;
+        else
+          while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (A[mid] <= target) lo = mid; else hi = mid;
+          }
+        float den = A[lo + 1] - A[lo];
+        float f = den > 0.0f ? (target - A[lo]) / den : 0.0f;
+        if (f > 1.0f) f = 1.0f;
+        q2 = g->q2n[lo] + f * (g->q2n[lo + 1] - g->q2n[lo]);
+      }
+      if (q2 > q2max) q2 = q2max;
+      cost = 1.0f - q2 / (2.0f * kq2);
+      if (cost < -1.0f) cost = -1.0f;
+      float u2 = rng_uniform(&h->rng);
+      if (0.5f * (1.0f + cost * cost) >= u2) break;
+    }
+    float sint = sqrtf(1.0f - cost * cost);
+    float sphi, cphi;
+    o_sincos2pi(rng_uniform(&h->rng), &sphi, &cphi);
+    rotate_dir(h->d, cost, sint, sphi, cphi);
+    h->seg = 0.0f;
+    return 1;
+  }
+  /* gamma conversion */
+  h->st.n_conv++;
+  if (g->pair_mode == 0) {
+    /* production cuts >> range with apply_cuts: e-, e+ (and its 2 mc2) stay on the spot */
+    deposit(h, h->E * h->w, m, vix, viy, viz);
+    return 0;
+  }
+  deposit(h, (h->E - 2.0f * MC2) * h->w, m, vix, viy, viz);
+  {
+    float cost = 2.0f * rng_uniform(&h->rng) - 1.0f;
+    float sint = sqrtf(1.0f - cost * cost);
+    float sphi, cphi;
+    o_sincos2pi(rng_uniform(&h->rng), &sphi, &cphi);
+    h->d[0] = sint * cphi; h->d[1] = sint * sphi; h->d[2] = cost;
+    h->E = MC2;
+    h->seg = 0.0f;
+    update_energy(h);
+    for (int a = 0; a < 3; ++a) { pend_p[a] = h->p[a]; pend_d[a] = -h->d[a]; }
+    *pend = h->in_phantom ? 1 : 2; /* frame the stored point/direction is expressed in */
+    h->st.tracks += 2;
+  }
+  return 1;
+}
+
+/* ------------------------------------------------------------------ primaries */
+
+static float gauss(rng_t *r) {
+  float u1 = rng_uniform(r), u2 = rng_uniform(r);
+  float s, c;
+  o_sincos2pi(u2, &s, &c);
+  return sqrtf(-2.0f * o_logf(u1)) * c;
+}
+
+static int lower_bound_f(const float *a, int n, float p) { /* first i with a[i] >= p */
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (a[mid] < p) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+static void generate_primary(hist_t *h, const osource_t *s) {
+  rng_t *r = &h->rng;
+  const gate_b200_source *d = &s->d;
+  float l[3] = {0.0f, 0.0f, 0.0f};
+  switch (d->pos_type) {
+  case GATE_B200_POS_POINT: break;
+  case GATE_B200_POS_BOX:
+    for (int a = 0; a < 3; ++a) l[a] = (2.0f * rng_uniform(r) - 1.0f) * (float)d->half_size[a];
+    break;
+  case GATE_B200_POS_SPHERE: {
+    float R = (float)d->radius;
+    for (;;) {
+      for (int a = 0; a < 3; ++a) l[a] = (2.0f * rng_uniform(r) - 1.0f) * R;
+      if (l[0] * l[0] + l[1] * l[1] + l[2] * l[2] <= R * R) break;
+    }
+  } break;
+  case GATE_B200_POS_DISC:
+  case GATE_B200_POS_CYLINDER: {
+    float R = (float)d->radius;
+    if (R > 0.0f)
+      for (;;) {
+        l[0] = (2.0f * rng_uniform(r) - 1.0f) * R;
+        l[1] = (2.0f * rng_uniform(r) - 1.0f) * R;
+        if (l[0] * l[0] + l[1] * l[1] <= R * R) break;
+      }
+    if (d->pos_type == GATE_B200_POS_DISC) {
+      if (d->sigma_x > 0.0) l[0] += gauss(r) * (float)d->sigma_x;
+      if (d->sigma_y > 0.0) l[1] += gauss(r) * (float)d->sigma_y;
+    } else {
+      l[2] = (2.0f * rng_uniform(r) - 1.0f) * (float)d->half_size[2];
+    }
+  } break;
+  case GATE_B200_POS_VOXELS: {
+    int nx = d->vox_size[0], ny = d->vox_size[1], nz = d->vox_size[2];
+    int i, j, k, tries;
+    tries = 0;
+    do { i = lower_bound_f(d->cdf_z, nz, rng_uniform(r)); } while (i >= nz && ++tries < 1000);
+    if (i >= nz) i = nz - 1;
+    tries = 0;
+    do { j = lower_bound_f(d->cdf_y + (size_t)i * ny, ny, rng_uniform(r)); } while (j >= ny && ++tries < 1000);
+    if (j >= ny) j = ny - 1;
+    tries = 0;
+    do { k = lower_bound_f(d->cdf_x + ((size_t)i * ny + j) * nx, nx, rng_uniform(r)); } while (k >= nx && ++tries < 1000);
+    if (k >= nx) k = nx - 1;
+    l[0] = (float)d->vox_origin[0] + (float)k * (float)d->vox_spacing[0];
+    l[1] = (float)d->vox_origin[1] + (float)j * (float)d->vox_spacing[1];
+    l[2] = (float)d->vox_origin[2] + (float)i * (float)d->vox_spacing[2];
+    l[0] += (rng_uniform(r) - 0.5f) * (float)d->vox_spacing[0];
+    l[1] += (rng_uniform(r) - 0.5f) * (float)d->vox_spacing[1];
+    l[2] += (rng_uniform(r) - 0.5f) * (float)d->vox_spacing[2];
+  } break;
+  }
+  aff_apply(&s->pos, l, h->p);
+
+  switch (d->dir_type) {
+  case GATE_B200_DIR_ISO: {
+    /* G4SPSAngDistribution::GenerateIsotropicFlux: momentum = -(sin t cos p, sin t sin p, cos t) */
+    float cost = s->cos_tmin - rng_uniform(r) * (s->cos_tmin - s->cos_tmax);
+    float s2 = 1.0f - cost * cost;
+    float sint = sqrtf(s2 > 0.0f ? s2 : 0.0f);
+    float turn = s->phi0_turn + s->dphi_turn * rng_uniform(r);
+    turn = turn - floorf(turn);
+    float sp, cp;
+    o_sincos2pi(turn, &sp, &cp);
+    float v[3] = {-sint * cp, -sint * sp, -cost};
+    if (d->dir_relative) rot_apply(s->dir_rot, v, h->d);
+    else { h->d[0] = v[0]; h->d[1] = v[1]; h->d[2] = v[2]; }
+  } break;
+  case GATE_B200_DIR_MOMENTUM:
+    h->d[0] = s->mom[0]; h->d[1] = s->mom[1]; h->d[2] = s->mom[2];
+    break;
+  case GATE_B200_DIR_FOCUSED: {
+    float v[3] = {s->focus[0] - h->p[0], s->focus[1] - h->p[1], s->focus[2] - h->p[2]};
+    float inv = 1.0f / sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    h->d[0] = v[0] * inv; h->d[1] = v[1] * inv; h->d[2] = v[2] * inv;
+  } break;
+  }
+
+  float E = 0.0f;
+  switch (d->ene_type) {
+  case GATE_B200_ENE_MONO: E = (float)d->mono_MeV; break;
+  case GATE_B200_ENE_GAUSS: E = (float)d->mono_MeV + gauss(r) * (float)d->sigma_MeV; break;
+  case GATE_B200_ENE_RANGE:
+    E = (float)d->e_min_MeV + rng_uniform(r) * ((float)d->e_max_MeV - (float)d->e_min_MeV);
+    break;
+  case GATE_B200_ENE_SPECTRUM_DISCRETE: {
+    float p = rng_uniform(r);
+    int i = 0;
+    while (i < d->n_spectrum - 1 && p >= s->spec_cdf[i]) ++i; /* IndexForProbability */
+    E = s->spec_e[i];
+  } break;
+  case GATE_B200_ENE_SPECTRUM_HISTOGRAM: {
+    float p = rng_uniform(r);
+    int i = 0;
+    while (i < d->n_spectrum - 1 && p >= s->spec_cdf[i]) ++i;
+    E = s->spec_e[i] + rng_uniform(r) * (s->spec_e[i + 1] - s->spec_e[i]);
+  } break;
+  case GATE_B200_ENE_SPECTRUM_HISTOGRAM_LINEAR: {
+    /* GateSPSEneDistribution.cpp:124-147 */
+    float p0 = rng_uniform(r);
+    int i = 0;
+    while (i < d->n_spectrum - 2 && p0 >= s->spec_cdf[i]) ++i;
+    float a = (s->spec_e[i] + s->spec_e[i + 1]) * 0.5f;
+    float b = (s->spec_e[i + 1] + s->spec_e[i + 2]) * 0.5f;
+    float dd = s->spec_cdf[i + 1] - s->spec_cdf[i];
+    float ad = dd < 0.0f ? -dd : dd;
+    if (ad < 1.1920929e-7f) {
+      E = a + rng_uniform(r) * (b - a);
+    } else {
+      float alpha = dd / (b - a);
+      float beta = s->spec_cdf[i] - alpha * a;
+      float norm = 0.5f * alpha * (b * b - a * a) + beta * (b - a);
+      float p = rng_uniform(r);
+      float sq = sqrtf((alpha * a + beta) * (alpha * a + beta) + 2.0f * alpha * norm * p);
+      float x = (-beta + sq) / alpha;
+      E = ((x - a) * (x - b) <= 0.0f) ? x : (-beta - sq) / alpha;
+    }
+  } break;
+  case GATE_B200_ENE_CDF: {
+    /* GateSPSEneDistribution.cpp:38-49 */
+    float x = rng_uniform(r);
+    int idx = lower_bound_f(s->spec_cdf, d->n_spectrum, x) - 1;
+    if (idx < 0) idx = 0;
+    if (idx > d->n_spectrum - 2) idx = d->n_spectrum - 2;
+    float ratio = (x - s->spec_cdf[idx]) / (s->spec_cdf[idx + 1] - s->spec_cdf[idx]);
+    E = s->spec_e[idx] + ratio * (s->spec_e[idx + 1] - s->spec_e[idx]);
+  } break;
+  }
+  h->E = E;
+  h->w = (float)d->weight;
+}
+
+/* ------------------------------------------------------------------ phase space */
+
+static void phsp_store(hist_t *h, int k, int flag) {
+  ophsp_t *P = &h->g->phsp[k];
+  h->stored = 1;
+  uint64_t idx;
+#pragma omp atomic capture
+  idx = P->n_rows++;
+  if (idx >= P->capacity) {
+#pragma omp atomic
+    P->n_dropped++;
+    return;
+  }
+  oracle_phsp_row *r = &P->rows[idx];
+  r->kinetic_energy = h->E;
+  for (int a = 0; a < 3; ++a) { r->position[a] = h->p[a]; r->direction[a] = h->d[a]; }
+  r->weight = h->w;
+  r->time_ns = h->path / C_MM_PER_NS;
+  r->event_id = (int64_t)h->hist;
+  r->flags = flag;
+}
+
+/* ------------------------------------------------------------------ one history */
+
+static void to_phantom(hist_t *h) {
+  float pl[3], dl[3];
+  aff_apply(&h->g->w2v, h->p, pl);
+  rot_apply(h->g->w2v.m, h->d, dl);
+  for (int a = 0; a < 3; ++a) { h->p[a] = pl[a]; h->d[a] = dl[a]; }
+}
+static void to_world(hist_t *h) {
+  float pw[3], dw[3];
+  aff_apply_inv(&h->g->w2v, h->p, pw);
+  rot_apply_inv(h->g->w2v.m, h->d, dw);
+  for (int a = 0; a < 3; ++a) { h->p[a] = pw[a]; h->d[a] = dw[a]; }
+}
+
+static void run_photon(hist_t *h, float pend_p[3], float pend_d[3], int *pend) {
+  oracle_engine *g = h->g;
+  int alive = 1;
+  if (h->E < g->e_cut) { /* below the table: absorbed where it starts */
+    h->st.edep_total_MeV += (double)(h->E * h->w);
+    return;
+  }
+  update_energy(h);
+  for (int iter = 0; alive && iter < 1000000; ++iter) {
+    if (!h->in_phantom) {
+      float t_exit, t0;
+      if (!inside_box(h->p, g->wh) || !ray_box(h->p, h->d, g->wh, &t0, &t_exit)) {
+        h->st.escaped++;
+        return;
+      }
+      int ev = 0; /* 0 interact, 1 leave world, 2 enter phantom, 3+2k enter plane k, 4+2k leave plane k */
+      float mu = tab(g->mu, g->ne, g->world_mat, h->ie, h->fe);
+      float t_best = -o_logf(rng_uniform(&h->rng)) / mu;
+      if (t_exit < t_best) { t_best = t_exit; ev = 1; }
+      if (g->has_vol) {
+        float pl[3], dl[3], ti, to;
+        aff_apply(&g->w2v, h->p, pl);
+        rot_apply(g->w2v.m, h->d, dl);
+        if (ray_box(pl, dl, g->half, &ti, &to) && ti < t_best) { t_best = ti; ev = 2; }
+      }
+      for (int k = 0; k < g->nphsp; ++k) {
+        float pb[3], db[3], ti, to;
+        aff_apply(&g->phsp[k].w2b, h->p, pb);
+        rot_apply(g->phsp[k].w2b.m, h->d, db);
+        if (!ray_box(pb, db, g->phsp[k].half, &ti, &to)) {
+          h->inside_plane[k] = 0;
+          continue;
+        }
+        if (h->inside_plane[k]) {
+          if (to < t_best) { t_best = to; ev = 4 + 2 * k; }
+        } else if (ti < t_best) { t_best = ti; ev = 3 + 2 * k; }
+      }
+      float step = (ev >= 2) ? t_best + NUDGE : t_best;
+      if (ev == 1) { h->st.escaped++; h->path += t_best; return; }
+      for (int a = 0; a < 3; ++a) h->p[a] = h->p[a] + h->d[a] * step;
+      h->path += step;
+      if (ev == 0) {
+        alive = interact(h, g->world_mat, 0, 0, 0, pend_p, pend_d, pend);
+      } else if (ev == 2) {
+        h->st.steps++;
+        to_phantom(h);
+        h->in_phantom = 1;
+        h->seg = 0.0f;
+      } else {
+        int k = (ev - 3) >> 1;
+        h->st.steps++;
+        if (((ev - 3) & 1) == 0) {
+          h->inside_plane[k] = 1;
+          if (g->phsp[k].steps & GATE_B200_PHSP_ENTERING) phsp_store(h, k, GATE_B200_PHSP_ENTERING);
+        } else {
+          h->inside_plane[k] = 0;
+          if (g->phsp[k].steps & GATE_B200_PHSP_EXITING) phsp_store(h, k, GATE_B200_PHSP_EXITING);
+        }
+      }
+    } else {
+      /* Woodcock delta tracking against the majorant of the materials in the volume */
+      float maj = g->maj[h->ie] + h->fe * (g->maj[h->ie + 1] - g->maj[h->ie]);
+      float s = -o_logf(rng_uniform(&h->rng)) / maj;
+      float q[3] = {h->p[0] + h->d[0] * s, h->p[1] + h->d[1] * s, h->p[2] + h->d[2] * s};
+      float fx = (q[0] + g->half[0]) * g->inv_sp[0];
+      float fy = (q[1] + g->half[1]) * g->inv_sp[1];
+      float fz = (q[2] + g->half[2]) * g->inv_sp[2];
+      if (fx < 0.0f || fy < 0.0f || fz < 0.0f || fx >= (float)g->n[0] || fy >= (float)g->n[1] ||
+          fz >= (float)g->n[2]) {
+        /* left the volume: restart from the exit point in the world frame */
+        float ti, to;
+        if (!ray_box(h->p, h->d, g->half, &ti, &to)) to = 0.0f;
+        float step = to + NUDGE;
+        for (int a = 0; a < 3; ++a) h->p[a] = h->p[a] + h->d[a] * step;
+        h->path += step;
+        h->st.steps++;
+        to_world(h);
+        h->in_phantom = 0;
+        continue;
+      }
+      h->p[0] = q[0]; h->p[1] = q[1]; h->p[2] = q[2];
+      h->path += s;
+      h->seg += s;
+      h->st.tentative_collisions++;
+      int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+      size_t flat = (size_t)ix + (size_t)g->n[0] * ((size_t)iy + (size_t)g->n[1] * (size_t)iz);
+      int m = g->label_bytes == 1 ? (int)((const uint8_t *)g->labels)[flat]
+                                  : (int)((const uint16_t *)g->labels)[flat];
+      float mu = tab(g->mu, g->ne, m, h->ie, h->fe);
+      if (rng_uniform(&h->rng) * maj <= mu)
+        alive = interact(h, m, ix, iy, iz, pend_p, pend_d, pend);
+    }
+  }
+}
+
+static void run_history(oracle_engine *g, const osource_t *s, uint64_t hist, gate_b200_stats *acc,
+                        oracle_trace *trace) {
+  hist_t h;
+  memset(&h, 0, sizeof h);
+  h.g = g; h.hist = hist; h.trace = trace;
+  if (trace) trace->n_dep = 0;
+  rng_init(&h.rng, g->seed, hist);
+  generate_primary(&h, s);
+  h.st.histories = 1; h.st.tracks = 1;
+  if (trace) {
+    trace->E0 = h.E;
+    for (int a = 0; a < 3; ++a) { trace->p0[a] = h.p[a]; trace->d0[a] = h.d[a]; }
+  }
+  float pend_p[3], pend_d[3];
+  int pend = 0;
+  /* region of the vertex */
+  {
+    float pl[3];
+    h.in_phantom = 0;
+    if (g->has_vol) {
+      aff_apply(&g->w2v, h.p, pl);
+      if (inside_box(pl, g->half)) { to_phantom(&h); h.in_phantom = 1; }
+    }
+    for (int k = 0; k < g->nphsp; ++k) {
+      float pb[3];
+      aff_apply(&g->phsp[k].w2b, h.p, pb);
+      h.inside_plane[k] = (!h.in_phantom) && inside_box(pb, g->phsp[k].half);
+    }
+  }
+  run_photon(&h, pend_p, pend_d, &pend);
+  if (pend) { /* second annihilation photon (pair_mode 1) */
+    /* pend_* are expressed in the frame current at creation (1 = phantom, 2 = world): go back
+     * to the world frame and find the region again */
+    float pw[3], dw[3];
+    if (pend == 1) {
+      aff_apply_inv(&g->w2v, pend_p, pw);
+      rot_apply_inv(g->w2v.m, pend_d, dw);
+    } else {
+      for (int a = 0; a < 3; ++a) { pw[a] = pend_p[a]; dw[a] = pend_d[a]; }
+    }
+    for (int a = 0; a < 3; ++a) { h.p[a] = pw[a]; h.d[a] = dw[a]; }
+    h.E = MC2; h.seg = 0.0f; h.in_phantom = 0;
+    if (g->has_vol) {
+      float pl[3];
+      aff_apply(&g->w2v, h.p, pl);
+      if (inside_box(pl, g->half)) { to_phantom(&h); h.in_phantom = 1; }
+    }
+    for (int k = 0; k < g->nphsp; ++k) {
+      float pb[3];
+      aff_apply(&g->phsp[k].w2b, h.p, pb);
+      h.inside_plane[k] = (!h.in_phantom) && inside_box(pb, g->phsp[k].half);
+    }
+    int pend2 = 0;
+    run_photon(&h, pend_p, pend_d, &pend2);
+  }
+  flush_buffer(&h);
+  if (g->nphsp > 0 && !h.stored) h.st.absorbed_events++;
+  /* accumulate */
+  acc->histories += h.st.histories; acc->tracks += h.st.tracks; acc->steps += h.st.steps;
+  acc->tentative_collisions += h.st.tentative_collisions;
+  acc->n_phot += h.st.n_phot; acc->n_compt += h.st.n_compt; acc->n_rayl += h.st.n_rayl;
+  acc->n_conv += h.st.n_conv; acc->deposits += h.st.deposits;
+  acc->flushed_entries += h.st.flushed_entries; acc->buffer_overflows += h.st.buffer_overflows;
+  acc->escaped += h.st.escaped; acc->absorbed_events += h.st.absorbed_events;
+  acc->edep_total_MeV += h.st.edep_total_MeV;
+  if (trace) {
+    trace->E_end = h.E;
+    trace->edep = (float)h.st.edep_total_MeV;
+    trace->n_tentative = (int)h.st.tentative_collisions;
+    trace->n_interactions = (int)(h.st.n_phot + h.st.n_compt + h.st.n_rayl + h.st.n_conv);
+  }
+}
+
+/* ------------------------------------------------------------------ API */
+
+static float *dup_f(const float *src, size_t n) {
+  float *p = (float *)malloc(n * sizeof(float));
+  memcpy(p, src, n * sizeof(float));
+  return p;
+}
+
+oracle_engine *oracle_create(uint64_t seed) {
+  oracle_engine *g = (oracle_engine *)calloc(1, sizeof *g);
+  g->seed = seed;
+  g->wh[0] = g->wh[1] = g->wh[2] = 1.0e6f;
+  return g;
+}
+
+void oracle_destroy(oracle_engine *g) {
+  if (!g) return;
+  free(g->dens); free(g->mu); free(g->cph); free(g->cco); free(g->cra); free(g->maj);
+  free(g->q2n); free(g->ray); free(g->sf); free(g->labels);
+  for (int i = 0; i < g->nsrc; ++i) { free(g->src[i].spec_e); free(g->src[i].spec_cdf); }
+  free(g->src);
+  for (int a = 0; a < g->ndose; ++a)
+    for (int k = 0; k < 5; ++k) free(g->dose[a].grid[k]);
+  for (int k = 0; k < g->nphsp; ++k) free(g->phsp[k].rows);
+  free(g);
+}
+
+int oracle_set_tables(oracle_engine *g, const gate_b200_tables *t) {
+  g->nmat = t->n_materials; g->ne = t->n_energy; g->nq = t->n_q; g->pair_mode = t->pair_mode;
+  size_t n = (size_t)g->nmat * g->ne, nqq = (size_t)g->nmat * g->nq;
+  g->dens = dup_f(t->density_g_cm3, g->nmat);
+  g->mu = dup_f(t->mu_total_per_mm, n);
+  g->cph = dup_f(t->cum_phot, n); g->cco = dup_f(t->cum_compt, n); g->cra = dup_f(t->cum_rayl, n);
+  g->ray = dup_f(t->rayl_cum_ff2, nqq); g->sf = dup_f(t->compt_sf, nqq);
+  double le0 = log(t->e_min_MeV), le1 = log(t->e_max_MeV);
+  g->ln_emin = (float)le0;
+  g->inv_dlne = (float)((double)(g->ne - 1) / (le1 - le0));
+  g->e_cut = (float)t->e_cut_MeV; g->e_min = (float)t->e_min_MeV; g->e_max = (float)t->e_max_MeV;
+  double lq0 = log(t->q2_min), lq1 = log(t->q2_max);
+  g->ln_q2min = (float)lq0;
+  g->inv_dlnq2 = (float)((double)(g->nq - 1) / (lq1 - lq0));
+  g->q2n = (float *)malloc(sizeof(float) * g->nq);
+  for (int j = 0; j < g->nq; ++j)
+    g->q2n[j] = (float)exp(lq0 + (lq1 - lq0) * (double)j / (double)(g->nq - 1));
+  g->maj = (float *)calloc(g->ne, sizeof(float));
+  return 0;
+}
+
+static void build_majorant(oracle_engine *g) {
+  /* majorant over the materials actually present in the volume */
+  char *present = (char *)calloc(g->nmat, 1);
+  size_t nv = (size_t)g->n[0] * g->n[1] * g->n[2];
+  for (size_t i = 0; i < nv; ++i) {
+    int m = g->label_bytes == 1 ? ((uint8_t *)g->labels)[i] : ((uint16_t *)g->labels)[i];
+    if (m < g->nmat) present[m] = 1;
+  }
+  for (int i = 0; i < g->ne; ++i) {
+    float mx = 0.0f;
+    for (int m = 0; m < g->nmat; ++m)
+      if (present[m] && g->mu[(size_t)m * g->ne + i] > mx) mx = g->mu[(size_t)m * g->ne + i];
+    g->maj[i] = mx;
+  }
+  free(present);
+}
+
+int oracle_set_world(oracle_engine *g, const double half[3], int material) {
+  for (int a = 0; a < 3; ++a) g->wh[a] = (float)half[a];
+  g->world_mat = material;
+  return 0;
+}
+
+int oracle_set_image_volume(oracle_engine *g, const void *labels, int label_bytes, const int size[3],
+                            const double spacing[3], const double w2v[12]) {
+  size_t nv = (size_t)size[0] * size[1] * size[2];
+  free(g->labels);
+  g->labels = malloc(nv * label_bytes);
+  memcpy(g->labels, labels, nv * label_bytes);
+  g->label_bytes = label_bytes;
+  for (int a = 0; a < 3; ++a) {
+    g->n[a] = size[a];
+    g->sp[a] = (float)spacing[a];
+    g->inv_sp[a] = (float)(1.0 / spacing[a]);
+    g->half[a] = (float)(0.5 * size[a] * spacing[a]);
+  }
+  aff_from_d(&g->w2v, w2v);
+  g->has_vol = 1;
+  build_majorant(g);
+  return 0;
+}
+
+int oracle_add_source(oracle_engine *g, const gate_b200_source *s) {
+  g->src = (osource_t *)realloc(g->src, sizeof(osource_t) * (g->nsrc + 1));
+  osource_t *o = &g->src[g->nsrc];
+  memset(o, 0, sizeof *o);
+  o->d = *s;
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) {
+      o->pos.m[3 * r + c] = (float)s->pos_rotation[3 * r + c];
+      o->dir_rot[3 * r + c] = (float)s->dir_rotation[3 * r + c];
+    }
+    o->pos.t[r] = (float)s->pos_translation[r];
+    o->mom[r] = (float)s->momentum[r];
+    o->focus[r] = (float)s->focus_point[r];
+  }
+  o->cos_tmin = (float)cos(s->theta[0]); o->cos_tmax = (float)cos(s->theta[1]);
+  o->phi0_turn = (float)(s->phi[0] / 6.283185307179586);
+  o->dphi_turn = (float)((s->phi[1] - s->phi[0]) / 6.283185307179586);
+  int ne = 0;
+  if (s->ene_type == GATE_B200_ENE_SPECTRUM_DISCRETE || s->ene_type == GATE_B200_ENE_CDF) ne = s->n_spectrum;
+  if (s->ene_type == GATE_B200_ENE_SPECTRUM_HISTOGRAM || s->ene_type == GATE_B200_ENE_SPECTRUM_HISTOGRAM_LINEAR)
+    ne = s->n_spectrum + 1;
+  if (ne > 0) {
+    o->spec_e = (float *)malloc(sizeof(float) * ne);
+    o->spec_cdf = (float *)malloc(sizeof(float) * s->n_spectrum);
+    for (int i = 0; i < ne; ++i) o->spec_e[i] = (float)s->spectrum_energy[i];
+    for (int i = 0; i < s->n_spectrum; ++i) o->spec_cdf[i] = (float)s->spectrum_cdf[i];
+  }
+  return g->nsrc++;
+}
+
+int oracle_add_dose_actor(oracle_engine *g, const gate_b200_dose_desc *d) {
+  if (g->ndose >= ORACLE_MAX_DOSE) return -1;
+  odose_t *D = &g->dose[g->ndose];
+  memset(D, 0, sizeof *D);
+  for (int a = 0; a < 3; ++a) D->size[a] = d->size[a];
+  D->flags = d->score_flags | GATE_B200_SCORE_EDEP;
+  D->hit_type = d->hit_type;
+  /* volume -> index = (world -> index) o (volume -> world), composed in double */
+  double w2v[12];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) w2v[4 * r + c] = (double)g->w2v.m[3 * r + c];
+    w2v[4 * r + 3] = (double)g->w2v.t[r];
+  }
+  double v2w[12]; /* inverse rigid */
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) v2w[4 * r + c] = w2v[4 * c + r];
+    v2w[4 * r + 3] = -(w2v[0 * 4 + r] * w2v[3] + w2v[1 * 4 + r] * w2v[7] + w2v[2 * 4 + r] * w2v[11]);
+  }
+  double comp[12];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 4; ++c) {
+      double acc = 0.0;
+      for (int k = 0; k < 3; ++k) acc += d->world_to_index[4 * r + k] * v2w[4 * k + c];
+      if (c == 3) acc += d->world_to_index[4 * r + 3];
+      comp[4 * r + c] = acc;
+    }
+  }
+  aff_from_d(&D->v2i, comp);
+  size_t nv = (size_t)D->size[0] * D->size[1] * D->size[2];
+  const int want[5] = {GATE_B200_SCORE_EDEP, GATE_B200_SCORE_EDEP_SQ, GATE_B200_SCORE_DOSE,
+                       GATE_B200_SCORE_DOSE_SQ, GATE_B200_SCORE_COUNTS};
+  for (int k = 0; k < 5; ++k)
+    D->grid[k] = (D->flags & want[k]) ? (double *)calloc(nv, sizeof(double)) : NULL;
+  return g->ndose++;
+}
+
+int oracle_add_phsp_actor(oracle_engine *g, const gate_b200_phsp_desc *d) {
+  if (g->nphsp >= ORACLE_MAX_PHSP) return -1;
+  ophsp_t *P = &g->phsp[g->nphsp];
+  memset(P, 0, sizeof *P);
+  for (int a = 0; a < 3; ++a) P->half[a] = (float)d->half_size[a];
+  aff_from_d(&P->w2b, d->world_to_box);
+  P->steps = d->steps_to_store;
+  P->capacity = d->capacity;
+  P->rows = (oracle_phsp_row *)calloc(d->capacity ? d->capacity : 1, sizeof(oracle_phsp_row));
+  return g->nphsp++;
+}
+
+void oracle_begin_run(oracle_engine *g) {
+  memset(&g->stats, 0, sizeof g->stats);
+  for (int a = 0; a < g->ndose; ++a) {
+    size_t nv = (size_t)g->dose[a].size[0] * g->dose[a].size[1] * g->dose[a].size[2];
+    for (int k = 0; k < 5; ++k)
+      if (g->dose[a].grid[k]) memset(g->dose[a].grid[k], 0, nv * sizeof(double));
+  }
+  for (int k = 0; k < g->nphsp; ++k) { g->phsp[k].n_rows = 0; g->phsp[k].n_dropped = 0; }
+}
+
+int oracle_run_source(oracle_engine *g, int source_id, uint64_t first, uint64_t n, int n_threads) {
+  const osource_t *s = &g->src[source_id];
+  gate_b200_stats total;
+  memset(&total, 0, sizeof total);
+#ifdef _OPENMP
+  if (n_threads > 0) omp_set_num_threads(n_threads);
+#pragma omp parallel
+  {
+    gate_b200_stats acc;
+    memset(&acc, 0, sizeof acc);
+#pragma omp for schedule(dynamic, 256)
+    for (int64_t i = 0; i < (int64_t)n; ++i) run_history(g, s, first + (uint64_t)i, &acc, NULL);
+#pragma omp critical
+    {
+      total.histories += acc.histories; total.tracks += acc.tracks; total.steps += acc.steps;
+      total.tentative_collisions += acc.tentative_collisions;
+      total.n_phot += acc.n_phot; total.n_compt += acc.n_compt; total.n_rayl += acc.n_rayl;
+      total.n_conv += acc.n_conv; total.deposits += acc.deposits;
+      total.flushed_entries += acc.flushed_entries; total.buffer_overflows += acc.buffer_overflows;
+      total.escaped += acc.escaped; total.absorbed_events += acc.absorbed_events;
+      total.edep_total_MeV += acc.edep_total_MeV;
+    }
+  }
+#else
+  (void)n_threads;
+  for (uint64_t i = 0; i < n; ++i) run_history(g, s, first + i, &total, NULL);
+#endif
+  gate_b200_stats *S = &g->stats;
+  S->histories += total.histories; S->tracks += total.tracks; S->steps += total.steps;
+  S->tentative_collisions += total.tentative_collisions;
+  S->n_phot += total.n_phot; S->n_compt += total.n_compt; S->n_rayl += total.n_rayl;
+  S->n_conv += total.n_conv; S->deposits += total.deposits;
+  S->flushed_entries += total.flushed_entries; S->buffer_overflows += total.buffer_overflows;
+  S->escaped += total.escaped; S->absorbed_events += total.absorbed_events;
+  S->edep_total_MeV += total.edep_total_MeV;
+  S->phsp_rows = 0; S->phsp_dropped = 0;
+  for (int k = 0; k < g->nphsp; ++k) {
+    uint64_t stored = g->phsp[k].n_rows < g->phsp[k].capacity ? g->phsp[k].n_rows : g->phsp[k].capacity;
+    S->phsp_rows += stored; S->phsp_dropped += g->phsp[k].n_dropped;
+  }
+  return 0;
+}
+
+int oracle_trace_history(oracle_engine *g, int source_id, uint64_t hist, oracle_trace *out) {
+  gate_b200_stats acc;
+  memset(&acc, 0, sizeof acc);
+  run_history(g, &g->src[source_id], hist, &acc, out);
+  return 0;
+}
+
+const double *oracle_dose_grid(oracle_engine *g, int actor, int which) { return g->dose[actor].grid[which]; }
+void oracle_get_stats(oracle_engine *g, gate_b200_stats *out) { *out = g->stats; }
+uint64_t oracle_phsp_rows(oracle_engine *g, int actor, const oracle_phsp_row **rows) {
+  *rows = g->phsp[actor].rows;
+  return g->phsp[actor].n_rows < g->phsp[actor].capacity ? g->phsp[actor].n_rows : g->phsp[actor].capacity;
+}
+
+/* exported for unit tests of the arithmetic contract */
+float oracle_logf(float x) { return o_logf(x); }
+float oracle_expf(float x) { return o_expf(x); }
+void oracle_sincos2pi(float t, float *s, float *c) { o_sincos2pi(t, s, c); }
+void oracle_philox(uint64_t seed, uint64_t hist, uint32_t block, uint32_t out[4]) {
+  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  uint32_t ctr[4] = {(uint32_t)hist, (uint32_t)(hist >> 32), block, 0};
+  philox_block(key, ctr, out);
+}
+void oracle_uniforms(uint64_t seed, uint64_t hist, int n, float *out) {
+  rng_t r;
+  rng_init(&r, seed, hist);
+  for (int i = 0; i < n; ++i) out[i] = rng_uniform(&r);
+}

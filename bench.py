@@ -214,7 +214,8 @@ def main():
     H = args.histories
     S = build_setup(args.config, H)
     eng = Engine(local, S.seed)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-default) stream shared by torch and the engine
+    torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     sids, dids, pids = S.apply(eng)
     sid = sids[0]

@@ -114,10 +114,12 @@ __device__ __forceinline__ void rot_apply_inv(const float m[9], const float y[3]
   for (int c = 0; c < 3; ++c) x[c] = m[c] * y[0] + m[3 + c] * y[1] + m[6 + c] * y[2];
 }
 
-// slab test against an origin-centred box: entry (>=0) and exit distance
-__device__ __forceinline__ bool ray_box(const float p[3], const float d[3], const float h[3],
-                                        float &t_in, float &t_out) {
+// slab test against an origin-centred box: entry (>=0) and exit distance plus the axes of the
+// entry / exit faces (-1 when the start point is inside). A zero-length chord is a miss.
+__device__ __forceinline__ bool ray_box_ax(const float p[3], const float d[3], const float h[3],
+                                           float &t_in, float &t_out, int &a_in, int &a_out) {
   float tmin = -kBig, tmax = kBig;
+  int ain = -1, aout = -1;
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     if (d[a] != 0.0f) {
@@ -125,16 +127,36 @@ __device__ __forceinline__ bool ray_box(const float p[3], const float d[3], cons
       float t1 = (-h[a] - p[a]) * inv;
       float t2 = (h[a] - p[a]) * inv;
       if (t1 > t2) { float s = t1; t1 = t2; t2 = s; }
-      if (t1 > tmin) tmin = t1;
-      if (t2 < tmax) tmax = t2;
+      if (t1 > tmin) { tmin = t1; ain = a; }
+      if (t2 < tmax) { tmax = t2; aout = a; }
     } else if (p[a] < -h[a] || p[a] > h[a]) {
       return false;
     }
   }
   float t0 = tmin > 0.0f ? tmin : 0.0f;
-  if (tmax < t0) return false;
+  if (tmax <= t0) return false;
   t_in = t0; t_out = tmax;
+  a_in = tmin > 0.0f ? ain : -1;
+  a_out = aout;
   return true;
+}
+__device__ __forceinline__ bool ray_box(const float p[3], const float d[3], const float h[3],
+                                        float &t_in, float &t_out) {
+  int ai, ao;
+  return ray_box_ax(p, d, h, t_in, t_out, ai, ao);
+}
+
+// Put coordinate `a` just inside / outside the face the ray crosses, so that the slab test and
+// the voxel-index test agree about the side even at grazing incidence (a push along the ray can
+// be smaller than one ulp of the coordinate).
+__device__ __forceinline__ void snap_to_face(float p[3], const float d[3], const float h[3], int a,
+                                             bool outward) {
+  if (a < 0) return;
+  float face = outward ? (h[a] * (1.0f + 1.0e-6f) + 1.0e-5f) : (h[a] * (1.0f - 1.0e-6f) - 1.0e-5f);
+  float v;
+  if (outward) v = d[a] > 0.0f ? face : -face;
+  else v = d[a] > 0.0f ? -face : face;
+  if (a == 0) p[0] = v; else if (a == 1) p[1] = v; else p[2] = v;
 }
 
 __device__ __forceinline__ bool inside_box(const float p[3], const float h[3]) {
@@ -669,11 +691,13 @@ __device__ __forceinline__ int world_step(const Params &P, History &h, Photon &g
   float mu = tab(P.mu, P.ne, P.world_mat, g.ie, g.fe);
   float t_best = -d_logf(rng_uniform(h.rng)) / mu;
   if (t_exit < t_best) { t_best = t_exit; ev = 1; }
+  int ax_in = -1;
   if (P.has_vol) {
     float pl[3], dl[3], ti, to;
+    int ai, ao;
     aff_apply(P.w2v, g.p, pl);
     rot_apply(P.w2v.m, g.d, dl);
-    if (ray_box(pl, dl, P.half, ti, to) && ti < t_best) { t_best = ti; ev = 2; }
+    if (ray_box_ax(pl, dl, P.half, ti, to, ai, ao) && ti < t_best) { t_best = ti; ev = 2; ax_in = ai; }
   }
   for (int k = 0; k < P.nphsp; ++k) {
     float pb[3], db[3], ti, to;
@@ -687,7 +711,7 @@ __device__ __forceinline__ int world_step(const Params &P, History &h, Photon &g
       if (to < t_best) { t_best = to; ev = 4 + 2 * k; }
     } else if (ti < t_best) { t_best = ti; ev = 3 + 2 * k; }
   }
-  float step = (ev >= 2) ? t_best + kNudge : t_best;
+  float step = (ev >= 3) ? t_best + kNudge : t_best;
   if (ev == 1) { c.esc++; g.path += t_best; return ST_DEAD; }
 #pragma unroll
   for (int a = 0; a < 3; ++a) g.p[a] = g.p[a] + g.d[a] * step;
@@ -697,6 +721,7 @@ __device__ __forceinline__ int world_step(const Params &P, History &h, Photon &g
   } else if (ev == 2) {
     c.steps++;
     to_volume(P, g);
+    snap_to_face(g.p, g.d, P.half, ax_in, false);
     g.seg = 0.0f;
     return ST_VOLUME;
   }
@@ -726,11 +751,12 @@ __device__ __forceinline__ int volume_step(const Params &P, const float *__restr
   if (fx < 0.0f || fy < 0.0f || fz < 0.0f || fx >= (float)P.n[0] || fy >= (float)P.n[1] ||
       fz >= (float)P.n[2]) {
     float ti, to;
-    if (!ray_box(g.p, g.d, P.half, ti, to)) to = 0.0f;
-    float step = to + kNudge;
+    int ai, ao;
+    if (!ray_box_ax(g.p, g.d, P.half, ti, to, ai, ao)) { to = 0.0f; ao = -1; }
 #pragma unroll
-    for (int a = 0; a < 3; ++a) g.p[a] = g.p[a] + g.d[a] * step;
-    g.path += step;
+    for (int a = 0; a < 3; ++a) g.p[a] = g.p[a] + g.d[a] * to;
+    snap_to_face(g.p, g.d, P.half, ao, true);
+    g.path += to;
     c.steps++;
     to_world(P, g);
     return ST_WORLD;

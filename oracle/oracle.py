@@ -43,7 +43,7 @@ TRACE_MAX = 64
 class Trace(C.Structure):
     _fields_ = [("E0", C.c_float), ("p0", C.c_float * 3), ("d0", C.c_float * 3),
                 ("E_end", C.c_float), ("edep", C.c_float), ("n_tentative", C.c_int),
-                ("n_interactions", C.c_int), ("n_dep", C.c_int), ("dep_e", C.c_float * TRACE_MAX)]
+                ("n_interactions", C.c_int), ("n_dep", C.c_int), ("n_iter", C.c_int), ("dep_e", C.c_float * TRACE_MAX)]
 
 
 _lib = None

@@ -30,6 +30,7 @@
 #include "transport_oracle.h"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -246,25 +247,45 @@ static void rot_apply_inv(const float m[9], const float y[3], float x[3]) {
   for (int c = 0; c < 3; ++c) x[c] = m[c] * y[0] + m[3 + c] * y[1] + m[6 + c] * y[2];
 }
 
-/* slab test against an origin-centred box; returns 1 on hit with entry (>=0) and exit */
-static int ray_box(const float p[3], const float d[3], const float h[3], float *t_in, float *t_out) {
+/* slab test against an origin-centred box; returns 1 on hit with entry (>=0) and exit
+ * distances and the axes of the entry / exit faces (-1 when the start point is inside).
+ * A zero-length chord (touching a face from outside) is a miss. */
+static int ray_box_ax(const float p[3], const float d[3], const float h[3], float *t_in, float *t_out,
+                      int *a_in, int *a_out) {
   float tmin = -BIG, tmax = BIG;
+  int ain = -1, aout = -1;
   for (int a = 0; a < 3; ++a) {
     if (d[a] != 0.0f) {
       float inv = 1.0f / d[a];
       float t1 = (-h[a] - p[a]) * inv;
       float t2 = (h[a] - p[a]) * inv;
       if (t1 > t2) { float s = t1; t1 = t2; t2 = s; }
-      if (t1 > tmin) tmin = t1;
-      if (t2 < tmax) tmax = t2;
+      if (t1 > tmin) { tmin = t1; ain = a; }
+      if (t2 < tmax) { tmax = t2; aout = a; }
     } else if (p[a] < -h[a] || p[a] > h[a]) {
       return 0;
     }
   }
   float t0 = tmin > 0.0f ? tmin : 0.0f;
-  if (tmax < t0) return 0;
+  if (tmax <= t0) return 0;
   *t_in = t0; *t_out = tmax;
+  *a_in = tmin > 0.0f ? ain : -1;
+  *a_out = aout;
   return 1;
+}
+static int ray_box(const float p[3], const float d[3], const float h[3], float *t_in, float *t_out) {
+  int ai, ao;
+  return ray_box_ax(p, d, h, t_in, t_out, &ai, &ao);
+}
+
+/* Put coordinate `a` just inside (sign -1) or just outside (+1) the face the ray crosses, so
+ * that the slab test and the voxel-index test agree about which side the point is on even at
+ * grazing incidence (a push along the ray can be smaller than one ulp of the coordinate). */
+static void snap_to_face(float p[3], const float d[3], const float h[3], int a, int outward) {
+  if (a < 0) return;
+  float face = outward ? (h[a] * (1.0f + 1.0e-6f) + 1.0e-5f) : (h[a] * (1.0f - 1.0e-6f) - 1.0e-5f);
+  if (outward) p[a] = d[a] > 0.0f ? face : -face;
+  else p[a] = d[a] > 0.0f ? -face : face;
 }
 
 static int inside_box(const float p[3], const float h[3]) {
@@ -751,6 +772,12 @@ static void run_photon(hist_t *h, float pend_p[3], float pend_d[3], int *pend) {
   }
   update_energy(h);
   for (int iter = 0; alive && iter < 1000000; ++iter) {
+    if (h->trace) h->trace->n_iter++;
+#ifdef ORACLE_DEBUG
+    if (h->trace && h->trace->n_iter < 40)
+      fprintf(stderr, "it %d reg %d p %.6f %.6f %.6f d %.6f %.6f %.6f E %.5f\n", iter, h->in_phantom,
+              h->p[0], h->p[1], h->p[2], h->d[0], h->d[1], h->d[2], h->E);
+#endif
     if (!h->in_phantom) {
       float t_exit, t0;
       if (!inside_box(h->p, g->wh) || !ray_box(h->p, h->d, g->wh, &t0, &t_exit)) {
@@ -761,11 +788,13 @@ static void run_photon(hist_t *h, float pend_p[3], float pend_d[3], int *pend) {
       float mu = tab(g->mu, g->ne, g->world_mat, h->ie, h->fe);
       float t_best = -o_logf(rng_uniform(&h->rng)) / mu;
       if (t_exit < t_best) { t_best = t_exit; ev = 1; }
+      int ax_in = -1;
       if (g->has_vol) {
         float pl[3], dl[3], ti, to;
+        int ai, ao;
         aff_apply(&g->w2v, h->p, pl);
         rot_apply(g->w2v.m, h->d, dl);
-        if (ray_box(pl, dl, g->half, &ti, &to) && ti < t_best) { t_best = ti; ev = 2; }
+        if (ray_box_ax(pl, dl, g->half, &ti, &to, &ai, &ao) && ti < t_best) { t_best = ti; ev = 2; ax_in = ai; }
       }
       for (int k = 0; k < g->nphsp; ++k) {
         float pb[3], db[3], ti, to;
@@ -779,7 +808,7 @@ static void run_photon(hist_t *h, float pend_p[3], float pend_d[3], int *pend) {
           if (to < t_best) { t_best = to; ev = 4 + 2 * k; }
         } else if (ti < t_best) { t_best = ti; ev = 3 + 2 * k; }
       }
-      float step = (ev >= 2) ? t_best + NUDGE : t_best;
+      float step = (ev >= 3) ? t_best + NUDGE : t_best;
       if (ev == 1) { h->st.escaped++; h->path += t_best; return; }
       for (int a = 0; a < 3; ++a) h->p[a] = h->p[a] + h->d[a] * step;
       h->path += step;
@@ -788,6 +817,7 @@ static void run_photon(hist_t *h, float pend_p[3], float pend_d[3], int *pend) {
       } else if (ev == 2) {
         h->st.steps++;
         to_phantom(h);
+        snap_to_face(h->p, h->d, g->half, ax_in, 0);
         h->in_phantom = 1;
         h->seg = 0.0f;
       } else {
@@ -813,10 +843,11 @@ static void run_photon(hist_t *h, float pend_p[3], float pend_d[3], int *pend) {
           fz >= (float)g->n[2]) {
         /* left the volume: restart from the exit point in the world frame */
         float ti, to;
-        if (!ray_box(h->p, h->d, g->half, &ti, &to)) to = 0.0f;
-        float step = to + NUDGE;
-        for (int a = 0; a < 3; ++a) h->p[a] = h->p[a] + h->d[a] * step;
-        h->path += step;
+        int ai, ao;
+        if (!ray_box_ax(h->p, h->d, g->half, &ti, &to, &ai, &ao)) { to = 0.0f; ao = -1; }
+        for (int a = 0; a < 3; ++a) h->p[a] = h->p[a] + h->d[a] * to;
+        snap_to_face(h->p, h->d, g->half, ao, 1);
+        h->path += to;
         h->st.steps++;
         to_world(h);
         h->in_phantom = 0;
@@ -842,7 +873,7 @@ static void run_history(oracle_engine *g, const osource_t *s, uint64_t hist, gat
   hist_t h;
   memset(&h, 0, sizeof h);
   h.g = g; h.hist = hist; h.trace = trace;
-  if (trace) trace->n_dep = 0;
+  if (trace) { trace->n_dep = 0; trace->n_iter = 0; }
   rng_init(&h.rng, g->seed, hist);
   generate_primary(&h, s);
   h.st.histories = 1; h.st.tracks = 1;

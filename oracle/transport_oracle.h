@@ -25,7 +25,7 @@ typedef struct {
 typedef struct {
   float E0, p0[3], d0[3];   /* primary */
   float E_end, edep;        /* photon energy when the history stopped, total deposited */
-  int n_tentative, n_interactions, n_dep;
+  int n_tentative, n_interactions, n_dep, n_iter;
   float dep_e[ORACLE_TRACE_MAX];
 } oracle_trace;
 

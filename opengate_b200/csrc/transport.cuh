@@ -152,10 +152,13 @@ __device__ __forceinline__ bool ray_box(const float p[3], const float d[3], cons
 __device__ __forceinline__ void snap_to_face(float p[3], const float d[3], const float h[3], int a,
                                              bool outward) {
   if (a < 0) return;
-  float face = outward ? (h[a] * (1.0f + 1.0e-6f) + 1.0e-5f) : (h[a] * (1.0f - 1.0e-6f) - 1.0e-5f);
+  // selects instead of p[a]/d[a]: a run-time index would push the photon state to local memory
+  const float ha = a == 0 ? h[0] : (a == 1 ? h[1] : h[2]);
+  const float da = a == 0 ? d[0] : (a == 1 ? d[1] : d[2]);
+  float face = outward ? (ha * (1.0f + 1.0e-6f) + 1.0e-5f) : (ha * (1.0f - 1.0e-6f) - 1.0e-5f);
   float v;
-  if (outward) v = d[a] > 0.0f ? face : -face;
-  else v = d[a] > 0.0f ? -face : face;
+  if (outward) v = da > 0.0f ? face : -face;
+  else v = da > 0.0f ? -face : face;
   if (a == 0) p[0] = v; else if (a == 1) p[1] = v; else p[2] = v;
 }
 
@@ -661,7 +664,7 @@ __device__ __forceinline__ void to_world(const Params &P, Photon &g) {
   for (int a = 0; a < 3; ++a) { g.p[a] = pw[a]; g.d[a] = dw[a]; }
 }
 
-enum { ST_FETCH = 0, ST_WORLD = 1, ST_VOLUME = 2, ST_DEAD = 3 };
+enum { ST_FETCH = 0, ST_WORLD = 1, ST_VOLUME = 2, ST_DEAD = 3, ST_INTERACT_W = 4, ST_INTERACT_V = 5, ST_DONE = 6 };
 
 // place a photon given in the world frame into its region; returns the state
 __device__ __forceinline__ int locate(const Params &P, History &h, Photon &g) {
@@ -717,7 +720,7 @@ __device__ __forceinline__ int world_step(const Params &P, History &h, Photon &g
   for (int a = 0; a < 3; ++a) g.p[a] = g.p[a] + g.d[a] * step;
   g.path += step;
   if (ev == 0) {
-    return interact(P, h, g, c, P.world_mat, false, 0, 0, 0) ? ST_WORLD : ST_DEAD;
+    return ST_INTERACT_W;   // real interaction in the world material, done in the interaction phase
   } else if (ev == 2) {
     c.steps++;
     to_volume(P, g);
@@ -740,7 +743,7 @@ __device__ __forceinline__ int world_step(const Params &P, History &h, Photon &g
 // one Woodcock candidate collision inside the image volume
 template <typename LabelT>
 __device__ __forceinline__ int volume_step(const Params &P, const float *__restrict__ s_maj, History &h,
-                                           Photon &g, Counters &c) {
+                                           Photon &g, Counters &c, int &mat) {
   float m0 = s_maj[g.ie], m1 = s_maj[g.ie + 1];
   float maj = m0 + g.fe * (m1 - m0);
   float s = -d_logf(rng_uniform(h.rng)) / maj;
@@ -769,13 +772,20 @@ __device__ __forceinline__ int volume_step(const Params &P, const float *__restr
   size_t flat = (size_t)ix + (size_t)P.n[0] * ((size_t)iy + (size_t)P.n[1] * (size_t)iz);
   int m = (int)__ldg(reinterpret_cast<const LabelT *>(P.labels) + flat);
   float mu = tab(P.mu, P.ne, m, g.ie, g.fe);
-  if (rng_uniform(h.rng) * maj <= mu)
-    return interact(P, h, g, c, m, true, ix, iy, iz) ? ST_VOLUME : ST_DEAD;
+  if (rng_uniform(h.rng) * maj <= mu) {
+    mat = m;                // accepted: the interaction itself runs in the interaction phase
+    return ST_INTERACT_V;
+  }
   return ST_VOLUME;
 }
 
 // ------------------------------------------------------------------------------ kernel
 
+// The kernel is a warp-level phase scheduler.  Every lane carries one photon whose state says
+// which kind of work it needs next (refill, world flight, Woodcock step, interaction).  In
+// each round the warp votes and runs ONE phase, the one most lanes are waiting for, so that
+// the long and rare code paths (interaction sampling, primary generation) execute with many
+// lanes at once instead of being dragged through on every round by one or two lanes.
 template <typename LabelT>
 __global__ void __launch_bounds__(256) transport_kernel(const __grid_constant__ Params P) {
   extern __shared__ float s_maj[];
@@ -790,38 +800,79 @@ __global__ void __launch_bounds__(256) transport_kernel(const __grid_constant__ 
   c.edep = 0.0;
   h.nbuf = 0; h.pend = 0; h.stored = 0; h.inside_mask = 0; h.edep = 0.0f; h.id = 0;
   int st = ST_FETCH;
+  int mat = 0;            // material of the pending interaction
+  bool open = false;      // a history is in flight (must be closed before the next fetch)
   const unsigned lane = threadIdx.x & 31u;
+  const unsigned FULL = 0xffffffffu;
 
   for (;;) {
-    if (st == ST_FETCH) {
-      // warp-aggregated claim of the next history ids
-      const unsigned act = __activemask();
-      const int leader = __ffs(act) - 1;
-      unsigned long long base = 0;
-      if ((int)lane == leader) base = atomicAdd(P.next, (unsigned long long)__popc(act));
-      base = __shfl_sync(act, base, leader);
-      const unsigned long long idx = base + (unsigned long long)__popc(act & ((1u << lane) - 1u));
-      if (idx >= P.count) break;
-      h.id = P.first + idx;
-      rng_init(h.rng, P.seed, h.id);
-      h.nbuf = 0; h.pend = 0; h.stored = 0; h.edep = 0.0f;
-      generate_primary(P, h, g);
-      g.path = 0.0f; g.seg = 0.0f; g.iter = 0;
-      c.hist++; c.tracks++;
-      st = locate(P, h, g);
-      if (g.E < P.e_cut) {
-        c.edep += (double)(g.E * g.w);
-        st = ST_DEAD;
-      } else {
-        energy_bin(P, g);
+    const unsigned bV = __ballot_sync(FULL, st == ST_VOLUME);
+    const unsigned bI = __ballot_sync(FULL, st == ST_INTERACT_V || st == ST_INTERACT_W);
+    const unsigned bW = __ballot_sync(FULL, st == ST_WORLD);
+    const unsigned bF = __ballot_sync(FULL, st == ST_FETCH);
+    if (!(bV | bI | bW | bF)) break;
+    const int nV = __popc(bV), nI = __popc(bI), nW = __popc(bW), nF = __popc(bF);
+
+    if (nV >= nI && nV >= nW && nV >= nF) {
+      // ---------------- Woodcock phase
+      if (st == ST_VOLUME) {
+        st = volume_step<LabelT>(P, s_maj, h, g, c, mat);
+        if (++g.iter >= kMaxIter) st = ST_DEAD;
       }
-    } else if (st == ST_VOLUME) {
-      st = volume_step<LabelT>(P, s_maj, h, g, c);
-      if (++g.iter >= kMaxIter) st = ST_DEAD;
-    } else if (st == ST_WORLD) {
-      st = world_step(P, h, g, c);
-      if (++g.iter >= kMaxIter) st = ST_DEAD;
+    } else if (nI >= nW && nI >= nF) {
+      // ---------------- interaction phase
+      if (st == ST_INTERACT_V || st == ST_INTERACT_W) {
+        const bool in_vol = st == ST_INTERACT_V;
+        int ix = 0, iy = 0, iz = 0;
+        if (in_vol) {   // same expressions as in volume_step: same voxel
+          ix = (int)((g.p[0] + P.half[0]) * P.inv_sp[0]);
+          iy = (int)((g.p[1] + P.half[1]) * P.inv_sp[1]);
+          iz = (int)((g.p[2] + P.half[2]) * P.inv_sp[2]);
+        }
+        const bool alive = interact(P, h, g, c, in_vol ? mat : P.world_mat, in_vol, ix, iy, iz);
+        st = alive ? (in_vol ? ST_VOLUME : ST_WORLD) : ST_DEAD;
+      }
+    } else if (nW >= nF) {
+      // ---------------- world phase
+      if (st == ST_WORLD) {
+        st = world_step(P, h, g, c);
+        if (++g.iter >= kMaxIter) st = ST_DEAD;
+      }
+    } else {
+      // ---------------- refill phase: close the finished history, claim the next id
+      if (st == ST_FETCH) {
+        if (open) {
+          flush_buffer(P, h, c);
+          if (P.nphsp > 0 && !h.stored) c.absorbed++;
+          open = false;
+        }
+        const unsigned act = __activemask();
+        const int leader = __ffs(act) - 1;
+        unsigned long long base = 0;
+        if ((int)lane == leader) base = atomicAdd(P.next, (unsigned long long)__popc(act));
+        base = __shfl_sync(act, base, leader);
+        const unsigned long long idx = base + (unsigned long long)__popc(act & ((1u << lane) - 1u));
+        if (idx >= P.count) {
+          st = ST_DONE;
+        } else {
+          h.id = P.first + idx;
+          rng_init(h.rng, P.seed, h.id);
+          h.nbuf = 0; h.pend = 0; h.stored = 0; h.edep = 0.0f;
+          generate_primary(P, h, g);
+          g.path = 0.0f; g.seg = 0.0f; g.iter = 0;
+          c.hist++; c.tracks++;
+          open = true;
+          st = locate(P, h, g);
+          if (g.E < P.e_cut) {
+            c.edep += (double)(g.E * g.w);
+            st = ST_DEAD;
+          } else {
+            energy_bin(P, g);
+          }
+        }
+      }
     }
+
     if (st == ST_DEAD) {
       if (h.pend) {
         // second annihilation photon of a conversion (pair_mode 1)
@@ -840,9 +891,7 @@ __global__ void __launch_bounds__(256) transport_kernel(const __grid_constant__ 
         st = locate(P, h, g);
         energy_bin(P, g);
       } else {
-        flush_buffer(P, h, c);
-        if (P.nphsp > 0 && !h.stored) c.absorbed++;
-        st = ST_FETCH;
+        st = ST_FETCH;   // the history is closed (flushed) in the refill phase
       }
     }
   }

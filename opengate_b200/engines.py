@@ -1,0 +1,425 @@
+"""`GpuSimulationEngine`: the run phase of a `Simulation` on the CUDA engine.
+
+Takes the place of the reference's `SimulationEngine` (opengate/engines.py:1414-1891: initialize
+:1721-1863, run_engine :1554-1630, start_and_stop :1632-1667) for the photon-in-image-volume path:
+it reads the resolved Python objects (volumes, physics, sources, actors), converts them ONCE into
+the C-ABI descriptors (`LowLevelSetup`), drives `libgate_b200.so` run by run the way
+`GateSourceManager::StartMasterThread` does (GateSourceManager.cpp:198-244: BeginOfRunAction ->
+beamOn -> EndOfRunAction per timing interval) and hands every actor its results in the reference's
+end-of-run life cycle.  Unsupported configuration -> `fatal()`.
+
+Multi-GPU: one process per GPU under torchrun (histories split `n//G + (g < n%G)` like the
+reference's thread split, sources/base.py:190-197; one sum all-reduce of the accumulator grids at
+the end of each run), or `sim.number_of_gpus = N` inside one process (N engines, host-side sum).
+"""
+
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import abi, multigpu, physics
+from .exception import fatal, warning
+from .setups import LowLevelSetup, dose_world_to_index
+from .units import g4_units
+from .volumes import __world_name__
+
+
+class SimulationOutput:
+    """What `Simulation.run()` returns (reference engines.py:1320-1411)."""
+
+    def __init__(self):
+        self.actors = {}
+        self.sources = {}
+        self.current_random_seed = None
+        self.expected_number_of_events = 0
+        self.warnings = []
+        self.log_output = ""
+        self.user_hook_log = []
+        self.device_stats = []     # gate_b200_stats per run (summed over GPUs)
+
+    def get_actor(self, name):
+        if name not in self.actors:
+            fatal(f'The actor "{name}" does not exist. Here is the list of actors: {list(self.actors)}')
+        return self.actors[name]
+
+    def get_source(self, name):
+        if name not in self.sources:
+            fatal(f'The source "{name}" does not exist. Here is the list of sources: {list(self.sources)}')
+        return self.sources[name]
+
+
+def invert_rigid(R, t):
+    Ri = np.asarray(R, dtype=np.float64).T
+    return Ri, -Ri @ np.asarray(t, dtype=np.float64)
+
+
+def affine34(R, t):
+    A = np.zeros((3, 4))
+    A[:, :3] = R
+    A[:, 3] = t
+    return A
+
+
+class GpuSimulationEngine:
+    def __init__(self, simulation, backend=None):
+        self.sim = simulation
+        self._backend = backend
+        self.setup = None
+        self.dose_actors = []
+        self.phsp_actors = []
+        self.stats_actors = []
+        self.source_objects = []
+        self.engines = []
+        self.ids = []
+        self.rank, self.world, self.local_rank = 0, 1, 0
+        self.dist = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def close(self):
+        for e in self.engines:
+            try:
+                e.close()
+            except Exception:
+                pass
+        self.engines = []
+
+    # ------------------------------------------------------------------------ configuration
+    def _phantom_volume(self):
+        """The ONE volume photons interact in besides the world: an ImageVolume, or (config 1)
+        a homogeneous Box carrying a DoseActor, represented as a 1-voxel label volume."""
+        sim = self.sim
+        vols = [v for v in sim.volume_manager.volumes.values() if v.name != __world_name__]
+        images = [v for v in vols if v.volume_type == "ImageVolume"]
+        dose_targets = {a.attached_to for a in sim.actor_manager.actors.values() if a.type_name == "DoseActor"}
+        phsp_targets = {a.attached_to for a in sim.actor_manager.actors.values() if a.type_name == "PhaseSpaceActor"}
+        world_mat = sim.world.material
+        phantom = None
+        if len(images) > 1:
+            fatal("The B200 GPU engine supports one ImageVolume per simulation")
+        if images:
+            phantom = images[0]
+        for v in vols:
+            if v is phantom:
+                continue
+            if v.volume_type != "BoxVolume":
+                fatal(f"Volume '{v.name}' of type {v.volume_type} is not supported by the B200 GPU engine")
+            if v.name in dose_targets or (v.material != world_mat and v.name not in phsp_targets):
+                if phantom is not None:
+                    fatal(f"Volume '{v.name}' ({v.material}) is a second material region besides '{phantom.name}': "
+                          f"the B200 GPU engine transports photons through the world and ONE phantom volume")
+                phantom = v
+            elif v.material != world_mat:
+                fatal(f"Box '{v.name}' holding a PhaseSpaceActor must be made of the world material "
+                      f"('{world_mat}') on the B200 GPU engine (it is a scoring plane, not a material region)")
+        if phantom is None:
+            fatal("No phantom volume: add an Image volume (or a Box with a DoseActor attached)")
+        for t in dose_targets:
+            if t != phantom.name:
+                fatal(f"DoseActor attached to '{t}': on the B200 GPU engine dose actors must be attached to the "
+                      f"phantom volume '{phantom.name}'")
+        if phantom.mother != __world_name__:
+            # nested placement is fine geometrically (world_transform composes it) as long as the
+            # mothers are made of the world material
+            m = phantom.mother_volume
+            while m is not None and m.name != __world_name__:
+                if m.material != world_mat:
+                    fatal(f"Mother volume '{m.name}' of the phantom is not made of the world material")
+                m = m.mother_volume
+        return phantom
+
+    def build_setup(self):
+        """Resolved Simulation -> LowLevelSetup (pure host code; no device needed)."""
+        sim = self.sim
+        pm = sim.physics_manager
+        db = sim.volume_manager.material_database
+        phantom = self._phantom_volume()
+        world = sim.world
+
+        # label volume ------------------------------------------------------------------------
+        if phantom.volume_type == "ImageVolume":
+            label_img = phantom.construct()
+            lut = dict(phantom.material_to_label_lut)
+            labels16 = label_img.array
+            spacing = tuple(float(x) for x in label_img.spacing)
+        else:
+            lut = {phantom.material: 0}
+            labels16 = np.zeros((1, 1, 1), dtype=np.uint16)
+            spacing = tuple(float(x) for x in phantom.size)
+        names = list(lut.keys())
+        if world.material not in lut:
+            names.append(world.material)
+        world_label = names.index(world.material)
+        labels = labels16.astype(np.uint8) if len(names) <= 256 else labels16.astype(np.uint16)
+        mats = [db.find_or_build_material(n) for n in names]
+
+        # sources -------------------------------------------------------------------------------
+        self.source_objects = list(sim.source_manager.sources.values())
+        e_max = 0.0
+        src_structs = []
+        for s in self.source_objects:
+            vol = sim.volume_manager.get_volume(s.attached_to)
+            src_structs.append(s.to_abi(None if vol.name == __world_name__ else vol))
+            e_max = max(e_max, s.max_energy())
+        if pm.energy_range_max is not None:
+            e_max = max(e_max, 0.0) if e_max > 0 else float(pm.energy_range_max)
+        if not e_max > 0:
+            fatal("Cannot determine the maximum photon energy of the sources")
+        tables = physics.build_photon_tables(
+            mats, e_max_mev=e_max, e_cut_mev=float(pm.photon_energy_cut), n_energy=int(pm.table_energy_nodes),
+            pair_mode=1 if pm.pair_production_mode == "annihilation" else 0)
+        half_phantom = 0.5 * np.asarray(labels16.shape[::-1]) * np.asarray(spacing)
+        pm.check_kerma_configuration(float(2 * np.max(half_phantom)))
+
+        # placement -----------------------------------------------------------------------------
+        Rv, tv = phantom.world_transform()
+        Ri, ti = invert_rigid(Rv, tv)
+        w2v = affine34(Ri, ti)
+        world_half = tuple(0.5 * float(x) for x in world.size)
+        if sim.check_volumes_overlap:
+            corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)]) * half_phantom
+            cw = corners @ Rv.T + tv
+            if np.any(np.abs(cw) > np.asarray(world_half) + 1e-9):
+                fatal(f"Volume '{phantom.name}' is not fully inside the world")
+
+        # actors --------------------------------------------------------------------------------
+        self.dose_actors, self.phsp_actors, self.stats_actors = [], [], []
+        dose_desc, phsp_desc = [], []
+        n_total = self.expected_number_of_events()
+        for a in sim.actor_manager.sorted_actors:
+            a.initialize()
+            if a.type_name == "DoseActor":
+                A = dose_world_to_index(a.size, a.spacing, translation=a.translation, vol_rotation=Rv, vol_translation=tv)
+                dose_desc.append(abi.make_dose_desc([int(x) for x in a.size], A, a.score_flags(), abi.HIT_TYPES[a.hit_type]))
+                self.dose_actors.append(a)
+            elif a.type_name == "PhaseSpaceActor":
+                box = a.attached_to_volume
+                Rb, tb = box.world_transform()
+                Rbi, tbi = invert_rigid(Rb, tb)
+                cap = a.max_rows if a.max_rows is not None else max(int(n_total) + 1024, 1024)
+                phsp_desc.append(abi.make_phsp_desc(box.half_size_mm, affine34(Rbi, tbi), a.steps_mask(), int(cap)))
+                self.phsp_actors.append(a)
+            elif a.type_name == "SimulationStatisticsActor":
+                self.stats_actors.append(a)
+            else:
+                fatal(f"Actor type {a.type_name} is not supported by the B200 GPU engine")
+        self.setup = LowLevelSetup(
+            name=f"{sim.name}", seed=int(sim.current_random_seed) & (2 ** 64 - 1), tables=tables,
+            world_half=world_half, world_material=world_label, labels=np.ascontiguousarray(labels), spacing=spacing,
+            world_to_volume=w2v, sources=src_structs, dose=dose_desc, phsp=phsp_desc, n_primaries=int(n_total))
+        return self.setup
+
+    def expected_number_of_events(self):
+        sim = self.sim
+        rng = np.random.default_rng(int(sim.current_random_seed) & 0xFFFFFFFF)
+        self._counts = []   # [run][source]
+        for r in range(len(sim.run_timing_intervals)):
+            self._counts.append([s.primaries_for_run(r, rng) for s in sim.source_manager.sources.values()])
+        return int(np.sum(self._counts)) if self._counts else 0
+
+    # ------------------------------------------------------------------------ devices
+    def _init_devices(self):
+        sim = self.sim
+        if self._backend is not None:
+            self.engines = [self._backend(0, self.setup.seed)]
+            return
+        from .core import Engine
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self.dist = dist
+                self.rank, self.world = dist.get_rank(), dist.get_world_size()
+                _, _, self.local_rank = multigpu.world_info()
+        except ImportError:
+            pass
+        if self.dist is not None:
+            if sim.number_of_gpus not in (None, self.world):
+                warning(f"number_of_gpus={sim.number_of_gpus} ignored: running under torchrun with {self.world} ranks")
+            self.engines = [Engine(self.local_rank, self.setup.seed)]
+        else:
+            n = int(sim.number_of_gpus or 1)
+            self.engines = [Engine(g, self.setup.seed) for g in range(n)]
+
+    @property
+    def n_shards(self):
+        return self.world if self.dist is not None else len(self.engines)
+
+    # ------------------------------------------------------------------------ run
+    def run_engine(self):
+        sim = self.sim
+        t_init = time.perf_counter()
+        self.build_setup()
+        self._init_devices()
+        self.ids = [self.setup.apply(e) for e in self.engines]
+        out = SimulationOutput()
+        out.current_random_seed = sim.current_random_seed
+        out.expected_number_of_events = self.setup.n_primaries
+        t_start = time.perf_counter()
+        base = 0
+        totals = {"events": 0, "tracks": 0, "steps": 0}
+        for run_index in range(len(sim.run_timing_intervals)):
+            st = self._run_one(run_index, base)
+            out.device_stats.append(st)
+            base += int(np.sum(self._counts[run_index]))
+            totals["events"] += st["histories"]
+            totals["tracks"] += st["tracks"]
+            totals["steps"] += st["steps"]
+        t_stop = time.perf_counter()
+        for a in self.stats_actors:
+            a.store(len(sim.run_timing_intervals), totals["events"], totals["tracks"], totals["steps"],
+                    (t_stop - t_start) * g4_units.s, (t_start - t_init) * g4_units.s,
+                    extra={"nb_threads": sim.number_of_threads, "nb_gpus": self.n_shards,
+                           "tentative_collisions": int(sum(s["tentative_collisions"] for s in out.device_stats))})
+        if self.rank == 0:
+            for a in sim.actor_manager.sorted_actors:
+                a.end_of_simulation()
+        out.actors = dict(sim.actor_manager.actors)
+        out.sources = dict(sim.source_manager.sources)
+        out.warnings = list(sim.warnings)
+        return out
+
+    def _launch(self, source_index, first, n):
+        """Enqueue n histories [first, first+n) of one source, split over the shards."""
+        chunk = int(self.sim.max_histories_per_launch)
+        if self.dist is not None:
+            off, cnt = multigpu.split_primaries(n, self.world, self.rank)
+            parts = [(self.engines[0], self.ids[0], first + off, cnt)]
+        else:
+            parts = []
+            for g, e in enumerate(self.engines):
+                off, cnt = multigpu.split_primaries(n, len(self.engines), g)
+                parts.append((e, self.ids[g], first + off, cnt))
+        for e, ids, f, cnt in parts:
+            done = 0
+            while done < cnt:
+                k = min(chunk, cnt - done)
+                e.run_source(ids[0][source_index], f + done, k)
+                done += k
+
+    def _sync(self):
+        for e in self.engines:
+            if hasattr(e, "sync"):
+                e.sync()
+
+    def _mean_uncertainty(self, actor_index, actor, n_events):
+        """GateDoseActor::ComputeMeanUncertainty over the data of ALL shards."""
+        if self.n_shards == 1 and hasattr(self.engines[0], "mean_uncertainty"):
+            return self.engines[0].mean_uncertainty(self.ids[0][1][actor_index], n_events,
+                                                    int(actor.uncertainty_top_voxels_count),
+                                                    float(actor.uncertainty_voxel_edep_threshold))
+        grids = self._gather_grids(actor_index, (abi.GRID_EDEP, abi.GRID_EDEP_SQ), reduce_in_place=False)
+        return host_mean_uncertainty(grids[abi.GRID_EDEP], grids[abi.GRID_EDEP_SQ], n_events,
+                                     int(actor.uncertainty_top_voxels_count), float(actor.uncertainty_voxel_edep_threshold))
+
+    def _gather_grids(self, actor_index, which_list, reduce_in_place=True):
+        """Sum of the accumulator grids of one dose actor over all shards -> {which: (z,y,x) float64}."""
+        out = {}
+        if self.dist is not None:
+            e, ids = self.engines[0], self.ids[0]
+            for w in which_list:
+                if reduce_in_place:
+                    t = multigpu.grid_tensor(e, ids[1][actor_index], w)
+                    self.dist.all_reduce(t)
+                    out[w] = e.dose_grid(ids[1][actor_index], w)
+                else:
+                    import torch
+                    t = multigpu.grid_tensor(e, ids[1][actor_index], w).clone()
+                    self.dist.all_reduce(t)
+                    nx, ny, nz = [int(x) for x in self.dose_actors[actor_index].size]
+                    out[w] = t.cpu().numpy().reshape(nz, ny, nx)
+                    del t
+                    torch.cuda.empty_cache()
+            return out
+        for w in which_list:
+            acc = None
+            for e, ids in zip(self.engines, self.ids):
+                g = e.dose_grid(ids[1][actor_index], w)
+                acc = g.copy() if acc is None else acc + g
+            out[w] = acc
+        return out
+
+    def _run_one(self, run_index, base):
+        sim = self.sim
+        for e in self.engines:
+            e.begin_run(run_index)
+        counts = self._counts[run_index]
+        goal_actors = [(i, a) for i, a in enumerate(self.dose_actors) if a.uncertainty_goal is not None]
+        first = base
+        n_run = 0
+        for si, n in enumerate(counts):
+            if n <= 0:
+                continue
+            if not goal_actors:
+                self._launch(si, first, n)
+                n_run += n
+            else:
+                # stop rule of GateDoseActor::EndOfEventAction (GateDoseActor.cpp:245-278): check after
+                # N events, then re-estimate N = (u/goal)^2 * n * overshoot
+                i, a = goal_actors[0]
+                done = 0
+                next_check = int(a.uncertainty_first_check_after_n_events)
+                while done < n:
+                    k = min(max(next_check - (n_run + done), 1), n - done)
+                    self._launch(si, first + done, k)
+                    done += k
+                    self._sync()
+                    u = self._mean_uncertainty(i, a, n_run + done)
+                    if u <= a.uncertainty_goal:
+                        break
+                    next_check = int((u / a.uncertainty_goal) ** 2 * (n_run + done) * a.uncertainty_overshoot_factor_N_events)
+                n_run += done
+            first += n
+        self._sync()
+        # statistics: summed over shards
+        st = None
+        for e in self.engines:
+            s = e.stats()
+            st = dict(s) if st is None else {k: (st[k] + s[k] if k != "kernel_ms" else max(st[k], s[k])) for k in st}
+        if self.dist is not None:
+            st = multigpu.reduce_counters(st, f"cuda:{self.local_rank}")
+        n_events = int(st["histories"])
+        # dose actors
+        for i, a in enumerate(self.dose_actors):
+            which = multigpu.active_grids(a.score_flags())
+            grids = self._gather_grids(i, which)
+            a.store_run(run_index, grids, n_events)
+        # phase space: rows of all shards concatenated (EventID is the global history id of the run)
+        for i, a in enumerate(self.phsp_actors):
+            rows = None
+            for e, ids in zip(self.engines, self.ids):
+                r = e.phsp(ids[2][i])
+                rows = r if rows is None else {k: np.concatenate([rows[k], r[k]]) for k in rows}
+            if self.dist is not None:
+                gathered = [None] * self.world
+                self.dist.all_gather_object(gathered, rows)
+                rows = {k: np.concatenate([g[k] for g in gathered]) for k in rows}
+            order = np.lexsort((rows["Time"], rows["EventID"]))
+            rows = {k: v[order] for k, v in rows.items()}
+            a.store_rows(rows, st["absorbed_events"] if a.store_absorbed_event else 0, event_offset=-base)
+            if st["phsp_dropped"]:
+                warning(f"PhaseSpaceActor '{a.name}': {st['phsp_dropped']} rows dropped (max_rows too small)")
+        return st
+
+
+def host_mean_uncertainty(edep, edep_sq, n_events, top_voxels, threshold):
+    """GateDoseActor::ComputeMeanUncertainty (GateDoseActor.cpp:280-330) on host arrays (multi-shard case)."""
+    n = max(float(n_events), 2.0)
+    flat = np.asarray(edep).ravel()
+    k = min(int(top_voxels), flat.size)
+    top = np.partition(flat, flat.size - k)[flat.size - k:] if k > 0 else np.zeros(0)
+    thr = (top.mean() if k > 0 else 0.0) * threshold
+    sel = flat > thr
+    if not sel.any():
+        return 1.0
+    val = flat[sel] / n
+    sq = np.asarray(edep_sq).ravel()[sel] / n
+    u = np.sqrt(np.clip((sq - val * val) / (n - 1.0), 0, None)) / val
+    u = np.minimum(u, 1.0)
+    s = u.sum()
+    return float(s / sel.sum()) if s > 0 else 1.0

@@ -188,6 +188,9 @@ def philox(seed, hist, block):
 # numpy restatements of the reference's host-side algorithms
 # ---------------------------------------------------------------------------------------
 
+G4_G_CM3 = 6.241509074460762e18   # opengate/utility.py:230 ("g/cm3")
+
+
 def hu_read_materials_table(path):
     """Restates opengate/geometry/materials.py:61-100 (HU_read_materials_table)."""
     elements = ["HU"]
@@ -287,7 +290,10 @@ def hounsfield_to_materials(density_tolerance_g_cm3, file_mat, file_density):
         dmin = hu_interp_density(hu_min, densities)
         dmax = hu_interp_density(hu_max, densities)
         ddiff = hu_max_density_difference(hu_min, hu_max, dmin, dmax, densities)
-        n = max(1, ddiff / density_tolerance_g_cm3)
+        # same arithmetic as the reference, which carries Geant4 units on both sides
+        # (ddiff * gcm3 / density_tolerance with density_tolerance = tol * gcm3): the rounding of
+        # the sub-interval bounds depends on it (pinned by tests/golden/schneider_reference.json)
+        n = max(1, ddiff * G4_G_CM3 / (density_tolerance_g_cm3 * G4_G_CM3))
         if "Air" in mat["name"] or "AIR" in mat["name"]:
             n = 1
         htol = (hu_max - hu_min) / n

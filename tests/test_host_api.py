@@ -1,0 +1,258 @@
+"""The drop-in layer: a GATE-10-style script (Simulation / add_volume('Image') / GenericSource /
+VoxelSource / DoseActor / PhaseSpaceActor / SimulationStatisticsActor) run through
+GpuSimulationEngine.  The host logic is exercised on CPU by injecting the oracle as the
+transport back end (tests/oracle_backend.py); the same scripts run on the CUDA engine in
+tests/test_gpu_parity.py::test_script_level_*."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import opengate_b200 as gate
+from opengate_b200 import image as gimage
+from opengate_b200.base import GateDeprecationError
+from oracle_backend import OracleBackend
+
+mm, cm, m = gate.g4_units.mm, gate.g4_units.cm, gate.g4_units.m
+keV, MeV, Bq, sec, deg = gate.g4_units.keV, gate.g4_units.MeV, gate.g4_units.Bq, gate.g4_units.s, gate.g4_units.deg
+
+
+def make_ct(tmp_path, n=(24, 20, 16), spacing=(10.0, 10.0, 12.0)):
+    nx, ny, nz = n
+    hu = np.full((nz, ny, nx), -1000, dtype=np.int16)
+    hu[2:-2, 3:-3, 3:-3] = 40
+    hu[4:-4, 6:-6, 6:10] = -750
+    hu[4:-4, 8:12, 14:17] = 900
+    img = gimage.Image(hu, spacing, origin=(-50.0, 20.0, 7.0))
+    p = tmp_path / "ct.mhd"
+    gimage.write_image(img, str(p))
+    return str(p), hu
+
+
+def ct_sim(tmp_path, n_primaries=4000, **kw):
+    path, hu = make_ct(tmp_path)
+    sim = gate.Simulation()
+    sim.random_seed = 987654321
+    sim.output_dir = str(tmp_path / "out")
+    sim.world.size = [2 * m, 2 * m, 2 * m]
+    ct = sim.add_volume("Image", "ct")
+    ct.image = path
+    ct.material = "G4_AIR"
+    tol = 0.05 * gate.g4_units.g_cm3
+    ct.voxel_materials, _ = gate.geometry.materials.HounsfieldUnit_to_material(sim, tol)
+    ct.translation = [5 * mm, -10 * mm, 0]
+    sim.physics_manager.physics_list_name = "G4EmStandardPhysics_option4"
+    sim.physics_manager.set_production_cut("world", "all", 1 * m)
+    sim.physics_manager.set_production_cut("ct", "all", 1 * m)
+    src = sim.add_source("GenericSource", "xray")
+    src.particle = "gamma"
+    src.energy.type = "spectrum_histogram"
+    src.energy.spectrum_energy_bin_edges = [40 * keV, 60 * keV, 80 * keV, 120 * keV]
+    src.energy.spectrum_weights = [1.0, 2.0, 0.5]
+    src.position.type = "disc"
+    src.position.radius = 30 * mm
+    src.position.translation = [0, 0, -400 * mm]
+    src.direction.type = "momentum"
+    src.direction.momentum = [0, 0, 1]
+    src.number_of_primaries = n_primaries
+    dose = sim.add_actor("DoseActor", "dose")
+    dose.attached_to = "ct"
+    dose.size = "like_image_volume"
+    dose.spacing = "like_image_volume"
+    dose.hit_type = "random"
+    dose.output_filename = "ct.mhd"
+    return sim, ct, src, dose, hu
+
+
+def test_ct_dose_script_end_to_end(tmp_path):
+    sim, ct, src, dose, hu = ct_sim(tmp_path)
+    dose.dose.active = True
+    dose.dose_uncertainty.active = True
+    dose.edep_uncertainty.active = True
+    dose.density.active = True
+    dose.counts.active = True
+    stats = sim.add_actor("SimulationStatisticsActor", "stats")
+    out = sim.run(_backend=OracleBackend)
+    assert out.current_random_seed == 987654321 and out.expected_number_of_events == 4000
+    assert stats.counts["events"] == 4000 and stats.counts["runs"] == 1 and stats.pps > 0
+    e = dose.edep.image
+    assert list(e.size) == [24, 20, 16] and np.allclose(e.spacing, [10, 10, 12])
+    # local coordinate system: centred on the volume (doseactors.py:170-232)
+    assert np.allclose(e.origin, [-115.0, -95.0, -90.0])
+    assert e.array.dtype == np.float64 and e.array.sum() > 0
+    # edep only where the beam passes; nothing scored outside the grid
+    st = out.device_stats[0]
+    assert e.array.sum() <= st["edep_total_MeV"] * (1 + 1e-9)
+    # dose [Gy] = sum(edep_i / rho_i) / (voxel volume) in Gy: check one homogeneous voxel by hand
+    d = dose.dose.image.array
+    dens = dose.density.image.array
+    vox_mm3 = 10 * 10 * 12
+    MeV_per_g_to_Gy = 1.602176634e-10
+    body = (hu == 40) & (e.array > 0)
+    k = np.argwhere(body)[0]
+    want = e.array[tuple(k)] / (dens[tuple(k)] * vox_mm3 * 1e-3) * MeV_per_g_to_Gy
+    assert d[tuple(k)] == pytest.approx(want, rel=1e-6)
+    # uncertainty images follow the reference algebra on (sum, sum of squares, N)
+    sq = dose.user_output["edep_with_uncertainty"].get_data("merged", 1).array
+    n = 4000
+    var = np.clip((sq / n - (e.array / n) ** 2) / (n - 1), 0, None)
+    want_u = np.divide(np.sqrt(var), e.array / n, out=np.zeros_like(var), where=e.array != 0)
+    np.testing.assert_allclose(dose.edep_uncertainty.image.array, want_u, rtol=1e-12)
+    assert np.all(dose.counts.image.array[e.array > 0] >= 1)
+    # files: names get the item suffix; squared items that were only activated for the uncertainty
+    # are not written (doseactors.py:575-589); sidecar json carries number_of_samples
+    files = sorted(os.listdir(tmp_path / "out"))
+    for f in ("ct_edep.mhd", "ct_edep_uncertainty.mhd", "ct_dose.mhd", "ct_dose_uncertainty.mhd", "ct_density.mhd", "ct_counts.mhd"):
+        assert f in files, (f, files)
+    assert "ct_edep_squared.mhd" not in files and "ct_dose_squared.mhd" not in files
+    assert json.load(open(tmp_path / "out" / "ct_edep.json")) == {"number_of_samples": 4000}
+    back = gimage.read_image(str(dose.edep.get_output_path()))
+    np.testing.assert_array_equal(back.array, e.array)
+    assert str(dose.edep.get_output_path()).endswith("out/ct_edep.mhd")
+
+
+def test_label_volume_is_integer_exact_and_placed_like_the_reference(tmp_path):
+    from opengate_b200.engines import GpuSimulationEngine
+    sim, ct, src, dose, hu = ct_sim(tmp_path)
+    sim.resolve_and_validate_config()
+    S = GpuSimulationEngine(sim).build_setup()
+    # label rule: np.digitize over the Schneider intervals, label 0 = volume material, in order of HU
+    lut = ct.material_to_label_lut
+    names = list(lut)
+    assert names[0] == "G4_AIR" and lut["Air_0"] == 1
+    vm = sorted(ct.voxel_materials, key=lambda r: r[0])
+    want = np.zeros_like(hu, dtype=np.uint16)
+    for lo, hi, name in vm:
+        want[(hu >= lo) & (hu < hi)] = lut[name]
+    assert np.array_equal(S.labels.astype(np.uint16), want)
+    assert S.labels.dtype == np.uint8 and len(S.tables.names) == 75
+    # the input image origin is NOT used for placement: the box is centred on `translation`
+    assert np.allclose(S.world_to_volume[:, 3], [-5, 10, 0]) and np.allclose(S.world_to_volume[:, :3], np.eye(3))
+    # output_coordinate_system = attached_to_image uses the image's own origin
+    dose.output_coordinate_system = "attached_to_image"
+    o, r = dose.output_origin_rotation()
+    assert np.allclose(o, [-50.0, 20.0, 7.0])
+
+
+def test_two_runs_and_run_merging(tmp_path):
+    sim, ct, src, dose, hu = ct_sim(tmp_path)
+    sim.run_timing_intervals = [[0, 1 * sec], [1 * sec, 2 * sec]]
+    src.number_of_primaries = [1500, 2500]
+    dose.edep_squared.active = True
+    dose.edep.keep_data_per_run = True
+    out = sim.run(_backend=OracleBackend)
+    assert [s["histories"] for s in out.device_stats] == [1500, 2500]
+    o = dose.user_output["edep_with_uncertainty"]
+    assert o.merged_samples == 4000
+    r0, r1 = dose.edep.get_data(0).array, dose.edep.get_data(1).array
+    np.testing.assert_allclose(dose.edep.image.array, r0 + r1, rtol=1e-14)
+    # the same 4000 histories in ONE run give the same total (history ids continue across runs)
+    sim2, ct2, src2, dose2, _ = ct_sim(tmp_path)
+    sim2.output_dir = str(tmp_path / "out2")
+    sim2.run(_backend=OracleBackend)
+    np.testing.assert_allclose(dose2.edep.image.array, dose.edep.image.array, rtol=1e-12)
+
+
+def test_voxel_source_and_phase_space_plane(tmp_path):
+    sim, ct, src, dose, hu = ct_sim(tmp_path)
+    sim.source_manager.sources.clear()
+    act = np.zeros((8, 10, 12), dtype=np.float32)
+    act[3:5, 4:6, 5:8] = 1.0
+    gimage.write_image(gimage.Image(act, (20.0, 20.0, 24.0)), str(tmp_path / "act.mhd"))
+    vs = sim.add_source("VoxelSource", "tc99m")
+    vs.attached_to = "ct"
+    vs.image = str(tmp_path / "act.mhd")
+    vs.particle = "gamma"
+    vs.energy.mono = 140.511 * keV
+    vs.direction.type = "iso"
+    vs.number_of_primaries = 6000
+    plane = sim.add_volume("Box", "plane")
+    plane.size = [600 * mm, 2 * mm, 600 * mm]
+    plane.translation = [0, 300 * mm, 0]
+    plane.material = "G4_AIR"
+    ph = sim.add_actor("PhaseSpaceActor", "phsp")
+    ph.attached_to = plane
+    ph.attributes = ["KineticEnergy", "PrePosition", "PreDirection", "Weight", "EventID", "TimeFromBeginOfEvent"]
+    ph.steps_to_store = "entering"
+    ph.store_absorbed_event = True
+    ph.output_filename = "plane.root"
+    sim.run(_backend=OracleBackend)
+    n = ph.total_number_of_entries
+    assert 0 < n < 6000 and ph.number_of_absorbed_events == 6000 - len(np.unique(ph.data["EventID"]))
+    assert set(ph.data) == {"KineticEnergy", "PrePosition_X", "PrePosition_Y", "PrePosition_Z", "PreDirection_X",
+                            "PreDirection_Y", "PreDirection_Z", "Weight", "EventID", "TimeFromBeginOfEvent"}
+    assert ph.data["EventID"].dtype == np.int32 and ph.data["KineticEnergy"].dtype == np.float64
+    # entering the plane box from below: on its -y face, moving towards +y; primaries keep 140.5 keV
+    y = ph.data["PrePosition_Y"]
+    on_face = np.abs(y - 299.0) < 2e-2
+    assert on_face.mean() > 0.98 and np.all((y > 298.99) & (y < 301.01))
+    assert np.all(ph.data["PreDirection_Y"][on_face] > 0)
+    assert ph.data["KineticEnergy"].max() == pytest.approx(0.140511, rel=1e-6)
+    assert np.all(ph.data["KineticEnergy"] > 0.001) and np.all(ph.data["EventID"] < 6000)
+    # uproot is absent here: ROOT request falls back to npz with the same columns
+    assert os.path.exists(tmp_path / "out" / "plane.npz")
+    # emission positions: all inside the hot block of the activity image, in the CT frame (+ translation)
+    d = dose.edep.image.array
+    assert d.sum() > 0
+
+
+def test_activity_source_draws_poisson_counts(tmp_path):
+    sim, ct, src, dose, hu = ct_sim(tmp_path)
+    src.number_of_primaries = 0
+    src.activity = 3000 * Bq
+    sim.run_timing_intervals = [[0, 1 * sec]]
+    out = sim.run(_backend=OracleBackend)
+    n = out.device_stats[0]["histories"]
+    # spectrum weights sum (x bin width) scales the activity (GateGenericSource.cpp:622-626)
+    scale = 1.0 * 0.02 + 2.0 * 0.02 + 0.5 * 0.04
+    assert abs(n - 3000 * scale) < 6 * np.sqrt(3000 * scale)
+
+
+def test_unsupported_configurations_are_fatal(tmp_path):
+    sim, ct, src, dose, hu = ct_sim(tmp_path)
+    with pytest.raises(Exception, match="gammas only"):
+        src.particle = "e-"
+    with pytest.raises(Exception, match="not an allowed value"):
+        dose.hit_type = "somewhere"
+    with pytest.raises(GateDeprecationError):
+        dose.dose = True
+    with pytest.raises(GateDeprecationError):
+        src.n = 10
+    with pytest.raises(Exception, match="not supported"):
+        sim.add_actor("LETActor", "let")
+    with pytest.raises(Exception, match="not supported"):
+        sim.add_volume("Sphere", "s")
+    sim.engine = "geant4"
+    with pytest.raises(Exception, match="reference's own SimulationEngine"):
+        sim.run(_backend=OracleBackend)
+    sim.engine = "b200"
+    dose.score_in = "G4_WATER"
+    with pytest.raises(Exception, match="score_in"):
+        sim.run(_backend=OracleBackend)
+    dose.score_in = "material"
+    src.direction.type = "beam2d"
+    with pytest.raises(Exception, match="direction.type"):
+        sim.run(_backend=OracleBackend)
+
+
+def test_uncertainty_goal_stops_the_run_early(tmp_path):
+    sim, ct, src, dose, hu = ct_sim(tmp_path, n_primaries=200000)
+    dose.uncertainty_goal = 0.25
+    dose.uncertainty_first_check_after_n_events = 2000
+    dose.uncertainty_top_voxels_count = 5
+    dose.uncertainty_voxel_edep_threshold = 0.7
+
+    class B(OracleBackend):
+        def mean_uncertainty(self, actor, n_events, top, thr):
+            from oracle.oracle import mean_uncertainty
+            from opengate_b200 import abi
+            return mean_uncertainty(self.dose_grid(actor, abi.GRID_EDEP), self.dose_grid(actor, abi.GRID_EDEP_SQ), n_events, top, thr)
+
+    out = sim.run(_backend=B)
+    n = out.device_stats[0]["histories"]
+    assert 2000 <= n < 200000
+    from opengate_b200.engines import host_mean_uncertainty
+    o = dose.user_output["edep_with_uncertainty"]
+    u = host_mean_uncertainty(o.get_data("merged", 0).array, o.get_data("merged", 1).array, n, 5, 0.7)
+    assert u <= 0.25

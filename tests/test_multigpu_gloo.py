@@ -1,0 +1,84 @@
+"""N>1 host logic on CPU: two gloo ranks shard the histories of one run by global history id
+(split rule of the reference, sources/base.py:190-197), reduce their grids, and must reproduce the
+single-rank result.  The transport itself is done by the CPU oracle (test infrastructure)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from opengate_b200 import abi, multigpu
+from opengate_b200.sources import scale_counts_for_rank
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_split_rule_matches_reference_formula():
+    for n in (0, 1, 7, 8, 1000003):
+        for world in (1, 2, 3, 8):
+            parts = [multigpu.split_primaries(n, world, r) for r in range(world)]
+            assert sum(c for _, c in parts) == n
+            assert [c for _, c in parts] == [int(scale_counts_for_rank(n, r, world)) for r in range(world)]
+            # contiguous, ordered id ranges
+            off = 0
+            for f, c in parts:
+                assert f == off
+                off += c
+
+
+def _worker(rank, world, port, n, q):
+    sys.path.insert(0, HERE)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.oracle import TransportOracle
+    from small_setups import c3
+    S = c3(n)
+    o = TransportOracle(S.seed)
+    sids, dids, _ = S.apply(o)
+    o.begin_run()
+    first, cnt = multigpu.split_primaries(n, world, rank)
+    o.run_source(sids[0], first, cnt, 0)
+    grids = {}
+    for w in multigpu.active_grids(S.dose[0].score_flags):
+        t = torch.from_numpy(np.array(o.dose_grid(0, w), dtype=np.float64, copy=True))
+        dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
+        grids[w] = t.numpy()
+    st = multigpu.reduce_counters(o.stats(), "cpu")
+    if rank == 0:
+        q.put((grids, st))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_run_equals_single_rank():
+    n = 6001
+    sys.path.insert(0, HERE)
+    from oracle.oracle import TransportOracle
+    from small_setups import c3
+    S = c3(n)
+    ref = TransportOracle(S.seed)
+    sids, _, _ = S.apply(ref)
+    ref.begin_run()
+    ref.run_source(sids[0], 0, n, 0)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    grids, st = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    a = ref.stats()
+    for k in ("histories", "tentative_collisions", "n_phot", "n_compt", "n_rayl", "deposits", "flushed_entries", "escaped"):
+        assert st[k] == a[k], k
+    for w, g in grids.items():
+        want = np.array(ref.dose_grid(0, w), dtype=np.float64)
+        if w == abi.GRID_COUNTS:
+            assert np.array_equal(g, want)
+        else:
+            np.testing.assert_allclose(g, want, rtol=1e-12, atol=0)

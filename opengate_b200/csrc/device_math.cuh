@@ -99,22 +99,33 @@ __device__ __forceinline__ void philox_block(uint32_t k0, uint32_t k1, uint32_t 
   r0 = c0; r1 = c1; r2 = c2; r3 = c3;
 }
 
-__device__ __forceinline__ void rng_init(Rng &r, uint64_t seed, uint64_t hist) {
-  r.k0 = (uint32_t)seed; r.k1 = (uint32_t)(seed >> 32);
-  r.h0 = (uint32_t)hist; r.h1 = (uint32_t)(hist >> 32);
-  r.blk = 0; r.pos = 4;
+__device__ __forceinline__ float u32_to_uniform(uint32_t x) {
+  // uniform in (0,1): the top 24 bits, centred in their bin
+  return (float)(x >> 8) * 5.9604644775390625e-8f + 2.98023223876953125e-8f;
 }
 
-// uniform in (0,1): the top 24 bits, centred in their bin
+__device__ __forceinline__ void rng_init(Rng &r, uint64_t seed, uint64_t hist, uint32_t blk) {
+  r.k0 = (uint32_t)seed; r.k1 = (uint32_t)(seed >> 32);
+  r.h0 = (uint32_t)hist; r.h1 = (uint32_t)(hist >> 32);
+  r.blk = blk; r.pos = 4;
+}
+
+// A phase call starts on a fresh block (DESIGN.md "random-number protocol").
+__device__ __forceinline__ void rng_begin(Rng &r) { r.pos = 4; }
+
+// one copy of the 10 rounds for all the lazy draws of the rare phases (code size)
+__device__ __noinline__ void rng_refill(Rng &r) {
+  philox_block(r.k0, r.k1, r.h0, r.h1, r.blk, 0u, r.o0, r.o1, r.o2, r.o3);
+  r.blk += 1u;
+  r.pos = 0;
+}
+
 __device__ __forceinline__ float rng_uniform(Rng &r) {
-  if (r.pos == 4) {
-    philox_block(r.k0, r.k1, r.h0, r.h1, r.blk, 0u, r.o0, r.o1, r.o2, r.o3);
-    r.blk += 1u;
-    r.pos = 0;
-  }
-  uint32_t x = r.pos == 0 ? r.o0 : (r.pos == 1 ? r.o1 : (r.pos == 2 ? r.o2 : r.o3));
+  if (r.pos == 4) rng_refill(r);
+  uint32_t x = r.o0;
+  r.o0 = r.o1; r.o1 = r.o2; r.o2 = r.o3;   // shift instead of a 4-way select on r.pos
   r.pos += 1;
-  return (float)(x >> 8) * 5.9604644775390625e-8f + 2.98023223876953125e-8f;
+  return u32_to_uniform(x);
 }
 
 }  // namespace gb2

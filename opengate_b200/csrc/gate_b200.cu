@@ -65,7 +65,7 @@ struct gate_b200_engine {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_events;
   double kernel_ms = 0.0;
   int sm_count = 148;
-  int block = 256, blocks_per_sm = 0;
+  int max_ctas = 148;                   // persistent CTAs (one per SM); scratch is sized for it
   int label_bytes = 0;
 };
 
@@ -165,8 +165,12 @@ int gate_b200_create(int device_id, uint64_t seed, gate_b200_engine **out) {
   h->P.stats = h->d_stats;
   h->P.edep_total = h->d_edep;
   h->P.wh[0] = h->P.wh[1] = h->P.wh[2] = 1.0e6f;
-  if (const char *s = getenv("GATE_B200_BLOCK")) h->block = std::max(32, atoi(s) / 32 * 32);
-  if (const char *s = getenv("GATE_B200_BLOCKS_PER_SM")) h->blocks_per_sm = atoi(s);
+  h->max_ctas = h->sm_count;
+  if (const char *s = getenv("GATE_B200_CTAS")) h->max_ctas = std::max(1, atoi(s));
+  // per-slot global scratch: coalescing buffers of the histories in flight, pending photons
+  const size_t nslots = (size_t)h->max_ctas * kSlots;
+  if (int rc = dev_alloc(h, &h->P.depbuf, nslots * kDepBuf)) return rc;
+  if (int rc = dev_alloc(h, &h->P.pend, nslots * 6)) return rc;
   return GATE_B200_OK;
 }
 
@@ -208,10 +212,21 @@ int gate_b200_set_tables(gate_b200_engine *h, const gate_b200_tables *t) {
   P.nmat = t->n_materials; P.ne = t->n_energy; P.nq = t->n_q; P.pair_mode = t->pair_mode;
   const size_t n = (size_t)P.nmat * P.ne, nqq = (size_t)P.nmat * P.nq;
   if (int rc = dev_upload(h, &P.dens, t->density_g_cm3, (size_t)P.nmat)) return rc;
-  if (int rc = dev_upload(h, &P.mu, t->mu_total_per_mm, n)) return rc;
-  if (int rc = dev_upload(h, &P.cph, t->cum_phot, n)) return rc;
-  if (int rc = dev_upload(h, &P.cco, t->cum_compt, n)) return rc;
-  if (int rc = dev_upload(h, &P.cra, t->cum_rayl, n)) return rc;
+  {
+    // energy-major re-packing of the material-major ABI arrays (same float values)
+    std::vector<float2> mu2(n);
+    std::vector<float4> prob(n);
+    for (int ie = 0; ie < P.ne; ++ie) {
+      const int ie1 = ie + 1 < P.ne ? ie + 1 : ie;
+      for (int m = 0; m < P.nmat; ++m) {
+        const size_t a = (size_t)m * P.ne + ie, b = (size_t)m * P.ne + ie1, o = (size_t)ie * P.nmat + m;
+        mu2[o] = make_float2(t->mu_total_per_mm[a], t->mu_total_per_mm[b]);
+        prob[o] = make_float4(t->cum_phot[a], t->cum_compt[a], t->cum_rayl[a], 0.0f);
+      }
+    }
+    if (int rc = dev_upload(h, &P.mu2, mu2.data(), n)) return rc;
+    if (int rc = dev_upload(h, &P.prob, prob.data(), n)) return rc;
+  }
   if (int rc = dev_upload(h, &P.ray, t->rayl_cum_ff2, nqq)) return rc;
   if (int rc = dev_upload(h, &P.sf, t->compt_sf, nqq)) return rc;
   h->h_mu.assign(t->mu_total_per_mm, t->mu_total_per_mm + n);
@@ -462,22 +477,18 @@ int gate_b200_run_source(gate_b200_engine *h, int32_t source_id, uint64_t first_
   P.first = first_history;
   P.count = n_histories;
   CU(cudaMemsetAsync(h->d_next, 0, sizeof(unsigned long long), h->stream));
-  const size_t smem = (size_t)P.ne * sizeof(float);
+  const size_t smem = sizeof(Smem) + (size_t)P.ne * sizeof(float);
   auto kern = (label_bytes == 2) ? transport_kernel<uint16_t> : transport_kernel<uint8_t>;
-  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int bps = h->blocks_per_sm;
-  if (bps <= 0) {
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, h->block, smem));
-    if (bps < 1) bps = 1;
-  }
-  unsigned long long want = (n_histories + h->block - 1) / h->block;
-  unsigned long long grid = std::min<unsigned long long>((unsigned long long)h->sm_count * bps, want);
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // persistent CTAs: one per SM, fewer only when there is not enough work to fill the slots
+  unsigned long long want = (n_histories + 255) / 256;
+  unsigned long long grid = std::min<unsigned long long>((unsigned long long)h->max_ctas, want);
   if (grid < 1) grid = 1;
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0));
   CU(cudaEventCreate(&e1));
   CU(cudaEventRecord(e0, h->stream));
-  kern<<<(unsigned)grid, h->block, smem, h->stream>>>(P);
+  kern<<<(unsigned)grid, kThreads, smem, h->stream>>>(P);
   CU(cudaGetLastError());
   CU(cudaEventRecord(e1, h->stream));
   h->pending_events.emplace_back(e0, e1);

@@ -1,16 +1,21 @@
 // transport.cuh — device data model + the photon transport kernel (sm_100a).
 //
-// One thread owns one photon history at a time (persistent threads, refilled from a global
-// history counter; Philox stream = history id).  Per history:
-//   primary generation  -> world flight (analytic, homogeneous world material)
-//   -> Woodcock delta tracking through the label volume against the majorant of the
-//      materials present -> Compton (Klein-Nishina x scattering function), Rayleigh (form
-//      factor), photoelectric, conversion -> kerma deposit into a per-history coalescing
-//      buffer -> at history end one (value, value^2) pair per touched voxel is added to the
-//      fp64 grids with warp-aggregated atomics.
+// Execution model (DESIGN.md "kernel"): one persistent CTA per SM owns kSlots photon slots whose
+// state lives in shared memory.  A photon is always waiting for exactly one kind of work:
+//   Q_V  Woodcock flight through the label volume (kWoodcockK speculative tentative collisions)
+//   Q_I  one real interaction (Compton / Rayleigh / photoelectric / conversion) + kerma deposit
+//   Q_W  one flight segment in the homogeneous world (entry, exit, phase-space planes)
+//   Q_E  end of a photon: second annihilation photon, or close the history (flush its coalesced
+//        deposits with warp-aggregated fp64 atomics) and start the next primary
+// and sits in the shared-memory ring queue of that kind.  Every warp of the CTA runs the same loop:
+// claim up to 32 slots from the fullest queue, run that phase for all of them in lock-step, push each
+// slot to the queue of its next phase.  This is stream compaction inside a persistent kernel: warps
+// always execute one code path with (nearly) all lanes, whatever the mix of photon states.
+// The history -> random-number mapping does not depend on the scheduling: every phase call starts on
+// a fresh Philox block of that history (counter = history id, block number).
 // Reference semantics restated (OpenGATE/opengate @ 9b07951): see include/gate_b200.h for the
 // file:line of each replaced interface; the oracle (oracle/transport_oracle.c) is the scalar
-// statement of the same algorithm.
+// statement of the same algorithm and is matched bit for bit.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -18,17 +23,30 @@
 #include "../../include/gate_b200.h"
 #include "device_math.cuh"
 
+#ifndef GB2_THREADS
+#define GB2_THREADS 1024
+#endif
+#ifndef GB2_SLOTS
+#define GB2_SLOTS 2048
+#endif
+
 namespace gb2 {
 
+constexpr int kThreads = GB2_THREADS;
+constexpr int kSlots = GB2_SLOTS;          // photon slots per CTA (power of two)
+constexpr int kSlotMask = kSlots - 1;
+constexpr int kWoodcockK = 4;              // tentative collisions per Woodcock call (2 Philox blocks)
 constexpr int kMaxDose = 4;
 constexpr int kMaxPhsp = 4;
-constexpr int kDepBuf = 32;            // per-history coalescing buffer entries
-constexpr float kNudge = 1.0e-3f;      // mm pushed across a boundary
+constexpr int kDepBuf = 32;                // per-history coalescing buffer entries
+constexpr float kNudge = 1.0e-3f;          // mm pushed across a boundary
 constexpr float kBig = 3.0e38f;
 constexpr float kMc2 = 0.51099891f;
-constexpr float kKPerMeV = 268.17264f; // photon wave number (1/bohr) per MeV
+constexpr float kKPerMeV = 268.17264f;     // photon wave number (1/bohr) per MeV
 constexpr float kCmmPerNs = 299.792458f;
 constexpr int kMaxIter = 1000000;
+
+enum { Q_V = 0, Q_I = 1, Q_W = 2, Q_E = 3, Q_COUNT = 4, Q_RETIRED = -1 };
 
 struct Affine { float m[9]; float t[3]; };
 
@@ -65,7 +83,9 @@ struct DPhsp {
   unsigned long long *n_rows, *n_dropped;
 };
 
-// indices into the device statistics array (unsigned long long)
+struct DepEntry { int key; float e; float d; int n; };   // one (voxel, history) partial sum
+
+// indices into the statistics array (unsigned long long)
 enum { S_HIST = 0, S_TRACKS, S_STEPS, S_TENT, S_PHOT, S_COMPT, S_RAYL, S_CONV, S_DEP, S_FLUSH,
        S_OVER, S_ESC, S_ABSORBED, S_COUNT };
 
@@ -74,7 +94,11 @@ struct Params {
   int nmat, ne, nq, pair_mode;
   float ln_emin, inv_dlne, e_cut;
   float ln_q2min, inv_dlnq2;
-  const float *dens, *mu, *cph, *cco, *cra, *maj, *q2n, *ray, *sf;
+  // energy-major tables: a photon keeps its energy between interactions, so all the Woodcock
+  // look-ups of one flight hit the same two rows
+  const float2 *mu2;     // [ne][nmat] {mu(ie), mu(ie+1)} total attenuation, 1/mm
+  const float4 *prob;    // [ne][nmat] {P(phot), P(phot)+P(compt), ...+P(rayl), 0}
+  const float *dens, *maj, *q2n, *ray, *sf;
   float wh[3];
   int world_mat;
   int has_vol;
@@ -91,7 +115,35 @@ struct Params {
   unsigned long long *next;      // history counter of this launch
   unsigned long long *stats;     // [S_COUNT]
   double *edep_total;
+  DepEntry *depbuf;              // [gridDim.x * kSlots][kDepBuf] coalescing buffers (global scratch)
+  float *pend;                   // [gridDim.x * kSlots][6] second annihilation photon (pair_mode 1)
 };
+
+// Shared memory of one CTA: photon slots (structure of arrays), the four ring queues, statistics.
+struct Smem {
+  float px[kSlots], py[kSlots], pz[kSlots];   // world frame outside the volume, volume frame inside
+  float dx[kSlots], dy[kSlots], dz[kSlots];
+  float E[kSlots], tbin[kSlots], w[kSlots], path[kSlots], seg[kSlots];
+  unsigned hlo[kSlots], hhi[kSlots], blk[kSlots];
+  int mat[kSlots];
+  unsigned flags[kSlots];
+  int iter[kSlots];
+  int cell[Q_COUNT][kSlots];
+  int head[Q_COUNT], tail[Q_COUNT], avail[Q_COUNT];
+  int retired;
+  unsigned long long stats[S_COUNT];
+  double edep;
+};
+
+// bits of Smem::flags
+constexpr unsigned F_INSIDE = 0xfu;        // bit k: currently inside phase-space box k
+constexpr unsigned F_STORED = 1u << 4;     // the history left at least one phase-space row
+constexpr unsigned F_PEND_SHIFT = 5;       // 0 none, 1 pending photon in the volume frame, 2 world frame
+constexpr unsigned F_PEND = 3u << F_PEND_SHIFT;
+constexpr unsigned F_INVOL = 1u << 7;      // the pending interaction is inside the image volume
+constexpr unsigned F_OPEN = 1u << 8;       // a history is in flight in this slot
+constexpr unsigned F_NBUF_SHIFT = 16;      // entries in the coalescing buffer
+constexpr unsigned F_NBUF = 0x3fu << F_NBUF_SHIFT;
 
 // ------------------------------------------------------------------------------ helpers
 
@@ -166,12 +218,6 @@ __device__ __forceinline__ bool inside_box(const float p[3], const float h[3]) {
   return p[0] > -h[0] && p[0] < h[0] && p[1] > -h[1] && p[1] < h[1] && p[2] > -h[2] && p[2] < h[2];
 }
 
-__device__ __forceinline__ float tab(const float *__restrict__ t, int ne, int m, int ie, float fe) {
-  const float *r = t + (size_t)m * ne + ie;
-  float a = __ldg(r), b = __ldg(r + 1);
-  return a + fe * (b - a);
-}
-
 __device__ __forceinline__ int lower_bound_f(const float *__restrict__ a, int n, float p) {
   int lo = 0, hi = n;
   while (lo < hi) {
@@ -181,48 +227,93 @@ __device__ __forceinline__ int lower_bound_f(const float *__restrict__ a, int n,
   return lo;
 }
 
-// ------------------------------------------------------------------------------ per-thread state
 
-struct Photon {
-  float p[3], d[3];   // world frame outside the volume, volume frame inside
+__device__ __forceinline__ int ld_vol(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
+__device__ __forceinline__ void st_vol(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
+
+// The coalescing buffers and the pending-photon scratch live in global memory and are handed from
+// warp to warp with the slot: access them at L2 (ld.cg / st.cg), never through the read-only path.
+__device__ __forceinline__ DepEntry ld_dep(const DepEntry *p) {
+  const int4 v = __ldcg(reinterpret_cast<const int4 *>(p));
+  DepEntry e; e.key = v.x; e.e = __int_as_float(v.y); e.d = __int_as_float(v.z); e.n = v.w;
+  return e;
+}
+__device__ __forceinline__ void st_dep(DepEntry *p, const DepEntry &e) {
+  __stcg(reinterpret_cast<int4 *>(p), make_int4(e.key, __float_as_int(e.e), __float_as_int(e.d), e.n));
+}
+
+__device__ __forceinline__ float tab_mu(const Params &P, int m, int ie, float fe) {
+  const float2 v = __ldg(P.mu2 + (size_t)ie * P.nmat + m);
+  return v.x + fe * (v.y - v.x);
+}
+
+// opportunistic warp aggregation of a statistics increment (the lanes that arrive together)
+__device__ __forceinline__ void stat_add(Smem &S, int idx, unsigned v) {
+  const unsigned act = __activemask();
+  const unsigned sum = __reduce_add_sync(act, v);
+  if ((int)(threadIdx.x & 31u) == __ffs(act) - 1 && sum) atomicAdd(&S.stats[idx], (unsigned long long)sum);
+}
+
+__device__ __forceinline__ void energy_bin_t(const Params &P, float E, float &t) {
+  t = (d_logf(E) - P.ln_emin) * P.inv_dlne;
+  if (t < 0.0f) t = 0.0f;
+}
+__device__ __forceinline__ void bin_split(const Params &P, float t, int &ie, float &fe) {
+  int i = (int)t;
+  if (i > P.ne - 2) i = P.ne - 2;
+  float f = t - (float)i;
+  if (f > 1.0f) f = 1.0f;
+  ie = i; fe = f;
+}
+
+// ------------------------------------------------------------------------------ photon in registers
+
+struct Ph {
+  float p[3], d[3];
   float E, w, path, seg, fe;
   int ie;
-  int iter;
-};
-
-struct History {
+  unsigned flags;
   Rng rng;
-  unsigned long long id;
-  int nbuf;
-  int inside_mask;     // bit k: currently inside phase-space box k
-  int stored;
-  int pend;            // 0 none, 1 pending photon stored in the volume frame, 2 world frame
-  float pend_p[3], pend_d[3];
-  float edep;          // everything deposited by this history
-  // coalescing buffer (local memory)
-  int bkey[kDepBuf];
-  float be[kDepBuf], bd[kDepBuf];
-  int bn[kDepBuf];
 };
 
-struct Counters {      // per-thread, flushed at the end of the kernel
-  unsigned int hist, tracks, steps, tent, phot, compt, rayl, conv, dep, flush, over, esc, absorbed;
-  double edep;
-};
+__device__ __forceinline__ void load_ph(const Params &P, const Smem &S, int s, Ph &g) {
+  g.p[0] = S.px[s]; g.p[1] = S.py[s]; g.p[2] = S.pz[s];
+  g.d[0] = S.dx[s]; g.d[1] = S.dy[s]; g.d[2] = S.dz[s];
+  g.E = S.E[s]; g.w = S.w[s]; g.path = S.path[s]; g.seg = S.seg[s];
+  bin_split(P, S.tbin[s], g.ie, g.fe);
+  g.flags = S.flags[s];
+  g.rng.k0 = (uint32_t)P.seed; g.rng.k1 = (uint32_t)(P.seed >> 32);
+  g.rng.h0 = S.hlo[s]; g.rng.h1 = S.hhi[s]; g.rng.blk = S.blk[s]; g.rng.pos = 4;
+}
+__device__ __forceinline__ void store_ph(Smem &S, int s, const Ph &g) {
+  S.px[s] = g.p[0]; S.py[s] = g.p[1]; S.pz[s] = g.p[2];
+  S.dx[s] = g.d[0]; S.dy[s] = g.d[1]; S.dz[s] = g.d[2];
+  S.E[s] = g.E; S.w[s] = g.w; S.path[s] = g.path; S.seg[s] = g.seg;
+  S.flags[s] = g.flags;
+  S.blk[s] = g.rng.blk;
+}
+__device__ __forceinline__ void set_energy(const Params &P, Smem &S, int s, Ph &g) {
+  float t;
+  energy_bin_t(P, g.E, t);
+  S.tbin[s] = t;
+  bin_split(P, t, g.ie, g.fe);
+}
 
 // ------------------------------------------------------------------------------ scoring
 
-// Add the coalesced (voxel, history) entries to the fp64 grids.  Lanes of the warp that flush
-// at the same time and hit the same voxel are combined first (one atomic per distinct
-// address); squares are summed per history, never of the combined value.
-__device__ __forceinline__ void flush_buffer(const Params &P, History &h, Counters &c) {
+// Add the coalesced (voxel, history) entries of a closed history to the fp64 grids.  Lanes that
+// flush together and hit the same voxel are combined first (one atomic per distinct address);
+// squares are summed per history, never of the combined value (GateDoseActor.cpp:359-381).
+__device__ __noinline__ void flush_buffer(const Params &P, const DepEntry *buf, int nbuf) {
   const unsigned lane = threadIdx.x & 31u;
-  for (int j = 0; j < h.nbuf; ++j) {
-    const int key = h.bkey[j];
+  unsigned flushed = 0;
+  for (int j = 0; j < nbuf; ++j) {
+    const DepEntry en = ld_dep(buf + j);
+    const int key = en.key;
     const int a = (int)((unsigned)key >> 28);
     const int v = key & 0x0fffffff;
-    double e = (double)h.be[j], d = (double)h.bd[j];
-    double e2 = e * e, d2 = d * d, n = (double)h.bn[j];
+    double e = (double)en.e, d = (double)en.d;
+    double e2 = e * e, d2 = d * d, n = (double)en.n;
     const unsigned act = __activemask();
     const unsigned grp = __match_any_sync(act, key);
     const int leader = __ffs(grp) - 1;
@@ -247,24 +338,29 @@ __device__ __forceinline__ void flush_buffer(const Params &P, History &h, Counte
       if (D.flags & GATE_B200_SCORE_DOSE_SQ) atomicAdd(D.grid[GATE_B200_GRID_DOSE_SQ] + v, d2);
       if (D.flags & GATE_B200_SCORE_COUNTS) atomicAdd(D.grid[GATE_B200_GRID_COUNTS] + v, n);
     }
-    c.flush++;
+    flushed++;
   }
-  h.nbuf = 0;
+  (void)flushed;
 }
 
+struct DepStat { unsigned dep, over, flush; double edep; };
+
 // deposit e (already weighted) at the photon position; in_vol selects whether dose actors see it
-__device__ __forceinline__ void deposit(const Params &P, History &h, Photon &g, Counters &c, float e,
-                                        int m, bool in_vol, int vix, int viy, int viz) {
-  h.edep += e;
-  c.edep += (double)e;
-  c.dep++;
+__device__ __noinline__ void deposit(const Params &P, Ph &g, DepEntry *buf, DepStat &ds, float e,
+                                     int m, bool in_vol) {
+  ds.edep += (double)e;
+  ds.dep++;
   if (!in_vol) return;
+  int nbuf = (int)((g.flags & F_NBUF) >> F_NBUF_SHIFT);
   for (int a = 0; a < P.ndose; ++a) {
     const DDose &D = P.dose[a];
     float pos[3] = {g.p[0], g.p[1], g.p[2]};
     if (D.hit_type != GATE_B200_HIT_POST) {
+      // pre/random/middle between the Geant4 pre and post step points; the Geant4 step starts at
+      // the voxel entry or at the previous interaction (GateDoseActor.cpp:144-178)
+      const int vi[3] = {(int)((g.p[0] + P.half[0]) * P.inv_sp[0]), (int)((g.p[1] + P.half[1]) * P.inv_sp[1]),
+                         (int)((g.p[2] + P.half[2]) * P.inv_sp[2])};
       float back = g.seg;
-      const int vi[3] = {vix, viy, viz};
 #pragma unroll
       for (int ax = 0; ax < 3; ++ax) {
         float dd = g.d[ax];
@@ -280,7 +376,7 @@ __device__ __forceinline__ void deposit(const Params &P, History &h, Photon &g, 
       }
       if (back < 0.0f) back = 0.0f;
       float fr = 1.0f;
-      if (D.hit_type == GATE_B200_HIT_RANDOM) fr = 1.0f - rng_uniform(h.rng);
+      if (D.hit_type == GATE_B200_HIT_RANDOM) fr = 1.0f - rng_uniform(g.rng);
       else if (D.hit_type == GATE_B200_HIT_MIDDLE) fr = 0.5f;
       float bk = back * fr;
 #pragma unroll
@@ -288,6 +384,7 @@ __device__ __forceinline__ void deposit(const Params &P, History &h, Photon &g, 
     }
     float ci[3];
     aff_apply(D.v2i, pos, ci);
+    // itk::ImageBase::TransformPhysicalPointToIndex: round half up, then region test
     float fx = floorf(ci[0] + 0.5f), fy = floorf(ci[1] + 0.5f), fz = floorf(ci[2] + 0.5f);
     if (fx < 0.0f || fy < 0.0f || fz < 0.0f || fx >= (float)D.size[0] || fy >= (float)D.size[1] ||
         fz >= (float)D.size[2])
@@ -296,19 +393,26 @@ __device__ __forceinline__ void deposit(const Params &P, History &h, Photon &g, 
     int key = (int)(((unsigned)a << 28) | (unsigned)v);
     float dd = e / __ldg(P.dens + m);
     int j;
-    for (j = 0; j < h.nbuf; ++j)
-      if (h.bkey[j] == key) break;
-    if (j == h.nbuf) {
-      if (h.nbuf == kDepBuf) {
-        flush_buffer(P, h, c);
-        c.over++;
+    for (j = 0; j < nbuf; ++j)
+      if (__ldcg(&buf[j].key) == key) break;
+    if (j == nbuf) {
+      if (nbuf == kDepBuf) {   // coalescing buffer full: write it out, start again
+        flush_buffer(P, buf, nbuf);
+        ds.flush += (unsigned)nbuf;
+        ds.over++;
+        nbuf = 0;
         j = 0;
       }
-      h.bkey[j] = key; h.be[j] = 0.0f; h.bd[j] = 0.0f; h.bn[j] = 0;
-      h.nbuf++;
+      DepEntry z; z.key = key; z.e = e; z.d = dd; z.n = 1;
+      st_dep(buf + j, z);
+      nbuf++;
+    } else {
+      DepEntry en = ld_dep(buf + j);
+      en.e += e; en.d += dd; en.n += 1;
+      st_dep(buf + j, en);
     }
-    h.be[j] += e; h.bd[j] += dd; h.bn[j] += 1;
   }
+  g.flags = (g.flags & ~F_NBUF) | ((unsigned)nbuf << F_NBUF_SHIFT);
 }
 
 // ------------------------------------------------------------------------------ physics
@@ -342,7 +446,7 @@ __device__ __forceinline__ int q2_segment(const Params &P, float q2) {
   while (j > 0 && __ldg(P.q2n + j) > q2) --j;
   return j;
 }
-__device__ __forceinline__ float interp_q2(const Params &P, const float *__restrict__ row, float q2) {
+__device__ __noinline__ float interp_q2(const Params &P, const float *__restrict__ row, float q2) {
   int j = q2_segment(P, q2);
   if (j < 0) return __ldg(row) * (q2 / __ldg(P.q2n));
   if (j >= P.nq - 1) return __ldg(row + P.nq - 1);
@@ -352,31 +456,28 @@ __device__ __forceinline__ float interp_q2(const Params &P, const float *__restr
   return r0 + f * (r1 - r0);
 }
 
-__device__ __forceinline__ void energy_bin(const Params &P, Photon &g) {
-  float t = (d_logf(g.E) - P.ln_emin) * P.inv_dlne;
-  if (t < 0.0f) t = 0.0f;
-  int i = (int)t;
-  if (i > P.ne - 2) i = P.ne - 2;
-  float f = t - (float)i;
-  if (f > 1.0f) f = 1.0f;
-  g.ie = i; g.fe = f;
-}
+struct IntStat { unsigned phot, compt, rayl, conv, tracks; };
 
-// one real interaction in material m; returns true if the photon survives
-__device__ __forceinline__ bool interact(const Params &P, History &h, Photon &g, Counters &c, int m,
-                                         bool in_vol, int vix, int viy, int viz) {
-  float u = rng_uniform(h.rng);
-  float pph = tab(P.cph, P.ne, m, g.ie, g.fe);
-  float pco = tab(P.cco, P.ne, m, g.ie, g.fe);
-  float pra = tab(P.cra, P.ne, m, g.ie, g.fe);
-  c.steps++;
+// one real interaction in material m; returns true if the photon survives.  pend[6] receives the
+// second annihilation photon (pair_mode 1).
+__device__ __forceinline__ bool interact(const Params &P, Ph &g, DepEntry *buf, DepStat &ds,
+                                         IntStat &is, float *pend, int m, bool in_vol,
+                                         bool &energy_changed) {
+  rng_begin(g.rng);
+  float u = rng_uniform(g.rng);
+  const float4 pa = __ldg(P.prob + (size_t)g.ie * P.nmat + m);
+  const float4 pb = __ldg(P.prob + (size_t)(g.ie + 1) * P.nmat + m);
+  float pph = pa.x + g.fe * (pb.x - pa.x);
+  float pco = pa.y + g.fe * (pb.y - pa.y);
+  float pra = pa.z + g.fe * (pb.z - pa.z);
+  energy_changed = false;
   if (u < pph) {
-    c.phot++;
-    deposit(P, h, g, c, g.E * g.w, m, in_vol, vix, viy, viz);
+    is.phot++;
+    deposit(P, g, buf, ds, g.E * g.w, m, in_vol);
     return false;
   }
   if (u < pco) {
-    c.compt++;
+    is.compt++;
     float E = g.E;
     float k = E / kMc2;
     float eps0 = 1.0f / (1.0f + 2.0f * k);
@@ -388,7 +489,7 @@ __device__ __forceinline__ bool interact(const Params &P, History &h, Photon &g,
     const float *sfrow = P.sf + (size_t)m * P.nq;
     float eps = 1.0f, onecost = 0.0f, sint2 = 0.0f;
     for (int it = 0; it < 1000; ++it) {
-      float u1 = rng_uniform(h.rng), u2 = rng_uniform(h.rng), u3 = rng_uniform(h.rng);
+      float u1 = rng_uniform(g.rng), u2 = rng_uniform(g.rng), u3 = rng_uniform(g.rng);
       float epssq;
       if (alpha1 > alpha2 * u1) {
         eps = d_expf(-alpha1 * u2);
@@ -402,28 +503,28 @@ __device__ __forceinline__ bool interact(const Params &P, History &h, Photon &g,
       float grej = 1.0f - eps * sint2 / (1.0f + epssq);
       if (grej < u3) continue;
       float sfv = interp_q2(P, sfrow, two_kq2 * onecost);
-      float u4 = rng_uniform(h.rng);
+      float u4 = rng_uniform(g.rng);
       if (u4 > sfv) continue;
       break;
     }
     float cost = 1.0f - onecost;
     float sint = sqrtf(sint2 > 0.0f ? sint2 : 0.0f);
     float sphi, cphi;
-    d_sincos2pi(rng_uniform(h.rng), sphi, cphi);
+    d_sincos2pi(rng_uniform(g.rng), sphi, cphi);
     float E1 = eps * E;
-    deposit(P, h, g, c, (E - E1) * g.w, m, in_vol, vix, viy, viz);
+    deposit(P, g, buf, ds, (E - E1) * g.w, m, in_vol);
     rotate_dir(g.d, cost, sint, sphi, cphi);
     g.E = E1;
     g.seg = 0.0f;
     if (E1 < P.e_cut) {
-      deposit(P, h, g, c, E1 * g.w, m, in_vol, vix, viy, viz);
+      deposit(P, g, buf, ds, E1 * g.w, m, in_vol);
       return false;
     }
-    energy_bin(P, g);
+    energy_changed = true;
     return true;
   }
   if (u < pra) {
-    c.rayl++;
+    is.rayl++;
     float kq = kKPerMeV * g.E;
     float kq2 = kq * kq;
     const float *A = P.ray + (size_t)m * P.nq;
@@ -434,7 +535,7 @@ __device__ __forceinline__ bool interact(const Params &P, History &h, Photon &g,
     const float a0 = __ldg(A);
     const float q20 = __ldg(P.q2n);
     for (int it = 0; it < 1000; ++it) {
-      float target = rng_uniform(h.rng) * amax;
+      float target = rng_uniform(g.rng) * amax;
       float q2;
       if (target < a0) {
         q2 = q20 * (target / a0);
@@ -456,35 +557,36 @@ __device__ __forceinline__ bool interact(const Params &P, History &h, Photon &g,
       if (q2 > q2max) q2 = q2max;
       cost = 1.0f - q2 / (2.0f * kq2);
       if (cost < -1.0f) cost = -1.0f;
-      float u2 = rng_uniform(h.rng);
+      float u2 = rng_uniform(g.rng);
       if (0.5f * (1.0f + cost * cost) >= u2) break;
     }
     float sint = sqrtf(1.0f - cost * cost);
     float sphi, cphi;
-    d_sincos2pi(rng_uniform(h.rng), sphi, cphi);
+    d_sincos2pi(rng_uniform(g.rng), sphi, cphi);
     rotate_dir(g.d, cost, sint, sphi, cphi);
     g.seg = 0.0f;
     return true;
   }
-  c.conv++;
+  is.conv++;
   if (P.pair_mode == 0) {
-    deposit(P, h, g, c, g.E * g.w, m, in_vol, vix, viy, viz);
+    // production cuts >> range with apply_cuts: e-, e+ (and its 2 mc2) stay on the spot
+    deposit(P, g, buf, ds, g.E * g.w, m, in_vol);
     return false;
   }
-  deposit(P, h, g, c, (g.E - 2.0f * kMc2) * g.w, m, in_vol, vix, viy, viz);
+  deposit(P, g, buf, ds, (g.E - 2.0f * kMc2) * g.w, m, in_vol);
   {
-    float cost = 2.0f * rng_uniform(h.rng) - 1.0f;
+    float cost = 2.0f * rng_uniform(g.rng) - 1.0f;
     float sint = sqrtf(1.0f - cost * cost);
     float sphi, cphi;
-    d_sincos2pi(rng_uniform(h.rng), sphi, cphi);
+    d_sincos2pi(rng_uniform(g.rng), sphi, cphi);
     g.d[0] = sint * cphi; g.d[1] = sint * sphi; g.d[2] = cost;
     g.E = kMc2;
     g.seg = 0.0f;
-    energy_bin(P, g);
+    energy_changed = true;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) { h.pend_p[a] = g.p[a]; h.pend_d[a] = -g.d[a]; }
-    h.pend = in_vol ? 1 : 2;
-    c.tracks += 2;
+    for (int a = 0; a < 3; ++a) { __stcg(pend + a, g.p[a]); __stcg(pend + 3 + a, -g.d[a]); }
+    g.flags = (g.flags & ~F_PEND) | ((in_vol ? 1u : 2u) << F_PEND_SHIFT);
+    is.tracks += 2;
   }
   return true;
 }
@@ -498,9 +600,21 @@ __device__ __forceinline__ float gauss(Rng &r) {
   return sqrtf(-2.0f * d_logf(u1)) * c;
 }
 
-__device__ __noinline__ void generate_primary(const Params &P, History &h, Photon &g) {
+// first i in [0, last] with p < cdf[i], `last` if there is none: the index the reference's linear
+// scan returns (GateSPSEneDistribution::IndexForProbability) for a non-decreasing cdf
+__device__ __forceinline__ int cdf_index(const float *__restrict__ cdf, int last, float p) {
+  int lo = 0, hi = last;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (p >= __ldg(cdf + mid)) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __noinline__ void generate_primary(const Params &P, Ph &g) {
   const DSource &S = P.src;
-  Rng &r = h.rng;
+  Rng &r = g.rng;
+  rng_begin(r);
   float l[3] = {0.0f, 0.0f, 0.0f};
   switch (S.pos_type) {
   case GATE_B200_POS_POINT: break;
@@ -554,6 +668,7 @@ __device__ __noinline__ void generate_primary(const Params &P, History &h, Photo
 
   switch (S.dir_type) {
   case GATE_B200_DIR_ISO: {
+    // G4SPSAngDistribution::GenerateIsotropicFlux: momentum = -(sin t cos p, sin t sin p, cos t)
     float cost = S.cos_tmin - rng_uniform(r) * (S.cos_tmin - S.cos_tmax);
     float s2 = 1.0f - cost * cost;
     float sint = sqrtf(s2 > 0.0f ? s2 : 0.0f);
@@ -581,22 +696,17 @@ __device__ __noinline__ void generate_primary(const Params &P, History &h, Photo
   case GATE_B200_ENE_GAUSS: E = S.mono + gauss(r) * S.sigma; break;
   case GATE_B200_ENE_RANGE: E = S.emin + rng_uniform(r) * (S.emax - S.emin); break;
   case GATE_B200_ENE_SPECTRUM_DISCRETE: {
-    float p = rng_uniform(r);
-    int i = 0;
-    while (i < S.n_spec - 1 && p >= __ldg(S.spec_cdf + i)) ++i;
+    int i = cdf_index(S.spec_cdf, S.n_spec - 1, rng_uniform(r));
     E = __ldg(S.spec_e + i);
   } break;
   case GATE_B200_ENE_SPECTRUM_HISTOGRAM: {
-    float p = rng_uniform(r);
-    int i = 0;
-    while (i < S.n_spec - 1 && p >= __ldg(S.spec_cdf + i)) ++i;
+    int i = cdf_index(S.spec_cdf, S.n_spec - 1, rng_uniform(r));
     float e0 = __ldg(S.spec_e + i), e1 = __ldg(S.spec_e + i + 1);
     E = e0 + rng_uniform(r) * (e1 - e0);
   } break;
   case GATE_B200_ENE_SPECTRUM_HISTOGRAM_LINEAR: {
-    float p0 = rng_uniform(r);
-    int i = 0;
-    while (i < S.n_spec - 2 && p0 >= __ldg(S.spec_cdf + i)) ++i;
+    // GateSPSEneDistribution.cpp:124-147
+    int i = cdf_index(S.spec_cdf, S.n_spec - 2, rng_uniform(r));
     float a = (__ldg(S.spec_e + i) + __ldg(S.spec_e + i + 1)) * 0.5f;
     float b = (__ldg(S.spec_e + i + 1) + __ldg(S.spec_e + i + 2)) * 0.5f;
     float dd = __ldg(S.spec_cdf + i + 1) - __ldg(S.spec_cdf + i);
@@ -614,6 +724,7 @@ __device__ __noinline__ void generate_primary(const Params &P, History &h, Photo
     }
   } break;
   case GATE_B200_ENE_CDF: {
+    // GateSPSEneDistribution.cpp:38-49
     float x = rng_uniform(r);
     int idx = lower_bound_f(S.spec_cdf, S.n_spec, x) - 1;
     if (idx < 0) idx = 0;
@@ -630,9 +741,9 @@ __device__ __noinline__ void generate_primary(const Params &P, History &h, Photo
 
 // ------------------------------------------------------------------------------ phase space
 
-__device__ __forceinline__ void phsp_store(const Params &P, History &h, const Photon &g, int k, int flag) {
+__device__ __forceinline__ void phsp_store(const Params &P, Ph &g, unsigned long long hist, int k, int flag) {
   const DPhsp &Q = P.phsp[k];
-  h.stored = 1;
+  g.flags |= F_STORED;
   unsigned long long idx = atomicAdd(Q.n_rows, 1ull);
   if (idx >= Q.capacity) {
     atomicAdd(Q.n_dropped, 1ull);
@@ -643,20 +754,20 @@ __device__ __forceinline__ void phsp_store(const Params &P, History &h, const Ph
   for (int a = 0; a < 3; ++a) { Q.pos[3 * idx + a] = g.p[a]; Q.dir[3 * idx + a] = g.d[a]; }
   Q.w[idx] = g.w;
   Q.t[idx] = g.path / kCmmPerNs;
-  Q.ev[idx] = (long long)h.id;
+  Q.ev[idx] = (long long)hist;
   Q.fl[idx] = flag;
 }
 
 // ------------------------------------------------------------------------------ regions
 
-__device__ __forceinline__ void to_volume(const Params &P, Photon &g) {
+__device__ __forceinline__ void to_volume(const Params &P, Ph &g) {
   float pl[3], dl[3];
   aff_apply(P.w2v, g.p, pl);
   rot_apply(P.w2v.m, g.d, dl);
 #pragma unroll
   for (int a = 0; a < 3; ++a) { g.p[a] = pl[a]; g.d[a] = dl[a]; }
 }
-__device__ __forceinline__ void to_world(const Params &P, Photon &g) {
+__device__ __forceinline__ void to_world(const Params &P, Ph &g) {
   float pw[3], dw[3];
   aff_apply_inv(P.w2v, g.p, pw);
   rot_apply_inv(P.w2v.m, g.d, dw);
@@ -664,253 +775,413 @@ __device__ __forceinline__ void to_world(const Params &P, Photon &g) {
   for (int a = 0; a < 3; ++a) { g.p[a] = pw[a]; g.d[a] = dw[a]; }
 }
 
-enum { ST_FETCH = 0, ST_WORLD = 1, ST_VOLUME = 2, ST_DEAD = 3, ST_INTERACT_W = 4, ST_INTERACT_V = 5, ST_DONE = 6 };
-
-// place a photon given in the world frame into its region; returns the state
-__device__ __forceinline__ int locate(const Params &P, History &h, Photon &g) {
-  int st = ST_WORLD;
+// place a photon given in the world frame into its region; returns the queue of its next phase
+__device__ __forceinline__ int locate(const Params &P, Ph &g) {
+  int st = Q_W;
   if (P.has_vol) {
     float pl[3];
     aff_apply(P.w2v, g.p, pl);
-    if (inside_box(pl, P.half)) { to_volume(P, g); st = ST_VOLUME; }
+    if (inside_box(pl, P.half)) { to_volume(P, g); st = Q_V; }
   }
-  h.inside_mask = 0;
+  g.flags &= ~F_INSIDE;
   for (int k = 0; k < P.nphsp; ++k) {
     float pb[3];
     aff_apply(P.phsp[k].w2b, g.p, pb);
-    if (st == ST_WORLD && inside_box(pb, P.phsp[k].half)) h.inside_mask |= (1 << k);
+    if (st == Q_W && inside_box(pb, P.phsp[k].half)) g.flags |= (1u << k);
   }
   return st;
 }
 
-// one step of a photon travelling in the world material (outside the image volume)
-__device__ __forceinline__ int world_step(const Params &P, History &h, Photon &g, Counters &c) {
+// ------------------------------------------------------------------------------ phases
+
+// Q_W: one flight segment of a photon travelling in the world material (outside the image volume)
+__device__ __noinline__ int phase_world(const Params &P, Smem &S, int slot) {
+  Ph g;
+  load_ph(P, S, slot, g);
+  int next;
+  unsigned n_esc = 0, n_steps = 0;
+  int it = S.iter[slot] + 1;
+  S.iter[slot] = it;
   float t_exit, t0;
-  if (!inside_box(g.p, P.wh) || !ray_box(g.p, g.d, P.wh, t0, t_exit)) {
-    c.esc++;
-    return ST_DEAD;
-  }
-  int ev = 0;
-  float mu = tab(P.mu, P.ne, P.world_mat, g.ie, g.fe);
-  float t_best = -d_logf(rng_uniform(h.rng)) / mu;
-  if (t_exit < t_best) { t_best = t_exit; ev = 1; }
-  int ax_in = -1;
-  if (P.has_vol) {
-    float pl[3], dl[3], ti, to;
-    int ai, ao;
-    aff_apply(P.w2v, g.p, pl);
-    rot_apply(P.w2v.m, g.d, dl);
-    if (ray_box_ax(pl, dl, P.half, ti, to, ai, ao) && ti < t_best) { t_best = ti; ev = 2; ax_in = ai; }
-  }
-  for (int k = 0; k < P.nphsp; ++k) {
-    float pb[3], db[3], ti, to;
-    aff_apply(P.phsp[k].w2b, g.p, pb);
-    rot_apply(P.phsp[k].w2b.m, g.d, db);
-    if (!ray_box(pb, db, P.phsp[k].half, ti, to)) {
-      h.inside_mask &= ~(1 << k);
-      continue;
-    }
-    if (h.inside_mask & (1 << k)) {
-      if (to < t_best) { t_best = to; ev = 4 + 2 * k; }
-    } else if (ti < t_best) { t_best = ti; ev = 3 + 2 * k; }
-  }
-  float step = (ev >= 3) ? t_best + kNudge : t_best;
-  if (ev == 1) { c.esc++; g.path += t_best; return ST_DEAD; }
-#pragma unroll
-  for (int a = 0; a < 3; ++a) g.p[a] = g.p[a] + g.d[a] * step;
-  g.path += step;
-  if (ev == 0) {
-    return ST_INTERACT_W;   // real interaction in the world material, done in the interaction phase
-  } else if (ev == 2) {
-    c.steps++;
-    to_volume(P, g);
-    snap_to_face(g.p, g.d, P.half, ax_in, false);
-    g.seg = 0.0f;
-    return ST_VOLUME;
-  }
-  int k = (ev - 3) >> 1;
-  c.steps++;
-  if (((ev - 3) & 1) == 0) {
-    h.inside_mask |= (1 << k);
-    if (P.phsp[k].steps & GATE_B200_PHSP_ENTERING) phsp_store(P, h, g, k, GATE_B200_PHSP_ENTERING);
+  if (it > kMaxIter) {
+    next = Q_E;
+  } else if (!inside_box(g.p, P.wh) || !ray_box(g.p, g.d, P.wh, t0, t_exit)) {
+    n_esc = 1;
+    next = Q_E;
   } else {
-    h.inside_mask &= ~(1 << k);
-    if (P.phsp[k].steps & GATE_B200_PHSP_EXITING) phsp_store(P, h, g, k, GATE_B200_PHSP_EXITING);
+    int ev = 0;   // 0 interact, 1 leave world, 2 enter volume, 3+2k enter plane k, 4+2k leave plane k
+    float mu = tab_mu(P, P.world_mat, g.ie, g.fe);
+    float t_best = -d_logf(rng_uniform(g.rng)) / mu;
+    if (t_exit < t_best) { t_best = t_exit; ev = 1; }
+    int ax_in = -1;
+    if (P.has_vol) {
+      float pl[3], dl[3], ti, to;
+      int ai, ao;
+      aff_apply(P.w2v, g.p, pl);
+      rot_apply(P.w2v.m, g.d, dl);
+      if (ray_box_ax(pl, dl, P.half, ti, to, ai, ao) && ti < t_best) { t_best = ti; ev = 2; ax_in = ai; }
+    }
+    for (int k = 0; k < P.nphsp; ++k) {
+      float pb[3], db[3], ti, to;
+      aff_apply(P.phsp[k].w2b, g.p, pb);
+      rot_apply(P.phsp[k].w2b.m, g.d, db);
+      if (!ray_box(pb, db, P.phsp[k].half, ti, to)) {
+        g.flags &= ~(1u << k);
+        continue;
+      }
+      if (g.flags & (1u << k)) {
+        if (to < t_best) { t_best = to; ev = 4 + 2 * k; }
+      } else if (ti < t_best) { t_best = ti; ev = 3 + 2 * k; }
+    }
+    float step = (ev >= 3) ? t_best + kNudge : t_best;
+    if (ev == 1) {
+      n_esc = 1;
+      g.path += t_best;
+      next = Q_E;
+    } else {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) g.p[a] = g.p[a] + g.d[a] * step;
+      g.path += step;
+      if (ev == 0) {
+        g.flags &= ~F_INVOL;
+        S.mat[slot] = P.world_mat;
+        next = Q_I;      // real interaction in the world material
+      } else if (ev == 2) {
+        n_steps = 1;
+        to_volume(P, g);
+        snap_to_face(g.p, g.d, P.half, ax_in, false);
+        g.seg = 0.0f;
+        next = Q_V;
+      } else {
+        const int k = (ev - 3) >> 1;
+        const unsigned long long hist = ((unsigned long long)g.rng.h1 << 32) | g.rng.h0;
+        n_steps = 1;
+        if (((ev - 3) & 1) == 0) {
+          g.flags |= (1u << k);
+          if (P.phsp[k].steps & GATE_B200_PHSP_ENTERING) phsp_store(P, g, hist, k, GATE_B200_PHSP_ENTERING);
+        } else {
+          g.flags &= ~(1u << k);
+          if (P.phsp[k].steps & GATE_B200_PHSP_EXITING) phsp_store(P, g, hist, k, GATE_B200_PHSP_EXITING);
+        }
+        next = Q_W;
+      }
+    }
   }
-  return ST_WORLD;
+  store_ph(S, slot, g);
+  stat_add(S, S_ESC, n_esc);
+  stat_add(S, S_STEPS, n_steps);
+  return next;
 }
 
-// one Woodcock candidate collision inside the image volume
+// Q_V: kWoodcockK tentative collisions of Woodcock delta tracking against the majorant of the
+// materials present in the volume.  The flight distances, positions, label gathers and attenuation
+// look-ups of all kWoodcockK iterations are issued up front (they only depend on the random numbers,
+// not on the outcome of the earlier iterations), so the dependent global loads of the iterations
+// overlap; the accept / leave decisions are then taken in order.  Arithmetic and order of the
+// floating-point operations are those of the sequential statement in the oracle.
 template <typename LabelT>
-__device__ __forceinline__ int volume_step(const Params &P, const float *__restrict__ s_maj, History &h,
-                                           Photon &g, Counters &c, int &mat) {
-  float m0 = s_maj[g.ie], m1 = s_maj[g.ie + 1];
-  float maj = m0 + g.fe * (m1 - m0);
-  float s = -d_logf(rng_uniform(h.rng)) / maj;
-  float q0 = g.p[0] + g.d[0] * s, q1 = g.p[1] + g.d[1] * s, q2 = g.p[2] + g.d[2] * s;
-  float fx = (q0 + P.half[0]) * P.inv_sp[0];
-  float fy = (q1 + P.half[1]) * P.inv_sp[1];
-  float fz = (q2 + P.half[2]) * P.inv_sp[2];
-  if (fx < 0.0f || fy < 0.0f || fz < 0.0f || fx >= (float)P.n[0] || fy >= (float)P.n[1] ||
-      fz >= (float)P.n[2]) {
+__device__ __forceinline__ int phase_volume(const Params &P, Smem &S, const float *__restrict__ s_maj, int slot,
+                                            unsigned &c_tent) {
+  float p0 = S.px[slot], p1 = S.py[slot], p2 = S.pz[slot];
+  const float d0 = S.dx[slot], d1 = S.dy[slot], d2 = S.dz[slot];
+  int ie; float fe;
+  bin_split(P, S.tbin[slot], ie, fe);
+  const unsigned blk = S.blk[slot];
+  S.blk[slot] = blk + 2u;
+  const int it = S.iter[slot] + 1;
+  S.iter[slot] = it;
+  if (it > kMaxIter) return Q_E;
+  const float m0 = s_maj[ie], m1 = s_maj[ie + 1];
+  const float maj = m0 + fe * (m1 - m0);
+  const float inv_maj = 1.0f / maj;
+  uint32_t r[2 * kWoodcockK];
+  {
+    const uint32_t k0 = (uint32_t)P.seed, k1 = (uint32_t)(P.seed >> 32);
+    const uint32_t h0 = S.hlo[slot], h1 = S.hhi[slot];
+    philox_block(k0, k1, h0, h1, blk, 0u, r[0], r[1], r[2], r[3]);
+    philox_block(k0, k1, h0, h1, blk + 1u, 0u, r[4], r[5], r[6], r[7]);
+  }
+  float s[kWoodcockK], q0[kWoodcockK], q1[kWoodcockK], q2[kWoodcockK], mu[kWoodcockK];
+  bool inb[kWoodcockK];
+  int lab[kWoodcockK];
+  const LabelT *__restrict__ labels = reinterpret_cast<const LabelT *>(P.labels);
+  const float2 *__restrict__ murow = P.mu2 + (size_t)ie * P.nmat;
+  {
+    float a0 = p0, a1 = p1, a2 = p2;
+#pragma unroll
+    for (int k = 0; k < kWoodcockK; ++k) {
+      s[k] = -d_logf(u32_to_uniform(r[2 * k])) * inv_maj;
+      a0 = a0 + d0 * s[k]; a1 = a1 + d1 * s[k]; a2 = a2 + d2 * s[k];
+      q0[k] = a0; q1[k] = a1; q2[k] = a2;
+      const float fx = (a0 + P.half[0]) * P.inv_sp[0];
+      const float fy = (a1 + P.half[1]) * P.inv_sp[1];
+      const float fz = (a2 + P.half[2]) * P.inv_sp[2];
+      inb[k] = !(fx < 0.0f || fy < 0.0f || fz < 0.0f || fx >= (float)P.n[0] || fy >= (float)P.n[1] ||
+                 fz >= (float)P.n[2]);
+      size_t flat = 0;
+      if (inb[k]) flat = (size_t)(int)fx + (size_t)P.n[0] * ((size_t)(int)fy + (size_t)P.n[1] * (size_t)(int)fz);
+      lab[k] = (int)__ldg(labels + flat);
+    }
+#pragma unroll
+    for (int k = 0; k < kWoodcockK; ++k) {
+      const float2 v = __ldg(murow + lab[k]);
+      mu[k] = v.x + fe * (v.y - v.x);
+    }
+  }
+  float path = S.path[slot], seg = S.seg[slot];
+  int next = Q_V;
+  unsigned tent = 0;
+  bool left = false;
+#pragma unroll
+  for (int k = 0; k < kWoodcockK; ++k) {
+    if (next != Q_V || left) continue;
+    if (!inb[k]) { left = true; continue; }
+    p0 = q0[k]; p1 = q1[k]; p2 = q2[k];
+    path += s[k];
+    seg += s[k];
+    tent++;
+    if (u32_to_uniform(r[2 * k + 1]) * maj <= mu[k]) {
+      S.mat[slot] = lab[k];
+      next = Q_I;       // accepted: the interaction itself runs in the interaction phase
+    }
+  }
+  c_tent += tent;
+  if (left) {
+    // left the volume: restart from the exit point in the world frame
+    float p[3] = {p0, p1, p2}, d[3] = {d0, d1, d2};
     float ti, to;
     int ai, ao;
-    if (!ray_box_ax(g.p, g.d, P.half, ti, to, ai, ao)) { to = 0.0f; ao = -1; }
+    if (!ray_box_ax(p, d, P.half, ti, to, ai, ao)) { to = 0.0f; ao = -1; }
 #pragma unroll
-    for (int a = 0; a < 3; ++a) g.p[a] = g.p[a] + g.d[a] * to;
-    snap_to_face(g.p, g.d, P.half, ao, true);
-    g.path += to;
-    c.steps++;
-    to_world(P, g);
-    return ST_WORLD;
+    for (int a = 0; a < 3; ++a) p[a] = p[a] + d[a] * to;
+    snap_to_face(p, d, P.half, ao, true);
+    path += to;
+    float pw[3], dw[3];
+    aff_apply_inv(P.w2v, p, pw);
+    rot_apply_inv(P.w2v.m, d, dw);
+    S.px[slot] = pw[0]; S.py[slot] = pw[1]; S.pz[slot] = pw[2];
+    S.dx[slot] = dw[0]; S.dy[slot] = dw[1]; S.dz[slot] = dw[2];
+    S.path[slot] = path;
+    next = Q_W;
+  } else {
+    S.px[slot] = p0; S.py[slot] = p1; S.pz[slot] = p2;
+    S.path[slot] = path; S.seg[slot] = seg;
+    if (next == Q_I) S.flags[slot] |= F_INVOL;
   }
-  g.p[0] = q0; g.p[1] = q1; g.p[2] = q2;
-  g.path += s;
-  g.seg += s;
-  c.tent++;
-  int ix = (int)fx, iy = (int)fy, iz = (int)fz;
-  size_t flat = (size_t)ix + (size_t)P.n[0] * ((size_t)iy + (size_t)P.n[1] * (size_t)iz);
-  int m = (int)__ldg(reinterpret_cast<const LabelT *>(P.labels) + flat);
-  float mu = tab(P.mu, P.ne, m, g.ie, g.fe);
-  if (rng_uniform(h.rng) * maj <= mu) {
-    mat = m;                // accepted: the interaction itself runs in the interaction phase
-    return ST_INTERACT_V;
+  stat_add(S, S_STEPS, left ? 1u : 0u);
+  return next;
+}
+
+// Q_I: one real interaction + kerma deposit into the coalescing buffer of the history
+__device__ __noinline__ int phase_interact(const Params &P, Smem &S, int slot, int gslot, double &c_edep) {
+  Ph g;
+  load_ph(P, S, slot, g);
+  const bool in_vol = (g.flags & F_INVOL) != 0;
+  const int m = S.mat[slot];
+  DepStat ds; ds.dep = 0; ds.over = 0; ds.flush = 0; ds.edep = 0.0;
+  IntStat is; is.phot = is.compt = is.rayl = is.conv = is.tracks = 0;
+  bool e_changed;
+  const bool alive = interact(P, g, P.depbuf + (size_t)gslot * kDepBuf, ds, is, P.pend + (size_t)gslot * 6, m, in_vol,
+                              e_changed);
+  if (alive && e_changed) set_energy(P, S, slot, g);
+  store_ph(S, slot, g);
+  c_edep += ds.edep;
+  stat_add(S, S_STEPS, 1u);
+  stat_add(S, S_PHOT, is.phot);
+  stat_add(S, S_COMPT, is.compt);
+  stat_add(S, S_RAYL, is.rayl);
+  stat_add(S, S_CONV, is.conv);
+  stat_add(S, S_TRACKS, is.tracks);
+  stat_add(S, S_DEP, ds.dep);
+  stat_add(S, S_OVER, ds.over);
+  stat_add(S, S_FLUSH, ds.flush);
+  return alive ? (in_vol ? Q_V : Q_W) : Q_E;
+}
+
+// Q_E: the photon of this slot is gone.  Either the history still owes its second annihilation
+// photon, or it is closed (coalesced deposits -> grids) and the slot claims the next history.
+__device__ __noinline__ int phase_end(const Params &P, Smem &S, int slot, int gslot, double &c_edep) {
+  Ph g;
+  load_ph(P, S, slot, g);
+  int next;
+  unsigned n_flush = 0, n_abs = 0, n_hist = 0;
+  if (g.flags & F_PEND) {
+    // second annihilation photon of a conversion (pair_mode 1): stored in the frame current at
+    // creation (1 = volume, 2 = world); go back to the world frame and find the region again
+    const float *pe = P.pend + (size_t)gslot * 6;
+    float pp[3] = {__ldcg(pe), __ldcg(pe + 1), __ldcg(pe + 2)}, pd[3] = {__ldcg(pe + 3), __ldcg(pe + 4), __ldcg(pe + 5)};
+    if (((g.flags & F_PEND) >> F_PEND_SHIFT) == 1u) {
+      aff_apply_inv(P.w2v, pp, g.p);
+      rot_apply_inv(P.w2v.m, pd, g.d);
+    } else {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { g.p[a] = pp[a]; g.d[a] = pd[a]; }
+    }
+    g.E = kMc2; g.seg = 0.0f;
+    g.flags &= ~F_PEND;
+    S.iter[slot] = 0;
+    next = locate(P, g);
+    set_energy(P, S, slot, g);
+    store_ph(S, slot, g);
+  } else {
+    if (g.flags & F_OPEN) {
+      const int nbuf = (int)((g.flags & F_NBUF) >> F_NBUF_SHIFT);
+      if (nbuf) flush_buffer(P, P.depbuf + (size_t)gslot * kDepBuf, nbuf);
+      n_flush = (unsigned)nbuf;
+      if (P.nphsp > 0 && !(g.flags & F_STORED)) n_abs = 1;
+    }
+    // claim the next history id (one atomic per group of lanes that arrive together)
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned act = __activemask();
+    const int leader = __ffs(act) - 1;
+    unsigned long long base = 0;
+    if ((int)lane == leader) base = atomicAdd(P.next, (unsigned long long)__popc(act));
+    base = __shfl_sync(act, base, leader);
+    const unsigned long long idx = base + (unsigned long long)__popc(act & ((1u << lane) - 1u));
+    if (idx >= P.count) {
+      S.flags[slot] = 0;
+      next = Q_RETIRED;
+    } else {
+      const unsigned long long id = P.first + idx;
+      rng_init(g.rng, P.seed, id, 0u);
+      S.hlo[slot] = g.rng.h0; S.hhi[slot] = g.rng.h1;
+      g.flags = F_OPEN;
+      generate_primary(P, g);
+      g.path = 0.0f; g.seg = 0.0f;
+      S.iter[slot] = 0;
+      n_hist = 1;
+      next = locate(P, g);
+      if (g.E < P.e_cut) {
+        c_edep += (double)(g.E * g.w);   // below the table: absorbed where it starts
+        next = Q_E;
+        S.tbin[slot] = 0.0f;
+      } else {
+        set_energy(P, S, slot, g);
+      }
+      store_ph(S, slot, g);
+    }
   }
-  return ST_VOLUME;
+  stat_add(S, S_FLUSH, n_flush);
+  stat_add(S, S_ABSORBED, n_abs);
+  stat_add(S, S_HIST, n_hist);
+  stat_add(S, S_TRACKS, n_hist);
+  return next;
 }
 
 // ------------------------------------------------------------------------------ kernel
 
-// The kernel is a warp-level phase scheduler.  Every lane carries one photon whose state says
-// which kind of work it needs next (refill, world flight, Woodcock step, interaction).  In
-// each round the warp votes and runs ONE phase, the one most lanes are waiting for, so that
-// the long and rare code paths (interaction sampling, primary generation) execute with many
-// lanes at once instead of being dragged through on every round by one or two lanes.
 template <typename LabelT>
-__global__ void __launch_bounds__(256) transport_kernel(const __grid_constant__ Params P) {
-  extern __shared__ float s_maj[];
-  for (int i = threadIdx.x; i < P.ne; i += blockDim.x) s_maj[i] = P.maj[i];
-  __syncthreads();
-
-  History h;
-  Photon g;
-  Counters c;
-  c.hist = c.tracks = c.steps = c.tent = c.phot = c.compt = c.rayl = c.conv = 0;
-  c.dep = c.flush = c.over = c.esc = c.absorbed = 0;
-  c.edep = 0.0;
-  h.nbuf = 0; h.pend = 0; h.stored = 0; h.inside_mask = 0; h.edep = 0.0f; h.id = 0;
-  int st = ST_FETCH;
-  int mat = 0;            // material of the pending interaction
-  bool open = false;      // a history is in flight (must be closed before the next fetch)
+__global__ void __launch_bounds__(kThreads, 1) transport_kernel(const __grid_constant__ Params P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+  float *s_maj = reinterpret_cast<float *>(smem_raw + sizeof(Smem));
   const unsigned lane = threadIdx.x & 31u;
   const unsigned FULL = 0xffffffffu;
 
+  for (int i = threadIdx.x; i < P.ne; i += kThreads) s_maj[i] = P.maj[i];
+  for (int i = threadIdx.x; i < kSlots; i += kThreads) {
+    S.flags[i] = 0; S.iter[i] = 0; S.blk[i] = 0; S.hlo[i] = 0; S.hhi[i] = 0; S.tbin[i] = 0.0f; S.mat[i] = 0;
+    S.cell[Q_V][i] = -1; S.cell[Q_I][i] = -1; S.cell[Q_W][i] = -1;
+    S.cell[Q_E][i] = i;                  // every slot starts by asking for a history
+  }
+  if (threadIdx.x < Q_COUNT) {
+    S.head[threadIdx.x] = 0;
+    S.tail[threadIdx.x] = threadIdx.x == Q_E ? kSlots : 0;
+    S.avail[threadIdx.x] = threadIdx.x == Q_E ? kSlots : 0;
+  }
+  if (threadIdx.x < S_COUNT) S.stats[threadIdx.x] = 0ull;
+  if (threadIdx.x == 0) { S.retired = 0; S.edep = 0.0; }
+  __syncthreads();
+
+  unsigned c_tent = 0;
+  double c_edep = 0.0;
+  int polls = 0;
+  const int slot_base = blockIdx.x * kSlots;
+
   for (;;) {
-    const unsigned bV = __ballot_sync(FULL, st == ST_VOLUME);
-    const unsigned bI = __ballot_sync(FULL, st == ST_INTERACT_V || st == ST_INTERACT_W);
-    const unsigned bW = __ballot_sync(FULL, st == ST_WORLD);
-    const unsigned bF = __ballot_sync(FULL, st == ST_FETCH);
-    if (!(bV | bI | bW | bF)) break;
-    const int nV = __popc(bV), nI = __popc(bI), nW = __popc(bW), nF = __popc(bF);
-
-    if (nV >= nI && nV >= nW && nV >= nF) {
-      // ---------------- Woodcock phase
-      if (st == ST_VOLUME) {
-        st = volume_step<LabelT>(P, s_maj, h, g, c, mat);
-        if (++g.iter >= kMaxIter) st = ST_DEAD;
-      }
-    } else if (nI >= nW && nI >= nF) {
-      // ---------------- interaction phase
-      if (st == ST_INTERACT_V || st == ST_INTERACT_W) {
-        const bool in_vol = st == ST_INTERACT_V;
-        int ix = 0, iy = 0, iz = 0;
-        if (in_vol) {   // same expressions as in volume_step: same voxel
-          ix = (int)((g.p[0] + P.half[0]) * P.inv_sp[0]);
-          iy = (int)((g.p[1] + P.half[1]) * P.inv_sp[1]);
-          iz = (int)((g.p[2] + P.half[2]) * P.inv_sp[2]);
+    // ---- claim up to 32 slots that wait for the same phase (lane 0 negotiates with the queues)
+    int q = -1, got = 0, base = 0;
+    if (lane == 0) {
+      for (;;) {
+        int best = ld_vol(&S.avail[0]), bq = 0;
+#pragma unroll
+        for (int t = 1; t < Q_COUNT; ++t) {
+          const int a = ld_vol(&S.avail[t]);
+          if (a > best) { best = a; bq = t; }
         }
-        const bool alive = interact(P, h, g, c, in_vol ? mat : P.world_mat, in_vol, ix, iy, iz);
-        st = alive ? (in_vol ? ST_VOLUME : ST_WORLD) : ST_DEAD;
-      }
-    } else if (nW >= nF) {
-      // ---------------- world phase
-      if (st == ST_WORLD) {
-        st = world_step(P, h, g, c);
-        if (++g.iter >= kMaxIter) st = ST_DEAD;
-      }
-    } else {
-      // ---------------- refill phase: close the finished history, claim the next id
-      if (st == ST_FETCH) {
-        if (open) {
-          flush_buffer(P, h, c);
-          if (P.nphsp > 0 && !h.stored) c.absorbed++;
-          open = false;
+        if (best >= 32 || (best > 0 && polls >= 2)) {
+          const int want = best < 32 ? best : 32;
+          const int old = atomicSub(&S.avail[bq], want);
+          const int g = old < want ? (old > 0 ? old : 0) : want;
+          if (g < want) atomicAdd(&S.avail[bq], want - g);
+          if (g > 0) { q = bq; got = g; base = atomicAdd(&S.head[bq], g); break; }
+          continue;
         }
-        const unsigned act = __activemask();
-        const int leader = __ffs(act) - 1;
-        unsigned long long base = 0;
-        if ((int)lane == leader) base = atomicAdd(P.next, (unsigned long long)__popc(act));
-        base = __shfl_sync(act, base, leader);
-        const unsigned long long idx = base + (unsigned long long)__popc(act & ((1u << lane) - 1u));
-        if (idx >= P.count) {
-          st = ST_DONE;
-        } else {
-          h.id = P.first + idx;
-          rng_init(h.rng, P.seed, h.id);
-          h.nbuf = 0; h.pend = 0; h.stored = 0; h.edep = 0.0f;
-          generate_primary(P, h, g);
-          g.path = 0.0f; g.seg = 0.0f; g.iter = 0;
-          c.hist++; c.tracks++;
-          open = true;
-          st = locate(P, h, g);
-          if (g.E < P.e_cut) {
-            c.edep += (double)(g.E * g.w);
-            st = ST_DEAD;
-          } else {
-            energy_bin(P, g);
-          }
-        }
+        if (best <= 0 && ld_vol(&S.retired) >= kSlots) { q = -2; break; }
+        ++polls;
+        __nanosleep(polls < 8 ? 32 : 256);
       }
     }
+    q = __shfl_sync(FULL, q, 0);
+    if (q == -2) break;
+    got = __shfl_sync(FULL, got, 0);
+    base = __shfl_sync(FULL, base, 0);
+    polls = 0;
+    int slot = -1;
+    if ((int)lane < got) {
+      int *c = &S.cell[q][(base + (int)lane) & kSlotMask];
+      while ((slot = ld_vol(c)) < 0) { }
+      st_vol(c, -1);
+    }
+    __threadfence_block();
 
-    if (st == ST_DEAD) {
-      if (h.pend) {
-        // second annihilation photon of a conversion (pair_mode 1)
-        float pw[3], dw[3];
-        if (h.pend == 1) {
-          aff_apply_inv(P.w2v, h.pend_p, pw);
-          rot_apply_inv(P.w2v.m, h.pend_d, dw);
-        } else {
+    // ---- run the phase for all claimed slots
+    int next = -3;     // -3: this lane holds no slot
+    if (slot >= 0) {
+      if (q == Q_V) next = phase_volume<LabelT>(P, S, s_maj, slot, c_tent);
+      else if (q == Q_I) next = phase_interact(P, S, slot, slot_base + slot, c_edep);
+      else if (q == Q_W) next = phase_world(P, S, slot);
+      else next = phase_end(P, S, slot, slot_base + slot, c_edep);
+    }
+    __syncwarp();
+    __threadfence_block();   // slot state visible before the slot is published again
+
+    // ---- push every slot to the queue of its next phase
 #pragma unroll
-          for (int a = 0; a < 3; ++a) { pw[a] = h.pend_p[a]; dw[a] = h.pend_d[a]; }
-        }
-#pragma unroll
-        for (int a = 0; a < 3; ++a) { g.p[a] = pw[a]; g.d[a] = dw[a]; }
-        g.E = kMc2; g.seg = 0.0f; g.iter = 0;
-        h.pend = 0;
-        st = locate(P, h, g);
-        energy_bin(P, g);
-      } else {
-        st = ST_FETCH;   // the history is closed (flushed) in the refill phase
+    for (int t = 0; t < Q_COUNT; ++t) {
+      const unsigned m = __ballot_sync(FULL, next == t);
+      if (!m) continue;
+      const int n = __popc(m), leader = __ffs(m) - 1;
+      int tk = 0;
+      if ((int)lane == leader) tk = atomicAdd(&S.tail[t], n);
+      tk = __shfl_sync(FULL, tk, leader);
+      if (next == t) {
+        int *c = &S.cell[t][(tk + __popc(m & ((1u << lane) - 1u))) & kSlotMask];
+        while (ld_vol(c) >= 0) { }   // the previous occupant is claimed, its reader clears it at once
+        st_vol(c, slot);
       }
+      __syncwarp();
+      if ((int)lane == leader) atomicAdd(&S.avail[t], n);
+    }
+    {
+      const unsigned m = __ballot_sync(FULL, next == Q_RETIRED);
+      if (m && lane == 0) atomicAdd(&S.retired, __popc(m));
     }
   }
 
-  // per-thread counters -> global statistics (warp reduce, one atomic per warp and counter)
-  unsigned int vals[S_COUNT] = {c.hist, c.tracks, c.steps, c.tent, c.phot, c.compt, c.rayl, c.conv,
-                                c.dep, c.flush, c.over, c.esc, c.absorbed};
-  __syncwarp();
+  // ---- statistics: per-thread -> warp -> CTA -> global
 #pragma unroll
-  for (int i = 0; i < S_COUNT; ++i) {
-    unsigned long long v = vals[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0 && v) atomicAdd(P.stats + i, v);
+  for (int o = 16; o > 0; o >>= 1) {
+    c_tent += __shfl_xor_sync(FULL, c_tent, o);
+    c_edep += __shfl_xor_sync(FULL, c_edep, o);
   }
-  double e = c.edep;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-  if (lane == 0 && e != 0.0) atomicAdd(P.edep_total, e);
+  if (lane == 0) {
+    if (c_tent) atomicAdd(&S.stats[S_TENT], (unsigned long long)c_tent);
+    if (c_edep != 0.0) atomicAdd(&S.edep, c_edep);
+  }
+  __syncthreads();
+  if (threadIdx.x < S_COUNT && S.stats[threadIdx.x]) atomicAdd(P.stats + threadIdx.x, S.stats[threadIdx.x]);
+  if (threadIdx.x == 0 && S.edep != 0.0) atomicAdd(P.edep_total, S.edep);
 }
 
 }  // namespace gb2

@@ -136,6 +136,12 @@ static void rng_init(rng_t *r, uint64_t seed, uint64_t history) {
   r->pos = 4;
 }
 
+/* Every phase call (primary generation, one world step, one Woodcock call, one interaction)
+ * starts on a fresh Philox block: whatever is left of the previous block is discarded.  This is
+ * part of the algorithm definition (DESIGN.md "random-number protocol"): it lets the device run
+ * the phases of one history on different warps without carrying generator output around. */
+static void rng_begin(rng_t *r) { r->pos = 4; }
+
 /* uniform in (0,1): 24 random bits, centred in their bin */
 static float rng_uniform(rng_t *r) {
   if (r->pos == 4) {
@@ -152,6 +158,7 @@ static float rng_uniform(rng_t *r) {
 #define ORACLE_MAX_PHSP 4
 #define ORACLE_MAX_DOSE 4
 #define DEP_BUF 32
+#define WOODCOCK_K 4
 #define NUDGE 1.0e-3f
 #define BIG 3.0e38f
 #define MC2 0.51099891f
@@ -455,6 +462,7 @@ static void update_energy(hist_t *h) { energy_bin(h->g, h->E, &h->ie, &h->fe); }
 static int interact(hist_t *h, int m, int vix, int viy, int viz, float pend_p[3], float pend_d[3],
                     int *pend) {
   oracle_engine *g = h->g;
+  rng_begin(&h->rng);
   float u = rng_uniform(&h->rng);
   float pph = tab(g->cph, g->ne, m, h->ie, h->fe);
   float pco = tab(g->cco, g->ne, m, h->ie, h->fe);
@@ -780,6 +788,7 @@ static void run_photon(hist_t *h, float pend_p[3], float pend_d[3], int *pend) {
 #endif
     if (!h->in_phantom) {
       float t_exit, t0;
+      rng_begin(&h->rng);
       if (!inside_box(h->p, g->wh) || !ray_box(h->p, h->d, g->wh, &t0, &t_exit)) {
         h->st.escaped++;
         return;
@@ -832,38 +841,48 @@ static void run_photon(hist_t *h, float pend_p[3], float pend_d[3], int *pend) {
         }
       }
     } else {
-      /* Woodcock delta tracking against the majorant of the materials in the volume */
+      /* Woodcock delta tracking against the majorant of the materials in the volume.
+       * One call = up to WOODCOCK_K tentative collisions fed by 2 Philox blocks: u[2k] gives
+       * the flight distance of iteration k, u[2k+1] its acceptance test. */
       float maj = g->maj[h->ie] + h->fe * (g->maj[h->ie + 1] - g->maj[h->ie]);
-      float s = -o_logf(rng_uniform(&h->rng)) / maj;
-      float q[3] = {h->p[0] + h->d[0] * s, h->p[1] + h->d[1] * s, h->p[2] + h->d[2] * s};
-      float fx = (q[0] + g->half[0]) * g->inv_sp[0];
-      float fy = (q[1] + g->half[1]) * g->inv_sp[1];
-      float fz = (q[2] + g->half[2]) * g->inv_sp[2];
-      if (fx < 0.0f || fy < 0.0f || fz < 0.0f || fx >= (float)g->n[0] || fy >= (float)g->n[1] ||
-          fz >= (float)g->n[2]) {
-        /* left the volume: restart from the exit point in the world frame */
-        float ti, to;
-        int ai, ao;
-        if (!ray_box_ax(h->p, h->d, g->half, &ti, &to, &ai, &ao)) { to = 0.0f; ao = -1; }
-        for (int a = 0; a < 3; ++a) h->p[a] = h->p[a] + h->d[a] * to;
-        snap_to_face(h->p, h->d, g->half, ao, 1);
-        h->path += to;
-        h->st.steps++;
-        to_world(h);
-        h->in_phantom = 0;
-        continue;
+      float inv_maj = 1.0f / maj;
+      float u[2 * WOODCOCK_K];
+      rng_begin(&h->rng);
+      for (int k = 0; k < 2 * WOODCOCK_K; ++k) u[k] = rng_uniform(&h->rng);
+      for (int k = 0; k < WOODCOCK_K; ++k) {
+        float s = -o_logf(u[2 * k]) * inv_maj;
+        float q[3] = {h->p[0] + h->d[0] * s, h->p[1] + h->d[1] * s, h->p[2] + h->d[2] * s};
+        float fx = (q[0] + g->half[0]) * g->inv_sp[0];
+        float fy = (q[1] + g->half[1]) * g->inv_sp[1];
+        float fz = (q[2] + g->half[2]) * g->inv_sp[2];
+        if (fx < 0.0f || fy < 0.0f || fz < 0.0f || fx >= (float)g->n[0] || fy >= (float)g->n[1] ||
+            fz >= (float)g->n[2]) {
+          /* left the volume: restart from the exit point in the world frame */
+          float ti, to;
+          int ai, ao;
+          if (!ray_box_ax(h->p, h->d, g->half, &ti, &to, &ai, &ao)) { to = 0.0f; ao = -1; }
+          for (int a = 0; a < 3; ++a) h->p[a] = h->p[a] + h->d[a] * to;
+          snap_to_face(h->p, h->d, g->half, ao, 1);
+          h->path += to;
+          h->st.steps++;
+          to_world(h);
+          h->in_phantom = 0;
+          break;
+        }
+        h->p[0] = q[0]; h->p[1] = q[1]; h->p[2] = q[2];
+        h->path += s;
+        h->seg += s;
+        h->st.tentative_collisions++;
+        int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+        size_t flat = (size_t)ix + (size_t)g->n[0] * ((size_t)iy + (size_t)g->n[1] * (size_t)iz);
+        int m = g->label_bytes == 1 ? (int)((const uint8_t *)g->labels)[flat]
+                                    : (int)((const uint16_t *)g->labels)[flat];
+        float mu = tab(g->mu, g->ne, m, h->ie, h->fe);
+        if (u[2 * k + 1] * maj <= mu) {
+          alive = interact(h, m, ix, iy, iz, pend_p, pend_d, pend);
+          break;
+        }
       }
-      h->p[0] = q[0]; h->p[1] = q[1]; h->p[2] = q[2];
-      h->path += s;
-      h->seg += s;
-      h->st.tentative_collisions++;
-      int ix = (int)fx, iy = (int)fy, iz = (int)fz;
-      size_t flat = (size_t)ix + (size_t)g->n[0] * ((size_t)iy + (size_t)g->n[1] * (size_t)iz);
-      int m = g->label_bytes == 1 ? (int)((const uint8_t *)g->labels)[flat]
-                                  : (int)((const uint16_t *)g->labels)[flat];
-      float mu = tab(g->mu, g->ne, m, h->ie, h->fe);
-      if (rng_uniform(&h->rng) * maj <= mu)
-        alive = interact(h, m, ix, iy, iz, pend_p, pend_d, pend);
     }
   }
 }

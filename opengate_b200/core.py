@@ -61,12 +61,13 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    lib_path = os.environ.get("GATE_B200_LIB", LIB_PATH)   # development: A/B builds of the same ABI
+    if not os.path.exists(lib_path):
         raise GateB200Error(
-            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            f"{lib_path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
             "The GPU engine has no CPU fallback."
         )
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(lib_path)
     vp, i32, u64 = C.c_void_p, C.c_int32, C.c_uint64
     L.gate_b200_abi_version.restype = C.c_int
     L.gate_b200_create.argtypes = [C.c_int, u64, C.POINTER(vp)]

@@ -465,12 +465,7 @@ int gate_b200_begin_run(gate_b200_engine *h, int32_t /*run_id*/) {
   return GATE_B200_OK;
 }
 
-int gate_b200_run_source(gate_b200_engine *h, int32_t source_id, uint64_t first_history, uint64_t n_histories) {
-  if (!h) return GATE_B200_EINVAL;
-  if (!h->have_tables) return fail(h, GATE_B200_ESTATE, "run_source before set_tables");
-  if (source_id < 0 || source_id >= (int)h->src.size()) return fail(h, GATE_B200_EINVAL, "unknown source %d", source_id);
-  if (n_histories == 0) return GATE_B200_OK;
-  CU(cudaSetDevice(h->device));
+static int launch_histories(gate_b200_engine *h, int32_t source_id, uint64_t first_history, uint64_t n_histories) {
   Params P = h->P;
   const int label_bytes = h->label_bytes;
   P.src = h->src[source_id].dev;
@@ -492,6 +487,22 @@ int gate_b200_run_source(gate_b200_engine *h, int32_t source_id, uint64_t first_
   CU(cudaGetLastError());
   CU(cudaEventRecord(e1, h->stream));
   h->pending_events.emplace_back(e0, e1);
+  return GATE_B200_OK;
+}
+
+int gate_b200_run_source(gate_b200_engine *h, int32_t source_id, uint64_t first_history, uint64_t n_histories) {
+  if (!h) return GATE_B200_EINVAL;
+  if (!h->have_tables) return fail(h, GATE_B200_ESTATE, "run_source before set_tables");
+  if (source_id < 0 || source_id >= (int)h->src.size()) return fail(h, GATE_B200_EINVAL, "unknown source %d", source_id);
+  if (n_histories == 0) return GATE_B200_OK;
+  CU(cudaSetDevice(h->device));
+  // a slot stores the history index inside its launch in 32 bits: longer requests become several launches
+  const uint64_t kMaxPerLaunch = 1ull << 31;
+  for (uint64_t done = 0; done < n_histories;) {
+    const uint64_t k = std::min<uint64_t>(kMaxPerLaunch, n_histories - done);
+    if (int rc = launch_histories(h, source_id, first_history + done, k)) return rc;
+    done += k;
+  }
   return GATE_B200_OK;
 }
 

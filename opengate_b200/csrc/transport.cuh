@@ -24,17 +24,16 @@
 #include "device_math.cuh"
 
 #ifndef GB2_THREADS
-#define GB2_THREADS 1024
+#define GB2_THREADS 512
 #endif
 #ifndef GB2_SLOTS
-#define GB2_SLOTS 2048
+#define GB2_SLOTS 3072
 #endif
 
 namespace gb2 {
 
 constexpr int kThreads = GB2_THREADS;
-constexpr int kSlots = GB2_SLOTS;          // photon slots per CTA (power of two)
-constexpr int kSlotMask = kSlots - 1;
+constexpr int kSlots = GB2_SLOTS;          // photon slots per CTA (< 65535: queue cells are 16 bit)
 constexpr int kWoodcockK = 4;              // tentative collisions per Woodcock call (2 Philox blocks)
 constexpr int kMaxDose = 4;
 constexpr int kMaxPhsp = 4;
@@ -44,7 +43,7 @@ constexpr float kBig = 3.0e38f;
 constexpr float kMc2 = 0.51099891f;
 constexpr float kKPerMeV = 268.17264f;     // photon wave number (1/bohr) per MeV
 constexpr float kCmmPerNs = 299.792458f;
-constexpr int kMaxIter = 1000000;
+constexpr unsigned kMaxBlocks = 4000000u; // Philox blocks one history may consume (runaway guard)
 
 enum { Q_V = 0, Q_I = 1, Q_W = 2, Q_E = 3, Q_COUNT = 4, Q_RETIRED = -1 };
 
@@ -123,17 +122,18 @@ struct Params {
 struct Smem {
   float px[kSlots], py[kSlots], pz[kSlots];   // world frame outside the volume, volume frame inside
   float dx[kSlots], dy[kSlots], dz[kSlots];
-  float E[kSlots], tbin[kSlots], w[kSlots], path[kSlots], seg[kSlots];
-  unsigned hlo[kSlots], hhi[kSlots], blk[kSlots];
-  int mat[kSlots];
-  unsigned flags[kSlots];
-  int iter[kSlots];
-  int cell[Q_COUNT][kSlots];
+  float E[kSlots], tbin[kSlots], path[kSlots], seg[kSlots];
+  unsigned hidx[kSlots];                      // history index inside this launch (id = first + hidx)
+  unsigned blk[kSlots];                       // next Philox block of the history
+  unsigned fm[kSlots];                        // flags (low 16 bits) | material of the pending interaction << 16
+  unsigned short cell[Q_COUNT][kSlots];       // ring queues of slot numbers, kEmpty = free cell
   int head[Q_COUNT], tail[Q_COUNT], avail[Q_COUNT];
+  int cur;                                    // phase the CTA is currently draining
   int retired;
   unsigned long long stats[S_COUNT];
   double edep;
 };
+constexpr unsigned kEmpty = 0xffffu;
 
 // bits of Smem::flags
 constexpr unsigned F_INSIDE = 0xfu;        // bit k: currently inside phase-space box k
@@ -142,8 +142,9 @@ constexpr unsigned F_PEND_SHIFT = 5;       // 0 none, 1 pending photon in the vo
 constexpr unsigned F_PEND = 3u << F_PEND_SHIFT;
 constexpr unsigned F_INVOL = 1u << 7;      // the pending interaction is inside the image volume
 constexpr unsigned F_OPEN = 1u << 8;       // a history is in flight in this slot
-constexpr unsigned F_NBUF_SHIFT = 16;      // entries in the coalescing buffer
+constexpr unsigned F_NBUF_SHIFT = 9;       // entries in the coalescing buffer (0..kDepBuf)
 constexpr unsigned F_NBUF = 0x3fu << F_NBUF_SHIFT;
+constexpr unsigned F_MASK = 0xffffu;
 
 // ------------------------------------------------------------------------------ helpers
 
@@ -230,6 +231,8 @@ __device__ __forceinline__ int lower_bound_f(const float *__restrict__ a, int n,
 
 __device__ __forceinline__ int ld_vol(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
 __device__ __forceinline__ void st_vol(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
+__device__ __forceinline__ unsigned ld_cell(const unsigned short *p) { return *reinterpret_cast<const volatile unsigned short *>(p); }
+__device__ __forceinline__ void st_cell(unsigned short *p, unsigned v) { *reinterpret_cast<volatile unsigned short *>(p) = (unsigned short)v; }
 
 // The coalescing buffers and the pending-photon scratch live in global memory and are handed from
 // warp to warp with the slot: access them at L2 (ld.cg / st.cg), never through the read-only path.
@@ -270,8 +273,8 @@ __device__ __forceinline__ void bin_split(const Params &P, float t, int &ie, flo
 
 struct Ph {
   float p[3], d[3];
-  float E, w, path, seg, fe;
-  int ie;
+  float E, path, seg, fe;
+  int ie, mat;
   unsigned flags;
   Rng rng;
 };
@@ -279,17 +282,20 @@ struct Ph {
 __device__ __forceinline__ void load_ph(const Params &P, const Smem &S, int s, Ph &g) {
   g.p[0] = S.px[s]; g.p[1] = S.py[s]; g.p[2] = S.pz[s];
   g.d[0] = S.dx[s]; g.d[1] = S.dy[s]; g.d[2] = S.dz[s];
-  g.E = S.E[s]; g.w = S.w[s]; g.path = S.path[s]; g.seg = S.seg[s];
+  g.E = S.E[s]; g.path = S.path[s]; g.seg = S.seg[s];
   bin_split(P, S.tbin[s], g.ie, g.fe);
-  g.flags = S.flags[s];
+  const unsigned fm = S.fm[s];
+  g.flags = fm & F_MASK;
+  g.mat = (int)(fm >> 16);
+  const unsigned long long id = P.first + S.hidx[s];
   g.rng.k0 = (uint32_t)P.seed; g.rng.k1 = (uint32_t)(P.seed >> 32);
-  g.rng.h0 = S.hlo[s]; g.rng.h1 = S.hhi[s]; g.rng.blk = S.blk[s]; g.rng.pos = 4;
+  g.rng.h0 = (uint32_t)id; g.rng.h1 = (uint32_t)(id >> 32); g.rng.blk = S.blk[s]; g.rng.pos = 4;
 }
 __device__ __forceinline__ void store_ph(Smem &S, int s, const Ph &g) {
   S.px[s] = g.p[0]; S.py[s] = g.p[1]; S.pz[s] = g.p[2];
   S.dx[s] = g.d[0]; S.dy[s] = g.d[1]; S.dz[s] = g.d[2];
-  S.E[s] = g.E; S.w[s] = g.w; S.path[s] = g.path; S.seg[s] = g.seg;
-  S.flags[s] = g.flags;
+  S.E[s] = g.E; S.path[s] = g.path; S.seg[s] = g.seg;
+  S.fm[s] = (g.flags & F_MASK) | ((unsigned)g.mat << 16);
   S.blk[s] = g.rng.blk;
 }
 __device__ __forceinline__ void set_energy(const Params &P, Smem &S, int s, Ph &g) {
@@ -473,7 +479,7 @@ __device__ __forceinline__ bool interact(const Params &P, Ph &g, DepEntry *buf, 
   energy_changed = false;
   if (u < pph) {
     is.phot++;
-    deposit(P, g, buf, ds, g.E * g.w, m, in_vol);
+    deposit(P, g, buf, ds, g.E * P.src.weight, m, in_vol);
     return false;
   }
   if (u < pco) {
@@ -512,12 +518,12 @@ __device__ __forceinline__ bool interact(const Params &P, Ph &g, DepEntry *buf, 
     float sphi, cphi;
     d_sincos2pi(rng_uniform(g.rng), sphi, cphi);
     float E1 = eps * E;
-    deposit(P, g, buf, ds, (E - E1) * g.w, m, in_vol);
+    deposit(P, g, buf, ds, (E - E1) * P.src.weight, m, in_vol);
     rotate_dir(g.d, cost, sint, sphi, cphi);
     g.E = E1;
     g.seg = 0.0f;
     if (E1 < P.e_cut) {
-      deposit(P, g, buf, ds, E1 * g.w, m, in_vol);
+      deposit(P, g, buf, ds, E1 * P.src.weight, m, in_vol);
       return false;
     }
     energy_changed = true;
@@ -570,10 +576,10 @@ __device__ __forceinline__ bool interact(const Params &P, Ph &g, DepEntry *buf, 
   is.conv++;
   if (P.pair_mode == 0) {
     // production cuts >> range with apply_cuts: e-, e+ (and its 2 mc2) stay on the spot
-    deposit(P, g, buf, ds, g.E * g.w, m, in_vol);
+    deposit(P, g, buf, ds, g.E * P.src.weight, m, in_vol);
     return false;
   }
-  deposit(P, g, buf, ds, (g.E - 2.0f * kMc2) * g.w, m, in_vol);
+  deposit(P, g, buf, ds, (g.E - 2.0f * kMc2) * P.src.weight, m, in_vol);
   {
     float cost = 2.0f * rng_uniform(g.rng) - 1.0f;
     float sint = sqrtf(1.0f - cost * cost);
@@ -736,7 +742,6 @@ __device__ __noinline__ void generate_primary(const Params &P, Ph &g) {
   } break;
   }
   g.E = E;
-  g.w = S.weight;
 }
 
 // ------------------------------------------------------------------------------ phase space
@@ -752,7 +757,7 @@ __device__ __forceinline__ void phsp_store(const Params &P, Ph &g, unsigned long
   Q.ke[idx] = g.E;
 #pragma unroll
   for (int a = 0; a < 3; ++a) { Q.pos[3 * idx + a] = g.p[a]; Q.dir[3 * idx + a] = g.d[a]; }
-  Q.w[idx] = g.w;
+  Q.w[idx] = P.src.weight;
   Q.t[idx] = g.path / kCmmPerNs;
   Q.ev[idx] = (long long)hist;
   Q.fl[idx] = flag;
@@ -800,10 +805,8 @@ __device__ __noinline__ int phase_world(const Params &P, Smem &S, int slot) {
   load_ph(P, S, slot, g);
   int next;
   unsigned n_esc = 0, n_steps = 0;
-  int it = S.iter[slot] + 1;
-  S.iter[slot] = it;
   float t_exit, t0;
-  if (it > kMaxIter) {
+  if (g.rng.blk > kMaxBlocks) {
     next = Q_E;
   } else if (!inside_box(g.p, P.wh) || !ray_box(g.p, g.d, P.wh, t0, t_exit)) {
     n_esc = 1;
@@ -844,7 +847,7 @@ __device__ __noinline__ int phase_world(const Params &P, Smem &S, int slot) {
       g.path += step;
       if (ev == 0) {
         g.flags &= ~F_INVOL;
-        S.mat[slot] = P.world_mat;
+        g.mat = P.world_mat;
         next = Q_I;      // real interaction in the world material
       } else if (ev == 2) {
         n_steps = 1;
@@ -882,24 +885,20 @@ __device__ __noinline__ int phase_world(const Params &P, Smem &S, int slot) {
 template <typename LabelT>
 __device__ __forceinline__ int phase_volume(const Params &P, Smem &S, const float *__restrict__ s_maj, int slot,
                                             unsigned &c_tent) {
+  const unsigned blk = S.blk[slot];
+  if (blk > kMaxBlocks) return Q_E;
+  S.blk[slot] = blk + 2u;
   float p0 = S.px[slot], p1 = S.py[slot], p2 = S.pz[slot];
   const float d0 = S.dx[slot], d1 = S.dy[slot], d2 = S.dz[slot];
   int ie; float fe;
   bin_split(P, S.tbin[slot], ie, fe);
-  const unsigned blk = S.blk[slot];
-  S.blk[slot] = blk + 2u;
-  const int it = S.iter[slot] + 1;
-  S.iter[slot] = it;
-  if (it > kMaxIter) return Q_E;
   const float m0 = s_maj[ie], m1 = s_maj[ie + 1];
   const float maj = m0 + fe * (m1 - m0);
   const float inv_maj = 1.0f / maj;
   uint32_t r[2 * kWoodcockK];
   {
-    const uint32_t k0 = (uint32_t)P.seed, k1 = (uint32_t)(P.seed >> 32);
-    const uint32_t h0 = S.hlo[slot], h1 = S.hhi[slot];
-    philox_block(k0, k1, h0, h1, blk, 0u, r[0], r[1], r[2], r[3]);
-    philox_block(k0, k1, h0, h1, blk + 1u, 0u, r[4], r[5], r[6], r[7]);
+    const unsigned long long id = P.first + S.hidx[slot];
+    philox_block2((uint32_t)P.seed, (uint32_t)(P.seed >> 32), (uint32_t)id, (uint32_t)(id >> 32), blk, r);
   }
   float s[kWoodcockK], q0[kWoodcockK], q1[kWoodcockK], q2[kWoodcockK], mu[kWoodcockK];
   bool inb[kWoodcockK];
@@ -930,6 +929,7 @@ __device__ __forceinline__ int phase_volume(const Params &P, Smem &S, const floa
   }
   float path = S.path[slot], seg = S.seg[slot];
   int next = Q_V;
+  int mat = 0;
   unsigned tent = 0;
   bool left = false;
 #pragma unroll
@@ -941,7 +941,7 @@ __device__ __forceinline__ int phase_volume(const Params &P, Smem &S, const floa
     seg += s[k];
     tent++;
     if (u32_to_uniform(r[2 * k + 1]) * maj <= mu[k]) {
-      S.mat[slot] = lab[k];
+      mat = lab[k];
       next = Q_I;       // accepted: the interaction itself runs in the interaction phase
     }
   }
@@ -966,7 +966,7 @@ __device__ __forceinline__ int phase_volume(const Params &P, Smem &S, const floa
   } else {
     S.px[slot] = p0; S.py[slot] = p1; S.pz[slot] = p2;
     S.path[slot] = path; S.seg[slot] = seg;
-    if (next == Q_I) S.flags[slot] |= F_INVOL;
+    if (next == Q_I) S.fm[slot] = (S.fm[slot] & F_MASK) | F_INVOL | ((unsigned)mat << 16);
   }
   stat_add(S, S_STEPS, left ? 1u : 0u);
   return next;
@@ -977,11 +977,10 @@ __device__ __noinline__ int phase_interact(const Params &P, Smem &S, int slot, i
   Ph g;
   load_ph(P, S, slot, g);
   const bool in_vol = (g.flags & F_INVOL) != 0;
-  const int m = S.mat[slot];
   DepStat ds; ds.dep = 0; ds.over = 0; ds.flush = 0; ds.edep = 0.0;
   IntStat is; is.phot = is.compt = is.rayl = is.conv = is.tracks = 0;
   bool e_changed;
-  const bool alive = interact(P, g, P.depbuf + (size_t)gslot * kDepBuf, ds, is, P.pend + (size_t)gslot * 6, m, in_vol,
+  const bool alive = interact(P, g, P.depbuf + (size_t)gslot * kDepBuf, ds, is, P.pend + (size_t)gslot * 6, g.mat, in_vol,
                               e_changed);
   if (alive && e_changed) set_energy(P, S, slot, g);
   store_ph(S, slot, g);
@@ -1019,7 +1018,6 @@ __device__ __noinline__ int phase_end(const Params &P, Smem &S, int slot, int gs
     }
     g.E = kMc2; g.seg = 0.0f;
     g.flags &= ~F_PEND;
-    S.iter[slot] = 0;
     next = locate(P, g);
     set_energy(P, S, slot, g);
     store_ph(S, slot, g);
@@ -1039,20 +1037,19 @@ __device__ __noinline__ int phase_end(const Params &P, Smem &S, int slot, int gs
     base = __shfl_sync(act, base, leader);
     const unsigned long long idx = base + (unsigned long long)__popc(act & ((1u << lane) - 1u));
     if (idx >= P.count) {
-      S.flags[slot] = 0;
+      S.fm[slot] = 0;
       next = Q_RETIRED;
     } else {
-      const unsigned long long id = P.first + idx;
-      rng_init(g.rng, P.seed, id, 0u);
-      S.hlo[slot] = g.rng.h0; S.hhi[slot] = g.rng.h1;
+      S.hidx[slot] = (unsigned)idx;
+      rng_init(g.rng, P.seed, P.first + idx, 0u);
       g.flags = F_OPEN;
+      g.mat = 0;
       generate_primary(P, g);
       g.path = 0.0f; g.seg = 0.0f;
-      S.iter[slot] = 0;
       n_hist = 1;
       next = locate(P, g);
       if (g.E < P.e_cut) {
-        c_edep += (double)(g.E * g.w);   // below the table: absorbed where it starts
+        c_edep += (double)(g.E * P.src.weight);   // below the table: absorbed where it starts
         next = Q_E;
         S.tbin[slot] = 0.0f;
       } else {
@@ -1080,9 +1077,10 @@ __global__ void __launch_bounds__(kThreads, 1) transport_kernel(const __grid_con
 
   for (int i = threadIdx.x; i < P.ne; i += kThreads) s_maj[i] = P.maj[i];
   for (int i = threadIdx.x; i < kSlots; i += kThreads) {
-    S.flags[i] = 0; S.iter[i] = 0; S.blk[i] = 0; S.hlo[i] = 0; S.hhi[i] = 0; S.tbin[i] = 0.0f; S.mat[i] = 0;
-    S.cell[Q_V][i] = -1; S.cell[Q_I][i] = -1; S.cell[Q_W][i] = -1;
-    S.cell[Q_E][i] = i;                  // every slot starts by asking for a history
+    S.fm[i] = 0; S.blk[i] = 0; S.hidx[i] = 0; S.tbin[i] = 0.0f;
+    S.cell[Q_V][i] = (unsigned short)kEmpty; S.cell[Q_I][i] = (unsigned short)kEmpty;
+    S.cell[Q_W][i] = (unsigned short)kEmpty;
+    S.cell[Q_E][i] = (unsigned short)i;   // every slot starts by asking for a history
   }
   if (threadIdx.x < Q_COUNT) {
     S.head[threadIdx.x] = 0;
@@ -1090,7 +1088,7 @@ __global__ void __launch_bounds__(kThreads, 1) transport_kernel(const __grid_con
     S.avail[threadIdx.x] = threadIdx.x == Q_E ? kSlots : 0;
   }
   if (threadIdx.x < S_COUNT) S.stats[threadIdx.x] = 0ull;
-  if (threadIdx.x == 0) { S.retired = 0; S.edep = 0.0; }
+  if (threadIdx.x == 0) { S.retired = 0; S.edep = 0.0; S.cur = Q_E; }
   __syncthreads();
 
   unsigned c_tent = 0;
@@ -1099,27 +1097,37 @@ __global__ void __launch_bounds__(kThreads, 1) transport_kernel(const __grid_con
   const int slot_base = blockIdx.x * kSlots;
 
   for (;;) {
-    // ---- claim up to 32 slots that wait for the same phase (lane 0 negotiates with the queues)
+    // ---- claim up to 32 slots that wait for the same phase (lane 0 negotiates with the queues).
+    // The CTA drains ONE queue at a time (S.cur): all warps run the same code, which keeps the
+    // instruction working set of the SM at one phase instead of the whole kernel.  When the current
+    // queue cannot fill a warp any more, the warp that notices moves the CTA to the fullest queue.
     int q = -1, got = 0, base = 0;
     if (lane == 0) {
       for (;;) {
-        int best = ld_vol(&S.avail[0]), bq = 0;
+        int bq = ld_vol(&S.cur);
+        int best = ld_vol(&S.avail[bq]);
+        if (best < 32) {
 #pragma unroll
-        for (int t = 1; t < Q_COUNT; ++t) {
-          const int a = ld_vol(&S.avail[t]);
-          if (a > best) { best = a; bq = t; }
+          for (int t = 0; t < Q_COUNT; ++t) {
+            const int a = ld_vol(&S.avail[t]);
+            if (a > best) { best = a; bq = t; }
+          }
         }
         if (best >= 32 || (best > 0 && polls >= 2)) {
           const int want = best < 32 ? best : 32;
           const int old = atomicSub(&S.avail[bq], want);
           const int g = old < want ? (old > 0 ? old : 0) : want;
           if (g < want) atomicAdd(&S.avail[bq], want - g);
-          if (g > 0) { q = bq; got = g; base = atomicAdd(&S.head[bq], g); break; }
+          if (g > 0) {
+            q = bq; got = g; base = atomicAdd(&S.head[bq], g);
+            st_vol(&S.cur, bq);
+            break;
+          }
           continue;
         }
         if (best <= 0 && ld_vol(&S.retired) >= kSlots) { q = -2; break; }
         ++polls;
-        __nanosleep(polls < 8 ? 32 : 256);
+        __nanosleep(polls < 8 ? 64 : 512);
       }
     }
     q = __shfl_sync(FULL, q, 0);
@@ -1129,9 +1137,11 @@ __global__ void __launch_bounds__(kThreads, 1) transport_kernel(const __grid_con
     polls = 0;
     int slot = -1;
     if ((int)lane < got) {
-      int *c = &S.cell[q][(base + (int)lane) & kSlotMask];
-      while ((slot = ld_vol(c)) < 0) { }
-      st_vol(c, -1);
+      unsigned short *c = &S.cell[q][(unsigned)(base + (int)lane) % (unsigned)kSlots];
+      unsigned v;
+      while ((v = ld_cell(c)) == kEmpty) { }
+      st_cell(c, kEmpty);
+      slot = (int)v;
     }
     __threadfence_block();
 
@@ -1156,9 +1166,9 @@ __global__ void __launch_bounds__(kThreads, 1) transport_kernel(const __grid_con
       if ((int)lane == leader) tk = atomicAdd(&S.tail[t], n);
       tk = __shfl_sync(FULL, tk, leader);
       if (next == t) {
-        int *c = &S.cell[t][(tk + __popc(m & ((1u << lane) - 1u))) & kSlotMask];
-        while (ld_vol(c) >= 0) { }   // the previous occupant is claimed, its reader clears it at once
-        st_vol(c, slot);
+        unsigned short *c = &S.cell[t][(unsigned)(tk + __popc(m & ((1u << lane) - 1u))) % (unsigned)kSlots];
+        while (ld_cell(c) != kEmpty) { }   // the previous occupant is claimed, its reader clears it at once
+        st_cell(c, (unsigned)slot);
       }
       __syncwarp();
       if ((int)lane == leader) atomicAdd(&S.avail[t], n);

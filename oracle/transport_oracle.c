@@ -159,6 +159,7 @@ static float rng_uniform(rng_t *r) {
 #define ORACLE_MAX_DOSE 4
 #define DEP_BUF 32
 #define WOODCOCK_K 4
+#define MAX_BLOCKS 4000000u
 #define NUDGE 1.0e-3f
 #define BIG 3.0e38f
 #define MC2 0.51099891f
@@ -779,7 +780,8 @@ static void run_photon(hist_t *h, float pend_p[3], float pend_d[3], int *pend) {
     return;
   }
   update_energy(h);
-  for (int iter = 0; alive && iter < 1000000; ++iter) {
+  for (int iter = 0; alive; ++iter) {
+    if (h->rng.ctr[2] > MAX_BLOCKS) break; /* runaway guard: Philox blocks one history may consume */
     if (h->trace) h->trace->n_iter++;
 #ifdef ORACLE_DEBUG
     if (h->trace && h->trace->n_iter < 40)

@@ -205,6 +205,8 @@ int gate_b200_set_tables(gate_b200_engine *h, const gate_b200_tables *t) {
   if (!h || !t) return GATE_B200_EINVAL;
   if (t->n_materials < 1 || t->n_energy < 2 || t->n_q < 2)
     return fail(h, GATE_B200_EINVAL, "tables: need >=1 material, >=2 energy and q nodes");
+  if (t->n_materials > kMaxMaterials)
+    return fail(h, GATE_B200_EINVAL, "tables: at most %d materials (got %d)", kMaxMaterials, t->n_materials);
   if (!(t->e_min_MeV > 0) || !(t->e_max_MeV > t->e_min_MeV) || !(t->q2_max > t->q2_min) || !(t->q2_min > 0))
     return fail(h, GATE_B200_EINVAL, "tables: bad grid limits");
   CU(cudaSetDevice(h->device));

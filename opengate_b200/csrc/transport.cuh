@@ -3,7 +3,8 @@
 // Execution model (DESIGN.md "kernel"): one persistent CTA per SM owns kSlots photon slots whose
 // state lives in shared memory.  A photon is always waiting for exactly one kind of work:
 //   Q_V  Woodcock flight through the label volume (kWoodcockK speculative tentative collisions)
-//   Q_I  one real interaction (Compton / Rayleigh / photoelectric / conversion) + kerma deposit
+//   Q_C  one Compton trial (Klein-Nishina x scattering function) and, if accepted, its final state
+//   Q_R  the rare interactions: Rayleigh, conversion with annihilation photons
 //   Q_W  one flight segment in the homogeneous world (entry, exit, phase-space planes)
 //   Q_E  end of a photon: second annihilation photon, or close the history (flush its coalesced
 //        deposits with warp-aggregated fp64 atomics) and start the next primary
@@ -24,7 +25,7 @@
 #include "device_math.cuh"
 
 #ifndef GB2_THREADS
-#define GB2_THREADS 512
+#define GB2_THREADS 1024
 #endif
 #ifndef GB2_SLOTS
 #define GB2_SLOTS 3072
@@ -45,7 +46,7 @@ constexpr float kKPerMeV = 268.17264f;     // photon wave number (1/bohr) per Me
 constexpr float kCmmPerNs = 299.792458f;
 constexpr unsigned kMaxBlocks = 4000000u; // Philox blocks one history may consume (runaway guard)
 
-enum { Q_V = 0, Q_I = 1, Q_W = 2, Q_E = 3, Q_COUNT = 4, Q_RETIRED = -1 };
+enum { Q_V = 0, Q_C = 1, Q_R = 2, Q_W = 3, Q_E = 4, Q_COUNT = 5, Q_RETIRED = -1 };
 
 struct Affine { float m[9]; float t[3]; };
 
@@ -125,7 +126,7 @@ struct Smem {
   float E[kSlots], tbin[kSlots], path[kSlots], seg[kSlots];
   unsigned hidx[kSlots];                      // history index inside this launch (id = first + hidx)
   unsigned blk[kSlots];                       // next Philox block of the history
-  unsigned fm[kSlots];                        // flags (low 16 bits) | material of the pending interaction << 16
+  unsigned fm[kSlots];                        // flags (low 20 bits) | material of the pending interaction << 20
   unsigned short cell[Q_COUNT][kSlots];       // ring queues of slot numbers, kEmpty = free cell
   int head[Q_COUNT], tail[Q_COUNT], avail[Q_COUNT];
   int cur;                                    // phase the CTA is currently draining
@@ -135,7 +136,7 @@ struct Smem {
 };
 constexpr unsigned kEmpty = 0xffffu;
 
-// bits of Smem::flags
+// bits of Smem::fm (flags in the low 20 bits, material label in the high 12)
 constexpr unsigned F_INSIDE = 0xfu;        // bit k: currently inside phase-space box k
 constexpr unsigned F_STORED = 1u << 4;     // the history left at least one phase-space row
 constexpr unsigned F_PEND_SHIFT = 5;       // 0 none, 1 pending photon in the volume frame, 2 world frame
@@ -144,7 +145,12 @@ constexpr unsigned F_INVOL = 1u << 7;      // the pending interaction is inside 
 constexpr unsigned F_OPEN = 1u << 8;       // a history is in flight in this slot
 constexpr unsigned F_NBUF_SHIFT = 9;       // entries in the coalescing buffer (0..kDepBuf)
 constexpr unsigned F_NBUF = 0x3fu << F_NBUF_SHIFT;
-constexpr unsigned F_MASK = 0xffffu;
+constexpr unsigned F_ABSORB = 1u << 15;    // Q_E: the photon is absorbed on the spot first (phot / conv kerma)
+constexpr unsigned F_EXIT = 1u << 16;      // Q_W: the photon is leaving the image volume (still in its frame)
+constexpr unsigned F_CONV = 1u << 17;      // the pending interaction is a conversion (else Rayleigh / phot)
+constexpr unsigned F_MAT_SHIFT = 20;
+constexpr unsigned F_MASK = (1u << F_MAT_SHIFT) - 1u;
+constexpr int kMaxMaterials = 1 << 12;
 
 // ------------------------------------------------------------------------------ helpers
 
@@ -286,7 +292,7 @@ __device__ __forceinline__ void load_ph(const Params &P, const Smem &S, int s, P
   bin_split(P, S.tbin[s], g.ie, g.fe);
   const unsigned fm = S.fm[s];
   g.flags = fm & F_MASK;
-  g.mat = (int)(fm >> 16);
+  g.mat = (int)(fm >> F_MAT_SHIFT);
   const unsigned long long id = P.first + S.hidx[s];
   g.rng.k0 = (uint32_t)P.seed; g.rng.k1 = (uint32_t)(P.seed >> 32);
   g.rng.h0 = (uint32_t)id; g.rng.h1 = (uint32_t)(id >> 32); g.rng.blk = S.blk[s]; g.rng.pos = 4;
@@ -295,7 +301,7 @@ __device__ __forceinline__ void store_ph(Smem &S, int s, const Ph &g) {
   S.px[s] = g.p[0]; S.py[s] = g.p[1]; S.pz[s] = g.p[2];
   S.dx[s] = g.d[0]; S.dy[s] = g.d[1]; S.dz[s] = g.d[2];
   S.E[s] = g.E; S.path[s] = g.path; S.seg[s] = g.seg;
-  S.fm[s] = (g.flags & F_MASK) | ((unsigned)g.mat << 16);
+  S.fm[s] = (g.flags & F_MASK) | ((unsigned)g.mat << F_MAT_SHIFT);
   S.blk[s] = g.rng.blk;
 }
 __device__ __forceinline__ void set_energy(const Params &P, Smem &S, int s, Ph &g) {
@@ -462,139 +468,22 @@ __device__ __noinline__ float interp_q2(const Params &P, const float *__restrict
   return r0 + f * (r1 - r0);
 }
 
-struct IntStat { unsigned phot, compt, rayl, conv, tracks; };
-
-// one real interaction in material m; returns true if the photon survives.  pend[6] receives the
-// second annihilation photon (pair_mode 1).
-__device__ __forceinline__ bool interact(const Params &P, Ph &g, DepEntry *buf, DepStat &ds,
-                                         IntStat &is, float *pend, int m, bool in_vol,
-                                         bool &energy_changed) {
-  rng_begin(g.rng);
-  float u = rng_uniform(g.rng);
-  const float4 pa = __ldg(P.prob + (size_t)g.ie * P.nmat + m);
-  const float4 pb = __ldg(P.prob + (size_t)(g.ie + 1) * P.nmat + m);
-  float pph = pa.x + g.fe * (pb.x - pa.x);
-  float pco = pa.y + g.fe * (pb.y - pa.y);
-  float pra = pa.z + g.fe * (pb.z - pa.z);
-  energy_changed = false;
-  if (u < pph) {
-    is.phot++;
-    deposit(P, g, buf, ds, g.E * P.src.weight, m, in_vol);
-    return false;
-  }
-  if (u < pco) {
-    is.compt++;
-    float E = g.E;
-    float k = E / kMc2;
-    float eps0 = 1.0f / (1.0f + 2.0f * k);
-    float eps0sq = eps0 * eps0;
-    float alpha1 = -d_logf(eps0);
-    float alpha2 = alpha1 + 0.5f * (1.0f - eps0sq);
-    float kq = kKPerMeV * E;
-    float two_kq2 = 2.0f * kq * kq;
-    const float *sfrow = P.sf + (size_t)m * P.nq;
-    float eps = 1.0f, onecost = 0.0f, sint2 = 0.0f;
-    for (int it = 0; it < 1000; ++it) {
-      float u1 = rng_uniform(g.rng), u2 = rng_uniform(g.rng), u3 = rng_uniform(g.rng);
-      float epssq;
-      if (alpha1 > alpha2 * u1) {
-        eps = d_expf(-alpha1 * u2);
-        epssq = eps * eps;
-      } else {
-        epssq = eps0sq + (1.0f - eps0sq) * u2;
-        eps = sqrtf(epssq);
-      }
-      onecost = (1.0f - eps) / (eps * k);
-      sint2 = onecost * (2.0f - onecost);
-      float grej = 1.0f - eps * sint2 / (1.0f + epssq);
-      if (grej < u3) continue;
-      float sfv = interp_q2(P, sfrow, two_kq2 * onecost);
-      float u4 = rng_uniform(g.rng);
-      if (u4 > sfv) continue;
-      break;
-    }
-    float cost = 1.0f - onecost;
-    float sint = sqrtf(sint2 > 0.0f ? sint2 : 0.0f);
-    float sphi, cphi;
-    d_sincos2pi(rng_uniform(g.rng), sphi, cphi);
-    float E1 = eps * E;
-    deposit(P, g, buf, ds, (E - E1) * P.src.weight, m, in_vol);
-    rotate_dir(g.d, cost, sint, sphi, cphi);
-    g.E = E1;
-    g.seg = 0.0f;
-    if (E1 < P.e_cut) {
-      deposit(P, g, buf, ds, E1 * P.src.weight, m, in_vol);
-      return false;
-    }
-    energy_changed = true;
-    return true;
-  }
-  if (u < pra) {
-    is.rayl++;
-    float kq = kKPerMeV * g.E;
-    float kq2 = kq * kq;
-    const float *A = P.ray + (size_t)m * P.nq;
-    float q2max = 4.0f * kq2;
-    int jmax = q2_segment(P, q2max);
-    float amax = interp_q2(P, A, q2max);
-    float cost = 1.0f;
-    const float a0 = __ldg(A);
-    const float q20 = __ldg(P.q2n);
-    for (int it = 0; it < 1000; ++it) {
-      float target = rng_uniform(g.rng) * amax;
-      float q2;
-      if (target < a0) {
-        q2 = q20 * (target / a0);
-      } else {
-        int lo = 0, hi = jmax < P.nq - 1 ? jmax + 1 : P.nq - 1;
-        if (target >= __ldg(A + hi)) lo = hi > 0 ? hi - 1 : 0;
-        else
-          while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (__ldg(A + mid) <= target) lo = mid; else hi = mid;
-          }
-        float al = __ldg(A + lo), ah = __ldg(A + lo + 1);
-        float den = ah - al;
-        float f = den > 0.0f ? (target - al) / den : 0.0f;
-        if (f > 1.0f) f = 1.0f;
-        float ql = __ldg(P.q2n + lo), qh = __ldg(P.q2n + lo + 1);
-        q2 = ql + f * (qh - ql);
-      }
-      if (q2 > q2max) q2 = q2max;
-      cost = 1.0f - q2 / (2.0f * kq2);
-      if (cost < -1.0f) cost = -1.0f;
-      float u2 = rng_uniform(g.rng);
-      if (0.5f * (1.0f + cost * cost) >= u2) break;
-    }
-    float sint = sqrtf(1.0f - cost * cost);
-    float sphi, cphi;
-    d_sincos2pi(rng_uniform(g.rng), sphi, cphi);
-    rotate_dir(g.d, cost, sint, sphi, cphi);
-    g.seg = 0.0f;
-    return true;
-  }
-  is.conv++;
-  if (P.pair_mode == 0) {
-    // production cuts >> range with apply_cuts: e-, e+ (and its 2 mc2) stay on the spot
-    deposit(P, g, buf, ds, g.E * P.src.weight, m, in_vol);
-    return false;
-  }
-  deposit(P, g, buf, ds, (g.E - 2.0f * kMc2) * P.src.weight, m, in_vol);
-  {
-    float cost = 2.0f * rng_uniform(g.rng) - 1.0f;
-    float sint = sqrtf(1.0f - cost * cost);
-    float sphi, cphi;
-    d_sincos2pi(rng_uniform(g.rng), sphi, cphi);
-    g.d[0] = sint * cphi; g.d[1] = sint * sphi; g.d[2] = cost;
-    g.E = kMc2;
-    g.seg = 0.0f;
-    energy_changed = true;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) { __stcg(pend + a, g.p[a]); __stcg(pend + 3 + a, -g.d[a]); }
-    g.flags = (g.flags & ~F_PEND) | ((in_vol ? 1u : 2u) << F_PEND_SHIFT);
-    is.tracks += 2;
-  }
-  return true;
+// Process selection from a variate v uniform in (0,1) (oracle select_process): inside the volume
+// v is the rescaled Woodcock acceptance variate, in the world the second uniform of the flight
+// block.  Sets the routing flags and returns the queue of the phase that carries the process out.
+__device__ __forceinline__ int route_interaction(const Params &P, unsigned &flags, int m, int ie, float fe, float v) {
+  const float4 pa = __ldg(P.prob + (size_t)ie * P.nmat + m);
+  const float4 pb = __ldg(P.prob + (size_t)(ie + 1) * P.nmat + m);
+  const float pph = pa.x + fe * (pb.x - pa.x);
+  const float pco = pa.y + fe * (pb.y - pa.y);
+  const float pra = pa.z + fe * (pb.z - pa.z);
+  flags &= ~(F_ABSORB | F_CONV);
+  if (v < pph) { flags |= F_ABSORB; return Q_E; }                  // photoelectric: kerma, dies
+  if (v < pco) return Q_C;
+  if (v < pra) return Q_R;
+  flags |= F_CONV;
+  if (P.pair_mode == 0) { flags |= F_ABSORB; return Q_E; }         // conversion, everything local
+  return Q_R;
 }
 
 // ------------------------------------------------------------------------------ primaries
@@ -799,12 +688,25 @@ __device__ __forceinline__ int locate(const Params &P, Ph &g) {
 
 // ------------------------------------------------------------------------------ phases
 
-// Q_W: one flight segment of a photon travelling in the world material (outside the image volume)
+// Q_W: one flight segment of a photon travelling in the world material (outside the image volume);
+// a photon that has just left the volume is first taken to its exit point and to the world frame.
 __device__ __noinline__ int phase_world(const Params &P, Smem &S, int slot) {
   Ph g;
   load_ph(P, S, slot, g);
   int next;
   unsigned n_esc = 0, n_steps = 0;
+  if (g.flags & F_EXIT) {
+    float ti, to;
+    int ai, ao;
+    if (!ray_box_ax(g.p, g.d, P.half, ti, to, ai, ao)) { to = 0.0f; ao = -1; }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) g.p[a] = g.p[a] + g.d[a] * to;
+    snap_to_face(g.p, g.d, P.half, ao, true);
+    g.path += to;
+    n_steps++;
+    to_world(P, g);
+    g.flags &= ~F_EXIT;
+  }
   float t_exit, t0;
   if (g.rng.blk > kMaxBlocks) {
     next = Q_E;
@@ -846,11 +748,12 @@ __device__ __noinline__ int phase_world(const Params &P, Smem &S, int slot) {
       for (int a = 0; a < 3; ++a) g.p[a] = g.p[a] + g.d[a] * step;
       g.path += step;
       if (ev == 0) {
+        // real interaction in the world material
         g.flags &= ~F_INVOL;
         g.mat = P.world_mat;
-        next = Q_I;      // real interaction in the world material
+        next = route_interaction(P, g.flags, g.mat, g.ie, g.fe, rng_uniform(g.rng));
       } else if (ev == 2) {
-        n_steps = 1;
+        n_steps++;
         to_volume(P, g);
         snap_to_face(g.p, g.d, P.half, ax_in, false);
         g.seg = 0.0f;
@@ -858,7 +761,7 @@ __device__ __noinline__ int phase_world(const Params &P, Smem &S, int slot) {
       } else {
         const int k = (ev - 3) >> 1;
         const unsigned long long hist = ((unsigned long long)g.rng.h1 << 32) | g.rng.h0;
-        n_steps = 1;
+        n_steps++;
         if (((ev - 3) & 1) == 0) {
           g.flags |= (1u << k);
           if (P.phsp[k].steps & GATE_B200_PHSP_ENTERING) phsp_store(P, g, hist, k, GATE_B200_PHSP_ENTERING);
@@ -928,82 +831,212 @@ __device__ __forceinline__ int phase_volume(const Params &P, Smem &S, const floa
     }
   }
   float path = S.path[slot], seg = S.seg[slot];
-  int next = Q_V;
   int mat = 0;
+  float vsel = 0.0f;
   unsigned tent = 0;
-  bool left = false;
+  bool left = false, hit = false;
 #pragma unroll
   for (int k = 0; k < kWoodcockK; ++k) {
-    if (next != Q_V || left) continue;
+    if (hit || left) continue;
     if (!inb[k]) { left = true; continue; }
     p0 = q0[k]; p1 = q1[k]; p2 = q2[k];
     path += s[k];
     seg += s[k];
     tent++;
-    if (u32_to_uniform(r[2 * k + 1]) * maj <= mu[k]) {
+    const float t = u32_to_uniform(r[2 * k + 1]) * maj;
+    if (t <= mu[k]) {       // accepted: a real interaction in material lab[k]
       mat = lab[k];
-      next = Q_I;       // accepted: the interaction itself runs in the interaction phase
+      vsel = t / mu[k];
+      hit = true;
     }
   }
   c_tent += tent;
+  S.px[slot] = p0; S.py[slot] = p1; S.pz[slot] = p2;
+  S.path[slot] = path; S.seg[slot] = seg;
+  int next = Q_V;
   if (left) {
-    // left the volume: restart from the exit point in the world frame
-    float p[3] = {p0, p1, p2}, d[3] = {d0, d1, d2};
-    float ti, to;
-    int ai, ao;
-    if (!ray_box_ax(p, d, P.half, ti, to, ai, ao)) { to = 0.0f; ao = -1; }
-#pragma unroll
-    for (int a = 0; a < 3; ++a) p[a] = p[a] + d[a] * to;
-    snap_to_face(p, d, P.half, ao, true);
-    path += to;
-    float pw[3], dw[3];
-    aff_apply_inv(P.w2v, p, pw);
-    rot_apply_inv(P.w2v.m, d, dw);
-    S.px[slot] = pw[0]; S.py[slot] = pw[1]; S.pz[slot] = pw[2];
-    S.dx[slot] = dw[0]; S.dy[slot] = dw[1]; S.dz[slot] = dw[2];
-    S.path[slot] = path;
+    S.fm[slot] |= F_EXIT;   // taken to the exit point and to the world frame by the world phase
     next = Q_W;
-  } else {
-    S.px[slot] = p0; S.py[slot] = p1; S.pz[slot] = p2;
-    S.path[slot] = path; S.seg[slot] = seg;
-    if (next == Q_I) S.fm[slot] = (S.fm[slot] & F_MASK) | F_INVOL | ((unsigned)mat << 16);
+  } else if (hit) {
+    unsigned flags = (S.fm[slot] & F_MASK) | F_INVOL;
+    next = route_interaction(P, flags, mat, ie, fe, vsel);
+    S.fm[slot] = flags | ((unsigned)mat << F_MAT_SHIFT);
   }
-  stat_add(S, S_STEPS, left ? 1u : 0u);
   return next;
 }
 
-// Q_I: one real interaction + kerma deposit into the coalescing buffer of the history
-__device__ __noinline__ int phase_interact(const Params &P, Smem &S, int slot, int gslot, double &c_edep) {
-  Ph g;
-  load_ph(P, S, slot, g);
-  const bool in_vol = (g.flags & F_INVOL) != 0;
+// Q_C: one Compton trial (Klein-Nishina composition-rejection x scattering function).  A rejected
+// trial simply stays in the queue: trials are independent, each call owns two fresh Philox blocks
+// (trial, final state), so the lanes of a warp never wait for each other's rejection loops.
+__device__ __noinline__ int phase_compton(const Params &P, Smem &S, int slot, int gslot, double &c_edep) {
+  const unsigned b0 = S.blk[slot];
+  S.blk[slot] = b0 + 2u;
+  const float E = S.E[slot];
+  const unsigned fm = S.fm[slot];
+  const int m = (int)(fm >> F_MAT_SHIFT);
+  uint32_t r[8];
+  {
+    const unsigned long long id = P.first + S.hidx[slot];
+    philox_block2((uint32_t)P.seed, (uint32_t)(P.seed >> 32), (uint32_t)id, (uint32_t)(id >> 32), b0, r);
+  }
+  const float k = E / kMc2;
+  const float eps0 = 1.0f / (1.0f + 2.0f * k);
+  const float eps0sq = eps0 * eps0;
+  const float alpha1 = -d_logf(eps0);
+  const float alpha2 = alpha1 + 0.5f * (1.0f - eps0sq);
+  const float kq = kKPerMeV * E;
+  const float two_kq2 = 2.0f * kq * kq;
+  const float u1 = u32_to_uniform(r[0]), u2 = u32_to_uniform(r[1]), u3 = u32_to_uniform(r[2]), u4 = u32_to_uniform(r[3]);
+  float eps, epssq;
+  if (alpha1 > alpha2 * u1) {
+    eps = d_expf(-alpha1 * u2);
+    epssq = eps * eps;
+  } else {
+    epssq = eps0sq + (1.0f - eps0sq) * u2;
+    eps = sqrtf(epssq);
+  }
+  const float onecost = (1.0f - eps) / (eps * k);
+  const float sint2 = onecost * (2.0f - onecost);
+  const float grej = 1.0f - eps * sint2 / (1.0f + epssq);
+  bool ok = !(grej < u3);
+  const float sfv = interp_q2(P, P.sf + (size_t)m * P.nq, two_kq2 * onecost);
+  if (u4 > sfv) ok = false;
+  int next = Q_C;
+  unsigned n_compt = 0;
   DepStat ds; ds.dep = 0; ds.over = 0; ds.flush = 0; ds.edep = 0.0;
-  IntStat is; is.phot = is.compt = is.rayl = is.conv = is.tracks = 0;
-  bool e_changed;
-  const bool alive = interact(P, g, P.depbuf + (size_t)gslot * kDepBuf, ds, is, P.pend + (size_t)gslot * 6, g.mat, in_vol,
-                              e_changed);
-  if (alive && e_changed) set_energy(P, S, slot, g);
-  store_ph(S, slot, g);
-  c_edep += ds.edep;
-  stat_add(S, S_STEPS, 1u);
-  stat_add(S, S_PHOT, is.phot);
-  stat_add(S, S_COMPT, is.compt);
-  stat_add(S, S_RAYL, is.rayl);
-  stat_add(S, S_CONV, is.conv);
-  stat_add(S, S_TRACKS, is.tracks);
+  if (ok) {
+    Ph g;
+    load_ph(P, S, slot, g);
+    // the rest of the call's random numbers: r[4] is the azimuth, deposits continue from r[5]
+    g.rng.blk = b0 + 2u; g.rng.pos = 1;
+    g.rng.o0 = r[5]; g.rng.o1 = r[6]; g.rng.o2 = r[7];
+    const bool in_vol = (g.flags & F_INVOL) != 0;
+    DepEntry *buf = P.depbuf + (size_t)gslot * kDepBuf;
+    n_compt = 1;
+    const float cost = 1.0f - onecost;
+    const float sint = sqrtf(sint2 > 0.0f ? sint2 : 0.0f);
+    float sphi, cphi;
+    d_sincos2pi(u32_to_uniform(r[4]), sphi, cphi);
+    const float E1 = eps * E;
+    deposit(P, g, buf, ds, (E - E1) * P.src.weight, m, in_vol);
+    rotate_dir(g.d, cost, sint, sphi, cphi);
+    g.E = E1;
+    g.seg = 0.0f;
+    if (E1 < P.e_cut) {
+      deposit(P, g, buf, ds, E1 * P.src.weight, m, in_vol);
+      next = Q_E;
+    } else {
+      set_energy(P, S, slot, g);
+      next = in_vol ? Q_V : Q_W;
+    }
+    store_ph(S, slot, g);
+    c_edep += ds.edep;
+  }
+  stat_add(S, S_COMPT, n_compt);
+  stat_add(S, S_STEPS, n_compt);
   stat_add(S, S_DEP, ds.dep);
   stat_add(S, S_OVER, ds.over);
   stat_add(S, S_FLUSH, ds.flush);
-  return alive ? (in_vol ? Q_V : Q_W) : Q_E;
+  return next;
 }
 
-// Q_E: the photon of this slot is gone.  Either the history still owes its second annihilation
-// photon, or it is closed (coalesced deposits -> grids) and the slot claims the next history.
+// Q_R: the rare interactions.  Rayleigh: q2 from the cumulative squared form factor, (1+cos^2)/2
+// test.  Conversion with pair_mode 1: deposit E - 2 mc2, emit two back-to-back 511 keV photons.
+__device__ __noinline__ int phase_rare(const Params &P, Smem &S, int slot, int gslot, double &c_edep) {
+  Ph g;
+  load_ph(P, S, slot, g);
+  const bool in_vol = (g.flags & F_INVOL) != 0;
+  const int m = g.mat;
+  unsigned n_rayl = 0, n_conv = 0;
+  DepStat ds; ds.dep = 0; ds.over = 0; ds.flush = 0; ds.edep = 0.0;
+  rng_begin(g.rng);
+  if (!(g.flags & F_CONV)) {
+    n_rayl = 1;
+    float kq = kKPerMeV * g.E;
+    float kq2 = kq * kq;
+    const float *A = P.ray + (size_t)m * P.nq;
+    float q2max = 4.0f * kq2;
+    int jmax = q2_segment(P, q2max);
+    float amax = interp_q2(P, A, q2max);
+    float cost = 1.0f;
+    const float a0 = __ldg(A);
+    const float q20 = __ldg(P.q2n);
+    for (int it = 0; it < 1000; ++it) {
+      float target = rng_uniform(g.rng) * amax;
+      float q2;
+      if (target < a0) {
+        q2 = q20 * (target / a0);
+      } else {
+        int lo = 0, hi = jmax < P.nq - 1 ? jmax + 1 : P.nq - 1;
+        if (target >= __ldg(A + hi)) lo = hi > 0 ? hi - 1 : 0;
+        else
+          while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (__ldg(A + mid) <= target) lo = mid; else hi = mid;
+          }
+        float al = __ldg(A + lo), ah = __ldg(A + lo + 1);
+        float den = ah - al;
+        float f = den > 0.0f ? (target - al) / den : 0.0f;
+        if (f > 1.0f) f = 1.0f;
+        float ql = __ldg(P.q2n + lo), qh = __ldg(P.q2n + lo + 1);
+        q2 = ql + f * (qh - ql);
+      }
+      if (q2 > q2max) q2 = q2max;
+      cost = 1.0f - q2 / (2.0f * kq2);
+      if (cost < -1.0f) cost = -1.0f;
+      float u2 = rng_uniform(g.rng);
+      if (0.5f * (1.0f + cost * cost) >= u2) break;
+    }
+    float sint = sqrtf(1.0f - cost * cost);
+    float sphi, cphi;
+    d_sincos2pi(rng_uniform(g.rng), sphi, cphi);
+    rotate_dir(g.d, cost, sint, sphi, cphi);
+    g.seg = 0.0f;
+  } else {
+    n_conv = 1;
+    deposit(P, g, P.depbuf + (size_t)gslot * kDepBuf, ds, (g.E - 2.0f * kMc2) * P.src.weight, m, in_vol);
+    float cost = 2.0f * rng_uniform(g.rng) - 1.0f;
+    float sint = sqrtf(1.0f - cost * cost);
+    float sphi, cphi;
+    d_sincos2pi(rng_uniform(g.rng), sphi, cphi);
+    g.d[0] = sint * cphi; g.d[1] = sint * sphi; g.d[2] = cost;
+    g.E = kMc2;
+    g.seg = 0.0f;
+    set_energy(P, S, slot, g);
+    float *pend = P.pend + (size_t)gslot * 6;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { __stcg(pend + a, g.p[a]); __stcg(pend + 3 + a, -g.d[a]); }
+    g.flags = (g.flags & ~(F_PEND | F_CONV)) | ((in_vol ? 1u : 2u) << F_PEND_SHIFT);
+  }
+  store_ph(S, slot, g);
+  c_edep += ds.edep;
+  stat_add(S, S_RAYL, n_rayl);
+  stat_add(S, S_CONV, n_conv);
+  stat_add(S, S_TRACKS, 2u * n_conv);
+  stat_add(S, S_STEPS, n_rayl + n_conv);
+  stat_add(S, S_DEP, ds.dep);
+  stat_add(S, S_OVER, ds.over);
+  stat_add(S, S_FLUSH, ds.flush);
+  return in_vol ? Q_V : Q_W;
+}
+
+// Q_E: the photon of this slot is gone: absorbed on the spot (photoelectric effect, conversion in
+// the kerma configuration), below the energy cut, or out of the world.  Either the history still
+// owes its second annihilation photon, or it is closed (coalesced deposits -> grids) and the slot
+// claims the next history.
 __device__ __noinline__ int phase_end(const Params &P, Smem &S, int slot, int gslot, double &c_edep) {
   Ph g;
   load_ph(P, S, slot, g);
   int next;
-  unsigned n_flush = 0, n_abs = 0, n_hist = 0;
+  unsigned n_flush = 0, n_abs = 0, n_hist = 0, n_phot = 0, n_conv = 0;
+  DepStat ds; ds.dep = 0; ds.over = 0; ds.flush = 0; ds.edep = 0.0;
+  if (g.flags & F_ABSORB) {
+    if (g.flags & F_CONV) n_conv = 1; else n_phot = 1;
+    rng_begin(g.rng);
+    deposit(P, g, P.depbuf + (size_t)gslot * kDepBuf, ds, g.E * P.src.weight, g.mat, (g.flags & F_INVOL) != 0);
+    g.flags &= ~(F_ABSORB | F_CONV);
+    c_edep += ds.edep;
+  }
   if (g.flags & F_PEND) {
     // second annihilation photon of a conversion (pair_mode 1): stored in the frame current at
     // creation (1 = volume, 2 = world); go back to the world frame and find the region again
@@ -1017,7 +1050,7 @@ __device__ __noinline__ int phase_end(const Params &P, Smem &S, int slot, int gs
       for (int a = 0; a < 3; ++a) { g.p[a] = pp[a]; g.d[a] = pd[a]; }
     }
     g.E = kMc2; g.seg = 0.0f;
-    g.flags &= ~F_PEND;
+    g.flags &= ~(F_PEND | F_EXIT);
     next = locate(P, g);
     set_energy(P, S, slot, g);
     store_ph(S, slot, g);
@@ -1058,10 +1091,15 @@ __device__ __noinline__ int phase_end(const Params &P, Smem &S, int slot, int gs
       store_ph(S, slot, g);
     }
   }
-  stat_add(S, S_FLUSH, n_flush);
+  stat_add(S, S_FLUSH, n_flush + ds.flush);
   stat_add(S, S_ABSORBED, n_abs);
   stat_add(S, S_HIST, n_hist);
   stat_add(S, S_TRACKS, n_hist);
+  stat_add(S, S_PHOT, n_phot);
+  stat_add(S, S_CONV, n_conv);
+  stat_add(S, S_STEPS, n_phot + n_conv);
+  stat_add(S, S_DEP, ds.dep);
+  stat_add(S, S_OVER, ds.over);
   return next;
 }
 
@@ -1078,14 +1116,13 @@ __global__ void __launch_bounds__(kThreads, 1) transport_kernel(const __grid_con
   for (int i = threadIdx.x; i < P.ne; i += kThreads) s_maj[i] = P.maj[i];
   for (int i = threadIdx.x; i < kSlots; i += kThreads) {
     S.fm[i] = 0; S.blk[i] = 0; S.hidx[i] = 0; S.tbin[i] = 0.0f;
-    S.cell[Q_V][i] = (unsigned short)kEmpty; S.cell[Q_I][i] = (unsigned short)kEmpty;
-    S.cell[Q_W][i] = (unsigned short)kEmpty;
-    S.cell[Q_E][i] = (unsigned short)i;   // every slot starts by asking for a history
+#pragma unroll
+    for (int t = 0; t < Q_COUNT; ++t) S.cell[t][i] = (unsigned short)(t == Q_E ? i : kEmpty);
   }
   if (threadIdx.x < Q_COUNT) {
     S.head[threadIdx.x] = 0;
     S.tail[threadIdx.x] = threadIdx.x == Q_E ? kSlots : 0;
-    S.avail[threadIdx.x] = threadIdx.x == Q_E ? kSlots : 0;
+    S.avail[threadIdx.x] = threadIdx.x == Q_E ? kSlots : 0;   // every slot starts by asking for a history
   }
   if (threadIdx.x < S_COUNT) S.stats[threadIdx.x] = 0ull;
   if (threadIdx.x == 0) { S.retired = 0; S.edep = 0.0; S.cur = Q_E; }
@@ -1149,33 +1186,37 @@ __global__ void __launch_bounds__(kThreads, 1) transport_kernel(const __grid_con
     int next = -3;     // -3: this lane holds no slot
     if (slot >= 0) {
       if (q == Q_V) next = phase_volume<LabelT>(P, S, s_maj, slot, c_tent);
-      else if (q == Q_I) next = phase_interact(P, S, slot, slot_base + slot, c_edep);
+      else if (q == Q_C) next = phase_compton(P, S, slot, slot_base + slot, c_edep);
+      else if (q == Q_E) next = phase_end(P, S, slot, slot_base + slot, c_edep);
       else if (q == Q_W) next = phase_world(P, S, slot);
-      else next = phase_end(P, S, slot, slot_base + slot, c_edep);
+      else next = phase_rare(P, S, slot, slot_base + slot, c_edep);
     }
     __syncwarp();
     __threadfence_block();   // slot state visible before the slot is published again
 
-    // ---- push every slot to the queue of its next phase
+    // ---- push every slot to the queue of its next phase: one pass, one leader lane per target queue
+    {
+      unsigned mine = 0;
 #pragma unroll
-    for (int t = 0; t < Q_COUNT; ++t) {
-      const unsigned m = __ballot_sync(FULL, next == t);
-      if (!m) continue;
-      const int n = __popc(m), leader = __ffs(m) - 1;
+      for (int t = 0; t < Q_COUNT; ++t) {
+        const unsigned m = __ballot_sync(FULL, next == t);
+        if (next == t) mine = m;
+      }
+      const unsigned mret = __ballot_sync(FULL, next == Q_RETIRED);
+      const bool pushing = next >= 0;
+      const int leader = pushing ? __ffs(mine) - 1 : (int)lane;
+      const int n = __popc(mine);
       int tk = 0;
-      if ((int)lane == leader) tk = atomicAdd(&S.tail[t], n);
+      if (pushing && (int)lane == leader) tk = atomicAdd(&S.tail[next], n);
       tk = __shfl_sync(FULL, tk, leader);
-      if (next == t) {
-        unsigned short *c = &S.cell[t][(unsigned)(tk + __popc(m & ((1u << lane) - 1u))) % (unsigned)kSlots];
+      if (pushing) {
+        unsigned short *c = &S.cell[next][(unsigned)(tk + __popc(mine & ((1u << lane) - 1u))) % (unsigned)kSlots];
         while (ld_cell(c) != kEmpty) { }   // the previous occupant is claimed, its reader clears it at once
         st_cell(c, (unsigned)slot);
       }
       __syncwarp();
-      if ((int)lane == leader) atomicAdd(&S.avail[t], n);
-    }
-    {
-      const unsigned m = __ballot_sync(FULL, next == Q_RETIRED);
-      if (m && lane == 0) atomicAdd(&S.retired, __popc(m));
+      if (pushing && (int)lane == leader) atomicAdd(&S.avail[next], n);
+      if (mret && lane == 0) atomicAdd(&S.retired, __popc(mret));
     }
   }
 

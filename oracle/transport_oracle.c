@@ -459,22 +459,33 @@ static float interp_q2(const oracle_engine *g, const float *row, float q2) {
 
 static void update_energy(hist_t *h) { energy_bin(h->g, h->E, &h->ie, &h->fe); }
 
-/* returns 1 if the photon survives */
-static int interact(hist_t *h, int m, int vix, int viy, int viz, float pend_p[3], float pend_d[3],
-                    int *pend) {
+/* Process selection.  v is uniform in (0,1): inside the volume it is the Woodcock acceptance
+ * variate rescaled, v = (u * majorant) / mu_total(material) (conditional on acceptance this is
+ * uniform, so no extra random number is needed); in the world it is the second uniform of the
+ * flight block.  Returns 0 phot, 1 compt, 2 rayl, 3 conv. */
+static int select_process(hist_t *h, int m, float v) {
   oracle_engine *g = h->g;
-  rng_begin(&h->rng);
-  float u = rng_uniform(&h->rng);
   float pph = tab(g->cph, g->ne, m, h->ie, h->fe);
   float pco = tab(g->cco, g->ne, m, h->ie, h->fe);
   float pra = tab(g->cra, g->ne, m, h->ie, h->fe);
   h->st.steps++;
-  if (u < pph) { /* photoelectric: everything stays here (kerma, fluorescence not tracked) */
+  if (v < pph) return 0;
+  if (v < pco) return 1;
+  if (v < pra) return 2;
+  return 3;
+}
+
+/* One real interaction of kind proc in material m; returns 1 if the photon survives. */
+static int interact(hist_t *h, int proc, int m, int vix, int viy, int viz, float pend_p[3], float pend_d[3],
+                    int *pend) {
+  oracle_engine *g = h->g;
+  if (proc == 0) { /* photoelectric: everything stays here (kerma, fluorescence not tracked) */
     h->st.n_phot++;
+    rng_begin(&h->rng);
     deposit(h, h->E * h->w, m, vix, viy, viz);
     return 0;
   }
-  if (u < pco) { /* Compton: Klein-Nishina composition-rejection x scattering function */
+  if (proc == 1) { /* Compton: Klein-Nishina composition-rejection x scattering function */
     h->st.n_compt++;
     float E = h->E;
     float k = E / MC2;
@@ -486,9 +497,15 @@ static int interact(hist_t *h, int m, int vix, int viy, int viz, float pend_p[3]
     float two_kq2 = 2.0f * kq * kq;
     const float *sfrow = g->sf + (size_t)m * g->nq;
     float eps = 1.0f, onecost = 0.0f, sint2 = 0.0f;
-    for (int it = 0; it < 1000; ++it) {
+    for (int it = 0; it < 100000; ++it) {
+      /* one trial = one call of the device's Compton phase: it owns two Philox blocks, the
+       * first feeds the trial (4 uniforms, all drawn), the second the final state */
+      uint32_t b0 = h->rng.ctr[2];
+      rng_begin(&h->rng);
       float u1 = rng_uniform(&h->rng), u2 = rng_uniform(&h->rng), u3 = rng_uniform(&h->rng);
+      float u4 = rng_uniform(&h->rng);
       float epssq;
+      int ok = 1;
       if (alpha1 > alpha2 * u1) {
         eps = o_expf(-alpha1 * u2);
         epssq = eps * eps;
@@ -499,11 +516,14 @@ static int interact(hist_t *h, int m, int vix, int viy, int viz, float pend_p[3]
       onecost = (1.0f - eps) / (eps * k);
       sint2 = onecost * (2.0f - onecost);
       float grej = 1.0f - eps * sint2 / (1.0f + epssq);
-      if (grej < u3) continue;
-      float sfv = interp_q2(g, sfrow, two_kq2 * onecost);
-      float u4 = rng_uniform(&h->rng);
-      if (u4 > sfv) continue;
-      break;
+      if (grej < u3) ok = 0;
+      if (ok) {
+        float sfv = interp_q2(g, sfrow, two_kq2 * onecost);
+        if (u4 > sfv) ok = 0;
+      }
+      if (ok) break;
+      h->rng.ctr[2] = b0 + 2u; /* rejected: the rest of the call's blocks is discarded */
+      h->rng.pos = 4;
     }
     float cost = 1.0f - onecost;
     float sint = sqrtf(sint2 > 0.0f ? sint2 : 0.0f);
@@ -521,8 +541,9 @@ static int interact(hist_t *h, int m, int vix, int viy, int viz, float pend_p[3]
     update_energy(h);
     return 1;
   }
-  if (u < pra) { /* Rayleigh: q2 from the cumulative squared form factor, (1+cos^2)/2 test */
+  if (proc == 2) { /* Rayleigh: q2 from the cumulative squared form factor, (1+cos^2)/2 test */
     h->st.n_rayl++;
+    rng_begin(&h->rng);
     float kq = K_PER_MEV * h->E;
     float kq2 = kq * kq;
     const float *A = g->ray + (size_t)m * g->nq;
@@ -563,6 +584,7 @@ static int interact(hist_t *h, int m, int vix, int viy, int viz, float pend_p[3]
   }
   /* gamma conversion */
   h->st.n_conv++;
+  rng_begin(&h->rng);
   if (g->pair_mode == 0) {
     /* production cuts >> range with apply_cuts: e-, e+ (and its 2 mc2) stay on the spot */
     deposit(h, h->E * h->w, m, vix, viy, viz);
@@ -824,7 +846,8 @@ static void run_photon(hist_t *h, float pend_p[3], float pend_d[3], int *pend) {
       for (int a = 0; a < 3; ++a) h->p[a] = h->p[a] + h->d[a] * step;
       h->path += step;
       if (ev == 0) {
-        alive = interact(h, g->world_mat, 0, 0, 0, pend_p, pend_d, pend);
+        int proc = select_process(h, g->world_mat, rng_uniform(&h->rng));
+        alive = interact(h, proc, g->world_mat, 0, 0, 0, pend_p, pend_d, pend);
       } else if (ev == 2) {
         h->st.steps++;
         to_phantom(h);
@@ -880,8 +903,10 @@ static void run_photon(hist_t *h, float pend_p[3], float pend_d[3], int *pend) {
         int m = g->label_bytes == 1 ? (int)((const uint8_t *)g->labels)[flat]
                                     : (int)((const uint16_t *)g->labels)[flat];
         float mu = tab(g->mu, g->ne, m, h->ie, h->fe);
-        if (u[2 * k + 1] * maj <= mu) {
-          alive = interact(h, m, ix, iy, iz, pend_p, pend_d, pend);
+        float t = u[2 * k + 1] * maj;
+        if (t <= mu) {
+          int proc = select_process(h, m, t / mu);
+          alive = interact(h, proc, m, ix, iy, iz, pend_p, pend_d, pend);
           break;
         }
       }

@@ -1,4 +1,8 @@
-for lib in "" opengate_b200/csrc/variant_t1024_s2048.so opengate_b200/csrc/variant_t256_s3072.so opengate_b200/csrc/variant_t512_s2048.so; do
-  echo "== lib=$lib"
-  for c in c3 c1; do env ${lib:+GATE_B200_LIB=$lib} timeout 120 python tools/profile_run.py --config $c --histories 20000000 --launches 2 | cut -c1-20,100-400; done
+#!/bin/bash
+# A/B timing of alternative builds of the C-ABI library (development aid):
+#   tools/ab_variants.sh "<lib1> <lib2> ..." "<configs>" [histories]
+libs=${1:-""}; cfgs=${2:-"c3 c1"}; n=${3:-20000000}
+for lib in "" $libs; do
+  echo "== lib=${lib:-default}"
+  for c in $cfgs; do env ${lib:+GATE_B200_LIB=$lib} timeout 120 python tools/profile_run.py --config $c --histories $n --launches 2 | cut -c1-24,100-400; done
 done

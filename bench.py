@@ -99,6 +99,18 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic_per_history(workload_key):
+    """DRAM bytes per history of the transport kernel from the committed `ncu --set full` capture
+    (profiles/traffic.json, written by tools/ncu_summary.py --traffic-json); None if absent."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        d = json.load(open(p))
+        e = d.get(workload_key)
+        return (float(e["dram_bytes_per_history"]), e.get("source")) if e else (None, None)
+    except Exception:
+        return None, None
+
+
 def algorithmic_bytes_per_history(st, label_bytes, n_grids, phsp_row_bytes=0):
     """B_hist = N_tent*s_label + N_flush*G*2*8 + f_out*s_rec  (SURVEY.md section 8d)."""
     n = max(st["histories"], 1)
@@ -183,7 +195,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c3")
-    ap.add_argument("--histories", type=int, default=100_000_000, help="histories per step per GPU")
+    ap.add_argument("--histories", type=int, default=200_000_000, help="histories per step per GPU")
     ap.add_argument("--e2e-histories", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -268,6 +280,7 @@ def main():
     kernel_ms = st["kernel_ms"] / max(args.steps, 1)
     achieved = b_hist * H / (kernel_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
+    t_hist, t_src = measured_traffic_per_history(args.config)
 
     line = None
     if rank == 0:
@@ -283,7 +296,8 @@ def main():
             "clocks": clocks,
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": (t_hist * H if t_hist else None), "traffic_source": t_src,
+                         "algorithmic_bytes_per_launch": b_hist * H, "peak_source": peak_src,
                          "kernel": "gb2::transport_kernel", "kernel_ms_per_launch": kernel_ms,
                          "bytes_per_history": b_hist, "tentative_collisions_per_history": n_tent,
                          "deposit_entries_per_history": n_dep, "phsp_rows_per_history": f_out,
@@ -310,26 +324,41 @@ def main():
 
 
 def measure_e2e(S, H, local, rank, world, torch, dist, steps=2):
-    from opengate_b200 import abi
+    """The same metric through the C-ABI from HOST buffers: every step creates an engine, uploads
+    the tables and the label volume from pinned host memory (H2D), runs H histories per GPU,
+    reduces the grids onto rank 0 (N > 1) and reads every active grid back into pinned host
+    memory (D2H).  Wall-clock around the whole sequence, max over ranks."""
+    import copy
+    from opengate_b200 import abi, multigpu
     from opengate_b200.core import Engine
     G = n_active_grids(S)
-    nvox = S.dose[0].size[0] * S.dose[0].size[1] * S.dose[0].size[2]
-    host_out = [np.empty((S.dose[0].size[2], S.dose[0].size[1], S.dose[0].size[0]), dtype=np.float64) for _ in range(G)]
-    which = [w for w, f in ((abi.GRID_EDEP, abi.SCORE_EDEP), (abi.GRID_EDEP_SQ, abi.SCORE_EDEP_SQ),
-                            (abi.GRID_DOSE, abi.SCORE_DOSE), (abi.GRID_DOSE_SQ, abi.SCORE_DOSE_SQ),
-                            (abi.GRID_COUNTS, abi.SCORE_COUNTS)) if (S.dose[0].score_flags | abi.SCORE_EDEP) & f]
+    nx, ny, nz = S.dose[0].size[0], S.dose[0].size[1], S.dose[0].size[2]
+    which = multigpu.active_grids(S.dose[0].score_flags)
+    host_out = [torch.empty((nz, ny, nx), dtype=torch.float64, pin_memory=True).numpy() for _ in range(G)] if rank == 0 else []
+    S = copy.copy(S)
+    pinned_labels = torch.empty(S.labels.shape, dtype=torch.uint8 if S.labels.dtype == np.uint8 else torch.int16, pin_memory=True)
+    lab = pinned_labels.numpy().view(S.labels.dtype)
+    lab[...] = S.labels
+    S.labels = lab
     t = S.tables
     h2d = S.labels.nbytes + sum(a.nbytes for a in (t.density, t.mu_total, t.cum_phot, t.cum_compt, t.cum_rayl,
                                                    t.rayl_cum_ff2, t.compt_sf))
-    d2h = G * nvox * 8
+    d2h = G * nx * ny * nz * 8
 
     def one(first):
         eng = Engine(local, S.seed)
         sids, dids, pids = S.apply(eng)       # H2D: tables + label volume (+ source CDFs)
         eng.begin_run()
         eng.run_source(sids[0], first, H)
-        for w, out in zip(which, host_out):   # D2H: every active accumulator grid
-            eng.dose_grid(dids[0], w, out)
+        if world > 1:
+            eng.sync()
+            multigpu.reduce_dose_grids(eng, dids, S, dst=0)
+            torch.cuda.synchronize()
+        if rank == 0:
+            for w, out in zip(which, host_out):   # D2H: every active accumulator grid
+                eng.dose_grid(dids[0], w, out)
+        else:
+            eng.sync()
         eng.close()
 
     one(rank * H)  # warm-up (page-in, allocator)
@@ -347,7 +376,8 @@ def measure_e2e(S, H, local, rank, world, torch, dist, steps=2):
     dt = float(tt.item())
     return {"value": world * H * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "histories_per_step_per_gpu": H, "steps": steps,
-            "what": "gate_b200 C-ABI from host buffers: create + set_tables + set_image_volume (H2D) + run + get_dose_grid of every grid (D2H) per step"}
+            "what": "gate_b200 C-ABI from pinned host buffers: create + set_tables + set_image_volume (H2D) + run"
+                    + (" + NCCL reduce to rank 0" if world > 1 else "") + " + get_dose_grid of every grid (D2H) per step"}
 
 
 if __name__ == "__main__":

@@ -132,3 +132,166 @@ def test_energy_conservation_full_size_property(cuda_required):
     assert st["edep_total_MeV"] == pytest.approx(200000 * 0.2, rel=1e-5)
     assert eng.dose_grid(0, abi.GRID_EDEP).sum() == pytest.approx(200000 * 0.2, rel=1e-5)
     eng.close()
+
+
+# ------------------------------------------------------------------------------ script level
+
+def test_script_level_ct_dose_matches_oracle(cuda_required, tmp_path):
+    """The drop-in layer on the CUDA engine: the same GATE-style script run with the product back end
+    and with the oracle back end gives the same DoseActor images (fp64 sums: order of additions)."""
+    import os
+    from test_host_api import ct_sim
+    from oracle_backend import OracleBackend
+    res = []
+    for backend, sub in ((None, "gpu"), (OracleBackend, "cpu")):
+        os.makedirs(tmp_path / sub, exist_ok=True)
+        sim, ct, src, dose, hu = ct_sim(tmp_path / sub, n_primaries=30000)
+        dose.dose.active = True
+        dose.dose_uncertainty.active = True
+        dose.edep_uncertainty.active = True
+        dose.counts.active = True
+        stats = sim.add_actor("SimulationStatisticsActor", "stats")
+        out = sim.run(_backend=backend)
+        res.append((dose, stats, out))
+    (dg, sg, og), (dc, sc, oc) = res
+    for k in ("histories", "tentative_collisions", "n_phot", "n_compt", "n_rayl", "deposits", "flushed_entries", "escaped"):
+        assert og.device_stats[0][k] == oc.device_stats[0][k], k
+    assert sg.counts["events"] == sc.counts["events"] == 30000 and sg.counts["steps"] == sc.counts["steps"]
+    for name in ("edep", "edep_uncertainty", "dose", "dose_uncertainty", "counts"):
+        a, b = getattr(dg, name).image.array, getattr(dc, name).image.array
+        assert np.array_equal(a != 0, b != 0), name
+        np.testing.assert_allclose(a, b, rtol=1e-9, atol=0, err_msg=name)
+    assert os.path.exists(dg.edep.get_output_path()) and os.path.exists(dg.dose_uncertainty.get_output_path())
+
+
+def test_script_level_voxel_source_phase_space(cuda_required, tmp_path):
+    import opengate_b200 as gate
+    from opengate_b200 import image as gimage
+    from test_host_api import ct_sim
+    from oracle_backend import OracleBackend
+    keV, mm = gate.g4_units.keV, gate.g4_units.mm
+    rows = []
+    for backend, sub in ((None, "gpu"), (OracleBackend, "cpu")):
+        (tmp_path / sub).mkdir(exist_ok=True)
+        sim, ct, src, dose, hu = ct_sim(tmp_path / sub)
+        sim.source_manager.sources.clear()
+        act = np.zeros((8, 10, 12), dtype=np.float32)
+        act[3:5, 4:6, 5:8] = 1.0
+        vs = sim.add_source("VoxelSource", "tc99m")
+        vs.attached_to = "ct"
+        vs.image = gimage.Image(act, (20.0, 20.0, 24.0))
+        vs.energy.mono = 140.511 * keV
+        vs.direction.type = "iso"
+        vs.number_of_primaries = 20000
+        plane = sim.add_volume("Box", "plane")
+        plane.size = [600 * mm, 2 * mm, 600 * mm]
+        plane.translation = [0, 300 * mm, 0]
+        ph = sim.add_actor("PhaseSpaceActor", "phsp")
+        ph.attached_to = plane
+        ph.attributes = ["KineticEnergy", "PrePosition", "PreDirection", "Weight", "EventID", "TimeFromBeginOfEvent"]
+        ph.store_absorbed_event = True
+        ph.write_to_disk = False
+        sim.run(_backend=backend)
+        rows.append(ph)
+    g, c = rows
+    assert g.total_number_of_entries == c.total_number_of_entries > 0
+    assert g.number_of_absorbed_events == c.number_of_absorbed_events
+    for k in g.data:
+        assert np.array_equal(g.data[k], c.data[k]), k
+
+
+# ------------------------------------------------------------------------------ BASELINE.json sizes
+
+@pytest.fixture(scope="module")
+def c3_full(cuda_required):
+    from opengate_b200 import setups
+    return setups.make_c3(n_primaries=4_000_000, flags=abi.SCORE_EDEP | abi.SCORE_EDEP_SQ | abi.SCORE_DOSE | abi.SCORE_COUNTS)
+
+
+def test_c3_full_size_properties(c3_full):
+    """512x512x300 CT, 75 materials (BASELINE.json config 3) at a size the oracle cannot be run at:
+    size-independent properties of the scoring.  (i) everything deposited inside the volume is in
+    the edep grid; (ii) dose = sum(e / rho(label at the deposit)): with dose grid == label grid,
+    dose * rho(label) == edep per voxel; (iii) counts are integers, and squares obey
+    sum(e^2) <= (sum e)^2 and >= (sum e)^2 / counts per voxel (Cauchy-Schwarz over the events)."""
+    from opengate_b200.core import Engine
+    S = c3_full
+    n = 4_000_000
+    eng = Engine(0, S.seed)
+    s, d, _ = S.apply(eng)
+    eng.begin_run()
+    eng.run_source(s[0], 0, n)
+    eng.sync()
+    st = eng.stats()
+    assert st["histories"] == n and st["buffer_overflows"] == 0
+    e = eng.dose_grid(0, abi.GRID_EDEP)
+    e2 = eng.dose_grid(0, abi.GRID_EDEP_SQ)
+    dose = eng.dose_grid(0, abi.GRID_DOSE)
+    cnt = eng.dose_grid(0, abi.GRID_COUNTS)
+    assert e.shape == (300, 512, 512)
+    # (i) the world is air: a little energy is deposited outside the volume
+    assert e.sum() <= st["edep_total_MeV"] * (1 + 1e-9) and e.sum() > 0.98 * st["edep_total_MeV"]
+    # (ii)
+    rho = S.tables.density.astype(np.float64)[S.labels]
+    m = e > 0
+    # (a deposit within one float ulp of a voxel face can be indexed into the neighbour voxel by the
+    # dose grid's own affine transform, as in the reference where both indices are computed
+    # independently: allow a 1e-5 fraction of such voxels)
+    bad = np.abs((dose * rho)[m] - e[m]) > 2e-6 * e[m]
+    assert bad.mean() < 1e-5, bad.sum()
+    # (iii)
+    assert np.array_equal(cnt, np.round(cnt)) and cnt.sum() == st["deposits"] - _deposits_outside(st, e, cnt)
+    assert np.all(e2[m] <= e[m] ** 2 * (1 + 1e-9))
+    assert np.all(e2[m] * cnt[m] >= e[m] ** 2 * (1 - 1e-9))
+    assert np.array_equal(m, cnt > 0) and np.array_equal(m, e2 > 0)
+    eng.close()
+
+
+def _deposits_outside(st, e, cnt):
+    # deposits in the world material (outside the image volume) are counted in the statistics only
+    return st["deposits"] - int(cnt.sum())
+
+
+def test_c3_full_size_linearity_and_sharding(c3_full):
+    """Two launches over disjoint history ranges add up to the launch over the union (what the
+    multi-GPU sharding relies on), at the full CT size."""
+    from opengate_b200.core import Engine
+    S = c3_full
+    a = Engine(0, S.seed)
+    sa, _, _ = S.apply(a)
+    a.begin_run()
+    a.run_source(sa[0], 0, 1_000_000)
+    a.sync()
+    whole = {w: a.dose_grid(0, w) for w in (abi.GRID_EDEP, abi.GRID_EDEP_SQ, abi.GRID_DOSE, abi.GRID_COUNTS)}
+    st_whole = a.stats()
+    a.begin_run()
+    a.run_source(sa[0], 0, 400_000)
+    a.sync()
+    p1 = {w: a.dose_grid(0, w) for w in whole}
+    a.begin_run()
+    a.run_source(sa[0], 400_000, 600_000)
+    a.sync()
+    st2 = a.stats()
+    for w in whole:
+        np.testing.assert_allclose(p1[w] + a.dose_grid(0, w), whole[w], rtol=1e-11, atol=0)
+    assert st2["histories"] == 600_000
+    a.close()
+    assert st_whole["histories"] == 1_000_000
+
+
+def test_c1_pencil_beam_same_voxel_aggregation(cuda_required):
+    """Pencil beam: every history deposits in the same voxel column, the warp-aggregated atomics
+    combine lanes that hit the same voxel; squares must still be per history."""
+    from opengate_b200 import setups
+    from opengate_b200.core import Engine
+    from oracle.oracle import TransportOracle
+    S = setups.make_c1(n_primaries=30000, grid=(3, 3, 2), spacing_mm=100.0, flags=abi.SCORE_EDEP | abi.SCORE_EDEP_SQ | abi.SCORE_COUNTS)
+    eng, orc = Engine(0, S.seed), TransportOracle(S.seed)
+    se, _, _ = S.apply(eng)
+    so, _, _ = S.apply(orc)
+    eng.begin_run(); orc.begin_run()
+    eng.run_source(se[0], 0, 30000); eng.sync()
+    orc.run_source(so[0], 0, 30000, 0)
+    for w in (abi.GRID_EDEP, abi.GRID_EDEP_SQ, abi.GRID_COUNTS):
+        np.testing.assert_allclose(eng.dose_grid(0, w), orc.dose_grid(0, w), rtol=1e-11)
+    eng.close()

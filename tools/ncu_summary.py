@@ -47,6 +47,8 @@ def main():
     ap.add_argument("--histories", type=float, default=0, help="histories in the profiled launch")
     ap.add_argument("--title", default="")
     ap.add_argument("--top", type=int, default=40)
+    ap.add_argument("--traffic-json", default="", help="update this json with dram bytes/history under --key")
+    ap.add_argument("--key", default="c3")
     a = ap.parse_args()
 
     raw = ncu_csv(a.rep, "raw")
@@ -68,6 +70,13 @@ def main():
             lines.append(f"| **traffic = dram read+write per launch** | {rd + wr:.4g} | byte |")
             if a.histories:
                 lines.append(f"| traffic per history ({a.histories:.3g} histories) | {(rd + wr) / a.histories:.1f} | byte |")
+                if a.traffic_json and li == 0:
+                    import json
+                    import os
+                    d = json.load(open(a.traffic_json)) if os.path.exists(a.traffic_json) else {}
+                    d[a.key] = {"dram_bytes_per_history": (rd + wr) / a.histories, "histories_in_capture": a.histories,
+                                "dram_read_bytes": rd, "dram_write_bytes": wr, "source": os.path.basename(a.out)}
+                    json.dump(d, open(a.traffic_json, "w"), indent=1)
         except Exception:
             pass
         lines.append("")

@@ -164,6 +164,29 @@ def test_script_level_ct_dose_matches_oracle(cuda_required, tmp_path):
     assert os.path.exists(dg.edep.get_output_path()) and os.path.exists(dg.dose_uncertainty.get_output_path())
 
 
+def test_script_level_rotated_volume_attached_source_coarse_dose_grid(cuda_required, tmp_path):
+    """Non-trivial frames: rotated + translated CT, source attached to it, dose grid with its own
+    spacing and translation, hit_type random: CUDA engine == oracle."""
+    from test_host_api import rotated_ct_sim
+    from oracle_backend import OracleBackend
+    res = []
+    for backend, sub in ((None, "gpu"), (OracleBackend, "cpu")):
+        (tmp_path / sub).mkdir(exist_ok=True)
+        sim, ct, src, dose, hu = rotated_ct_sim(tmp_path / sub, n_primaries=30000)
+        dose.dose.active = True
+        dose.edep_squared.active = True
+        dose.counts.active = True
+        out = sim.run(_backend=backend)
+        res.append((dose, out))
+    (dg, og), (dc, oc) = res
+    for k in ("histories", "tentative_collisions", "n_phot", "n_compt", "n_rayl", "deposits", "flushed_entries", "escaped", "steps"):
+        assert og.device_stats[0][k] == oc.device_stats[0][k], k
+    for name in ("edep", "edep_squared", "dose", "counts"):
+        a, b = getattr(dg, name).image.array, getattr(dc, name).image.array
+        assert a.sum() > 0
+        np.testing.assert_allclose(a, b, rtol=1e-9, atol=0, err_msg=name)
+
+
 def test_script_level_voxel_source_phase_space(cuda_required, tmp_path):
     import opengate_b200 as gate
     from opengate_b200 import image as gimage

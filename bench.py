@@ -195,7 +195,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c3")
-    ap.add_argument("--histories", type=int, default=200_000_000, help="histories per step per GPU")
+    ap.add_argument("--histories", type=int, default=500_000_000, help="histories per step per GPU")
     ap.add_argument("--e2e-histories", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "transport.cuh"
@@ -275,19 +276,34 @@ int gate_b200_set_image_volume(gate_b200_engine *h, const void *labels, int32_t 
   Params &P = h->P;
   const size_t nv = (size_t)size[0] * size[1] * size[2];
   if (nv == 0) return fail(h, GATE_B200_EINVAL, "empty image volume");
-  // materials present -> majorant (same rule as the oracle's build_majorant)
+  // materials present -> majorant (same rule as the oracle's build_majorant); the scan of the label
+  // volume is split over host threads (it is inside the end-to-end path of every run)
   std::vector<char> present(P.nmat, 0);
-  if (label_bytes == 1) {
-    const uint8_t *l = static_cast<const uint8_t *>(labels);
-    for (size_t i = 0; i < nv; ++i) {
-      if (l[i] >= P.nmat) return fail(h, GATE_B200_EINVAL, "label %d at voxel %zu has no material", (int)l[i], i);
-      present[l[i]] = 1;
-    }
-  } else {
-    const uint16_t *l = static_cast<const uint16_t *>(labels);
-    for (size_t i = 0; i < nv; ++i) {
-      if (l[i] >= P.nmat) return fail(h, GATE_B200_EINVAL, "label %d at voxel %zu has no material", (int)l[i], i);
-      present[l[i]] = 1;
+  {
+    const int nthreads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::vector<char>> part(nthreads, std::vector<char>(P.nmat, 0));
+    std::vector<long long> bad(nthreads, -1);
+    std::vector<std::thread> pool;
+    for (int tid = 0; tid < nthreads; ++tid)
+      pool.emplace_back([&, tid]() {
+        const size_t i0 = nv * (size_t)tid / nthreads, i1 = nv * (size_t)(tid + 1) / nthreads;
+        char *pr = part[tid].data();
+        if (label_bytes == 1) {
+          const uint8_t *l = static_cast<const uint8_t *>(labels);
+          for (size_t i = i0; i < i1; ++i) { if (l[i] >= P.nmat) { bad[tid] = (long long)i; break; } pr[l[i]] = 1; }
+        } else {
+          const uint16_t *l = static_cast<const uint16_t *>(labels);
+          for (size_t i = i0; i < i1; ++i) { if (l[i] >= P.nmat) { bad[tid] = (long long)i; break; } pr[l[i]] = 1; }
+        }
+      });
+    for (auto &t : pool) t.join();
+    for (int tid = 0; tid < nthreads; ++tid) {
+      if (bad[tid] >= 0) {
+        const size_t i = (size_t)bad[tid];
+        const int lab = label_bytes == 1 ? (int)static_cast<const uint8_t *>(labels)[i] : (int)static_cast<const uint16_t *>(labels)[i];
+        return fail(h, GATE_B200_EINVAL, "label %d at voxel %zu has no material", lab, i);
+      }
+      for (int m = 0; m < P.nmat; ++m) present[m] |= part[tid][m];
     }
   }
   std::vector<float> maj(P.ne, 0.f);

@@ -9,7 +9,7 @@ from opengate_b200 import abi
 
 pytestmark = pytest.mark.gpu
 
-from small_setups import SMALL, c1  # noqa: E402
+from small_setups import ALL_FLAGS, SMALL, c1  # noqa: E402
 
 INT_KEYS = ["histories", "tracks", "steps", "tentative_collisions", "n_phot", "n_compt", "n_rayl", "n_conv",
             "deposits", "flushed_entries", "buffer_overflows", "escaped", "phsp_rows", "phsp_dropped",
@@ -318,3 +318,115 @@ def test_c1_pencil_beam_same_voxel_aggregation(cuda_required):
     for w in (abi.GRID_EDEP, abi.GRID_EDEP_SQ, abi.GRID_COUNTS):
         np.testing.assert_allclose(eng.dose_grid(0, w), orc.dose_grid(0, w), rtol=1e-11)
     eng.close()
+
+
+# ------------------------------------------------------------------------------ edge cases
+
+def _both(S, n, first=0, source=0):
+    from opengate_b200.core import Engine
+    from oracle.oracle import TransportOracle
+    eng, orc = Engine(0, S.seed), TransportOracle(S.seed)
+    ie, io = S.apply(eng), S.apply(orc)
+    eng.begin_run(); orc.begin_run()
+    return eng, orc, ie, io
+
+
+def test_zero_and_tiny_history_counts(cuda_required):
+    """Empty and ragged inputs: 0 histories is a no-op, 1 and 33 histories (less than a warp, one
+    more than a warp) run and match."""
+    S = SMALL["c3"](100)
+    for n in (0, 1, 33):
+        eng, orc, (se, de, pe), (so, do, po) = _both(S, n)
+        eng.run_source(se[0], 7, n); eng.sync()
+        if n:
+            orc.run_source(so[0], 7, n, 0)
+        a, b = eng.stats(), orc.stats()
+        assert a["histories"] == n == b["histories"]
+        for k in INT_KEYS:
+            assert a[k] == b[k], (n, k)
+        np.testing.assert_allclose(eng.dose_grid(0, abi.GRID_EDEP), orc.dose_grid(0, abi.GRID_EDEP), rtol=1e-12)
+        eng.close()
+
+
+def test_uint16_label_volume(cuda_required):
+    """The reference's label type is unsigned short (GateImageNestedParameterisation.h:24); the
+    engine takes uint16 volumes as they are (uint8 is only a packing used when <= 256 materials)."""
+    S = SMALL["c3"](8000)
+    S.labels = S.labels.astype(np.uint16)
+    eng, orc, ids = run_both(S, 8000)
+    compare(eng, orc, S, ids)
+    eng.close()
+
+
+def test_two_dose_actors_two_sources_and_exiting_phase_space(cuda_required):
+    """Several actors and sources in one engine: a fine and a coarse dose grid (different hit types),
+    a second source, phase-space rows on entering AND exiting."""
+    from opengate_b200 import setups
+    S = SMALL["c4"](6000)
+    nx, ny, nz = S.labels.shape[::-1]
+    A2 = setups.dose_world_to_index((5, 4, 3), (100.0, 120.0, 90.0), translation=(10.0, -20.0, 5.0))
+    S.dose.append(abi.make_dose_desc((5, 4, 3), A2, ALL_FLAGS, abi.HIT_RANDOM))
+    s2, keep2 = abi.make_source(pos_type=abi.POS_SPHERE, radius=30.0, pos_translation=(0, -300.0, 0), dir_type=abi.DIR_FOCUSED,
+                                focus_point=(0, 0, 0), ene_type=abi.ENE_GAUSS, mono=0.08, sigma=0.005)
+    S.sources.append((s2, keep2))
+    S.phsp[0].steps_to_store = abi.PHSP_ENTERING | abi.PHSP_EXITING
+    from opengate_b200.core import Engine
+    from oracle.oracle import TransportOracle
+    eng, orc = Engine(0, S.seed), TransportOracle(S.seed)
+    se, de, pe = S.apply(eng)
+    so, do, po = S.apply(orc)
+    eng.begin_run(); orc.begin_run()
+    eng.run_source(se[0], 0, 6000); eng.run_source(se[1], 6000, 4000); eng.sync()
+    orc.run_source(so[0], 0, 6000, 0); orc.run_source(so[1], 6000, 4000, 0)
+    compare(eng, orc, S, (se, de, pe))
+    rows = eng.phsp(pe[0])
+    assert set(np.unique(rows["Flags"])) == {abi.PHSP_ENTERING, abi.PHSP_EXITING}
+    assert rows["EventID"].max() >= 6000          # rows of the second source carry its history ids
+    eng.close()
+
+
+def test_phase_space_capacity_overflow_is_counted_not_written(cuda_required):
+    S = SMALL["c4"](20000)
+    S.phsp[0].capacity = 50
+    eng, orc, ids = run_both(S, 20000)
+    a, b = eng.stats(), orc.stats()
+    assert a["phsp_rows"] == 50 == b["phsp_rows"] and a["phsp_dropped"] == b["phsp_dropped"] > 0
+    assert len(eng.phsp(ids[2][0])["EventID"]) == 50
+    eng.close()
+
+
+def test_energy_source_types_and_positions(cuda_required):
+    """Every position / direction / energy sampler of the source ABI against the oracle."""
+    base = SMALL["c1"](10)
+    edges = np.array([0.02, 0.04, 0.07, 0.1, 0.15])
+    w = np.array([1.0, 3.0, 2.0, 0.5])
+    from opengate_b200.setups import histogram_cdf
+    cdf_lin = np.cumsum(w + 0.1)
+    variants = [
+        dict(pos_type=abi.POS_BOX, half_size=(20, 10, 5), ene_type=abi.ENE_RANGE, e_min=0.05, e_max=0.3),
+        dict(pos_type=abi.POS_SPHERE, radius=25.0, ene_type=abi.ENE_GAUSS, mono=0.3, sigma=0.02),
+        dict(pos_type=abi.POS_DISC, radius=15.0, sigma_x=2.0, sigma_y=3.0, ene_type=abi.ENE_SPECTRUM_DISCRETE,
+             spectrum_energy=np.array([0.08, 0.14, 0.36]), spectrum_cdf=np.array([0.2, 0.9, 1.0])),
+        dict(pos_type=abi.POS_CYLINDER, radius=10.0, half_size=(0, 0, 30.0), ene_type=abi.ENE_SPECTRUM_HISTOGRAM,
+             spectrum_energy=edges, spectrum_cdf=histogram_cdf(edges, w)),
+        dict(pos_type=abi.POS_POINT, ene_type=abi.ENE_SPECTRUM_HISTOGRAM_LINEAR, spectrum_energy=edges,
+             spectrum_cdf=cdf_lin / cdf_lin[-1]),
+        dict(pos_type=abi.POS_POINT, ene_type=abi.ENE_CDF, spectrum_energy=np.array([0.05, 0.1, 0.2, 0.4]),
+             spectrum_cdf=np.array([0.0, 0.3, 0.8, 1.0])),
+    ]
+    rot = np.array([[0.0, 0.0, -1.0], [0.0, 1.0, 0.0], [1.0, 0.0, 0.0]])
+    dirs = [dict(dir_type=abi.DIR_ISO), dict(dir_type=abi.DIR_MOMENTUM, momentum=(0.1, 0.2, 1.0)),
+            dict(dir_type=abi.DIR_FOCUSED, focus_point=(5.0, -5.0, 100.0)),
+            dict(dir_type=abi.DIR_ISO, theta=(0.1, 0.6), phi=(0.5, 2.0), dir_relative=True, dir_rotation=rot)]
+    for i, v in enumerate(variants):
+        kw = dict(v)
+        kw.update(dirs[i % len(dirs)])
+        kw.setdefault("pos_translation", (3.0, -4.0, -200.0))
+        s, keep = abi.make_source(**kw)
+        S = SMALL["c1"](10)
+        S.tables = base.tables
+        S.sources = [(s, keep)]
+        eng, orc, ids = run_both(S, 4000)
+        compare(eng, orc, S, ids)
+        assert eng.stats()["histories"] == 4000
+        eng.close()

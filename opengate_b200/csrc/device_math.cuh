@@ -1,7 +1,8 @@
 // device_math.cuh — the arithmetic contract of the transport kernel.
 //
-// Only IEEE single-precision +,-,*,/ and sqrt are used (the file is compiled with
-// -fmad=false, so nvcc never contracts a*b+c into an FMA); logarithm, exponential and
+// Only IEEE single-precision +,-,*,/, sqrt and the fused multiply-add where __fmaf_rn is written
+// (the file is compiled with -fmad=false, so nvcc never contracts a*b+c on its own: an FMA is
+// part of the specification, the oracle writes fmaf() at the same places); logarithm, exponential and
 // sin/cos are the polynomials below, not the CUDA math library, so that a scalar CPU
 // implementation of the same formulas (oracle/transport_oracle.c) reproduces every history
 // bit for bit.
@@ -13,27 +14,28 @@ namespace gb2 {
 __device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
 __device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }
 
-// natural logarithm: x = m 2^k, m in [sqrt(1/2), sqrt(2)); log(m) by the classic
-// s = f/(2+f) series with a degree-4 minimax polynomial in s^2 (FreeBSD msun e_logf.c).
+// natural logarithm: x = m 2^k, m in [sqrt(1/2), sqrt(2)); log(m) = f - f^2/2 + f^3 P(f), f = m - 1,
+// P of degree 8 (fitted by tools/fit_log_poly.py, < 0.8 ulp), Horner with fused multiply-adds:
+// no division, 22 instructions.
 __device__ __forceinline__ float d_logf(float x) {
   const float ln2_hi = 6.9313812256e-01f, ln2_lo = 9.0580006145e-06f;
-  const float Lg1 = 0.66666662693f, Lg2 = 0.40000972152f, Lg3 = 0.28498786688f,
-              Lg4 = 0.24279078841f;
+  const float c0 = 0.3333331048488617f, c1 = -0.24999986588954926f, c2 = 0.20002226531505585f,
+              c3 = -0.16669249534606934f, c4 = 0.14218655228614807f, c5 = -0.12384366989135742f,
+              c6 = 0.1187300980091095f, c7 = -0.1178971379995346f, c8 = 0.06915182620286942f;
   uint32_t ix = f2u(x);
   ix += 0x3f800000u - 0x3f3504f3u;
   int k = (int)(ix >> 23) - 0x7f;
   ix = (ix & 0x007fffffu) + 0x3f3504f3u;
-  float m = u2f(ix);
-  float f = m - 1.0f;
-  float s = f / (2.0f + f);
-  float z = s * s;
-  float w = z * z;
-  float t1 = w * (Lg2 + w * Lg4);
-  float t2 = z * (Lg1 + w * Lg3);
-  float R = t2 + t1;
-  float hfsq = 0.5f * f * f;
+  float f = u2f(ix) - 1.0f;
+  float p = c8;
+  p = __fmaf_rn(p, f, c7); p = __fmaf_rn(p, f, c6); p = __fmaf_rn(p, f, c5); p = __fmaf_rn(p, f, c4);
+  p = __fmaf_rn(p, f, c3); p = __fmaf_rn(p, f, c2); p = __fmaf_rn(p, f, c1); p = __fmaf_rn(p, f, c0);
+  float z = f * f;
   float dk = (float)k;
-  return s * (hfsq + R) + dk * ln2_lo - hfsq + f + dk * ln2_hi;
+  float y = (f * z) * p;
+  y = __fmaf_rn(dk, ln2_lo, y);
+  y = __fmaf_rn(-0.5f, z, y);
+  return __fmaf_rn(dk, ln2_hi, f + y);
 }
 
 // exp(x) for moderate |x|: x = n ln2 + r, degree-6 Taylor polynomial in r, scale by 2^n.
@@ -123,7 +125,8 @@ __device__ __forceinline__ void philox_block2(uint32_t k0, uint32_t k1, uint32_t
 
 __device__ __forceinline__ float u32_to_uniform(uint32_t x) {
   // uniform in (0,1): the top 24 bits, centred in their bin
-  return (float)(x >> 8) * 5.9604644775390625e-8f + 2.98023223876953125e-8f;
+  // (the product is exact, so the fused form rounds once exactly like multiply-then-add)
+  return __fmaf_rn((float)(x >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f);
 }
 
 __device__ __forceinline__ void rng_init(Rng &r, uint64_t seed, uint64_t hist, uint32_t blk) {

@@ -276,6 +276,7 @@ int gate_b200_set_image_volume(gate_b200_engine *h, const void *labels, int32_t 
   Params &P = h->P;
   const size_t nv = (size_t)size[0] * size[1] * size[2];
   if (nv == 0) return fail(h, GATE_B200_EINVAL, "empty image volume");
+  if (nv >= (1ull << 31)) return fail(h, GATE_B200_EINVAL, "image volume must have fewer than 2^31 voxels");
   // materials present -> majorant (same rule as the oracle's build_majorant); the scan of the label
   // volume is split over host threads (it is inside the end-to-end path of every run)
   std::vector<char> present(P.nmat, 0);
@@ -323,6 +324,7 @@ int gate_b200_set_image_volume(gate_b200_engine *h, const void *labels, int32_t 
     P.n[a] = size[a];
     P.sp[a] = (float)spacing[a];
     P.inv_sp[a] = (float)(1.0 / spacing[a]);
+    P.hs[a] = (float)(0.5 * size[a]);
     P.half[a] = (float)(0.5 * size[a] * spacing[a]);
   }
   affine_from_double(P.w2v, world_to_volume);

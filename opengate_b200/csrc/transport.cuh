@@ -36,6 +36,10 @@ namespace gb2 {
 constexpr int kThreads = GB2_THREADS;
 constexpr int kSlots = GB2_SLOTS;          // photon slots per CTA (< 65535: queue cells are 16 bit)
 constexpr int kWoodcockK = 4;              // tentative collisions per Woodcock call (2 Philox blocks)
+#ifndef GB2_VWIDTH
+#define GB2_VWIDTH 1
+#endif
+constexpr int kVWidth = GB2_VWIDTH;        // slots one lane carries through a Woodcock call
 constexpr int kMaxDose = 4;
 constexpr int kMaxPhsp = 4;
 constexpr int kDepBuf = 32;                // per-history coalescing buffer entries
@@ -103,7 +107,7 @@ struct Params {
   int world_mat;
   int has_vol;
   int n[3];
-  float half[3], inv_sp[3], sp[3];
+  float half[3], inv_sp[3], sp[3], hs[3];   // hs = n / 2: voxel coordinate = p * inv_sp + hs
   Affine w2v;
   const void *labels;
   int ndose;
@@ -253,7 +257,7 @@ __device__ __forceinline__ void st_dep(DepEntry *p, const DepEntry &e) {
 
 __device__ __forceinline__ float tab_mu(const Params &P, int m, int ie, float fe) {
   const float2 v = __ldg(P.mu2 + (size_t)ie * P.nmat + m);
-  return v.x + fe * (v.y - v.x);
+  return __fmaf_rn(fe, v.y - v.x, v.x);
 }
 
 // opportunistic warp aggregation of a statistics increment (the lanes that arrive together)
@@ -261,6 +265,24 @@ __device__ __forceinline__ void stat_add(Smem &S, int idx, unsigned v) {
   const unsigned act = __activemask();
   const unsigned sum = __reduce_add_sync(act, v);
   if ((int)(threadIdx.x & 31u) == __ffs(act) - 1 && sum) atomicAdd(&S.stats[idx], (unsigned long long)sum);
+}
+// Several small per-lane event counts of one phase call packed into bit fields of one word: ONE warp
+// reduction for all of them (a field of `bits` bits holds the sum over 32 lanes, so every per-lane
+// count must stay below 2^bits / 32).  Returns the packed sums on the leader lane, 0 elsewhere.
+__device__ __forceinline__ unsigned stat_reduce_packed(unsigned packed) {
+  const unsigned act = __activemask();
+  const unsigned sum = __reduce_add_sync(act, packed);
+  return (int)(threadIdx.x & 31u) == __ffs(act) - 1 ? sum : 0u;
+}
+__device__ __forceinline__ void stat_bump(Smem &S, int idx, unsigned v) {
+  if (v) atomicAdd(&S.stats[idx], (unsigned long long)v);
+}
+// the rare part of a deposit's bookkeeping: coalescing-buffer overflows
+__device__ __forceinline__ void stat_overflow(Smem &S, unsigned over, unsigned flush) {
+  if (__any_sync(__activemask(), over != 0u)) {
+    stat_add(S, S_OVER, over);
+    stat_add(S, S_FLUSH, flush);
+  }
 }
 
 __device__ __forceinline__ void energy_bin_t(const Params &P, float E, float &t) {
@@ -474,9 +496,9 @@ __device__ __noinline__ float interp_q2(const Params &P, const float *__restrict
 __device__ __forceinline__ int route_interaction(const Params &P, unsigned &flags, int m, int ie, float fe, float v) {
   const float4 pa = __ldg(P.prob + (size_t)ie * P.nmat + m);
   const float4 pb = __ldg(P.prob + (size_t)(ie + 1) * P.nmat + m);
-  const float pph = pa.x + fe * (pb.x - pa.x);
-  const float pco = pa.y + fe * (pb.y - pa.y);
-  const float pra = pa.z + fe * (pb.z - pa.z);
+  const float pph = __fmaf_rn(fe, pb.x - pa.x, pa.x);
+  const float pco = __fmaf_rn(fe, pb.y - pa.y, pa.y);
+  const float pra = __fmaf_rn(fe, pb.z - pa.z, pa.z);
   flags &= ~(F_ABSORB | F_CONV);
   if (v < pph) { flags |= F_ABSORB; return Q_E; }                  // photoelectric: kerma, dies
   if (v < pco) return Q_C;
@@ -774,8 +796,11 @@ __device__ __noinline__ int phase_world(const Params &P, Smem &S, int slot) {
     }
   }
   store_ph(S, slot, g);
-  stat_add(S, S_ESC, n_esc);
-  stat_add(S, S_STEPS, n_steps);
+  {
+    const unsigned t = stat_reduce_packed(n_esc | (n_steps << 8));
+    stat_bump(S, S_ESC, t & 0xffu);
+    stat_bump(S, S_STEPS, t >> 8);
+  }
   return next;
 }
 
@@ -785,51 +810,72 @@ __device__ __noinline__ int phase_world(const Params &P, Smem &S, int slot) {
 // not on the outcome of the earlier iterations), so the dependent global loads of the iterations
 // overlap; the accept / leave decisions are then taken in order.  Arithmetic and order of the
 // floating-point operations are those of the sequential statement in the oracle.
+// The call is split into three stages (gather labels / gather attenuation / decide) so that one lane
+// can run them for kVWidth slots side by side: kVWidth * kWoodcockK independent gathers in flight per
+// thread, which is what hides the DRAM/L2 latency at 32 warps per SM.
+struct VCall {
+  float s[kWoodcockK];          // flight lengths
+  uint32_t racc[kWoodcockK];    // acceptance variates (raw Philox words)
+  int lab[kWoodcockK];          // labels at the tentative collision points
+  float mu[kWoodcockK];
+  unsigned inb;                 // bit k: point k is inside the volume
+  unsigned blk;
+  int ie;
+  float fe, maj;
+};
+
 template <typename LabelT>
-__device__ __forceinline__ int phase_volume(const Params &P, Smem &S, const float *__restrict__ s_maj, int slot,
-                                            unsigned &c_tent) {
-  const unsigned blk = S.blk[slot];
-  if (blk > kMaxBlocks) return Q_E;
-  S.blk[slot] = blk + 2u;
-  float p0 = S.px[slot], p1 = S.py[slot], p2 = S.pz[slot];
+__device__ __forceinline__ void volume_gather_labels(const Params &P, const Smem &S, const float *__restrict__ s_maj,
+                                                     int slot, VCall &c) {
+  c.blk = S.blk[slot];
+  float a0 = S.px[slot], a1 = S.py[slot], a2 = S.pz[slot];
   const float d0 = S.dx[slot], d1 = S.dy[slot], d2 = S.dz[slot];
-  int ie; float fe;
-  bin_split(P, S.tbin[slot], ie, fe);
-  const float m0 = s_maj[ie], m1 = s_maj[ie + 1];
-  const float maj = m0 + fe * (m1 - m0);
-  const float inv_maj = 1.0f / maj;
+  bin_split(P, S.tbin[slot], c.ie, c.fe);
+  const float m0 = s_maj[c.ie], m1 = s_maj[c.ie + 1];
+  c.maj = __fmaf_rn(c.fe, m1 - m0, m0);
+  const float inv_maj = 1.0f / c.maj;
   uint32_t r[2 * kWoodcockK];
   {
     const unsigned long long id = P.first + S.hidx[slot];
-    philox_block2((uint32_t)P.seed, (uint32_t)(P.seed >> 32), (uint32_t)id, (uint32_t)(id >> 32), blk, r);
+    philox_block2((uint32_t)P.seed, (uint32_t)(P.seed >> 32), (uint32_t)id, (uint32_t)(id >> 32), c.blk, r);
   }
-  float s[kWoodcockK], q0[kWoodcockK], q1[kWoodcockK], q2[kWoodcockK], mu[kWoodcockK];
-  bool inb[kWoodcockK];
-  int lab[kWoodcockK];
   const LabelT *__restrict__ labels = reinterpret_cast<const LabelT *>(P.labels);
-  const float2 *__restrict__ murow = P.mu2 + (size_t)ie * P.nmat;
-  {
-    float a0 = p0, a1 = p1, a2 = p2;
+  c.inb = 0u;
 #pragma unroll
-    for (int k = 0; k < kWoodcockK; ++k) {
-      s[k] = -d_logf(u32_to_uniform(r[2 * k])) * inv_maj;
-      a0 = a0 + d0 * s[k]; a1 = a1 + d1 * s[k]; a2 = a2 + d2 * s[k];
-      q0[k] = a0; q1[k] = a1; q2[k] = a2;
-      const float fx = (a0 + P.half[0]) * P.inv_sp[0];
-      const float fy = (a1 + P.half[1]) * P.inv_sp[1];
-      const float fz = (a2 + P.half[2]) * P.inv_sp[2];
-      inb[k] = !(fx < 0.0f || fy < 0.0f || fz < 0.0f || fx >= (float)P.n[0] || fy >= (float)P.n[1] ||
-                 fz >= (float)P.n[2]);
-      size_t flat = 0;
-      if (inb[k]) flat = (size_t)(int)fx + (size_t)P.n[0] * ((size_t)(int)fy + (size_t)P.n[1] * (size_t)(int)fz);
-      lab[k] = (int)__ldg(labels + flat);
+  for (int k = 0; k < kWoodcockK; ++k) {
+    c.s[k] = -d_logf(u32_to_uniform(r[2 * k])) * inv_maj;
+    c.racc[k] = r[2 * k + 1];
+    a0 = __fmaf_rn(d0, c.s[k], a0); a1 = __fmaf_rn(d1, c.s[k], a1); a2 = __fmaf_rn(d2, c.s[k], a2);
+    // continuous voxel coordinate: a / spacing + n / 2 in one fused operation
+    const float fx = __fmaf_rn(a0, P.inv_sp[0], P.hs[0]);
+    const float fy = __fmaf_rn(a1, P.inv_sp[1], P.hs[1]);
+    const float fz = __fmaf_rn(a2, P.inv_sp[2], P.hs[2]);
+    // 0 <= f < n  <=>  0 <= floor(f) < n; inside, floor(f) is the voxel index (int)f of the oracle
+    const int ix = __float2int_rd(fx), iy = __float2int_rd(fy), iz = __float2int_rd(fz);
+    const bool in = (unsigned)ix < (unsigned)P.n[0] && (unsigned)iy < (unsigned)P.n[1] && (unsigned)iz < (unsigned)P.n[2];
+    unsigned flat = 0;   // the ABI bounds the volume to < 2^31 voxels
+    if (in) {
+      flat = (unsigned)ix + (unsigned)P.n[0] * ((unsigned)iy + (unsigned)P.n[1] * (unsigned)iz);
+      c.inb |= 1u << k;
     }
-#pragma unroll
-    for (int k = 0; k < kWoodcockK; ++k) {
-      const float2 v = __ldg(murow + lab[k]);
-      mu[k] = v.x + fe * (v.y - v.x);
-    }
+    c.lab[k] = (int)__ldg(labels + flat);
   }
+}
+
+__device__ __forceinline__ void volume_gather_mu(const Params &P, VCall &c) {
+  const float2 *__restrict__ murow = P.mu2 + (size_t)c.ie * P.nmat;
+#pragma unroll
+  for (int k = 0; k < kWoodcockK; ++k) {
+    const float2 v = __ldg(murow + c.lab[k]);
+    c.mu[k] = __fmaf_rn(c.fe, v.y - v.x, v.x);
+  }
+}
+
+__device__ __forceinline__ int volume_decide(const Params &P, Smem &S, int slot, const VCall &c, unsigned &c_tent) {
+  if (c.blk > kMaxBlocks) return Q_E;
+  S.blk[slot] = c.blk + 2u;
+  float p0 = S.px[slot], p1 = S.py[slot], p2 = S.pz[slot];
+  const float d0 = S.dx[slot], d1 = S.dy[slot], d2 = S.dz[slot];
   float path = S.path[slot], seg = S.seg[slot];
   int mat = 0;
   float vsel = 0.0f;
@@ -838,15 +884,16 @@ __device__ __forceinline__ int phase_volume(const Params &P, Smem &S, const floa
 #pragma unroll
   for (int k = 0; k < kWoodcockK; ++k) {
     if (hit || left) continue;
-    if (!inb[k]) { left = true; continue; }
-    p0 = q0[k]; p1 = q1[k]; p2 = q2[k];
-    path += s[k];
-    seg += s[k];
+    if (!(c.inb & (1u << k))) { left = true; continue; }
+    // the same sequence of operations that produced the gather address
+    p0 = __fmaf_rn(d0, c.s[k], p0); p1 = __fmaf_rn(d1, c.s[k], p1); p2 = __fmaf_rn(d2, c.s[k], p2);
+    path += c.s[k];
+    seg += c.s[k];
     tent++;
-    const float t = u32_to_uniform(r[2 * k + 1]) * maj;
-    if (t <= mu[k]) {       // accepted: a real interaction in material lab[k]
-      mat = lab[k];
-      vsel = t / mu[k];
+    const float t = u32_to_uniform(c.racc[k]) * c.maj;
+    if (t <= c.mu[k]) {       // accepted: a real interaction in material lab[k]
+      mat = c.lab[k];
+      vsel = t / c.mu[k];
       hit = true;
     }
   }
@@ -859,7 +906,7 @@ __device__ __forceinline__ int phase_volume(const Params &P, Smem &S, const floa
     next = Q_W;
   } else if (hit) {
     unsigned flags = (S.fm[slot] & F_MASK) | F_INVOL;
-    next = route_interaction(P, flags, mat, ie, fe, vsel);
+    next = route_interaction(P, flags, mat, c.ie, c.fe, vsel);
     S.fm[slot] = flags | ((unsigned)mat << F_MAT_SHIFT);
   }
   return next;
@@ -932,11 +979,13 @@ __device__ __noinline__ int phase_compton(const Params &P, Smem &S, int slot, in
     store_ph(S, slot, g);
     c_edep += ds.edep;
   }
-  stat_add(S, S_COMPT, n_compt);
-  stat_add(S, S_STEPS, n_compt);
-  stat_add(S, S_DEP, ds.dep);
-  stat_add(S, S_OVER, ds.over);
-  stat_add(S, S_FLUSH, ds.flush);
+  {
+    const unsigned t = stat_reduce_packed(n_compt | (ds.dep << 8));
+    stat_bump(S, S_COMPT, t & 0xffu);
+    stat_bump(S, S_STEPS, t & 0xffu);
+    stat_bump(S, S_DEP, t >> 8);
+  }
+  stat_overflow(S, ds.over, ds.flush);
   return next;
 }
 
@@ -1010,13 +1059,16 @@ __device__ __noinline__ int phase_rare(const Params &P, Smem &S, int slot, int g
   }
   store_ph(S, slot, g);
   c_edep += ds.edep;
-  stat_add(S, S_RAYL, n_rayl);
-  stat_add(S, S_CONV, n_conv);
-  stat_add(S, S_TRACKS, 2u * n_conv);
-  stat_add(S, S_STEPS, n_rayl + n_conv);
-  stat_add(S, S_DEP, ds.dep);
-  stat_add(S, S_OVER, ds.over);
-  stat_add(S, S_FLUSH, ds.flush);
+  {
+    const unsigned t = stat_reduce_packed(n_rayl | (n_conv << 8) | (ds.dep << 16));
+    const unsigned tr = t & 0xffu, tc = (t >> 8) & 0xffu;
+    stat_bump(S, S_RAYL, tr);
+    stat_bump(S, S_CONV, tc);
+    stat_bump(S, S_TRACKS, 2u * tc);
+    stat_bump(S, S_STEPS, tr + tc);
+    stat_bump(S, S_DEP, t >> 16);
+  }
+  stat_overflow(S, ds.over, ds.flush);
   return in_vol ? Q_V : Q_W;
 }
 
@@ -1091,15 +1143,20 @@ __device__ __noinline__ int phase_end(const Params &P, Smem &S, int slot, int gs
       store_ph(S, slot, g);
     }
   }
-  stat_add(S, S_FLUSH, n_flush + ds.flush);
-  stat_add(S, S_ABSORBED, n_abs);
-  stat_add(S, S_HIST, n_hist);
-  stat_add(S, S_TRACKS, n_hist);
-  stat_add(S, S_PHOT, n_phot);
-  stat_add(S, S_CONV, n_conv);
-  stat_add(S, S_STEPS, n_phot + n_conv);
-  stat_add(S, S_DEP, ds.dep);
-  stat_add(S, S_OVER, ds.over);
+  stat_add(S, S_FLUSH, n_flush);
+  {
+    // five 6-bit fields: every count is 0 or 1 per lane
+    const unsigned t = stat_reduce_packed(n_abs | (n_hist << 6) | (n_phot << 12) | (n_conv << 18) | (ds.dep << 24));
+    const unsigned th = (t >> 6) & 63u, tp = (t >> 12) & 63u, tc = (t >> 18) & 63u;
+    stat_bump(S, S_ABSORBED, t & 63u);
+    stat_bump(S, S_HIST, th);
+    stat_bump(S, S_TRACKS, th);
+    stat_bump(S, S_PHOT, tp);
+    stat_bump(S, S_CONV, tc);
+    stat_bump(S, S_STEPS, tp + tc);
+    stat_bump(S, S_DEP, t >> 24);
+  }
+  stat_overflow(S, ds.over, ds.flush);
   return next;
 }
 
@@ -1134,7 +1191,8 @@ __global__ void __launch_bounds__(kThreads, 1) transport_kernel(const __grid_con
   const int slot_base = blockIdx.x * kSlots;
 
   for (;;) {
-    // ---- claim up to 32 slots that wait for the same phase (lane 0 negotiates with the queues).
+    // ---- claim slots that wait for the same phase (lane 0 negotiates with the queues): up to 32,
+    // or up to 32 * kVWidth for the Woodcock phase, where every lane carries kVWidth slots.
     // The CTA drains ONE queue at a time (S.cur): all warps run the same code, which keeps the
     // instruction working set of the SM at one phase instead of the whole kernel.  When the current
     // queue cannot fill a warp any more, the warp that notices moves the CTA to the fullest queue.
@@ -1151,7 +1209,8 @@ __global__ void __launch_bounds__(kThreads, 1) transport_kernel(const __grid_con
           }
         }
         if (best >= 32 || (best > 0 && polls >= 2)) {
-          const int want = best < 32 ? best : 32;
+          const int cap = bq == Q_V ? 32 * kVWidth : 32;
+          const int want = best < cap ? best : cap;
           const int old = atomicSub(&S.avail[bq], want);
           const int g = old < want ? (old > 0 ? old : 0) : want;
           if (g < want) atomicAdd(&S.avail[bq], want - g);
@@ -1172,50 +1231,62 @@ __global__ void __launch_bounds__(kThreads, 1) transport_kernel(const __grid_con
     got = __shfl_sync(FULL, got, 0);
     base = __shfl_sync(FULL, base, 0);
     polls = 0;
-    int slot = -1;
-    if ((int)lane < got) {
-      unsigned short *c = &S.cell[q][(unsigned)(base + (int)lane) % (unsigned)kSlots];
-      unsigned v;
-      while ((v = ld_cell(c)) == kEmpty) { }
-      st_cell(c, kEmpty);
-      slot = (int)v;
+    int slot[kVWidth], next[kVWidth];    // next = -3: this lane holds no slot in that column
+#pragma unroll
+    for (int w = 0; w < kVWidth; ++w) {
+      slot[w] = -1;
+      next[w] = -3;
+      if (32 * w + (int)lane < got) {
+        unsigned short *c = &S.cell[q][(unsigned)(base + 32 * w + (int)lane) % (unsigned)kSlots];
+        unsigned v;
+        while ((v = ld_cell(c)) == kEmpty) { }
+        st_cell(c, kEmpty);
+        slot[w] = (int)v;
+      }
     }
     __threadfence_block();
 
     // ---- run the phase for all claimed slots
-    int next = -3;     // -3: this lane holds no slot
-    if (slot >= 0) {
-      if (q == Q_V) next = phase_volume<LabelT>(P, S, s_maj, slot, c_tent);
-      else if (q == Q_C) next = phase_compton(P, S, slot, slot_base + slot, c_edep);
-      else if (q == Q_E) next = phase_end(P, S, slot, slot_base + slot, c_edep);
-      else if (q == Q_W) next = phase_world(P, S, slot);
-      else next = phase_rare(P, S, slot, slot_base + slot, c_edep);
+    if (q == Q_V) {
+      VCall vc[kVWidth];
+#pragma unroll
+      for (int w = 0; w < kVWidth; ++w)
+        if (slot[w] >= 0) volume_gather_labels<LabelT>(P, S, s_maj, slot[w], vc[w]);
+#pragma unroll
+      for (int w = 0; w < kVWidth; ++w)
+        if (slot[w] >= 0) volume_gather_mu(P, vc[w]);
+#pragma unroll
+      for (int w = 0; w < kVWidth; ++w)
+        if (slot[w] >= 0) next[w] = volume_decide(P, S, slot[w], vc[w], c_tent);
+    } else if (slot[0] >= 0) {
+      if (q == Q_C) next[0] = phase_compton(P, S, slot[0], slot_base + slot[0], c_edep);
+      else if (q == Q_E) next[0] = phase_end(P, S, slot[0], slot_base + slot[0], c_edep);
+      else if (q == Q_W) next[0] = phase_world(P, S, slot[0]);
+      else next[0] = phase_rare(P, S, slot[0], slot_base + slot[0], c_edep);
     }
     __syncwarp();
     __threadfence_block();   // slot state visible before the slot is published again
 
     // ---- push every slot to the queue of its next phase: one pass, one leader lane per target queue
-    {
-      unsigned mine = 0;
 #pragma unroll
-      for (int t = 0; t < Q_COUNT; ++t) {
-        const unsigned m = __ballot_sync(FULL, next == t);
-        if (next == t) mine = m;
-      }
-      const unsigned mret = __ballot_sync(FULL, next == Q_RETIRED);
-      const bool pushing = next >= 0;
+    for (int w = 0; w < kVWidth; ++w) {
+      if (w > 0 && (q != Q_V || got <= 32 * w)) break;   // warp-uniform
+      const int nx = next[w];
+      const unsigned mine = __match_any_sync(FULL, nx);   // the lanes that go to the same queue
+      const unsigned mret = __ballot_sync(FULL, nx == Q_RETIRED);
+      const bool pushing = nx >= 0;
       const int leader = pushing ? __ffs(mine) - 1 : (int)lane;
       const int n = __popc(mine);
       int tk = 0;
-      if (pushing && (int)lane == leader) tk = atomicAdd(&S.tail[next], n);
+      if (pushing && (int)lane == leader) tk = atomicAdd(&S.tail[nx], n);
       tk = __shfl_sync(FULL, tk, leader);
       if (pushing) {
-        unsigned short *c = &S.cell[next][(unsigned)(tk + __popc(mine & ((1u << lane) - 1u))) % (unsigned)kSlots];
+        unsigned short *c = &S.cell[nx][(unsigned)(tk + __popc(mine & ((1u << lane) - 1u))) % (unsigned)kSlots];
         while (ld_cell(c) != kEmpty) { }   // the previous occupant is claimed, its reader clears it at once
-        st_cell(c, (unsigned)slot);
+        st_cell(c, (unsigned)slot[w]);
       }
       __syncwarp();
-      if (pushing && (int)lane == leader) atomicAdd(&S.avail[next], n);
+      if (pushing && (int)lane == leader) atomicAdd(&S.avail[nx], n);
       if (mret && lane == 0) atomicAdd(&S.retired, __popc(mret));
     }
   }

@@ -2,8 +2,9 @@
  *
  * A scalar, single-precision restatement of the photon-in-image-volume dose path, written
  * independently of opengate_b200/csrc/ but to the same arithmetic specification
- * (DESIGN.md section "Arithmetic contract"): IEEE float +,-,*,/ ,sqrt only, no FMA
- * contraction (compile with -ffp-contract=off), own log/exp/sincos polynomials, Philox4x32-10
+ * (DESIGN.md section "Arithmetic contract"): IEEE float +,-,*,/ ,sqrt and the fused multiply-add
+ * exactly where fmaf() is written (never by compiler contraction: compile with
+ * -ffp-contract=off), own log/exp/sincos polynomials, Philox4x32-10
  * keyed by (seed, history id).  Under that contract the CUDA engine must reproduce every
  * history bit for bit; the accumulated grids then differ only by the order of the double
  * additions.
@@ -42,26 +43,28 @@
 static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
-/* natural logarithm, msun/musl style argument reduction + degree-4 even polynomial */
+/* natural logarithm: x = m 2^k with m in [sqrt(1/2), sqrt(2)); log(m) = f - f^2/2 + f^3 P(f), f = m - 1,
+ * P a degree-8 polynomial fitted for this repository (tools/fit_log_poly.py; < 0.8 ulp on the ranges the
+ * transport uses), evaluated by Horner's rule with fused multiply-adds: no division. */
 static float o_logf(float x) {
   const float ln2_hi = 6.9313812256e-01f, ln2_lo = 9.0580006145e-06f;
-  const float Lg1 = 0.66666662693f, Lg2 = 0.40000972152f, Lg3 = 0.28498786688f,
-              Lg4 = 0.24279078841f;
+  const float c0 = 0.3333331048488617f, c1 = -0.24999986588954926f, c2 = 0.20002226531505585f,
+              c3 = -0.16669249534606934f, c4 = 0.14218655228614807f, c5 = -0.12384366989135742f,
+              c6 = 0.1187300980091095f, c7 = -0.1178971379995346f, c8 = 0.06915182620286942f;
   uint32_t ix = f2u(x);
   ix += 0x3f800000u - 0x3f3504f3u;
   int k = (int)(ix >> 23) - 0x7f;
   ix = (ix & 0x007fffffu) + 0x3f3504f3u;
-  float m = u2f(ix);
-  float f = m - 1.0f;
-  float s = f / (2.0f + f);
-  float z = s * s;
-  float w = z * z;
-  float t1 = w * (Lg2 + w * Lg4);
-  float t2 = z * (Lg1 + w * Lg3);
-  float R = t2 + t1;
-  float hfsq = 0.5f * f * f;
+  float f = u2f(ix) - 1.0f;
+  float p = c8;
+  p = fmaf(p, f, c7); p = fmaf(p, f, c6); p = fmaf(p, f, c5); p = fmaf(p, f, c4);
+  p = fmaf(p, f, c3); p = fmaf(p, f, c2); p = fmaf(p, f, c1); p = fmaf(p, f, c0);
+  float z = f * f;
   float dk = (float)k;
-  return s * (hfsq + R) + dk * ln2_lo - hfsq + f + dk * ln2_hi;
+  float y = (f * z) * p;
+  y = fmaf(dk, ln2_lo, y);
+  y = fmaf(-0.5f, z, y);
+  return fmaf(dk, ln2_hi, f + y);
 }
 
 /* exp(x) for moderate |x| (used on [-6,0]) */
@@ -204,7 +207,7 @@ struct oracle_engine {
   float wh[3];
   int world_mat;
   int has_vol, n[3], label_bytes;
-  float half[3], inv_sp[3], sp[3];
+  float half[3], inv_sp[3], sp[3], hs[3];
   affine_t w2v;
   void *labels;
   /* actors, sources */
@@ -313,7 +316,7 @@ static void energy_bin(const oracle_engine *g, float E, int *ie, float *fe) {
 }
 static float tab(const float *t, int ne, int m, int ie, float fe) {
   const float *r = t + (size_t)m * ne + ie;
-  return r[0] + fe * (r[1] - r[0]);
+  return fmaf(fe, r[1] - r[0], r[0]);
 }
 
 /* ------------------------------------------------------------------ scoring */
@@ -869,17 +872,18 @@ static void run_photon(hist_t *h, float pend_p[3], float pend_d[3], int *pend) {
       /* Woodcock delta tracking against the majorant of the materials in the volume.
        * One call = up to WOODCOCK_K tentative collisions fed by 2 Philox blocks: u[2k] gives
        * the flight distance of iteration k, u[2k+1] its acceptance test. */
-      float maj = g->maj[h->ie] + h->fe * (g->maj[h->ie + 1] - g->maj[h->ie]);
+      float maj = fmaf(h->fe, g->maj[h->ie + 1] - g->maj[h->ie], g->maj[h->ie]);
       float inv_maj = 1.0f / maj;
       float u[2 * WOODCOCK_K];
       rng_begin(&h->rng);
       for (int k = 0; k < 2 * WOODCOCK_K; ++k) u[k] = rng_uniform(&h->rng);
       for (int k = 0; k < WOODCOCK_K; ++k) {
         float s = -o_logf(u[2 * k]) * inv_maj;
-        float q[3] = {h->p[0] + h->d[0] * s, h->p[1] + h->d[1] * s, h->p[2] + h->d[2] * s};
-        float fx = (q[0] + g->half[0]) * g->inv_sp[0];
-        float fy = (q[1] + g->half[1]) * g->inv_sp[1];
-        float fz = (q[2] + g->half[2]) * g->inv_sp[2];
+        float q[3] = {fmaf(h->d[0], s, h->p[0]), fmaf(h->d[1], s, h->p[1]), fmaf(h->d[2], s, h->p[2])};
+        /* continuous voxel coordinate: q / spacing + n / 2 in one fused operation */
+        float fx = fmaf(q[0], g->inv_sp[0], g->hs[0]);
+        float fy = fmaf(q[1], g->inv_sp[1], g->hs[1]);
+        float fz = fmaf(q[2], g->inv_sp[2], g->hs[2]);
         if (fx < 0.0f || fy < 0.0f || fz < 0.0f || fx >= (float)g->n[0] || fy >= (float)g->n[1] ||
             fz >= (float)g->n[2]) {
           /* left the volume: restart from the exit point in the world frame */
@@ -1069,6 +1073,7 @@ int oracle_set_image_volume(oracle_engine *g, const void *labels, int label_byte
     g->n[a] = size[a];
     g->sp[a] = (float)spacing[a];
     g->inv_sp[a] = (float)(1.0 / spacing[a]);
+    g->hs[a] = (float)(0.5 * size[a]);
     g->half[a] = (float)(0.5 * size[a] * spacing[a]);
   }
   aff_from_d(&g->w2v, w2v);

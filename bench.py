@@ -37,6 +37,18 @@ def build_setup(name, histories):
         return setups.make_c1(n_primaries=histories)
     if name == "c4":
         return setups.make_c4(n_primaries=histories)
+    if name in ("c3tle", "c3tle_nosq"):
+        # config 3 scored by the track-length estimator (TLEDoseActor, EPDL database) instead of the
+        # analog DoseActor: dose + edep with event-wise squares (c3tle) or plain sums (c3tle_nosq)
+        from opengate_b200 import abi
+        S = setups.make_c3(n_primaries=histories)
+        d0 = S.dose[0]
+        A = np.array(d0.world_to_index[:]).reshape(3, 4)
+        flags = abi.SCORE_EDEP | abi.SCORE_DOSE | (abi.SCORE_EDEP_SQ if name == "c3tle" else 0)
+        S.dose = []
+        S.add_tle_actor(tuple(d0.size), A, flags, database="EPDL")
+        S.name = S.name.replace("DoseActor dose+edep2", "TLEDoseActor dose+edep" + ("+edep2" if name == "c3tle" else ""))
+        return S
     if name == "c3small":  # CPU-container debugging only
         return setups.make_c3(nx=128, ny=128, nz=75, spacing=(3.9, 3.9, 4.0), n_primaries=histories)
     raise SystemExit(f"unknown config {name}")
@@ -112,17 +124,24 @@ def measured_traffic_per_history(workload_key):
 
 
 def algorithmic_bytes_per_history(st, label_bytes, n_grids, phsp_row_bytes=0):
-    """B_hist = N_tent*s_label + N_flush*G*2*8 + f_out*s_rec  (SURVEY.md section 8d)."""
+    """B_hist = (N_tent + N_chord)*s_label + (N_flush + N_tle)*G*2*8 + f_out*s_rec  (SURVEY.md section 8d;
+    a TLE actor adds one label gather per voxel chord and one RMW per grid and (voxel, history) sum)."""
     n = max(st["histories"], 1)
     n_tent = st["tentative_collisions"] / n
-    n_dep = st["flushed_entries"] / n
+    n_dep = (st["flushed_entries"] + st.get("tle_entries", 0)) / n
+    n_chord = st.get("tle_steps", 0) / n
     f_out = st["phsp_rows"] / n
-    return n_tent * label_bytes + n_dep * n_grids * 2 * 8 + f_out * phsp_row_bytes, n_tent, n_dep, f_out
+    return (n_tent + n_chord) * label_bytes + n_dep * n_grids * 2 * 8 + f_out * phsp_row_bytes, n_tent, n_dep, f_out
+
+
+def desc0(S):
+    """descriptor of the first scoring grid (a DoseActor, else the TLEDoseActor)"""
+    return S.dose[0] if S.dose else S.tle[0][0]
 
 
 def n_active_grids(S):
     from opengate_b200 import abi
-    f = S.dose[0].score_flags | abi.SCORE_EDEP if S.dose else 0
+    f = desc0(S).score_flags | abi.SCORE_EDEP
     return bin(f & 31).count("1")
 
 
@@ -291,7 +310,7 @@ def main():
             "config": {"workload": S.name, "histories_per_step_per_gpu": H, "seed": S.seed,
                        "label_dtype": str(S.labels.dtype), "n_materials": len(S.tables.names),
                        "l2": "256 MB L2 flush before every step; accumulator grids "
-                             f"({G} x {S.dose[0].size[0] * S.dose[0].size[1] * S.dose[0].size[2] * 8 / 1e6:.0f} MB) exceed L2",
+                             f"({G} x {desc0(S).size[0] * desc0(S).size[1] * desc0(S).size[2] * 8 / 1e6:.0f} MB) exceed L2",
                        "parallelism": f"histories sharded over {world} GPU(s), NCCL reduce of {G} grids at end of run" if world > 1 else "1 GPU"},
             "clocks": clocks,
             "gpu_launches": args.steps,
@@ -301,9 +320,11 @@ def main():
                          "kernel": "gb2::transport_kernel", "kernel_ms_per_launch": kernel_ms,
                          "bytes_per_history": b_hist, "tentative_collisions_per_history": n_tent,
                          "deposit_entries_per_history": n_dep, "phsp_rows_per_history": f_out,
-                         "label_bytes": label_bytes, "grids_per_deposit": G},
+                         "label_bytes": label_bytes, "grids_per_deposit": G,
+                         "tle_chords_per_history": st.get("tle_steps", 0) / max(st["histories"], 1)},
             "stats": {k: st[k] for k in ("histories", "tentative_collisions", "n_phot", "n_compt", "n_rayl", "n_conv",
-                                         "flushed_entries", "buffer_overflows", "escaped", "edep_total_MeV")},
+                                         "flushed_entries", "buffer_overflows", "escaped", "edep_total_MeV",
+                                         "tle_steps", "tle_entries", "tle_overflows")},
         }
     eng.close()
     del flush_buf
@@ -332,8 +353,8 @@ def measure_e2e(S, H, local, rank, world, torch, dist, steps=2):
     from opengate_b200 import abi, multigpu
     from opengate_b200.core import Engine
     G = n_active_grids(S)
-    nx, ny, nz = S.dose[0].size[0], S.dose[0].size[1], S.dose[0].size[2]
-    which = multigpu.active_grids(S.dose[0].score_flags)
+    nx, ny, nz = desc0(S).size[0], desc0(S).size[1], desc0(S).size[2]
+    which = multigpu.active_grids(desc0(S).score_flags)
     host_out = [torch.empty((nz, ny, nx), dtype=torch.float64, pin_memory=True).numpy() for _ in range(G)] if rank == 0 else []
     S = copy.copy(S)
     pinned_labels = torch.empty(S.labels.shape, dtype=torch.uint8 if S.labels.dtype == np.uint8 else torch.int16, pin_memory=True)
@@ -342,7 +363,7 @@ def measure_e2e(S, H, local, rank, world, torch, dist, steps=2):
     S.labels = lab
     t = S.tables
     h2d = S.labels.nbytes + sum(a.nbytes for a in (t.density, t.mu_total, t.cum_phot, t.cum_compt, t.cum_rayl,
-                                                   t.rayl_cum_ff2, t.compt_sf))
+                                                   t.rayl_cum_ff2, t.compt_sf)) + sum(k.nbytes for _, _, k in S.tle)
     d2h = G * nx * ny * nz * 8
 
     def one(first):

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GATE_B200_ABI_VERSION 1
+#define GATE_B200_ABI_VERSION 2
 
 enum {
   GATE_B200_OK = 0,
@@ -121,6 +121,24 @@ typedef struct {
   int32_t hit_type;
 } gate_b200_dose_desc;
 
+/* ---- TLE dose actor ---------------------------------------------------------------------
+ * Replaces: GateTLEDoseActor (GateTLEDoseActor.cpp:185-300): a DoseActor whose gammas score with
+ * the track-length estimator.  Every step of a TLE gamma inside the attached image volume (one
+ * step = the chord of one image voxel, as Geant4 steps through the nested parameterisation)
+ * deposits  edep = w * 0.1 * E * (mu_en/rho)(material, E) * L[mm] * rho[g/cm3]  (:252-266) at a
+ * point of the chord chosen by hit_type, dose = edep / rho; the secondaries of a TLE gamma do not
+ * deposit (:60-74, :236-243).  TLE applies when E <= energy_threshold_MeV (tle_threshold_type
+ * "energy", :224-226; +inf = type "None": always); above it the actor scores like a DoseActor.
+ * A gamma at or below energy_min_MeV deposits w*E on the spot and stops (:268-271).
+ * mu_en_over_rho is GateMaterialMuHandler::GetMuEnOverRho (GateMaterialMuHandler.cpp:75-79,
+ * database "NIST" | "EPDL") evaluated by the caller on the energy nodes of gate_b200_tables.
+ * The actor shares the id space and the grid accessors of the dose actors. */
+typedef struct {
+  double energy_min_MeV;
+  double energy_threshold_MeV;
+  const float *mu_en_over_rho;    /* [n_materials][n_energy] cm2/g                         */
+} gate_b200_tle_desc;
+
 /* ---- phase-space actor --------------------------------------------------------------------
  * Replaces: GatePhaseSpaceActor::SteppingAction (GatePhaseSpaceActor.cpp:119-201) for a Box
  * volume placed in the world, steps_to_store entering/exiting, and the digi attributes
@@ -163,6 +181,9 @@ typedef struct {
   uint64_t absorbed_events;       /* histories that never reached any phase-space plane  */
   double edep_total_MeV;          /* everything deposited (also outside scoring grids)   */
   double kernel_ms;               /* device time of the transport launches of this run   */
+  uint64_t tle_steps;             /* voxel chords scored by track-length estimators      */
+  uint64_t tle_entries;           /* TLE sums written to the grids (table entries/chords) */
+  uint64_t tle_overflows;         /* per-history TLE table evictions (0 = squares exact) */
 } gate_b200_stats;
 
 /* ---- life cycle --------------------------------------------------------------------------- */
@@ -188,6 +209,8 @@ int gate_b200_set_image_volume(gate_b200_engine *h, const void *labels, int32_t 
                                const double world_to_volume[12]);
 int gate_b200_add_source(gate_b200_engine *h, const gate_b200_source *s, int32_t *source_id);
 int gate_b200_add_dose_actor(gate_b200_engine *h, const gate_b200_dose_desc *d, int32_t *actor_id);
+int gate_b200_add_tle_dose_actor(gate_b200_engine *h, const gate_b200_dose_desc *d,
+                                 const gate_b200_tle_desc *t, int32_t *actor_id);
 int gate_b200_add_phsp_actor(gate_b200_engine *h, const gate_b200_phsp_desc *d, int32_t *actor_id);
 
 /* Replaces: GateSourceManager::StartMasterThread run loop (GateSourceManager.cpp:198-244):

@@ -10,7 +10,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enums --------------------------------------------------------------------------------
 POS_POINT, POS_BOX, POS_SPHERE, POS_DISC, POS_CYLINDER, POS_VOXELS = range(6)
@@ -61,6 +61,11 @@ class DoseDesc(C.Structure):
                 ("score_flags", C.c_int32), ("hit_type", C.c_int32)]
 
 
+class TleDesc(C.Structure):
+    _fields_ = [("energy_min_MeV", C.c_double), ("energy_threshold_MeV", C.c_double),
+                ("mu_en_over_rho", _fp)]
+
+
 class PhspDesc(C.Structure):
     _fields_ = [("half_size", C.c_double * 3), ("world_to_box", C.c_double * 12),
                 ("steps_to_store", C.c_int32), ("capacity", C.c_uint64)]
@@ -80,6 +85,7 @@ class Stats(C.Structure):
         ("escaped", C.c_uint64), ("phsp_rows", C.c_uint64), ("phsp_dropped", C.c_uint64),
         ("absorbed_events", C.c_uint64),
         ("edep_total_MeV", C.c_double), ("kernel_ms", C.c_double),
+        ("tle_steps", C.c_uint64), ("tle_entries", C.c_uint64), ("tle_overflows", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -177,6 +183,17 @@ def make_dose_desc(size, world_to_index12, score_flags, hit_type):
     d.score_flags = int(score_flags)
     d.hit_type = int(hit_type)
     return d
+
+
+def make_tle_desc(mu_en_over_rho, energy_threshold=float("inf"), energy_min=0.0):
+    """gate_b200_tle_desc; mu_en_over_rho: float32 [n_materials][n_energy] on the table's energy nodes.
+    Returns (struct, keepalive)."""
+    t = TleDesc()
+    a = np.ascontiguousarray(mu_en_over_rho, dtype=np.float32)
+    t.energy_min_MeV = float(energy_min)
+    t.energy_threshold_MeV = float(energy_threshold)
+    t.mu_en_over_rho = fptr(a)
+    return t, a
 
 
 def make_phsp_desc(half_size, world_to_box12, steps_to_store, capacity):

@@ -29,7 +29,7 @@ EXPORTS = [
     "gate_b200_abi_version", "gate_b200_create", "gate_b200_destroy", "gate_b200_last_error",
     "gate_b200_set_stream", "gate_b200_set_tables", "gate_b200_set_world",
     "gate_b200_set_image_volume", "gate_b200_add_source", "gate_b200_add_dose_actor",
-    "gate_b200_add_phsp_actor", "gate_b200_begin_run", "gate_b200_run_source", "gate_b200_sync",
+    "gate_b200_add_tle_dose_actor", "gate_b200_add_phsp_actor", "gate_b200_begin_run", "gate_b200_run_source", "gate_b200_sync",
     "gate_b200_get_dose_grid", "gate_b200_dose_grid_device_ptr", "gate_b200_set_dose_grid",
     "gate_b200_mean_uncertainty", "gate_b200_phsp_count", "gate_b200_get_phsp",
     "gate_b200_get_stats", "gate_b200_timed_run",
@@ -81,6 +81,7 @@ def load_library():
     L.gate_b200_set_image_volume.argtypes = [vp, vp, i32, C.POINTER(i32), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.gate_b200_add_source.argtypes = [vp, C.POINTER(abi.Source), C.POINTER(i32)]
     L.gate_b200_add_dose_actor.argtypes = [vp, C.POINTER(abi.DoseDesc), C.POINTER(i32)]
+    L.gate_b200_add_tle_dose_actor.argtypes = [vp, C.POINTER(abi.DoseDesc), C.POINTER(abi.TleDesc), C.POINTER(i32)]
     L.gate_b200_add_phsp_actor.argtypes = [vp, C.POINTER(abi.PhspDesc), C.POINTER(i32)]
     L.gate_b200_begin_run.argtypes = [vp, i32]
     L.gate_b200_run_source.argtypes = [vp, i32, u64, u64]
@@ -172,6 +173,13 @@ class Engine:
     def add_dose_actor(self, desc):
         aid = C.c_int32(-1)
         self._check(self.L.gate_b200_add_dose_actor(self.h, C.byref(desc), C.byref(aid)))
+        self._dose_sizes.append(tuple(desc.size))
+        return aid.value
+
+    def add_tle_dose_actor(self, desc, tle_desc, keep=None):
+        self._keep.append(keep)
+        aid = C.c_int32(-1)
+        self._check(self.L.gate_b200_add_tle_dose_actor(self.h, C.byref(desc), C.byref(tle_desc), C.byref(aid)))
         self._dose_sizes.append(tuple(desc.size))
         return aid.value
 

@@ -446,6 +446,59 @@ int gate_b200_add_dose_actor(gate_b200_engine *h, const gate_b200_dose_desc *d, 
   return GATE_B200_OK;
 }
 
+int gate_b200_add_tle_dose_actor(gate_b200_engine *h, const gate_b200_dose_desc *d, const gate_b200_tle_desc *t,
+                                 int32_t *actor_id) {
+  if (!h || !d || !t) return GATE_B200_EINVAL;
+  if (!t->mu_en_over_rho) return fail(h, GATE_B200_EINVAL, "tle: mu_en_over_rho table missing");
+  if (!h->have_volume) return fail(h, GATE_B200_ESTATE, "add_tle_dose_actor needs the image volume first");
+  Params &P = h->P;
+  if (P.n[0] > 65535 || P.n[1] > 65535) return fail(h, GATE_B200_EINVAL, "tle: image volume wider than 65535 voxels");
+  int32_t id = -1;
+  if (int rc = gate_b200_add_dose_actor(h, d, &id)) return rc;
+  DDose &D = h->dose[id].dev;
+  D.tle = 1;
+  D.tle_thr = t->energy_threshold_MeV > 3.0e38 ? kBig : (float)t->energy_threshold_MeV;
+  {
+    // energy-major pairs, like the attenuation table (same float values as the caller's array)
+    const size_t n = (size_t)P.nmat * P.ne;
+    std::vector<float2> m2(n);
+    for (int ie = 0; ie < P.ne; ++ie) {
+      const int ie1 = ie + 1 < P.ne ? ie + 1 : ie;
+      for (int m = 0; m < P.nmat; ++m)
+        m2[(size_t)ie * P.nmat + m] = make_float2(t->mu_en_over_rho[(size_t)m * P.ne + ie], t->mu_en_over_rho[(size_t)m * P.ne + ie1]);
+    }
+    if (int rc = dev_upload(h, &D.muen2, m2.data(), n)) return rc;
+  }
+  // the grid is the image grid when volume point -> index is p / spacing + n / 2 - 1 / 2 on the image's own
+  // lattice (same test as the oracle's grid_is_image_grid): the voxel of a chord is then the image voxel
+  D.aligned = 1;
+  for (int a = 0; a < 3; ++a) {
+    if (D.size[a] != P.n[a]) D.aligned = 0;
+    for (int c = 0; c < 3; ++c) {
+      const double want = a == c ? 1.0 / (double)P.sp[a] : 0.0;
+      if (fabs((double)D.v2i.m[3 * a + c] - want) > 1.0e-6 * (1.0 / (double)P.sp[a])) D.aligned = 0;
+    }
+    if (fabs((double)D.v2i.t[a] - (0.5 * (double)P.n[a] - 0.5)) > 1.0e-4) D.aligned = 0;
+  }
+  const float emin = (float)t->energy_min_MeV;
+  if (P.ntle == 0 || emin > P.tle_emin) P.tle_emin = emin;
+  if (P.ntle == 0 || D.tle_thr > P.tle_thr_max) P.tle_thr_max = D.tle_thr;
+  P.ntle++;
+  const size_t nslots = (size_t)h->max_ctas * kSlots;
+  if (!P.tle_state) {
+    if (int rc = dev_alloc(h, &P.tle_state, nslots, true)) return rc;
+  }
+  if ((D.flags & (GATE_B200_SCORE_EDEP_SQ | GATE_B200_SCORE_DOSE_SQ)) && !P.tle_tab) {
+    // per-history tables (event-wise squares): 32 KB per photon slot, empty = key -1
+    if (int rc = dev_alloc(h, &P.tle_tab, nslots * kTleH)) return rc;
+    CU(cudaMemsetAsync(P.tle_tab, 0xff, nslots * kTleH * sizeof(DepEntry), h->stream));
+    if (int rc = dev_alloc(h, &P.tle_list, nslots * kTleMax)) return rc;
+  }
+  P.dose[id] = D;
+  if (actor_id) *actor_id = id;
+  return GATE_B200_OK;
+}
+
 int gate_b200_add_phsp_actor(gate_b200_engine *h, const gate_b200_phsp_desc *d, int32_t *actor_id) {
   if (!h || !d) return GATE_B200_EINVAL;
   if ((int)h->phsp.size() >= kMaxPhsp) return fail(h, GATE_B200_EINVAL, "at most %d phase-space actors", kMaxPhsp);
@@ -500,7 +553,8 @@ static int launch_histories(gate_b200_engine *h, int32_t source_id, uint64_t fir
   P.count = n_histories;
   CU(cudaMemsetAsync(h->d_next, 0, sizeof(unsigned long long), h->stream));
   const size_t smem = sizeof(Smem) + (size_t)P.ne * sizeof(float);
-  auto kern = (label_bytes == 2) ? transport_kernel<uint16_t> : transport_kernel<uint8_t>;
+  auto kern = P.ntle > 0 ? ((label_bytes == 2) ? transport_kernel<uint16_t, true> : transport_kernel<uint8_t, true>)
+                         : ((label_bytes == 2) ? transport_kernel<uint16_t, false> : transport_kernel<uint8_t, false>);
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // persistent CTAs: one per SM, fewer only when there is not enough work to fill the slots
   unsigned long long want = (n_histories + 255) / 256;
@@ -661,6 +715,7 @@ int gate_b200_get_stats(gate_b200_engine *h, gate_b200_stats *out) {
   out->n_phot = s[S_PHOT]; out->n_compt = s[S_COMPT]; out->n_rayl = s[S_RAYL]; out->n_conv = s[S_CONV];
   out->deposits = s[S_DEP]; out->flushed_entries = s[S_FLUSH]; out->buffer_overflows = s[S_OVER];
   out->escaped = s[S_ESC]; out->absorbed_events = s[S_ABSORBED];
+  out->tle_steps = s[S_TLE_STEPS]; out->tle_entries = s[S_TLE_ENT]; out->tle_overflows = s[S_TLE_OVER];
   CU(cudaMemcpy(&out->edep_total_MeV, h->d_edep, sizeof(double), cudaMemcpyDeviceToHost));
   for (auto &A : h->phsp) {
     unsigned long long n = 0, d = 0;

@@ -8,6 +8,8 @@
 //   Q_W  one flight segment in the homogeneous world (entry, exit, phase-space planes)
 //   Q_E  end of a photon: second annihilation photon, or close the history (flush its coalesced
 //        deposits with warp-aggregated fp64 atomics) and start the next primary
+//   Q_T  track-length estimator: walk kTleSteps voxel chords of the flight that just ended (or
+//        write kTleSteps entries of the history's TLE table to the grids), re-queued until done
 // and sits in the shared-memory ring queue of that kind.  Every warp of the CTA runs the same loop:
 // claim up to 32 slots from the fullest queue, run that phase for all of them in lock-step, push each
 // slot to the queue of its next phase.  This is stream compaction inside a persistent kernel: warps
@@ -28,7 +30,10 @@
 #define GB2_THREADS 1024
 #endif
 #ifndef GB2_SLOTS
-#define GB2_SLOTS 3072
+// 64 B of shared memory per slot (52 B photon state + 6 queue cells): 3040 slots + the majorant keep
+// the CTA below the 195 KB a block can use under the 196 KB carve-out, which leaves 60 KB of L1 for the
+// table gathers (measured: 3072 slots with 6 queues fall into the 228 KB carve-out, C3 1.08e9 -> 6.8e8/s)
+#define GB2_SLOTS 3040
 #endif
 
 namespace gb2 {
@@ -43,6 +48,11 @@ constexpr int kVWidth = GB2_VWIDTH;        // slots one lane carries through a W
 constexpr int kMaxDose = 4;
 constexpr int kMaxPhsp = 4;
 constexpr int kDepBuf = 32;                // per-history coalescing buffer entries
+constexpr int kTleSteps = 16;              // voxel chords (or table entries) per call of the TLE phase
+constexpr int kTleLog2 = 12;
+constexpr int kTleH = 1 << kTleLog2;       // per-history table of (actor, voxel) sums (TLE actor with squares)
+constexpr int kTleMax = 3072;              // entries at which the table is written out (an overflow)
+constexpr int kTleEmpty = -1;
 constexpr float kNudge = 1.0e-3f;          // mm pushed across a boundary
 constexpr float kBig = 3.0e38f;
 constexpr float kMc2 = 0.51099891f;
@@ -50,7 +60,7 @@ constexpr float kKPerMeV = 268.17264f;     // photon wave number (1/bohr) per Me
 constexpr float kCmmPerNs = 299.792458f;
 constexpr unsigned kMaxBlocks = 4000000u; // Philox blocks one history may consume (runaway guard)
 
-enum { Q_V = 0, Q_C = 1, Q_R = 2, Q_W = 3, Q_E = 4, Q_COUNT = 5, Q_RETIRED = -1 };
+enum { Q_V = 0, Q_C = 1, Q_R = 2, Q_W = 3, Q_E = 4, Q_T = 5, Q_COUNT = 6, Q_RETIRED = -1 };
 
 struct Affine { float m[9]; float t[3]; };
 
@@ -74,6 +84,10 @@ struct DDose {
   Affine v2i;
   int flags, hit_type;
   double *grid[5];
+  // track-length estimator (GateTLEDoseActor): tle = 1; aligned = the grid is the image grid
+  int tle, aligned;
+  float tle_thr;
+  const float2 *muen2;   // [ne][nmat] {mu_en/rho(ie), mu_en/rho(ie+1)}, cm2/g
 };
 
 struct DPhsp {
@@ -91,7 +105,7 @@ struct DepEntry { int key; float e; float d; int n; };   // one (voxel, history)
 
 // indices into the statistics array (unsigned long long)
 enum { S_HIST = 0, S_TRACKS, S_STEPS, S_TENT, S_PHOT, S_COMPT, S_RAYL, S_CONV, S_DEP, S_FLUSH,
-       S_OVER, S_ESC, S_ABSORBED, S_COUNT };
+       S_OVER, S_ESC, S_ABSORBED, S_TLE_STEPS, S_TLE_ENT, S_TLE_OVER, S_COUNT };
 
 struct Params {
   unsigned long long seed;
@@ -121,6 +135,13 @@ struct Params {
   double *edep_total;
   DepEntry *depbuf;              // [gridDim.x * kSlots][kDepBuf] coalescing buffers (global scratch)
   float *pend;                   // [gridDim.x * kSlots][6] second annihilation photon (pair_mode 1)
+  // track-length estimators (dose actors with tle = 1)
+  int ntle;
+  float tle_emin, tle_thr_max;
+  DepEntry *tle_tab;             // [slots][kTleH] per-history (actor, voxel) sums, only with squares
+  unsigned short *tle_list;      // [slots][kTleMax] occupied table cells in insertion order
+  uint4 *tle_state;              // [slots] {t along the flight (-1 new flight, -2 writing the table out),
+                                 //          ix | iy << 16 (or next list entry), iz, entries in the table}
 };
 
 // Shared memory of one CTA: photon slots (structure of arrays), the four ring queues, statistics.
@@ -152,6 +173,8 @@ constexpr unsigned F_NBUF = 0x3fu << F_NBUF_SHIFT;
 constexpr unsigned F_ABSORB = 1u << 15;    // Q_E: the photon is absorbed on the spot first (phot / conv kerma)
 constexpr unsigned F_EXIT = 1u << 16;      // Q_W: the photon is leaving the image volume (still in its frame)
 constexpr unsigned F_CONV = 1u << 17;      // the pending interaction is a conversion (else Rayleigh / phot)
+constexpr unsigned F_NEXT_SHIFT = 18;      // Q_T: queue to continue with, minus one (Q_C..Q_E)
+constexpr unsigned F_NEXT = 3u << F_NEXT_SHIFT;
 constexpr unsigned F_MAT_SHIFT = 20;
 constexpr unsigned F_MASK = (1u << F_MAT_SHIFT) - 1u;
 constexpr int kMaxMaterials = 1 << 12;
@@ -284,6 +307,12 @@ __device__ __forceinline__ void stat_overflow(Smem &S, unsigned over, unsigned f
     stat_add(S, S_FLUSH, flush);
   }
 }
+__device__ __forceinline__ void stat_tle_overflow(Smem &S, unsigned over, unsigned ent) {
+  if (__any_sync(__activemask(), over != 0u)) {
+    stat_add(S, S_TLE_OVER, over);
+    stat_add(S, S_TLE_ENT, ent);
+  }
+}
 
 __device__ __forceinline__ void energy_bin_t(const Params &P, float E, float &t) {
   t = (d_logf(E) - P.ln_emin) * P.inv_dlne;
@@ -335,59 +364,104 @@ __device__ __forceinline__ void set_energy(const Params &P, Smem &S, int s, Ph &
 
 // ------------------------------------------------------------------------------ scoring
 
-// Add the coalesced (voxel, history) entries of a closed history to the fp64 grids.  Lanes that
-// flush together and hit the same voxel are combined first (one atomic per distinct address);
-// squares are summed per history, never of the combined value (GateDoseActor.cpp:359-381).
-__device__ __noinline__ void flush_buffer(const Params &P, const DepEntry *buf, int nbuf) {
+// Add one (voxel, history) sum to the fp64 grids.  Lanes that arrive together and hit the same
+// voxel are combined first (one atomic per distinct address); squares are summed per history, never
+// of the combined value (GateDoseActor.cpp:359-381).
+__device__ __forceinline__ void grid_add(const Params &P, const DepEntry &en) {
   const unsigned lane = threadIdx.x & 31u;
-  unsigned flushed = 0;
-  for (int j = 0; j < nbuf; ++j) {
-    const DepEntry en = ld_dep(buf + j);
-    const int key = en.key;
-    const int a = (int)((unsigned)key >> 28);
-    const int v = key & 0x0fffffff;
-    double e = (double)en.e, d = (double)en.d;
-    double e2 = e * e, d2 = d * d, n = (double)en.n;
-    const unsigned act = __activemask();
-    const unsigned grp = __match_any_sync(act, key);
-    const int leader = __ffs(grp) - 1;
-    if (grp != (1u << lane)) {
-      // serial accumulation into the leader, every member of the group walks the same list
-      double se = 0.0, se2 = 0.0, sd = 0.0, sd2 = 0.0, sn = 0.0;
-      for (unsigned rem = grp; rem; rem &= rem - 1) {
-        const int src = __ffs(rem) - 1;
-        se += __shfl_sync(grp, e, src);
-        se2 += __shfl_sync(grp, e2, src);
-        sd += __shfl_sync(grp, d, src);
-        sd2 += __shfl_sync(grp, d2, src);
-        sn += __shfl_sync(grp, n, src);
-      }
-      e = se; e2 = se2; d = sd; d2 = sd2; n = sn;
+  const int key = en.key;
+  const int a = (int)((unsigned)key >> 28);
+  const int v = key & 0x0fffffff;
+  double e = (double)en.e, d = (double)en.d;
+  double e2 = e * e, d2 = d * d, n = (double)en.n;
+  const unsigned act = __activemask();
+  const unsigned grp = __match_any_sync(act, key);
+  const int leader = __ffs(grp) - 1;
+  if (grp != (1u << lane)) {
+    // serial accumulation into the leader, every member of the group walks the same list
+    double se = 0.0, se2 = 0.0, sd = 0.0, sd2 = 0.0, sn = 0.0;
+    for (unsigned rem = grp; rem; rem &= rem - 1) {
+      const int src = __ffs(rem) - 1;
+      se += __shfl_sync(grp, e, src);
+      se2 += __shfl_sync(grp, e2, src);
+      sd += __shfl_sync(grp, d, src);
+      sd2 += __shfl_sync(grp, d2, src);
+      sn += __shfl_sync(grp, n, src);
     }
-    if ((int)lane == leader) {
-      const DDose &D = P.dose[a];
-      atomicAdd(D.grid[GATE_B200_GRID_EDEP] + v, e);
-      if (D.flags & GATE_B200_SCORE_EDEP_SQ) atomicAdd(D.grid[GATE_B200_GRID_EDEP_SQ] + v, e2);
-      if (D.flags & GATE_B200_SCORE_DOSE) atomicAdd(D.grid[GATE_B200_GRID_DOSE] + v, d);
-      if (D.flags & GATE_B200_SCORE_DOSE_SQ) atomicAdd(D.grid[GATE_B200_GRID_DOSE_SQ] + v, d2);
-      if (D.flags & GATE_B200_SCORE_COUNTS) atomicAdd(D.grid[GATE_B200_GRID_COUNTS] + v, n);
-    }
-    flushed++;
+    e = se; e2 = se2; d = sd; d2 = sd2; n = sn;
   }
-  (void)flushed;
+  if ((int)lane == leader) {
+    const DDose &D = P.dose[a];
+    atomicAdd(D.grid[GATE_B200_GRID_EDEP] + v, e);
+    if (D.flags & GATE_B200_SCORE_EDEP_SQ) atomicAdd(D.grid[GATE_B200_GRID_EDEP_SQ] + v, e2);
+    if (D.flags & GATE_B200_SCORE_DOSE) atomicAdd(D.grid[GATE_B200_GRID_DOSE] + v, d);
+    if (D.flags & GATE_B200_SCORE_DOSE_SQ) atomicAdd(D.grid[GATE_B200_GRID_DOSE_SQ] + v, d2);
+    if ((D.flags & GATE_B200_SCORE_COUNTS) && n != 0.0) atomicAdd(D.grid[GATE_B200_GRID_COUNTS] + v, n);
+  }
 }
 
-struct DepStat { unsigned dep, over, flush; double edep; };
+// Add the coalesced (voxel, history) entries of a closed history to the fp64 grids.
+__device__ __noinline__ void flush_buffer(const Params &P, const DepEntry *buf, int nbuf) {
+  for (int j = 0; j < nbuf; ++j) grid_add(P, ld_dep(buf + j));
+}
 
-// deposit e (already weighted) at the photon position; in_vol selects whether dose actors see it
+// ---- per-history table of the TLE actors that score squares: open addressing, Fibonacci hash.
+// A history touches hundreds of voxels along its flights; the event-wise squares need its sum per
+// voxel (GateTLEDoseActor.cpp:281-299 -> ScoreSquaredValue), so the sums are kept here until the
+// history ends.  The table of a slot is only ever touched by the lane that holds the slot.
+__device__ __noinline__ void tle_flush_all(const Params &P, int gslot, unsigned nlist) {
+  DepEntry *tab = P.tle_tab + (size_t)gslot * kTleH;
+  const unsigned short *list = P.tle_list + (size_t)gslot * kTleMax;
+  for (unsigned j = 0; j < nlist; ++j) {
+    const unsigned hh = __ldcg(list + j);
+    grid_add(P, ld_dep(tab + hh));
+    __stcg(&tab[hh].key, kTleEmpty);
+  }
+}
+__device__ __noinline__ void tle_table_add(const Params &P, int gslot, unsigned &nlist, int key, float e, float d,
+                                           int n, unsigned &n_ent, unsigned &n_over) {
+  DepEntry *tab = P.tle_tab + (size_t)gslot * kTleH;
+  unsigned hh = ((unsigned)key * 2654435761u) >> (32 - kTleLog2);
+  for (;;) {
+    DepEntry en = ld_dep(tab + hh);
+    if (en.key == key) {
+      en.e += e; en.d += d; en.n += n;
+      st_dep(tab + hh, en);
+      return;
+    }
+    if (en.key == kTleEmpty) {
+      if (nlist == (unsigned)kTleMax) {   // table full: write it out, start again
+        tle_flush_all(P, gslot, nlist);
+        n_ent += nlist;
+        n_over++;
+        nlist = 0;
+        hh = ((unsigned)key * 2654435761u) >> (32 - kTleLog2);
+      }
+      DepEntry z; z.key = key; z.e = e; z.d = d; z.n = n;
+      st_dep(tab + hh, z);
+      __stcg(P.tle_list + (size_t)gslot * kTleMax + nlist, (unsigned short)hh);
+      nlist++;
+      return;
+    }
+    hh = (hh + 1u) & (unsigned)(kTleH - 1);
+  }
+}
+
+struct DepStat { unsigned dep, over, flush, tle_ent, tle_over; double edep; };
+
+// deposit e (already weighted) at the photon position; in_vol selects whether dose actors see it.
+// e_tle: flight energy of the gamma whose secondaries deposit here (a TLE actor ignores them while that
+// gamma scores by track length, GateTLEDoseActor.cpp:236-243); kBig for a gamma absorbed below the cut.
+template <bool kTle>
 __device__ __noinline__ void deposit(const Params &P, Ph &g, DepEntry *buf, DepStat &ds, float e,
-                                     int m, bool in_vol) {
+                                     int m, bool in_vol, float e_tle, int gslot) {
   ds.edep += (double)e;
   ds.dep++;
   if (!in_vol) return;
   int nbuf = (int)((g.flags & F_NBUF) >> F_NBUF_SHIFT);
   for (int a = 0; a < P.ndose; ++a) {
     const DDose &D = P.dose[a];
+    if (kTle && D.tle && e_tle <= D.tle_thr) continue;
     float pos[3] = {g.p[0], g.p[1], g.p[2]};
     if (D.hit_type != GATE_B200_HIT_POST) {
       // pre/random/middle between the Geant4 pre and post step points; the Geant4 step starts at
@@ -426,6 +500,13 @@ __device__ __noinline__ void deposit(const Params &P, Ph &g, DepEntry *buf, DepS
     int v = (int)fx + D.size[0] * ((int)fy + D.size[1] * (int)fz);
     int key = (int)(((unsigned)a << 28) | (unsigned)v);
     float dd = e / __ldg(P.dens + m);
+    if (kTle && D.tle && (D.flags & (GATE_B200_SCORE_EDEP_SQ | GATE_B200_SCORE_DOSE_SQ))) {
+      unsigned nl = __ldcg(&P.tle_state[gslot].w);
+      const unsigned before = nl;
+      tle_table_add(P, gslot, nl, key, e, dd, 1, ds.tle_ent, ds.tle_over);
+      if (nl != before) __stcg(&P.tle_state[gslot].w, nl);
+      continue;
+    }
     int j;
     for (j = 0; j < nbuf; ++j)
       if (__ldcg(&buf[j].key) == key) break;
@@ -871,7 +952,8 @@ __device__ __forceinline__ void volume_gather_mu(const Params &P, VCall &c) {
   }
 }
 
-__device__ __forceinline__ int volume_decide(const Params &P, Smem &S, int slot, const VCall &c, unsigned &c_tent) {
+template <bool kTle>
+__device__ __forceinline__ int volume_decide(const Params &P, Smem &S, int slot, int gslot, const VCall &c, unsigned &c_tent) {
   if (c.blk > kMaxBlocks) return Q_E;
   S.blk[slot] = c.blk + 2u;
   float p0 = S.px[slot], p1 = S.py[slot], p2 = S.pz[slot];
@@ -909,12 +991,19 @@ __device__ __forceinline__ int volume_decide(const Params &P, Smem &S, int slot,
     next = route_interaction(P, flags, mat, c.ie, c.fe, vsel);
     S.fm[slot] = flags | ((unsigned)mat << F_MAT_SHIFT);
   }
+  if (kTle && next != Q_V && S.E[slot] <= P.tle_thr_max) {
+    // the flight has ended (interaction or exit): score its voxel chords first, then carry on
+    S.fm[slot] |= (unsigned)(next - 1) << F_NEXT_SHIFT;
+    __stcg(&P.tle_state[gslot].x, __float_as_uint(-1.0f));
+    next = Q_T;
+  }
   return next;
 }
 
 // Q_C: one Compton trial (Klein-Nishina composition-rejection x scattering function).  A rejected
 // trial simply stays in the queue: trials are independent, each call owns two fresh Philox blocks
 // (trial, final state), so the lanes of a warp never wait for each other's rejection loops.
+template <bool kTle>
 __device__ __noinline__ int phase_compton(const Params &P, Smem &S, int slot, int gslot, double &c_edep) {
   const unsigned b0 = S.blk[slot];
   S.blk[slot] = b0 + 2u;
@@ -950,7 +1039,7 @@ __device__ __noinline__ int phase_compton(const Params &P, Smem &S, int slot, in
   if (u4 > sfv) ok = false;
   int next = Q_C;
   unsigned n_compt = 0;
-  DepStat ds; ds.dep = 0; ds.over = 0; ds.flush = 0; ds.edep = 0.0;
+  DepStat ds; ds.dep = 0; ds.over = 0; ds.flush = 0; ds.tle_ent = 0; ds.tle_over = 0; ds.edep = 0.0;
   if (ok) {
     Ph g;
     load_ph(P, S, slot, g);
@@ -965,12 +1054,12 @@ __device__ __noinline__ int phase_compton(const Params &P, Smem &S, int slot, in
     float sphi, cphi;
     d_sincos2pi(u32_to_uniform(r[4]), sphi, cphi);
     const float E1 = eps * E;
-    deposit(P, g, buf, ds, (E - E1) * P.src.weight, m, in_vol);
+    deposit<kTle>(P, g, buf, ds, (E - E1) * P.src.weight, m, in_vol, E, gslot);
     rotate_dir(g.d, cost, sint, sphi, cphi);
     g.E = E1;
     g.seg = 0.0f;
-    if (E1 < P.e_cut) {
-      deposit(P, g, buf, ds, E1 * P.src.weight, m, in_vol);
+    if (E1 < P.e_cut || (kTle && in_vol && E1 <= P.tle_emin)) {
+      deposit<kTle>(P, g, buf, ds, E1 * P.src.weight, m, in_vol, kBig, gslot);
       next = Q_E;
     } else {
       set_energy(P, S, slot, g);
@@ -986,18 +1075,20 @@ __device__ __noinline__ int phase_compton(const Params &P, Smem &S, int slot, in
     stat_bump(S, S_DEP, t >> 8);
   }
   stat_overflow(S, ds.over, ds.flush);
+  if (kTle) stat_tle_overflow(S, ds.tle_over, ds.tle_ent);
   return next;
 }
 
 // Q_R: the rare interactions.  Rayleigh: q2 from the cumulative squared form factor, (1+cos^2)/2
 // test.  Conversion with pair_mode 1: deposit E - 2 mc2, emit two back-to-back 511 keV photons.
+template <bool kTle>
 __device__ __noinline__ int phase_rare(const Params &P, Smem &S, int slot, int gslot, double &c_edep) {
   Ph g;
   load_ph(P, S, slot, g);
   const bool in_vol = (g.flags & F_INVOL) != 0;
   const int m = g.mat;
   unsigned n_rayl = 0, n_conv = 0;
-  DepStat ds; ds.dep = 0; ds.over = 0; ds.flush = 0; ds.edep = 0.0;
+  DepStat ds; ds.dep = 0; ds.over = 0; ds.flush = 0; ds.tle_ent = 0; ds.tle_over = 0; ds.edep = 0.0;
   rng_begin(g.rng);
   if (!(g.flags & F_CONV)) {
     n_rayl = 1;
@@ -1043,7 +1134,7 @@ __device__ __noinline__ int phase_rare(const Params &P, Smem &S, int slot, int g
     g.seg = 0.0f;
   } else {
     n_conv = 1;
-    deposit(P, g, P.depbuf + (size_t)gslot * kDepBuf, ds, (g.E - 2.0f * kMc2) * P.src.weight, m, in_vol);
+    deposit<kTle>(P, g, P.depbuf + (size_t)gslot * kDepBuf, ds, (g.E - 2.0f * kMc2) * P.src.weight, m, in_vol, g.E, gslot);
     float cost = 2.0f * rng_uniform(g.rng) - 1.0f;
     float sint = sqrtf(1.0f - cost * cost);
     float sphi, cphi;
@@ -1069,6 +1160,7 @@ __device__ __noinline__ int phase_rare(const Params &P, Smem &S, int slot, int g
     stat_bump(S, S_DEP, t >> 16);
   }
   stat_overflow(S, ds.over, ds.flush);
+  if (kTle) stat_tle_overflow(S, ds.tle_over, ds.tle_ent);
   return in_vol ? Q_V : Q_W;
 }
 
@@ -1076,16 +1168,17 @@ __device__ __noinline__ int phase_rare(const Params &P, Smem &S, int slot, int g
 // the kerma configuration), below the energy cut, or out of the world.  Either the history still
 // owes its second annihilation photon, or it is closed (coalesced deposits -> grids) and the slot
 // claims the next history.
+template <bool kTle>
 __device__ __noinline__ int phase_end(const Params &P, Smem &S, int slot, int gslot, double &c_edep) {
   Ph g;
   load_ph(P, S, slot, g);
   int next;
   unsigned n_flush = 0, n_abs = 0, n_hist = 0, n_phot = 0, n_conv = 0;
-  DepStat ds; ds.dep = 0; ds.over = 0; ds.flush = 0; ds.edep = 0.0;
+  DepStat ds; ds.dep = 0; ds.over = 0; ds.flush = 0; ds.tle_ent = 0; ds.tle_over = 0; ds.edep = 0.0;
   if (g.flags & F_ABSORB) {
     if (g.flags & F_CONV) n_conv = 1; else n_phot = 1;
     rng_begin(g.rng);
-    deposit(P, g, P.depbuf + (size_t)gslot * kDepBuf, ds, g.E * P.src.weight, g.mat, (g.flags & F_INVOL) != 0);
+    deposit<kTle>(P, g, P.depbuf + (size_t)gslot * kDepBuf, ds, g.E * P.src.weight, g.mat, (g.flags & F_INVOL) != 0, g.E, gslot);
     g.flags &= ~(F_ABSORB | F_CONV);
     c_edep += ds.edep;
   }
@@ -1106,6 +1199,13 @@ __device__ __noinline__ int phase_end(const Params &P, Smem &S, int slot, int gs
     next = locate(P, g);
     set_energy(P, S, slot, g);
     store_ph(S, slot, g);
+  } else if (kTle && (g.flags & F_OPEN) && P.tle_tab && __ldcg(&P.tle_state[gslot].w) != 0u) {
+    // the history's TLE table goes to the grids first: chunked, in the TLE phase; then back here
+    __stcg(&P.tle_state[gslot].x, __float_as_uint(-2.0f));
+    __stcg(&P.tle_state[gslot].y, 0u);
+    g.flags = (g.flags & ~F_NEXT) | ((unsigned)(Q_E - 1) << F_NEXT_SHIFT);
+    store_ph(S, slot, g);
+    next = Q_T;
   } else {
     if (g.flags & F_OPEN) {
       const int nbuf = (int)((g.flags & F_NBUF) >> F_NBUF_SHIFT);
@@ -1157,12 +1257,163 @@ __device__ __noinline__ int phase_end(const Params &P, Smem &S, int slot, int gs
     stat_bump(S, S_DEP, t >> 24);
   }
   stat_overflow(S, ds.over, ds.flush);
+  if (kTle) stat_tle_overflow(S, ds.tle_over, ds.tle_ent);
   return next;
+}
+
+// Q_T: the track-length estimator (GateTLEDoseActor::ScoreTLEDepositStep, GateTLEDoseActor.cpp:252-300).
+// The flight that just ended at the photon position started `seg` before it and, for a photon that is
+// leaving the volume, runs on to the exit face.  One Geant4 step of the reference is the chord of one
+// image voxel; every chord deposits edep = w * 0.1 * E * mu_en/rho * L * rho (dose = edep / rho) at a
+// point of the chord chosen by hit_type.  The voxel walk is an Amanatides-Woo traversal whose face
+// distances are always computed from the integer voxel index; a call walks kTleSteps chords and the
+// slot is queued again until the flight is done (lanes never wait for each other's long flights).
+// The same phase writes the per-history table out at the end of a history (tle_state.x == -2).
+template <typename LabelT>
+__device__ __noinline__ int phase_tle(const Params &P, Smem &S, int slot, int gslot) {
+  const unsigned fm = S.fm[slot];
+  uint4 st = __ldcg(P.tle_state + gslot);
+  float tcur = __uint_as_float(st.x);
+  unsigned nlist = st.w;
+  unsigned n_steps = 0, n_ent = 0, n_over = 0;
+  bool done = false;
+  if (tcur == -2.0f) {
+    DepEntry *tab = P.tle_tab + (size_t)gslot * kTleH;
+    const unsigned short *list = P.tle_list + (size_t)gslot * kTleMax;
+    unsigned j = st.y;
+    const unsigned jend = nlist < j + (unsigned)kTleSteps ? nlist : j + (unsigned)kTleSteps;
+    for (; j < jend; ++j) {
+      const unsigned hh = __ldcg(list + j);
+      grid_add(P, ld_dep(tab + hh));
+      __stcg(&tab[hh].key, kTleEmpty);
+      n_ent++;
+    }
+    done = j >= nlist;
+    st.y = j;
+    if (done) { st.x = __float_as_uint(-1.0f); st.y = 0u; st.w = 0u; }
+  } else {
+    const float p[3] = {S.px[slot], S.py[slot], S.pz[slot]};
+    const float d[3] = {S.dx[slot], S.dy[slot], S.dz[slot]};
+    const float seg = S.seg[slot], E = S.E[slot];
+    int ie; float fe;
+    bin_split(P, S.tbin[slot], ie, fe);
+    float to = 0.0f;
+    if (fm & F_EXIT) {
+      float ti; int ai, ao;
+      if (!ray_box_ax(p, d, P.half, ti, to, ai, ao)) to = 0.0f;
+    }
+    const float t_end = seg + to;
+    float s[3], inv_d[3];
+    int i[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      s[a] = __fmaf_rn(-d[a], seg, p[a]);
+      inv_d[a] = d[a] != 0.0f ? 1.0f / d[a] : 0.0f;
+    }
+    if (tcur < 0.0f) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        int v = (int)floorf(__fmaf_rn(s[a], P.inv_sp[a], P.hs[a]));
+        if (v < 0) v = 0;
+        if (v > P.n[a] - 1) v = P.n[a] - 1;
+        i[a] = v;
+      }
+      tcur = 0.0f;
+    } else {
+      i[0] = (int)(st.y & 0xffffu); i[1] = (int)(st.y >> 16); i[2] = (int)st.z;
+    }
+    const float kE = (0.1f * E) * P.src.weight;
+    Rng r;
+    {
+      const unsigned long long id = P.first + S.hidx[slot];
+      r.k0 = (uint32_t)P.seed; r.k1 = (uint32_t)(P.seed >> 32);
+      r.h0 = (uint32_t)id; r.h1 = (uint32_t)(id >> 32); r.blk = S.blk[slot]; r.pos = 4;
+    }
+    const LabelT *__restrict__ labels = reinterpret_cast<const LabelT *>(P.labels);
+    for (int it = 0; it < kTleSteps; ++it) {
+      float tn = kBig;
+      int ax = -1;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        float face;
+        if (d[a] > 0.0f) face = __fmaf_rn((float)(i[a] + 1), P.sp[a], -P.half[a]);
+        else if (d[a] < 0.0f) face = __fmaf_rn((float)i[a], P.sp[a], -P.half[a]);
+        else continue;
+        const float tb = (face - s[a]) * inv_d[a];
+        if (tb < tn) { tn = tb; ax = a; }
+      }
+      const bool last = !(tn < t_end);
+      const float tnext = last ? t_end : tn;
+      const float L = tnext - tcur;
+      if (L > 0.0f) {
+        const unsigned flat = (unsigned)i[0] + (unsigned)P.n[0] * ((unsigned)i[1] + (unsigned)P.n[1] * (unsigned)i[2]);
+        const int m = (int)__ldg(labels + flat);
+        const float rho = __ldg(P.dens + m);
+        n_steps++;
+        for (int a = 0; a < P.ndose; ++a) {
+          const DDose &D = P.dose[a];
+          if (!D.tle || !(E <= D.tle_thr)) continue;
+          const float2 mv = __ldg(D.muen2 + (size_t)ie * P.nmat + m);
+          const float muen = __fmaf_rn(fe, mv.y - mv.x, mv.x);
+          const float e = ((kE * muen) * L) * rho;
+          const float dd = e / rho;
+          int v;
+          if (D.aligned) {
+            v = (int)flat;
+          } else {
+            float fr = 1.0f;
+            if (D.hit_type == GATE_B200_HIT_RANDOM) fr = rng_uniform(r);
+            else if (D.hit_type == GATE_B200_HIT_MIDDLE) fr = 0.5f;
+            else if (D.hit_type == GATE_B200_HIT_PRE) fr = 0.0f;
+            const float tp = __fmaf_rn(fr, L, tcur);
+            const float pos[3] = {__fmaf_rn(d[0], tp, s[0]), __fmaf_rn(d[1], tp, s[1]), __fmaf_rn(d[2], tp, s[2])};
+            float ci[3];
+            aff_apply(D.v2i, pos, ci);
+            const float fx = floorf(ci[0] + 0.5f), fy = floorf(ci[1] + 0.5f), fz = floorf(ci[2] + 0.5f);
+            if (fx < 0.0f || fy < 0.0f || fz < 0.0f || fx >= (float)D.size[0] || fy >= (float)D.size[1] ||
+                fz >= (float)D.size[2])
+              continue;
+            v = (int)fx + D.size[0] * ((int)fy + D.size[1] * (int)fz);
+          }
+          const int key = (int)(((unsigned)a << 28) | (unsigned)v);
+          if (D.flags & (GATE_B200_SCORE_EDEP_SQ | GATE_B200_SCORE_DOSE_SQ)) {
+            tle_table_add(P, gslot, nlist, key, e, dd, 0, n_ent, n_over);
+          } else {
+            DepEntry z; z.key = key; z.e = e; z.d = dd; z.n = 0;
+            grid_add(P, z);
+            n_ent++;
+          }
+        }
+      }
+      if (last) { done = true; break; }
+      if (tnext > tcur) tcur = tnext;
+      // selects instead of i[ax]/d[ax]: a run-time index would push the walk state to local memory
+      const float dax = ax == 0 ? d[0] : (ax == 1 ? d[1] : d[2]);
+      const int stp = dax > 0.0f ? 1 : -1;
+      int iv;
+      if (ax == 0) { i[0] += stp; iv = i[0]; } else if (ax == 1) { i[1] += stp; iv = i[1]; } else { i[2] += stp; iv = i[2]; }
+      const int nax = ax == 0 ? P.n[0] : (ax == 1 ? P.n[1] : P.n[2]);
+      if (iv < 0 || iv >= nax) { done = true; break; }
+    }
+    S.blk[slot] = r.blk;
+    st.x = __float_as_uint(done ? -1.0f : tcur);
+    st.y = (unsigned)i[0] | ((unsigned)i[1] << 16);
+    st.z = (unsigned)i[2];
+    st.w = nlist;
+  }
+  __stcg(P.tle_state + gslot, st);
+  stat_add(S, S_TLE_STEPS, n_steps);
+  stat_add(S, S_TLE_ENT, n_ent);
+  stat_tle_overflow(S, n_over, 0u);
+  if (!done) return Q_T;
+  S.fm[slot] = fm & ~F_NEXT;
+  return (int)((fm & F_NEXT) >> F_NEXT_SHIFT) + 1;
 }
 
 // ------------------------------------------------------------------------------ kernel
 
-template <typename LabelT>
+// kTle: the engine has track-length-estimator actors (the plain kernel carries none of that code)
+template <typename LabelT, bool kTle>
 __global__ void __launch_bounds__(kThreads, 1) transport_kernel(const __grid_constant__ Params P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem &S = *reinterpret_cast<Smem *>(smem_raw);
@@ -1257,12 +1508,13 @@ __global__ void __launch_bounds__(kThreads, 1) transport_kernel(const __grid_con
         if (slot[w] >= 0) volume_gather_mu(P, vc[w]);
 #pragma unroll
       for (int w = 0; w < kVWidth; ++w)
-        if (slot[w] >= 0) next[w] = volume_decide(P, S, slot[w], vc[w], c_tent);
+        if (slot[w] >= 0) next[w] = volume_decide<kTle>(P, S, slot[w], slot_base + slot[w], vc[w], c_tent);
     } else if (slot[0] >= 0) {
-      if (q == Q_C) next[0] = phase_compton(P, S, slot[0], slot_base + slot[0], c_edep);
-      else if (q == Q_E) next[0] = phase_end(P, S, slot[0], slot_base + slot[0], c_edep);
+      if (q == Q_C) next[0] = phase_compton<kTle>(P, S, slot[0], slot_base + slot[0], c_edep);
+      else if (q == Q_E) next[0] = phase_end<kTle>(P, S, slot[0], slot_base + slot[0], c_edep);
       else if (q == Q_W) next[0] = phase_world(P, S, slot[0]);
-      else next[0] = phase_rare(P, S, slot[0], slot_base + slot[0], c_edep);
+      else if (kTle && q == Q_T) next[0] = phase_tle<LabelT>(P, S, slot[0], slot_base + slot[0]);
+      else next[0] = phase_rare<kTle>(P, S, slot[0], slot_base + slot[0], c_edep);
     }
     __syncwarp();
     __threadfence_block();   // slot state visible before the slot is published again

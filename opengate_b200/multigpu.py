@@ -51,8 +51,11 @@ def reduce_dose_grids(engine, actor_ids, setup_or_flags, dst=0, group=None):
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
+    descs = None
+    if hasattr(setup_or_flags, "dose"):   # dose actors first, then the TLE dose actors (engine id order)
+        descs = list(setup_or_flags.dose) + [t[0] for t in getattr(setup_or_flags, "tle", [])]
     for i, a in enumerate(actor_ids):
-        flags = setup_or_flags.dose[i].score_flags if hasattr(setup_or_flags, "dose") else setup_or_flags[i]
+        flags = descs[i].score_flags if descs is not None else setup_or_flags[i]
         for w in active_grids(flags):
             dist.reduce(grid_tensor(engine, a, w), dst=dst, op=dist.ReduceOp.SUM, group=group)
 

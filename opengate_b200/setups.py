@@ -116,6 +116,8 @@ class LowLevelSetup:
     dose: list = field(default_factory=list)          # DoseDesc
     phsp: list = field(default_factory=list)          # PhspDesc
     n_primaries: int = 0
+    tle: list = field(default_factory=list)           # (DoseDesc, TleDesc, keepalive): TLE dose actors
+    materials: list = field(default_factory=list)     # MaterialSpec per label (for the mu_en database)
 
     def apply(self, eng):
         eng.set_tables(self.tables)
@@ -123,8 +125,20 @@ class LowLevelSetup:
         eng.set_image_volume(self.labels, self.spacing, self.world_to_volume)
         sids = [eng.add_source(s, keep) for s, keep in self.sources]
         dids = [eng.add_dose_actor(d) for d in self.dose]
+        dids += [eng.add_tle_dose_actor(d, t, keep) for d, t, keep in self.tle]
         pids = [eng.add_phsp_actor(p) for p in self.phsp]
         return sids, dids, pids
+
+    def add_tle_actor(self, size, world_to_index, flags, hit_type=abi.HIT_RANDOM, threshold=float("inf"),
+                      energy_min=0.0, database="EPDL"):
+        """Attach a TLEDoseActor (GateTLEDoseActor): mu_en/rho per material from the reference's element
+        database evaluated on the table's energy nodes (mu_handler)."""
+        from . import mu_handler
+        muen = mu_handler.mu_en_table_on_grid(self.materials, self.tables.energy, database)
+        d = abi.make_dose_desc(size, world_to_index, flags, hit_type)
+        t, keep = abi.make_tle_desc(muen, threshold, energy_min)
+        self.tle.append((d, t, keep))
+        return len(self.dose) + len(self.tle) - 1
 
 
 def identity34():
@@ -167,7 +181,8 @@ def make_c1(n_primaries=1_000_000, flags=abi.SCORE_EDEP | abi.SCORE_EDEP_SQ, hit
     A = dose_world_to_index(grid, (spacing_mm,) * 3)
     d = abi.make_dose_desc(grid, A, flags, hit_type)
     return LowLevelSetup("C1 1MeV pencil beam / 30 cm water box / 2 mm DoseActor", seed, T, (500, 500, 500), 1,
-                         labels, (300.0, 300.0, 300.0), identity34(), [(s, keep)], [d], [], n_primaries)
+                         labels, (300.0, 300.0, 300.0), identity34(), [(s, keep)], [d], [], n_primaries,
+                         materials=mats)
 
 
 def make_c2(n=256, n_primaries=100_000_000, flags=abi.SCORE_EDEP | abi.SCORE_EDEP_SQ | abi.SCORE_DOSE | abi.SCORE_DOSE_SQ,
@@ -192,7 +207,7 @@ def make_c2(n=256, n_primaries=100_000_000, flags=abi.SCORE_EDEP | abi.SCORE_EDE
     wm = names.index("Air")
     return LowLevelSetup(f"C2 6MV 10x10 / {n}^3 slab water-lung-bone / DoseActor dose+uncertainty", seed, T,
                          (half + 200, half + 200, half + 200), wm, labels, (1.0, 1.0, 1.0), identity34(),
-                         [(s, keep)], [d], [], n_primaries)
+                         [(s, keep)], [d], [], n_primaries, materials=mats)
 
 
 def schneider_materials(tol_g_cm3=0.05):
@@ -240,7 +255,7 @@ def make_c3(nx=512, ny=512, nz=300, n_primaries=1_000_000_000, seed=987654321,
     wh = tuple(float(max(h + 100.0, source_distance + 100.0)) for h in half)
     return LowLevelSetup(f"C3 120kVp cone / {nx}x{ny}x{nz} synthetic CT Schneider({len(names)} mat) / DoseActor dose+edep2",
                          seed, T, wh, names.index("G4_AIR"), labels, tuple(spacing), identity34(), [(s, keep)], [d], [],
-                         n_primaries)
+                         n_primaries, materials=mats)
 
 
 def make_c4(nx=256, ny=256, nz=150, spacing=(2.0, 2.0, 2.0), n_act=128, act_spacing=4.0, n_primaries=1_000_000_000,
@@ -275,4 +290,4 @@ def make_c4(nx=256, ny=256, nz=150, spacing=(2.0, 2.0, 2.0), n_act=128, act_spac
     d = abi.make_dose_desc((nx, ny, nz), A, abi.SCORE_EDEP, abi.HIT_POST)
     return LowLevelSetup(f"C4 Tc-99m VoxelSource {n_act}^3 / {nx}x{ny}x{nz} CT / PhaseSpace plane entering", seed, T,
                          (400.0, 400.0, 400.0), names.index("G4_AIR"), labels, tuple(spacing), identity34(),
-                         [(s, keep)], [d], [p], n_primaries)
+                         [(s, keep)], [d], [p], n_primaries, materials=mats)

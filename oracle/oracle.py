@@ -63,6 +63,7 @@ def lib():
                                               C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.oracle_add_source.argtypes = [C.c_void_p, C.POINTER(abi.Source)]
         L.oracle_add_dose_actor.argtypes = [C.c_void_p, C.POINTER(abi.DoseDesc)]
+        L.oracle_add_tle_dose_actor.argtypes = [C.c_void_p, C.POINTER(abi.DoseDesc), C.POINTER(abi.TleDesc)]
         L.oracle_add_phsp_actor.argtypes = [C.c_void_p, C.POINTER(abi.PhspDesc)]
         L.oracle_begin_run.argtypes = [C.c_void_p]
         L.oracle_run_source.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_int]
@@ -126,6 +127,11 @@ class TransportOracle:
     def add_dose_actor(self, desc):
         self._dose_sizes.append(tuple(desc.size))
         return self.L.oracle_add_dose_actor(self.h, C.byref(desc))
+
+    def add_tle_dose_actor(self, desc, tle_desc, keep=None):
+        self._keep.append(keep)
+        self._dose_sizes.append(tuple(desc.size))
+        return self.L.oracle_add_tle_dose_actor(self.h, C.byref(desc), C.byref(tle_desc))
 
     def add_phsp_actor(self, desc):
         return self.L.oracle_add_phsp_actor(self.h, C.byref(desc))

@@ -162,6 +162,10 @@ static float rng_uniform(rng_t *r) {
 #define ORACLE_MAX_DOSE 4
 #define DEP_BUF 32
 #define WOODCOCK_K 4
+#define TLE_STEPS 16   /* voxel chords per call of the device's march phase (each call: fresh Philox block) */
+#define TLE_H 4096     /* per-history table of (actor, voxel) sums of a TLE actor with squares */
+#define TLE_MAX 3072   /* entries at which the table is written out (counted as an overflow) */
+#define TLE_EMPTY (-1)
 #define MAX_BLOCKS 4000000u
 #define NUDGE 1.0e-3f
 #define BIG 3.0e38f
@@ -185,6 +189,10 @@ typedef struct {
   affine_t v2i;      /* phantom-local point -> continuous index */
   int flags, hit_type;
   double *grid[5];
+  /* track-length estimator (GateTLEDoseActor): tle = 1, aligned = the grid is the image grid */
+  int tle, aligned;
+  float tle_thr;
+  float *muen;       /* [nmat][ne] mu_en/rho, cm2/g */
 } odose_t;
 
 typedef struct {
@@ -213,6 +221,9 @@ struct oracle_engine {
   /* actors, sources */
   int nsrc; osource_t *src;
   int ndose; odose_t dose[ORACLE_MAX_DOSE];
+  int ntle;            /* dose actors that are track-length estimators */
+  float tle_emin;      /* max energy_min over them */
+  float tle_thr_max;   /* max threshold over them */
   int nphsp; ophsp_t phsp[ORACLE_MAX_PHSP];
   gate_b200_stats stats;
   char err[256];
@@ -232,6 +243,7 @@ typedef struct {
   int stored;
   uint64_t hist;
   dep_t buf[DEP_BUF]; int nbuf;
+  dep_t *ttab; uint16_t *tlist; int nlist;   /* TLE table of this history (thread scratch) */
   gate_b200_stats st;
   oracle_trace *trace;
 } hist_t;
@@ -321,10 +333,20 @@ static float tab(const float *t, int ne, int m, int ie, float fe) {
 
 /* ------------------------------------------------------------------ scoring */
 
+static void grid_add(oracle_engine *g, const dep_t *b);
+
 static void flush_buffer(hist_t *h) {
   oracle_engine *g = h->g;
   for (int j = 0; j < h->nbuf; ++j) {
-    dep_t *b = &h->buf[j];
+    grid_add(g, &h->buf[j]);
+    h->st.flushed_entries++;
+  }
+  h->nbuf = 0;
+}
+
+/* one (actor, voxel) sum of one history -> the fp64 grids */
+static void grid_add(oracle_engine *g, const dep_t *b) {
+  {
     int a = (int)((uint32_t)b->key >> 28);
     int v = b->key & 0x0fffffff;
     odose_t *D = &g->dose[a];
@@ -348,13 +370,43 @@ static void flush_buffer(hist_t *h) {
 #pragma omp atomic
       D->grid[GATE_B200_GRID_COUNTS][v] += (double)b->n;
     }
-    h->st.flushed_entries++;
   }
-  h->nbuf = 0;
 }
 
-/* deposit e (already weighted) at the current phantom-frame point, material m */
-static void deposit(hist_t *h, float e, int m, int vix, int viy, int viz) {
+/* ---- per-history table of a TLE actor that scores squares: open addressing, Fibonacci hash */
+static void tle_flush(hist_t *h) {
+  for (int j = 0; j < h->nlist; ++j) {
+    dep_t *b = &h->ttab[h->tlist[j]];
+    grid_add(h->g, b);
+    b->key = TLE_EMPTY;
+    h->st.tle_entries++;
+  }
+  h->nlist = 0;
+}
+static void tle_table_add(hist_t *h, int key, float e, float d, int n) {
+  uint32_t hh = ((uint32_t)key * 2654435761u) >> 20;   /* 32 - log2(TLE_H) */
+  for (;;) {
+    dep_t *b = &h->ttab[hh];
+    if (b->key == key) { b->e += e; b->d += d; b->n += n; return; }
+    if (b->key == TLE_EMPTY) {
+      if (h->nlist == TLE_MAX) {   /* table full: write it out, start again (squares of this history split) */
+        tle_flush(h);
+        h->st.tle_overflows++;
+        hh = ((uint32_t)key * 2654435761u) >> 20;
+        b = &h->ttab[hh];
+      }
+      b->key = key; b->e = e; b->d = d; b->n = n;
+      h->tlist[h->nlist++] = (uint16_t)hh;
+      return;
+    }
+    hh = (hh + 1u) & (TLE_H - 1u);
+  }
+}
+
+/* deposit e (already weighted) at the current phantom-frame point, material m.  e_tle: flight energy
+ * of the gamma whose secondaries deposit here (a TLE actor ignores them while that gamma scores by
+ * track length, GateTLEDoseActor.cpp:236-243); BIG for a gamma absorbed below the cut (always scored). */
+static void deposit(hist_t *h, float e, int m, int vix, int viy, int viz, float e_tle) {
   oracle_engine *g = h->g;
   h->st.edep_total_MeV += (double)e;
   h->st.deposits++;
@@ -365,6 +417,7 @@ static void deposit(hist_t *h, float e, int m, int vix, int viy, int viz) {
   if (!h->in_phantom) return; /* dose actors are attached to the image volume */
   for (int a = 0; a < g->ndose; ++a) {
     odose_t *D = &g->dose[a];
+    if (D->tle && e_tle <= D->tle_thr) continue;
     float pos[3] = {h->p[0], h->p[1], h->p[2]};
     if (D->hit_type != GATE_B200_HIT_POST) {
       /* GateDoseActor.cpp:144-178: pre/random/middle between the Geant4 pre and post step
@@ -400,6 +453,10 @@ static void deposit(hist_t *h, float e, int m, int vix, int viy, int viz) {
     int v = (int)fx + D->size[0] * ((int)fy + D->size[1] * (int)fz);
     int key = (int)(((uint32_t)a << 28) | (uint32_t)v);
     float dd = e / g->dens[m];
+    if (D->tle && (D->flags & (GATE_B200_SCORE_EDEP_SQ | GATE_B200_SCORE_DOSE_SQ))) {
+      tle_table_add(h, key, e, dd, 1);
+      continue;
+    }
     int j;
     for (j = 0; j < h->nbuf; ++j)
       if (h->buf[j].key == key) break;
@@ -485,7 +542,7 @@ static int interact(hist_t *h, int proc, int m, int vix, int viy, int viz, float
   if (proc == 0) { /* photoelectric: everything stays here (kerma, fluorescence not tracked) */
     h->st.n_phot++;
     rng_begin(&h->rng);
-    deposit(h, h->E * h->w, m, vix, viy, viz);
+    deposit(h, h->E * h->w, m, vix, viy, viz, h->E);
     return 0;
   }
   if (proc == 1) { /* Compton: Klein-Nishina composition-rejection x scattering function */
@@ -533,12 +590,12 @@ static int interact(hist_t *h, int proc, int m, int vix, int viy, int viz, float
     float sphi, cphi;
     o_sincos2pi(rng_uniform(&h->rng), &sphi, &cphi);
     float E1 = eps * E;
-    deposit(h, (E - E1) * h->w, m, vix, viy, viz);
+    deposit(h, (E - E1) * h->w, m, vix, viy, viz, E);
     rotate_dir(h->d, cost, sint, sphi, cphi);
     h->E = E1;
     h->seg = 0.0f;
-    if (E1 < g->e_cut) {
-      deposit(h, E1 * h->w, m, vix, viy, viz);
+    if (E1 < g->e_cut || (h->in_phantom && E1 <= g->tle_emin)) {
+      deposit(h, E1 * h->w, m, vix, viy, viz, BIG);
       return 0;
     }
     update_energy(h);
@@ -590,10 +647,10 @@ static int interact(hist_t *h, int proc, int m, int vix, int viy, int viz, float
   rng_begin(&h->rng);
   if (g->pair_mode == 0) {
     /* production cuts >> range with apply_cuts: e-, e+ (and its 2 mc2) stay on the spot */
-    deposit(h, h->E * h->w, m, vix, viy, viz);
+    deposit(h, h->E * h->w, m, vix, viy, viz, h->E);
     return 0;
   }
-  deposit(h, (h->E - 2.0f * MC2) * h->w, m, vix, viy, viz);
+  deposit(h, (h->E - 2.0f * MC2) * h->w, m, vix, viy, viz, h->E);
   {
     float cost = 2.0f * rng_uniform(&h->rng) - 1.0f;
     float sint = sqrtf(1.0f - cost * cost);
@@ -782,6 +839,92 @@ static void phsp_store(hist_t *h, int k, int flag) {
   r->flags = flag;
 }
 
+/* ------------------------------------------------------------------ track-length estimator */
+
+/* Score the straight flight that ends at h->p (volume frame): it started h->seg before and, when the
+ * gamma is leaving the volume, continues for `to` up to the exit face.  One Geant4 step of the
+ * reference = the chord of one image voxel (GateImageNestedParameterisation); each chord deposits
+ * edep = w * 0.1 * E * mu_en/rho * L * rho at a point chosen by hit_type and dose = edep / rho
+ * (GateTLEDoseActor::ScoreTLEDepositStep, GateTLEDoseActor.cpp:252-300).  The voxel walk is an
+ * Amanatides-Woo traversal whose face distances are always computed from the integer voxel index.
+ * The device runs the walk in calls of TLE_STEPS iterations, each on a fresh Philox block. */
+static void tle_march(hist_t *h, float to) {
+  oracle_engine *g = h->g;
+  if (!g->ntle || !(h->E <= g->tle_thr_max)) return;
+  const float t_end = h->seg + to;
+  float s[3], inv_d[3];
+  int i[3];
+  for (int a = 0; a < 3; ++a) {
+    s[a] = fmaf(-h->d[a], h->seg, h->p[a]);
+    inv_d[a] = h->d[a] != 0.0f ? 1.0f / h->d[a] : 0.0f;
+    int v = (int)floorf(fmaf(s[a], g->inv_sp[a], g->hs[a]));
+    if (v < 0) v = 0;
+    if (v > g->n[a] - 1) v = g->n[a] - 1;
+    i[a] = v;
+  }
+  const float kE = (0.1f * h->E) * h->w;
+  float tcur = 0.0f;
+  for (int it = 0;; ++it) {
+    if (it % TLE_STEPS == 0) rng_begin(&h->rng);
+    float tn = BIG;
+    int ax = -1;
+    for (int a = 0; a < 3; ++a) {
+      float face;
+      if (h->d[a] > 0.0f) face = fmaf((float)(i[a] + 1), g->sp[a], -g->half[a]);
+      else if (h->d[a] < 0.0f) face = fmaf((float)i[a], g->sp[a], -g->half[a]);
+      else continue;
+      float tb = (face - s[a]) * inv_d[a];
+      if (tb < tn) { tn = tb; ax = a; }
+    }
+    const int last = !(tn < t_end);
+    const float tnext = last ? t_end : tn;
+    const float L = tnext - tcur;
+    if (L > 0.0f) {
+      const size_t flat = (size_t)i[0] + (size_t)g->n[0] * ((size_t)i[1] + (size_t)g->n[1] * (size_t)i[2]);
+      const int m = g->label_bytes == 1 ? (int)((const uint8_t *)g->labels)[flat] : (int)((const uint16_t *)g->labels)[flat];
+      const float rho = g->dens[m];
+      h->st.tle_steps++;
+      for (int a = 0; a < g->ndose; ++a) {
+        odose_t *D = &g->dose[a];
+        if (!D->tle || !(h->E <= D->tle_thr)) continue;
+        const float muen = tab(D->muen, g->ne, m, h->ie, h->fe);
+        const float e = ((kE * muen) * L) * rho;
+        const float dd = e / rho;
+        int v;
+        if (D->aligned) {
+          v = (int)flat;
+        } else {
+          float fr = 1.0f;
+          if (D->hit_type == GATE_B200_HIT_RANDOM) fr = rng_uniform(&h->rng);
+          else if (D->hit_type == GATE_B200_HIT_MIDDLE) fr = 0.5f;
+          else if (D->hit_type == GATE_B200_HIT_PRE) fr = 0.0f;
+          const float tp = fmaf(fr, L, tcur);
+          float pos[3] = {fmaf(h->d[0], tp, s[0]), fmaf(h->d[1], tp, s[1]), fmaf(h->d[2], tp, s[2])};
+          float c[3];
+          aff_apply(&D->v2i, pos, c);
+          float fx = floorf(c[0] + 0.5f), fy = floorf(c[1] + 0.5f), fz = floorf(c[2] + 0.5f);
+          if (fx < 0.0f || fy < 0.0f || fz < 0.0f || fx >= (float)D->size[0] || fy >= (float)D->size[1] ||
+              fz >= (float)D->size[2])
+            continue;
+          v = (int)fx + D->size[0] * ((int)fy + D->size[1] * (int)fz);
+        }
+        const int key = (int)(((uint32_t)a << 28) | (uint32_t)v);
+        if (D->flags & (GATE_B200_SCORE_EDEP_SQ | GATE_B200_SCORE_DOSE_SQ)) {
+          tle_table_add(h, key, e, dd, 0);
+        } else {
+          dep_t b; b.key = key; b.e = e; b.d = dd; b.n = 0;
+          grid_add(g, &b);
+          h->st.tle_entries++;
+        }
+      }
+    }
+    if (last) break;
+    if (tnext > tcur) tcur = tnext;
+    i[ax] += h->d[ax] > 0.0f ? 1 : -1;
+    if (i[ax] < 0 || i[ax] >= g->n[ax]) break;
+  }
+}
+
 /* ------------------------------------------------------------------ one history */
 
 static void to_phantom(hist_t *h) {
@@ -890,6 +1033,7 @@ static void run_photon(hist_t *h, float pend_p[3], float pend_d[3], int *pend) {
           float ti, to;
           int ai, ao;
           if (!ray_box_ax(h->p, h->d, g->half, &ti, &to, &ai, &ao)) { to = 0.0f; ao = -1; }
+          tle_march(h, to);
           for (int a = 0; a < 3; ++a) h->p[a] = h->p[a] + h->d[a] * to;
           snap_to_face(h->p, h->d, g->half, ao, 1);
           h->path += to;
@@ -910,6 +1054,7 @@ static void run_photon(hist_t *h, float pend_p[3], float pend_d[3], int *pend) {
         float t = u[2 * k + 1] * maj;
         if (t <= mu) {
           int proc = select_process(h, m, t / mu);
+          tle_march(h, 0.0f);
           alive = interact(h, proc, m, ix, iy, iz, pend_p, pend_d, pend);
           break;
         }
@@ -918,11 +1063,14 @@ static void run_photon(hist_t *h, float pend_p[3], float pend_d[3], int *pend) {
   }
 }
 
+typedef struct { dep_t *tab; uint16_t *list; } tle_scratch;
+
 static void run_history(oracle_engine *g, const osource_t *s, uint64_t hist, gate_b200_stats *acc,
-                        oracle_trace *trace) {
+                        oracle_trace *trace, tle_scratch *ts) {
   hist_t h;
   memset(&h, 0, sizeof h);
   h.g = g; h.hist = hist; h.trace = trace;
+  h.ttab = ts->tab; h.tlist = ts->list; h.nlist = 0;
   if (trace) { trace->n_dep = 0; trace->n_iter = 0; }
   rng_init(&h.rng, g->seed, hist);
   generate_primary(&h, s);
@@ -974,6 +1122,7 @@ static void run_history(oracle_engine *g, const osource_t *s, uint64_t hist, gat
     run_photon(&h, pend_p, pend_d, &pend2);
   }
   flush_buffer(&h);
+  tle_flush(&h);
   if (g->nphsp > 0 && !h.stored) h.st.absorbed_events++;
   /* accumulate */
   acc->histories += h.st.histories; acc->tracks += h.st.tracks; acc->steps += h.st.steps;
@@ -983,6 +1132,7 @@ static void run_history(oracle_engine *g, const osource_t *s, uint64_t hist, gat
   acc->flushed_entries += h.st.flushed_entries; acc->buffer_overflows += h.st.buffer_overflows;
   acc->escaped += h.st.escaped; acc->absorbed_events += h.st.absorbed_events;
   acc->edep_total_MeV += h.st.edep_total_MeV;
+  acc->tle_steps += h.st.tle_steps; acc->tle_entries += h.st.tle_entries; acc->tle_overflows += h.st.tle_overflows;
   if (trace) {
     trace->E_end = h.E;
     trace->edep = (float)h.st.edep_total_MeV;
@@ -1014,6 +1164,7 @@ void oracle_destroy(oracle_engine *g) {
   free(g->src);
   for (int a = 0; a < g->ndose; ++a)
     for (int k = 0; k < 5; ++k) free(g->dose[a].grid[k]);
+  for (int a = 0; a < g->ndose; ++a) free(g->dose[a].muen);
   for (int k = 0; k < g->nphsp; ++k) free(g->phsp[k].rows);
   free(g);
 }
@@ -1148,6 +1299,35 @@ int oracle_add_dose_actor(oracle_engine *g, const gate_b200_dose_desc *d) {
   return g->ndose++;
 }
 
+/* the grid is the image grid when volume point -> index is p / spacing + n / 2 - 1 / 2 on the image's
+ * own lattice: then the voxel of a chord is the image voxel and hit_type cannot matter */
+static int grid_is_image_grid(const oracle_engine *g, const odose_t *D) {
+  for (int a = 0; a < 3; ++a) {
+    if (D->size[a] != g->n[a]) return 0;
+    for (int c = 0; c < 3; ++c) {
+      double want = a == c ? 1.0 / (double)g->sp[a] : 0.0;
+      if (fabs((double)D->v2i.m[3 * a + c] - want) > 1.0e-6 * (1.0 / (double)g->sp[a])) return 0;
+    }
+    if (fabs((double)D->v2i.t[a] - (0.5 * (double)g->n[a] - 0.5)) > 1.0e-4) return 0;
+  }
+  return 1;
+}
+
+int oracle_add_tle_dose_actor(oracle_engine *g, const gate_b200_dose_desc *d, const gate_b200_tle_desc *t) {
+  int id = oracle_add_dose_actor(g, d);
+  if (id < 0) return id;
+  odose_t *D = &g->dose[id];
+  D->tle = 1;
+  D->tle_thr = t->energy_threshold_MeV > 3.0e38 ? BIG : (float)t->energy_threshold_MeV;
+  D->muen = dup_f(t->mu_en_over_rho, (size_t)g->nmat * g->ne);
+  D->aligned = grid_is_image_grid(g, D);
+  float emin = (float)t->energy_min_MeV;
+  if (g->ntle == 0 || emin > g->tle_emin) g->tle_emin = emin;
+  if (g->ntle == 0 || D->tle_thr > g->tle_thr_max) g->tle_thr_max = D->tle_thr;
+  g->ntle++;
+  return id;
+}
+
 int oracle_add_phsp_actor(oracle_engine *g, const gate_b200_phsp_desc *d) {
   if (g->nphsp >= ORACLE_MAX_PHSP) return -1;
   ophsp_t *P = &g->phsp[g->nphsp];
@@ -1170,6 +1350,13 @@ void oracle_begin_run(oracle_engine *g) {
   for (int k = 0; k < g->nphsp; ++k) { g->phsp[k].n_rows = 0; g->phsp[k].n_dropped = 0; }
 }
 
+static void tle_scratch_init(tle_scratch *ts) {
+  ts->tab = (dep_t *)malloc(TLE_H * sizeof(dep_t));
+  ts->list = (uint16_t *)malloc(TLE_MAX * sizeof(uint16_t));
+  for (int i = 0; i < TLE_H; ++i) ts->tab[i].key = TLE_EMPTY;
+}
+static void tle_scratch_free(tle_scratch *ts) { free(ts->tab); free(ts->list); }
+
 int oracle_run_source(oracle_engine *g, int source_id, uint64_t first, uint64_t n, int n_threads) {
   const osource_t *s = &g->src[source_id];
   gate_b200_stats total;
@@ -1180,8 +1367,11 @@ int oracle_run_source(oracle_engine *g, int source_id, uint64_t first, uint64_t 
   {
     gate_b200_stats acc;
     memset(&acc, 0, sizeof acc);
+    tle_scratch ts;
+    tle_scratch_init(&ts);
 #pragma omp for schedule(dynamic, 256)
-    for (int64_t i = 0; i < (int64_t)n; ++i) run_history(g, s, first + (uint64_t)i, &acc, NULL);
+    for (int64_t i = 0; i < (int64_t)n; ++i) run_history(g, s, first + (uint64_t)i, &acc, NULL, &ts);
+    tle_scratch_free(&ts);
 #pragma omp critical
     {
       total.histories += acc.histories; total.tracks += acc.tracks; total.steps += acc.steps;
@@ -1191,11 +1381,17 @@ int oracle_run_source(oracle_engine *g, int source_id, uint64_t first, uint64_t 
       total.flushed_entries += acc.flushed_entries; total.buffer_overflows += acc.buffer_overflows;
       total.escaped += acc.escaped; total.absorbed_events += acc.absorbed_events;
       total.edep_total_MeV += acc.edep_total_MeV;
+      total.tle_steps += acc.tle_steps; total.tle_entries += acc.tle_entries; total.tle_overflows += acc.tle_overflows;
     }
   }
 #else
   (void)n_threads;
-  for (uint64_t i = 0; i < n; ++i) run_history(g, s, first + i, &total, NULL);
+  {
+    tle_scratch ts;
+    tle_scratch_init(&ts);
+    for (uint64_t i = 0; i < n; ++i) run_history(g, s, first + i, &total, NULL, &ts);
+    tle_scratch_free(&ts);
+  }
 #endif
   gate_b200_stats *S = &g->stats;
   S->histories += total.histories; S->tracks += total.tracks; S->steps += total.steps;
@@ -1205,6 +1401,7 @@ int oracle_run_source(oracle_engine *g, int source_id, uint64_t first, uint64_t 
   S->flushed_entries += total.flushed_entries; S->buffer_overflows += total.buffer_overflows;
   S->escaped += total.escaped; S->absorbed_events += total.absorbed_events;
   S->edep_total_MeV += total.edep_total_MeV;
+  S->tle_steps += total.tle_steps; S->tle_entries += total.tle_entries; S->tle_overflows += total.tle_overflows;
   S->phsp_rows = 0; S->phsp_dropped = 0;
   for (int k = 0; k < g->nphsp; ++k) {
     uint64_t stored = g->phsp[k].n_rows < g->phsp[k].capacity ? g->phsp[k].n_rows : g->phsp[k].capacity;
@@ -1216,7 +1413,10 @@ int oracle_run_source(oracle_engine *g, int source_id, uint64_t first, uint64_t 
 int oracle_trace_history(oracle_engine *g, int source_id, uint64_t hist, oracle_trace *out) {
   gate_b200_stats acc;
   memset(&acc, 0, sizeof acc);
-  run_history(g, &g->src[source_id], hist, &acc, out);
+  tle_scratch ts;
+  tle_scratch_init(&ts);
+  run_history(g, &g->src[source_id], hist, &acc, out, &ts);
+  tle_scratch_free(&ts);
   return 0;
 }
 

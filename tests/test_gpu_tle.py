@@ -1,0 +1,109 @@
+"""GPU parity of the track-length estimator (TLEDoseActor): the CUDA engine through the C-ABI against
+the CPU oracle on identical inputs.  Counters are bit-exact; the fp64 grids differ only by the order of
+the double additions (rtol 1e-12); per-history sums are float and order-deterministic on both sides."""
+import numpy as np
+import pytest
+
+from opengate_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+from test_gpu_parity import INT_KEYS, run_both  # noqa: E402
+from tle_setups import SQ, c1_tle, c3_tle, c4_tle, long_thin  # noqa: E402
+
+TLE_KEYS = ["tle_steps", "tle_entries", "tle_overflows"]
+GRIDS = ((abi.GRID_EDEP, abi.SCORE_EDEP), (abi.GRID_EDEP_SQ, abi.SCORE_EDEP_SQ), (abi.GRID_DOSE, abi.SCORE_DOSE),
+         (abi.GRID_DOSE_SQ, abi.SCORE_DOSE_SQ), (abi.GRID_COUNTS, abi.SCORE_COUNTS))
+
+
+def compare_all(eng, orc, S, ids):
+    se, de, pe = ids
+    a, b = eng.stats(), orc.stats()
+    for k in INT_KEYS + TLE_KEYS:
+        assert a[k] == b[k], (k, a[k], b[k])
+    descs = list(S.dose) + [t[0] for t in S.tle]
+    for d in de:
+        flags = descs[d].score_flags | abi.SCORE_EDEP
+        for which, fl in GRIDS:
+            if not flags & fl:
+                continue
+            g, o = eng.dose_grid(d, which), orc.dose_grid(d, which)
+            assert np.array_equal(g != 0, o != 0), f"support differs actor {d} grid {which}"
+            np.testing.assert_allclose(g, o, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("mk,kw", [
+    (c1_tle, {}),                                        # unaligned grid, random point on the chord (rng in the march)
+    (c1_tle, {"hit": abi.HIT_MIDDLE}),
+    (c1_tle, {"hit": abi.HIT_PRE, "flags": abi.SCORE_EDEP | abi.SCORE_DOSE}),
+    (c3_tle, {}),                                        # aligned grid, per-history table (squares)
+    (c3_tle, {"flags": abi.SCORE_EDEP | abi.SCORE_DOSE}),  # no squares: direct warp-aggregated atomics
+    (c3_tle, {"coarse": True}),                          # coarser, unaligned grid
+    (c3_tle, {"threshold": 0.06}),                       # hybrid: analog above 60 keV
+    (c3_tle, {"threshold": 0.0, "hit": abi.HIT_POST}),   # never TLE
+    (c3_tle, {"energy_min": 0.03}),                      # gammas at or below 30 keV stop on the spot
+    (c4_tle, {}),                                        # primaries born inside the volume, phase-space plane
+])
+def test_tle_engine_matches_oracle(cuda_required, mk, kw):
+    n = 6000
+    S = mk(n, **kw)
+    eng, orc, ids = run_both(S, n)
+    compare_all(eng, orc, S, ids)
+    if kw.get("threshold", 1.0) > 0:
+        assert eng.stats()["tle_steps"] > 0
+    eng.close()
+
+
+def test_tle_table_overflow_matches_oracle(cuda_required):
+    S = long_thin(300)
+    eng, orc, ids = run_both(S, 300)
+    compare_all(eng, orc, S, ids)
+    assert eng.stats()["tle_overflows"] > 0
+    eng.close()
+
+
+def test_tle_split_launches_and_offsets(cuda_required):
+    # the same histories in one launch or three, starting at an offset: identical sums
+    from opengate_b200.core import Engine
+    S = c3_tle(9000)
+    e1, e3 = Engine(0, S.seed), Engine(0, S.seed)
+    s1, d1, _ = S.apply(e1)
+    s3, d3, _ = S.apply(e3)
+    e1.begin_run(); e3.begin_run()
+    e1.run_source(s1[0], 1000, 9000)
+    for k in range(3):
+        e3.run_source(s3[0], 1000 + 3000 * k, 3000)
+    e1.sync(); e3.sync()
+    for which in (abi.GRID_EDEP, abi.GRID_EDEP_SQ, abi.GRID_DOSE, abi.GRID_DOSE_SQ):
+        np.testing.assert_allclose(e1.dose_grid(d1[-1], which), e3.dose_grid(d3[-1], which), rtol=1e-12)
+    assert e1.stats()["tle_steps"] == e3.stats()["tle_steps"]
+    e1.close(); e3.close()
+
+
+def test_tle_full_size_c3_properties(cuda_required):
+    # BASELINE config 3 at full size (512x512x300, 75 materials): analog DoseActor + TLEDoseActor in one
+    # run, the reference's own acceptance pattern (test081): totals and depth profile agree
+    from opengate_b200 import setups
+    from opengate_b200.core import Engine
+    n = 2_000_000
+    S = setups.make_c3(n_primaries=n, flags=abi.SCORE_EDEP | abi.SCORE_DOSE)
+    A = np.array(S.dose[0].world_to_index[:]).reshape(3, 4)
+    S.add_tle_actor(tuple(S.dose[0].size), A, SQ, database="EPDL")
+    eng = Engine(0, S.seed)
+    sid, did, _ = S.apply(eng)
+    eng.begin_run()
+    eng.run_source(sid[0], 0, n)
+    eng.sync()
+    st = eng.stats()
+    assert st["histories"] == n and st["tle_overflows"] <= n // 100000   # histories touching > 3072 voxels
+    ea, et = eng.dose_grid(did[0], abi.GRID_EDEP), eng.dose_grid(did[1], abi.GRID_EDEP)
+    assert et.sum() == pytest.approx(ea.sum(), rel=0.01)
+    pa, pt = ea.sum(axis=(0, 1)), et.sum(axis=(0, 1))
+    sa, stt = pa.reshape(16, -1).sum(axis=1), pt.reshape(16, -1).sum(axis=1)
+    big = sa > 0.01 * sa.sum()
+    np.testing.assert_allclose(stt[big], sa[big], rtol=0.05)
+    # variance reduction: many more voxels see a score, and the per-voxel relative uncertainty drops
+    assert (et > 0).sum() > 5 * (ea > 0).sum()
+    e2 = eng.dose_grid(did[1], abi.GRID_EDEP_SQ)
+    assert np.all(e2[et > 0] > 0) and np.all(e2 * n >= et * et * (1 - 1e-9))   # Cauchy-Schwarz per voxel
+    eng.close()

@@ -461,6 +461,40 @@ def _resample_nearest_like(dimg, size, spacing, translation):
     return gimage.Image(out, spacing, dimg.origin, dimg.direction)
 
 
+class TLEDoseActor(DoseActor):
+    """TLE = Track Length Estimator (reference doseactors.py:722-775, C++ GateTLEDoseActor.cpp): a DoseActor
+    whose gammas deposit  w * E * mu_en/rho * L * rho  along every voxel chord of their flight instead of
+    at the interaction points; `database` ("EPDL" | "NIST") selects the mu_en/rho tables of
+    GateMaterialMuHandler.  On the GPU engine the march over the voxel chords is a phase of the transport
+    kernel (`phase_tle`)."""
+
+    user_info_defaults = {
+        "energy_min": (0.0, {"doc": "Kill the gamma if below this energy"}),
+        "tle_threshold": (np.inf, {"doc": "Define a criterium to enable TLE or not. It can be in terms of gamma energy or "
+                                   "in secondary particle range depending on the provided tle_threshold_type"}),
+        "tle_threshold_type": ("None", {"doc": "No threshold (None), by gamma energy (energy), or by the range of the "
+                                        "secondary electron (max range / average range: need Geant4's CSDA "
+                                        "ranges, not available on the GPU engine)"}),
+        "database": ("EPDL", {"doc": "which database to use", "allowed_values": ("EPDL", "NIST")}),
+    }
+
+    def initialize(self):
+        if self.score_in != "material":
+            fatal(f"TLEDoseActor cannot score in {self.score_in}, only 'material' is allowed.")
+        t = self.tle_threshold_type
+        if t not in ("None", "energy", "max range", "average range"):
+            fatal("You did not define a correct threshold type")     # GateTLEDoseActor.cpp:47-52
+        if t in ("max range", "average range"):
+            fatal(f"TLEDoseActor '{self.name}': tle_threshold_type = '{t}' needs the CSDA electron ranges of "
+                  f"G4EmCalculator (GateTLEDoseActor.cpp:96-107), which the B200 GPU engine does not have; "
+                  f"use 'energy' or 'None'")
+        super().initialize()
+
+    def tle_energy_threshold(self):
+        """E <= threshold scores by track length; 'None' -> always (GateTLEDoseActor.cpp:224-243)."""
+        return float(self.tle_threshold) if self.tle_threshold_type == "energy" else float("inf")
+
+
 class PhaseSpaceActor(ActorBase):
     """Stores particle attributes when a photon enters / exits the attached Box volume."""
 
@@ -613,5 +647,5 @@ class SimulationStatisticsActor(ActorBase):
                 f"duration {c['duration'] / g4_units.s:.4f} s\npps      {self.pps:.1f}\n")
 
 
-actor_types = {"DoseActor": DoseActor, "PhaseSpaceActor": PhaseSpaceActor,
+actor_types = {"DoseActor": DoseActor, "TLEDoseActor": TLEDoseActor, "PhaseSpaceActor": PhaseSpaceActor,
                "SimulationStatisticsActor": SimulationStatisticsActor}

@@ -30,10 +30,11 @@
 #define GB2_THREADS 1024
 #endif
 #ifndef GB2_SLOTS
-// 64 B of shared memory per slot (52 B photon state + 6 queue cells): 3040 slots + the majorant keep
-// the CTA below the 195 KB a block can use under the 196 KB carve-out, which leaves 60 KB of L1 for the
-// table gathers (measured: 3072 slots with 6 queues fall into the 228 KB carve-out, C3 1.08e9 -> 6.8e8/s)
-#define GB2_SLOTS 3040
+// 64 B of shared memory per slot (52 B photon state + 6 queue cells).  The slot count sets the shared
+// memory carve-out of the SM and with it what is left as L1 for the table gathers (measured on B200,
+// profiles/experiments/README.md): 3072 slots + 6 queues fall into the 228 KB carve-out (C3 6.8e8/s),
+// 3040 fit the 196 KB one (1.05e9/s), 2528 the 164 KB one (1.12e9/s), 2016 the 132 KB one (1.06e9/s).
+#define GB2_SLOTS 2528
 #endif
 
 namespace gb2 {

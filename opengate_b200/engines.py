@@ -97,7 +97,7 @@ class GpuSimulationEngine:
         sim = self.sim
         vols = [v for v in sim.volume_manager.volumes.values() if v.name != __world_name__]
         images = [v for v in vols if v.volume_type == "ImageVolume"]
-        dose_targets = {a.attached_to for a in sim.actor_manager.actors.values() if a.type_name == "DoseActor"}
+        dose_targets = {a.attached_to for a in sim.actor_manager.actors.values() if a.type_name in ("DoseActor", "TLEDoseActor")}
         phsp_targets = {a.attached_to for a in sim.actor_manager.actors.values() if a.type_name == "PhaseSpaceActor"}
         world_mat = sim.world.material
         phantom = None
@@ -190,6 +190,7 @@ class GpuSimulationEngine:
 
         # actors --------------------------------------------------------------------------------
         self.dose_actors, self.phsp_actors, self.stats_actors = [], [], []
+        tle_actors, tle_desc = [], []
         dose_desc, phsp_desc = [], []
         n_total = self.expected_number_of_events()
         for a in sim.actor_manager.sorted_actors:
@@ -198,6 +199,11 @@ class GpuSimulationEngine:
                 A = dose_world_to_index(a.size, a.spacing, translation=a.translation, vol_rotation=Rv, vol_translation=tv)
                 dose_desc.append(abi.make_dose_desc([int(x) for x in a.size], A, a.score_flags(), abi.HIT_TYPES[a.hit_type]))
                 self.dose_actors.append(a)
+            elif a.type_name == "TLEDoseActor":
+                A = dose_world_to_index(a.size, a.spacing, translation=a.translation, vol_rotation=Rv, vol_translation=tv)
+                tle_desc.append(([int(x) for x in a.size], A, a.score_flags(), abi.HIT_TYPES[a.hit_type],
+                                 a.tle_energy_threshold(), float(a.energy_min), a.database))
+                tle_actors.append(a)
             elif a.type_name == "PhaseSpaceActor":
                 box = a.attached_to_volume
                 Rb, tb = box.world_transform()
@@ -212,7 +218,12 @@ class GpuSimulationEngine:
         self.setup = LowLevelSetup(
             name=f"{sim.name}", seed=int(sim.current_random_seed) & (2 ** 64 - 1), tables=tables,
             world_half=world_half, world_material=world_label, labels=np.ascontiguousarray(labels), spacing=spacing,
-            world_to_volume=w2v, sources=src_structs, dose=dose_desc, phsp=phsp_desc, n_primaries=int(n_total))
+            world_to_volume=w2v, sources=src_structs, dose=dose_desc, phsp=phsp_desc, n_primaries=int(n_total),
+            materials=mats)
+        # TLE dose actors come after the plain ones in the engine's actor id space
+        for size, A, flags, hit, thr, emin, database in tle_desc:
+            self.setup.add_tle_actor(size, A, flags, hit_type=hit, threshold=thr, energy_min=emin, database=database)
+        self.dose_actors += tle_actors
         return self.setup
 
     def expected_number_of_events(self):

@@ -107,3 +107,34 @@ def test_tle_full_size_c3_properties(cuda_required):
     e2 = eng.dose_grid(did[1], abi.GRID_EDEP_SQ)
     assert np.all(e2[et > 0] > 0) and np.all(e2 * n >= et * et * (1 - 1e-9))   # Cauchy-Schwarz per voxel
     eng.close()
+
+
+def test_script_level_tle_actor_matches_oracle(cuda_required, tmp_path):
+    """TLEDoseActor through the drop-in layer: the GATE-style script of the reference's test081 pattern
+    (DoseActor + TLEDoseActor on one voxelised volume) on the CUDA engine and on the oracle back end."""
+    import os
+    from test_host_api import ct_sim
+    from oracle_backend import OracleBackend
+    res = []
+    for backend, sub in ((None, "gpu"), (OracleBackend, "cpu")):
+        os.makedirs(tmp_path / sub, exist_ok=True)
+        sim, ct, src, dose, hu = ct_sim(tmp_path / sub, n_primaries=20000)
+        tle = sim.add_actor("TLEDoseActor", "tle")
+        tle.attached_to = "ct"
+        tle.size = [12, 10, 8]
+        tle.spacing = [20.0, 20.0, 24.0]          # coarser than the image: unaligned grid, hit_type random
+        tle.dose.active = True
+        tle.dose_uncertainty.active = True
+        tle.edep_uncertainty.active = True
+        tle.output_filename = "tle.mhd"
+        out = sim.run(_backend=backend)
+        res.append((dose, tle, out))
+    (dg, tg, og), (dc, tc, oc) = res
+    for k in ("histories", "tentative_collisions", "deposits", "tle_steps", "tle_entries", "tle_overflows"):
+        assert og.device_stats[0][k] == oc.device_stats[0][k], k
+    for name in ("edep", "edep_uncertainty", "dose", "dose_uncertainty"):
+        a, b = getattr(tg, name).image.array, getattr(tc, name).image.array
+        assert np.array_equal(a != 0, b != 0), name
+        np.testing.assert_allclose(a, b, rtol=1e-9, atol=0, err_msg=name)
+    assert tg.edep.image.array.sum() == pytest.approx(dg.edep.image.array.sum(), rel=0.03)
+    assert os.path.exists(tg.edep.get_output_path())

@@ -290,3 +290,59 @@ def test_uncertainty_goal_stops_the_run_early(tmp_path):
     o = dose.user_output["edep_with_uncertainty"]
     u = host_mean_uncertainty(o.get_data("merged", 0).array, o.get_data("merged", 1).array, n, 5, 0.7)
     assert u <= 0.25
+
+
+def test_tle_dose_actor_next_to_analog_dose_actor(tmp_path):
+    """The reference's own TLE check (test081_tle_2_vox.py:80-98): a DoseActor and a TLEDoseActor on the
+    same voxelised volume in one run; the two estimators must agree, the TLE one with far less noise."""
+    sim, ct, src, dose, hu = ct_sim(tmp_path, n_primaries=20000)
+    dose.edep_uncertainty.active = True
+    tle = sim.add_actor("TLEDoseActor", "tle")
+    tle.attached_to = "ct"
+    tle.size = "like_image_volume"
+    tle.spacing = "like_image_volume"
+    tle.output_filename = "tle.mhd"
+    tle.dose.active = True
+    tle.edep_uncertainty.active = True
+    tle.database = "NIST"
+    out = sim.run(_backend=OracleBackend)
+    ea, et = dose.edep.image.array, tle.edep.image.array
+    assert et.sum() == pytest.approx(ea.sum(), rel=0.03)
+    ua, ut = dose.edep_uncertainty.image.array, tle.edep_uncertainty.image.array
+    body = (hu == 40) & (ea > 0)
+    assert np.median(ut[body]) < 0.5 * np.median(ua[body])
+    assert out.device_stats[0]["tle_steps"] > 0 and out.device_stats[0]["tle_overflows"] == 0
+    files = sorted(os.listdir(tmp_path / "out"))
+    for f in ("tle_edep.mhd", "tle_edep_uncertainty.mhd", "tle_dose.mhd", "ct_edep.mhd"):
+        assert f in files, (f, files)
+    assert json.load(open(tmp_path / "out" / "tle_edep.json")) == {"number_of_samples": 20000}
+
+
+def test_tle_dose_actor_user_info(tmp_path):
+    sim, ct, src, dose, hu = ct_sim(tmp_path, n_primaries=2000)
+    tle = sim.add_actor("TLEDoseActor", "tle")
+    tle.attached_to = "ct"
+    tle.size = "like_image_volume"
+    tle.spacing = "like_image_volume"
+    assert tle.database == "EPDL" and tle.tle_threshold_type == "None" and tle.energy_min == 0.0
+    with pytest.raises(Exception):
+        tle.database = "simulated"
+    # energy threshold: gammas above it score like a DoseActor
+    tle.tle_threshold_type = "energy"
+    tle.tle_threshold = 70 * keV
+    out = sim.run(_backend=OracleBackend)
+    assert 0 < out.device_stats[0]["tle_steps"]
+    assert tle.edep.image.array.sum() == pytest.approx(dose.edep.image.array.sum(), rel=0.1)
+    for bad, msg in (("max range", "CSDA"), ("bogus", "correct threshold type")):
+        sim2, ct2, src2, dose2, _ = ct_sim(tmp_path, n_primaries=10)
+        t2 = sim2.add_actor("TLEDoseActor", "tle")
+        t2.attached_to = "ct"
+        t2.tle_threshold_type = bad
+        with pytest.raises(Exception, match=msg):
+            sim2.run(_backend=OracleBackend)
+    sim3, ct3, src3, dose3, _ = ct_sim(tmp_path, n_primaries=10)
+    t3 = sim3.add_actor("TLEDoseActor", "tle")
+    t3.attached_to = "ct"
+    t3.score_in = "G4_WATER"
+    with pytest.raises(Exception, match="TLEDoseActor cannot score in G4_WATER"):
+        sim3.run(_backend=OracleBackend)

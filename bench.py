@@ -366,21 +366,36 @@ def measure_e2e(S, H, local, rank, world, torch, dist, steps=2):
                                                    t.rayl_cum_ff2, t.compt_sf)) + sum(k.nbytes for _, _, k in S.tle)
     d2h = G * nx * ny * nz * 8
 
-    def one(first):
+    parts = {"create": 0.0, "setup_h2d": 0.0, "run": 0.0, "reduce": 0.0, "d2h": 0.0, "destroy": 0.0}
+
+    def one(first, acc=None):
+        # the section clocks only explain the total: the run is launched asynchronously, so the
+        # stream is drained at the end of "run" (the D2H copy would wait for it anyway)
+        t = [time.perf_counter()]
+
+        def lap(key):
+            t.append(time.perf_counter())
+            if acc is not None:
+                acc[key] += t[-1] - t[-2]
+
         eng = Engine(local, S.seed)
+        lap("create")
         sids, dids, pids = S.apply(eng)       # H2D: tables + label volume (+ source CDFs)
+        lap("setup_h2d")
         eng.begin_run()
         eng.run_source(sids[0], first, H)
+        eng.sync()
+        lap("run")
         if world > 1:
-            eng.sync()
             multigpu.reduce_dose_grids(eng, dids, S, dst=0)
             torch.cuda.synchronize()
+        lap("reduce")
         if rank == 0:
             for w, out in zip(which, host_out):   # D2H: every active accumulator grid
                 eng.dose_grid(dids[0], w, out)
-        else:
-            eng.sync()
+        lap("d2h")
         eng.close()
+        lap("destroy")
 
     one(rank * H)  # warm-up (page-in, allocator)
     if world > 1:
@@ -388,7 +403,7 @@ def measure_e2e(S, H, local, rank, world, torch, dist, steps=2):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for i in range(steps):
-        one((1 + i) * world * H + rank * H)
+        one((1 + i) * world * H + rank * H, parts)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
@@ -397,6 +412,7 @@ def measure_e2e(S, H, local, rank, world, torch, dist, steps=2):
     dt = float(tt.item())
     return {"value": world * H * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "histories_per_step_per_gpu": H, "steps": steps,
+            "ms_per_step_by_section_rank0": {k: 1e3 * v / steps for k, v in parts.items()},
             "what": "gate_b200 C-ABI from pinned host buffers: create + set_tables + set_image_volume (H2D) + run"
                     + (" + NCCL reduce to rank 0" if world > 1 else "") + " + get_dose_grid of every grid (D2H) per step"}
 

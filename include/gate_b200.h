@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GATE_B200_ABI_VERSION 2
+#define GATE_B200_ABI_VERSION 3
 
 enum {
   GATE_B200_OK = 0,
@@ -68,11 +68,13 @@ typedef struct {
  * GateSPSVoxelsPosDistribution.cpp:29-72, GateVSource.cpp:95-107 (attached-volume frame).
  * All frames are already composed to WORLD by the caller. */
 enum { GATE_B200_POS_POINT = 0, GATE_B200_POS_BOX = 1, GATE_B200_POS_SPHERE = 2,
-       GATE_B200_POS_DISC = 3, GATE_B200_POS_CYLINDER = 4, GATE_B200_POS_VOXELS = 5 };
-enum { GATE_B200_DIR_ISO = 0, GATE_B200_DIR_MOMENTUM = 1, GATE_B200_DIR_FOCUSED = 2 };
+       GATE_B200_POS_DISC = 3, GATE_B200_POS_CYLINDER = 4, GATE_B200_POS_VOXELS = 5,
+       GATE_B200_POS_PHSP = 6 };
+enum { GATE_B200_DIR_ISO = 0, GATE_B200_DIR_MOMENTUM = 1, GATE_B200_DIR_FOCUSED = 2,
+       GATE_B200_DIR_PHSP = 3 };
 enum { GATE_B200_ENE_MONO = 0, GATE_B200_ENE_GAUSS = 1, GATE_B200_ENE_RANGE = 2,
        GATE_B200_ENE_SPECTRUM_DISCRETE = 3, GATE_B200_ENE_SPECTRUM_HISTOGRAM = 4,
-       GATE_B200_ENE_SPECTRUM_HISTOGRAM_LINEAR = 5, GATE_B200_ENE_CDF = 6 };
+       GATE_B200_ENE_SPECTRUM_HISTOGRAM_LINEAR = 5, GATE_B200_ENE_CDF = 6, GATE_B200_ENE_PHSP = 7 };
 
 typedef struct {
   int32_t pos_type;
@@ -100,6 +102,21 @@ typedef struct {
   const float *cdf_z;             /* [nz]                                                  */
   const float *cdf_y;             /* [nz][ny]                                              */
   const float *cdf_x;             /* [nz][ny][nx]                                          */
+  /* phase-space replay (pos_type == PHSP, ene_type == PHSP, dir_type == PHSP or ISO).
+   * Replaces: GatePhaseSpaceSource::GeneratePrimaries/GenerateOnePrimary
+   * (GatePhaseSpaceSource.cpp:92-178) fed by PhaseSpaceSourceGenerator.generate
+   * (sources/phspsources.py:119-258): the event with global id i replays entry
+   * (phsp_entry_start + i) % phsp_n_entries (sequential reading, wrapping at the end of the
+   * file).  Position: entry -> pos_rotation/pos_translation (identity for global_flag);
+   * direction: entry, normalised, rotated by dir_rotation when dir_relative (dir_type ISO =
+   * isotropic_direction); energy and weight (x `weight`) per entry.  Arrays are float32 as the
+   * reference's batches (phspsources.py:195-210); phsp_weight may be NULL (= 1). */
+  uint64_t phsp_n_entries;
+  uint64_t phsp_entry_start;
+  const float *phsp_pos_x, *phsp_pos_y, *phsp_pos_z;   /* [phsp_n_entries] mm            */
+  const float *phsp_dir_x, *phsp_dir_y, *phsp_dir_z;   /* NULL with dir_type ISO         */
+  const float *phsp_energy;                             /* MeV                            */
+  const float *phsp_weight;
 } gate_b200_source;
 
 /* ---- dose actor -------------------------------------------------------------------------

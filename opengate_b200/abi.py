@@ -10,13 +10,13 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # enums --------------------------------------------------------------------------------
-POS_POINT, POS_BOX, POS_SPHERE, POS_DISC, POS_CYLINDER, POS_VOXELS = range(6)
-DIR_ISO, DIR_MOMENTUM, DIR_FOCUSED = range(3)
+POS_POINT, POS_BOX, POS_SPHERE, POS_DISC, POS_CYLINDER, POS_VOXELS, POS_PHSP = range(7)
+DIR_ISO, DIR_MOMENTUM, DIR_FOCUSED, DIR_PHSP = range(4)
 (ENE_MONO, ENE_GAUSS, ENE_RANGE, ENE_SPECTRUM_DISCRETE, ENE_SPECTRUM_HISTOGRAM,
- ENE_SPECTRUM_HISTOGRAM_LINEAR, ENE_CDF) = range(7)
+ ENE_SPECTRUM_HISTOGRAM_LINEAR, ENE_CDF, ENE_PHSP) = range(8)
 HIT_RANDOM, HIT_PRE, HIT_POST, HIT_MIDDLE = range(4)
 SCORE_EDEP, SCORE_EDEP_SQ, SCORE_DOSE, SCORE_DOSE_SQ, SCORE_COUNTS = 1, 2, 4, 8, 16
 GRID_EDEP, GRID_EDEP_SQ, GRID_DOSE, GRID_DOSE_SQ, GRID_COUNTS = range(5)
@@ -53,6 +53,10 @@ class Source(C.Structure):
         ("weight", C.c_double),
         ("vox_size", C.c_int32 * 3), ("vox_spacing", C.c_double * 3), ("vox_origin", C.c_double * 3),
         ("cdf_z", _fp), ("cdf_y", _fp), ("cdf_x", _fp),
+        ("phsp_n_entries", C.c_uint64), ("phsp_entry_start", C.c_uint64),
+        ("phsp_pos_x", _fp), ("phsp_pos_y", _fp), ("phsp_pos_z", _fp),
+        ("phsp_dir_x", _fp), ("phsp_dir_y", _fp), ("phsp_dir_z", _fp),
+        ("phsp_energy", _fp), ("phsp_weight", _fp),
     ]
 
 
@@ -134,8 +138,9 @@ def make_source(pos_type=POS_POINT, half_size=(0, 0, 0), radius=0.0, sigma_x=0.0
                 ene_type=ENE_MONO, mono=0.0, sigma=0.0, e_min=0.0, e_max=0.0,
                 spectrum_energy=None, spectrum_cdf=None, weight=1.0,
                 vox_size=(0, 0, 0), vox_spacing=(1, 1, 1), vox_origin=(0, 0, 0),
-                cdf_z=None, cdf_y=None, cdf_x=None):
-    """Fill a gate_b200_source; returns (struct, keepalive list)."""
+                cdf_z=None, cdf_y=None, cdf_x=None, phsp=None, phsp_entry_start=0):
+    """Fill a gate_b200_source; returns (struct, keepalive list).
+    phsp: dict of float32 arrays pos_x/y/z, energy and optionally dir_x/y/z, weight (phase-space replay)."""
     s = Source()
     keep = []
     s.pos_type = pos_type
@@ -173,6 +178,16 @@ def make_source(pos_type=POS_POINT, half_size=(0, 0, 0), radius=0.0, sigma_x=0.0
         cx = np.ascontiguousarray(cdf_x, dtype=np.float32)
         keep += [cz, cy, cx]
         s.cdf_z, s.cdf_y, s.cdf_x = fptr(cz), fptr(cy), fptr(cx)
+    if phsp is not None:
+        cols = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in phsp.items() if v is not None}
+        n = len(cols["pos_x"])
+        for k, v in cols.items():
+            if len(v) != n:
+                raise ValueError(f"phase-space column '{k}' has {len(v)} entries, expected {n}")
+            keep.append(v)
+            setattr(s, "phsp_" + k, fptr(v))
+        s.phsp_n_entries = n
+        s.phsp_entry_start = int(phsp_entry_start)
     return s, keep
 
 

@@ -500,7 +500,7 @@ class PhaseSpaceActor(ActorBase):
 
     SUPPORTED = ("KineticEnergy", "Weight", "EventID", "PrePosition", "Position", "PostPosition", "PreDirection",
                  "Direction", "PostDirection", "GlobalTime", "LocalTime", "TimeFromBeginOfEvent", "ParticleName",
-                 "PDGCode", "TrackID", "ParentID")
+                 "PDGCode", "TrackID", "ParentID", "PrePositionLocal", "PostPositionLocal", "PreDirectionLocal")
 
     user_info_defaults = {
         "attributes": ([], {"doc": "Names of the attributes to store"}),
@@ -569,6 +569,16 @@ class PhaseSpaceActor(ActorBase):
             elif a in ("PreDirection", "Direction", "PostDirection"):
                 for i, ax in enumerate("XYZ"):
                     cols[f"{a}_{ax}"] = rows["Direction"][:, i].astype(np.float64)
+            elif a in ("PrePositionLocal", "PostPositionLocal", "PreDirectionLocal"):
+                # coordinates of the attached volume (top transform of the touchable,
+                # GateDigiAttributeList.cpp:241-254,282-288): p_local = R^T (p - t), d_local = R^T d
+                R, t = self.attached_to_volume.world_transform()
+                if a == "PreDirectionLocal":
+                    loc = rows["Direction"].astype(np.float64) @ np.asarray(R, dtype=np.float64)
+                else:
+                    loc = (rows["Position"].astype(np.float64) - np.asarray(t, dtype=np.float64)) @ np.asarray(R, dtype=np.float64)
+                for i, ax in enumerate("XYZ"):
+                    cols[f"{a}_{ax}"] = np.ascontiguousarray(loc[:, i])
             elif a in ("GlobalTime", "LocalTime", "TimeFromBeginOfEvent"):
                 cols[a] = rows["Time"].astype(np.float64)
             elif a == "ParticleName":

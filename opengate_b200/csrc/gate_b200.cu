@@ -6,6 +6,7 @@
 // constants), and launches gb2::transport_kernel as a persistent grid sized from the SM
 // count.  No torch, no pybind: plain CUDA runtime.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -13,7 +14,6 @@
 #include <cstring>
 #include <new>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "transport.cuh"
@@ -93,24 +93,70 @@ int fail(gate_b200_engine *h, int code, const char *fmt, ...) {
                   __FILE__, __LINE__);                                                       \
   } while (0)
 
+// Device memory comes from the device's default stream-ordered pool (cudaMallocAsync) with the
+// release threshold lifted: an engine's gigabytes of accumulator grids and scratch go back to the
+// pool when it is destroyed and the next engine of the process gets them without a trip to the
+// driver (measured on B200, C3: cudaFree of one engine's buffers 185 ms, cudaMalloc 60 ms per run).
+// Everything is allocated, filled and used in the order of h->stream.
 template <typename T>
 int dev_alloc(gate_b200_engine *h, T **out, size_t n, bool zero = false) {
   void *p = nullptr;
-  CU(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
-  if (zero) CU(cudaMemsetAsync(p, 0, std::max<size_t>(n, 1) * sizeof(T), h->stream));
+  CU(cudaMallocAsync(&p, std::max<size_t>(n, 1) * sizeof(T), h->stream));
   h->allocs.push_back(p);
+  if (zero) CU(cudaMemsetAsync(p, 0, std::max<size_t>(n, 1) * sizeof(T), h->stream));
   *out = static_cast<T *>(p);
   return 0;
 }
 
+// host -> device in stream order; returns when the host buffer may be reused (pageable memory is
+// staged by the runtime before cudaMemcpyAsync returns, pinned memory needs the synchronize)
 template <typename T>
 int dev_upload(gate_b200_engine *h, const T **out, const T *src, size_t n) {
   T *p = nullptr;
   int rc = dev_alloc(h, &p, n);
   if (rc) return rc;
-  CU(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  CU(cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   *out = p;
   return 0;
+}
+
+// Which labels occur in the volume (bit set, one bit per material) and the first voxel whose label
+// has no material: one pass over the device copy of the label volume.
+template <typename LabelT>
+__global__ void __launch_bounds__(256) label_scan_kernel(const LabelT *__restrict__ labels, unsigned long long nv, int nmat,
+                                                         unsigned *__restrict__ present, unsigned long long *first_bad) {
+  extern __shared__ unsigned s_present[];
+  const int nw = (nmat + 31) >> 5;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) s_present[i] = 0u;
+  __syncthreads();
+  constexpr int kPer = 16 / (int)sizeof(LabelT);          // labels per 16-byte load
+  const unsigned long long nvec = nv / kPer;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  auto see = [&](unsigned l, unsigned long long idx) {
+    if (l >= (unsigned)nmat) { atomicMin(first_bad, idx); return; }
+    if (!((s_present[l >> 5] >> (l & 31u)) & 1u)) atomicOr(&s_present[l >> 5], 1u << (l & 31u));
+  };
+  const uint4 *v4 = reinterpret_cast<const uint4 *>(labels);   // cudaMalloc'ed: 256-byte aligned
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const uint4 v = __ldg(v4 + i);
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (sizeof(LabelT) == 1) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) see((w[k] >> (8 * b)) & 0xffu, i * kPer + 4 * k + b);
+      } else {
+        see(w[k] & 0xffffu, i * kPer + 2 * k);
+        see(w[k] >> 16, i * kPer + 2 * k + 1);
+      }
+    }
+  }
+  for (unsigned long long i = nvec * kPer + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride)
+    see((unsigned)labels[i], i);
+  __syncthreads();
+  for (int i = threadIdx.x; i < nw; i += blockDim.x)
+    if (s_present[i]) atomicOr(&present[i], s_present[i]);
 }
 
 void affine_from_double(Affine &a, const double m12[12]) {
@@ -155,12 +201,37 @@ int gate_b200_create(int device_id, uint64_t seed, gate_b200_engine **out) {
                 cudaGetErrorString(e));
   if (device_id < 0 || device_id >= ndev)
     return fail(h, GATE_B200_EINVAL, "device %d out of range (%d devices)", device_id, ndev);
+  const bool trace = getenv("GATE_B200_TRACE") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!trace) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[gate_b200_create] %-18s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   CU(cudaSetDevice(device_id));
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, device_id));
-  h->sm_count = prop.multiProcessorCount;
+  lap("set_device");
+  // three attributes instead of cudaGetDeviceProperties (2.4 ms per call on B200)
+  int sm_count = 0, l2_persist_max = 0, l2_window_max = 0;
+  CU(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device_id));
+  CU(cudaDeviceGetAttribute(&l2_persist_max, cudaDevAttrMaxPersistingL2CacheSize, device_id));
+  CU(cudaDeviceGetAttribute(&l2_window_max, cudaDevAttrMaxAccessPolicyWindowSize, device_id));
+  h->sm_count = sm_count;
+  lap("device_attributes");
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->own_stream = true;
+  lap("stream_create");
+  {
+    // keep freed blocks in the pool for the next engine of this process (GATE_B200_POOL_RETAIN=0:
+    // give them back to the driver at the next synchronisation, the CUDA default)
+    const char *s = getenv("GATE_B200_POOL_RETAIN");
+    if (!s || atoi(s) != 0) {
+      cudaMemPool_t pool;
+      CU(cudaDeviceGetDefaultMemPool(&pool, device_id));
+      uint64_t thr = UINT64_MAX;
+      CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    }
+  }
   if (int rc = dev_alloc(h, &h->d_next, 1, true)) return rc;
   if (int rc = dev_alloc(h, &h->d_stats, (size_t)S_COUNT, true)) return rc;
   if (int rc = dev_alloc(h, &h->d_edep, 1, true)) return rc;
@@ -171,13 +242,16 @@ int gate_b200_create(int device_id, uint64_t seed, gate_b200_engine **out) {
   h->P.wh[0] = h->P.wh[1] = h->P.wh[2] = 1.0e6f;
   h->max_ctas = h->sm_count;
   if (const char *s = getenv("GATE_B200_CTAS")) h->max_ctas = std::max(1, atoi(s));
-  h->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
-  h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+  h->l2_persist_max = (size_t)l2_persist_max;
+  h->l2_window_max = (size_t)l2_window_max;
   if (const char *s = getenv("GATE_B200_L2_PERSIST")) h->l2_persist = atoi(s) != 0;
   // per-slot global scratch: coalescing buffers of the histories in flight, pending photons
   const size_t nslots = (size_t)h->max_ctas * kSlots;
+  lap("pool + counters");
   if (int rc = dev_alloc(h, &h->P.depbuf, nslots * kDepBuf)) return rc;
   if (int rc = dev_alloc(h, &h->P.pend, nslots * 6)) return rc;
+  if (int rc = dev_alloc(h, &h->P.slot_w, nslots)) return rc;
+  lap("slot scratch");
   return GATE_B200_OK;
 }
 
@@ -186,7 +260,8 @@ void gate_b200_destroy(gate_b200_engine *h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto &pr : h->pending_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
-  for (void *p : h->allocs) cudaFree(p);
+  for (void *p : h->allocs) cudaFreeAsync(p, h->stream);
+  if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -277,35 +352,37 @@ int gate_b200_set_image_volume(gate_b200_engine *h, const void *labels, int32_t 
   const size_t nv = (size_t)size[0] * size[1] * size[2];
   if (nv == 0) return fail(h, GATE_B200_EINVAL, "empty image volume");
   if (nv >= (1ull << 31)) return fail(h, GATE_B200_EINVAL, "image volume must have fewer than 2^31 voxels");
+  // the label volume goes to the device first (stream order; the caller's buffer may be pinned)
+  uint8_t *dl = nullptr;
+  if (int rc = dev_alloc(h, &dl, nv * label_bytes)) return rc;
+  CU(cudaMemcpyAsync(dl, labels, nv * label_bytes, cudaMemcpyHostToDevice, h->stream));
   // materials present -> majorant (same rule as the oracle's build_majorant); the scan of the label
-  // volume is split over host threads (it is inside the end-to-end path of every run)
+  // volume runs on the device copy (it is inside the end-to-end path of every run)
   std::vector<char> present(P.nmat, 0);
   {
-    const int nthreads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    std::vector<std::vector<char>> part(nthreads, std::vector<char>(P.nmat, 0));
-    std::vector<long long> bad(nthreads, -1);
-    std::vector<std::thread> pool;
-    for (int tid = 0; tid < nthreads; ++tid)
-      pool.emplace_back([&, tid]() {
-        const size_t i0 = nv * (size_t)tid / nthreads, i1 = nv * (size_t)(tid + 1) / nthreads;
-        char *pr = part[tid].data();
-        if (label_bytes == 1) {
-          const uint8_t *l = static_cast<const uint8_t *>(labels);
-          for (size_t i = i0; i < i1; ++i) { if (l[i] >= P.nmat) { bad[tid] = (long long)i; break; } pr[l[i]] = 1; }
-        } else {
-          const uint16_t *l = static_cast<const uint16_t *>(labels);
-          for (size_t i = i0; i < i1; ++i) { if (l[i] >= P.nmat) { bad[tid] = (long long)i; break; } pr[l[i]] = 1; }
-        }
-      });
-    for (auto &t : pool) t.join();
-    for (int tid = 0; tid < nthreads; ++tid) {
-      if (bad[tid] >= 0) {
-        const size_t i = (size_t)bad[tid];
-        const int lab = label_bytes == 1 ? (int)static_cast<const uint8_t *>(labels)[i] : (int)static_cast<const uint16_t *>(labels)[i];
-        return fail(h, GATE_B200_EINVAL, "label %d at voxel %zu has no material", lab, i);
-      }
-      for (int m = 0; m < P.nmat; ++m) present[m] |= part[tid][m];
+    const int nw = (P.nmat + 31) / 32;
+    unsigned *d_present = nullptr;
+    unsigned long long *d_bad = nullptr;
+    if (int rc = dev_alloc(h, &d_present, (size_t)nw, true)) return rc;
+    if (int rc = dev_alloc(h, &d_bad, 1)) return rc;
+    CU(cudaMemsetAsync(d_bad, 0xff, sizeof(unsigned long long), h->stream));
+    const int blocks = (int)std::min<size_t>((size_t)h->sm_count * 8, (nv + 4095) / 4096);
+    if (label_bytes == 1)
+      label_scan_kernel<uint8_t><<<blocks, 256, nw * sizeof(unsigned), h->stream>>>(dl, nv, P.nmat, d_present, d_bad);
+    else
+      label_scan_kernel<uint16_t><<<blocks, 256, nw * sizeof(unsigned), h->stream>>>(reinterpret_cast<const uint16_t *>(dl), nv, P.nmat, d_present, d_bad);
+    CU(cudaGetLastError());
+    std::vector<unsigned> words(nw, 0u);
+    unsigned long long bad = ~0ull;
+    CU(cudaMemcpyAsync(words.data(), d_present, nw * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (bad != ~0ull) {
+      const size_t i = (size_t)bad;
+      const int lab = label_bytes == 1 ? (int)static_cast<const uint8_t *>(labels)[i] : (int)static_cast<const uint16_t *>(labels)[i];
+      return fail(h, GATE_B200_EINVAL, "label %d at voxel %zu has no material", lab, i);
     }
+    for (int m = 0; m < P.nmat; ++m) present[m] = (char)((words[m >> 5] >> (m & 31)) & 1u);
   }
   std::vector<float> maj(P.ne, 0.f);
   for (int i = 0; i < P.ne; ++i) {
@@ -314,10 +391,8 @@ int gate_b200_set_image_volume(gate_b200_engine *h, const void *labels, int32_t 
       if (present[m] && h->h_mu[(size_t)m * P.ne + i] > mx) mx = h->h_mu[(size_t)m * P.ne + i];
     maj[i] = mx;
   }
-  CU(cudaMemcpy(h->d_maj, maj.data(), maj.size() * sizeof(float), cudaMemcpyHostToDevice));
-  uint8_t *dl = nullptr;
-  if (int rc = dev_alloc(h, &dl, nv * label_bytes)) return rc;
-  CU(cudaMemcpy(dl, labels, nv * label_bytes, cudaMemcpyHostToDevice));
+  CU(cudaMemcpyAsync(h->d_maj, maj.data(), maj.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   h->d_labels = dl;
   P.labels = dl;
   for (int a = 0; a < 3; ++a) {
@@ -343,9 +418,13 @@ int gate_b200_add_source(gate_b200_engine *h, const gate_b200_source *s, int32_t
   memset(&d, 0, sizeof d);
   d.pos_type = s->pos_type; d.dir_type = s->dir_type; d.ene_type = s->ene_type;
   d.dir_relative = s->dir_relative;
-  if (d.pos_type < 0 || d.pos_type > GATE_B200_POS_VOXELS) return fail(h, GATE_B200_EINVAL, "bad pos_type %d", d.pos_type);
-  if (d.dir_type < 0 || d.dir_type > GATE_B200_DIR_FOCUSED) return fail(h, GATE_B200_EINVAL, "bad dir_type %d", d.dir_type);
-  if (d.ene_type < 0 || d.ene_type > GATE_B200_ENE_CDF) return fail(h, GATE_B200_EINVAL, "bad ene_type %d", d.ene_type);
+  if (d.pos_type < 0 || d.pos_type > GATE_B200_POS_PHSP) return fail(h, GATE_B200_EINVAL, "bad pos_type %d", d.pos_type);
+  if (d.dir_type < 0 || d.dir_type > GATE_B200_DIR_PHSP) return fail(h, GATE_B200_EINVAL, "bad dir_type %d", d.dir_type);
+  if (d.ene_type < 0 || d.ene_type > GATE_B200_ENE_PHSP) return fail(h, GATE_B200_EINVAL, "bad ene_type %d", d.ene_type);
+  const bool phsp = d.pos_type == GATE_B200_POS_PHSP;
+  if (phsp != (d.ene_type == GATE_B200_ENE_PHSP) || (!phsp && d.dir_type == GATE_B200_DIR_PHSP) ||
+      (phsp && d.dir_type != GATE_B200_DIR_PHSP && d.dir_type != GATE_B200_DIR_ISO))
+    return fail(h, GATE_B200_EINVAL, "phase-space source: pos_type PHSP goes with ene_type PHSP and dir_type PHSP or ISO");
   for (int r = 0; r < 3; ++r) {
     for (int c = 0; c < 3; ++c) {
       d.pos.m[3 * r + c] = (float)s->pos_rotation[3 * r + c];
@@ -387,6 +466,27 @@ int gate_b200_add_source(gate_b200_engine *h, const gate_b200_source *s, int32_t
     if (int rc = dev_upload(h, &d.cdf_z, s->cdf_z, nz)) return rc;
     if (int rc = dev_upload(h, &d.cdf_y, s->cdf_y, nz * ny)) return rc;
     if (int rc = dev_upload(h, &d.cdf_x, s->cdf_x, nz * ny * nx)) return rc;
+  }
+  if (phsp) {
+    const uint64_t n = s->phsp_n_entries;
+    const bool need_dir = d.dir_type == GATE_B200_DIR_PHSP;
+    if (n == 0 || !s->phsp_pos_x || !s->phsp_pos_y || !s->phsp_pos_z || !s->phsp_energy ||
+        (need_dir && (!s->phsp_dir_x || !s->phsp_dir_y || !s->phsp_dir_z)))
+      return fail(h, GATE_B200_EINVAL, "phase-space source: position, energy%s columns and n_entries > 0 are required",
+                  need_dir ? ", direction" : "");
+    // two 16-byte records per entry: one coalesced load each for consecutive events
+    std::vector<float4> a(n), b(n);
+    for (uint64_t i = 0; i < n; ++i) {
+      a[i] = make_float4(s->phsp_pos_x[i], s->phsp_pos_y[i], s->phsp_pos_z[i], s->phsp_energy[i]);
+      b[i] = make_float4(need_dir ? s->phsp_dir_x[i] : 0.0f, need_dir ? s->phsp_dir_y[i] : 0.0f,
+                         need_dir ? s->phsp_dir_z[i] : 1.0f, s->phsp_weight ? s->phsp_weight[i] : 1.0f);
+      if (need_dir && !(b[i].x * b[i].x + b[i].y * b[i].y + b[i].z * b[i].z > 0.0f))
+        return fail(h, GATE_B200_EINVAL, "phase-space source: entry %llu has a null direction", (unsigned long long)i);
+    }
+    if (int rc = dev_upload(h, &d.ph_a, a.data(), (size_t)n)) return rc;
+    if (int rc = dev_upload(h, &d.ph_b, b.data(), (size_t)n)) return rc;
+    d.ph_n = n;
+    d.ph_start = s->phsp_entry_start % n;
   }
   h->src.push_back(rec);
   if (source_id) *source_id = (int32_t)h->src.size() - 1;

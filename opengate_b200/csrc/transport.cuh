@@ -78,6 +78,9 @@ struct DSource {
   int vox_n[3];
   float vox_sp[3], vox_org[3];
   const float *cdf_z, *cdf_y, *cdf_x;
+  // phase-space replay: entry e = (ph_start + history id) % ph_n, ph_a[e] = {x, y, z, E}, ph_b[e] = {dx, dy, dz, w}
+  const float4 *ph_a, *ph_b;
+  unsigned long long ph_n, ph_start;
 };
 
 struct DDose {
@@ -136,6 +139,7 @@ struct Params {
   double *edep_total;
   DepEntry *depbuf;              // [gridDim.x * kSlots][kDepBuf] coalescing buffers (global scratch)
   float *pend;                   // [gridDim.x * kSlots][6] second annihilation photon (pair_mode 1)
+  float *slot_w;                 // [gridDim.x * kSlots] weight of the history in the slot (phase-space sources)
   // track-length estimators (dose actors with tle = 1)
   int ntle;
   float tle_emin, tle_thr_max;
@@ -277,6 +281,12 @@ __device__ __forceinline__ DepEntry ld_dep(const DepEntry *p) {
 }
 __device__ __forceinline__ void st_dep(DepEntry *p, const DepEntry &e) {
   __stcg(reinterpret_cast<int4 *>(p), make_int4(e.key, __float_as_int(e.e), __float_as_int(e.d), e.n));
+}
+
+// statistical weight of the history in a slot: per entry for a phase-space source (written by
+// generate_primary), the source's constant otherwise
+__device__ __forceinline__ float hist_weight(const Params &P, int gslot) {
+  return P.src.ph_b ? __ldcg(P.slot_w + gslot) : P.src.weight;
 }
 
 __device__ __forceinline__ float tab_mu(const Params &P, int m, int ie, float fe) {
@@ -610,12 +620,23 @@ __device__ __forceinline__ int cdf_index(const float *__restrict__ cdf, int last
   return lo;
 }
 
-__device__ __noinline__ void generate_primary(const Params &P, Ph &g) {
+__device__ __noinline__ void generate_primary(const Params &P, Ph &g, int gslot) {
   const DSource &S = P.src;
   Rng &r = g.rng;
   rng_begin(r);
   float l[3] = {0.0f, 0.0f, 0.0f};
+  float4 ea = make_float4(0.0f, 0.0f, 0.0f, 0.0f), eb = ea;
   switch (S.pos_type) {
+  case GATE_B200_POS_PHSP: {
+    // GatePhaseSpaceSource::GenerateOnePrimary (GatePhaseSpaceSource.cpp:137-166): sequential entries,
+    // wrapping at the end of the file (phspsources.py:119-146)
+    const unsigned long long id = ((unsigned long long)r.h1 << 32) | r.h0;
+    const unsigned long long en = (S.ph_start + id) % S.ph_n;
+    ea = __ldg(S.ph_a + en);
+    eb = __ldg(S.ph_b + en);
+    l[0] = ea.x; l[1] = ea.y; l[2] = ea.z;
+    __stcg(P.slot_w + gslot, eb.w * S.weight);
+  } break;
   case GATE_B200_POS_POINT: break;
   case GATE_B200_POS_BOX:
     for (int a = 0; a < 3; ++a) l[a] = (2.0f * rng_uniform(r) - 1.0f) * S.half[a];
@@ -687,10 +708,18 @@ __device__ __noinline__ void generate_primary(const Params &P, Ph &g) {
     float inv = 1.0f / sqrtf(v0 * v0 + v1 * v1 + v2 * v2);
     g.d[0] = v0 * inv; g.d[1] = v1 * inv; g.d[2] = v2 * inv;
   } break;
+  case GATE_B200_DIR_PHSP: {
+    // direction / direction.mag(), then the rotation of the attached volume (GatePhaseSpaceSource.cpp:158-162)
+    float inv = 1.0f / sqrtf(eb.x * eb.x + eb.y * eb.y + eb.z * eb.z);
+    float v[3] = {eb.x * inv, eb.y * inv, eb.z * inv};
+    if (S.dir_relative) rot_apply(S.dir_rot, v, g.d);
+    else { g.d[0] = v[0]; g.d[1] = v[1]; g.d[2] = v[2]; }
+  } break;
   }
 
   float E = 0.0f;
   switch (S.ene_type) {
+  case GATE_B200_ENE_PHSP: E = ea.w; break;
   case GATE_B200_ENE_MONO: E = S.mono; break;
   case GATE_B200_ENE_GAUSS: E = S.mono + gauss(r) * S.sigma; break;
   case GATE_B200_ENE_RANGE: E = S.emin + rng_uniform(r) * (S.emax - S.emin); break;
@@ -739,7 +768,7 @@ __device__ __noinline__ void generate_primary(const Params &P, Ph &g) {
 
 // ------------------------------------------------------------------------------ phase space
 
-__device__ __forceinline__ void phsp_store(const Params &P, Ph &g, unsigned long long hist, int k, int flag) {
+__device__ __forceinline__ void phsp_store(const Params &P, Ph &g, unsigned long long hist, int k, int flag, int gslot) {
   const DPhsp &Q = P.phsp[k];
   g.flags |= F_STORED;
   unsigned long long idx = atomicAdd(Q.n_rows, 1ull);
@@ -750,7 +779,7 @@ __device__ __forceinline__ void phsp_store(const Params &P, Ph &g, unsigned long
   Q.ke[idx] = g.E;
 #pragma unroll
   for (int a = 0; a < 3; ++a) { Q.pos[3 * idx + a] = g.p[a]; Q.dir[3 * idx + a] = g.d[a]; }
-  Q.w[idx] = P.src.weight;
+  Q.w[idx] = hist_weight(P, gslot);
   Q.t[idx] = g.path / kCmmPerNs;
   Q.ev[idx] = (long long)hist;
   Q.fl[idx] = flag;
@@ -794,7 +823,7 @@ __device__ __forceinline__ int locate(const Params &P, Ph &g) {
 
 // Q_W: one flight segment of a photon travelling in the world material (outside the image volume);
 // a photon that has just left the volume is first taken to its exit point and to the world frame.
-__device__ __noinline__ int phase_world(const Params &P, Smem &S, int slot) {
+__device__ __noinline__ int phase_world(const Params &P, Smem &S, int slot, int gslot) {
   Ph g;
   load_ph(P, S, slot, g);
   int next;
@@ -868,10 +897,10 @@ __device__ __noinline__ int phase_world(const Params &P, Smem &S, int slot) {
         n_steps++;
         if (((ev - 3) & 1) == 0) {
           g.flags |= (1u << k);
-          if (P.phsp[k].steps & GATE_B200_PHSP_ENTERING) phsp_store(P, g, hist, k, GATE_B200_PHSP_ENTERING);
+          if (P.phsp[k].steps & GATE_B200_PHSP_ENTERING) phsp_store(P, g, hist, k, GATE_B200_PHSP_ENTERING, gslot);
         } else {
           g.flags &= ~(1u << k);
-          if (P.phsp[k].steps & GATE_B200_PHSP_EXITING) phsp_store(P, g, hist, k, GATE_B200_PHSP_EXITING);
+          if (P.phsp[k].steps & GATE_B200_PHSP_EXITING) phsp_store(P, g, hist, k, GATE_B200_PHSP_EXITING, gslot);
         }
         next = Q_W;
       }
@@ -1055,12 +1084,13 @@ __device__ __noinline__ int phase_compton(const Params &P, Smem &S, int slot, in
     float sphi, cphi;
     d_sincos2pi(u32_to_uniform(r[4]), sphi, cphi);
     const float E1 = eps * E;
-    deposit<kTle>(P, g, buf, ds, (E - E1) * P.src.weight, m, in_vol, E, gslot);
+    const float wgt = hist_weight(P, gslot);
+    deposit<kTle>(P, g, buf, ds, (E - E1) * wgt, m, in_vol, E, gslot);
     rotate_dir(g.d, cost, sint, sphi, cphi);
     g.E = E1;
     g.seg = 0.0f;
     if (E1 < P.e_cut || (kTle && in_vol && E1 <= P.tle_emin)) {
-      deposit<kTle>(P, g, buf, ds, E1 * P.src.weight, m, in_vol, kBig, gslot);
+      deposit<kTle>(P, g, buf, ds, E1 * wgt, m, in_vol, kBig, gslot);
       next = Q_E;
     } else {
       set_energy(P, S, slot, g);
@@ -1135,7 +1165,7 @@ __device__ __noinline__ int phase_rare(const Params &P, Smem &S, int slot, int g
     g.seg = 0.0f;
   } else {
     n_conv = 1;
-    deposit<kTle>(P, g, P.depbuf + (size_t)gslot * kDepBuf, ds, (g.E - 2.0f * kMc2) * P.src.weight, m, in_vol, g.E, gslot);
+    deposit<kTle>(P, g, P.depbuf + (size_t)gslot * kDepBuf, ds, (g.E - 2.0f * kMc2) * hist_weight(P, gslot), m, in_vol, g.E, gslot);
     float cost = 2.0f * rng_uniform(g.rng) - 1.0f;
     float sint = sqrtf(1.0f - cost * cost);
     float sphi, cphi;
@@ -1179,7 +1209,7 @@ __device__ __noinline__ int phase_end(const Params &P, Smem &S, int slot, int gs
   if (g.flags & F_ABSORB) {
     if (g.flags & F_CONV) n_conv = 1; else n_phot = 1;
     rng_begin(g.rng);
-    deposit<kTle>(P, g, P.depbuf + (size_t)gslot * kDepBuf, ds, g.E * P.src.weight, g.mat, (g.flags & F_INVOL) != 0, g.E, gslot);
+    deposit<kTle>(P, g, P.depbuf + (size_t)gslot * kDepBuf, ds, g.E * hist_weight(P, gslot), g.mat, (g.flags & F_INVOL) != 0, g.E, gslot);
     g.flags &= ~(F_ABSORB | F_CONV);
     c_edep += ds.edep;
   }
@@ -1230,12 +1260,12 @@ __device__ __noinline__ int phase_end(const Params &P, Smem &S, int slot, int gs
       rng_init(g.rng, P.seed, P.first + idx, 0u);
       g.flags = F_OPEN;
       g.mat = 0;
-      generate_primary(P, g);
+      generate_primary(P, g, gslot);
       g.path = 0.0f; g.seg = 0.0f;
       n_hist = 1;
       next = locate(P, g);
       if (g.E < P.e_cut) {
-        c_edep += (double)(g.E * P.src.weight);   // below the table: absorbed where it starts
+        c_edep += (double)(g.E * hist_weight(P, gslot));   // below the table: absorbed where it starts
         next = Q_E;
         S.tbin[slot] = 0.0f;
       } else {
@@ -1323,7 +1353,7 @@ __device__ __noinline__ int phase_tle(const Params &P, Smem &S, int slot, int gs
     } else {
       i[0] = (int)(st.y & 0xffffu); i[1] = (int)(st.y >> 16); i[2] = (int)st.z;
     }
-    const float kE = (0.1f * E) * P.src.weight;
+    const float kE = (0.1f * E) * hist_weight(P, gslot);
     Rng r;
     {
       const unsigned long long id = P.first + S.hidx[slot];
@@ -1513,7 +1543,7 @@ __global__ void __launch_bounds__(kThreads, 1) transport_kernel(const __grid_con
     } else if (slot[0] >= 0) {
       if (q == Q_C) next[0] = phase_compton<kTle>(P, S, slot[0], slot_base + slot[0], c_edep);
       else if (q == Q_E) next[0] = phase_end<kTle>(P, S, slot[0], slot_base + slot[0], c_edep);
-      else if (q == Q_W) next[0] = phase_world(P, S, slot[0]);
+      else if (q == Q_W) next[0] = phase_world(P, S, slot[0], slot_base + slot[0]);
       else if (kTle && q == Q_T) next[0] = phase_tle<LabelT>(P, S, slot[0], slot_base + slot[0]);
       else next[0] = phase_rare<kTle>(P, S, slot[0], slot_base + slot[0], c_edep);
     }

@@ -328,7 +328,182 @@ class VoxelSource(GenericSource):
         return s, keep
 
 
-source_types = {"GenericSource": GenericSource, "VoxelSource": VoxelSource}
+def read_phase_space_columns(path, keys):
+    """Columns `keys` (those present) of a phase-space file -> dict of numpy arrays, and the number of
+    entries.  `.root`: first tree of the file through uproot, exactly as the reference reads it
+    (sources/phspsources.py:59-75,153-158); `.npz`: the column archive PhaseSpaceActor writes when
+    uproot is not installed (actors.py)."""
+    path = str(path)
+    if path.endswith(".npz") or path.endswith(".npy"):
+        with np.load(path, allow_pickle=False) as f:
+            cols = {k: np.asarray(f[k]) for k in keys if k in f.files}
+            avail = list(f.files)
+    else:
+        try:
+            import uproot
+        except ImportError:
+            fatal(f"PhaseSpaceSource: reading '{path}' needs the uproot package (as in the reference); "
+                  f"the .npz column archives written by PhaseSpaceActor can be read without it")
+        f = uproot.open(path)
+        branches = f.keys()
+        if len(branches) == 0:
+            fatal(f"PhaseSpaceSourceGenerator: No usable branches in the root file {path}. Aborting.")
+        tree = f[branches[0]]
+        avail = list(tree.keys())
+        cols = tree.arrays([k for k in keys if k in avail], library="numpy")
+    return cols, avail
+
+
+class PhaseSpaceSource(SourceBase):
+    """Source of particles replayed from a phase-space file: position + direction + energy + weight of
+    every event are read from the file (sources/phspsources.py:262-590, GatePhaseSpaceSource.cpp:92-178).
+    The whole file is uploaded to the device once; the event with global id i replays entry
+    (entry_start + i) % num_entries, the order in which the reference's generator walks the file
+    (sequential batches, restart from the beginning at the end: phspsources.py:119-146)."""
+
+    user_info_defaults = {
+        "phsp_file": (None, {"doc": "Filename of the phase-space file (root). This is required", "is_input_file": True}),
+        "entry_start": (None, {"doc": "Starting particle in the phase-space"}),
+        "particle": ("", {"doc": "Particle name; empty: read the PDGCode column"}),
+        "global_flag": (False, {"doc": "If true, the positions of the generated particles in the phase-space are in the "
+                                       "world coordinate system. If false, they are relative to the volume this source is attached to"}),
+        "isotropic_direction": (False, {"doc": "Position, energy and weight from the phase space, isotropic momentum"}),
+        "translate_position": (False, {"doc": "Add position.translation to the positions"}),
+        "rotate_direction": (False, {"doc": "Rotate the directions by position.rotation"}),
+        "batch_size": (10000, {"doc": "Batch size to read the phsp (the GPU engine uploads the whole file once)"}),
+        "position_key": ("PrePositionLocal", {"doc": "Key of the position; sets position_key_x/y/z by adding _X _Y _Z"}),
+        "position_key_x": (None, {"doc": "Key in the phsp that contain the position X of the particle"}),
+        "position_key_y": (None, {"doc": "Key in the phsp that contain the position Y of the particle"}),
+        "position_key_z": (None, {"doc": "Key in the phsp that contain the position Z of the particle"}),
+        "position": (Box({"translation": [0, 0, 0], "rotation": np.eye(3)}),
+                     {"doc": "Default position+rotation if it is not read in the phsp"}),
+        "direction_key": ("PreDirectionLocal", {"doc": "Key of the direction; sets direction_key_x/y/z by adding _X _Y _Z"}),
+        "direction_key_x": (None, {"doc": "Key in the phsp that contain the direction X of the particle"}),
+        "direction_key_y": (None, {"doc": "Key in the phsp that contain the direction Y of the particle"}),
+        "direction_key_z": (None, {"doc": "Key in the phsp that contain the direction Z of the particle"}),
+        "energy_key": ("KineticEnergy", {"doc": "Key in the phsp that contain the energy of the particle"}),
+        "weight_key": ("Weight", {"doc": "Key in the phsp that contain the weight of the particle"}),
+        "PDGCode_key": ("PDGCode", {"doc": "Key in the phsp that contains the PDGCode of the particle"}),
+        "generate_until_next_primary": (False, {"doc": "not supported on the GPU engine"}),
+        "primary_lower_energy_threshold": (0, {"doc": "not supported on the GPU engine"}),
+        "primary_PDGCode": (0, {"doc": "not supported on the GPU engine"}),
+        "verbose": (False, {"doc": "print the particles"}),
+        "verbose_batch": (False, {"doc": "print the batches"}),
+    }
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.num_entries = None
+        self._columns = None
+        self._freeze()
+
+    def resolve_and_validate_config(self, run_timing_intervals):
+        super().resolve_and_validate_config(run_timing_intervals)
+        ui = self.user_info
+        ctx = f"PhaseSpaceSource '{self.name}'"
+        if ui.phsp_file is None:
+            fatal(f"{ctx}: phsp_file is required")
+        if int(ui.batch_size) < 1:
+            fatal("PhaseSpaceSourceGenerator: Batch size should be > 0")
+        if ui.particle not in ("", None, "None", "gamma"):
+            fatal(f"{ctx}: the B200 GPU engine transports gammas only (particle = '{ui.particle}' is not supported)")
+        if ui.generate_until_next_primary:
+            fatal(f"{ctx}: generate_until_next_primary is not supported by the B200 GPU engine")
+        if ui.activity > 0:
+            fatal(f"{ctx}: 'activity' is not supported for a phase-space source on the B200 GPU engine")
+        if ui.entry_start is None:
+            ui.entry_start = 0
+        if not np.isscalar(ui.entry_start):
+            fatal("entry_start must be a simple number is mono-thread mode")
+        for k3 in ("position", "direction"):
+            for ax in "xyz":
+                if ui[f"{k3}_key_{ax}"] is None:
+                    ui[f"{k3}_key_{ax}"] = f"{ui[k3 + '_key']}_{ax.upper()}"
+
+    def load_columns(self):
+        """float32 columns after the Python-side transforms of PhaseSpaceSourceGenerator.generate
+        (phspsources.py:195-235)."""
+        if self._columns is not None:
+            return self._columns
+        ui = self.user_info
+        keys = [ui.position_key_x, ui.position_key_y, ui.position_key_z, ui.energy_key]
+        if not ui.isotropic_direction:
+            keys += [ui.direction_key_x, ui.direction_key_y, ui.direction_key_z]
+        opt = [k for k in (ui.weight_key, ui.PDGCode_key) if k]
+        raw, avail = read_phase_space_columns(ui.phsp_file, keys + opt)
+        for k in keys:
+            if k not in raw:
+                fatal(f"PhaseSpaceSource: Key '{k}' not found. Available: {avail}")
+        f32 = lambda k: np.array(raw[k], dtype=np.float32, copy=True, order="C")
+        c = {"pos_x": f32(ui.position_key_x), "pos_y": f32(ui.position_key_y), "pos_z": f32(ui.position_key_z),
+             "energy": f32(ui.energy_key)}
+        n = len(c["pos_x"])
+        if n == 0:
+            fatal(f"PhaseSpaceSource '{self.name}': the phase-space file {ui.phsp_file} is empty")
+        if len(c["energy"]) != n:
+            fatal(f"Size mismatch: Pos {n} vs Energy {len(c['energy'])}")
+        if not ui.isotropic_direction:
+            c.update(dir_x=f32(ui.direction_key_x), dir_y=f32(ui.direction_key_y), dir_z=f32(ui.direction_key_z))
+        c["weight"] = f32(ui.weight_key) if ui.weight_key and ui.weight_key in raw else np.ones(n, dtype=np.float32)
+        if ui.particle in ("", None, "None"):
+            if ui.PDGCode_key not in raw:
+                fatal(f"PhaseSpaceSource: Key '{ui.PDGCode_key}' not found. Available: {avail}")
+            pdg = np.asarray(raw[ui.PDGCode_key]).astype(np.int32)
+            if np.any(pdg != 22):
+                bad = int(pdg[pdg != 22][0])
+                fatal(f"PhaseSpaceSource '{self.name}': the phase space holds particles other than gammas "
+                      f"(PDGCode {bad}); the B200 GPU engine transports gammas only")
+        if ui.translate_position:
+            t = ui.position.translation
+            c["pos_x"] += float(t[0])
+            c["pos_y"] += float(t[1])
+            c["pos_z"] += float(t[2])
+        if ui.rotate_direction and not ui.isotropic_direction:
+            pts = np.column_stack((c["dir_x"], c["dir_y"], c["dir_z"])).astype(np.float64)
+            rot = pts @ np.asarray(ui.position.rotation, dtype=np.float64).T
+            for i, ax in enumerate("xyz"):
+                c[f"dir_{ax}"] = np.ascontiguousarray(rot[:, i], dtype=np.float32)
+        if not ui.isotropic_direction:
+            nrm = c["dir_x"].astype(np.float64) ** 2 + c["dir_y"].astype(np.float64) ** 2 + c["dir_z"].astype(np.float64) ** 2
+            if np.any(nrm <= 0):
+                fatal(f"PhaseSpaceSource '{self.name}': entry {int(np.argmax(nrm <= 0))} has a null direction")
+        self.num_entries = n
+        self._columns = c
+        return c
+
+    def max_energy(self):
+        return float(np.max(self.load_columns()["energy"]))
+
+    @property
+    def cycle_count(self):
+        """How many times the replay passed the end of the file (phspsources.py:133-146)."""
+        if self.num_entries is None:
+            return 0
+        n_events = int(np.sum(self.user_info.number_of_primaries))
+        return int((int(self.user_info.entry_start) % self.num_entries + n_events) // self.num_entries)
+
+    def to_abi(self, attached_volume):
+        ui = self.user_info
+        c = self.load_columns()
+        n = self.num_entries
+        start = int(ui.entry_start)
+        if start > n:
+            warning(f"In source {self.name} entry_start = {start} while the phsp contains {n}. "
+                    f"We consider {start % n} instead (modulo)")
+        if ui.global_flag or attached_volume is None:
+            R, t = np.eye(3), np.zeros(3)
+        else:
+            R, t = attached_volume.world_transform()
+        kw = dict(pos_type=abi.POS_PHSP, ene_type=abi.ENE_PHSP, pos_rotation=R, pos_translation=t,
+                  dir_relative=not ui.global_flag, dir_rotation=R, weight=1.0, phsp=c, phsp_entry_start=start % n)
+        if ui.isotropic_direction:
+            kw.update(dir_type=abi.DIR_ISO, theta=(0.0, np.pi), phi=(0.0, 2 * np.pi))
+        else:
+            kw.update(dir_type=abi.DIR_PHSP)
+        return abi.make_source(**kw)
+
+
+source_types = {"GenericSource": GenericSource, "VoxelSource": VoxelSource, "PhaseSpaceSource": PhaseSpaceSource}
 
 
 def scale_counts_for_rank(counts, rank, world):
@@ -337,4 +512,4 @@ def scale_counts_for_rank(counts, rank, world):
     return counts // world + np.asarray(rank < counts % world, dtype=np.int64)
 
 
-__all__ = ["GenericSource", "VoxelSource", "SourceBase", "source_types", "scale_counts_for_rank", "warning"]
+__all__ = ["GenericSource", "VoxelSource", "PhaseSpaceSource", "SourceBase", "source_types", "scale_counts_for_rank", "warning"]

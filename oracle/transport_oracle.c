@@ -689,7 +689,17 @@ static void generate_primary(hist_t *h, const osource_t *s) {
   rng_t *r = &h->rng;
   const gate_b200_source *d = &s->d;
   float l[3] = {0.0f, 0.0f, 0.0f};
+  float ed[3] = {0.0f, 0.0f, 1.0f}, eE = 0.0f, ew = 1.0f;   /* phase-space entry */
   switch (d->pos_type) {
+  case GATE_B200_POS_PHSP: {
+    /* GatePhaseSpaceSource::GenerateOnePrimary (GatePhaseSpaceSource.cpp:137-166); entries are read
+     * sequentially and wrap at the end of the file (sources/phspsources.py:119-146) */
+    const uint64_t en = (d->phsp_entry_start % d->phsp_n_entries + h->hist) % d->phsp_n_entries;
+    l[0] = d->phsp_pos_x[en]; l[1] = d->phsp_pos_y[en]; l[2] = d->phsp_pos_z[en];
+    if (d->dir_type == GATE_B200_DIR_PHSP) { ed[0] = d->phsp_dir_x[en]; ed[1] = d->phsp_dir_y[en]; ed[2] = d->phsp_dir_z[en]; }
+    eE = d->phsp_energy[en];
+    if (d->phsp_weight) ew = d->phsp_weight[en];
+  } break;
   case GATE_B200_POS_POINT: break;
   case GATE_B200_POS_BOX:
     for (int a = 0; a < 3; ++a) l[a] = (2.0f * rng_uniform(r) - 1.0f) * (float)d->half_size[a];
@@ -761,10 +771,18 @@ static void generate_primary(hist_t *h, const osource_t *s) {
     float inv = 1.0f / sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
     h->d[0] = v[0] * inv; h->d[1] = v[1] * inv; h->d[2] = v[2] * inv;
   } break;
+  case GATE_B200_DIR_PHSP: {
+    /* direction / direction.mag(), then the rotation of the attached volume (GatePhaseSpaceSource.cpp:158-162) */
+    float inv = 1.0f / sqrtf(ed[0] * ed[0] + ed[1] * ed[1] + ed[2] * ed[2]);
+    float v[3] = {ed[0] * inv, ed[1] * inv, ed[2] * inv};
+    if (d->dir_relative) rot_apply(s->dir_rot, v, h->d);
+    else { h->d[0] = v[0]; h->d[1] = v[1]; h->d[2] = v[2]; }
+  } break;
   }
 
   float E = 0.0f;
   switch (d->ene_type) {
+  case GATE_B200_ENE_PHSP: E = eE; break;
   case GATE_B200_ENE_MONO: E = (float)d->mono_MeV; break;
   case GATE_B200_ENE_GAUSS: E = (float)d->mono_MeV + gauss(r) * (float)d->sigma_MeV; break;
   case GATE_B200_ENE_RANGE:
@@ -814,7 +832,7 @@ static void generate_primary(hist_t *h, const osource_t *s) {
   } break;
   }
   h->E = E;
-  h->w = (float)d->weight;
+  h->w = d->pos_type == GATE_B200_POS_PHSP ? ew * (float)d->weight : (float)d->weight;
 }
 
 /* ------------------------------------------------------------------ phase space */

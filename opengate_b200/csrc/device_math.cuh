@@ -139,7 +139,7 @@ __device__ __forceinline__ void rng_init(Rng &r, uint64_t seed, uint64_t hist, u
 __device__ __forceinline__ void rng_begin(Rng &r) { r.pos = 4; }
 
 // one copy of the 10 rounds for all the lazy draws of the rare phases (code size)
-__device__ __noinline__ void rng_refill(Rng &r) {
+__device__ __forceinline__ void rng_refill(Rng &r) {
   philox_block(r.k0, r.k1, r.h0, r.h1, r.blk, 0u, r.o0, r.o1, r.o2, r.o3);
   r.blk += 1u;
   r.pos = 0;

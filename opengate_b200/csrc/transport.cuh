@@ -29,6 +29,9 @@
 #ifndef GB2_THREADS
 #define GB2_THREADS 1024
 #endif
+#ifndef GB2_MIN_CTAS
+#define GB2_MIN_CTAS 1                     // resident CTAs per SM the register budget is compiled for
+#endif
 #ifndef GB2_SLOTS
 // 64 B of shared memory per slot (52 B photon state + 6 queue cells).  The slot count sets the shared
 // memory carve-out of the SM and with it what is left as L1 for the table gathers (measured on B200,
@@ -161,7 +164,7 @@ struct Smem {
   int head[Q_COUNT], tail[Q_COUNT], avail[Q_COUNT];
   int cur;                                    // phase the CTA is currently draining
   int retired;
-  unsigned long long stats[S_COUNT];
+  unsigned stats_lo[S_COUNT], stats_hi[S_COUNT];   // 64-bit counters as two words: shared memory has no native 64-bit add
   double edep;
 };
 constexpr unsigned kEmpty = 0xffffu;
@@ -294,11 +297,17 @@ __device__ __forceinline__ float tab_mu(const Params &P, int m, int ie, float fe
   return __fmaf_rn(fe, v.y - v.x, v.x);
 }
 
+// 64-bit statistics counter in shared memory: a native 32-bit add plus a carry (a 64-bit atomicAdd on
+// shared memory is a compare-and-swap loop)
+__device__ __forceinline__ void stat_add64(Smem &S, int idx, unsigned v) {
+  const unsigned old = atomicAdd(&S.stats_lo[idx], v);
+  if (old + v < old) atomicAdd(&S.stats_hi[idx], 1u);
+}
 // opportunistic warp aggregation of a statistics increment (the lanes that arrive together)
 __device__ __forceinline__ void stat_add(Smem &S, int idx, unsigned v) {
   const unsigned act = __activemask();
   const unsigned sum = __reduce_add_sync(act, v);
-  if ((int)(threadIdx.x & 31u) == __ffs(act) - 1 && sum) atomicAdd(&S.stats[idx], (unsigned long long)sum);
+  if ((int)(threadIdx.x & 31u) == __ffs(act) - 1 && sum) stat_add64(S, idx, sum);
 }
 // Several small per-lane event counts of one phase call packed into bit fields of one word: ONE warp
 // reduction for all of them (a field of `bits` bits holds the sum over 32 lanes, so every per-lane
@@ -309,7 +318,7 @@ __device__ __forceinline__ unsigned stat_reduce_packed(unsigned packed) {
   return (int)(threadIdx.x & 31u) == __ffs(act) - 1 ? sum : 0u;
 }
 __device__ __forceinline__ void stat_bump(Smem &S, int idx, unsigned v) {
-  if (v) atomicAdd(&S.stats[idx], (unsigned long long)v);
+  if (v) stat_add64(S, idx, v);
 }
 // the rare part of a deposit's bookkeeping: coalescing-buffer overflows
 __device__ __forceinline__ void stat_overflow(Smem &S, unsigned over, unsigned flush) {
@@ -375,6 +384,14 @@ __device__ __forceinline__ void set_energy(const Params &P, Smem &S, int s, Ph &
 
 // ------------------------------------------------------------------------------ scoring
 
+// Fire-and-forget fp64 add on a GLOBAL address.  atomicAdd(double*) on the generic pointers of Params
+// compiles to ATOM.E.ADD.F64 with a predicate result the warp waits for (then a QSPC test and a CAS
+// loop for the shared-memory case): one blocking L2/DRAM round trip per grid.  red.global has no
+// result: the adds of the three or four grids of a deposit leave back to back.
+__device__ __forceinline__ void red_add_f64(double *p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
+}
+
 // Add one (voxel, history) sum to the fp64 grids.  Lanes that arrive together and hit the same
 // voxel are combined first (one atomic per distinct address); squares are summed per history, never
 // of the combined value (GateDoseActor.cpp:359-381).
@@ -403,16 +420,16 @@ __device__ __forceinline__ void grid_add(const Params &P, const DepEntry &en) {
   }
   if ((int)lane == leader) {
     const DDose &D = P.dose[a];
-    atomicAdd(D.grid[GATE_B200_GRID_EDEP] + v, e);
-    if (D.flags & GATE_B200_SCORE_EDEP_SQ) atomicAdd(D.grid[GATE_B200_GRID_EDEP_SQ] + v, e2);
-    if (D.flags & GATE_B200_SCORE_DOSE) atomicAdd(D.grid[GATE_B200_GRID_DOSE] + v, d);
-    if (D.flags & GATE_B200_SCORE_DOSE_SQ) atomicAdd(D.grid[GATE_B200_GRID_DOSE_SQ] + v, d2);
-    if ((D.flags & GATE_B200_SCORE_COUNTS) && n != 0.0) atomicAdd(D.grid[GATE_B200_GRID_COUNTS] + v, n);
+    red_add_f64(D.grid[GATE_B200_GRID_EDEP] + v, e);
+    if (D.flags & GATE_B200_SCORE_EDEP_SQ) red_add_f64(D.grid[GATE_B200_GRID_EDEP_SQ] + v, e2);
+    if (D.flags & GATE_B200_SCORE_DOSE) red_add_f64(D.grid[GATE_B200_GRID_DOSE] + v, d);
+    if (D.flags & GATE_B200_SCORE_DOSE_SQ) red_add_f64(D.grid[GATE_B200_GRID_DOSE_SQ] + v, d2);
+    if ((D.flags & GATE_B200_SCORE_COUNTS) && n != 0.0) red_add_f64(D.grid[GATE_B200_GRID_COUNTS] + v, n);
   }
 }
 
 // Add the coalesced (voxel, history) entries of a closed history to the fp64 grids.
-__device__ __noinline__ void flush_buffer(const Params &P, const DepEntry *buf, int nbuf) {
+__device__ __forceinline__ void flush_buffer(const Params &P, const DepEntry *buf, int nbuf) {
   for (int j = 0; j < nbuf; ++j) grid_add(P, ld_dep(buf + j));
 }
 
@@ -420,7 +437,7 @@ __device__ __noinline__ void flush_buffer(const Params &P, const DepEntry *buf, 
 // A history touches hundreds of voxels along its flights; the event-wise squares need its sum per
 // voxel (GateTLEDoseActor.cpp:281-299 -> ScoreSquaredValue), so the sums are kept here until the
 // history ends.  The table of a slot is only ever touched by the lane that holds the slot.
-__device__ __noinline__ void tle_flush_all(const Params &P, int gslot, unsigned nlist) {
+__device__ __forceinline__ void tle_flush_all(const Params &P, int gslot, unsigned nlist) {
   DepEntry *tab = P.tle_tab + (size_t)gslot * kTleH;
   const unsigned short *list = P.tle_list + (size_t)gslot * kTleMax;
   for (unsigned j = 0; j < nlist; ++j) {
@@ -429,7 +446,7 @@ __device__ __noinline__ void tle_flush_all(const Params &P, int gslot, unsigned 
     __stcg(&tab[hh].key, kTleEmpty);
   }
 }
-__device__ __noinline__ void tle_table_add(const Params &P, int gslot, unsigned &nlist, int key, float e, float d,
+__device__ __forceinline__ void tle_table_add(const Params &P, int gslot, unsigned &nlist, int key, float e, float d,
                                            int n, unsigned &n_ent, unsigned &n_over) {
   DepEntry *tab = P.tle_tab + (size_t)gslot * kTleH;
   unsigned hh = ((unsigned)key * 2654435761u) >> (32 - kTleLog2);
@@ -464,7 +481,7 @@ struct DepStat { unsigned dep, over, flush, tle_ent, tle_over; double edep; };
 // e_tle: flight energy of the gamma whose secondaries deposit here (a TLE actor ignores them while that
 // gamma scores by track length, GateTLEDoseActor.cpp:236-243); kBig for a gamma absorbed below the cut.
 template <bool kTle>
-__device__ __noinline__ void deposit(const Params &P, Ph &g, DepEntry *buf, DepStat &ds, float e,
+__device__ __forceinline__ void deposit(const Params &P, Ph &g, DepEntry *buf, DepStat &ds, float e,
                                      int m, bool in_vol, float e_tle, int gslot) {
   ds.edep += (double)e;
   ds.dep++;
@@ -572,7 +589,7 @@ __device__ __forceinline__ int q2_segment(const Params &P, float q2) {
   while (j > 0 && __ldg(P.q2n + j) > q2) --j;
   return j;
 }
-__device__ __noinline__ float interp_q2(const Params &P, const float *__restrict__ row, float q2) {
+__device__ __forceinline__ float interp_q2(const Params &P, const float *__restrict__ row, float q2) {
   int j = q2_segment(P, q2);
   if (j < 0) return __ldg(row) * (q2 / __ldg(P.q2n));
   if (j >= P.nq - 1) return __ldg(row + P.nq - 1);
@@ -620,7 +637,7 @@ __device__ __forceinline__ int cdf_index(const float *__restrict__ cdf, int last
   return lo;
 }
 
-__device__ __noinline__ void generate_primary(const Params &P, Ph &g, int gslot) {
+__device__ __forceinline__ void generate_primary(const Params &P, Ph &g, int gslot) {
   const DSource &S = P.src;
   Rng &r = g.rng;
   rng_begin(r);
@@ -823,7 +840,7 @@ __device__ __forceinline__ int locate(const Params &P, Ph &g) {
 
 // Q_W: one flight segment of a photon travelling in the world material (outside the image volume);
 // a photon that has just left the volume is first taken to its exit point and to the world frame.
-__device__ __noinline__ int phase_world(const Params &P, Smem &S, int slot, int gslot) {
+__device__ __forceinline__ int phase_world(const Params &P, Smem &S, int slot, int gslot) {
   Ph g;
   load_ph(P, S, slot, g);
   int next;
@@ -1034,7 +1051,7 @@ __device__ __forceinline__ int volume_decide(const Params &P, Smem &S, int slot,
 // trial simply stays in the queue: trials are independent, each call owns two fresh Philox blocks
 // (trial, final state), so the lanes of a warp never wait for each other's rejection loops.
 template <bool kTle>
-__device__ __noinline__ int phase_compton(const Params &P, Smem &S, int slot, int gslot, double &c_edep) {
+__device__ __forceinline__ int phase_compton(const Params &P, Smem &S, int slot, int gslot, double &c_edep) {
   const unsigned b0 = S.blk[slot];
   S.blk[slot] = b0 + 2u;
   const float E = S.E[slot];
@@ -1113,7 +1130,7 @@ __device__ __noinline__ int phase_compton(const Params &P, Smem &S, int slot, in
 // Q_R: the rare interactions.  Rayleigh: q2 from the cumulative squared form factor, (1+cos^2)/2
 // test.  Conversion with pair_mode 1: deposit E - 2 mc2, emit two back-to-back 511 keV photons.
 template <bool kTle>
-__device__ __noinline__ int phase_rare(const Params &P, Smem &S, int slot, int gslot, double &c_edep) {
+__device__ __forceinline__ int phase_rare(const Params &P, Smem &S, int slot, int gslot, double &c_edep) {
   Ph g;
   load_ph(P, S, slot, g);
   const bool in_vol = (g.flags & F_INVOL) != 0;
@@ -1200,7 +1217,7 @@ __device__ __noinline__ int phase_rare(const Params &P, Smem &S, int slot, int g
 // owes its second annihilation photon, or it is closed (coalesced deposits -> grids) and the slot
 // claims the next history.
 template <bool kTle>
-__device__ __noinline__ int phase_end(const Params &P, Smem &S, int slot, int gslot, double &c_edep) {
+__device__ __forceinline__ int phase_end(const Params &P, Smem &S, int slot, int gslot, double &c_edep) {
   Ph g;
   load_ph(P, S, slot, g);
   int next;
@@ -1301,7 +1318,7 @@ __device__ __noinline__ int phase_end(const Params &P, Smem &S, int slot, int gs
 // slot is queued again until the flight is done (lanes never wait for each other's long flights).
 // The same phase writes the per-history table out at the end of a history (tle_state.x == -2).
 template <typename LabelT>
-__device__ __noinline__ int phase_tle(const Params &P, Smem &S, int slot, int gslot) {
+__device__ __forceinline__ int phase_tle(const Params &P, Smem &S, int slot, int gslot) {
   const unsigned fm = S.fm[slot];
   uint4 st = __ldcg(P.tle_state + gslot);
   float tcur = __uint_as_float(st.x);
@@ -1445,7 +1462,7 @@ __device__ __noinline__ int phase_tle(const Params &P, Smem &S, int slot, int gs
 
 // kTle: the engine has track-length-estimator actors (the plain kernel carries none of that code)
 template <typename LabelT, bool kTle>
-__global__ void __launch_bounds__(kThreads, 1) transport_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(kThreads, GB2_MIN_CTAS) transport_kernel(const __grid_constant__ Params P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem &S = *reinterpret_cast<Smem *>(smem_raw);
   float *s_maj = reinterpret_cast<float *>(smem_raw + sizeof(Smem));
@@ -1463,7 +1480,7 @@ __global__ void __launch_bounds__(kThreads, 1) transport_kernel(const __grid_con
     S.tail[threadIdx.x] = threadIdx.x == Q_E ? kSlots : 0;
     S.avail[threadIdx.x] = threadIdx.x == Q_E ? kSlots : 0;   // every slot starts by asking for a history
   }
-  if (threadIdx.x < S_COUNT) S.stats[threadIdx.x] = 0ull;
+  if (threadIdx.x < S_COUNT) { S.stats_lo[threadIdx.x] = 0u; S.stats_hi[threadIdx.x] = 0u; }
   if (threadIdx.x == 0) { S.retired = 0; S.edep = 0.0; S.cur = Q_E; }
   __syncthreads();
 
@@ -1581,11 +1598,14 @@ __global__ void __launch_bounds__(kThreads, 1) transport_kernel(const __grid_con
     c_edep += __shfl_xor_sync(FULL, c_edep, o);
   }
   if (lane == 0) {
-    if (c_tent) atomicAdd(&S.stats[S_TENT], (unsigned long long)c_tent);
+    if (c_tent) stat_add64(S, S_TENT, c_tent);
     if (c_edep != 0.0) atomicAdd(&S.edep, c_edep);
   }
   __syncthreads();
-  if (threadIdx.x < S_COUNT && S.stats[threadIdx.x]) atomicAdd(P.stats + threadIdx.x, S.stats[threadIdx.x]);
+  if (threadIdx.x < S_COUNT) {
+    const unsigned long long v = ((unsigned long long)S.stats_hi[threadIdx.x] << 32) | S.stats_lo[threadIdx.x];
+    if (v) atomicAdd(P.stats + threadIdx.x, v);
+  }
   if (threadIdx.x == 0 && S.edep != 0.0) atomicAdd(P.edep_total, S.edep);
 }
 

@@ -683,7 +683,7 @@ static int launch_histories(gate_b200_engine *h, int32_t source_id, uint64_t fir
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(P.ntle > 0 ? kTleThreads : kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = h->stream;
   cfg.attrs = attr;

@@ -27,7 +27,12 @@
 #include "device_math.cuh"
 
 #ifndef GB2_THREADS
-#define GB2_THREADS 1024
+// 28 warps x 72 registers.  Measured on B200 with everything inlined (profiles/experiments/README.md):
+// 1024 threads (64 registers, 216 B of spills) C3 1.40e9 / C2 1.25e9 / C1 1.11e9 primaries/s,
+// 896 (72 registers) 1.42 / 1.30 / 1.10, 768 (80 registers) 1.42 / 1.33 / 1.08; two CTAs of 640 threads
+// per SM (48 registers, 40 warps) 0.81 / 0.89 / 0.75: more warps do not help, spills and a second
+// phase's code in the instruction cache hurt.
+#define GB2_THREADS 896
 #endif
 #ifndef GB2_MIN_CTAS
 #define GB2_MIN_CTAS 1                     // resident CTAs per SM the register budget is compiled for
@@ -43,6 +48,13 @@
 namespace gb2 {
 
 constexpr int kThreads = GB2_THREADS;
+#ifndef GB2_TLE_THREADS
+#define GB2_TLE_THREADS 640              // 96 registers: the march state stays in registers (C3 TLE +5..9 % over 896 threads)
+#endif
+// the kernel with the track-length-estimator phase runs with fewer threads and more registers each
+// (the voxel march keeps a long walk state live; at 72 registers it spills 700 bytes)
+constexpr int kTleThreads = GB2_TLE_THREADS;
+template <bool kTle> constexpr int threads_of() { return kTle ? kTleThreads : kThreads; }
 constexpr int kSlots = GB2_SLOTS;          // photon slots per CTA (< 65535: queue cells are 16 bit)
 constexpr int kWoodcockK = 4;              // tentative collisions per Woodcock call (2 Philox blocks)
 #ifndef GB2_VWIDTH
@@ -1462,15 +1474,15 @@ __device__ __forceinline__ int phase_tle(const Params &P, Smem &S, int slot, int
 
 // kTle: the engine has track-length-estimator actors (the plain kernel carries none of that code)
 template <typename LabelT, bool kTle>
-__global__ void __launch_bounds__(kThreads, GB2_MIN_CTAS) transport_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(threads_of<kTle>(), GB2_MIN_CTAS) transport_kernel(const __grid_constant__ Params P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem &S = *reinterpret_cast<Smem *>(smem_raw);
   float *s_maj = reinterpret_cast<float *>(smem_raw + sizeof(Smem));
   const unsigned lane = threadIdx.x & 31u;
   const unsigned FULL = 0xffffffffu;
 
-  for (int i = threadIdx.x; i < P.ne; i += kThreads) s_maj[i] = P.maj[i];
-  for (int i = threadIdx.x; i < kSlots; i += kThreads) {
+  for (int i = threadIdx.x; i < P.ne; i += blockDim.x) s_maj[i] = P.maj[i];
+  for (int i = threadIdx.x; i < kSlots; i += blockDim.x) {
     S.fm[i] = 0; S.blk[i] = 0; S.hidx[i] = 0; S.tbin[i] = 0.0f;
 #pragma unroll
     for (int t = 0; t < Q_COUNT; ++t) S.cell[t][i] = (unsigned short)(t == Q_E ? i : kEmpty);

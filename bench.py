@@ -227,6 +227,12 @@ def main():
         run_reference(args)
         return
 
+    # stdout carries exactly ONE line (the JSON): anything libraries print while the bench runs
+    # (NCCL's version banner on communicator creation) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -338,7 +344,11 @@ def main():
         line["e2e"] = e2e
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(S, args.cpu_seconds)
-        print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

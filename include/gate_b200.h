@@ -241,9 +241,15 @@ int gate_b200_sync(gate_b200_engine *h);
 /* Replaces: fetch_from_cpp_image (doseactors.py:255-270): copy one accumulator grid
  * (double, nx*ny*nz) to the host. */
 int gate_b200_get_dose_grid(gate_b200_engine *h, int32_t actor_id, int32_t which, double *out);
-/* Device pointer of an accumulator grid (for the NCCL reduce done by the host plumbing). */
-int gate_b200_dose_grid_device_ptr(gate_b200_engine *h, int32_t actor_id, int32_t which,
-                                   void **ptr, uint64_t *n_elements);
+/* Device buffers that hold the accumulators of one dose actor, for the sum-reduce over GPUs done by
+ * the host plumbing (NCCL; the reference merges parallel runs by summing images offline,
+ * actors/dataitems.py:1238-1247).  On the device the scored ones of the sums edep, edep2, dose, dose2
+ * of a voxel are the doubles of ONE record (stride 1, 2 or 4 doubles for 1, 2 or 3-4 scored sums, in
+ * that order: a deposit touches one 32-byte DRAM sector): buffer 0 is that record array
+ * (stride * nvox doubles), buffer 1 the counts image (nvox doubles) when it is scored.
+ * get/set_dose_grid convert between the records and the dense x-fastest arrays of the ABI. */
+int gate_b200_dose_buffers(gate_b200_engine *h, int32_t actor_id, int32_t max_buffers, void **ptrs,
+                           uint64_t *n_elements, int32_t *n_buffers);
 /* Host -> device overwrite of an accumulator (used after a reduce / for merging runs). */
 int gate_b200_set_dose_grid(gate_b200_engine *h, int32_t actor_id, int32_t which, const double *in);
 /* Replaces: GateDoseActor::ComputeMeanUncertainty (GateDoseActor.cpp:280-330). */

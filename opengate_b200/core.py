@@ -30,7 +30,7 @@ EXPORTS = [
     "gate_b200_set_stream", "gate_b200_set_tables", "gate_b200_set_world",
     "gate_b200_set_image_volume", "gate_b200_add_source", "gate_b200_add_dose_actor",
     "gate_b200_add_tle_dose_actor", "gate_b200_add_phsp_actor", "gate_b200_begin_run", "gate_b200_run_source", "gate_b200_sync",
-    "gate_b200_get_dose_grid", "gate_b200_dose_grid_device_ptr", "gate_b200_set_dose_grid",
+    "gate_b200_get_dose_grid", "gate_b200_dose_buffers", "gate_b200_set_dose_grid",
     "gate_b200_mean_uncertainty", "gate_b200_phsp_count", "gate_b200_get_phsp",
     "gate_b200_get_stats", "gate_b200_timed_run",
 ]
@@ -88,7 +88,7 @@ def load_library():
     L.gate_b200_sync.argtypes = [vp]
     L.gate_b200_get_dose_grid.argtypes = [vp, i32, i32, C.POINTER(C.c_double)]
     L.gate_b200_set_dose_grid.argtypes = [vp, i32, i32, C.POINTER(C.c_double)]
-    L.gate_b200_dose_grid_device_ptr.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(u64)]
+    L.gate_b200_dose_buffers.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(u64), C.POINTER(i32)]
     L.gate_b200_mean_uncertainty.argtypes = [vp, i32, u64, i32, C.c_double, C.POINTER(C.c_double)]
     L.gate_b200_phsp_count.argtypes = [vp, i32, C.POINTER(u64)]
     L.gate_b200_get_phsp.argtypes = [vp, i32, u64, C.POINTER(abi.PhspColumns), C.POINTER(u64)]
@@ -215,11 +215,14 @@ class Engine:
         a = np.ascontiguousarray(array, dtype=np.float64)
         self._check(self.L.gate_b200_set_dose_grid(self.h, actor, which, a.ctypes.data_as(C.POINTER(C.c_double))))
 
-    def dose_grid_device_ptr(self, actor, which):
-        p = C.c_void_p()
-        n = C.c_uint64()
-        self._check(self.L.gate_b200_dose_grid_device_ptr(self.h, actor, which, C.byref(p), C.byref(n)))
-        return p.value, n.value
+    def dose_buffers(self, actor):
+        """[(device pointer, number of doubles)]: the voxel-record array (multigpu.record_layout) and, when
+        scored, the counts image of one dose actor (what a multi-GPU sum-reduce has to touch)."""
+        ptrs = (C.c_void_p * 2)()
+        ns = (C.c_uint64 * 2)()
+        nb = C.c_int32()
+        self._check(self.L.gate_b200_dose_buffers(self.h, actor, 2, ptrs, ns, C.byref(nb)))
+        return [(ptrs[i], ns[i]) for i in range(nb.value)]
 
     def mean_uncertainty(self, actor, n_events, top_voxels, threshold):
         out = C.c_double()

@@ -31,6 +31,7 @@ struct DoseActor {
   gate_b200_dose_desc desc;
   DDose dev;
   size_t nvox = 0;
+  double *rec = nullptr;      // [nvox][gstride] voxel records: the scored ones of {edep, edep2, dose, dose2}
 };
 
 struct PhspActor {
@@ -62,6 +63,8 @@ struct gate_b200_engine {
   unsigned long long *d_next = nullptr;
   unsigned long long *d_stats = nullptr;
   double *d_edep = nullptr;
+  double *d_stage = nullptr;            // dense staging array of get/set_dose_grid
+  size_t stage_elems = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_events;
   double kernel_ms = 0.0;
@@ -157,6 +160,18 @@ __global__ void __launch_bounds__(256) label_scan_kernel(const LabelT *__restric
   __syncthreads();
   for (int i = threadIdx.x; i < nw; i += blockDim.x)
     if (s_present[i]) atomicOr(&present[i], s_present[i]);
+}
+
+// component k of every voxel record <-> a dense array (the layout the ABI hands to the caller)
+__global__ void __launch_bounds__(256) grid_extract_kernel(const double *__restrict__ comp, size_t n, size_t stride,
+                                                           double *__restrict__ dense) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dense[i] = comp[i * stride];
+}
+__global__ void __launch_bounds__(256) grid_scatter_kernel(double *__restrict__ comp, size_t n, size_t stride,
+                                                           const double *__restrict__ dense) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    comp[i * stride] = dense[i];
 }
 
 void affine_from_double(Affine &a, const double m12[12]) {
@@ -534,10 +549,16 @@ int gate_b200_add_dose_actor(gate_b200_engine *h, const gate_b200_dose_desc *d, 
   affine_from_double(D.v2i, comp);
   const int want[5] = {GATE_B200_SCORE_EDEP, GATE_B200_SCORE_EDEP_SQ, GATE_B200_SCORE_DOSE,
                        GATE_B200_SCORE_DOSE_SQ, GATE_B200_SCORE_COUNTS};
-  for (int k = 0; k < 5; ++k) {
-    if (D.flags & want[k]) {
-      if (int rc = dev_alloc(h, &D.grid[k], nv, true)) return rc;
-    }
+  // one 32-byte record per voxel for the four sums (a deposit touches one DRAM sector instead of
+  // one per grid); the counts image, rarely asked for, is a plain array
+  int n_active = 0;
+  for (int k = 0; k < 4; ++k) n_active += (D.flags & want[k]) ? 1 : 0;
+  D.gstride = n_active <= 1 ? 1 : (n_active == 2 ? 2 : 4);      // a record never straddles a sector
+  if (int rc = dev_alloc(h, &A.rec, nv * (size_t)D.gstride, true)) return rc;
+  for (int k = 0, slot = 0; k < 4; ++k)
+    if (D.flags & want[k]) D.grid[k] = A.rec + slot++;
+  if (D.flags & want[4]) {
+    if (int rc = dev_alloc(h, &D.grid[4], nv, true)) return rc;
   }
   h->dose.push_back(A);
   h->P.dose[h->dose.size() - 1] = D;
@@ -631,9 +652,11 @@ int gate_b200_add_phsp_actor(gate_b200_engine *h, const gate_b200_phsp_desc *d, 
 int gate_b200_begin_run(gate_b200_engine *h, int32_t /*run_id*/) {
   if (!h) return GATE_B200_EINVAL;
   CU(cudaSetDevice(h->device));
-  for (auto &A : h->dose)
-    for (int k = 0; k < 5; ++k)
-      if (A.dev.grid[k]) CU(cudaMemsetAsync(A.dev.grid[k], 0, A.nvox * sizeof(double), h->stream));
+  for (auto &A : h->dose) {
+    CU(cudaMemsetAsync(A.rec, 0, A.nvox * (size_t)A.dev.gstride * sizeof(double), h->stream));
+    if (A.dev.grid[GATE_B200_GRID_COUNTS])
+      CU(cudaMemsetAsync(A.dev.grid[GATE_B200_GRID_COUNTS], 0, A.nvox * sizeof(double), h->stream));
+  }
   for (auto &A : h->phsp) {
     CU(cudaMemsetAsync(A.dev.n_rows, 0, sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(A.dev.n_dropped, 0, sizeof(unsigned long long), h->stream));
@@ -743,13 +766,31 @@ static int check_grid(gate_b200_engine *h, int32_t actor_id, int32_t which, doub
   return 0;
 }
 
+// dense staging array for get/set_dose_grid (kept for the life of the engine, grown on demand)
+static int staging(gate_b200_engine *h, size_t n, double **out) {
+  if (h->stage_elems < n) {
+    if (int rc = dev_alloc(h, &h->d_stage, n)) return rc;   // an older, smaller one stays in `allocs` until destroy
+    h->stage_elems = n;
+  }
+  *out = h->d_stage;
+  return 0;
+}
+
 int gate_b200_get_dose_grid(gate_b200_engine *h, int32_t actor_id, int32_t which, double *out) {
   if (!h || !out) return GATE_B200_EINVAL;
   double *p; size_t n;
   if (int rc = check_grid(h, actor_id, which, &p, &n)) return rc;
   CU(cudaSetDevice(h->device));
+  const size_t stride = (size_t)h->dose[actor_id].dev.gstride;
+  if (which != GATE_B200_GRID_COUNTS && stride > 1) {
+    double *dense;
+    if (int rc = staging(h, n, &dense)) return rc;
+    grid_extract_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(p, n, stride, dense);
+    CU(cudaGetLastError());
+    p = dense;
+  }
+  CU(cudaMemcpyAsync(out, p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  CU(cudaMemcpy(out, p, n * sizeof(double), cudaMemcpyDeviceToHost));
   return GATE_B200_OK;
 }
 
@@ -758,18 +799,31 @@ int gate_b200_set_dose_grid(gate_b200_engine *h, int32_t actor_id, int32_t which
   double *p; size_t n;
   if (int rc = check_grid(h, actor_id, which, &p, &n)) return rc;
   CU(cudaSetDevice(h->device));
+  const size_t stride = (size_t)h->dose[actor_id].dev.gstride;
+  if (which == GATE_B200_GRID_COUNTS || stride == 1) {
+    CU(cudaMemcpyAsync(p, in, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  } else {
+    double *dense;
+    if (int rc = staging(h, n, &dense)) return rc;
+    CU(cudaMemcpyAsync(dense, in, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    grid_scatter_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(p, n, stride, dense);
+    CU(cudaGetLastError());
+  }
   CU(cudaStreamSynchronize(h->stream));
-  CU(cudaMemcpy(p, in, n * sizeof(double), cudaMemcpyHostToDevice));
   return GATE_B200_OK;
 }
 
-int gate_b200_dose_grid_device_ptr(gate_b200_engine *h, int32_t actor_id, int32_t which, void **ptr,
-                                   uint64_t *n_elements) {
-  if (!h || !ptr) return GATE_B200_EINVAL;
-  double *p; size_t n;
-  if (int rc = check_grid(h, actor_id, which, &p, &n)) return rc;
-  *ptr = p;
-  if (n_elements) *n_elements = n;
+int gate_b200_dose_buffers(gate_b200_engine *h, int32_t actor_id, int32_t max_buffers, void **ptrs,
+                           uint64_t *n_elements, int32_t *n_buffers) {
+  if (!h || !ptrs || !n_elements || !n_buffers) return GATE_B200_EINVAL;
+  if (actor_id < 0 || actor_id >= (int)h->dose.size()) return fail(h, GATE_B200_EINVAL, "unknown dose actor %d", actor_id);
+  DoseActor &A = h->dose[actor_id];
+  int nb = 0;
+  if (nb < max_buffers) { ptrs[nb] = A.rec; n_elements[nb] = (uint64_t)A.nvox * (uint64_t)A.dev.gstride; ++nb; }
+  if (A.dev.grid[GATE_B200_GRID_COUNTS] && nb < max_buffers) {
+    ptrs[nb] = A.dev.grid[GATE_B200_GRID_COUNTS]; n_elements[nb] = (uint64_t)A.nvox; ++nb;
+  }
+  *n_buffers = nb;
   return GATE_B200_OK;
 }
 

@@ -102,7 +102,12 @@ struct DDose {
   int size[3];
   Affine v2i;
   int flags, hit_type;
+  // accumulators: the scored ones of edep, edep2, dose, dose2 are the doubles of ONE record per voxel
+  // (1, 2 or 4 doubles: all the adds of a deposit land in one 32-byte DRAM sector); grid[k] points at
+  // component k of voxel 0 and consecutive voxels are gstride doubles apart.  counts (grid[4]) is a
+  // plain array.
   double *grid[5];
+  int gstride;
   // track-length estimator (GateTLEDoseActor): tle = 1; aligned = the grid is the image grid
   int tle, aligned;
   float tle_thr;
@@ -432,10 +437,11 @@ __device__ __forceinline__ void grid_add(const Params &P, const DepEntry &en) {
   }
   if ((int)lane == leader) {
     const DDose &D = P.dose[a];
-    red_add_f64(D.grid[GATE_B200_GRID_EDEP] + v, e);
-    if (D.flags & GATE_B200_SCORE_EDEP_SQ) red_add_f64(D.grid[GATE_B200_GRID_EDEP_SQ] + v, e2);
-    if (D.flags & GATE_B200_SCORE_DOSE) red_add_f64(D.grid[GATE_B200_GRID_DOSE] + v, d);
-    if (D.flags & GATE_B200_SCORE_DOSE_SQ) red_add_f64(D.grid[GATE_B200_GRID_DOSE_SQ] + v, d2);
+    const size_t o = (size_t)v * (size_t)D.gstride;
+    red_add_f64(D.grid[GATE_B200_GRID_EDEP] + o, e);
+    if (D.flags & GATE_B200_SCORE_EDEP_SQ) red_add_f64(D.grid[GATE_B200_GRID_EDEP_SQ] + o, e2);
+    if (D.flags & GATE_B200_SCORE_DOSE) red_add_f64(D.grid[GATE_B200_GRID_DOSE] + o, d);
+    if (D.flags & GATE_B200_SCORE_DOSE_SQ) red_add_f64(D.grid[GATE_B200_GRID_DOSE_SQ] + o, d2);
     if ((D.flags & GATE_B200_SCORE_COUNTS) && n != 0.0) red_add_f64(D.grid[GATE_B200_GRID_COUNTS] + v, n);
   }
 }

@@ -8,11 +8,11 @@
 
 namespace gb2 {
 
-__global__ void max_below_kernel(const double *__restrict__ g, size_t n, double bound,
+__global__ void max_below_kernel(const double *__restrict__ g, size_t n, size_t stride, double bound,
                                  unsigned long long *out_bits) {
   unsigned long long best = 0ull;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    double v = g[i];
+    double v = g[i * stride];
     if (v < bound && v > 0.0) {
       unsigned long long b = (unsigned long long)__double_as_longlong(v);
       if (b > best) best = b;
@@ -25,24 +25,24 @@ __global__ void max_below_kernel(const double *__restrict__ g, size_t n, double 
   if ((threadIdx.x & 31) == 0 && best) atomicMax(out_bits, best);
 }
 
-__global__ void count_equal_kernel(const double *__restrict__ g, size_t n, double value,
+__global__ void count_equal_kernel(const double *__restrict__ g, size_t n, size_t stride, double value,
                                    unsigned long long *out_count) {
   unsigned long long c = 0;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    if (g[i] == value) ++c;
+    if (g[i * stride] == value) ++c;
   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out_count, c);
 }
 
-__global__ void mean_unc_kernel(const double *__restrict__ e, const double *__restrict__ e2, size_t n,
+__global__ void mean_unc_kernel(const double *__restrict__ e, const double *__restrict__ e2, size_t n, size_t stride,
                                 double thr, double nev, double *out_sum, unsigned long long *out_cnt) {
   double s = 0.0;
   unsigned long long c = 0;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    double val = e[i];
+    double val = e[i * stride];
     if (val > thr) {
       val /= nev;
-      double sq = e2[i] / nev;
+      double sq = e2[i * stride] / nev;
       double u = (1.0 / (nev - 1.0)) * (sq - val * val);
       if (u < 0.0) u = 0.0;
       u = sqrt(u) / val;
@@ -80,14 +80,14 @@ extern "C" int gate_b200_mean_uncertainty(gate_b200_engine *h, int32_t actor_id,
   long long taken = 0;
   while (taken < top_voxels) {
     CU(cudaMemsetAsync(d_u, 0, 2 * sizeof(unsigned long long), h->stream));
-    gb2::max_below_kernel<<<blocks, threads, 0, h->stream>>>(e, A.nvox, bound, d_u);
+    gb2::max_below_kernel<<<blocks, threads, 0, h->stream>>>(e, A.nvox, (size_t)A.dev.gstride, bound, d_u);
     unsigned long long bits = 0;
     CU(cudaMemcpyAsync(&bits, d_u, sizeof bits, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     if (bits == 0) break;  // only zeros left: they add nothing to the sum
     double v;
     memcpy(&v, &bits, sizeof v);
-    gb2::count_equal_kernel<<<blocks, threads, 0, h->stream>>>(e, A.nvox, v, d_u + 1);
+    gb2::count_equal_kernel<<<blocks, threads, 0, h->stream>>>(e, A.nvox, (size_t)A.dev.gstride, v, d_u + 1);
     unsigned long long cnt = 0;
     CU(cudaMemcpyAsync(&cnt, d_u + 1, sizeof cnt, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -100,7 +100,7 @@ extern "C" int gate_b200_mean_uncertainty(gate_b200_engine *h, int32_t actor_id,
   const double mean_max = denom > 0 ? sum / (double)denom : 0.0;
   CU(cudaMemsetAsync(d_u, 0, 2 * sizeof(unsigned long long), h->stream));
   CU(cudaMemsetAsync(d_s, 0, sizeof(double), h->stream));
-  gb2::mean_unc_kernel<<<blocks, threads, 0, h->stream>>>(e, e2, A.nvox, mean_max * threshold, nev, d_s, d_u);
+  gb2::mean_unc_kernel<<<blocks, threads, 0, h->stream>>>(e, e2, A.nvox, (size_t)A.dev.gstride, mean_max * threshold, nev, d_s, d_u);
   double s = 0.0;
   unsigned long long c = 0;
   CU(cudaMemcpyAsync(&s, d_s, sizeof s, cudaMemcpyDeviceToHost, h->stream));

@@ -333,19 +333,29 @@ class GpuSimulationEngine:
         out = {}
         if self.dist is not None:
             e, ids = self.engines[0], self.ids[0]
-            for w in which_list:
-                if reduce_in_place:
-                    t = multigpu.grid_tensor(e, ids[1][actor_index], w)
+            aid = ids[1][actor_index]
+            bufs = multigpu.buffer_tensors(e, aid)     # [records {edep, edep2, dose, dose2} x nvox, (counts)]
+            if reduce_in_place:
+                for t in bufs:
                     self.dist.all_reduce(t)
-                    out[w] = e.dose_grid(ids[1][actor_index], w)
-                else:
-                    import torch
-                    t = multigpu.grid_tensor(e, ids[1][actor_index], w).clone()
-                    self.dist.all_reduce(t)
-                    nx, ny, nz = [int(x) for x in self.dose_actors[actor_index].size]
-                    out[w] = t.cpu().numpy().reshape(nz, ny, nx)
-                    del t
-                    torch.cuda.empty_cache()
+                for w in which_list:
+                    out[w] = e.dose_grid(aid, w)
+            else:
+                import torch
+                t = bufs[0].clone()
+                self.dist.all_reduce(t)
+                nx, ny, nz = [int(x) for x in self.dose_actors[actor_index].size]
+                stride, offset = multigpu.record_layout(self.dose_actors[actor_index].score_flags())
+                rec = t.view(nz, ny, nx, stride)
+                for w in which_list:
+                    if w == abi.GRID_COUNTS:
+                        c = bufs[1].clone()
+                        self.dist.all_reduce(c)
+                        out[w] = c.cpu().numpy().reshape(nz, ny, nx)
+                    else:
+                        out[w] = rec[..., offset[w]].contiguous().cpu().numpy()
+                del t, rec
+                torch.cuda.empty_cache()
             return out
         for w in which_list:
             acc = None

@@ -1,10 +1,10 @@
 """Multi-GPU plumbing: one process per GPU (torchrun), histories sharded by global history id,
-one NCCL sum-reduce of every accumulator grid at the end of a run.
+one NCCL sum-reduce of the accumulator records at the end of a run.
 
 The reference has no collective at all: its parallel runs are merged offline by summing images
 and `number_of_samples` (opengate/actors/dataitems.py:1238-1247; thread split rule
 opengate/sources/base.py:190-197).  Here the same merge is one `torch.distributed.reduce`
-per grid over NVLink, on the device buffers the C-ABI exposes.
+per dose actor over NVLink, on the device buffers the C-ABI exposes (`gate_b200_dose_buffers`).
 """
 
 from __future__ import annotations
@@ -32,11 +32,21 @@ class _DeviceArray:
         self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
-def grid_tensor(engine, actor, which):
-    """torch view (no copy) of one fp64 accumulator grid living in the engine's device memory."""
+def buffer_tensors(engine, actor):
+    """torch views (no copy) of the accumulator buffers of one dose actor in the engine's device memory:
+    the voxel records (the scored ones of edep, edep2, dose, dose2: stride * nvox doubles, see
+    record_layout) and, when scored, the counts image."""
     import torch
-    ptr, n = engine.dose_grid_device_ptr(actor, which)
-    return torch.as_tensor(_DeviceArray(ptr, n), device=torch.device("cuda", engine.device))
+    return [torch.as_tensor(_DeviceArray(ptr, n), device=torch.device("cuda", engine.device))
+            for ptr, n in engine.dose_buffers(actor)]
+
+
+def record_layout(score_flags):
+    """(stride, {grid: offset}) of the voxel records of a dose actor: the scored ones of edep, edep2,
+    dose, dose2 in that order, 1, 2 or 4 doubles per voxel (same rule as gate_b200_add_dose_actor)."""
+    act = [w for w in active_grids(score_flags) if w != abi.GRID_COUNTS]
+    stride = 1 if len(act) <= 1 else (2 if len(act) == 2 else 4)
+    return stride, {w: i for i, w in enumerate(act)}
 
 
 def active_grids(score_flags):
@@ -46,18 +56,15 @@ def active_grids(score_flags):
                            (abi.GRID_COUNTS, abi.SCORE_COUNTS)) if f & b]
 
 
-def reduce_dose_grids(engine, actor_ids, setup_or_flags, dst=0, group=None):
-    """Sum every active grid of the given actors onto rank `dst` (in place, NCCL or gloo)."""
+def reduce_dose_grids(engine, actor_ids, setup_or_flags=None, dst=0, group=None):
+    """Sum the accumulator buffers of the given actors onto rank `dst` (in place, NCCL): one reduce of
+    the voxel-record array per actor (+ one of the counts image when it is scored)."""
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
-    descs = None
-    if hasattr(setup_or_flags, "dose"):   # dose actors first, then the TLE dose actors (engine id order)
-        descs = list(setup_or_flags.dose) + [t[0] for t in getattr(setup_or_flags, "tle", [])]
-    for i, a in enumerate(actor_ids):
-        flags = descs[i].score_flags if descs is not None else setup_or_flags[i]
-        for w in active_grids(flags):
-            dist.reduce(grid_tensor(engine, a, w), dst=dst, op=dist.ReduceOp.SUM, group=group)
+    for a in actor_ids:
+        for t in buffer_tensors(engine, a):
+            dist.reduce(t, dst=dst, op=dist.ReduceOp.SUM, group=group)
 
 
 def reduce_counters(stats: dict, device, group=None):

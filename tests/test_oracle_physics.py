@@ -134,3 +134,48 @@ def test_spectrum_histogram_sampling_reproduces_weights():
     sel = p > 5e-3
     assert np.all(np.abs(got[sel] - p[sel]) / p[sel] < 0.12), np.abs(got[sel] - p[sel]) / p[sel]
     assert e0.min() >= edges[0] and e0.max() <= edges[-1]
+
+
+@pytest.mark.parametrize("material,energies,tol", [
+    ("G4_WATER", (0.03, 0.06, 0.1, 0.3, 1.0), 0.015),          # measured deviations: -0.7 ... +0.4 %
+    ("G4_AIR", (0.03, 0.1, 0.5), 0.015),                        # -0.8 ... +0.3 %
+    ("G4_BONE_COMPACT_ICRU", (0.04, 0.08, 0.2, 0.6), 0.015),    # -0.2 ... +0.2 %
+])
+def test_energy_transfer_coefficient_matches_reference_mu_en_database(material, energies, tol):
+    """The process split and the Compton final state of the restated physics against the ONE per-process
+    quantity the reference tree pins: mu_en/rho of its GateMuTables database (GateMuDatabase.h, looked up as
+    GateMaterialMuHandler does, `opengate_b200/mu_handler.py` == the reference's own code, test_mu_handler).
+    In the kerma configuration mu_tr = [sigma_phot E + sigma_compt <T>] / E; <T> is measured from traced
+    oracle histories: the first deposit of a history is the energy handed to electrons at its first
+    non-Rayleigh interaction (Rayleigh changes neither E nor the deposits), so
+    mean(first deposit) / E = mu_tr / (mu - mu_Rayl).  mu_en = mu_tr (1 - g) with g < 1 % here."""
+    from opengate_b200 import mu_handler
+    db = materials.MaterialDatabase()
+    db.read_from_file(materials.DEFAULT_DB)
+    mat = db.find_or_build_material(material)
+    ref = mu_handler.material_table(mat, "EPDL")
+    n = 20000
+    for energy in energies:
+        S, T, mats = water_slab_setup(energy, 1.0e6 if material == "G4_AIR" else 4000.0, n, material=material)
+        S.phsp = []
+        S.world_half = (3.0e6, 3.0e6, 3.0e6)
+        o = TransportOracle(S.seed)
+        sids, _, _ = S.apply(o)
+        first = []
+        for h in range(n):
+            tr = o.trace(sids[0], h)
+            if tr.n_dep > 0:
+                first.append(tr.dep_e[0])
+        assert len(first) > 0.8 * n     # the rest left the slab sideways after Rayleigh scatters only
+        frac = float(np.mean(first)) / energy
+        sem = float(np.std(first)) / energy / np.sqrt(len(first))
+        # process probabilities at this energy, same interpolation as the device
+        t = (np.log(energy) - np.log(T.e_min)) / (np.log(T.e_max) - np.log(T.e_min)) * (T.n_energy - 1)
+        i = min(int(t), T.n_energy - 2)
+        f = t - i
+        lerp = lambda a: float(a[0, i] + f * (a[0, i + 1] - a[0, i]))  # noqa: E731
+        p_rayl = lerp(T.cum_rayl) - lerp(T.cum_compt)
+        mu_rho = T.mu_per_mm(0, energy) * 10.0 / mats[0].density_g_cm3          # cm2/g
+        mu_tr = frac * mu_rho * (1.0 - p_rayl)
+        want = ref.mu_en_over_rho(energy)
+        assert abs(mu_tr - want) < tol * want + 4 * sem * mu_rho, (material, energy, mu_tr, want)

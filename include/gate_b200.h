@@ -69,9 +69,9 @@ typedef struct {
  * All frames are already composed to WORLD by the caller. */
 enum { GATE_B200_POS_POINT = 0, GATE_B200_POS_BOX = 1, GATE_B200_POS_SPHERE = 2,
        GATE_B200_POS_DISC = 3, GATE_B200_POS_CYLINDER = 4, GATE_B200_POS_VOXELS = 5,
-       GATE_B200_POS_PHSP = 6 };
+       GATE_B200_POS_PHSP = 6, GATE_B200_POS_SURFACE_SPHERE = 7 };
 enum { GATE_B200_DIR_ISO = 0, GATE_B200_DIR_MOMENTUM = 1, GATE_B200_DIR_FOCUSED = 2,
-       GATE_B200_DIR_PHSP = 3 };
+       GATE_B200_DIR_PHSP = 3, GATE_B200_DIR_COS = 4, GATE_B200_DIR_BEAM2D = 5 };
 enum { GATE_B200_ENE_MONO = 0, GATE_B200_ENE_GAUSS = 1, GATE_B200_ENE_RANGE = 2,
        GATE_B200_ENE_SPECTRUM_DISCRETE = 3, GATE_B200_ENE_SPECTRUM_HISTOGRAM = 4,
        GATE_B200_ENE_SPECTRUM_HISTOGRAM_LINEAR = 5, GATE_B200_ENE_CDF = 6, GATE_B200_ENE_PHSP = 7 };
@@ -117,6 +117,11 @@ typedef struct {
   const float *phsp_dir_x, *phsp_dir_y, *phsp_dir_z;   /* NULL with dir_type ISO         */
   const float *phsp_energy;                             /* MeV                            */
   const float *phsp_weight;
+  /* dir_type BEAM2D (GateGenericSource.cpp:428-433 -> G4SPSAngDistribution beam2d): angular deviations
+   * drawn from two Gaussians, rad.  dir_type COS (cosine law) uses theta / phi like ISO.  Both, and
+   * pos_type SURFACE_SPHERE (points on the sphere of `radius`), are Geant4 G4SPS* algorithms that are
+   * not in the reference tree: restated from the published sources. */
+  double dir_sigma[2];
 } gate_b200_source;
 
 /* ---- dose actor -------------------------------------------------------------------------

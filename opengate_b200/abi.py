@@ -13,8 +13,8 @@ import numpy as np
 ABI_VERSION = 3
 
 # enums --------------------------------------------------------------------------------
-POS_POINT, POS_BOX, POS_SPHERE, POS_DISC, POS_CYLINDER, POS_VOXELS, POS_PHSP = range(7)
-DIR_ISO, DIR_MOMENTUM, DIR_FOCUSED, DIR_PHSP = range(4)
+POS_POINT, POS_BOX, POS_SPHERE, POS_DISC, POS_CYLINDER, POS_VOXELS, POS_PHSP, POS_SURFACE_SPHERE = range(8)
+DIR_ISO, DIR_MOMENTUM, DIR_FOCUSED, DIR_PHSP, DIR_COS, DIR_BEAM2D = range(6)
 (ENE_MONO, ENE_GAUSS, ENE_RANGE, ENE_SPECTRUM_DISCRETE, ENE_SPECTRUM_HISTOGRAM,
  ENE_SPECTRUM_HISTOGRAM_LINEAR, ENE_CDF, ENE_PHSP) = range(8)
 HIT_RANDOM, HIT_PRE, HIT_POST, HIT_MIDDLE = range(4)
@@ -57,6 +57,7 @@ class Source(C.Structure):
         ("phsp_pos_x", _fp), ("phsp_pos_y", _fp), ("phsp_pos_z", _fp),
         ("phsp_dir_x", _fp), ("phsp_dir_y", _fp), ("phsp_dir_z", _fp),
         ("phsp_energy", _fp), ("phsp_weight", _fp),
+        ("dir_sigma", C.c_double * 2),
     ]
 
 
@@ -138,7 +139,7 @@ def make_source(pos_type=POS_POINT, half_size=(0, 0, 0), radius=0.0, sigma_x=0.0
                 ene_type=ENE_MONO, mono=0.0, sigma=0.0, e_min=0.0, e_max=0.0,
                 spectrum_energy=None, spectrum_cdf=None, weight=1.0,
                 vox_size=(0, 0, 0), vox_spacing=(1, 1, 1), vox_origin=(0, 0, 0),
-                cdf_z=None, cdf_y=None, cdf_x=None, phsp=None, phsp_entry_start=0):
+                cdf_z=None, cdf_y=None, cdf_x=None, phsp=None, phsp_entry_start=0, dir_sigma=(0.0, 0.0)):
     """Fill a gate_b200_source; returns (struct, keepalive list).
     phsp: dict of float32 arrays pos_x/y/z, energy and optionally dir_x/y/z, weight (phase-space replay)."""
     s = Source()
@@ -159,6 +160,7 @@ def make_source(pos_type=POS_POINT, half_size=(0, 0, 0), radius=0.0, sigma_x=0.0
     s.momentum = (C.c_double * 3)(*mom)
     s.focus_point = (C.c_double * 3)(*[float(x) for x in focus_point])
     s.dir_relative = 1 if dir_relative else 0
+    s.dir_sigma = (C.c_double * 2)(*[float(x) for x in dir_sigma])
     s.dir_rotation = (C.c_double * 9)(*np.asarray(eye if dir_rotation is None else dir_rotation, float).reshape(-1))
     s.ene_type = ene_type
     s.mono_MeV, s.sigma_MeV, s.e_min_MeV, s.e_max_MeV = float(mono), float(sigma), float(e_min), float(e_max)

@@ -433,8 +433,8 @@ int gate_b200_add_source(gate_b200_engine *h, const gate_b200_source *s, int32_t
   memset(&d, 0, sizeof d);
   d.pos_type = s->pos_type; d.dir_type = s->dir_type; d.ene_type = s->ene_type;
   d.dir_relative = s->dir_relative;
-  if (d.pos_type < 0 || d.pos_type > GATE_B200_POS_PHSP) return fail(h, GATE_B200_EINVAL, "bad pos_type %d", d.pos_type);
-  if (d.dir_type < 0 || d.dir_type > GATE_B200_DIR_PHSP) return fail(h, GATE_B200_EINVAL, "bad dir_type %d", d.dir_type);
+  if (d.pos_type < 0 || d.pos_type > GATE_B200_POS_SURFACE_SPHERE) return fail(h, GATE_B200_EINVAL, "bad pos_type %d", d.pos_type);
+  if (d.dir_type < 0 || d.dir_type > GATE_B200_DIR_BEAM2D) return fail(h, GATE_B200_EINVAL, "bad dir_type %d", d.dir_type);
   if (d.ene_type < 0 || d.ene_type > GATE_B200_ENE_PHSP) return fail(h, GATE_B200_EINVAL, "bad ene_type %d", d.ene_type);
   const bool phsp = d.pos_type == GATE_B200_POS_PHSP;
   if (phsp != (d.ene_type == GATE_B200_ENE_PHSP) || (!phsp && d.dir_type == GATE_B200_DIR_PHSP) ||
@@ -455,6 +455,8 @@ int gate_b200_add_source(gate_b200_engine *h, const gate_b200_source *s, int32_t
   }
   d.radius = (float)s->radius; d.sigma_x = (float)s->sigma_x; d.sigma_y = (float)s->sigma_y;
   d.cos_tmin = (float)cos(s->theta[0]); d.cos_tmax = (float)cos(s->theta[1]);
+  d.sin2_tmin = (float)(sin(s->theta[0]) * sin(s->theta[0])); d.sin2_tmax = (float)(sin(s->theta[1]) * sin(s->theta[1]));
+  d.dir_sx = (float)s->dir_sigma[0]; d.dir_sy = (float)s->dir_sigma[1];
   d.phi0_turn = (float)(s->phi[0] / 6.283185307179586);
   d.dphi_turn = (float)((s->phi[1] - s->phi[0]) / 6.283185307179586);
   d.mono = (float)s->mono_MeV; d.sigma = (float)s->sigma_MeV;

@@ -86,6 +86,7 @@ struct DSource {
   Affine pos;
   float dir_rot[9];
   float cos_tmin, cos_tmax, phi0_turn, dphi_turn;
+  float sin2_tmin, sin2_tmax, dir_sx, dir_sy;   // cosine law, beam2d
   float mom[3], focus[3];
   float mono, sigma, emin, emax, weight;
   int n_spec;
@@ -699,6 +700,15 @@ __device__ __forceinline__ void generate_primary(const Params &P, Ph &g, int gsl
       l[2] = (2.0f * rng_uniform(r) - 1.0f) * S.half[2];
     }
   } break;
+  case GATE_B200_POS_SURFACE_SPHERE: {
+    // G4SPSPosDistribution::GeneratePointsOnSurface, Sphere: theta = acos(1 - 2u), phi = 2 pi u'
+    const float cost = 1.0f - 2.0f * rng_uniform(r);
+    const float s2 = 1.0f - cost * cost;
+    const float sint = sqrtf(s2 > 0.0f ? s2 : 0.0f);
+    float sp, cp;
+    d_sincos2pi(rng_uniform(r), sp, cp);
+    l[0] = S.radius * sint * cp; l[1] = S.radius * sint * sp; l[2] = S.radius * cost;
+  } break;
   case GATE_B200_POS_VOXELS: {
     const int nx = S.vox_n[0], ny = S.vox_n[1], nz = S.vox_n[2];
     int i, j, k, tries;
@@ -742,6 +752,39 @@ __device__ __forceinline__ void generate_primary(const Params &P, Ph &g, int gsl
     float v0 = S.focus[0] - g.p[0], v1 = S.focus[1] - g.p[1], v2 = S.focus[2] - g.p[2];
     float inv = 1.0f / sqrtf(v0 * v0 + v1 * v1 + v2 * v2);
     g.d[0] = v0 * inv; g.d[1] = v1 * inv; g.d[2] = v2 * inv;
+  } break;
+  case GATE_B200_DIR_COS: {
+    // G4SPSAngDistribution::GenerateCosineLawFlux: sin^2(theta) uniform between sin^2(min) and sin^2(max)
+    const float st2 = rng_uniform(r) * (S.sin2_tmax - S.sin2_tmin) + S.sin2_tmin;
+    const float sint = sqrtf(st2 > 0.0f ? st2 : 0.0f);
+    const float c2 = 1.0f - st2;
+    const float cost = sqrtf(c2 > 0.0f ? c2 : 0.0f);
+    float turn = S.phi0_turn + S.dphi_turn * rng_uniform(r);
+    turn = turn - floorf(turn);
+    float sp, cp;
+    d_sincos2pi(turn, sp, cp);
+    float v[3] = {-sint * cp, -sint * sp, -cost};
+    if (S.dir_relative) rot_apply(S.dir_rot, v, g.d);
+    else { g.d[0] = v[0]; g.d[1] = v[1]; g.d[2] = v[2]; }
+  } break;
+  case GATE_B200_DIR_BEAM2D: {
+    // G4SPSAngDistribution::GenerateBeamFlux (beam2d): px, py ~ N(0, sigma_x/y), theta = |(px, py)|,
+    // phi = atan2(py, px); momentum = -(sin t cos p, sin t sin p, cos t).  cos p = px / theta and
+    // sin p = py / theta, so no inverse trigonometric function is needed.
+    const float px = gauss(r) * S.dir_sx;
+    const float py = gauss(r) * S.dir_sy;
+    const float th = sqrtf(px * px + py * py);
+    float v[3] = {0.0f, 0.0f, -1.0f};
+    if (th != 0.0f) {
+      float turn = th * 0.15915494309189535f;
+      turn = turn - floorf(turn);
+      float st, ct;
+      d_sincos2pi(turn, st, ct);
+      const float k = st / th;
+      v[0] = -(k * px); v[1] = -(k * py); v[2] = -ct;
+    }
+    if (S.dir_relative) rot_apply(S.dir_rot, v, g.d);
+    else { g.d[0] = v[0]; g.d[1] = v[1]; g.d[2] = v[2]; }
   } break;
   case GATE_B200_DIR_PHSP: {
     // direction / direction.mag(), then the rotation of the attached volume (GatePhaseSpaceSource.cpp:158-162)

@@ -140,13 +140,11 @@ class GenericSource(SourceBase):
             fatal(f"In {ctx}: size and translation must be 3-vectors")
         if np.asarray(p.rotation).shape != (3, 3):
             fatal(f"In {ctx}: 'rotation' must be convertible to a 3x3 matrix/array, but got: {p.rotation}")
-        if p.type == "surface_sphere":
-            fatal(f"In {ctx}: position.type 'surface_sphere' is not supported by the B200 GPU engine")
         if p.confine:
             fatal(f"In {ctx}: position.confine is not supported by the B200 GPU engine")
-        if d.type not in {"iso", "momentum", "focused"}:
+        if d.type not in {"iso", "momentum", "focused", "beam2d", "cos"}:
             fatal(f"In {ctx}: direction.type '{d.type}' is not supported by the B200 GPU engine "
-                  f"(supported: iso, momentum, focused)")
+                  f"(supported: iso, momentum, focused, beam2d, cos)")
         if d.angular_acceptance.get("policy") not in (None, "None"):
             fatal(f"In {ctx}: direction.angular_acceptance is not supported by the B200 GPU engine")
         et = "CDF" if e.is_cdf else e.type
@@ -229,7 +227,8 @@ class GenericSource(SourceBase):
         R_pos, t_pos, R_vol = self._frames(attached_volume)
         kw = {}
         kw["pos_type"] = {"point": abi.POS_POINT, "box": abi.POS_BOX, "sphere": abi.POS_SPHERE,
-                          "disc": abi.POS_DISC, "cylinder": abi.POS_CYLINDER}[p.type]
+                          "disc": abi.POS_DISC, "cylinder": abi.POS_CYLINDER,
+                          "surface_sphere": abi.POS_SURFACE_SPHERE}[p.type]
         half = [0.5 * float(s) for s in p.size]
         if p.type == "cylinder":
             half[2] = float(p.dz) if p.dz is not None else 0.0   # G4 SetHalfZ(dz), GateGenericSource.cpp:350-352
@@ -239,8 +238,13 @@ class GenericSource(SourceBase):
         # GLOBAL rotation of the source (attached volume x position.rotation) is applied
         # (GateGenericSource.cpp:176-195, GateSPSAngDistribution.cpp:10-18)
         relative = bool(self.direction_relative_to_attached_volume)
-        if d.type == "iso":
-            kw.update(dir_type=abi.DIR_ISO, theta=d.theta, phi=d.phi, dir_relative=relative, dir_rotation=R_pos)
+        if d.type in ("iso", "cos"):
+            kw.update(dir_type=abi.DIR_ISO if d.type == "iso" else abi.DIR_COS, theta=d.theta, phi=d.phi,
+                      dir_relative=relative, dir_rotation=R_pos)
+        elif d.type == "beam2d":
+            # two Gaussian angular deviations around -z of the source frame (GateGenericSource.cpp:428-433)
+            kw.update(dir_type=abi.DIR_BEAM2D, dir_sigma=[float(x) for x in d.sigma], dir_relative=relative,
+                      dir_rotation=R_pos)
         elif d.type == "momentum":
             m = np.asarray(d.momentum, dtype=np.float64)
             if relative:

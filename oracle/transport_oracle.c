@@ -180,6 +180,7 @@ typedef struct {
   affine_t pos;      /* local -> world */
   float dir_rot[9];
   float cos_tmin, cos_tmax, phi0_turn, dphi_turn;
+  float sin2_tmin, sin2_tmax, dir_sx, dir_sy;
   float mom[3], focus[3];
   float *spec_e, *spec_cdf;
 } osource_t;
@@ -727,6 +728,16 @@ static void generate_primary(hist_t *h, const osource_t *s) {
       l[2] = (2.0f * rng_uniform(r) - 1.0f) * (float)d->half_size[2];
     }
   } break;
+  case GATE_B200_POS_SURFACE_SPHERE: {
+    /* G4SPSPosDistribution::GeneratePointsOnSurface, Sphere: theta = acos(1 - 2u), phi = 2 pi u' */
+    float R = (float)d->radius;
+    float cost = 1.0f - 2.0f * rng_uniform(r);
+    float s2 = 1.0f - cost * cost;
+    float sint = sqrtf(s2 > 0.0f ? s2 : 0.0f);
+    float sp, cp;
+    o_sincos2pi(rng_uniform(r), &sp, &cp);
+    l[0] = R * sint * cp; l[1] = R * sint * sp; l[2] = R * cost;
+  } break;
   case GATE_B200_POS_VOXELS: {
     int nx = d->vox_size[0], ny = d->vox_size[1], nz = d->vox_size[2];
     int i, j, k, tries;
@@ -770,6 +781,38 @@ static void generate_primary(hist_t *h, const osource_t *s) {
     float v[3] = {s->focus[0] - h->p[0], s->focus[1] - h->p[1], s->focus[2] - h->p[2]};
     float inv = 1.0f / sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
     h->d[0] = v[0] * inv; h->d[1] = v[1] * inv; h->d[2] = v[2] * inv;
+  } break;
+  case GATE_B200_DIR_COS: {
+    /* G4SPSAngDistribution::GenerateCosineLawFlux: sin^2(theta) uniform between sin^2(min) and sin^2(max) */
+    float st2 = rng_uniform(r) * (s->sin2_tmax - s->sin2_tmin) + s->sin2_tmin;
+    float sint = sqrtf(st2 > 0.0f ? st2 : 0.0f);
+    float c2 = 1.0f - st2;
+    float cost = sqrtf(c2 > 0.0f ? c2 : 0.0f);
+    float turn = s->phi0_turn + s->dphi_turn * rng_uniform(r);
+    turn = turn - floorf(turn);
+    float sp, cp;
+    o_sincos2pi(turn, &sp, &cp);
+    float v[3] = {-sint * cp, -sint * sp, -cost};
+    if (d->dir_relative) rot_apply(s->dir_rot, v, h->d);
+    else { h->d[0] = v[0]; h->d[1] = v[1]; h->d[2] = v[2]; }
+  } break;
+  case GATE_B200_DIR_BEAM2D: {
+    /* G4SPSAngDistribution::GenerateBeamFlux (beam2d): px, py ~ N(0, sigma), theta = |(px, py)|,
+     * phi = atan2(py, px), momentum = -(sin t cos p, sin t sin p, cos t) with cos p = px / theta */
+    float px = gauss(r) * s->dir_sx;
+    float py = gauss(r) * s->dir_sy;
+    float th = sqrtf(px * px + py * py);
+    float v[3] = {0.0f, 0.0f, -1.0f};
+    if (th != 0.0f) {
+      float turn = th * 0.15915494309189535f;
+      turn = turn - floorf(turn);
+      float st, ct;
+      o_sincos2pi(turn, &st, &ct);
+      float k = st / th;
+      v[0] = -(k * px); v[1] = -(k * py); v[2] = -ct;
+    }
+    if (d->dir_relative) rot_apply(s->dir_rot, v, h->d);
+    else { h->d[0] = v[0]; h->d[1] = v[1]; h->d[2] = v[2]; }
   } break;
   case GATE_B200_DIR_PHSP: {
     /* direction / direction.mag(), then the rotation of the attached volume (GatePhaseSpaceSource.cpp:158-162) */
@@ -1266,6 +1309,8 @@ int oracle_add_source(oracle_engine *g, const gate_b200_source *s) {
     o->focus[r] = (float)s->focus_point[r];
   }
   o->cos_tmin = (float)cos(s->theta[0]); o->cos_tmax = (float)cos(s->theta[1]);
+  o->sin2_tmin = (float)(sin(s->theta[0]) * sin(s->theta[0])); o->sin2_tmax = (float)(sin(s->theta[1]) * sin(s->theta[1]));
+  o->dir_sx = (float)s->dir_sigma[0]; o->dir_sy = (float)s->dir_sigma[1];
   o->phi0_turn = (float)(s->phi[0] / 6.283185307179586);
   o->dphi_turn = (float)((s->phi[1] - s->phi[0]) / 6.283185307179586);
   int ne = 0;

@@ -413,6 +413,12 @@ def test_energy_source_types_and_positions(cuda_required):
              spectrum_cdf=cdf_lin / cdf_lin[-1]),
         dict(pos_type=abi.POS_POINT, ene_type=abi.ENE_CDF, spectrum_energy=np.array([0.05, 0.1, 0.2, 0.4]),
              spectrum_cdf=np.array([0.0, 0.3, 0.8, 1.0])),
+        dict(pos_type=abi.POS_SURFACE_SPHERE, radius=40.0, ene_type=abi.ENE_MONO, mono=0.2),
+        dict(pos_type=abi.POS_DISC, radius=5.0, ene_type=abi.ENE_MONO, mono=0.15, dir_type=abi.DIR_COS,
+             theta=(0.0, 1.2), phi=(0.3, 5.0), dir_relative=True,
+             dir_rotation=np.array([[1.0, 0.0, 0.0], [0.0, -1.0, 0.0], [0.0, 0.0, -1.0]])),
+        dict(pos_type=abi.POS_POINT, ene_type=abi.ENE_MONO, mono=0.3, dir_type=abi.DIR_BEAM2D, dir_sigma=(0.05, 0.2),
+             dir_relative=True, dir_rotation=np.array([[1.0, 0.0, 0.0], [0.0, -1.0, 0.0], [0.0, 0.0, -1.0]])),
     ]
     rot = np.array([[0.0, 0.0, -1.0], [0.0, 1.0, 0.0], [1.0, 0.0, 0.0]])
     dirs = [dict(dir_type=abi.DIR_ISO), dict(dir_type=abi.DIR_MOMENTUM, momentum=(0.1, 0.2, 1.0)),
@@ -420,7 +426,8 @@ def test_energy_source_types_and_positions(cuda_required):
             dict(dir_type=abi.DIR_ISO, theta=(0.1, 0.6), phi=(0.5, 2.0), dir_relative=True, dir_rotation=rot)]
     for i, v in enumerate(variants):
         kw = dict(v)
-        kw.update(dirs[i % len(dirs)])
+        if "dir_type" not in kw:
+            kw.update(dirs[i % len(dirs)])
         kw.setdefault("pos_translation", (3.0, -4.0, -200.0))
         s, keep = abi.make_source(**kw)
         S = SMALL["c1"](10)

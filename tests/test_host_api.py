@@ -265,7 +265,7 @@ def test_unsupported_configurations_are_fatal(tmp_path):
     with pytest.raises(Exception, match="score_in"):
         sim.run(_backend=OracleBackend)
     dose.score_in = "material"
-    src.direction.type = "beam2d"
+    src.direction.type = "histogram"
     with pytest.raises(Exception, match="direction.type"):
         sim.run(_backend=OracleBackend)
 

@@ -179,3 +179,37 @@ def test_energy_transfer_coefficient_matches_reference_mu_en_database(material, 
         mu_tr = frac * mu_rho * (1.0 - p_rayl)
         want = ref.mu_en_over_rho(energy)
         assert abs(mu_tr - want) < tol * want + 4 * sem * mu_rho, (material, energy, mu_tr, want)
+
+
+def test_surface_sphere_cosine_law_and_beam2d_samplers():
+    """The three G4SPS* samplers restated from the published Geant4 algorithms (their source is not in the
+    reference tree): points on a sphere surface, cosine-law directions, 2-D Gaussian beam divergence."""
+    S, T, _ = water_slab_setup(0.1, 10.0, 10)
+    o = TransportOracle(S.seed)
+    flip = np.array([[1.0, 0.0, 0.0], [0.0, -1.0, 0.0], [0.0, 0.0, -1.0]])   # the G4 flux points to -z: turn it to +z
+    S.sources = [
+        abi.make_source(pos_type=abi.POS_SURFACE_SPHERE, radius=25.0, pos_translation=(1.0, 2.0, -500.0),
+                        dir_type=abi.DIR_COS, theta=(0.0, np.pi / 2), dir_relative=True, dir_rotation=flip,
+                        ene_type=abi.ENE_MONO, mono=0.1),
+        abi.make_source(pos_type=abi.POS_POINT, pos_translation=(0.0, 0.0, -500.0), dir_type=abi.DIR_BEAM2D,
+                        dir_sigma=(0.02, 0.05), dir_relative=True, dir_rotation=flip, ene_type=abi.ENE_MONO, mono=0.1),
+    ]
+    sids, _, _ = S.apply(o)
+    n = 20000
+    tr = [o.trace(sids[0], h) for h in range(n)]
+    p = np.array([t.p0[:] for t in tr]) - np.array([1.0, 2.0, -500.0])
+    d = np.array([t.d0[:] for t in tr])
+    assert np.allclose(np.linalg.norm(p, axis=1), 25.0, atol=1e-3)
+    assert np.all(np.abs(p.mean(axis=0)) < 4 * 25.0 / np.sqrt(3 * n))          # uniform on the sphere: mean 0
+    assert abs(np.mean(p[:, 2] ** 2) - 25.0 ** 2 / 3) < 0.03 * 25.0 ** 2        # <z^2> = R^2 / 3
+    assert np.allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-5)
+    assert np.all(d[:, 2] >= 0)
+    assert abs(d[:, 2].mean() - 2.0 / 3.0) < 4 * np.sqrt(1.0 / 18.0 / n)        # pdf 2 cos(t) sin(t): <cos t> = 2/3
+    tr = [o.trace(sids[1], h) for h in range(n)]
+    d = np.array([t.d0[:] for t in tr])
+    assert np.allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-5)
+    assert d[:, 2].min() > 0.95
+    # small angles: d_x ~ N(0, sigma_x), d_y ~ -N(0, sigma_y) (the flip), independent
+    assert d[:, 0].std() == pytest.approx(0.02, rel=0.03)
+    assert d[:, 1].std() == pytest.approx(0.05, rel=0.03)
+    assert abs(np.corrcoef(d[:, 0], d[:, 1])[0, 1]) < 0.03

@@ -215,6 +215,10 @@ int gate_b200_abi_version(void);
  * number of GPUs or on scheduling. */
 int gate_b200_create(int device_id, uint64_t seed, gate_b200_engine **out);
 void gate_b200_destroy(gate_b200_engine *h);
+/* Device memory of destroyed engines stays in the device's stream-ordered pool so that the next engine of
+ * the process gets it without a trip to the driver (GATE_B200_POOL_RETAIN=0 disables this).  This call
+ * hands the cached blocks back (cudaMemPoolTrimTo 0), e.g. before another library needs the memory. */
+int gate_b200_release_cached_memory(int device_id);
 const char *gate_b200_last_error(const gate_b200_engine *h);
 /* Launch on the caller's stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = own. */
 int gate_b200_set_stream(gate_b200_engine *h, void *cuda_stream);

@@ -26,7 +26,7 @@ NVCC_FLAGS = [
 ]
 
 EXPORTS = [
-    "gate_b200_abi_version", "gate_b200_create", "gate_b200_destroy", "gate_b200_last_error",
+    "gate_b200_abi_version", "gate_b200_create", "gate_b200_destroy", "gate_b200_release_cached_memory", "gate_b200_last_error",
     "gate_b200_set_stream", "gate_b200_set_tables", "gate_b200_set_world",
     "gate_b200_set_image_volume", "gate_b200_add_source", "gate_b200_add_dose_actor",
     "gate_b200_add_tle_dose_actor", "gate_b200_add_phsp_actor", "gate_b200_begin_run", "gate_b200_run_source", "gate_b200_sync",
@@ -72,6 +72,8 @@ def load_library():
     L.gate_b200_abi_version.restype = C.c_int
     L.gate_b200_create.argtypes = [C.c_int, u64, C.POINTER(vp)]
     L.gate_b200_destroy.argtypes = [vp]
+    L.gate_b200_release_cached_memory.argtypes = [C.c_int]
+    L.gate_b200_release_cached_memory.restype = C.c_int
     L.gate_b200_destroy.restype = None
     L.gate_b200_last_error.argtypes = [vp]
     L.gate_b200_last_error.restype = C.c_char_p
@@ -102,6 +104,13 @@ def load_library():
         raise GateB200Error(f"ABI mismatch: library {v}, python {abi.ABI_VERSION}")
     _lib = L
     return L
+
+
+def release_cached_memory(device=0):
+    """Give the device memory cached from destroyed engines back to the driver (gate_b200_release_cached_memory)."""
+    rc = load_library().gate_b200_release_cached_memory(int(device))
+    if rc != 0:
+        raise GateB200Error(f"gate_b200_release_cached_memory failed ({rc})")
 
 
 class Engine:

@@ -281,6 +281,14 @@ void gate_b200_destroy(gate_b200_engine *h) {
   delete h;
 }
 
+int gate_b200_release_cached_memory(int device_id) {
+  cudaMemPool_t pool;
+  if (cudaSetDevice(device_id) != cudaSuccess) return GATE_B200_ECUDA;
+  if (cudaDeviceSynchronize() != cudaSuccess) return GATE_B200_ECUDA;
+  if (cudaDeviceGetDefaultMemPool(&pool, device_id) != cudaSuccess) return GATE_B200_ECUDA;
+  return cudaMemPoolTrimTo(pool, 0) == cudaSuccess ? GATE_B200_OK : GATE_B200_ECUDA;
+}
+
 const char *gate_b200_last_error(const gate_b200_engine *h) { return h ? h->err.c_str() : "null engine"; }
 
 int gate_b200_set_stream(gate_b200_engine *h, void *cuda_stream) {

@@ -437,3 +437,25 @@ def test_energy_source_types_and_positions(cuda_required):
         compare(eng, orc, S, ids)
         assert eng.stats()["histories"] == 4000
         eng.close()
+
+
+def test_pool_reuse_and_release_of_cached_device_memory(cuda_required):
+    """Engines allocate from the device's stream-ordered pool: a second engine of the process reuses the
+    blocks of a destroyed one; gate_b200_release_cached_memory hands them back to the driver."""
+    import torch
+    from opengate_b200 import core
+    S = SMALL["c3"](1000)
+    free0, _ = torch.cuda.mem_get_info(0)
+    for _ in range(2):
+        eng = core.Engine(0, S.seed)
+        se, de, pe = S.apply(eng)
+        eng.begin_run()
+        eng.run_source(se[0], 0, 1000)
+        eng.sync()
+        assert eng.stats()["histories"] == 1000
+        eng.close()
+    cached, _ = torch.cuda.mem_get_info(0)
+    assert cached < free0                      # the pool keeps the engine's blocks
+    core.release_cached_memory(0)
+    after, _ = torch.cuda.mem_get_info(0)
+    assert after > cached

@@ -445,6 +445,7 @@ def test_pool_reuse_and_release_of_cached_device_memory(cuda_required):
     import torch
     from opengate_b200 import core
     S = SMALL["c3"](1000)
+    core.release_cached_memory(0)              # what earlier tests of this process left in the pool
     free0, _ = torch.cuda.mem_get_info(0)
     for _ in range(2):
         eng = core.Engine(0, S.seed)

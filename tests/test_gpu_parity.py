@@ -460,3 +460,4 @@ def test_pool_reuse_and_release_of_cached_device_memory(cuda_required):
     core.release_cached_memory(0)
     after, _ = torch.cuda.mem_get_info(0)
     assert after > cached
+

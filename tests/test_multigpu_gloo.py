@@ -82,3 +82,17 @@ def test_two_rank_run_equals_single_rank():
             assert np.array_equal(g, want)
         else:
             np.testing.assert_allclose(g, want, rtol=1e-12, atol=0)
+
+
+def test_record_layout_follows_the_device_rule():
+    """Voxel records of a dose actor: the scored ones of edep, edep2, dose, dose2 in that order, 1, 2 or 4
+    doubles per voxel (gate_b200_add_dose_actor); the host side of the multi-GPU reduce relies on it."""
+    from opengate_b200 import abi
+    E, E2, D, D2, C = abi.SCORE_EDEP, abi.SCORE_EDEP_SQ, abi.SCORE_DOSE, abi.SCORE_DOSE_SQ, abi.SCORE_COUNTS
+    assert multigpu.record_layout(0) == (1, {abi.GRID_EDEP: 0})                       # edep is always scored
+    assert multigpu.record_layout(E | C) == (1, {abi.GRID_EDEP: 0})
+    assert multigpu.record_layout(E | E2) == (2, {abi.GRID_EDEP: 0, abi.GRID_EDEP_SQ: 1})
+    assert multigpu.record_layout(E | D) == (2, {abi.GRID_EDEP: 0, abi.GRID_DOSE: 1})
+    assert multigpu.record_layout(E | E2 | D) == (4, {abi.GRID_EDEP: 0, abi.GRID_EDEP_SQ: 1, abi.GRID_DOSE: 2})
+    assert multigpu.record_layout(E | E2 | D | D2 | C)[0] == 4
+    assert multigpu.record_layout(E | D | D2)[1] == {abi.GRID_EDEP: 0, abi.GRID_DOSE: 1, abi.GRID_DOSE_SQ: 2}

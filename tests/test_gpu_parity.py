@@ -461,3 +461,40 @@ def test_pool_reuse_and_release_of_cached_device_memory(cuda_required):
     after, _ = torch.cuda.mem_get_info(0)
     assert after > cached
 
+
+
+@pytest.mark.parametrize("flags", [abi.SCORE_EDEP, abi.SCORE_EDEP | abi.SCORE_DOSE, abi.SCORE_EDEP | abi.SCORE_DOSE | abi.SCORE_DOSE_SQ,
+                                   ALL_FLAGS])
+def test_voxel_record_buffers_match_the_dense_grids(cuda_required, flags):
+    """gate_b200_dose_buffers exposes the record array the multi-GPU reduce works on; its layout
+    (multigpu.record_layout) must agree with what get_dose_grid extracts, and set_dose_grid must invert it."""
+    import torch
+    from opengate_b200 import multigpu
+    from opengate_b200.core import Engine
+    S = SMALL["c3"](3000)
+    S.dose[0].score_flags = flags
+    eng = Engine(0, S.seed)
+    se, de, pe = S.apply(eng)
+    eng.begin_run()
+    eng.run_source(se[0], 0, 3000)
+    eng.sync()
+    bufs = multigpu.buffer_tensors(eng, de[0])
+    stride, offset = multigpu.record_layout(flags)
+    nx, ny, nz = [int(x) for x in S.dose[0].size]
+    assert bufs[0].numel() == stride * nx * ny * nz
+    rec = bufs[0].view(nz, ny, nx, stride).cpu().numpy()
+    for w in multigpu.active_grids(flags):
+        g = eng.dose_grid(de[0], w)
+        if w == abi.GRID_COUNTS:
+            assert np.array_equal(bufs[1].cpu().numpy().reshape(nz, ny, nx), g)
+        else:
+            assert np.array_equal(rec[..., offset[w]], g)
+    assert eng.dose_grid(de[0], abi.GRID_EDEP).sum() > 0
+    # host -> device overwrite of one component leaves the others alone
+    e0 = eng.dose_grid(de[0], abi.GRID_EDEP)
+    eng.set_dose_grid(de[0], abi.GRID_EDEP, 2.0 * e0)
+    assert np.array_equal(eng.dose_grid(de[0], abi.GRID_EDEP), 2.0 * e0)
+    for w in multigpu.active_grids(flags):
+        if w not in (abi.GRID_EDEP, abi.GRID_COUNTS):
+            assert np.array_equal(eng.dose_grid(de[0], w), rec[..., offset[w]])
+    eng.close()

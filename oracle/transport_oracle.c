@@ -21,12 +21,21 @@
  *     GateSPSVoxelsPosDistribution.cpp:29-72, GateSingleParticleSource.cpp:89-137
  *     (position, then direction, then energy)
  *   - phase-space entering/exiting rows: GatePhaseSpaceActor.cpp:119-201
+ *   - phase-space replay source: GatePhaseSpaceSource.cpp:92-178, sources/phspsources.py:119-258
+ *   - track-length estimator: GateTLEDoseActor.cpp:185-300 (mu_en tables: GateMaterialMuHandler.cpp:159-263,
+ *     GateMuTables.cpp:47-107, restated in opengate_b200/mu_handler.py and checked against the reference's
+ *     own GateMuTables.cpp compiled into oracle/_ref)
+ *   - G4SPS position / direction samplers (surface_sphere, cosine law, beam2d): Geant4, not in the tree,
+ *     restated from the published algorithms
  *   - photon physics: Geant4 11.4.2 is NOT in the reference tree; the
  *     interaction sampling follows the published algorithms (Klein-Nishina composition-
  *     rejection of the Geant4 Physics Reference Manual "Compton scattering", scattering-
  *     function rejection and form-factor sampling as in the Livermore models, Woodcock
  *     delta tracking).  PARITY UNPINNED against Geant4 for this part: no golden vector of
  *     the reference's transport is available in this container (tests/data submodule absent).
+ *     What the tree does pin (tests/test_oracle_physics.py, tests/test_golden_reference.py): total
+ *     attenuation = NIST (opengate/data/PhotonAttenuation.py), and the energy-transfer coefficient
+ *     mu_tr/rho of this physics = mu_en/rho of the reference's EPDL database within 0.8 %.
  */
 #include "transport_oracle.h"
 

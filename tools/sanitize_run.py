@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""Small runs of every kernel variant for compute-sanitizer (development aid):
+    compute-sanitizer --tool memcheck|initcheck python tools/sanitize_run.py"""
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import numpy as np  # noqa: E402
+
+from opengate_b200 import abi  # noqa: E402
+from opengate_b200.core import Engine  # noqa: E402
+import small_setups  # noqa: E402
+import tle_setups  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+cases = {"c1": small_setups.c1(n), "c2": small_setups.c2(n), "c3": small_setups.c3(n), "c4": small_setups.c4(n),
+         "c3_tle_sq": tle_setups.c3_tle(n), "c3_tle_nosq": tle_setups.c3_tle(n, flags=abi.SCORE_EDEP | abi.SCORE_DOSE),
+         "c4_tle": tle_setups.c4_tle(n)}
+S = small_setups.c3(n)
+S.labels = S.labels.astype(np.uint16)
+cases["c3_u16"] = S
+for name, S in cases.items():
+    eng = Engine(0, S.seed)
+    se, de, pe = S.apply(eng)
+    eng.begin_run()
+    eng.run_source(se[0], 0, n)
+    eng.sync()
+    st = eng.stats()
+    for d in de:
+        eng.dose_grid(d, abi.GRID_EDEP)
+    for p in pe:
+        eng.phsp(p)
+    print(name, st["histories"], st["tentative_collisions"], st["tle_steps"], flush=True)
+    eng.close()

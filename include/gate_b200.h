@@ -233,6 +233,16 @@ int gate_b200_set_world(gate_b200_engine *h, const double half_size[3], int32_t 
 int gate_b200_set_image_volume(gate_b200_engine *h, const void *labels, int32_t label_bytes,
                                const int32_t size[3], const double spacing[3],
                                const double world_to_volume[12]);
+/* Replaces: ImageVolume.create_label_image (geometry/volumes.py:1200-1243) + the above: the HU image goes
+ * to the device and the label volume is made there, label = bin_labels[np.digitize(hu, bins)]
+ * (bins sorted ascending, n_bins entries; bin_labels n_bins + 1 entries; integer-exact: the comparison
+ * is done in double like numpy's).  labels_out (may be NULL) receives the label volume
+ * (nx*ny*nz entries of label_bytes) for callers that want the host copy the reference keeps. */
+enum { GATE_B200_HU_INT16 = 0, GATE_B200_HU_FLOAT32 = 1, GATE_B200_HU_FLOAT64 = 2 };
+int gate_b200_set_image_volume_hu(gate_b200_engine *h, const void *hu, int32_t hu_type, const int32_t size[3],
+                                  const double spacing[3], const double world_to_volume[12], int32_t n_bins,
+                                  const double *bins, const uint16_t *bin_labels, int32_t label_bytes,
+                                  void *labels_out);
 int gate_b200_add_source(gate_b200_engine *h, const gate_b200_source *s, int32_t *source_id);
 int gate_b200_add_dose_actor(gate_b200_engine *h, const gate_b200_dose_desc *d, int32_t *actor_id);
 int gate_b200_add_tle_dose_actor(gate_b200_engine *h, const gate_b200_dose_desc *d,

@@ -28,7 +28,7 @@ NVCC_FLAGS = [
 EXPORTS = [
     "gate_b200_abi_version", "gate_b200_create", "gate_b200_destroy", "gate_b200_release_cached_memory", "gate_b200_last_error",
     "gate_b200_set_stream", "gate_b200_set_tables", "gate_b200_set_world",
-    "gate_b200_set_image_volume", "gate_b200_add_source", "gate_b200_add_dose_actor",
+    "gate_b200_set_image_volume", "gate_b200_set_image_volume_hu", "gate_b200_add_source", "gate_b200_add_dose_actor",
     "gate_b200_add_tle_dose_actor", "gate_b200_add_phsp_actor", "gate_b200_begin_run", "gate_b200_run_source", "gate_b200_sync",
     "gate_b200_get_dose_grid", "gate_b200_dose_buffers", "gate_b200_set_dose_grid",
     "gate_b200_mean_uncertainty", "gate_b200_phsp_count", "gate_b200_get_phsp",
@@ -81,6 +81,8 @@ def load_library():
     L.gate_b200_set_tables.argtypes = [vp, C.POINTER(abi.Tables)]
     L.gate_b200_set_world.argtypes = [vp, C.POINTER(C.c_double), i32]
     L.gate_b200_set_image_volume.argtypes = [vp, vp, i32, C.POINTER(i32), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.gate_b200_set_image_volume_hu.argtypes = [vp, vp, i32, C.POINTER(i32), C.POINTER(C.c_double), C.POINTER(C.c_double), i32,
+                                                C.POINTER(C.c_double), C.POINTER(C.c_uint16), i32, vp]
     L.gate_b200_add_source.argtypes = [vp, C.POINTER(abi.Source), C.POINTER(i32)]
     L.gate_b200_add_dose_actor.argtypes = [vp, C.POINTER(abi.DoseDesc), C.POINTER(i32)]
     L.gate_b200_add_tle_dose_actor.argtypes = [vp, C.POINTER(abi.DoseDesc), C.POINTER(abi.TleDesc), C.POINTER(i32)]
@@ -172,6 +174,27 @@ class Engine:
             self.h, lab.ctypes.data_as(C.c_void_p), lab.dtype.itemsize, (C.c_int32 * 3)(nx, ny, nz),
             (C.c_double * 3)(*[float(x) for x in spacing]),
             (C.c_double * 12)(*np.asarray(world_to_volume12, float).reshape(-1))))
+
+    def set_image_volume_hu(self, hu_zyx, spacing, world_to_volume12, bins, bin_labels, label_bytes=1, want_labels=False):
+        """HU image -> label volume on the device (np.digitize rule of ImageVolume.create_label_image).
+        Returns the label array (z,y,x) when want_labels, else None."""
+        hu = np.ascontiguousarray(hu_zyx)
+        types = {np.dtype(np.int16): 0, np.dtype(np.float32): 1, np.dtype(np.float64): 2}
+        if hu.dtype not in types:
+            hu = hu.astype(np.float64)
+        nz, ny, nx = hu.shape
+        b = np.ascontiguousarray(bins, dtype=np.float64)
+        bl = np.ascontiguousarray(bin_labels, dtype=np.uint16)
+        if len(bl) != len(b) + 1:
+            raise GateB200Error("bin_labels must have len(bins) + 1 entries")
+        out = np.empty((nz, ny, nx), dtype=np.uint8 if label_bytes == 1 else np.uint16) if want_labels else None
+        self._check(self.L.gate_b200_set_image_volume_hu(
+            self.h, hu.ctypes.data_as(C.c_void_p), types[hu.dtype], (C.c_int32 * 3)(nx, ny, nz),
+            (C.c_double * 3)(*[float(x) for x in spacing]),
+            (C.c_double * 12)(*np.asarray(world_to_volume12, float).reshape(-1)), len(b),
+            b.ctypes.data_as(C.POINTER(C.c_double)), bl.ctypes.data_as(C.POINTER(C.c_uint16)), int(label_bytes),
+            out.ctypes.data_as(C.c_void_p) if out is not None else None))
+        return out
 
     def add_source(self, src_struct, keep=None):
         self._keep.append(keep)

@@ -162,6 +162,33 @@ __global__ void __launch_bounds__(256) label_scan_kernel(const LabelT *__restric
     if (s_present[i]) atomicOr(&present[i], s_present[i]);
 }
 
+// HU -> label on the device: label = bin_labels[np.digitize(hu, bins)] with sorted bins, i.e. the number
+// of bins <= hu (an upper bound search in double: exactly what numpy does after promoting the HU type;
+// reference geometry/volumes.py:1200-1243).  bins and labels are staged in shared memory.
+constexpr int kMaxHuBins = 4096;
+template <typename HuT, typename LabT>
+__global__ void __launch_bounds__(256) hu_to_label_kernel(const HuT *__restrict__ hu, size_t n, int n_bins,
+                                                          const double *__restrict__ bins, const uint16_t *__restrict__ bin_labels,
+                                                          LabT *__restrict__ out) {
+  extern __shared__ __align__(8) unsigned char hu_smem[];
+  double *s_bins = reinterpret_cast<double *>(hu_smem);
+  uint16_t *s_lab = reinterpret_cast<uint16_t *>(s_bins + n_bins);
+  for (int i = threadIdx.x; i < n_bins; i += blockDim.x) s_bins[i] = bins[i];
+  for (int i = threadIdx.x; i <= n_bins; i += blockDim.x) s_lab[i] = bin_labels[i];
+  __syncthreads();
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double x = (double)hu[i];
+    int lo = 0, hi = n_bins;            // first index with bins[idx] > x
+    if (x != x) lo = n_bins;            // numpy sorts NaN last
+    else
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_bins[mid] <= x) lo = mid + 1; else hi = mid;
+      }
+    out[i] = (LabT)s_lab[lo];
+  }
+}
+
 // component k of every voxel record <-> a dense array (the layout the ABI hands to the caller)
 __global__ void __launch_bounds__(256) grid_extract_kernel(const double *__restrict__ comp, size_t n, size_t stride,
                                                            double *__restrict__ dense) {
@@ -363,24 +390,14 @@ int gate_b200_set_world(gate_b200_engine *h, const double half_size[3], int32_t 
   return GATE_B200_OK;
 }
 
-int gate_b200_set_image_volume(gate_b200_engine *h, const void *labels, int32_t label_bytes,
-                               const int32_t size[3], const double spacing[3],
-                               const double world_to_volume[12]) {
-  if (!h || !labels || !size || !spacing || !world_to_volume) return GATE_B200_EINVAL;
-  if (!h->have_tables) return fail(h, GATE_B200_ESTATE, "set_image_volume before set_tables");
-  if (label_bytes != 1 && label_bytes != 2) return fail(h, GATE_B200_EINVAL, "label_bytes must be 1 or 2");
-  if (!h->dose.empty()) return fail(h, GATE_B200_ESTATE, "set_image_volume after add_dose_actor");
-  CU(cudaSetDevice(h->device));
+// Common tail of the two ways to hand over the image volume: `dl` is the device copy of the label volume.
+// Scans it for the materials present (-> majorant, same rule as the oracle's build_majorant) and for labels
+// without a material (the scan is inside the end-to-end path of every run, hence on the device), then
+// records the geometry.  `host_labels` (may be null) only serves the error message.
+static int finish_image_volume(gate_b200_engine *h, uint8_t *dl, const void *host_labels, int32_t label_bytes,
+                               const int32_t size[3], const double spacing[3], const double world_to_volume[12]) {
   Params &P = h->P;
   const size_t nv = (size_t)size[0] * size[1] * size[2];
-  if (nv == 0) return fail(h, GATE_B200_EINVAL, "empty image volume");
-  if (nv >= (1ull << 31)) return fail(h, GATE_B200_EINVAL, "image volume must have fewer than 2^31 voxels");
-  // the label volume goes to the device first (stream order; the caller's buffer may be pinned)
-  uint8_t *dl = nullptr;
-  if (int rc = dev_alloc(h, &dl, nv * label_bytes)) return rc;
-  CU(cudaMemcpyAsync(dl, labels, nv * label_bytes, cudaMemcpyHostToDevice, h->stream));
-  // materials present -> majorant (same rule as the oracle's build_majorant); the scan of the label
-  // volume runs on the device copy (it is inside the end-to-end path of every run)
   std::vector<char> present(P.nmat, 0);
   {
     const int nw = (P.nmat + 31) / 32;
@@ -402,8 +419,13 @@ int gate_b200_set_image_volume(gate_b200_engine *h, const void *labels, int32_t 
     CU(cudaStreamSynchronize(h->stream));
     if (bad != ~0ull) {
       const size_t i = (size_t)bad;
-      const int lab = label_bytes == 1 ? (int)static_cast<const uint8_t *>(labels)[i] : (int)static_cast<const uint16_t *>(labels)[i];
-      return fail(h, GATE_B200_EINVAL, "label %d at voxel %zu has no material", lab, i);
+      uint16_t v16 = 0;
+      if (host_labels) {
+        v16 = label_bytes == 1 ? (uint16_t)static_cast<const uint8_t *>(host_labels)[i] : static_cast<const uint16_t *>(host_labels)[i];
+      } else {
+        CU(cudaMemcpy(&v16, dl + i * (size_t)label_bytes, (size_t)label_bytes, cudaMemcpyDeviceToHost));   // little endian
+      }
+      return fail(h, GATE_B200_EINVAL, "label %d at voxel %zu has no material", (int)v16, i);
     }
     for (int m = 0; m < P.nmat; ++m) present[m] = (char)((words[m >> 5] >> (m & 31)) & 1u);
   }
@@ -431,6 +453,77 @@ int gate_b200_set_image_volume(gate_b200_engine *h, const void *labels, int32_t 
   h->label_bytes = label_bytes;
   h->label_total_bytes = nv * (size_t)label_bytes;
   return GATE_B200_OK;
+}
+
+static int check_volume_args(gate_b200_engine *h, int32_t label_bytes, const int32_t size[3], size_t *nv) {
+  if (!h->have_tables) return fail(h, GATE_B200_ESTATE, "set_image_volume before set_tables");
+  if (label_bytes != 1 && label_bytes != 2) return fail(h, GATE_B200_EINVAL, "label_bytes must be 1 or 2");
+  if (!h->dose.empty()) return fail(h, GATE_B200_ESTATE, "set_image_volume after add_dose_actor");
+  *nv = (size_t)size[0] * size[1] * size[2];
+  if (*nv == 0) return fail(h, GATE_B200_EINVAL, "empty image volume");
+  if (*nv >= (1ull << 31)) return fail(h, GATE_B200_EINVAL, "image volume must have fewer than 2^31 voxels");
+  return 0;
+}
+
+int gate_b200_set_image_volume(gate_b200_engine *h, const void *labels, int32_t label_bytes,
+                               const int32_t size[3], const double spacing[3],
+                               const double world_to_volume[12]) {
+  if (!h || !labels || !size || !spacing || !world_to_volume) return GATE_B200_EINVAL;
+  size_t nv = 0;
+  if (int rc = check_volume_args(h, label_bytes, size, &nv)) return rc;
+  CU(cudaSetDevice(h->device));
+  // the label volume goes to the device first (stream order; the caller's buffer may be pinned)
+  uint8_t *dl = nullptr;
+  if (int rc = dev_alloc(h, &dl, nv * label_bytes)) return rc;
+  CU(cudaMemcpyAsync(dl, labels, nv * label_bytes, cudaMemcpyHostToDevice, h->stream));
+  return finish_image_volume(h, dl, labels, label_bytes, size, spacing, world_to_volume);
+}
+
+int gate_b200_set_image_volume_hu(gate_b200_engine *h, const void *hu, int32_t hu_type, const int32_t size[3],
+                                  const double spacing[3], const double world_to_volume[12], int32_t n_bins,
+                                  const double *bins, const uint16_t *bin_labels, int32_t label_bytes,
+                                  void *labels_out) {
+  if (!h || !hu || !size || !spacing || !world_to_volume || !bins || !bin_labels) return GATE_B200_EINVAL;
+  if (hu_type < GATE_B200_HU_INT16 || hu_type > GATE_B200_HU_FLOAT64) return fail(h, GATE_B200_EINVAL, "bad hu_type %d", hu_type);
+  if (n_bins < 1 || n_bins > kMaxHuBins) return fail(h, GATE_B200_EINVAL, "n_bins must be 1..%d", kMaxHuBins);
+  for (int i = 1; i < n_bins; ++i)
+    if (!(bins[i] >= bins[i - 1])) return fail(h, GATE_B200_EINVAL, "bins must be sorted");
+  size_t nv = 0;
+  if (int rc = check_volume_args(h, label_bytes, size, &nv)) return rc;
+  for (int i = 0; i <= n_bins; ++i)
+    if (label_bytes == 1 && bin_labels[i] > 255) return fail(h, GATE_B200_EINVAL, "label %d does not fit one byte", (int)bin_labels[i]);
+  CU(cudaSetDevice(h->device));
+  const size_t hu_bytes = hu_type == GATE_B200_HU_INT16 ? 2 : (hu_type == GATE_B200_HU_FLOAT32 ? 4 : 8);
+  uint8_t *d_hu = nullptr, *dl = nullptr;
+  double *d_bins = nullptr;
+  uint16_t *d_bl = nullptr;
+  CU(cudaMallocAsync((void **)&d_hu, nv * hu_bytes, h->stream));          // temporary: freed below in stream order
+  CU(cudaMemcpyAsync(d_hu, hu, nv * hu_bytes, cudaMemcpyHostToDevice, h->stream));
+  if (int rc = dev_alloc(h, &d_bins, (size_t)n_bins)) return rc;
+  if (int rc = dev_alloc(h, &d_bl, (size_t)n_bins + 1)) return rc;
+  CU(cudaMemcpyAsync(d_bins, bins, n_bins * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(d_bl, bin_labels, ((size_t)n_bins + 1) * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+  if (int rc = dev_alloc(h, &dl, nv * label_bytes)) return rc;
+  const int blocks = (int)std::min<size_t>((size_t)h->sm_count * 8, (nv + 255) / 256);
+  const size_t smem = (size_t)n_bins * sizeof(double) + ((size_t)n_bins + 1) * sizeof(uint16_t);
+#define GB2_LAUNCH_HU(HuT, LabT)                                                                                   \
+  hu_to_label_kernel<HuT, LabT><<<blocks, 256, smem, h->stream>>>(reinterpret_cast<const HuT *>(d_hu), nv, n_bins, \
+                                                                  d_bins, d_bl, reinterpret_cast<LabT *>(dl))
+  if (label_bytes == 1) {
+    if (hu_type == GATE_B200_HU_INT16) GB2_LAUNCH_HU(int16_t, uint8_t);
+    else if (hu_type == GATE_B200_HU_FLOAT32) GB2_LAUNCH_HU(float, uint8_t);
+    else GB2_LAUNCH_HU(double, uint8_t);
+  } else {
+    if (hu_type == GATE_B200_HU_INT16) GB2_LAUNCH_HU(int16_t, uint16_t);
+    else if (hu_type == GATE_B200_HU_FLOAT32) GB2_LAUNCH_HU(float, uint16_t);
+    else GB2_LAUNCH_HU(double, uint16_t);
+  }
+#undef GB2_LAUNCH_HU
+  CU(cudaGetLastError());
+  CU(cudaFreeAsync(d_hu, h->stream));
+  if (labels_out) CU(cudaMemcpyAsync(labels_out, dl, nv * label_bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return finish_image_volume(h, dl, nullptr, label_bytes, size, spacing, world_to_volume);
 }
 
 int gate_b200_add_source(gate_b200_engine *h, const gate_b200_source *s, int32_t *source_id) {

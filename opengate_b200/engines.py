@@ -20,6 +20,7 @@ import time
 import numpy as np
 
 from . import abi, multigpu, physics
+from . import materials as gmat
 from .exception import fatal, warning
 from .setups import LowLevelSetup, dose_world_to_index
 from .units import g4_units
@@ -143,20 +144,35 @@ class GpuSimulationEngine:
         world = sim.world
 
         # label volume ------------------------------------------------------------------------
-        if phantom.volume_type == "ImageVolume":
+        hu = hu_bins = hu_bin_labels = None
+        if phantom.volume_type == "ImageVolume" and not phantom.dump_label_image:
+            # the HU image and the np.digitize table go to the engine, which makes the label volume on the
+            # device (ImageVolume.create_label_image, volumes.py:1200-1243); no host pass over the voxels
+            phantom.material_to_label_lut = phantom.create_material_to_label_lut()
+            phantom.load_input_image()
+            lut = dict(phantom.material_to_label_lut)
+            hu = phantom.itk_image.array
+            hu_bins, hu_bin_labels = gmat.label_bins(phantom.voxel_materials, lut)
+            labels16 = None
+            volume_shape = hu.shape
+            spacing = tuple(float(x) for x in phantom.itk_image.spacing)
+        elif phantom.volume_type == "ImageVolume":
             label_img = phantom.construct()
             lut = dict(phantom.material_to_label_lut)
             labels16 = label_img.array
+            volume_shape = labels16.shape
             spacing = tuple(float(x) for x in label_img.spacing)
         else:
             lut = {phantom.material: 0}
             labels16 = np.zeros((1, 1, 1), dtype=np.uint16)
+            volume_shape = labels16.shape
             spacing = tuple(float(x) for x in phantom.size)
         names = list(lut.keys())
         if world.material not in lut:
             names.append(world.material)
         world_label = names.index(world.material)
-        labels = labels16.astype(np.uint8) if len(names) <= 256 else labels16.astype(np.uint16)
+        label_bytes = 1 if len(names) <= 256 else 2
+        labels = None if labels16 is None else labels16.astype(np.uint8 if label_bytes == 1 else np.uint16)
         mats = [db.find_or_build_material(n) for n in names]
 
         # sources -------------------------------------------------------------------------------
@@ -174,7 +190,7 @@ class GpuSimulationEngine:
         tables = physics.build_photon_tables(
             mats, e_max_mev=e_max, e_cut_mev=float(pm.photon_energy_cut), n_energy=int(pm.table_energy_nodes),
             pair_mode=1 if pm.pair_production_mode == "annihilation" else 0)
-        half_phantom = 0.5 * np.asarray(labels16.shape[::-1]) * np.asarray(spacing)
+        half_phantom = 0.5 * np.asarray(volume_shape[::-1]) * np.asarray(spacing)
         pm.check_kerma_configuration(float(2 * np.max(half_phantom)))
 
         # placement -----------------------------------------------------------------------------
@@ -217,9 +233,10 @@ class GpuSimulationEngine:
                 fatal(f"Actor type {a.type_name} is not supported by the B200 GPU engine")
         self.setup = LowLevelSetup(
             name=f"{sim.name}", seed=int(sim.current_random_seed) & (2 ** 64 - 1), tables=tables,
-            world_half=world_half, world_material=world_label, labels=np.ascontiguousarray(labels), spacing=spacing,
+            world_half=world_half, world_material=world_label,
+            labels=None if labels is None else np.ascontiguousarray(labels), spacing=spacing,
             world_to_volume=w2v, sources=src_structs, dose=dose_desc, phsp=phsp_desc, n_primaries=int(n_total),
-            materials=mats)
+            materials=mats, hu=hu, hu_bins=hu_bins, hu_bin_labels=hu_bin_labels, label_bytes=label_bytes)
         # TLE dose actors come after the plain ones in the engine's actor id space
         for size, A, flags, hit, thr, emin, database in tle_desc:
             self.setup.add_tle_actor(size, A, flags, hit_type=hit, threshold=thr, energy_min=emin, database=database)

@@ -363,6 +363,15 @@ def create_label_array(hu_array, material, voxel_materials, lut=None):
     [lo, hi) intervals, values outside every interval (or in a gap) get label 0."""
     if lut is None:
         lut = create_material_to_label_lut(material, voxel_materials)
+    bins_sorted, labels_sorted = label_bins(voxel_materials, lut)
+    arr = np.array(labels_sorted, dtype=np.ushort)[np.digitize(hu_array, bins=bins_sorted)]
+    return arr, lut
+
+
+def label_bins(voxel_materials, lut):
+    """(sorted bin edges, label per np.digitize index) of the label rule above: one table of
+    len(bins) + 1 labels.  The GPU engine sends it with the HU image and does the digitize on the
+    device (gate_b200_set_image_volume_hu)."""
     rows = sorted(voxel_materials, key=lambda x: x[0])
     bins = [r[0] for r in rows]
     gaps = set(r[1] for r in rows).difference(bins)
@@ -371,5 +380,4 @@ def create_label_array(hu_array, material, voxel_materials, lut=None):
     order = sorted(zip(bins, labels), key=lambda p: p[0])
     bins_sorted = [b for b, _ in order]
     labels_sorted = [0] + [l for _, l in order]
-    arr = np.array(labels_sorted, dtype=np.ushort)[np.digitize(hu_array, bins=bins_sorted)]
-    return arr, lut
+    return bins_sorted, labels_sorted

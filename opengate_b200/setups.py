@@ -118,11 +118,28 @@ class LowLevelSetup:
     n_primaries: int = 0
     tle: list = field(default_factory=list)           # (DoseDesc, TleDesc, keepalive): TLE dose actors
     materials: list = field(default_factory=list)     # MaterialSpec per label (for the mu_en database)
+    # the volume as an HU image + the np.digitize table of ImageVolume.create_label_image (labels is then None
+    # until someone asks for label_array()): the CUDA engine makes the label volume on the device
+    hu: np.ndarray = None
+    hu_bins: list = None
+    hu_bin_labels: list = None
+    label_bytes: int = 1
+
+    def label_array(self):
+        """(z,y,x) label volume; made on the host from the HU image when it was not given."""
+        if self.labels is None:
+            lab = np.array(self.hu_bin_labels, dtype=np.ushort)[np.digitize(self.hu, bins=self.hu_bins)]
+            self.labels = np.ascontiguousarray(lab.astype(np.uint8 if self.label_bytes == 1 else np.uint16))
+        return self.labels
 
     def apply(self, eng):
         eng.set_tables(self.tables)
         eng.set_world(self.world_half, self.world_material)
-        eng.set_image_volume(self.labels, self.spacing, self.world_to_volume)
+        if self.hu is not None and self.labels is None and hasattr(eng, "set_image_volume_hu"):
+            eng.set_image_volume_hu(self.hu, self.spacing, self.world_to_volume, self.hu_bins, self.hu_bin_labels,
+                                    self.label_bytes)
+        else:
+            eng.set_image_volume(self.label_array(), self.spacing, self.world_to_volume)
         sids = [eng.add_source(s, keep) for s, keep in self.sources]
         dids = [eng.add_dose_actor(d) for d in self.dose]
         dids += [eng.add_tle_dose_actor(d, t, keep) for d, t, keep in self.tle]

@@ -498,3 +498,70 @@ def test_voxel_record_buffers_match_the_dense_grids(cuda_required, flags):
         if w not in (abi.GRID_EDEP, abi.GRID_COUNTS):
             assert np.array_equal(eng.dose_grid(de[0], w), rec[..., offset[w]])
     eng.close()
+
+
+@pytest.mark.parametrize("hu_dtype,label_bytes", [(np.int16, 1), (np.float32, 1), (np.float64, 2), (np.int16, 2)])
+def test_hu_to_label_on_the_device_is_integer_exact(cuda_required, hu_dtype, label_bytes):
+    """gate_b200_set_image_volume_hu: the label volume made on the device equals np.digitize over the interval
+    table of ImageVolume.create_label_image (volumes.py:1200-1243) voxel for voxel: Schneider intervals, a gap
+    (label 0), unsorted input rows, values on the bin edges, below the first and above the last bin."""
+    from opengate_b200 import materials as gmat
+    from opengate_b200.core import Engine
+    S = SMALL["c3"](2000)
+    nmat = len(S.tables.names)
+    rng = np.random.default_rng(17)
+    # intervals [lo, hi) -> label; a gap between 300 and 350; rows deliberately out of order
+    edges = np.array([-1050.0, -950.0, -700.5, -100.0, 0.0, 15.25, 120.0, 300.0])
+    rows = [[edges[i], edges[i + 1], f"m{i}"] for i in range(len(edges) - 1)] + [[350.0, 3000.0, "metal"]]
+    rows = [rows[i] for i in rng.permutation(len(rows))]
+    lut = {"default": 0}
+    for i, r in enumerate(sorted(rows, key=lambda x: x[0])):
+        lut[r[2]] = 1 + (i * 7) % (nmat - 1)                     # any labels below n_materials
+    bins, bin_labels = gmat.label_bins(rows, lut)
+    shape = (37, 41, 53)                                          # odd sizes: the scan's vector tail
+    hu = rng.uniform(-1200, 3500, shape)
+    hu.flat[: len(bins)] = bins                                   # exactly on the edges
+    hu.flat[100:110] = [-5000, 5000, 299.999, 300.0, 349.999, 350.0, 0.0, -0.0, 15.25, 15.2499]
+    hu = np.round(hu).astype(hu_dtype) if hu_dtype == np.int16 else hu.astype(hu_dtype)
+    if hu_dtype != np.int16:
+        hu.flat[200] = np.nan
+    want = np.array(bin_labels, dtype=np.uint16)[np.digitize(hu, bins=bins)]
+    eng = Engine(0, S.seed)
+    eng.set_tables(S.tables)
+    eng.set_world(S.world_half, S.world_material)
+    got = eng.set_image_volume_hu(hu, (2.0, 2.0, 2.5), S.world_to_volume, bins, bin_labels, label_bytes, want_labels=True)
+    assert got.dtype == (np.uint8 if label_bytes == 1 else np.uint16)
+    assert np.array_equal(got.astype(np.uint16), want)
+    # and the engine runs on it exactly as on an uploaded label volume
+    src, keep = S.sources[0]
+    sid = eng.add_source(src, keep)
+    eng.begin_run()
+    eng.run_source(sid, 0, 2000)
+    eng.sync()
+    a = eng.stats()
+    eng.close()
+    eng2 = Engine(0, S.seed)
+    eng2.set_tables(S.tables)
+    eng2.set_world(S.world_half, S.world_material)
+    eng2.set_image_volume(want.astype(got.dtype), (2.0, 2.0, 2.5), S.world_to_volume)
+    sid = eng2.add_source(src, keep)
+    eng2.begin_run()
+    eng2.run_source(sid, 0, 2000)
+    eng2.sync()
+    b = eng2.stats()
+    eng2.close()
+    for k in INT_KEYS:
+        assert a[k] == b[k], k
+
+
+def test_hu_path_rejects_labels_without_material(cuda_required):
+    from opengate_b200.core import Engine, GateB200Error
+    S = SMALL["c1"](10)
+    eng = Engine(0, S.seed)
+    eng.set_tables(S.tables)
+    eng.set_world(S.world_half, S.world_material)
+    hu = np.zeros((4, 4, 4), np.int16)
+    hu[1, 2, 3] = 500
+    with pytest.raises(GateB200Error, match="label 77 at voxel 27 has no material"):
+        eng.set_image_volume_hu(hu, (1.0, 1.0, 1.0), S.world_to_volume, [100.0], [0, 77], 1)
+    eng.close()

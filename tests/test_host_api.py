@@ -159,8 +159,11 @@ def test_label_volume_is_integer_exact_and_placed_like_the_reference(tmp_path):
     want = np.zeros_like(hu, dtype=np.uint16)
     for lo, hi, name in vm:
         want[(hu >= lo) & (hu < hi)] = lut[name]
-    assert np.array_equal(S.labels.astype(np.uint16), want)
-    assert S.labels.dtype == np.uint8 and len(S.tables.names) == 75
+    # the engine hands the HU image + the digitize table to the device; the host restatement of the same rule
+    assert S.labels is None and S.hu is not None and S.label_bytes == 1
+    lab = S.label_array()
+    assert np.array_equal(lab.astype(np.uint16), want)
+    assert lab.dtype == np.uint8 and len(S.tables.names) == 75
     # the input image origin is NOT used for placement: the box is centred on `translation`
     assert np.allclose(S.world_to_volume[:, 3], [-5, 10, 0]) and np.allclose(S.world_to_volume[:, :3], np.eye(3))
     # output_coordinate_system = attached_to_image uses the image's own origin

@@ -258,14 +258,18 @@ class GpuSimulationEngine:
             self.engines = [self._backend(0, self.setup.seed)]
             return
         from .core import Engine
-        try:
-            import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized():
-                self.dist = dist
-                self.rank, self.world = dist.get_rank(), dist.get_world_size()
-                _, _, self.local_rank = multigpu.world_info()
-        except ImportError:
-            pass
+        # torch.distributed only matters when the script runs under torchrun and has initialised a process
+        # group: do not pay the import of torch (4 s) in a plain single-process run
+        import sys
+        if "torch" in sys.modules:
+            try:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized():
+                    self.dist = dist
+                    self.rank, self.world = dist.get_rank(), dist.get_world_size()
+                    _, _, self.local_rank = multigpu.world_info()
+            except ImportError:
+                pass
         if self.dist is not None:
             if sim.number_of_gpus not in (None, self.world):
                 warning(f"number_of_gpus={sim.number_of_gpus} ignored: running under torchrun with {self.world} ranks")
@@ -377,8 +381,8 @@ class GpuSimulationEngine:
         for w in which_list:
             acc = None
             for e, ids in zip(self.engines, self.ids):
-                g = e.dose_grid(ids[1][actor_index], w)
-                acc = g.copy() if acc is None else acc + g
+                g = e.dose_grid(ids[1][actor_index], w)      # a fresh host array per call
+                acc = g if acc is None else acc + g
             out[w] = acc
         return out
 

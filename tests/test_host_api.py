@@ -349,3 +349,59 @@ def test_tle_dose_actor_user_info(tmp_path):
     t3.score_in = "G4_WATER"
     with pytest.raises(Exception, match="TLEDoseActor cannot score in G4_WATER"):
         sim3.run(_backend=OracleBackend)
+
+
+def test_user_facing_api_surface_checklist():
+    """every attribute of the reference's user interface on this path exists on the mirror."""
+    sim = gate.Simulation()
+    missing = []
+
+    def need(obj, prefix, names, key=False):
+        for n in names:
+            ok = (n in obj) if key else True
+            if not key:
+                try:
+                    getattr(obj, n)
+                except Exception:
+                    ok = False
+            if not ok:
+                missing.append(f"{prefix}.{n}")
+
+    need(sim, "sim", ["output_dir", "random_seed", "number_of_threads", "run_timing_intervals", "progress_bar", "run"])
+    need(sim.world, "world", ["size", "material"])
+    need(sim.volume_manager, "volume_manager", ["add_material_database"])
+    need(sim.volume_manager.material_database, "material_database", ["add_material_weights"])
+    need(sim.physics_manager, "physics_manager", ["physics_list_name", "global_production_cuts", "set_production_cut",
+                                                  "apply_cuts", "enable_decay"])
+    need(sim.physics_manager.global_production_cuts, "global_production_cuts",
+         ["all", "gamma", "electron", "positron", "proton"], key=True)
+    v = sim.add_volume("Image", "ct")
+    need(v, "image", ["image", "voxel_materials", "material", "mother", "translation", "rotation", "dump_label_image",
+                      "set_materials_from_voxelisation"])
+    for kind in ("GenericSource", "VoxelSource"):
+        s = sim.add_source(kind, kind)
+        need(s, kind, ["particle", "number_of_primaries", "activity", "half_life", "attached_to", "weight"])
+        need(s.position, kind + ".position", ["type", "radius", "size", "translation", "rotation", "sigma_x", "sigma_y"], key=True)
+        need(s.direction, kind + ".direction", ["type", "momentum", "focus_point", "theta", "phi", "sigma"], key=True)
+        need(s.energy, kind + ".energy", ["type", "mono", "sigma_gauss", "spectrum_weights", "spectrum_energies",
+                                          "spectrum_energy_bin_edges", "spectrum_histogram_interpolation"], key=True)
+    need(sim.source_manager.sources["VoxelSource"], "VoxelSource", ["image"])
+    ps = sim.add_source("PhaseSpaceSource", "ps")
+    need(ps, "PhaseSpaceSource", ["phsp_file", "entry_start", "particle", "global_flag", "isotropic_direction", "translate_position",
+                                  "rotate_direction", "batch_size", "position_key", "direction_key", "energy_key", "weight_key",
+                                  "PDGCode_key", "generate_until_next_primary", "cycle_count"])
+    for kind in ("DoseActor", "TLEDoseActor"):
+        d = sim.add_actor(kind, kind)
+        need(d, kind, ["attached_to", "size", "spacing", "translation", "rotation", "hit_type", "output_coordinate_system",
+                       "output_filename", "score_in", "uncertainty_goal", "edep", "edep_squared", "edep_uncertainty", "dose",
+                       "dose_squared", "dose_uncertainty", "density", "counts"])
+        need(d.edep, kind + ".edep", ["active", "write_to_disk", "output_filename", "keep_data_per_run", "get_output_path",
+                                      "get_data", "image"])
+    need(sim.actor_manager.actors["TLEDoseActor"], "TLEDoseActor", ["energy_min", "database"])
+    p = sim.add_actor("PhaseSpaceActor", "p")
+    need(p, "PhaseSpaceActor", ["attached_to", "attributes", "steps_to_store", "store_absorbed_event", "output_filename",
+                                "get_output_path", "total_number_of_entries", "number_of_absorbed_events"])
+    st = sim.add_actor("SimulationStatisticsActor", "st")
+    need(st, "SimulationStatisticsActor", ["counts", "pps", "track_types_flag"])
+    assert hasattr(gate.geometry.materials, "HounsfieldUnit_to_material")
+    assert missing == []

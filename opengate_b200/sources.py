@@ -366,33 +366,34 @@ class PhaseSpaceSource(SourceBase):
     (sequential batches, restart from the beginning at the end: phspsources.py:119-146)."""
 
     user_info_defaults = {
-        "phsp_file": (None, {"doc": "Filename of the phase-space file (root). This is required", "is_input_file": True}),
-        "entry_start": (None, {"doc": "Starting particle in the phase-space"}),
-        "particle": ("", {"doc": "Particle name; empty: read the PDGCode column"}),
-        "global_flag": (False, {"doc": "If true, the positions of the generated particles in the phase-space are in the "
-                                       "world coordinate system. If false, they are relative to the volume this source is attached to"}),
-        "isotropic_direction": (False, {"doc": "Position, energy and weight from the phase space, isotropic momentum"}),
-        "translate_position": (False, {"doc": "Add position.translation to the positions"}),
-        "rotate_direction": (False, {"doc": "Rotate the directions by position.rotation"}),
-        "batch_size": (10000, {"doc": "Batch size to read the phsp (the GPU engine uploads the whole file once)"}),
-        "position_key": ("PrePositionLocal", {"doc": "Key of the position; sets position_key_x/y/z by adding _X _Y _Z"}),
-        "position_key_x": (None, {"doc": "Key in the phsp that contain the position X of the particle"}),
-        "position_key_y": (None, {"doc": "Key in the phsp that contain the position Y of the particle"}),
-        "position_key_z": (None, {"doc": "Key in the phsp that contain the position Z of the particle"}),
+        "phsp_file": (None, {"doc": "Phase-space file to replay (.root through uproot, or a .npz column archive). Required.",
+                             "is_input_file": True}),
+        "entry_start": (None, {"doc": "Index of the first entry to replay (taken modulo the number of entries)"}),
+        "particle": ("", {"doc": "'gamma', or empty to check the PDGCode column (the GPU engine replays gammas only)"}),
+        "global_flag": (False, {"doc": "True: positions / directions in the file are world coordinates; "
+                                       "False: coordinates of the volume the source is attached to"}),
+        "isotropic_direction": (False, {"doc": "Take position, energy and weight from the file, draw the direction isotropically"}),
+        "translate_position": (False, {"doc": "Shift every position by position.translation"}),
+        "rotate_direction": (False, {"doc": "Turn every direction by position.rotation"}),
+        "batch_size": (10000, {"doc": "Kept for compatibility: the GPU engine uploads the whole file once"}),
+        "position_key": ("PrePositionLocal", {"doc": "Column prefix of the position (_X, _Y, _Z are appended)"}),
+        "position_key_x": (None, {"doc": "Column of the x position (default: position_key + '_X')"}),
+        "position_key_y": (None, {"doc": "Column of the y position"}),
+        "position_key_z": (None, {"doc": "Column of the z position"}),
         "position": (Box({"translation": [0, 0, 0], "rotation": np.eye(3)}),
-                     {"doc": "Default position+rotation if it is not read in the phsp"}),
-        "direction_key": ("PreDirectionLocal", {"doc": "Key of the direction; sets direction_key_x/y/z by adding _X _Y _Z"}),
-        "direction_key_x": (None, {"doc": "Key in the phsp that contain the direction X of the particle"}),
-        "direction_key_y": (None, {"doc": "Key in the phsp that contain the direction Y of the particle"}),
-        "direction_key_z": (None, {"doc": "Key in the phsp that contain the direction Z of the particle"}),
-        "energy_key": ("KineticEnergy", {"doc": "Key in the phsp that contain the energy of the particle"}),
-        "weight_key": ("Weight", {"doc": "Key in the phsp that contain the weight of the particle"}),
-        "PDGCode_key": ("PDGCode", {"doc": "Key in the phsp that contains the PDGCode of the particle"}),
-        "generate_until_next_primary": (False, {"doc": "not supported on the GPU engine"}),
-        "primary_lower_energy_threshold": (0, {"doc": "not supported on the GPU engine"}),
-        "primary_PDGCode": (0, {"doc": "not supported on the GPU engine"}),
-        "verbose": (False, {"doc": "print the particles"}),
-        "verbose_batch": (False, {"doc": "print the batches"}),
+                     {"doc": "Translation / rotation used by translate_position and rotate_direction"}),
+        "direction_key": ("PreDirectionLocal", {"doc": "Column prefix of the direction (_X, _Y, _Z are appended)"}),
+        "direction_key_x": (None, {"doc": "Column of the x direction (default: direction_key + '_X')"}),
+        "direction_key_y": (None, {"doc": "Column of the y direction"}),
+        "direction_key_z": (None, {"doc": "Column of the z direction"}),
+        "energy_key": ("KineticEnergy", {"doc": "Column of the kinetic energy (MeV)"}),
+        "weight_key": ("Weight", {"doc": "Column of the statistical weight (all ones when absent)"}),
+        "PDGCode_key": ("PDGCode", {"doc": "Column of the PDG code, read when 'particle' is empty"}),
+        "generate_until_next_primary": (False, {"doc": "Several particles per event: not supported on the GPU engine"}),
+        "primary_lower_energy_threshold": (0, {"doc": "Only with generate_until_next_primary"}),
+        "primary_PDGCode": (0, {"doc": "Only with generate_until_next_primary"}),
+        "verbose": (False, {"doc": "Accepted for compatibility"}),
+        "verbose_batch": (False, {"doc": "Accepted for compatibility"}),
     }
 
     def __init__(self, *a, **kw):

@@ -261,3 +261,47 @@ def test_gpu_phase_space_source_weights_reach_phase_space_rows_and_tle(cuda_requ
     compare_all(eng, orc, T, ids)
     assert eng.stats()["tle_steps"] > 0
     eng.close()
+
+
+@pytest.mark.gpu
+def test_gpu_script_level_phase_space_chain_matches_oracle_backend(cuda_required, tmp_path):
+    """Script level, both directions of the wire format: a PhaseSpaceActor file written by a GPU run is
+    replayed by a PhaseSpaceSource on the GPU and on the oracle back end: identical dose grids."""
+    from scipy.spatial.transform import Rotation
+    from oracle_backend import OracleBackend
+    mm, keV = gate.g4_units.mm, gate.g4_units.keV
+    sim, box, dose = _plane_sim(tmp_path / "a")
+    src = sim.add_source("GenericSource", "beam")
+    src.energy.mono = 150 * keV
+    src.position.type = "disc"
+    src.position.radius = 20 * mm
+    src.position.translation = [0, 0, 300 * mm]
+    src.direction.type = "iso"
+    src.direction.theta = [0, 10 * gate.g4_units.deg]          # the iso flux of G4 points towards -z
+    src.number_of_primaries = 20000
+    plane = sim.add_volume("Box", "plane")
+    plane.size = [400 * mm, 400 * mm, 2 * mm]
+    plane.translation = [10 * mm, -5 * mm, 120 * mm]
+    plane.rotation = Rotation.from_euler("y", 12, degrees=True).as_matrix()
+    ph = sim.add_actor("PhaseSpaceActor", "phsp")
+    ph.attached_to = plane
+    ph.attributes = ["KineticEnergy", "PrePositionLocal", "PreDirectionLocal", "Weight", "PDGCode"]
+    ph.output_filename = "plane.npz"
+    sim.run()                                                    # CUDA engine
+    assert ph.total_number_of_entries > 1000
+    out = []
+    for backend, sub in ((None, "gpu"), (OracleBackend, "cpu")):
+        sim2, box2, dose2 = _plane_sim(tmp_path / sub)
+        p2 = sim2.add_volume("Box", "plane")
+        p2.size, p2.translation, p2.rotation = plane.size, plane.translation, plane.rotation
+        s2 = sim2.add_source("PhaseSpaceSource", "replay")
+        s2.attached_to = "plane"
+        s2.phsp_file = str(ph.get_output_path())
+        s2.number_of_primaries = 30000                           # wraps around the file
+        dose2.edep_uncertainty.active = True
+        sim2.run(_backend=backend)
+        out.append((dose2.edep.image.array.copy(), dose2.edep_squared.image.array.copy()))
+    (ge, gs), (ce, cs) = out
+    assert ge.sum() > 0
+    np.testing.assert_allclose(ge, ce, rtol=1e-9, atol=0)
+    np.testing.assert_allclose(gs, cs, rtol=1e-9, atol=0)

@@ -49,6 +49,16 @@ def build_setup(name, histories):
         S.add_tle_actor(tuple(d0.size), A, flags, database="EPDL")
         S.name = S.name.replace("DoseActor dose+edep2", "TLEDoseActor dose+edep" + ("+edep2" if name == "c3tle" else ""))
         return S
+    if name == "c3_hit_random":
+        # config 3 with the reference's DEFAULT hit_type ("random": a point between the pre- and post-step
+        # points of the Geant4 step).  For a dose grid equal to the image grid the voxel is the same as with
+        # "post" (a Geant4 step never leaves its voxel); the bench uses "post", this variant measures the cost
+        # of emulating the default.
+        from opengate_b200 import abi
+        S = setups.make_c3(n_primaries=histories)
+        S.dose[0].hit_type = abi.HIT_RANDOM
+        S.name += " hit_type=random"
+        return S
     if name == "c3small":  # CPU-container debugging only
         return setups.make_c3(nx=128, ny=128, nz=75, spacing=(3.9, 3.9, 4.0), n_primaries=histories)
     raise SystemExit(f"unknown config {name}")

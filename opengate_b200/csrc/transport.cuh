@@ -54,7 +54,7 @@ constexpr int kThreads = GB2_THREADS;
 // the kernel with the track-length-estimator phase runs with fewer threads and more registers each
 // (the voxel march keeps a long walk state live; at 72 registers it spills 700 bytes)
 constexpr int kTleThreads = GB2_TLE_THREADS;
-template <bool kTle> constexpr int threads_of() { return kTle ? kTleThreads : kThreads; }
+template <bool kIsTle> constexpr int threads_of() { return kIsTle ? kTleThreads : kThreads; }
 constexpr int kSlots = GB2_SLOTS;          // photon slots per CTA (< 65535: queue cells are 16 bit)
 constexpr int kWoodcockK = 4;              // tentative collisions per Woodcock call (2 Philox blocks)
 #ifndef GB2_VWIDTH
@@ -306,7 +306,9 @@ __device__ __forceinline__ void st_dep(DepEntry *p, const DepEntry &e) {
 
 // statistical weight of the history in a slot: per entry for a phase-space source (written by
 // generate_primary), the source's constant otherwise
+template <int kMode>
 __device__ __forceinline__ float hist_weight(const Params &P, int gslot) {
+  if (kMode == 2) return P.src.weight;
   return P.src.ph_b ? __ldcg(P.slot_w + gslot) : P.src.weight;
 }
 
@@ -499,18 +501,19 @@ struct DepStat { unsigned dep, over, flush, tle_ent, tle_over; double edep; };
 // deposit e (already weighted) at the photon position; in_vol selects whether dose actors see it.
 // e_tle: flight energy of the gamma whose secondaries deposit here (a TLE actor ignores them while that
 // gamma scores by track length, GateTLEDoseActor.cpp:236-243); kBig for a gamma absorbed below the cut.
-template <bool kTle>
+template <int kMode>
 __device__ __forceinline__ void deposit(const Params &P, Ph &g, DepEntry *buf, DepStat &ds, float e,
                                      int m, bool in_vol, float e_tle, int gslot) {
   ds.edep += (double)e;
   ds.dep++;
   if (!in_vol) return;
   int nbuf = (int)((g.flags & F_NBUF) >> F_NBUF_SHIFT);
-  for (int a = 0; a < P.ndose; ++a) {
-    const DDose &D = P.dose[a];
-    if (kTle && D.tle && e_tle <= D.tle_thr) continue;
+  const int ndose = kMode == 2 ? 1 : P.ndose;
+  for (int a = 0; a < ndose; ++a) {
+    const DDose &D = P.dose[kMode == 2 ? 0 : a];
+    if ((kMode == 1) && D.tle && e_tle <= D.tle_thr) continue;
     float pos[3] = {g.p[0], g.p[1], g.p[2]};
-    if (D.hit_type != GATE_B200_HIT_POST) {
+    if (kMode != 2 && D.hit_type != GATE_B200_HIT_POST) {
       // pre/random/middle between the Geant4 pre and post step points; the Geant4 step starts at
       // the voxel entry or at the previous interaction (GateDoseActor.cpp:144-178)
       const int vi[3] = {(int)((g.p[0] + P.half[0]) * P.inv_sp[0]), (int)((g.p[1] + P.half[1]) * P.inv_sp[1]),
@@ -547,7 +550,7 @@ __device__ __forceinline__ void deposit(const Params &P, Ph &g, DepEntry *buf, D
     int v = (int)fx + D.size[0] * ((int)fy + D.size[1] * (int)fz);
     int key = (int)(((unsigned)a << 28) | (unsigned)v);
     float dd = e / __ldg(P.dens + m);
-    if (kTle && D.tle && (D.flags & (GATE_B200_SCORE_EDEP_SQ | GATE_B200_SCORE_DOSE_SQ))) {
+    if ((kMode == 1) && D.tle && (D.flags & (GATE_B200_SCORE_EDEP_SQ | GATE_B200_SCORE_DOSE_SQ))) {
       unsigned nl = __ldcg(&P.tle_state[gslot].w);
       const unsigned before = nl;
       tle_table_add(P, gslot, nl, key, e, dd, 1, ds.tle_ent, ds.tle_over);
@@ -846,6 +849,7 @@ __device__ __forceinline__ void generate_primary(const Params &P, Ph &g, int gsl
 
 // ------------------------------------------------------------------------------ phase space
 
+template <int kMode>
 __device__ __forceinline__ void phsp_store(const Params &P, Ph &g, unsigned long long hist, int k, int flag, int gslot) {
   const DPhsp &Q = P.phsp[k];
   g.flags |= F_STORED;
@@ -857,7 +861,7 @@ __device__ __forceinline__ void phsp_store(const Params &P, Ph &g, unsigned long
   Q.ke[idx] = g.E;
 #pragma unroll
   for (int a = 0; a < 3; ++a) { Q.pos[3 * idx + a] = g.p[a]; Q.dir[3 * idx + a] = g.d[a]; }
-  Q.w[idx] = hist_weight(P, gslot);
+  Q.w[idx] = hist_weight<kMode>(P, gslot);
   Q.t[idx] = g.path / kCmmPerNs;
   Q.ev[idx] = (long long)hist;
   Q.fl[idx] = flag;
@@ -881,6 +885,7 @@ __device__ __forceinline__ void to_world(const Params &P, Ph &g) {
 }
 
 // place a photon given in the world frame into its region; returns the queue of its next phase
+template <int kMode>
 __device__ __forceinline__ int locate(const Params &P, Ph &g) {
   int st = Q_W;
   if (P.has_vol) {
@@ -889,7 +894,7 @@ __device__ __forceinline__ int locate(const Params &P, Ph &g) {
     if (inside_box(pl, P.half)) { to_volume(P, g); st = Q_V; }
   }
   g.flags &= ~F_INSIDE;
-  for (int k = 0; k < P.nphsp; ++k) {
+  for (int k = 0; k < (kMode == 2 ? 0 : P.nphsp); ++k) {
     float pb[3];
     aff_apply(P.phsp[k].w2b, g.p, pb);
     if (st == Q_W && inside_box(pb, P.phsp[k].half)) g.flags |= (1u << k);
@@ -901,6 +906,7 @@ __device__ __forceinline__ int locate(const Params &P, Ph &g) {
 
 // Q_W: one flight segment of a photon travelling in the world material (outside the image volume);
 // a photon that has just left the volume is first taken to its exit point and to the world frame.
+template <int kMode>
 __device__ __forceinline__ int phase_world(const Params &P, Smem &S, int slot, int gslot) {
   Ph g;
   load_ph(P, S, slot, g);
@@ -937,7 +943,7 @@ __device__ __forceinline__ int phase_world(const Params &P, Smem &S, int slot, i
       rot_apply(P.w2v.m, g.d, dl);
       if (ray_box_ax(pl, dl, P.half, ti, to, ai, ao) && ti < t_best) { t_best = ti; ev = 2; ax_in = ai; }
     }
-    for (int k = 0; k < P.nphsp; ++k) {
+    for (int k = 0; k < (kMode == 2 ? 0 : P.nphsp); ++k) {
       float pb[3], db[3], ti, to;
       aff_apply(P.phsp[k].w2b, g.p, pb);
       rot_apply(P.phsp[k].w2b.m, g.d, db);
@@ -975,10 +981,10 @@ __device__ __forceinline__ int phase_world(const Params &P, Smem &S, int slot, i
         n_steps++;
         if (((ev - 3) & 1) == 0) {
           g.flags |= (1u << k);
-          if (P.phsp[k].steps & GATE_B200_PHSP_ENTERING) phsp_store(P, g, hist, k, GATE_B200_PHSP_ENTERING, gslot);
+          if (P.phsp[k].steps & GATE_B200_PHSP_ENTERING) phsp_store<kMode>(P, g, hist, k, GATE_B200_PHSP_ENTERING, gslot);
         } else {
           g.flags &= ~(1u << k);
-          if (P.phsp[k].steps & GATE_B200_PHSP_EXITING) phsp_store(P, g, hist, k, GATE_B200_PHSP_EXITING, gslot);
+          if (P.phsp[k].steps & GATE_B200_PHSP_EXITING) phsp_store<kMode>(P, g, hist, k, GATE_B200_PHSP_EXITING, gslot);
         }
         next = Q_W;
       }
@@ -1060,7 +1066,7 @@ __device__ __forceinline__ void volume_gather_mu(const Params &P, VCall &c) {
   }
 }
 
-template <bool kTle>
+template <int kMode>
 __device__ __forceinline__ int volume_decide(const Params &P, Smem &S, int slot, int gslot, const VCall &c, unsigned &c_tent) {
   if (c.blk > kMaxBlocks) return Q_E;
   S.blk[slot] = c.blk + 2u;
@@ -1099,7 +1105,7 @@ __device__ __forceinline__ int volume_decide(const Params &P, Smem &S, int slot,
     next = route_interaction(P, flags, mat, c.ie, c.fe, vsel);
     S.fm[slot] = flags | ((unsigned)mat << F_MAT_SHIFT);
   }
-  if (kTle && next != Q_V && S.E[slot] <= P.tle_thr_max) {
+  if ((kMode == 1) && next != Q_V && S.E[slot] <= P.tle_thr_max) {
     // the flight has ended (interaction or exit): score its voxel chords first, then carry on
     S.fm[slot] |= (unsigned)(next - 1) << F_NEXT_SHIFT;
     __stcg(&P.tle_state[gslot].x, __float_as_uint(-1.0f));
@@ -1111,7 +1117,7 @@ __device__ __forceinline__ int volume_decide(const Params &P, Smem &S, int slot,
 // Q_C: one Compton trial (Klein-Nishina composition-rejection x scattering function).  A rejected
 // trial simply stays in the queue: trials are independent, each call owns two fresh Philox blocks
 // (trial, final state), so the lanes of a warp never wait for each other's rejection loops.
-template <bool kTle>
+template <int kMode>
 __device__ __forceinline__ int phase_compton(const Params &P, Smem &S, int slot, int gslot, double &c_edep) {
   const unsigned b0 = S.blk[slot];
   S.blk[slot] = b0 + 2u;
@@ -1162,13 +1168,13 @@ __device__ __forceinline__ int phase_compton(const Params &P, Smem &S, int slot,
     float sphi, cphi;
     d_sincos2pi(u32_to_uniform(r[4]), sphi, cphi);
     const float E1 = eps * E;
-    const float wgt = hist_weight(P, gslot);
-    deposit<kTle>(P, g, buf, ds, (E - E1) * wgt, m, in_vol, E, gslot);
+    const float wgt = hist_weight<kMode>(P, gslot);
+    deposit<kMode>(P, g, buf, ds, (E - E1) * wgt, m, in_vol, E, gslot);
     rotate_dir(g.d, cost, sint, sphi, cphi);
     g.E = E1;
     g.seg = 0.0f;
-    if (E1 < P.e_cut || (kTle && in_vol && E1 <= P.tle_emin)) {
-      deposit<kTle>(P, g, buf, ds, E1 * wgt, m, in_vol, kBig, gslot);
+    if (E1 < P.e_cut || ((kMode == 1) && in_vol && E1 <= P.tle_emin)) {
+      deposit<kMode>(P, g, buf, ds, E1 * wgt, m, in_vol, kBig, gslot);
       next = Q_E;
     } else {
       set_energy(P, S, slot, g);
@@ -1184,13 +1190,13 @@ __device__ __forceinline__ int phase_compton(const Params &P, Smem &S, int slot,
     stat_bump(S, S_DEP, t >> 8);
   }
   stat_overflow(S, ds.over, ds.flush);
-  if (kTle) stat_tle_overflow(S, ds.tle_over, ds.tle_ent);
+  if ((kMode == 1)) stat_tle_overflow(S, ds.tle_over, ds.tle_ent);
   return next;
 }
 
 // Q_R: the rare interactions.  Rayleigh: q2 from the cumulative squared form factor, (1+cos^2)/2
 // test.  Conversion with pair_mode 1: deposit E - 2 mc2, emit two back-to-back 511 keV photons.
-template <bool kTle>
+template <int kMode>
 __device__ __forceinline__ int phase_rare(const Params &P, Smem &S, int slot, int gslot, double &c_edep) {
   Ph g;
   load_ph(P, S, slot, g);
@@ -1243,7 +1249,7 @@ __device__ __forceinline__ int phase_rare(const Params &P, Smem &S, int slot, in
     g.seg = 0.0f;
   } else {
     n_conv = 1;
-    deposit<kTle>(P, g, P.depbuf + (size_t)gslot * kDepBuf, ds, (g.E - 2.0f * kMc2) * hist_weight(P, gslot), m, in_vol, g.E, gslot);
+    deposit<kMode>(P, g, P.depbuf + (size_t)gslot * kDepBuf, ds, (g.E - 2.0f * kMc2) * hist_weight<kMode>(P, gslot), m, in_vol, g.E, gslot);
     float cost = 2.0f * rng_uniform(g.rng) - 1.0f;
     float sint = sqrtf(1.0f - cost * cost);
     float sphi, cphi;
@@ -1269,7 +1275,7 @@ __device__ __forceinline__ int phase_rare(const Params &P, Smem &S, int slot, in
     stat_bump(S, S_DEP, t >> 16);
   }
   stat_overflow(S, ds.over, ds.flush);
-  if (kTle) stat_tle_overflow(S, ds.tle_over, ds.tle_ent);
+  if ((kMode == 1)) stat_tle_overflow(S, ds.tle_over, ds.tle_ent);
   return in_vol ? Q_V : Q_W;
 }
 
@@ -1277,7 +1283,7 @@ __device__ __forceinline__ int phase_rare(const Params &P, Smem &S, int slot, in
 // the kerma configuration), below the energy cut, or out of the world.  Either the history still
 // owes its second annihilation photon, or it is closed (coalesced deposits -> grids) and the slot
 // claims the next history.
-template <bool kTle>
+template <int kMode>
 __device__ __forceinline__ int phase_end(const Params &P, Smem &S, int slot, int gslot, double &c_edep) {
   Ph g;
   load_ph(P, S, slot, g);
@@ -1287,7 +1293,7 @@ __device__ __forceinline__ int phase_end(const Params &P, Smem &S, int slot, int
   if (g.flags & F_ABSORB) {
     if (g.flags & F_CONV) n_conv = 1; else n_phot = 1;
     rng_begin(g.rng);
-    deposit<kTle>(P, g, P.depbuf + (size_t)gslot * kDepBuf, ds, g.E * hist_weight(P, gslot), g.mat, (g.flags & F_INVOL) != 0, g.E, gslot);
+    deposit<kMode>(P, g, P.depbuf + (size_t)gslot * kDepBuf, ds, g.E * hist_weight<kMode>(P, gslot), g.mat, (g.flags & F_INVOL) != 0, g.E, gslot);
     g.flags &= ~(F_ABSORB | F_CONV);
     c_edep += ds.edep;
   }
@@ -1305,10 +1311,10 @@ __device__ __forceinline__ int phase_end(const Params &P, Smem &S, int slot, int
     }
     g.E = kMc2; g.seg = 0.0f;
     g.flags &= ~(F_PEND | F_EXIT);
-    next = locate(P, g);
+    next = locate<kMode>(P, g);
     set_energy(P, S, slot, g);
     store_ph(S, slot, g);
-  } else if (kTle && (g.flags & F_OPEN) && P.tle_tab && __ldcg(&P.tle_state[gslot].w) != 0u) {
+  } else if ((kMode == 1) && (g.flags & F_OPEN) && P.tle_tab && __ldcg(&P.tle_state[gslot].w) != 0u) {
     // the history's TLE table goes to the grids first: chunked, in the TLE phase; then back here
     __stcg(&P.tle_state[gslot].x, __float_as_uint(-2.0f));
     __stcg(&P.tle_state[gslot].y, 0u);
@@ -1320,7 +1326,7 @@ __device__ __forceinline__ int phase_end(const Params &P, Smem &S, int slot, int
       const int nbuf = (int)((g.flags & F_NBUF) >> F_NBUF_SHIFT);
       if (nbuf) flush_buffer(P, P.depbuf + (size_t)gslot * kDepBuf, nbuf);
       n_flush = (unsigned)nbuf;
-      if (P.nphsp > 0 && !(g.flags & F_STORED)) n_abs = 1;
+      if (kMode != 2 && P.nphsp > 0 && !(g.flags & F_STORED)) n_abs = 1;
     }
     // claim the next history id (one atomic per group of lanes that arrive together)
     const unsigned lane = threadIdx.x & 31u;
@@ -1341,9 +1347,9 @@ __device__ __forceinline__ int phase_end(const Params &P, Smem &S, int slot, int
       generate_primary(P, g, gslot);
       g.path = 0.0f; g.seg = 0.0f;
       n_hist = 1;
-      next = locate(P, g);
+      next = locate<kMode>(P, g);
       if (g.E < P.e_cut) {
-        c_edep += (double)(g.E * hist_weight(P, gslot));   // below the table: absorbed where it starts
+        c_edep += (double)(g.E * hist_weight<kMode>(P, gslot));   // below the table: absorbed where it starts
         next = Q_E;
         S.tbin[slot] = 0.0f;
       } else {
@@ -1366,7 +1372,7 @@ __device__ __forceinline__ int phase_end(const Params &P, Smem &S, int slot, int
     stat_bump(S, S_DEP, t >> 24);
   }
   stat_overflow(S, ds.over, ds.flush);
-  if (kTle) stat_tle_overflow(S, ds.tle_over, ds.tle_ent);
+  if ((kMode == 1)) stat_tle_overflow(S, ds.tle_over, ds.tle_ent);
   return next;
 }
 
@@ -1431,7 +1437,7 @@ __device__ __forceinline__ int phase_tle(const Params &P, Smem &S, int slot, int
     } else {
       i[0] = (int)(st.y & 0xffffu); i[1] = (int)(st.y >> 16); i[2] = (int)st.z;
     }
-    const float kE = (0.1f * E) * hist_weight(P, gslot);
+    const float kE = (0.1f * E) * hist_weight<1>(P, gslot);
     Rng r;
     {
       const unsigned long long id = P.first + S.hidx[slot];
@@ -1521,9 +1527,12 @@ __device__ __forceinline__ int phase_tle(const Params &P, Smem &S, int slot, int
 
 // ------------------------------------------------------------------------------ kernel
 
-// kTle: the engine has track-length-estimator actors (the plain kernel carries none of that code)
-template <typename LabelT, bool kTle>
-__global__ void __launch_bounds__(threads_of<kTle>(), GB2_MIN_CTAS) transport_kernel(const __grid_constant__ Params P) {
+// kMode 1: the engine has track-length-estimator actors (the plain kernels carry none of that code);
+// kMode 2: the common dose run -- ONE dose actor with hit_type post, no phase-space actor, no phase-space
+// source -- whose actor loop, hit-point emulation, plane loops and weight look-ups are resolved at
+// compile time (the descriptor fields become immediate constant-bank operands); kMode 0: everything else
+template <typename LabelT, int kMode>
+__global__ void __launch_bounds__(threads_of<(kMode == 1)>(), GB2_MIN_CTAS) transport_kernel(const __grid_constant__ Params P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem &S = *reinterpret_cast<Smem *>(smem_raw);
   float *s_maj = reinterpret_cast<float *>(smem_raw + sizeof(Smem));
@@ -1617,13 +1626,13 @@ __global__ void __launch_bounds__(threads_of<kTle>(), GB2_MIN_CTAS) transport_ke
         if (slot[w] >= 0) volume_gather_mu(P, vc[w]);
 #pragma unroll
       for (int w = 0; w < kVWidth; ++w)
-        if (slot[w] >= 0) next[w] = volume_decide<kTle>(P, S, slot[w], slot_base + slot[w], vc[w], c_tent);
+        if (slot[w] >= 0) next[w] = volume_decide<kMode>(P, S, slot[w], slot_base + slot[w], vc[w], c_tent);
     } else if (slot[0] >= 0) {
-      if (q == Q_C) next[0] = phase_compton<kTle>(P, S, slot[0], slot_base + slot[0], c_edep);
-      else if (q == Q_E) next[0] = phase_end<kTle>(P, S, slot[0], slot_base + slot[0], c_edep);
-      else if (q == Q_W) next[0] = phase_world(P, S, slot[0], slot_base + slot[0]);
-      else if (kTle && q == Q_T) next[0] = phase_tle<LabelT>(P, S, slot[0], slot_base + slot[0]);
-      else next[0] = phase_rare<kTle>(P, S, slot[0], slot_base + slot[0], c_edep);
+      if (q == Q_C) next[0] = phase_compton<kMode>(P, S, slot[0], slot_base + slot[0], c_edep);
+      else if (q == Q_E) next[0] = phase_end<kMode>(P, S, slot[0], slot_base + slot[0], c_edep);
+      else if (q == Q_W) next[0] = phase_world<kMode>(P, S, slot[0], slot_base + slot[0]);
+      else if ((kMode == 1) && q == Q_T) next[0] = phase_tle<LabelT>(P, S, slot[0], slot_base + slot[0]);
+      else next[0] = phase_rare<kMode>(P, S, slot[0], slot_base + slot[0], c_edep);
     }
     __syncwarp();
     __threadfence_block();   // slot state visible before the slot is published again

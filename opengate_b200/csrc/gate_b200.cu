@@ -780,16 +780,17 @@ static int launch_histories(gate_b200_engine *h, int32_t source_id, uint64_t fir
   CU(cudaMemsetAsync(h->d_next, 0, sizeof(unsigned long long), h->stream));
   const size_t smem = sizeof(Smem) + (size_t)P.ne * sizeof(float);
   // kernel variant: 1 = with the TLE phase; 2 / 3 = the common dose run (one dose actor, no phase-space actor
-  // or source) with those choices compiled in, 2 for hit_type post, 3 for the other hit types; 0 = everything else
-  const bool simple = P.ntle == 0 && P.ndose == 1 && P.nphsp == 0 && P.src.ph_b == nullptr && !getenv("GATE_B200_GENERAL_KERNEL");
-  const int mode = P.ntle > 0 ? 1 : (simple ? (P.dose[0].hit_type == GATE_B200_HIT_POST ? 2 : 3) : 0);
+  // or source) with those choices compiled in, 2 for hit_type post, 3 for the other hit types; 4 = one dose actor
+  // with phase-space actors; 0 = everything else
+  const bool one_dose = P.ntle == 0 && P.ndose == 1 && P.src.ph_b == nullptr && !getenv("GATE_B200_GENERAL_KERNEL");
+  const int mode = P.ntle > 0 ? 1 : !one_dose ? 0 : P.nphsp > 0 ? 4 : (P.dose[0].hit_type == GATE_B200_HIT_POST ? 2 : 3);
   auto kern = transport_kernel<uint8_t, 0>;
   if (label_bytes == 2) {
     kern = mode == 1 ? transport_kernel<uint16_t, 1> : mode == 2 ? transport_kernel<uint16_t, 2>
-         : mode == 3 ? transport_kernel<uint16_t, 3> : transport_kernel<uint16_t, 0>;
+         : mode == 3 ? transport_kernel<uint16_t, 3> : mode == 4 ? transport_kernel<uint16_t, 4> : transport_kernel<uint16_t, 0>;
   } else {
     kern = mode == 1 ? transport_kernel<uint8_t, 1> : mode == 2 ? transport_kernel<uint8_t, 2>
-         : mode == 3 ? transport_kernel<uint8_t, 3> : transport_kernel<uint8_t, 0>;
+         : mode == 3 ? transport_kernel<uint8_t, 3> : mode == 4 ? transport_kernel<uint8_t, 4> : transport_kernel<uint8_t, 0>;
   }
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // persistent CTAs: one per SM, fewer only when there is not enough work to fill the slots

@@ -894,7 +894,7 @@ __device__ __forceinline__ int locate(const Params &P, Ph &g) {
     if (inside_box(pl, P.half)) { to_volume(P, g); st = Q_V; }
   }
   g.flags &= ~F_INSIDE;
-  for (int k = 0; k < (kMode >= 2 ? 0 : P.nphsp); ++k) {
+  for (int k = 0; k < ((kMode == 2 || kMode == 3) ? 0 : P.nphsp); ++k) {
     float pb[3];
     aff_apply(P.phsp[k].w2b, g.p, pb);
     if (st == Q_W && inside_box(pb, P.phsp[k].half)) g.flags |= (1u << k);
@@ -943,7 +943,7 @@ __device__ __forceinline__ int phase_world(const Params &P, Smem &S, int slot, i
       rot_apply(P.w2v.m, g.d, dl);
       if (ray_box_ax(pl, dl, P.half, ti, to, ai, ao) && ti < t_best) { t_best = ti; ev = 2; ax_in = ai; }
     }
-    for (int k = 0; k < (kMode >= 2 ? 0 : P.nphsp); ++k) {
+    for (int k = 0; k < ((kMode == 2 || kMode == 3) ? 0 : P.nphsp); ++k) {
       float pb[3], db[3], ti, to;
       aff_apply(P.phsp[k].w2b, g.p, pb);
       rot_apply(P.phsp[k].w2b.m, g.d, db);
@@ -1326,7 +1326,7 @@ __device__ __forceinline__ int phase_end(const Params &P, Smem &S, int slot, int
       const int nbuf = (int)((g.flags & F_NBUF) >> F_NBUF_SHIFT);
       if (nbuf) flush_buffer(P, P.depbuf + (size_t)gslot * kDepBuf, nbuf);
       n_flush = (unsigned)nbuf;
-      if (kMode < 2 && P.nphsp > 0 && !(g.flags & F_STORED)) n_abs = 1;
+      if (kMode != 2 && kMode != 3 && P.nphsp > 0 && !(g.flags & F_STORED)) n_abs = 1;
     }
     // claim the next history id (one atomic per group of lanes that arrive together)
     const unsigned lane = threadIdx.x & 31u;
@@ -1531,7 +1531,8 @@ __device__ __forceinline__ int phase_tle(const Params &P, Smem &S, int slot, int
 // kMode 2 and 3: the common dose run -- ONE dose actor, no phase-space actor, no phase-space source -- whose
 // actor loop, plane loops and weight look-ups are resolved at compile time (the descriptor fields become
 // immediate constant-bank operands); 2 also compiles hit_type post in, 3 keeps the hit-point emulation (the
-// reference's default hit_type is random); kMode 0: everything else
+// reference's default hit_type is random); kMode 4: ONE dose actor with phase-space actors (their loops stay);
+// kMode 0: everything else
 template <typename LabelT, int kMode>
 __global__ void __launch_bounds__(threads_of<(kMode == 1)>(), GB2_MIN_CTAS) transport_kernel(const __grid_constant__ Params P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -415,6 +415,7 @@ __device__ __forceinline__ void red_add_f64(double *p, double v) {
 // Add one (voxel, history) sum to the fp64 grids.  Lanes that arrive together and hit the same
 // voxel are combined first (one atomic per distinct address); squares are summed per history, never
 // of the combined value (GateDoseActor.cpp:359-381).
+template <int kMode = 0>
 __device__ __forceinline__ void grid_add(const Params &P, const DepEntry &en) {
   const unsigned lane = threadIdx.x & 31u;
   const int key = en.key;
@@ -439,7 +440,7 @@ __device__ __forceinline__ void grid_add(const Params &P, const DepEntry &en) {
     e = se; e2 = se2; d = sd; d2 = sd2; n = sn;
   }
   if ((int)lane == leader) {
-    const DDose &D = P.dose[a];
+    const DDose &D = P.dose[kMode >= 2 ? 0 : a];   // variants 2-4: the one dose actor, fields as immediates
     const size_t o = (size_t)v * (size_t)D.gstride;
     red_add_f64(D.grid[GATE_B200_GRID_EDEP] + o, e);
     if (D.flags & GATE_B200_SCORE_EDEP_SQ) red_add_f64(D.grid[GATE_B200_GRID_EDEP_SQ] + o, e2);
@@ -450,8 +451,9 @@ __device__ __forceinline__ void grid_add(const Params &P, const DepEntry &en) {
 }
 
 // Add the coalesced (voxel, history) entries of a closed history to the fp64 grids.
+template <int kMode = 0>
 __device__ __forceinline__ void flush_buffer(const Params &P, const DepEntry *buf, int nbuf) {
-  for (int j = 0; j < nbuf; ++j) grid_add(P, ld_dep(buf + j));
+  for (int j = 0; j < nbuf; ++j) grid_add<kMode>(P, ld_dep(buf + j));
 }
 
 // ---- per-history table of the TLE actors that score squares: open addressing, Fibonacci hash.
@@ -562,7 +564,7 @@ __device__ __forceinline__ void deposit(const Params &P, Ph &g, DepEntry *buf, D
       if (__ldcg(&buf[j].key) == key) break;
     if (j == nbuf) {
       if (nbuf == kDepBuf) {   // coalescing buffer full: write it out, start again
-        flush_buffer(P, buf, nbuf);
+        flush_buffer<kMode>(P, buf, nbuf);
         ds.flush += (unsigned)nbuf;
         ds.over++;
         nbuf = 0;
@@ -1324,7 +1326,7 @@ __device__ __forceinline__ int phase_end(const Params &P, Smem &S, int slot, int
   } else {
     if (g.flags & F_OPEN) {
       const int nbuf = (int)((g.flags & F_NBUF) >> F_NBUF_SHIFT);
-      if (nbuf) flush_buffer(P, P.depbuf + (size_t)gslot * kDepBuf, nbuf);
+      if (nbuf) flush_buffer<kMode>(P, P.depbuf + (size_t)gslot * kDepBuf, nbuf);
       n_flush = (unsigned)nbuf;
       if (kMode != 2 && kMode != 3 && P.nphsp > 0 && !(g.flags & F_STORED)) n_abs = 1;
     }

@@ -35,7 +35,9 @@ def compare_dose(value_a, rel_unc_a, value_b, rel_unc_b, total_tolerance=0.005, 
     sigma = np.sqrt(sa[sel] ** 2 + sb[sel] ** 2)
     ok_sigma = sigma > 0
     z = np.abs(a[sel] - b[sel])[ok_sigma] / sigma[ok_sigma]
-    frac = float(np.mean(z <= n_sigma)) if z.size else 1.0
+    # no voxel with a usable uncertainty (uncertainty images missing or all zero): nothing was compared, which
+    # is a FAILED acceptance, never a vacuous pass
+    frac = float(np.mean(z <= n_sigma)) if z.size else 0.0
     out = {
         "total_ratio": total_ratio,
         "total_ok": abs(total_ratio - 1.0) <= total_tolerance,
@@ -43,7 +45,7 @@ def compare_dose(value_a, rel_unc_a, value_b, rel_unc_b, total_tolerance=0.005, 
         "fraction_within_n_sigma": frac,
         "mean_pull": float(np.mean((a[sel] - b[sel])[ok_sigma] / sigma[ok_sigma])) if z.size else 0.0,
         "rms_pull": float(np.sqrt(np.mean(z ** 2))) if z.size else 0.0,
-        "voxel_ok": frac >= min_pass_fraction,
+        "voxel_ok": bool(z.size > 0 and frac >= min_pass_fraction),
     }
     out["ok"] = bool(out["total_ok"] and out["voxel_ok"])
     return out

@@ -107,17 +107,29 @@ class ActorOutputImage:
             self.items[i]["write_to_disk"] = bool(value)
 
     def set_output_filename(self, value, item="all"):
+        """Reference semantics (actoroutput.py:996-1018, actors/base.py:449-457): a name given for ALL items (what
+        `actor.output_filename = ...` does) gets the item suffix inserted per item; a name given for ONE item
+        (`actor.edep.output_filename = ...`) is stored verbatim."""
+        if item == "all":
+            for i, cfg in self.items.items():
+                if value in (None, "", "auto") or not cfg["suffix"]:
+                    cfg["output_filename"] = value
+                else:
+                    cfg["output_filename"] = _insert_suffix(value, cfg["suffix"])
+            return
         for i in self._ids(item):
-            self.items[i]["output_filename"] = value
+            self.items[i]["output_filename"] = None if value is None else str(value)
 
     def get_output_filename(self, item=0):
         f = self.items[item]["output_filename"]
-        suffix = self.items[item]["suffix"]
         if f == "auto":
+            # _generate_auto_output_filename (actoroutput.py:1041-1052): only the automatic name gets the suffix here
             f = f"{self.name}_from_{self.actor.type_name.lower()}_{self.actor.name}.{self.default_ext}"
+            suffix = self.items[item]["suffix"]
+            return _insert_suffix(f, suffix) if suffix else f
         if f in (None, ""):
             return None
-        return _insert_suffix(f, suffix) if suffix else f
+        return f
 
     def get_output_path(self, which="merged", item=0):
         f = self.get_output_filename(item)
@@ -198,7 +210,7 @@ class UserInterfaceToActorOutputImage:
     active = property(lambda s: s._o.get_active(s._item), lambda s, v: s._o.set_active(v, s._item))
     write_to_disk = property(lambda s: s._o.get_write_to_disk(s._item), lambda s, v: s._o.set_write_to_disk(v, s._item))
     output_filename = property(lambda s: s._o.get_output_filename(s._item),
-                               lambda s, v: s._o.items[s._item].__setitem__("output_filename", v))
+                               lambda s, v: s._o.set_output_filename(v, item=s._item))
     keep_data_per_run = property(lambda s: s._o.items[s._item]["keep_data_per_run"],
                                  lambda s, v: s._o.items[s._item].__setitem__("keep_data_per_run", bool(v)))
 

@@ -74,6 +74,9 @@ struct gate_b200_engine {
   size_t label_total_bytes = 0;
   size_t l2_persist_max = 0, l2_window_max = 0;
   bool l2_persist = false;               // measured on B200: a persisting window for the labels is slower (C3 6.0e8 vs 1.0e9/s)
+  size_t l2_limit_set = 0;               // cudaLimitPersistingL2CacheSize this engine applied to ITS device
+  unsigned long long *d_unc_u = nullptr; // scratch of gate_b200_mean_uncertainty: {max bits, count}
+  double *d_unc_s = nullptr;             //                                         sum
 };
 
 namespace {
@@ -804,10 +807,9 @@ static int launch_histories(gate_b200_engine *h, int32_t source_id, uint64_t fir
   if (h->l2_persist && h->d_labels && h->l2_persist_max > 0 && h->l2_window_max > 0 && h->label_total_bytes > (1u << 20)) {
     const size_t win = std::min(h->label_total_bytes, h->l2_window_max);
     const size_t persist = std::min(win, h->l2_persist_max);
-    static thread_local size_t limit_set = 0;
-    if (limit_set != persist) {
+    if (h->l2_limit_set != persist) {   // the limit is per DEVICE: remembered in the handle, not per thread
       CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist));
-      limit_set = persist;
+      h->l2_limit_set = persist;
     }
     attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
     attr[0].val.accessPolicyWindow.base_ptr = h->d_labels;
@@ -883,7 +885,13 @@ static int check_grid(gate_b200_engine *h, int32_t actor_id, int32_t which, doub
 // dense staging array for get/set_dose_grid (kept for the life of the engine, grown on demand)
 static int staging(gate_b200_engine *h, size_t n, double **out) {
   if (h->stage_elems < n) {
-    if (int rc = dev_alloc(h, &h->d_stage, n)) return rc;   // an older, smaller one stays in `allocs` until destroy
+    if (h->d_stage) {   // the outgrown one goes back to the pool in stream order
+      h->allocs.erase(std::remove(h->allocs.begin(), h->allocs.end(), (void *)h->d_stage), h->allocs.end());
+      CU(cudaFreeAsync(h->d_stage, h->stream));
+      h->d_stage = nullptr;
+      h->stage_elems = 0;
+    }
+    if (int rc = dev_alloc(h, &h->d_stage, n)) return rc;
     h->stage_elems = n;
   }
   *out = h->d_stage;

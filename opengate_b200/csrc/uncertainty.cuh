@@ -68,10 +68,14 @@ extern "C" int gate_b200_mean_uncertainty(gate_b200_engine *h, int32_t actor_id,
   const double *e = A.dev.grid[GATE_B200_GRID_EDEP], *e2 = A.dev.grid[GATE_B200_GRID_EDEP_SQ];
   if (!e || !e2) return fail(h, GATE_B200_EINVAL, "mean uncertainty needs edep and edep_squared");
   CU(cudaSetDevice(h->device));
-  unsigned long long *d_u = nullptr;
-  double *d_s = nullptr;
-  CU(cudaMalloc(&d_u, 2 * sizeof(unsigned long long)));
-  CU(cudaMalloc(&d_s, sizeof(double)));
+  // scratch from the engine's stream-ordered pool, allocated once and freed with the engine (an early return
+  // on a CUDA error leaks nothing)
+  if (!h->d_unc_u) {
+    if (int rc = dev_alloc(h, &h->d_unc_u, 2)) return rc;
+    if (int rc = dev_alloc(h, &h->d_unc_s, 1)) return rc;
+  }
+  unsigned long long *d_u = h->d_unc_u;
+  double *d_s = h->d_unc_s;
   const int blocks = h->sm_count * 8, threads = 256;
   double nev = (double)n_events;
   if (nev < 2.0) nev = 2.0;
@@ -106,8 +110,6 @@ extern "C" int gate_b200_mean_uncertainty(gate_b200_engine *h, int32_t actor_id,
   CU(cudaMemcpyAsync(&s, d_s, sizeof s, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaMemcpyAsync(&c, d_u, sizeof c, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  cudaFree(d_u);
-  cudaFree(d_s);
   *out = (c > 0 && s > 0.0) ? s / (double)c : 1.0;
   return GATE_B200_OK;
 }

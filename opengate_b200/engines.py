@@ -258,18 +258,6 @@ class GpuSimulationEngine:
             self.engines = [self._backend(0, self.setup.seed)]
             return
         from .core import Engine
-        # torch.distributed only matters when the script runs under torchrun and has initialised a process
-        # group: do not pay the import of torch (4 s) in a plain single-process run
-        import sys
-        if "torch" in sys.modules:
-            try:
-                import torch.distributed as dist
-                if dist.is_available() and dist.is_initialized():
-                    self.dist = dist
-                    self.rank, self.world = dist.get_rank(), dist.get_world_size()
-                    _, _, self.local_rank = multigpu.world_info()
-            except ImportError:
-                pass
         if self.dist is not None:
             if sim.number_of_gpus not in (None, self.world):
                 warning(f"number_of_gpus={sim.number_of_gpus} ignored: running under torchrun with {self.world} ranks")
@@ -283,9 +271,38 @@ class GpuSimulationEngine:
         return self.world if self.dist is not None else len(self.engines)
 
     # ------------------------------------------------------------------------ run
+    def _detect_process_group(self):
+        """torch.distributed only matters when the script runs under torchrun and has initialised a process
+        group: do not pay the import of torch (4 s) in a plain single-process run."""
+        import sys
+        if self._backend is not None and not getattr(self._backend, "distributed", False):
+            return
+        if "torch" in sys.modules:
+            try:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized():
+                    self.dist = dist
+                    self.rank, self.world = dist.get_rank(), dist.get_world_size()
+                    _, _, self.local_rank = multigpu.world_info()
+            except ImportError:
+                pass
+
+    def _share_random_seed(self):
+        """All ranks of a run must use ONE seed: the Philox key of every history (results independent of the
+        number of GPUs) and the Poisson draw of activity sources in expected_number_of_events() (all ranks
+        must agree on the count they split).  random_seed='auto' draws it per process, so rank 0's is
+        broadcast; an explicit integer seed is the same everywhere already and goes through unchanged."""
+        if self.dist is None:
+            return
+        box = [int(self.sim.current_random_seed)]
+        self.dist.broadcast_object_list(box, src=0)
+        self.sim.current_random_seed = int(box[0])
+
     def run_engine(self):
         sim = self.sim
         t_init = time.perf_counter()
+        self._detect_process_group()
+        self._share_random_seed()
         self.build_setup()
         self._init_devices()
         self.ids = [self.setup.apply(e) for e in self.engines]
@@ -352,6 +369,15 @@ class GpuSimulationEngine:
     def _gather_grids(self, actor_index, which_list, reduce_in_place=True):
         """Sum of the accumulator grids of one dose actor over all shards -> {which: (z,y,x) float64}."""
         out = {}
+        if self.dist is not None and not hasattr(self.engines[0], "dose_buffers"):
+            # an injected back end without device buffers (tests: the CPU oracle under a gloo group): host reduce
+            import torch
+            e, ids = self.engines[0], self.ids[0]
+            for w in which_list:
+                t = torch.from_numpy(np.array(e.dose_grid(ids[1][actor_index], w), dtype=np.float64, copy=True))
+                self.dist.all_reduce(t)
+                out[w] = t.numpy()
+            return out
         if self.dist is not None:
             e, ids = self.engines[0], self.ids[0]
             aid = ids[1][actor_index]
@@ -359,6 +385,10 @@ class GpuSimulationEngine:
             if reduce_in_place:
                 for t in bufs:
                     self.dist.all_reduce(t)
+                # a (non-async) NCCL all_reduce only orders torch's current stream after the collective; the
+                # engine extracts and copies on its OWN non-blocking stream: wait for the reduction on the host
+                # before handing the buffers back to it (the engine's earlier work was drained by _sync())
+                multigpu.device_synchronize(e.device)
                 for w in which_list:
                     out[w] = e.dose_grid(aid, w)
             else:
@@ -424,7 +454,7 @@ class GpuSimulationEngine:
             s = e.stats()
             st = dict(s) if st is None else {k: (st[k] + s[k] if k != "kernel_ms" else max(st[k], s[k])) for k in st}
         if self.dist is not None:
-            st = multigpu.reduce_counters(st, f"cuda:{self.local_rank}")
+            st = multigpu.reduce_counters(st, "cpu" if self._backend is not None else f"cuda:{self.local_rank}")
         n_events = int(st["histories"])
         # dose actors
         for i, a in enumerate(self.dose_actors):

@@ -41,6 +41,12 @@ def buffer_tensors(engine, actor):
             for ptr, n in engine.dose_buffers(actor)]
 
 
+def device_synchronize(device):
+    """Host-side wait for everything queued on `device` (torch's streams, NCCL's and the engine's)."""
+    import torch
+    torch.cuda.synchronize(torch.device("cuda", int(device)))
+
+
 def record_layout(score_flags):
     """(stride, {grid: offset}) of the voxel records of a dose actor: the scored ones of edep, edep2,
     dose, dose2 in that order, 1, 2 or 4 doubles per voxel (same rule as gate_b200_add_dose_actor)."""

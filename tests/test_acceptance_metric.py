@@ -54,3 +54,10 @@ def test_label_comparison_is_integer_exact():
     b[1, 2, 3] += 1
     r = acceptance.compare_labels(a, b)
     assert not r["ok"] and r["different_voxels"] == 1
+
+
+def test_no_comparable_voxel_is_a_failure_not_a_vacuous_pass():
+    from opengate_b200 import acceptance
+    a = np.ones((4, 4, 4))
+    r = acceptance.compare_dose(a, np.zeros_like(a), a, np.zeros_like(a))
+    assert r["voxels_compared"] == 0 and not r["voxel_ok"] and not r["ok"]

@@ -405,3 +405,21 @@ def test_user_facing_api_surface_checklist():
     need(st, "SimulationStatisticsActor", ["counts", "pps", "track_types_flag"])
     assert hasattr(gate.geometry.materials, "HounsfieldUnit_to_material")
     assert missing == []
+
+
+def test_output_filename_semantics_follow_the_reference(tmp_path):
+    """actoroutput.py:996-1058 + actors/base.py:449-457: the actor-level name fans out with the item suffix,
+    a name set on ONE output is kept verbatim, 'auto' gets the suffix when the name is generated."""
+    sim, ct, src, dose, hu = ct_sim(tmp_path)
+    assert dose.edep.output_filename == "ct_edep.mhd"
+    assert dose.edep_uncertainty.output_filename == "ct_edep_uncertainty.mhd"
+    assert dose.dose.output_filename == "ct_dose.mhd"
+    dose.edep.output_filename = "x.mhd"
+    assert dose.edep.output_filename == "x.mhd"                       # verbatim, no suffix
+    assert dose.edep_uncertainty.output_filename == "ct_edep_uncertainty.mhd"
+    assert str(dose.edep.get_output_path()).endswith("/x.mhd")
+    dose2 = sim.add_actor("DoseActor", "d2")
+    dose2.attached_to = "ct"
+    assert dose2.edep.output_filename == "edep_with_uncertainty_from_doseactor_d2_edep.mhd"   # actoroutput.py:488-490
+    dose.dose.output_filename = None
+    assert dose.dose.output_filename is None

@@ -96,3 +96,69 @@ def test_record_layout_follows_the_device_rule():
     assert multigpu.record_layout(E | E2 | D) == (4, {abi.GRID_EDEP: 0, abi.GRID_EDEP_SQ: 1, abi.GRID_DOSE: 2})
     assert multigpu.record_layout(E | E2 | D | D2 | C)[0] == 4
     assert multigpu.record_layout(E | D | D2)[1] == {abi.GRID_EDEP: 0, abi.GRID_DOSE: 1, abi.GRID_DOSE_SQ: 2}
+
+
+# ------------------------------------------------------------------------------ the engine's own N>1 path
+
+def _engine_worker(rank, world, port, tmp, q):
+    """Simulation.run() under a 2-rank gloo group with random_seed='auto' and an activity source: the ranks
+    must agree on ONE seed (rank 0's) and on the Poisson event count they split, and the merged result must be
+    what a single process gives with that seed."""
+    sys.path.insert(0, HERE)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import random
+    random.seed(1000 + rank)                      # 'auto' would draw different seeds on the two ranks
+    import opengate_b200 as gate
+    from oracle_backend import OracleBackend
+    from test_host_api import ct_sim
+
+    class Backend(OracleBackend):
+        distributed = True
+
+    import pathlib
+    d = pathlib.Path(tmp) / f"rank{rank}"
+    d.mkdir(exist_ok=True)
+    sim, ct, src, dose, hu = ct_sim(d, n_primaries=0)
+    sim.random_seed = "auto"
+    src.number_of_primaries = 0
+    src.activity = 5000 * gate.g4_units.Bq
+    sim.run_timing_intervals = [[0, 1 * gate.g4_units.s]]
+    dose.edep_uncertainty.active = True
+    out = sim.run(_backend=Backend)
+    q.put((rank, int(sim.current_random_seed), int(out.device_stats[0]["histories"]),
+           dose.edep.image.array.copy() if rank == 0 else None, dose.edep_uncertainty.image.array.copy() if rank == 0 else None))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_engine_under_a_process_group_shares_seed_and_counts(tmp_path):
+    sys.path.insert(0, HERE)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_engine_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in range(2)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, seed0, n0, edep, unc), (_, seed1, n1, _, _) = res
+    assert seed0 == seed1                          # one seed for the whole job
+    assert n0 == n1 and 300 < n0 < 550             # one Poisson draw (activity x spectrum-weight sum, GateGenericSource.cpp:622-626), split over the ranks
+    # the single-process run with that seed gives the same images
+    import opengate_b200 as gate
+    from oracle_backend import OracleBackend
+    from test_host_api import ct_sim
+    (tmp_path / "single").mkdir()
+    sim, ct, src, dose, hu = ct_sim(tmp_path / "single", n_primaries=0)
+    sim.random_seed = seed0
+    src.number_of_primaries = 0
+    src.activity = 5000 * gate.g4_units.Bq
+    sim.run_timing_intervals = [[0, 1 * gate.g4_units.s]]
+    dose.edep_uncertainty.active = True
+    out = sim.run(_backend=OracleBackend)
+    assert out.device_stats[0]["histories"] == n0
+    np.testing.assert_allclose(edep, dose.edep.image.array, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(unc, dose.edep_uncertainty.image.array, rtol=1e-9, atol=0)

@@ -121,16 +121,22 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def measured_traffic_per_history(workload_key):
+def measured_traffic_per_history(workload_key, kernel_name):
     """DRAM bytes per history of the transport kernel from the committed `ncu --set full` capture
-    (profiles/traffic.json, written by tools/ncu_summary.py --traffic-json); None if absent."""
+    (profiles/traffic.json, written by tools/ncu_summary.py --traffic-json).  The figure is used only when the
+    capture is of the SAME kernel instantiation as the one just launched (entry["kernel"] == kernel_name);
+    otherwise (None, why)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         d = json.load(open(p))
-        e = d.get(workload_key)
-        return (float(e["dram_bytes_per_history"]), e.get("source")) if e else (None, None)
     except Exception:
-        return None, None
+        return None, "no profiles/traffic.json"
+    e = d.get(workload_key)
+    if not e:
+        return None, f"no ncu capture of workload '{workload_key}'"
+    if e.get("kernel") != kernel_name:
+        return None, f"capture {e.get('source')} is of '{e.get('kernel')}', launched '{kernel_name}'"
+    return float(e["dram_bytes_per_history"]), f"{e.get('source')} ({e.get('kernel')}, {e.get('histories_in_capture'):.3g} histories)"
 
 
 def algorithmic_bytes_per_history(st, label_bytes, n_grids, phsp_row_bytes=0):
@@ -294,10 +300,24 @@ def main():
     ev0.record(stream)
     for _ in range(args.steps):
         step()
+    reduce_check = None
     if world > 1:
+        # correctness of the one exchange step, checked on the numbers themselves: the sum over the voxel records
+        # on rank 0 after the reduce must equal the sum over ranks of the per-rank sums taken before it
+        bufs = [t for a in dids for t in multigpu.buffer_tensors(eng, a)]
+        before = torch.stack([t.sum() for t in bufs])
         multigpu.reduce_dose_grids(eng, dids, S, dst=0)
+        after = torch.stack([t.sum() for t in bufs])
     ev1.record(stream)
     barrier()
+    if world > 1:
+        dist.all_reduce(before)
+        nhist = torch.tensor([eng.stats()["histories"]], device="cuda", dtype=torch.int64)
+        dist.all_reduce(nhist)
+        if rank == 0:
+            rel = float(((after - before).abs() / before.abs().clamp_min(1e-300)).max())
+            ok = rel < 1e-9 and int(nhist.item()) == world * H * args.steps and float(before.min()) > 0
+            reduce_check = "ok" if ok else f"FAILED: rel {rel:.3e}, histories {int(nhist.item())} vs {world * H * args.steps}"
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -315,7 +335,8 @@ def main():
     kernel_ms = st["kernel_ms"] / max(args.steps, 1)
     achieved = b_hist * H / (kernel_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
-    t_hist, t_src = measured_traffic_per_history(args.config)
+    kernel_name = eng.kernel_name()
+    t_hist, t_src = measured_traffic_per_history(args.config, kernel_name)
 
     line = None
     if rank == 0:
@@ -330,10 +351,14 @@ def main():
                        "parallelism": f"histories sharded over {world} GPU(s), NCCL reduce of {G} grids at end of run" if world > 1 else "1 GPU"},
             "clocks": clocks,
             "gpu_launches": args.steps,
+            "reduce_check": reduce_check,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (t_hist * H if t_hist else None), "traffic_source": t_src,
                          "algorithmic_bytes_per_launch": b_hist * H, "peak_source": peak_src,
-                         "kernel": "gb2::transport_kernel", "kernel_ms_per_launch": kernel_ms,
+                         "kernel": kernel_name, "kernel_ms_per_launch": kernel_ms,
+                         # the reference's label type is unsigned short (GateImageNestedParameterisation.h:24);
+                         # the engine packs <= 256 materials into one byte: the same run counted with 2-byte labels
+                         "frac_with_2_byte_labels": (b_hist + n_tent * (2 - label_bytes)) * H / (kernel_ms * 1e-3) / 1e9 / peak,
                          "bytes_per_history": b_hist, "tentative_collisions_per_history": n_tent,
                          "deposit_entries_per_history": n_dep, "phsp_rows_per_history": f_out,
                          "label_bytes": label_bytes, "grids_per_deposit": G,

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GATE_B200_ABI_VERSION 3
+#define GATE_B200_ABI_VERSION 4
 
 enum {
   GATE_B200_OK = 0,
@@ -278,6 +278,11 @@ int gate_b200_phsp_count(gate_b200_engine *h, int32_t actor_id, uint64_t *n_rows
 int gate_b200_get_phsp(gate_b200_engine *h, int32_t actor_id, uint64_t max_rows,
                        const gate_b200_phsp_columns *out, uint64_t *n_rows);
 int gate_b200_get_stats(gate_b200_engine *h, gate_b200_stats *out);
+/* Name of the transport-kernel instantiation of the most recent launch of this engine, spelled as the CUDA
+ * tools print it (e.g. "gb2::transport_kernel<unsigned char, 2>"; "" before the first launch): lets a caller tie
+ * a measurement to the profiler capture of the SAME kernel variant (bench.py's roofline.traffic).  No reference
+ * counterpart (the reference has no device code). */
+const char *gate_b200_kernel_name(const gate_b200_engine *h);
 
 /* One-call convenience used by benchmarks: upload nothing, just time `n` histories of an
  * already configured source (same as run_source + sync) and return device milliseconds. */

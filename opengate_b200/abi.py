@@ -10,7 +10,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # enums --------------------------------------------------------------------------------
 POS_POINT, POS_BOX, POS_SPHERE, POS_DISC, POS_CYLINDER, POS_VOXELS, POS_PHSP, POS_SURFACE_SPHERE = range(8)

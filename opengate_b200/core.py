@@ -32,7 +32,7 @@ EXPORTS = [
     "gate_b200_add_tle_dose_actor", "gate_b200_add_phsp_actor", "gate_b200_begin_run", "gate_b200_run_source", "gate_b200_sync",
     "gate_b200_get_dose_grid", "gate_b200_dose_buffers", "gate_b200_set_dose_grid",
     "gate_b200_mean_uncertainty", "gate_b200_phsp_count", "gate_b200_get_phsp",
-    "gate_b200_get_stats", "gate_b200_timed_run",
+    "gate_b200_get_stats", "gate_b200_timed_run", "gate_b200_kernel_name",
 ]
 
 
@@ -77,6 +77,8 @@ def load_library():
     L.gate_b200_destroy.restype = None
     L.gate_b200_last_error.argtypes = [vp]
     L.gate_b200_last_error.restype = C.c_char_p
+    L.gate_b200_kernel_name.argtypes = [vp]
+    L.gate_b200_kernel_name.restype = C.c_char_p
     L.gate_b200_set_stream.argtypes = [vp, vp]
     L.gate_b200_set_tables.argtypes = [vp, C.POINTER(abi.Tables)]
     L.gate_b200_set_world.argtypes = [vp, C.POINTER(C.c_double), i32]
@@ -99,7 +101,7 @@ def load_library():
     L.gate_b200_get_stats.argtypes = [vp, C.POINTER(abi.Stats)]
     L.gate_b200_timed_run.argtypes = [vp, i32, u64, u64, C.POINTER(C.c_double)]
     for name in EXPORTS:
-        if name not in ("gate_b200_destroy", "gate_b200_last_error"):
+        if name not in ("gate_b200_destroy", "gate_b200_last_error", "gate_b200_kernel_name"):
             getattr(L, name).restype = C.c_int
     v = L.gate_b200_abi_version()
     if v != abi.ABI_VERSION:
@@ -281,6 +283,10 @@ class Engine:
         got = C.c_uint64()
         self._check(self.L.gate_b200_get_phsp(self.h, actor, C.c_uint64(n), C.byref(cols), C.byref(got)))
         return out
+
+    def kernel_name(self):
+        """instantiation of the most recent transport launch, e.g. 'gb2::transport_kernel<unsigned char, 2>'"""
+        return self.L.gate_b200_kernel_name(self.h).decode()
 
     def stats(self):
         s = abi.Stats()

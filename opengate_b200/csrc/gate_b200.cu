@@ -68,6 +68,7 @@ struct gate_b200_engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_events;
   double kernel_ms = 0.0;
+  std::string kernel_name;               // instantiation of the most recent launch
   int sm_count = 148;
   int max_ctas = 148;                   // persistent CTAs (one per SM); scratch is sized for it
   int label_bytes = 0;
@@ -320,6 +321,7 @@ int gate_b200_release_cached_memory(int device_id) {
 }
 
 const char *gate_b200_last_error(const gate_b200_engine *h) { return h ? h->err.c_str() : "null engine"; }
+const char *gate_b200_kernel_name(const gate_b200_engine *h) { return h ? h->kernel_name.c_str() : ""; }
 
 int gate_b200_set_stream(gate_b200_engine *h, void *cuda_stream) {
   if (!h) return GATE_B200_EINVAL;
@@ -794,6 +796,11 @@ static int launch_histories(gate_b200_engine *h, int32_t source_id, uint64_t fir
   } else {
     kern = mode == 1 ? transport_kernel<uint8_t, 1> : mode == 2 ? transport_kernel<uint8_t, 2>
          : mode == 3 ? transport_kernel<uint8_t, 3> : mode == 4 ? transport_kernel<uint8_t, 4> : transport_kernel<uint8_t, 0>;
+  }
+  {
+    char nm[96];
+    snprintf(nm, sizeof nm, "gb2::transport_kernel<unsigned %s, %d>", label_bytes == 2 ? "short" : "char", mode);
+    h->kernel_name = nm;
   }
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // persistent CTAs: one per SM, fewer only when there is not enough work to fill the slots

@@ -22,11 +22,12 @@ from opengate_b200 import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "_build", "liboracle.so")
+_LIB64 = os.path.join(_HERE, "_build", "liboracle64.so")   # -DORACLE_FP64: the same algorithm in double precision
 
 
 def build(force=False):
     src = os.path.join(_HERE, "transport_oracle.c")
-    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+    if force or any(not os.path.exists(l) or os.path.getmtime(l) < os.path.getmtime(src) for l in (_LIB, _LIB64)):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _LIB
 
@@ -46,14 +47,15 @@ class Trace(C.Structure):
                 ("n_interactions", C.c_int), ("n_dep", C.c_int), ("n_iter", C.c_int), ("dep_e", C.c_float * TRACE_MAX)]
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
+def lib(fp64=False):
+    """The C oracle: the single-precision build the CUDA engine matches bit for bit, or (fp64=True) the
+    double-precision build of the same source (-DORACLE_FP64)."""
+    if fp64 not in _libs:
         build()
-        L = C.CDLL(_LIB)
+        L = C.CDLL(_LIB64 if fp64 else _LIB)
         L.oracle_create.restype = C.c_void_p
         L.oracle_create.argtypes = [C.c_uint64]
         L.oracle_destroy.argtypes = [C.c_void_p]
@@ -80,15 +82,15 @@ def lib():
         L.oracle_sincos2pi.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.oracle_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32)]
         L.oracle_uniforms.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_float)]
-        _lib = L
-    return _lib
+        _libs[fp64] = L
+    return _libs[fp64]
 
 
 class TransportOracle:
     """Same call sequence as opengate_b200.core.Engine, executed by the scalar C oracle."""
 
-    def __init__(self, seed):
-        self.L = lib()
+    def __init__(self, seed, fp64=False):
+        self.L = lib(fp64)
         self.h = C.c_void_p(self.L.oracle_create(C.c_uint64(seed)))
         self._keep = []
         self._dose_sizes = []

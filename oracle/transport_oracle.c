@@ -116,6 +116,34 @@ static void o_sincos2pi(float t, float *s, float *c) {
   else { *s = -cs; *c = sn; }
 }
 
+/* ------------------------------------------------------------------ precision switch
+ * Default build (liboracle.so): real_t = float and the functions above: the arithmetic contract the CUDA
+ * engine reproduces bit for bit.  -DORACLE_FP64 (liboracle64.so): the SAME algorithm and random-number
+ * protocol carried out in double precision with libm's log / exp / sin / cos -- the arithmetic of the
+ * reference (Geant4 and itk::Image<double,3> are double throughout).  It exists to show that the
+ * single-precision transport of the engine stays inside the acceptance tolerances (tests/test_fp64_acceptance.py);
+ * the tables are the same float values in both builds. */
+#ifdef ORACLE_FP64
+typedef double real_t;
+#define R_FMA(a, b, c) fma((a), (b), (c))
+#define R_SQRT(x) sqrt(x)
+#define R_FLOOR(x) floor(x)
+#define R_LOG(x) log(x)
+#define R_EXP(x) exp(x)
+static void R_SINCOS2PI(double t, double *s, double *c) {
+  const double a = 6.283185307179586476925286766559 * t;
+  *s = sin(a); *c = cos(a);
+}
+#else
+typedef float real_t;
+#define R_FMA(a, b, c) fmaf((a), (b), (c))
+#define R_SQRT(x) sqrtf(x)
+#define R_FLOOR(x) floorf(x)
+#define R_LOG(x) o_logf(x)
+#define R_EXP(x) o_expf(x)
+#define R_SINCOS2PI(t, s, c) o_sincos2pi((t), (s), (c))
+#endif
+
 /* ------------------------------------------------------------------ Philox4x32-10 */
 
 typedef struct {
@@ -155,17 +183,17 @@ static void rng_init(rng_t *r, uint64_t seed, uint64_t history) {
 static void rng_begin(rng_t *r) { r->pos = 4; }
 
 /* uniform in (0,1): 24 random bits, centred in their bin */
-static float rng_uniform(rng_t *r) {
+static real_t rng_uniform(rng_t *r) {
   if (r->pos == 4) {
     philox_block(r->key, r->ctr, r->out);
     r->ctr[2] += 1u;
     r->pos = 0;
   }
   uint32_t x = r->out[r->pos++];
-  return (float)(x >> 8) * 5.9604644775390625e-8f + 2.98023223876953125e-8f;
+  return (real_t)(x >> 8) * 5.9604644775390625e-8f + 2.98023223876953125e-8f;
 }
 
-/* ------------------------------------------------------------------ model (float copies) */
+/* ------------------------------------------------------------------ model (real_t copies) */
 
 #define ORACLE_MAX_PHSP 4
 #define ORACLE_MAX_DOSE 4
@@ -182,16 +210,16 @@ static float rng_uniform(rng_t *r) {
 #define K_PER_MEV 268.17264f /* photon wave number (1/bohr) per MeV */
 #define C_MM_PER_NS 299.792458f
 
-typedef struct { float m[9]; float t[3]; } affine_t; /* y = m x + t */
+typedef struct { real_t m[9]; real_t t[3]; } affine_t; /* y = m x + t */
 
 typedef struct {
   gate_b200_source d;
   affine_t pos;      /* local -> world */
-  float dir_rot[9];
-  float cos_tmin, cos_tmax, phi0_turn, dphi_turn;
-  float sin2_tmin, sin2_tmax, dir_sx, dir_sy;
-  float mom[3], focus[3];
-  float *spec_e, *spec_cdf;
+  real_t dir_rot[9];
+  real_t cos_tmin, cos_tmax, phi0_turn, dphi_turn;
+  real_t sin2_tmin, sin2_tmax, dir_sx, dir_sy;
+  real_t mom[3], focus[3];
+  float *spec_e, *spec_cdf;   /* as handed to the device */
 } osource_t;
 
 typedef struct {
@@ -201,12 +229,12 @@ typedef struct {
   double *grid[5];
   /* track-length estimator (GateTLEDoseActor): tle = 1, aligned = the grid is the image grid */
   int tle, aligned;
-  float tle_thr;
-  float *muen;       /* [nmat][ne] mu_en/rho, cm2/g */
+  real_t tle_thr;
+  float *muen;        /* [nmat][ne] mu_en/rho, cm2/g */
 } odose_t;
 
 typedef struct {
-  float half[3];
+  real_t half[3];
   affine_t w2b;
   int steps;
   uint64_t capacity;
@@ -218,37 +246,37 @@ struct oracle_engine {
   uint64_t seed;
   /* tables */
   int nmat, ne, nq, pair_mode;
-  float ln_emin, inv_dlne, e_cut, e_min, e_max;
-  float ln_q2min, inv_dlnq2;
-  float *dens, *mu, *cph, *cco, *cra, *maj, *q2n, *ray, *sf;
+  real_t ln_emin, inv_dlne, e_cut, e_min, e_max;
+  real_t ln_q2min, inv_dlnq2;
+  float *dens, *mu, *cph, *cco, *cra, *maj, *q2n, *ray, *sf;   /* tables: the float values the device holds */
   /* geometry */
-  float wh[3];
+  real_t wh[3];
   int world_mat;
   int has_vol, n[3], label_bytes;
-  float half[3], inv_sp[3], sp[3], hs[3];
+  real_t half[3], inv_sp[3], sp[3], hs[3];
   affine_t w2v;
   void *labels;
   /* actors, sources */
   int nsrc; osource_t *src;
   int ndose; odose_t dose[ORACLE_MAX_DOSE];
   int ntle;            /* dose actors that are track-length estimators */
-  float tle_emin;      /* max energy_min over them */
-  float tle_thr_max;   /* max threshold over them */
+  real_t tle_emin;      /* max energy_min over them */
+  real_t tle_thr_max;   /* max threshold over them */
   int nphsp; ophsp_t phsp[ORACLE_MAX_PHSP];
   gate_b200_stats stats;
   char err[256];
 };
 
-typedef struct { int key; float e; float d; int n; } dep_t;
+typedef struct { int key; real_t e; real_t d; int n; } dep_t;
 
 typedef struct {
   oracle_engine *g;
   rng_t rng;
-  float p[3], d[3];  /* world frame in WORLD, phantom frame in PHANTOM */
-  float E, w, path;
+  real_t p[3], d[3];  /* world frame in WORLD, phantom frame in PHANTOM */
+  real_t E, w, path;
   int in_phantom;
-  int ie; float fe;  /* energy bin + fraction */
-  float seg;         /* path since last step point inside the phantom */
+  int ie; real_t fe;  /* energy bin + fraction */
+  real_t seg;         /* path since last step point inside the phantom */
   int inside_plane[ORACLE_MAX_PHSP];
   int stored;
   uint64_t hist;
@@ -260,53 +288,53 @@ typedef struct {
 
 static void aff_from_d(affine_t *a, const double m12[12]) {
   for (int r = 0; r < 3; ++r) {
-    for (int c = 0; c < 3; ++c) a->m[3 * r + c] = (float)m12[4 * r + c];
-    a->t[r] = (float)m12[4 * r + 3];
+    for (int c = 0; c < 3; ++c) a->m[3 * r + c] = (real_t)m12[4 * r + c];
+    a->t[r] = (real_t)m12[4 * r + 3];
   }
 }
-static void aff_apply(const affine_t *a, const float x[3], float y[3]) {
+static void aff_apply(const affine_t *a, const real_t x[3], real_t y[3]) {
   for (int r = 0; r < 3; ++r)
     y[r] = a->m[3 * r] * x[0] + a->m[3 * r + 1] * x[1] + a->m[3 * r + 2] * x[2] + a->t[r];
 }
-static void rot_apply(const float m[9], const float x[3], float y[3]) {
+static void rot_apply(const real_t m[9], const real_t x[3], real_t y[3]) {
   for (int r = 0; r < 3; ++r) y[r] = m[3 * r] * x[0] + m[3 * r + 1] * x[1] + m[3 * r + 2] * x[2];
 }
 /* inverse of a rigid transform y = m x + t :  x = m^T (y - t) */
-static void aff_apply_inv(const affine_t *a, const float y[3], float x[3]) {
-  float v[3] = {y[0] - a->t[0], y[1] - a->t[1], y[2] - a->t[2]};
+static void aff_apply_inv(const affine_t *a, const real_t y[3], real_t x[3]) {
+  real_t v[3] = {y[0] - a->t[0], y[1] - a->t[1], y[2] - a->t[2]};
   for (int c = 0; c < 3; ++c) x[c] = a->m[c] * v[0] + a->m[3 + c] * v[1] + a->m[6 + c] * v[2];
 }
-static void rot_apply_inv(const float m[9], const float y[3], float x[3]) {
+static void rot_apply_inv(const real_t m[9], const real_t y[3], real_t x[3]) {
   for (int c = 0; c < 3; ++c) x[c] = m[c] * y[0] + m[3 + c] * y[1] + m[6 + c] * y[2];
 }
 
 /* slab test against an origin-centred box; returns 1 on hit with entry (>=0) and exit
  * distances and the axes of the entry / exit faces (-1 when the start point is inside).
  * A zero-length chord (touching a face from outside) is a miss. */
-static int ray_box_ax(const float p[3], const float d[3], const float h[3], float *t_in, float *t_out,
+static int ray_box_ax(const real_t p[3], const real_t d[3], const real_t h[3], real_t *t_in, real_t *t_out,
                       int *a_in, int *a_out) {
-  float tmin = -BIG, tmax = BIG;
+  real_t tmin = -BIG, tmax = BIG;
   int ain = -1, aout = -1;
   for (int a = 0; a < 3; ++a) {
     if (d[a] != 0.0f) {
-      float inv = 1.0f / d[a];
-      float t1 = (-h[a] - p[a]) * inv;
-      float t2 = (h[a] - p[a]) * inv;
-      if (t1 > t2) { float s = t1; t1 = t2; t2 = s; }
+      real_t inv = 1.0f / d[a];
+      real_t t1 = (-h[a] - p[a]) * inv;
+      real_t t2 = (h[a] - p[a]) * inv;
+      if (t1 > t2) { real_t s = t1; t1 = t2; t2 = s; }
       if (t1 > tmin) { tmin = t1; ain = a; }
       if (t2 < tmax) { tmax = t2; aout = a; }
     } else if (p[a] < -h[a] || p[a] > h[a]) {
       return 0;
     }
   }
-  float t0 = tmin > 0.0f ? tmin : 0.0f;
+  real_t t0 = tmin > 0.0f ? tmin : 0.0f;
   if (tmax <= t0) return 0;
   *t_in = t0; *t_out = tmax;
   *a_in = tmin > 0.0f ? ain : -1;
   *a_out = aout;
   return 1;
 }
-static int ray_box(const float p[3], const float d[3], const float h[3], float *t_in, float *t_out) {
+static int ray_box(const real_t p[3], const real_t d[3], const real_t h[3], real_t *t_in, real_t *t_out) {
   int ai, ao;
   return ray_box_ax(p, d, h, t_in, t_out, &ai, &ao);
 }
@@ -314,31 +342,31 @@ static int ray_box(const float p[3], const float d[3], const float h[3], float *
 /* Put coordinate `a` just inside (sign -1) or just outside (+1) the face the ray crosses, so
  * that the slab test and the voxel-index test agree about which side the point is on even at
  * grazing incidence (a push along the ray can be smaller than one ulp of the coordinate). */
-static void snap_to_face(float p[3], const float d[3], const float h[3], int a, int outward) {
+static void snap_to_face(real_t p[3], const real_t d[3], const real_t h[3], int a, int outward) {
   if (a < 0) return;
-  float face = outward ? (h[a] * (1.0f + 1.0e-6f) + 1.0e-5f) : (h[a] * (1.0f - 1.0e-6f) - 1.0e-5f);
+  real_t face = outward ? (h[a] * (1.0f + 1.0e-6f) + 1.0e-5f) : (h[a] * (1.0f - 1.0e-6f) - 1.0e-5f);
   if (outward) p[a] = d[a] > 0.0f ? face : -face;
   else p[a] = d[a] > 0.0f ? -face : face;
 }
 
-static int inside_box(const float p[3], const float h[3]) {
+static int inside_box(const real_t p[3], const real_t h[3]) {
   return p[0] > -h[0] && p[0] < h[0] && p[1] > -h[1] && p[1] < h[1] && p[2] > -h[2] && p[2] < h[2];
 }
 
 /* ------------------------------------------------------------------ table access */
 
-static void energy_bin(const oracle_engine *g, float E, int *ie, float *fe) {
-  float t = (o_logf(E) - g->ln_emin) * g->inv_dlne;
+static void energy_bin(const oracle_engine *g, real_t E, int *ie, real_t *fe) {
+  real_t t = (R_LOG(E) - g->ln_emin) * g->inv_dlne;
   if (t < 0.0f) t = 0.0f;
   int i = (int)t;
   if (i > g->ne - 2) i = g->ne - 2;
-  float f = t - (float)i;
+  real_t f = t - (real_t)i;
   if (f > 1.0f) f = 1.0f;
   *ie = i; *fe = f;
 }
-static float tab(const float *t, int ne, int m, int ie, float fe) {
+static real_t tab(const float *t, int ne, int m, int ie, real_t fe) {
   const float *r = t + (size_t)m * ne + ie;
-  return fmaf(fe, r[1] - r[0], r[0]);
+  return R_FMA(fe, (real_t)r[1] - (real_t)r[0], (real_t)r[0]);
 }
 
 /* ------------------------------------------------------------------ scoring */
@@ -393,7 +421,7 @@ static void tle_flush(hist_t *h) {
   }
   h->nlist = 0;
 }
-static void tle_table_add(hist_t *h, int key, float e, float d, int n) {
+static void tle_table_add(hist_t *h, int key, real_t e, real_t d, int n) {
   uint32_t hh = ((uint32_t)key * 2654435761u) >> 20;   /* 32 - log2(TLE_H) */
   for (;;) {
     dep_t *b = &h->ttab[hh];
@@ -416,7 +444,7 @@ static void tle_table_add(hist_t *h, int key, float e, float d, int n) {
 /* deposit e (already weighted) at the current phantom-frame point, material m.  e_tle: flight energy
  * of the gamma whose secondaries deposit here (a TLE actor ignores them while that gamma scores by
  * track length, GateTLEDoseActor.cpp:236-243); BIG for a gamma absorbed below the cut (always scored). */
-static void deposit(hist_t *h, float e, int m, int vix, int viy, int viz, float e_tle) {
+static void deposit(hist_t *h, real_t e, int m, int vix, int viy, int viz, real_t e_tle) {
   oracle_engine *g = h->g;
   h->st.edep_total_MeV += (double)e;
   h->st.deposits++;
@@ -428,41 +456,41 @@ static void deposit(hist_t *h, float e, int m, int vix, int viy, int viz, float 
   for (int a = 0; a < g->ndose; ++a) {
     odose_t *D = &g->dose[a];
     if (D->tle && e_tle <= D->tle_thr) continue;
-    float pos[3] = {h->p[0], h->p[1], h->p[2]};
+    real_t pos[3] = {h->p[0], h->p[1], h->p[2]};
     if (D->hit_type != GATE_B200_HIT_POST) {
       /* GateDoseActor.cpp:144-178: pre/random/middle between the Geant4 pre and post step
        * points; the Geant4 step starts at the voxel entry or at the previous interaction */
-      float back = h->seg;
+      real_t back = h->seg;
       const int vi[3] = {vix, viy, viz};
       for (int ax = 0; ax < 3; ++ax) {
-        float dd = h->d[ax];
+        real_t dd = h->d[ax];
         if (dd > 0.0f) {
-          float lo = -g->half[ax] + (float)vi[ax] * g->sp[ax];
-          float tb = (h->p[ax] - lo) / dd;
+          real_t lo = -g->half[ax] + (real_t)vi[ax] * g->sp[ax];
+          real_t tb = (h->p[ax] - lo) / dd;
           if (tb < back) back = tb;
         } else if (dd < 0.0f) {
-          float hi = -g->half[ax] + (float)(vi[ax] + 1) * g->sp[ax];
-          float tb = (h->p[ax] - hi) / dd;
+          real_t hi = -g->half[ax] + (real_t)(vi[ax] + 1) * g->sp[ax];
+          real_t tb = (h->p[ax] - hi) / dd;
           if (tb < back) back = tb;
         }
       }
       if (back < 0.0f) back = 0.0f;
-      float fr = 1.0f;
+      real_t fr = 1.0f;
       if (D->hit_type == GATE_B200_HIT_RANDOM) fr = 1.0f - rng_uniform(&h->rng);
       else if (D->hit_type == GATE_B200_HIT_MIDDLE) fr = 0.5f;
-      float bk = back * fr;
+      real_t bk = back * fr;
       for (int ax = 0; ax < 3; ++ax) pos[ax] = h->p[ax] - h->d[ax] * bk;
     }
-    float c[3];
+    real_t c[3];
     aff_apply(&D->v2i, pos, c);
     /* itk::ImageBase::TransformPhysicalPointToIndex: round half up, then region test */
-    float fx = floorf(c[0] + 0.5f), fy = floorf(c[1] + 0.5f), fz = floorf(c[2] + 0.5f);
-    if (fx < 0.0f || fy < 0.0f || fz < 0.0f || fx >= (float)D->size[0] || fy >= (float)D->size[1] ||
-        fz >= (float)D->size[2])
+    real_t fx = R_FLOOR(c[0] + 0.5f), fy = R_FLOOR(c[1] + 0.5f), fz = R_FLOOR(c[2] + 0.5f);
+    if (fx < 0.0f || fy < 0.0f || fz < 0.0f || fx >= (real_t)D->size[0] || fy >= (real_t)D->size[1] ||
+        fz >= (real_t)D->size[2])
       continue;
     int v = (int)fx + D->size[0] * ((int)fy + D->size[1] * (int)fz);
     int key = (int)(((uint32_t)a << 28) | (uint32_t)v);
-    float dd = e / g->dens[m];
+    real_t dd = e / g->dens[m];
     if (D->tle && (D->flags & (GATE_B200_SCORE_EDEP_SQ | GATE_B200_SCORE_DOSE_SQ))) {
       tle_table_add(h, key, e, dd, 1);
       continue;
@@ -485,31 +513,31 @@ static void deposit(hist_t *h, float e, int m, int vix, int viy, int viz, float 
 
 /* ------------------------------------------------------------------ direction change */
 
-static void rotate_dir(float d[3], float cost, float sint, float sphi, float cphi) {
-  float u = d[0], v = d[1], w = d[2];
-  float nu, nv, nw;
-  float aw = w < 0.0f ? -w : w;
+static void rotate_dir(real_t d[3], real_t cost, real_t sint, real_t sphi, real_t cphi) {
+  real_t u = d[0], v = d[1], w = d[2];
+  real_t nu, nv, nw;
+  real_t aw = w < 0.0f ? -w : w;
   if (aw < 0.99999f) {
-    float sz = sqrtf(1.0f - w * w);
-    float a = sint / sz;
+    real_t sz = R_SQRT(1.0f - w * w);
+    real_t a = sint / sz;
     nu = u * cost + a * (u * w * cphi - v * sphi);
     nv = v * cost + a * (v * w * cphi + u * sphi);
     nw = w * cost - sint * sz * cphi;
   } else {
-    float sg = w < 0.0f ? -1.0f : 1.0f;
+    real_t sg = w < 0.0f ? -1.0f : 1.0f;
     nu = sint * cphi; nv = sint * sphi; nw = sg * cost;
   }
-  float inv = 1.0f / sqrtf(nu * nu + nv * nv + nw * nw);
+  real_t inv = 1.0f / R_SQRT(nu * nu + nv * nv + nw * nw);
   d[0] = nu * inv; d[1] = nv * inv; d[2] = nw * inv;
 }
 
 /* ------------------------------------------------------------------ momentum-transfer tables */
 
-static int q2_segment(const oracle_engine *g, float q2) {
+static int q2_segment(const oracle_engine *g, real_t q2) {
   /* largest j with q2n[j] <= q2, -1 if below the first node, nq-1 if above the last */
   if (q2 < g->q2n[0]) return -1;
   if (q2 >= g->q2n[g->nq - 1]) return g->nq - 1;
-  float t = (o_logf(q2) - g->ln_q2min) * g->inv_dlnq2;
+  real_t t = (R_LOG(q2) - g->ln_q2min) * g->inv_dlnq2;
   int j = (int)t;
   if (j < 0) j = 0;
   if (j > g->nq - 2) j = g->nq - 2;
@@ -517,11 +545,11 @@ static int q2_segment(const oracle_engine *g, float q2) {
   while (j > 0 && g->q2n[j] > q2) --j;
   return j;
 }
-static float interp_q2(const oracle_engine *g, const float *row, float q2) {
+static real_t interp_q2(const oracle_engine *g, const float *row, real_t q2) {
   int j = q2_segment(g, q2);
   if (j < 0) return row[0] * (q2 / g->q2n[0]);
   if (j >= g->nq - 1) return row[g->nq - 1];
-  float f = (q2 - g->q2n[j]) / (g->q2n[j + 1] - g->q2n[j]);
+  real_t f = (q2 - g->q2n[j]) / (g->q2n[j + 1] - g->q2n[j]);
   return row[j] + f * (row[j + 1] - row[j]);
 }
 
@@ -533,11 +561,11 @@ static void update_energy(hist_t *h) { energy_bin(h->g, h->E, &h->ie, &h->fe); }
  * variate rescaled, v = (u * majorant) / mu_total(material) (conditional on acceptance this is
  * uniform, so no extra random number is needed); in the world it is the second uniform of the
  * flight block.  Returns 0 phot, 1 compt, 2 rayl, 3 conv. */
-static int select_process(hist_t *h, int m, float v) {
+static int select_process(hist_t *h, int m, real_t v) {
   oracle_engine *g = h->g;
-  float pph = tab(g->cph, g->ne, m, h->ie, h->fe);
-  float pco = tab(g->cco, g->ne, m, h->ie, h->fe);
-  float pra = tab(g->cra, g->ne, m, h->ie, h->fe);
+  real_t pph = tab(g->cph, g->ne, m, h->ie, h->fe);
+  real_t pco = tab(g->cco, g->ne, m, h->ie, h->fe);
+  real_t pra = tab(g->cra, g->ne, m, h->ie, h->fe);
   h->st.steps++;
   if (v < pph) return 0;
   if (v < pco) return 1;
@@ -546,7 +574,7 @@ static int select_process(hist_t *h, int m, float v) {
 }
 
 /* One real interaction of kind proc in material m; returns 1 if the photon survives. */
-static int interact(hist_t *h, int proc, int m, int vix, int viy, int viz, float pend_p[3], float pend_d[3],
+static int interact(hist_t *h, int proc, int m, int vix, int viy, int viz, real_t pend_p[3], real_t pend_d[3],
                     int *pend) {
   oracle_engine *g = h->g;
   if (proc == 0) { /* photoelectric: everything stays here (kerma, fluorescence not tracked) */
@@ -557,49 +585,49 @@ static int interact(hist_t *h, int proc, int m, int vix, int viy, int viz, float
   }
   if (proc == 1) { /* Compton: Klein-Nishina composition-rejection x scattering function */
     h->st.n_compt++;
-    float E = h->E;
-    float k = E / MC2;
-    float eps0 = 1.0f / (1.0f + 2.0f * k);
-    float eps0sq = eps0 * eps0;
-    float alpha1 = -o_logf(eps0);
-    float alpha2 = alpha1 + 0.5f * (1.0f - eps0sq);
-    float kq = K_PER_MEV * E;
-    float two_kq2 = 2.0f * kq * kq;
+    real_t E = h->E;
+    real_t k = E / MC2;
+    real_t eps0 = 1.0f / (1.0f + 2.0f * k);
+    real_t eps0sq = eps0 * eps0;
+    real_t alpha1 = -R_LOG(eps0);
+    real_t alpha2 = alpha1 + 0.5f * (1.0f - eps0sq);
+    real_t kq = K_PER_MEV * E;
+    real_t two_kq2 = 2.0f * kq * kq;
     const float *sfrow = g->sf + (size_t)m * g->nq;
-    float eps = 1.0f, onecost = 0.0f, sint2 = 0.0f;
+    real_t eps = 1.0f, onecost = 0.0f, sint2 = 0.0f;
     for (int it = 0; it < 100000; ++it) {
       /* one trial = one call of the device's Compton phase: it owns two Philox blocks, the
        * first feeds the trial (4 uniforms, all drawn), the second the final state */
       uint32_t b0 = h->rng.ctr[2];
       rng_begin(&h->rng);
-      float u1 = rng_uniform(&h->rng), u2 = rng_uniform(&h->rng), u3 = rng_uniform(&h->rng);
-      float u4 = rng_uniform(&h->rng);
-      float epssq;
+      real_t u1 = rng_uniform(&h->rng), u2 = rng_uniform(&h->rng), u3 = rng_uniform(&h->rng);
+      real_t u4 = rng_uniform(&h->rng);
+      real_t epssq;
       int ok = 1;
       if (alpha1 > alpha2 * u1) {
-        eps = o_expf(-alpha1 * u2);
+        eps = R_EXP(-alpha1 * u2);
         epssq = eps * eps;
       } else {
         epssq = eps0sq + (1.0f - eps0sq) * u2;
-        eps = sqrtf(epssq);
+        eps = R_SQRT(epssq);
       }
       onecost = (1.0f - eps) / (eps * k);
       sint2 = onecost * (2.0f - onecost);
-      float grej = 1.0f - eps * sint2 / (1.0f + epssq);
+      real_t grej = 1.0f - eps * sint2 / (1.0f + epssq);
       if (grej < u3) ok = 0;
       if (ok) {
-        float sfv = interp_q2(g, sfrow, two_kq2 * onecost);
+        real_t sfv = interp_q2(g, sfrow, two_kq2 * onecost);
         if (u4 > sfv) ok = 0;
       }
       if (ok) break;
       h->rng.ctr[2] = b0 + 2u; /* rejected: the rest of the call's blocks is discarded */
       h->rng.pos = 4;
     }
-    float cost = 1.0f - onecost;
-    float sint = sqrtf(sint2 > 0.0f ? sint2 : 0.0f);
-    float sphi, cphi;
-    o_sincos2pi(rng_uniform(&h->rng), &sphi, &cphi);
-    float E1 = eps * E;
+    real_t cost = 1.0f - onecost;
+    real_t sint = R_SQRT(sint2 > 0.0f ? sint2 : 0.0f);
+    real_t sphi, cphi;
+    R_SINCOS2PI(rng_uniform(&h->rng), &sphi, &cphi);
+    real_t E1 = eps * E;
     deposit(h, (E - E1) * h->w, m, vix, viy, viz, E);
     rotate_dir(h->d, cost, sint, sphi, cphi);
     h->E = E1;
@@ -614,16 +642,16 @@ static int interact(hist_t *h, int proc, int m, int vix, int viy, int viz, float
   if (proc == 2) { /* Rayleigh: q2 from the cumulative squared form factor, (1+cos^2)/2 test */
     h->st.n_rayl++;
     rng_begin(&h->rng);
-    float kq = K_PER_MEV * h->E;
-    float kq2 = kq * kq;
+    real_t kq = K_PER_MEV * h->E;
+    real_t kq2 = kq * kq;
     const float *A = g->ray + (size_t)m * g->nq;
-    float q2max = 4.0f * kq2;
+    real_t q2max = 4.0f * kq2;
     int jmax = q2_segment(g, q2max);
-    float amax = interp_q2(g, A, q2max);
-    float cost = 1.0f;
+    real_t amax = interp_q2(g, A, q2max);
+    real_t cost = 1.0f;
     for (int it = 0; it < 1000; ++it) {
-      float target = rng_uniform(&h->rng) * amax;
-      float q2;
+      real_t target = rng_uniform(&h->rng) * amax;
+      real_t q2;
       if (target < A[0]) {
         q2 = g->q2n[0] * (target / A[0]);
       } else {
@@ -634,20 +662,20 @@ static int interact(hist_t *h, int proc, int m, int vix, int viy, int viz, float
             int mid = (lo + hi) >> 1;
             if (A[mid] <= target) lo = mid; else hi = mid;
           }
-        float den = A[lo + 1] - A[lo];
-        float f = den > 0.0f ? (target - A[lo]) / den : 0.0f;
+        real_t den = A[lo + 1] - A[lo];
+        real_t f = den > 0.0f ? (target - A[lo]) / den : 0.0f;
         if (f > 1.0f) f = 1.0f;
         q2 = g->q2n[lo] + f * (g->q2n[lo + 1] - g->q2n[lo]);
       }
       if (q2 > q2max) q2 = q2max;
       cost = 1.0f - q2 / (2.0f * kq2);
       if (cost < -1.0f) cost = -1.0f;
-      float u2 = rng_uniform(&h->rng);
+      real_t u2 = rng_uniform(&h->rng);
       if (0.5f * (1.0f + cost * cost) >= u2) break;
     }
-    float sint = sqrtf(1.0f - cost * cost);
-    float sphi, cphi;
-    o_sincos2pi(rng_uniform(&h->rng), &sphi, &cphi);
+    real_t sint = R_SQRT(1.0f - cost * cost);
+    real_t sphi, cphi;
+    R_SINCOS2PI(rng_uniform(&h->rng), &sphi, &cphi);
     rotate_dir(h->d, cost, sint, sphi, cphi);
     h->seg = 0.0f;
     return 1;
@@ -662,10 +690,10 @@ static int interact(hist_t *h, int proc, int m, int vix, int viy, int viz, float
   }
   deposit(h, (h->E - 2.0f * MC2) * h->w, m, vix, viy, viz, h->E);
   {
-    float cost = 2.0f * rng_uniform(&h->rng) - 1.0f;
-    float sint = sqrtf(1.0f - cost * cost);
-    float sphi, cphi;
-    o_sincos2pi(rng_uniform(&h->rng), &sphi, &cphi);
+    real_t cost = 2.0f * rng_uniform(&h->rng) - 1.0f;
+    real_t sint = R_SQRT(1.0f - cost * cost);
+    real_t sphi, cphi;
+    R_SINCOS2PI(rng_uniform(&h->rng), &sphi, &cphi);
     h->d[0] = sint * cphi; h->d[1] = sint * sphi; h->d[2] = cost;
     h->E = MC2;
     h->seg = 0.0f;
@@ -679,14 +707,14 @@ static int interact(hist_t *h, int proc, int m, int vix, int viy, int viz, float
 
 /* ------------------------------------------------------------------ primaries */
 
-static float gauss(rng_t *r) {
-  float u1 = rng_uniform(r), u2 = rng_uniform(r);
-  float s, c;
-  o_sincos2pi(u2, &s, &c);
-  return sqrtf(-2.0f * o_logf(u1)) * c;
+static real_t gauss(rng_t *r) {
+  real_t u1 = rng_uniform(r), u2 = rng_uniform(r);
+  real_t s, c;
+  R_SINCOS2PI(u2, &s, &c);
+  return R_SQRT(-2.0f * R_LOG(u1)) * c;
 }
 
-static int lower_bound_f(const float *a, int n, float p) { /* first i with a[i] >= p */
+static int lower_bound_f(const float *a, int n, real_t p) { /* first i with a[i] >= p */
   int lo = 0, hi = n;
   while (lo < hi) {
     int mid = (lo + hi) >> 1;
@@ -698,8 +726,8 @@ static int lower_bound_f(const float *a, int n, float p) { /* first i with a[i] 
 static void generate_primary(hist_t *h, const osource_t *s) {
   rng_t *r = &h->rng;
   const gate_b200_source *d = &s->d;
-  float l[3] = {0.0f, 0.0f, 0.0f};
-  float ed[3] = {0.0f, 0.0f, 1.0f}, eE = 0.0f, ew = 1.0f;   /* phase-space entry */
+  real_t l[3] = {0.0f, 0.0f, 0.0f};
+  real_t ed[3] = {0.0f, 0.0f, 1.0f}, eE = 0.0f, ew = 1.0f;   /* phase-space entry */
   switch (d->pos_type) {
   case GATE_B200_POS_PHSP: {
     /* GatePhaseSpaceSource::GenerateOnePrimary (GatePhaseSpaceSource.cpp:137-166); entries are read
@@ -712,10 +740,10 @@ static void generate_primary(hist_t *h, const osource_t *s) {
   } break;
   case GATE_B200_POS_POINT: break;
   case GATE_B200_POS_BOX:
-    for (int a = 0; a < 3; ++a) l[a] = (2.0f * rng_uniform(r) - 1.0f) * (float)d->half_size[a];
+    for (int a = 0; a < 3; ++a) l[a] = (2.0f * rng_uniform(r) - 1.0f) * (real_t)d->half_size[a];
     break;
   case GATE_B200_POS_SPHERE: {
-    float R = (float)d->radius;
+    real_t R = (real_t)d->radius;
     for (;;) {
       for (int a = 0; a < 3; ++a) l[a] = (2.0f * rng_uniform(r) - 1.0f) * R;
       if (l[0] * l[0] + l[1] * l[1] + l[2] * l[2] <= R * R) break;
@@ -723,7 +751,7 @@ static void generate_primary(hist_t *h, const osource_t *s) {
   } break;
   case GATE_B200_POS_DISC:
   case GATE_B200_POS_CYLINDER: {
-    float R = (float)d->radius;
+    real_t R = (real_t)d->radius;
     if (R > 0.0f)
       for (;;) {
         l[0] = (2.0f * rng_uniform(r) - 1.0f) * R;
@@ -731,20 +759,20 @@ static void generate_primary(hist_t *h, const osource_t *s) {
         if (l[0] * l[0] + l[1] * l[1] <= R * R) break;
       }
     if (d->pos_type == GATE_B200_POS_DISC) {
-      if (d->sigma_x > 0.0) l[0] += gauss(r) * (float)d->sigma_x;
-      if (d->sigma_y > 0.0) l[1] += gauss(r) * (float)d->sigma_y;
+      if (d->sigma_x > 0.0) l[0] += gauss(r) * (real_t)d->sigma_x;
+      if (d->sigma_y > 0.0) l[1] += gauss(r) * (real_t)d->sigma_y;
     } else {
-      l[2] = (2.0f * rng_uniform(r) - 1.0f) * (float)d->half_size[2];
+      l[2] = (2.0f * rng_uniform(r) - 1.0f) * (real_t)d->half_size[2];
     }
   } break;
   case GATE_B200_POS_SURFACE_SPHERE: {
     /* G4SPSPosDistribution::GeneratePointsOnSurface, Sphere: theta = acos(1 - 2u), phi = 2 pi u' */
-    float R = (float)d->radius;
-    float cost = 1.0f - 2.0f * rng_uniform(r);
-    float s2 = 1.0f - cost * cost;
-    float sint = sqrtf(s2 > 0.0f ? s2 : 0.0f);
-    float sp, cp;
-    o_sincos2pi(rng_uniform(r), &sp, &cp);
+    real_t R = (real_t)d->radius;
+    real_t cost = 1.0f - 2.0f * rng_uniform(r);
+    real_t s2 = 1.0f - cost * cost;
+    real_t sint = R_SQRT(s2 > 0.0f ? s2 : 0.0f);
+    real_t sp, cp;
+    R_SINCOS2PI(rng_uniform(r), &sp, &cp);
     l[0] = R * sint * cp; l[1] = R * sint * sp; l[2] = R * cost;
   } break;
   case GATE_B200_POS_VOXELS: {
@@ -759,12 +787,12 @@ static void generate_primary(hist_t *h, const osource_t *s) {
     tries = 0;
     do { k = lower_bound_f(d->cdf_x + ((size_t)i * ny + j) * nx, nx, rng_uniform(r)); } while (k >= nx && ++tries < 1000);
     if (k >= nx) k = nx - 1;
-    l[0] = (float)d->vox_origin[0] + (float)k * (float)d->vox_spacing[0];
-    l[1] = (float)d->vox_origin[1] + (float)j * (float)d->vox_spacing[1];
-    l[2] = (float)d->vox_origin[2] + (float)i * (float)d->vox_spacing[2];
-    l[0] += (rng_uniform(r) - 0.5f) * (float)d->vox_spacing[0];
-    l[1] += (rng_uniform(r) - 0.5f) * (float)d->vox_spacing[1];
-    l[2] += (rng_uniform(r) - 0.5f) * (float)d->vox_spacing[2];
+    l[0] = (real_t)d->vox_origin[0] + (real_t)k * (real_t)d->vox_spacing[0];
+    l[1] = (real_t)d->vox_origin[1] + (real_t)j * (real_t)d->vox_spacing[1];
+    l[2] = (real_t)d->vox_origin[2] + (real_t)i * (real_t)d->vox_spacing[2];
+    l[0] += (rng_uniform(r) - 0.5f) * (real_t)d->vox_spacing[0];
+    l[1] += (rng_uniform(r) - 0.5f) * (real_t)d->vox_spacing[1];
+    l[2] += (rng_uniform(r) - 0.5f) * (real_t)d->vox_spacing[2];
   } break;
   }
   aff_apply(&s->pos, l, h->p);
@@ -772,14 +800,14 @@ static void generate_primary(hist_t *h, const osource_t *s) {
   switch (d->dir_type) {
   case GATE_B200_DIR_ISO: {
     /* G4SPSAngDistribution::GenerateIsotropicFlux: momentum = -(sin t cos p, sin t sin p, cos t) */
-    float cost = s->cos_tmin - rng_uniform(r) * (s->cos_tmin - s->cos_tmax);
-    float s2 = 1.0f - cost * cost;
-    float sint = sqrtf(s2 > 0.0f ? s2 : 0.0f);
-    float turn = s->phi0_turn + s->dphi_turn * rng_uniform(r);
-    turn = turn - floorf(turn);
-    float sp, cp;
-    o_sincos2pi(turn, &sp, &cp);
-    float v[3] = {-sint * cp, -sint * sp, -cost};
+    real_t cost = s->cos_tmin - rng_uniform(r) * (s->cos_tmin - s->cos_tmax);
+    real_t s2 = 1.0f - cost * cost;
+    real_t sint = R_SQRT(s2 > 0.0f ? s2 : 0.0f);
+    real_t turn = s->phi0_turn + s->dphi_turn * rng_uniform(r);
+    turn = turn - R_FLOOR(turn);
+    real_t sp, cp;
+    R_SINCOS2PI(turn, &sp, &cp);
+    real_t v[3] = {-sint * cp, -sint * sp, -cost};
     if (d->dir_relative) rot_apply(s->dir_rot, v, h->d);
     else { h->d[0] = v[0]; h->d[1] = v[1]; h->d[2] = v[2]; }
   } break;
@@ -787,37 +815,37 @@ static void generate_primary(hist_t *h, const osource_t *s) {
     h->d[0] = s->mom[0]; h->d[1] = s->mom[1]; h->d[2] = s->mom[2];
     break;
   case GATE_B200_DIR_FOCUSED: {
-    float v[3] = {s->focus[0] - h->p[0], s->focus[1] - h->p[1], s->focus[2] - h->p[2]};
-    float inv = 1.0f / sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    real_t v[3] = {s->focus[0] - h->p[0], s->focus[1] - h->p[1], s->focus[2] - h->p[2]};
+    real_t inv = 1.0f / R_SQRT(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
     h->d[0] = v[0] * inv; h->d[1] = v[1] * inv; h->d[2] = v[2] * inv;
   } break;
   case GATE_B200_DIR_COS: {
     /* G4SPSAngDistribution::GenerateCosineLawFlux: sin^2(theta) uniform between sin^2(min) and sin^2(max) */
-    float st2 = rng_uniform(r) * (s->sin2_tmax - s->sin2_tmin) + s->sin2_tmin;
-    float sint = sqrtf(st2 > 0.0f ? st2 : 0.0f);
-    float c2 = 1.0f - st2;
-    float cost = sqrtf(c2 > 0.0f ? c2 : 0.0f);
-    float turn = s->phi0_turn + s->dphi_turn * rng_uniform(r);
-    turn = turn - floorf(turn);
-    float sp, cp;
-    o_sincos2pi(turn, &sp, &cp);
-    float v[3] = {-sint * cp, -sint * sp, -cost};
+    real_t st2 = rng_uniform(r) * (s->sin2_tmax - s->sin2_tmin) + s->sin2_tmin;
+    real_t sint = R_SQRT(st2 > 0.0f ? st2 : 0.0f);
+    real_t c2 = 1.0f - st2;
+    real_t cost = R_SQRT(c2 > 0.0f ? c2 : 0.0f);
+    real_t turn = s->phi0_turn + s->dphi_turn * rng_uniform(r);
+    turn = turn - R_FLOOR(turn);
+    real_t sp, cp;
+    R_SINCOS2PI(turn, &sp, &cp);
+    real_t v[3] = {-sint * cp, -sint * sp, -cost};
     if (d->dir_relative) rot_apply(s->dir_rot, v, h->d);
     else { h->d[0] = v[0]; h->d[1] = v[1]; h->d[2] = v[2]; }
   } break;
   case GATE_B200_DIR_BEAM2D: {
     /* G4SPSAngDistribution::GenerateBeamFlux (beam2d): px, py ~ N(0, sigma), theta = |(px, py)|,
      * phi = atan2(py, px), momentum = -(sin t cos p, sin t sin p, cos t) with cos p = px / theta */
-    float px = gauss(r) * s->dir_sx;
-    float py = gauss(r) * s->dir_sy;
-    float th = sqrtf(px * px + py * py);
-    float v[3] = {0.0f, 0.0f, -1.0f};
+    real_t px = gauss(r) * s->dir_sx;
+    real_t py = gauss(r) * s->dir_sy;
+    real_t th = R_SQRT(px * px + py * py);
+    real_t v[3] = {0.0f, 0.0f, -1.0f};
     if (th != 0.0f) {
-      float turn = th * 0.15915494309189535f;
-      turn = turn - floorf(turn);
-      float st, ct;
-      o_sincos2pi(turn, &st, &ct);
-      float k = st / th;
+      real_t turn = th * 0.15915494309189535f;
+      turn = turn - R_FLOOR(turn);
+      real_t st, ct;
+      R_SINCOS2PI(turn, &st, &ct);
+      real_t k = st / th;
       v[0] = -(k * px); v[1] = -(k * py); v[2] = -ct;
     }
     if (d->dir_relative) rot_apply(s->dir_rot, v, h->d);
@@ -825,66 +853,66 @@ static void generate_primary(hist_t *h, const osource_t *s) {
   } break;
   case GATE_B200_DIR_PHSP: {
     /* direction / direction.mag(), then the rotation of the attached volume (GatePhaseSpaceSource.cpp:158-162) */
-    float inv = 1.0f / sqrtf(ed[0] * ed[0] + ed[1] * ed[1] + ed[2] * ed[2]);
-    float v[3] = {ed[0] * inv, ed[1] * inv, ed[2] * inv};
+    real_t inv = 1.0f / R_SQRT(ed[0] * ed[0] + ed[1] * ed[1] + ed[2] * ed[2]);
+    real_t v[3] = {ed[0] * inv, ed[1] * inv, ed[2] * inv};
     if (d->dir_relative) rot_apply(s->dir_rot, v, h->d);
     else { h->d[0] = v[0]; h->d[1] = v[1]; h->d[2] = v[2]; }
   } break;
   }
 
-  float E = 0.0f;
+  real_t E = 0.0f;
   switch (d->ene_type) {
   case GATE_B200_ENE_PHSP: E = eE; break;
-  case GATE_B200_ENE_MONO: E = (float)d->mono_MeV; break;
-  case GATE_B200_ENE_GAUSS: E = (float)d->mono_MeV + gauss(r) * (float)d->sigma_MeV; break;
+  case GATE_B200_ENE_MONO: E = (real_t)d->mono_MeV; break;
+  case GATE_B200_ENE_GAUSS: E = (real_t)d->mono_MeV + gauss(r) * (real_t)d->sigma_MeV; break;
   case GATE_B200_ENE_RANGE:
-    E = (float)d->e_min_MeV + rng_uniform(r) * ((float)d->e_max_MeV - (float)d->e_min_MeV);
+    E = (real_t)d->e_min_MeV + rng_uniform(r) * ((real_t)d->e_max_MeV - (real_t)d->e_min_MeV);
     break;
   case GATE_B200_ENE_SPECTRUM_DISCRETE: {
-    float p = rng_uniform(r);
+    real_t p = rng_uniform(r);
     int i = 0;
     while (i < d->n_spectrum - 1 && p >= s->spec_cdf[i]) ++i; /* IndexForProbability */
     E = s->spec_e[i];
   } break;
   case GATE_B200_ENE_SPECTRUM_HISTOGRAM: {
-    float p = rng_uniform(r);
+    real_t p = rng_uniform(r);
     int i = 0;
     while (i < d->n_spectrum - 1 && p >= s->spec_cdf[i]) ++i;
     E = s->spec_e[i] + rng_uniform(r) * (s->spec_e[i + 1] - s->spec_e[i]);
   } break;
   case GATE_B200_ENE_SPECTRUM_HISTOGRAM_LINEAR: {
     /* GateSPSEneDistribution.cpp:124-147 */
-    float p0 = rng_uniform(r);
+    real_t p0 = rng_uniform(r);
     int i = 0;
     while (i < d->n_spectrum - 2 && p0 >= s->spec_cdf[i]) ++i;
-    float a = (s->spec_e[i] + s->spec_e[i + 1]) * 0.5f;
-    float b = (s->spec_e[i + 1] + s->spec_e[i + 2]) * 0.5f;
-    float dd = s->spec_cdf[i + 1] - s->spec_cdf[i];
-    float ad = dd < 0.0f ? -dd : dd;
+    real_t a = (s->spec_e[i] + s->spec_e[i + 1]) * 0.5f;
+    real_t b = (s->spec_e[i + 1] + s->spec_e[i + 2]) * 0.5f;
+    real_t dd = s->spec_cdf[i + 1] - s->spec_cdf[i];
+    real_t ad = dd < 0.0f ? -dd : dd;
     if (ad < 1.1920929e-7f) {
       E = a + rng_uniform(r) * (b - a);
     } else {
-      float alpha = dd / (b - a);
-      float beta = s->spec_cdf[i] - alpha * a;
-      float norm = 0.5f * alpha * (b * b - a * a) + beta * (b - a);
-      float p = rng_uniform(r);
-      float sq = sqrtf((alpha * a + beta) * (alpha * a + beta) + 2.0f * alpha * norm * p);
-      float x = (-beta + sq) / alpha;
+      real_t alpha = dd / (b - a);
+      real_t beta = s->spec_cdf[i] - alpha * a;
+      real_t norm = 0.5f * alpha * (b * b - a * a) + beta * (b - a);
+      real_t p = rng_uniform(r);
+      real_t sq = R_SQRT((alpha * a + beta) * (alpha * a + beta) + 2.0f * alpha * norm * p);
+      real_t x = (-beta + sq) / alpha;
       E = ((x - a) * (x - b) <= 0.0f) ? x : (-beta - sq) / alpha;
     }
   } break;
   case GATE_B200_ENE_CDF: {
     /* GateSPSEneDistribution.cpp:38-49 */
-    float x = rng_uniform(r);
+    real_t x = rng_uniform(r);
     int idx = lower_bound_f(s->spec_cdf, d->n_spectrum, x) - 1;
     if (idx < 0) idx = 0;
     if (idx > d->n_spectrum - 2) idx = d->n_spectrum - 2;
-    float ratio = (x - s->spec_cdf[idx]) / (s->spec_cdf[idx + 1] - s->spec_cdf[idx]);
+    real_t ratio = (x - s->spec_cdf[idx]) / (s->spec_cdf[idx + 1] - s->spec_cdf[idx]);
     E = s->spec_e[idx] + ratio * (s->spec_e[idx + 1] - s->spec_e[idx]);
   } break;
   }
   h->E = E;
-  h->w = d->pos_type == GATE_B200_POS_PHSP ? ew * (float)d->weight : (float)d->weight;
+  h->w = d->pos_type == GATE_B200_POS_PHSP ? ew * (real_t)d->weight : (real_t)d->weight;
 }
 
 /* ------------------------------------------------------------------ phase space */
@@ -918,63 +946,63 @@ static void phsp_store(hist_t *h, int k, int flag) {
  * (GateTLEDoseActor::ScoreTLEDepositStep, GateTLEDoseActor.cpp:252-300).  The voxel walk is an
  * Amanatides-Woo traversal whose face distances are always computed from the integer voxel index.
  * The device runs the walk in calls of TLE_STEPS iterations, each on a fresh Philox block. */
-static void tle_march(hist_t *h, float to) {
+static void tle_march(hist_t *h, real_t to) {
   oracle_engine *g = h->g;
   if (!g->ntle || !(h->E <= g->tle_thr_max)) return;
-  const float t_end = h->seg + to;
-  float s[3], inv_d[3];
+  const real_t t_end = h->seg + to;
+  real_t s[3], inv_d[3];
   int i[3];
   for (int a = 0; a < 3; ++a) {
-    s[a] = fmaf(-h->d[a], h->seg, h->p[a]);
+    s[a] = R_FMA(-h->d[a], h->seg, h->p[a]);
     inv_d[a] = h->d[a] != 0.0f ? 1.0f / h->d[a] : 0.0f;
-    int v = (int)floorf(fmaf(s[a], g->inv_sp[a], g->hs[a]));
+    int v = (int)R_FLOOR(R_FMA(s[a], g->inv_sp[a], g->hs[a]));
     if (v < 0) v = 0;
     if (v > g->n[a] - 1) v = g->n[a] - 1;
     i[a] = v;
   }
-  const float kE = (0.1f * h->E) * h->w;
-  float tcur = 0.0f;
+  const real_t kE = (0.1f * h->E) * h->w;
+  real_t tcur = 0.0f;
   for (int it = 0;; ++it) {
     if (it % TLE_STEPS == 0) rng_begin(&h->rng);
-    float tn = BIG;
+    real_t tn = BIG;
     int ax = -1;
     for (int a = 0; a < 3; ++a) {
-      float face;
-      if (h->d[a] > 0.0f) face = fmaf((float)(i[a] + 1), g->sp[a], -g->half[a]);
-      else if (h->d[a] < 0.0f) face = fmaf((float)i[a], g->sp[a], -g->half[a]);
+      real_t face;
+      if (h->d[a] > 0.0f) face = R_FMA((real_t)(i[a] + 1), g->sp[a], -g->half[a]);
+      else if (h->d[a] < 0.0f) face = R_FMA((real_t)i[a], g->sp[a], -g->half[a]);
       else continue;
-      float tb = (face - s[a]) * inv_d[a];
+      real_t tb = (face - s[a]) * inv_d[a];
       if (tb < tn) { tn = tb; ax = a; }
     }
     const int last = !(tn < t_end);
-    const float tnext = last ? t_end : tn;
-    const float L = tnext - tcur;
+    const real_t tnext = last ? t_end : tn;
+    const real_t L = tnext - tcur;
     if (L > 0.0f) {
       const size_t flat = (size_t)i[0] + (size_t)g->n[0] * ((size_t)i[1] + (size_t)g->n[1] * (size_t)i[2]);
       const int m = g->label_bytes == 1 ? (int)((const uint8_t *)g->labels)[flat] : (int)((const uint16_t *)g->labels)[flat];
-      const float rho = g->dens[m];
+      const real_t rho = g->dens[m];
       h->st.tle_steps++;
       for (int a = 0; a < g->ndose; ++a) {
         odose_t *D = &g->dose[a];
         if (!D->tle || !(h->E <= D->tle_thr)) continue;
-        const float muen = tab(D->muen, g->ne, m, h->ie, h->fe);
-        const float e = ((kE * muen) * L) * rho;
-        const float dd = e / rho;
+        const real_t muen = tab(D->muen, g->ne, m, h->ie, h->fe);
+        const real_t e = ((kE * muen) * L) * rho;
+        const real_t dd = e / rho;
         int v;
         if (D->aligned) {
           v = (int)flat;
         } else {
-          float fr = 1.0f;
+          real_t fr = 1.0f;
           if (D->hit_type == GATE_B200_HIT_RANDOM) fr = rng_uniform(&h->rng);
           else if (D->hit_type == GATE_B200_HIT_MIDDLE) fr = 0.5f;
           else if (D->hit_type == GATE_B200_HIT_PRE) fr = 0.0f;
-          const float tp = fmaf(fr, L, tcur);
-          float pos[3] = {fmaf(h->d[0], tp, s[0]), fmaf(h->d[1], tp, s[1]), fmaf(h->d[2], tp, s[2])};
-          float c[3];
+          const real_t tp = R_FMA(fr, L, tcur);
+          real_t pos[3] = {R_FMA(h->d[0], tp, s[0]), R_FMA(h->d[1], tp, s[1]), R_FMA(h->d[2], tp, s[2])};
+          real_t c[3];
           aff_apply(&D->v2i, pos, c);
-          float fx = floorf(c[0] + 0.5f), fy = floorf(c[1] + 0.5f), fz = floorf(c[2] + 0.5f);
-          if (fx < 0.0f || fy < 0.0f || fz < 0.0f || fx >= (float)D->size[0] || fy >= (float)D->size[1] ||
-              fz >= (float)D->size[2])
+          real_t fx = R_FLOOR(c[0] + 0.5f), fy = R_FLOOR(c[1] + 0.5f), fz = R_FLOOR(c[2] + 0.5f);
+          if (fx < 0.0f || fy < 0.0f || fz < 0.0f || fx >= (real_t)D->size[0] || fy >= (real_t)D->size[1] ||
+              fz >= (real_t)D->size[2])
             continue;
           v = (int)fx + D->size[0] * ((int)fy + D->size[1] * (int)fz);
         }
@@ -998,19 +1026,19 @@ static void tle_march(hist_t *h, float to) {
 /* ------------------------------------------------------------------ one history */
 
 static void to_phantom(hist_t *h) {
-  float pl[3], dl[3];
+  real_t pl[3], dl[3];
   aff_apply(&h->g->w2v, h->p, pl);
   rot_apply(h->g->w2v.m, h->d, dl);
   for (int a = 0; a < 3; ++a) { h->p[a] = pl[a]; h->d[a] = dl[a]; }
 }
 static void to_world(hist_t *h) {
-  float pw[3], dw[3];
+  real_t pw[3], dw[3];
   aff_apply_inv(&h->g->w2v, h->p, pw);
   rot_apply_inv(h->g->w2v.m, h->d, dw);
   for (int a = 0; a < 3; ++a) { h->p[a] = pw[a]; h->d[a] = dw[a]; }
 }
 
-static void run_photon(hist_t *h, float pend_p[3], float pend_d[3], int *pend) {
+static void run_photon(hist_t *h, real_t pend_p[3], real_t pend_d[3], int *pend) {
   oracle_engine *g = h->g;
   int alive = 1;
   if (h->E < g->e_cut) { /* below the table: absorbed where it starts */
@@ -1027,26 +1055,26 @@ static void run_photon(hist_t *h, float pend_p[3], float pend_d[3], int *pend) {
               h->p[0], h->p[1], h->p[2], h->d[0], h->d[1], h->d[2], h->E);
 #endif
     if (!h->in_phantom) {
-      float t_exit, t0;
+      real_t t_exit, t0;
       rng_begin(&h->rng);
       if (!inside_box(h->p, g->wh) || !ray_box(h->p, h->d, g->wh, &t0, &t_exit)) {
         h->st.escaped++;
         return;
       }
       int ev = 0; /* 0 interact, 1 leave world, 2 enter phantom, 3+2k enter plane k, 4+2k leave plane k */
-      float mu = tab(g->mu, g->ne, g->world_mat, h->ie, h->fe);
-      float t_best = -o_logf(rng_uniform(&h->rng)) / mu;
+      real_t mu = tab(g->mu, g->ne, g->world_mat, h->ie, h->fe);
+      real_t t_best = -R_LOG(rng_uniform(&h->rng)) / mu;
       if (t_exit < t_best) { t_best = t_exit; ev = 1; }
       int ax_in = -1;
       if (g->has_vol) {
-        float pl[3], dl[3], ti, to;
+        real_t pl[3], dl[3], ti, to;
         int ai, ao;
         aff_apply(&g->w2v, h->p, pl);
         rot_apply(g->w2v.m, h->d, dl);
         if (ray_box_ax(pl, dl, g->half, &ti, &to, &ai, &ao) && ti < t_best) { t_best = ti; ev = 2; ax_in = ai; }
       }
       for (int k = 0; k < g->nphsp; ++k) {
-        float pb[3], db[3], ti, to;
+        real_t pb[3], db[3], ti, to;
         aff_apply(&g->phsp[k].w2b, h->p, pb);
         rot_apply(g->phsp[k].w2b.m, h->d, db);
         if (!ray_box(pb, db, g->phsp[k].half, &ti, &to)) {
@@ -1057,7 +1085,7 @@ static void run_photon(hist_t *h, float pend_p[3], float pend_d[3], int *pend) {
           if (to < t_best) { t_best = to; ev = 4 + 2 * k; }
         } else if (ti < t_best) { t_best = ti; ev = 3 + 2 * k; }
       }
-      float step = (ev >= 3) ? t_best + NUDGE : t_best;
+      real_t step = (ev >= 3) ? t_best + NUDGE : t_best;
       if (ev == 1) { h->st.escaped++; h->path += t_best; return; }
       for (int a = 0; a < 3; ++a) h->p[a] = h->p[a] + h->d[a] * step;
       h->path += step;
@@ -1085,22 +1113,22 @@ static void run_photon(hist_t *h, float pend_p[3], float pend_d[3], int *pend) {
       /* Woodcock delta tracking against the majorant of the materials in the volume.
        * One call = up to WOODCOCK_K tentative collisions fed by 2 Philox blocks: u[2k] gives
        * the flight distance of iteration k, u[2k+1] its acceptance test. */
-      float maj = fmaf(h->fe, g->maj[h->ie + 1] - g->maj[h->ie], g->maj[h->ie]);
-      float inv_maj = 1.0f / maj;
-      float u[2 * WOODCOCK_K];
+      real_t maj = R_FMA(h->fe, g->maj[h->ie + 1] - g->maj[h->ie], g->maj[h->ie]);
+      real_t inv_maj = 1.0f / maj;
+      real_t u[2 * WOODCOCK_K];
       rng_begin(&h->rng);
       for (int k = 0; k < 2 * WOODCOCK_K; ++k) u[k] = rng_uniform(&h->rng);
       for (int k = 0; k < WOODCOCK_K; ++k) {
-        float s = -o_logf(u[2 * k]) * inv_maj;
-        float q[3] = {fmaf(h->d[0], s, h->p[0]), fmaf(h->d[1], s, h->p[1]), fmaf(h->d[2], s, h->p[2])};
+        real_t s = -R_LOG(u[2 * k]) * inv_maj;
+        real_t q[3] = {R_FMA(h->d[0], s, h->p[0]), R_FMA(h->d[1], s, h->p[1]), R_FMA(h->d[2], s, h->p[2])};
         /* continuous voxel coordinate: q / spacing + n / 2 in one fused operation */
-        float fx = fmaf(q[0], g->inv_sp[0], g->hs[0]);
-        float fy = fmaf(q[1], g->inv_sp[1], g->hs[1]);
-        float fz = fmaf(q[2], g->inv_sp[2], g->hs[2]);
-        if (fx < 0.0f || fy < 0.0f || fz < 0.0f || fx >= (float)g->n[0] || fy >= (float)g->n[1] ||
-            fz >= (float)g->n[2]) {
+        real_t fx = R_FMA(q[0], g->inv_sp[0], g->hs[0]);
+        real_t fy = R_FMA(q[1], g->inv_sp[1], g->hs[1]);
+        real_t fz = R_FMA(q[2], g->inv_sp[2], g->hs[2]);
+        if (fx < 0.0f || fy < 0.0f || fz < 0.0f || fx >= (real_t)g->n[0] || fy >= (real_t)g->n[1] ||
+            fz >= (real_t)g->n[2]) {
           /* left the volume: restart from the exit point in the world frame */
-          float ti, to;
+          real_t ti, to;
           int ai, ao;
           if (!ray_box_ax(h->p, h->d, g->half, &ti, &to, &ai, &ao)) { to = 0.0f; ao = -1; }
           tle_march(h, to);
@@ -1120,8 +1148,8 @@ static void run_photon(hist_t *h, float pend_p[3], float pend_d[3], int *pend) {
         size_t flat = (size_t)ix + (size_t)g->n[0] * ((size_t)iy + (size_t)g->n[1] * (size_t)iz);
         int m = g->label_bytes == 1 ? (int)((const uint8_t *)g->labels)[flat]
                                     : (int)((const uint16_t *)g->labels)[flat];
-        float mu = tab(g->mu, g->ne, m, h->ie, h->fe);
-        float t = u[2 * k + 1] * maj;
+        real_t mu = tab(g->mu, g->ne, m, h->ie, h->fe);
+        real_t t = u[2 * k + 1] * maj;
         if (t <= mu) {
           int proc = select_process(h, m, t / mu);
           tle_march(h, 0.0f);
@@ -1149,18 +1177,18 @@ static void run_history(oracle_engine *g, const osource_t *s, uint64_t hist, gat
     trace->E0 = h.E;
     for (int a = 0; a < 3; ++a) { trace->p0[a] = h.p[a]; trace->d0[a] = h.d[a]; }
   }
-  float pend_p[3], pend_d[3];
+  real_t pend_p[3], pend_d[3];
   int pend = 0;
   /* region of the vertex */
   {
-    float pl[3];
+    real_t pl[3];
     h.in_phantom = 0;
     if (g->has_vol) {
       aff_apply(&g->w2v, h.p, pl);
       if (inside_box(pl, g->half)) { to_phantom(&h); h.in_phantom = 1; }
     }
     for (int k = 0; k < g->nphsp; ++k) {
-      float pb[3];
+      real_t pb[3];
       aff_apply(&g->phsp[k].w2b, h.p, pb);
       h.inside_plane[k] = (!h.in_phantom) && inside_box(pb, g->phsp[k].half);
     }
@@ -1169,7 +1197,7 @@ static void run_history(oracle_engine *g, const osource_t *s, uint64_t hist, gat
   if (pend) { /* second annihilation photon (pair_mode 1) */
     /* pend_* are expressed in the frame current at creation (1 = phantom, 2 = world): go back
      * to the world frame and find the region again */
-    float pw[3], dw[3];
+    real_t pw[3], dw[3];
     if (pend == 1) {
       aff_apply_inv(&g->w2v, pend_p, pw);
       rot_apply_inv(g->w2v.m, pend_d, dw);
@@ -1179,12 +1207,12 @@ static void run_history(oracle_engine *g, const osource_t *s, uint64_t hist, gat
     for (int a = 0; a < 3; ++a) { h.p[a] = pw[a]; h.d[a] = dw[a]; }
     h.E = MC2; h.seg = 0.0f; h.in_phantom = 0;
     if (g->has_vol) {
-      float pl[3];
+      real_t pl[3];
       aff_apply(&g->w2v, h.p, pl);
       if (inside_box(pl, g->half)) { to_phantom(&h); h.in_phantom = 1; }
     }
     for (int k = 0; k < g->nphsp; ++k) {
-      float pb[3];
+      real_t pb[3];
       aff_apply(&g->phsp[k].w2b, h.p, pb);
       h.inside_plane[k] = (!h.in_phantom) && inside_box(pb, g->phsp[k].half);
     }
@@ -1205,7 +1233,7 @@ static void run_history(oracle_engine *g, const osource_t *s, uint64_t hist, gat
   acc->tle_steps += h.st.tle_steps; acc->tle_entries += h.st.tle_entries; acc->tle_overflows += h.st.tle_overflows;
   if (trace) {
     trace->E_end = h.E;
-    trace->edep = (float)h.st.edep_total_MeV;
+    trace->edep = (real_t)h.st.edep_total_MeV;
     trace->n_tentative = (int)h.st.tentative_collisions;
     trace->n_interactions = (int)(h.st.n_phot + h.st.n_compt + h.st.n_rayl + h.st.n_conv);
   }
@@ -1247,15 +1275,15 @@ int oracle_set_tables(oracle_engine *g, const gate_b200_tables *t) {
   g->cph = dup_f(t->cum_phot, n); g->cco = dup_f(t->cum_compt, n); g->cra = dup_f(t->cum_rayl, n);
   g->ray = dup_f(t->rayl_cum_ff2, nqq); g->sf = dup_f(t->compt_sf, nqq);
   double le0 = log(t->e_min_MeV), le1 = log(t->e_max_MeV);
-  g->ln_emin = (float)le0;
-  g->inv_dlne = (float)((double)(g->ne - 1) / (le1 - le0));
-  g->e_cut = (float)t->e_cut_MeV; g->e_min = (float)t->e_min_MeV; g->e_max = (float)t->e_max_MeV;
+  g->ln_emin = (real_t)le0;
+  g->inv_dlne = (real_t)((double)(g->ne - 1) / (le1 - le0));
+  g->e_cut = (real_t)t->e_cut_MeV; g->e_min = (real_t)t->e_min_MeV; g->e_max = (real_t)t->e_max_MeV;
   double lq0 = log(t->q2_min), lq1 = log(t->q2_max);
-  g->ln_q2min = (float)lq0;
-  g->inv_dlnq2 = (float)((double)(g->nq - 1) / (lq1 - lq0));
+  g->ln_q2min = (real_t)lq0;
+  g->inv_dlnq2 = (real_t)((double)(g->nq - 1) / (lq1 - lq0));
   g->q2n = (float *)malloc(sizeof(float) * g->nq);
   for (int j = 0; j < g->nq; ++j)
-    g->q2n[j] = (float)exp(lq0 + (lq1 - lq0) * (double)j / (double)(g->nq - 1));
+    g->q2n[j] = (real_t)exp(lq0 + (lq1 - lq0) * (double)j / (double)(g->nq - 1));
   g->maj = (float *)calloc(g->ne, sizeof(float));
   return 0;
 }
@@ -1269,7 +1297,7 @@ static void build_majorant(oracle_engine *g) {
     if (m < g->nmat) present[m] = 1;
   }
   for (int i = 0; i < g->ne; ++i) {
-    float mx = 0.0f;
+    real_t mx = 0.0f;
     for (int m = 0; m < g->nmat; ++m)
       if (present[m] && g->mu[(size_t)m * g->ne + i] > mx) mx = g->mu[(size_t)m * g->ne + i];
     g->maj[i] = mx;
@@ -1278,7 +1306,7 @@ static void build_majorant(oracle_engine *g) {
 }
 
 int oracle_set_world(oracle_engine *g, const double half[3], int material) {
-  for (int a = 0; a < 3; ++a) g->wh[a] = (float)half[a];
+  for (int a = 0; a < 3; ++a) g->wh[a] = (real_t)half[a];
   g->world_mat = material;
   return 0;
 }
@@ -1292,10 +1320,10 @@ int oracle_set_image_volume(oracle_engine *g, const void *labels, int label_byte
   g->label_bytes = label_bytes;
   for (int a = 0; a < 3; ++a) {
     g->n[a] = size[a];
-    g->sp[a] = (float)spacing[a];
-    g->inv_sp[a] = (float)(1.0 / spacing[a]);
-    g->hs[a] = (float)(0.5 * size[a]);
-    g->half[a] = (float)(0.5 * size[a] * spacing[a]);
+    g->sp[a] = (real_t)spacing[a];
+    g->inv_sp[a] = (real_t)(1.0 / spacing[a]);
+    g->hs[a] = (real_t)(0.5 * size[a]);
+    g->half[a] = (real_t)(0.5 * size[a] * spacing[a]);
   }
   aff_from_d(&g->w2v, w2v);
   g->has_vol = 1;
@@ -1310,18 +1338,18 @@ int oracle_add_source(oracle_engine *g, const gate_b200_source *s) {
   o->d = *s;
   for (int r = 0; r < 3; ++r) {
     for (int c = 0; c < 3; ++c) {
-      o->pos.m[3 * r + c] = (float)s->pos_rotation[3 * r + c];
-      o->dir_rot[3 * r + c] = (float)s->dir_rotation[3 * r + c];
+      o->pos.m[3 * r + c] = (real_t)s->pos_rotation[3 * r + c];
+      o->dir_rot[3 * r + c] = (real_t)s->dir_rotation[3 * r + c];
     }
-    o->pos.t[r] = (float)s->pos_translation[r];
-    o->mom[r] = (float)s->momentum[r];
-    o->focus[r] = (float)s->focus_point[r];
+    o->pos.t[r] = (real_t)s->pos_translation[r];
+    o->mom[r] = (real_t)s->momentum[r];
+    o->focus[r] = (real_t)s->focus_point[r];
   }
-  o->cos_tmin = (float)cos(s->theta[0]); o->cos_tmax = (float)cos(s->theta[1]);
-  o->sin2_tmin = (float)(sin(s->theta[0]) * sin(s->theta[0])); o->sin2_tmax = (float)(sin(s->theta[1]) * sin(s->theta[1]));
-  o->dir_sx = (float)s->dir_sigma[0]; o->dir_sy = (float)s->dir_sigma[1];
-  o->phi0_turn = (float)(s->phi[0] / 6.283185307179586);
-  o->dphi_turn = (float)((s->phi[1] - s->phi[0]) / 6.283185307179586);
+  o->cos_tmin = (real_t)cos(s->theta[0]); o->cos_tmax = (real_t)cos(s->theta[1]);
+  o->sin2_tmin = (real_t)(sin(s->theta[0]) * sin(s->theta[0])); o->sin2_tmax = (real_t)(sin(s->theta[1]) * sin(s->theta[1]));
+  o->dir_sx = (real_t)s->dir_sigma[0]; o->dir_sy = (real_t)s->dir_sigma[1];
+  o->phi0_turn = (real_t)(s->phi[0] / 6.283185307179586);
+  o->dphi_turn = (real_t)((s->phi[1] - s->phi[0]) / 6.283185307179586);
   int ne = 0;
   if (s->ene_type == GATE_B200_ENE_SPECTRUM_DISCRETE || s->ene_type == GATE_B200_ENE_CDF) ne = s->n_spectrum;
   if (s->ene_type == GATE_B200_ENE_SPECTRUM_HISTOGRAM || s->ene_type == GATE_B200_ENE_SPECTRUM_HISTOGRAM_LINEAR)
@@ -1329,8 +1357,8 @@ int oracle_add_source(oracle_engine *g, const gate_b200_source *s) {
   if (ne > 0) {
     o->spec_e = (float *)malloc(sizeof(float) * ne);
     o->spec_cdf = (float *)malloc(sizeof(float) * s->n_spectrum);
-    for (int i = 0; i < ne; ++i) o->spec_e[i] = (float)s->spectrum_energy[i];
-    for (int i = 0; i < s->n_spectrum; ++i) o->spec_cdf[i] = (float)s->spectrum_cdf[i];
+    for (int i = 0; i < ne; ++i) o->spec_e[i] = (real_t)s->spectrum_energy[i];
+    for (int i = 0; i < s->n_spectrum; ++i) o->spec_cdf[i] = (real_t)s->spectrum_cdf[i];
   }
   return g->nsrc++;
 }
@@ -1390,10 +1418,10 @@ int oracle_add_tle_dose_actor(oracle_engine *g, const gate_b200_dose_desc *d, co
   if (id < 0) return id;
   odose_t *D = &g->dose[id];
   D->tle = 1;
-  D->tle_thr = t->energy_threshold_MeV > 3.0e38 ? BIG : (float)t->energy_threshold_MeV;
+  D->tle_thr = t->energy_threshold_MeV > 3.0e38 ? BIG : (real_t)t->energy_threshold_MeV;
   D->muen = dup_f(t->mu_en_over_rho, (size_t)g->nmat * g->ne);
   D->aligned = grid_is_image_grid(g, D);
-  float emin = (float)t->energy_min_MeV;
+  real_t emin = (real_t)t->energy_min_MeV;
   if (g->ntle == 0 || emin > g->tle_emin) g->tle_emin = emin;
   if (g->ntle == 0 || D->tle_thr > g->tle_thr_max) g->tle_thr_max = D->tle_thr;
   g->ntle++;
@@ -1404,7 +1432,7 @@ int oracle_add_phsp_actor(oracle_engine *g, const gate_b200_phsp_desc *d) {
   if (g->nphsp >= ORACLE_MAX_PHSP) return -1;
   ophsp_t *P = &g->phsp[g->nphsp];
   memset(P, 0, sizeof *P);
-  for (int a = 0; a < 3; ++a) P->half[a] = (float)d->half_size[a];
+  for (int a = 0; a < 3; ++a) P->half[a] = (real_t)d->half_size[a];
   aff_from_d(&P->w2b, d->world_to_box);
   P->steps = d->steps_to_store;
   P->capacity = d->capacity;

@@ -232,7 +232,7 @@ def c3_full(cuda_required):
 
 
 def test_c3_full_size_properties(c3_full):
-    """512x512x300 CT, 75 materials (BASELINE.json config 3) at a size the oracle cannot be run at:
+    """512x512x300 CT, 75 materials (BASELINE.json config 3) beyond what the bit-exact comparison of tests/test_fullsize_parity.py already covers:
     size-independent properties of the scoring.  (i) everything deposited inside the volume is in
     the edep grid; (ii) dose = sum(e / rho(label at the deposit)): with dose grid == label grid,
     dose * rho(label) == edep per voxel; (iii) counts are integers, and squares obey

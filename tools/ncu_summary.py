@@ -40,6 +40,87 @@ RAW = [
 ]
 
 
+def d_kernel_name(hdr, vals):
+    """the instantiation as gate_b200_kernel_name() spells it: 'gb2::transport_kernel<unsigned char, 2>'"""
+    import re
+    nm = dict(zip(hdr, vals)).get("Kernel Name", "")
+    m = re.search(r"transport_kernel<[^>]*>", nm)
+    return ("gb2::" + m.group(0)) if m else nm
+
+
+# the phases of the persistent kernel by the device functions inlined into it (transport.cuh): which share of the
+# issue slots / stall samples each queue's phase takes
+PHASES = {
+    "Q_V woodcock": ("volume_gather_labels", "volume_gather_mu", "volume_decide", "route_interaction", "tab_mu", "bin_split", "shell_flight"),
+    "Q_C compton": ("phase_compton", "interp_q2", "q2_segment", "rotate_dir"),
+    "Q_E end/primary": ("phase_end", "generate_primary", "locate", "cdf_index", "lower_bound_f", "gauss", "flush_buffer", "grid_add", "red_add_f64"),
+    "Q_W world": ("phase_world", "ray_box_ax", "ray_box", "snap_to_face", "to_world", "to_volume", "inside_box", "aff_apply", "rot_apply", "aff_apply_inv", "rot_apply_inv", "phsp_store"),
+    "Q_R rare": ("phase_rare",),
+    "Q_T tle": ("phase_tle", "tle_table_add", "tle_flush_all"),
+    "deposit": ("deposit", "ld_dep", "st_dep", "hist_weight"),
+    "scheduler (claim/push)": ("transport_kernel", "ld_vol", "st_vol", "ld_cell", "st_cell"),
+    "state load/store": ("load_ph", "store_ph", "set_energy", "energy_bin_t"),
+    "statistics": ("stat_add64", "stat_add", "stat_reduce_packed", "stat_bump", "stat_overflow", "stat_tle_overflow"),
+}
+
+
+def phase_table(rep, srcf):
+    """per-phase share of samples / instructions from the source page (functions are inlined: lines are mapped to
+    the device function that contains them)"""
+    import bisect
+    import re
+    src = ncu_csv(rep, "source", ["--print-source", "cuda,sass"])
+    hdr, cur, agg = None, None, []
+    for r in src:
+        if len(r) >= 2 and r[0] == "File Path":
+            cur = r[1].split("/")[-1]
+            continue
+        if r and r[0] == "Line No":
+            hdr = r
+            continue
+        if r and r[0].isdigit() and hdr and len(r) == len(hdr):
+            d = {}
+            for k, v in zip(hdr, r):
+                d.setdefault(k, v)
+            g = lambda k: int(d.get(k) or 0)   # noqa: E731
+            agg.append((cur, int(r[0]), g("# Samples"), g("Instructions Executed"), g("Thread Instructions Executed"),
+                        g("stall_long_sb"), g("stall_no_inst")))
+    lines = open(srcf).read().split("\n")
+    funcs = []
+    for i, l in enumerate(lines):
+        if re.match(r"\s*(__device__|__global__)", l) or (re.match(r"\s*template", l) and i + 1 < len(lines) and re.match(r"\s*(__device__|__global__)", lines[i + 1])):
+            txt = " ".join(lines[i:i + 3])
+            m = re.search(r"\b(\w+)\s*\(", re.sub(r"__launch_bounds__\([^)]*\)(\s*,\s*\w+\))?", "", re.sub(r"template\s*<[^>]*>", "", txt)))
+            if m and (not funcs or funcs[-1][1] != m.group(1) or funcs[-1][0] < i):
+                funcs.append((i + 1, m.group(1)))
+    starts = [f[0] for f in funcs]
+    f2p = {fn: ph for ph, fns in PHASES.items() for fn in fns}
+    tot = [0] * 5
+    by = {}
+    for f, ln, smp, ins, tins, lsb, ni in agg:
+        if f == "transport.cuh":
+            i = bisect.bisect_right(starts, ln) - 1
+            fn = funcs[i][1] if i >= 0 else "?"
+            ph = f2p.get(fn, "other (" + fn + ")")
+        elif f == "device_math.cuh":
+            ph = "math: philox/log/exp/sincos"
+        else:
+            ph = "intrinsics headers (shfl, atomics, ...)"
+        a = by.setdefault(ph, [0] * 5)
+        for k, v in enumerate((smp, ins, tins, lsb, ni)):
+            a[k] += v
+            tot[k] += v
+    out = ["## by phase (source-level samples; device functions are inlined into the one kernel)", "",
+           "| phase | % stall samples | % warp instructions | lanes / instruction | % of samples: long_scoreboard | no_instruction |",
+           "|---|---|---|---|---|---|"]
+    for ph, v in sorted(by.items(), key=lambda kv: -kv[1][0]):
+        if v[0] * 200 < max(tot[0], 1):
+            continue
+        out.append(f"| {ph} | {100 * v[0] / max(tot[0], 1):.1f} | {100 * v[1] / max(tot[1], 1):.1f} | {v[2] / max(v[1], 1):.1f} | "
+                   f"{100 * v[3] / max(tot[0], 1):.1f} | {100 * v[4] / max(tot[0], 1):.1f} |")
+    return out + [""]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("rep")
@@ -49,6 +130,7 @@ def main():
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--traffic-json", default="", help="update this json with dram bytes/history under --key")
     ap.add_argument("--key", default="c3")
+    ap.add_argument("--source", default="opengate_b200/csrc/transport.cuh", help="transport.cuh of the profiled build")
     a = ap.parse_args()
 
     raw = ncu_csv(a.rep, "raw")
@@ -74,13 +156,19 @@ def main():
                     import json
                     import os
                     d = json.load(open(a.traffic_json)) if os.path.exists(a.traffic_json) else {}
+                    kn = d_kernel_name(hdr, vals)
                     d[a.key] = {"dram_bytes_per_history": (rd + wr) / a.histories, "histories_in_capture": a.histories,
-                                "dram_read_bytes": rd, "dram_write_bytes": wr, "source": os.path.basename(a.out)}
+                                "dram_read_bytes": rd, "dram_write_bytes": wr, "source": os.path.basename(a.out),
+                                "kernel": kn}
                     json.dump(d, open(a.traffic_json, "w"), indent=1)
         except Exception:
             pass
         lines.append("")
 
+    try:
+        lines += phase_table(a.rep, a.source)
+    except Exception as e:   # the phase table is a convenience: never lose the rest of the summary over it
+        lines += [f"(phase table failed: {e})", ""]
     src = ncu_csv(a.rep, "source", ["--print-source", "cuda,sass"])
     cur, agg = None, []
     for r in src:

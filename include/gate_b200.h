@@ -260,6 +260,20 @@ int gate_b200_sync(gate_b200_engine *h);
 /* Replaces: fetch_from_cpp_image (doseactors.py:255-270): copy one accumulator grid
  * (double, nx*ny*nz) to the host. */
 int gate_b200_get_dose_grid(gate_b200_engine *h, int32_t actor_id, int32_t which, double *out);
+/* The same with every value multiplied by `scale` on the device: the end-of-run unit conversion of
+ * DoseActor.EndOfRunActionMasterThread (doseactors.py:685-696: dose /= Gy * voxel volume, squares by its square)
+ * without a host pass over the image. */
+int gate_b200_get_dose_grid_scaled(gate_b200_engine *h, int32_t actor_id, int32_t which, double scale, double *out);
+/* Replaces: the uncertainty item of the reference's data containers (actors/dataitems.py:1956-1993 with
+ * utility.py:551-560) evaluated on the device from the value and squared-value accumulators of one run:
+ * out = sqrt(clip((S2/n - (S/n)^2) / (n - 1), 0)) / (S/n) where S != 0, else 0; which = GATE_B200_GRID_EDEP or
+ * GATE_B200_GRID_DOSE (needs the matching squares); n = number of events (> 1). */
+int gate_b200_get_uncertainty(gate_b200_engine *h, int32_t actor_id, int32_t which, uint64_t n_events, double *out);
+/* Page-lock / unlock a caller-owned host buffer (cudaHostRegister): a get_* call into a registered buffer runs
+ * at the full host-link rate, and the caller can prepare (allocate + register) its output arrays while a run is
+ * in flight.  No reference counterpart (its images never leave host memory). */
+int gate_b200_host_register(void *ptr, uint64_t bytes);
+int gate_b200_host_unregister(void *ptr);
 /* Device buffers that hold the accumulators of one dose actor, for the sum-reduce over GPUs done by
  * the host plumbing (NCCL; the reference merges parallel runs by summing images offline,
  * actors/dataitems.py:1238-1247).  On the device the scored ones of the sums edep, edep2, dose, dose2

@@ -79,6 +79,8 @@ class ActorOutputImage:
         self.samples_per_run = {}
         self.merged = None
         self.merged_samples = 0
+        self.merged_runs = 0
+        self.uncertainty_per_run = {}   # run -> Image evaluated by the engine on the device (single-run fast path)
 
     # configuration ------------------------------------------------------------------------
     def _ids(self, item):
@@ -150,10 +152,16 @@ class ActorOutputImage:
     def set_number_of_samples(self, run_index, n):
         self.samples_per_run[run_index] = int(n)
 
+    def store_uncertainty(self, run_index, image):
+        """relative uncertainty of the run, already evaluated (on the device) from the sums of this run"""
+        self.uncertainty_per_run[run_index] = image
+
     def end_of_run(self, run_index):
         run = self.data_per_run[run_index]
+        keep = any(c["keep_data_per_run"] for c in self.items.values())
         if self.merged is None:
-            self.merged = {i: (None if im is None else gimage.Image(im.array.copy(), im.spacing, im.origin, im.direction))
+            # the first run IS the merged data; it is copied only when the per-run data stay alive beside it
+            self.merged = {i: (None if im is None else (gimage.Image(im.array.copy(), im.spacing, im.origin, im.direction) if keep else im))
                            for i, im in run.items()}
         else:
             for i, im in run.items():
@@ -164,7 +172,8 @@ class ActorOutputImage:
                     else:
                         self.merged[i].array += im.array
         self.merged_samples += self.samples_per_run.get(run_index, 0)
-        if not any(c["keep_data_per_run"] for c in self.items.values()):
+        self.merged_runs += 1
+        if not keep:
             # like the reference: per-run data are dropped unless explicitly kept
             self.data_per_run[run_index] = {i: None for i in run}
 
@@ -177,6 +186,14 @@ class ActorOutputImage:
             v = src.get(0)
             if v is None:
                 return None
+            if item == "uncertainty":
+                # evaluated by the engine from the sums of the run: valid for that run, and for the merged data
+                # while they consist of that one run
+                runs = list(self.uncertainty_per_run)
+                if which != "merged" and int(which) in self.uncertainty_per_run:
+                    return self.uncertainty_per_run[int(which)]
+                if which == "merged" and self.merged_runs == 1 and len(runs) == 1:
+                    return self.uncertainty_per_run[runs[0]]
             sq = src.get(1)
             arr = uncertainty_from_squares(v.array, None if sq is None else sq.array, n, which=item)
             return gimage.Image(arr, v.spacing, v.origin, v.direction)
@@ -356,15 +373,19 @@ class DoseActor(ActorBase):
                   f"(only 'material')")
         e, d = self.user_output["edep_with_uncertainty"], self.user_output["dose_with_uncertainty"]
         e.set_active(True, item=0)
+        # squares the user did not ask for, scored only because an uncertainty needs them
+        self.__dict__["_squares_for_uncertainty_only"] = set()
         if e.get_active(item=("uncertainty",)) or self.uncertainty_goal is not None:
             if not e.get_active(item=1):
                 e.set_write_to_disk(False, item=1)
                 e.set_active(True, item=1)
+                self._squares_for_uncertainty_only.add("edep")
         if d.get_active(item=("uncertainty",)):
             d.set_active(True, item=0)
             if not d.get_active(item=1):
                 d.set_write_to_disk(False, item=1)
                 d.set_active(True, item=1)
+                self._squares_for_uncertainty_only.add("dose")
         if d.get_active(item=1):
             d.set_active(True, item=0)
         if self.user_output["density"].get_active() and vol.volume_type != "ImageVolume":
@@ -409,9 +430,40 @@ class DoseActor(ActorBase):
         Rw, tw = vol.world_transform()
         return Rw @ origin_local + tw, Rw @ R
 
-    def store_run(self, run_index, grids, n_events):
-        """Receive the accumulator grids of one run (dict which -> float64 (z,y,x) array) and
-        apply what DoseActor.EndOfRunActionMasterThread does (doseactors.py:662-715)."""
+    def dose_scale(self):
+        """engine dose grid = sum(edep[MeV] / rho[g/cm3]); reference: edep / density (G4 units), then
+        / (Gy * voxel volume) (GateDoseActor.cpp:206-217, doseactors.py:685-696)"""
+        sp = np.asarray(self.spacing, dtype=np.float64)
+        return 1.0 / (g4_units.g_cm3 * g4_units.Gy * sp[0] * sp[1] * sp[2])
+
+    def fetch_plan(self, single_run):
+        """What the engine has to bring back for one run: [(key, kind, grid, scale)], kind 'grid' (an accumulator,
+        multiplied by `scale` on the device: the Gy conversion of doseactors.py:685-696) or 'uncertainty' (the
+        relative-uncertainty image evaluated on the device).  With `sim.lean_outputs`, squares that are scored only
+        because an uncertainty image needs them stay on the device when the run is the only one (nothing to merge):
+        the uncertainty comes back instead."""
+        from . import abi
+        e, d = self.user_output["edep_with_uncertainty"], self.user_output["dose_with_uncertainty"]
+        s = self.dose_scale()
+        lean = set()
+        if single_run and self.uncertainty_goal is None and getattr(self.simulation, "lean_outputs", False):
+            lean = getattr(self, "_squares_for_uncertainty_only", set())
+        plan = [(abi.GRID_EDEP, "grid", abi.GRID_EDEP, 1.0)]
+        if e.get_active(item=1):
+            plan.append(("edep_unc", "uncertainty", abi.GRID_EDEP, 1.0) if "edep" in lean else (abi.GRID_EDEP_SQ, "grid", abi.GRID_EDEP_SQ, 1.0))
+        if d.get_active(item=0):
+            plan.append((abi.GRID_DOSE, "grid", abi.GRID_DOSE, s))
+        if d.get_active(item=1):
+            plan.append(("dose_unc", "uncertainty", abi.GRID_DOSE, 1.0) if "dose" in lean else (abi.GRID_DOSE_SQ, "grid", abi.GRID_DOSE_SQ, s * s))
+        if self.user_output["counts"].get_active():
+            plan.append((abi.GRID_COUNTS, "grid", abi.GRID_COUNTS, 1.0))
+        return plan
+
+    def store_run(self, run_index, grids, n_events, scaled=False):
+        """Receive the accumulator grids of one run (dict which -> float64 (z,y,x) array, plus 'edep_unc' /
+        'dose_unc' when the engine evaluated the uncertainty) and apply what
+        DoseActor.EndOfRunActionMasterThread does (doseactors.py:662-715).  scaled: the dose grids already
+        carry the Gy conversion (done on the device)."""
         from . import abi
         self.NbOfEvent = int(n_events)
         origin, rot = self.output_origin_rotation()
@@ -423,16 +475,20 @@ class DoseActor(ActorBase):
         e = self.user_output["edep_with_uncertainty"]
         e.store_data(run_index, img(grids.get(abi.GRID_EDEP)), img(grids.get(abi.GRID_EDEP_SQ)))
         e.set_number_of_samples(run_index, n_events)
+        if grids.get("edep_unc") is not None:
+            e.store_uncertainty(run_index, img(grids["edep_unc"]))
         d = self.user_output["dose_with_uncertainty"]
         if d.get_active(item="any"):
-            # engine grid = sum(edep[MeV] / rho[g/cm3]); reference: edep / density (G4 units) then
-            # / (Gy * voxel volume) (GateDoseActor.cpp:206-217, doseactors.py:685-696)
-            scale = 1.0 / (g4_units.g_cm3 * g4_units.Gy * sp[0] * sp[1] * sp[2])
+            scale = 1.0 if scaled else self.dose_scale()
             dose = grids.get(abi.GRID_DOSE)
             dose_sq = grids.get(abi.GRID_DOSE_SQ)
-            d.store_data(run_index, img(None if dose is None else dose * scale),
-                         img(None if dose_sq is None else dose_sq * scale * scale))
+            if scale != 1.0:
+                dose = None if dose is None else dose * scale
+                dose_sq = None if dose_sq is None else dose_sq * (scale * scale)
+            d.store_data(run_index, img(dose), img(dose_sq))
             d.set_number_of_samples(run_index, n_events)
+            if grids.get("dose_unc") is not None:
+                d.store_uncertainty(run_index, img(grids["dose_unc"]))
         c = self.user_output["counts"]
         if c.get_active():
             c.store_data(run_index, img(grids.get(abi.GRID_COUNTS)))

@@ -33,6 +33,7 @@ EXPORTS = [
     "gate_b200_get_dose_grid", "gate_b200_dose_buffers", "gate_b200_set_dose_grid",
     "gate_b200_mean_uncertainty", "gate_b200_phsp_count", "gate_b200_get_phsp",
     "gate_b200_get_stats", "gate_b200_timed_run", "gate_b200_kernel_name",
+    "gate_b200_get_dose_grid_scaled", "gate_b200_get_uncertainty", "gate_b200_host_register", "gate_b200_host_unregister",
 ]
 
 
@@ -94,6 +95,10 @@ def load_library():
     L.gate_b200_sync.argtypes = [vp]
     L.gate_b200_get_dose_grid.argtypes = [vp, i32, i32, C.POINTER(C.c_double)]
     L.gate_b200_set_dose_grid.argtypes = [vp, i32, i32, C.POINTER(C.c_double)]
+    L.gate_b200_get_dose_grid_scaled.argtypes = [vp, i32, i32, C.c_double, C.POINTER(C.c_double)]
+    L.gate_b200_get_uncertainty.argtypes = [vp, i32, i32, u64, C.POINTER(C.c_double)]
+    L.gate_b200_host_register.argtypes = [vp, u64]
+    L.gate_b200_host_unregister.argtypes = [vp]
     L.gate_b200_dose_buffers.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(u64), C.POINTER(i32)]
     L.gate_b200_mean_uncertainty.argtypes = [vp, i32, u64, i32, C.c_double, C.POINTER(C.c_double)]
     L.gate_b200_phsp_count.argtypes = [vp, i32, C.POINTER(u64)]
@@ -238,12 +243,32 @@ class Engine:
         return ms.value
 
     # results -------------------------------------------------------------------------
-    def dose_grid(self, actor, which, out=None):
+    def dose_grid(self, actor, which, out=None, scale=1.0):
+        """one accumulator grid as a (z,y,x) float64 array, every value multiplied by `scale` on the device"""
         nx, ny, nz = self._dose_sizes[actor]
         if out is None:
             out = np.empty((nz, ny, nx), dtype=np.float64)
-        self._check(self.L.gate_b200_get_dose_grid(self.h, actor, which, out.ctypes.data_as(C.POINTER(C.c_double))))
+        self._check(self.L.gate_b200_get_dose_grid_scaled(self.h, actor, which, float(scale), out.ctypes.data_as(C.POINTER(C.c_double))))
         return out
+
+    def uncertainty_grid(self, actor, which, n_events, out=None):
+        """relative uncertainty image of edep (which = GRID_EDEP) or dose (GRID_DOSE) of the run, computed on the device"""
+        nx, ny, nz = self._dose_sizes[actor]
+        if out is None:
+            out = np.empty((nz, ny, nx), dtype=np.float64)
+        self._check(self.L.gate_b200_get_uncertainty(self.h, actor, which, C.c_uint64(int(n_events)), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def dose_grid_shape(self, actor):
+        nx, ny, nz = self._dose_sizes[actor]
+        return (nz, ny, nx)
+
+    def pin(self, array):
+        """page-lock a numpy array in place (gate_b200_host_register); False if the driver refuses"""
+        return self.L.gate_b200_host_register(array.ctypes.data_as(C.c_void_p), C.c_uint64(array.nbytes)) == 0
+
+    def unpin(self, array):
+        self.L.gate_b200_host_unregister(array.ctypes.data_as(C.c_void_p))
 
     def set_dose_grid(self, actor, which, array):
         a = np.ascontiguousarray(array, dtype=np.float64)

@@ -195,9 +195,21 @@ __global__ void __launch_bounds__(256) hu_to_label_kernel(const HuT *__restrict_
 
 // component k of every voxel record <-> a dense array (the layout the ABI hands to the caller)
 __global__ void __launch_bounds__(256) grid_extract_kernel(const double *__restrict__ comp, size_t n, size_t stride,
-                                                           double *__restrict__ dense) {
+                                                           double scale, double *__restrict__ dense) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    dense[i] = comp[i * stride];
+    dense[i] = comp[i * stride] * scale;
+}
+// relative uncertainty of the mean from sum(x) and sum(x^2) over n events (utility.py:551-560, dataitems.py:1956-1993);
+// IEEE double division and square root, no contraction: the same bits as the numpy expressions
+__global__ void __launch_bounds__(256) grid_uncertainty_kernel(const double *__restrict__ val, const double *__restrict__ sq, size_t n,
+                                                               size_t stride, double nev, double *__restrict__ dense) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double v = val[i * stride];
+    const double mean = v / nev;
+    double var = (sq[i * stride] / nev - mean * mean) / (nev - 1.0);
+    if (var < 0.0) var = 0.0;
+    dense[i] = v != 0.0 ? sqrt(var) / mean : 0.0;
+  }
 }
 __global__ void __launch_bounds__(256) grid_scatter_kernel(double *__restrict__ comp, size_t n, size_t stride,
                                                            const double *__restrict__ dense) {
@@ -905,22 +917,52 @@ static int staging(gate_b200_engine *h, size_t n, double **out) {
   return 0;
 }
 
-int gate_b200_get_dose_grid(gate_b200_engine *h, int32_t actor_id, int32_t which, double *out) {
+int gate_b200_get_dose_grid_scaled(gate_b200_engine *h, int32_t actor_id, int32_t which, double scale, double *out) {
   if (!h || !out) return GATE_B200_EINVAL;
   double *p; size_t n;
   if (int rc = check_grid(h, actor_id, which, &p, &n)) return rc;
   CU(cudaSetDevice(h->device));
-  const size_t stride = (size_t)h->dose[actor_id].dev.gstride;
-  if (which != GATE_B200_GRID_COUNTS && stride > 1) {
+  const size_t stride = which == GATE_B200_GRID_COUNTS ? 1 : (size_t)h->dose[actor_id].dev.gstride;
+  if (stride > 1 || scale != 1.0) {
     double *dense;
     if (int rc = staging(h, n, &dense)) return rc;
-    grid_extract_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(p, n, stride, dense);
+    grid_extract_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(p, n, stride, scale, dense);
     CU(cudaGetLastError());
     p = dense;
   }
   CU(cudaMemcpyAsync(out, p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return GATE_B200_OK;
+}
+
+int gate_b200_get_dose_grid(gate_b200_engine *h, int32_t actor_id, int32_t which, double *out) {
+  return gate_b200_get_dose_grid_scaled(h, actor_id, which, 1.0, out);
+}
+
+int gate_b200_get_uncertainty(gate_b200_engine *h, int32_t actor_id, int32_t which, uint64_t n_events, double *out) {
+  if (!h || !out) return GATE_B200_EINVAL;
+  if (which != GATE_B200_GRID_EDEP && which != GATE_B200_GRID_DOSE) return fail(h, GATE_B200_EINVAL, "uncertainty of grid %d: edep or dose only", which);
+  if (n_events < 2) return fail(h, GATE_B200_EINVAL, "uncertainty needs more than one event");
+  double *v, *sq; size_t n;
+  if (int rc = check_grid(h, actor_id, which, &v, &n)) return rc;
+  if (int rc = check_grid(h, actor_id, which + 1, &sq, &n)) return rc;   // the squares follow their values in the enum
+  CU(cudaSetDevice(h->device));
+  double *dense;
+  if (int rc = staging(h, n, &dense)) return rc;
+  grid_uncertainty_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(v, sq, n, (size_t)h->dose[actor_id].dev.gstride, (double)n_events, dense);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, dense, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return GATE_B200_OK;
+}
+
+int gate_b200_host_register(void *ptr, uint64_t bytes) {
+  if (!ptr || !bytes) return GATE_B200_EINVAL;
+  return cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable) == cudaSuccess ? GATE_B200_OK : (cudaGetLastError(), GATE_B200_ECUDA);
+}
+int gate_b200_host_unregister(void *ptr) {
+  if (!ptr) return GATE_B200_EINVAL;
+  return cudaHostUnregister(ptr) == cudaSuccess ? GATE_B200_OK : (cudaGetLastError(), GATE_B200_ECUDA);
 }
 
 int gate_b200_set_dose_grid(gate_b200_engine *h, int32_t actor_id, int32_t which, const double *in) {

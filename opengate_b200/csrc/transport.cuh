@@ -57,6 +57,9 @@ constexpr int kTleThreads = GB2_TLE_THREADS;
 template <bool kIsTle> constexpr int threads_of() { return kIsTle ? kTleThreads : kThreads; }
 constexpr int kSlots = GB2_SLOTS;          // photon slots per CTA (< 65535: queue cells are 16 bit)
 constexpr int kWoodcockK = 4;              // tentative collisions per Woodcock call (2 Philox blocks)
+#ifndef GB2_COMPTON_LAZY
+#define GB2_COMPTON_LAZY 0
+#endif
 #ifndef GB2_VWIDTH
 #define GB2_VWIDTH 1
 #endif
@@ -518,8 +521,10 @@ __device__ __forceinline__ void deposit(const Params &P, Ph &g, DepEntry *buf, D
     if (kMode != 2 && D.hit_type != GATE_B200_HIT_POST) {
       // pre/random/middle between the Geant4 pre and post step points; the Geant4 step starts at
       // the voxel entry or at the previous interaction (GateDoseActor.cpp:144-178)
-      const int vi[3] = {(int)((g.p[0] + P.half[0]) * P.inv_sp[0]), (int)((g.p[1] + P.half[1]) * P.inv_sp[1]),
-                         (int)((g.p[2] + P.half[2]) * P.inv_sp[2])};
+      // the image voxel of the interaction point, by the SAME expression that gathered its label in the Woodcock
+      // call (a differently rounded index disagreed with the oracle for one deposit in 3.5e6 on the full CT)
+      const int vi[3] = {__float2int_rd(__fmaf_rn(g.p[0], P.inv_sp[0], P.hs[0])), __float2int_rd(__fmaf_rn(g.p[1], P.inv_sp[1], P.hs[1])),
+                         __float2int_rd(__fmaf_rn(g.p[2], P.inv_sp[2], P.hs[2]))};
       float back = g.seg;
 #pragma unroll
       for (int ax = 0; ax < 3; ++ax) {
@@ -1127,10 +1132,14 @@ __device__ __forceinline__ int phase_compton(const Params &P, Smem &S, int slot,
   const unsigned fm = S.fm[slot];
   const int m = (int)(fm >> F_MAT_SHIFT);
   uint32_t r[8];
-  {
-    const unsigned long long id = P.first + S.hidx[slot];
-    philox_block2((uint32_t)P.seed, (uint32_t)(P.seed >> 32), (uint32_t)id, (uint32_t)(id >> 32), b0, r);
-  }
+  const unsigned long long id = P.first + S.hidx[slot];
+#if GB2_COMPTON_LAZY
+  // the trial needs the first block only; the second one (azimuth, hit-point draws) is generated when the trial is
+  // accepted (same blocks, same numbers: the protocol does not change)
+  philox_block((uint32_t)P.seed, (uint32_t)(P.seed >> 32), (uint32_t)id, (uint32_t)(id >> 32), b0, 0u, r[0], r[1], r[2], r[3]);
+#else
+  philox_block2((uint32_t)P.seed, (uint32_t)(P.seed >> 32), (uint32_t)id, (uint32_t)(id >> 32), b0, r);
+#endif
   const float k = E / kMc2;
   const float eps0 = 1.0f / (1.0f + 2.0f * k);
   const float eps0sq = eps0 * eps0;
@@ -1159,6 +1168,9 @@ __device__ __forceinline__ int phase_compton(const Params &P, Smem &S, int slot,
   if (ok) {
     Ph g;
     load_ph(P, S, slot, g);
+#if GB2_COMPTON_LAZY
+    philox_block((uint32_t)P.seed, (uint32_t)(P.seed >> 32), (uint32_t)id, (uint32_t)(id >> 32), b0 + 1u, 0u, r[4], r[5], r[6], r[7]);
+#endif
     // the rest of the call's random numbers: r[4] is the azimuth, deposits continue from r[5]
     g.rng.blk = b0 + 2u; g.rng.pos = 1;
     g.rng.o0 = r[5]; g.rng.o1 = r[6]; g.rng.o2 = r[7];

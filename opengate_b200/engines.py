@@ -356,6 +356,41 @@ class GpuSimulationEngine:
             if hasattr(e, "sync"):
                 e.sync()
 
+    # ---- host memory of the outputs, made ready while the device is busy ---------------------------------
+    def _prepare_outputs(self, single_run):
+        """The histories are in flight and the host has nothing to do: allocate the (z,y,x) float64 arrays the dose
+        actors will keep and page-lock them (worker threads: first touch + cudaHostRegister of 0.6 GB per image at
+        config-3 size), so that the copies after the run go at the full host-link rate into their final place."""
+        self._prepared = {}
+        e = self.engines[0] if self.engines else None
+        if self.dist is not None or len(self.engines) != 1 or not hasattr(e, "pin"):
+            return
+        from concurrent.futures import ThreadPoolExecutor
+        jobs = [(i, key) for i, a in enumerate(self.dose_actors) for key, _, _, _ in a.fetch_plan(single_run)]
+        if not jobs:
+            return
+        pool = ThreadPoolExecutor(max_workers=min(len(jobs), 4))
+
+        def make(i):
+            arr = np.empty(e.dose_grid_shape(self.ids[0][1][i]), dtype=np.float64)
+            return arr, (arr.nbytes >= (1 << 20) and e.pin(arr))
+
+        self._prepared = {job: pool.submit(make, job[0]) for job in jobs}
+        pool.shutdown(wait=False)
+
+    def _take_prepared(self, actor_index, key, engine):
+        fut = getattr(self, "_prepared", {}).get((actor_index, key))
+        if fut is None:
+            return None
+        arr, pinned = fut.result()
+        if pinned:
+            self.__dict__.setdefault("_pinned", []).append(arr)
+        return arr
+
+    def _release_prepared(self, actor_index, engine):
+        for arr in self.__dict__.pop("_pinned", []):
+            engine.unpin(arr)
+
     def _mean_uncertainty(self, actor_index, actor, n_events):
         """GateDoseActor::ComputeMeanUncertainty over the data of ALL shards."""
         if self.n_shards == 1 and hasattr(self.engines[0], "mean_uncertainty"):
@@ -447,6 +482,7 @@ class GpuSimulationEngine:
                     next_check = int((u / a.uncertainty_goal) ** 2 * (n_run + done) * a.uncertainty_overshoot_factor_N_events)
                 n_run += done
             first += n
+        self._prepare_outputs(len(sim.run_timing_intervals) == 1)
         self._sync()
         # statistics: summed over shards
         st = None
@@ -457,10 +493,26 @@ class GpuSimulationEngine:
             st = multigpu.reduce_counters(st, "cpu" if self._backend is not None else f"cuda:{self.local_rank}")
         n_events = int(st["histories"])
         # dose actors
+        single_run = len(sim.run_timing_intervals) == 1
+        fast = self.dist is None and len(self.engines) == 1 and n_events > 1
         for i, a in enumerate(self.dose_actors):
-            which = multigpu.active_grids(a.score_flags())
-            grids = self._gather_grids(i, which)
-            a.store_run(run_index, grids, n_events)
+            if fast:
+                # one device: the unit conversion and the uncertainty are done there, every image comes back once
+                # into the array the actor keeps (prepared while the histories were running, see _prepare_outputs)
+                e, aid = self.engines[0], self.ids[0][1][i]
+                grids = {}
+                for key, kind, which, scale in a.fetch_plan(single_run):
+                    out = self._take_prepared(i, key, e)
+                    if kind == "grid":
+                        grids[key] = e.dose_grid(aid, which, out=out, scale=scale)
+                    else:
+                        grids[key] = e.uncertainty_grid(aid, which, n_events, out=out)
+                self._release_prepared(i, e)
+                a.store_run(run_index, grids, n_events, scaled=True)
+            else:
+                which = multigpu.active_grids(a.score_flags())
+                grids = self._gather_grids(i, which)
+                a.store_run(run_index, grids, n_events)
         # phase space: rows of all shards concatenated (EventID is the global history id of the run)
         for i, a in enumerate(self.phsp_actors):
             rows = None

@@ -206,6 +206,11 @@ class Simulation(GateObject):
                             "reference's engine, only available in the reference package)",
                             "allowed_values": ("b200", "geant4")}),
         "max_histories_per_launch": (200_000_000, {"doc": "GPU engine: histories per kernel launch"}),
+        "lean_outputs": (False, {"doc": "GPU engine: squared-sum images that are scored only because an uncertainty image "
+                                        "needs them stay on the device in a single-run simulation and the uncertainty image is "
+                                        "evaluated there (same bits as the host algebra); the squared images are then not "
+                                        "available on the actor.  Default False: every active item comes back, as in the "
+                                        "reference."}),
     }
 
     def __init__(self, name="simulation", **kwargs):

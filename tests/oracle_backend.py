@@ -20,9 +20,23 @@ class OracleBackend(TransportOracle):
     def sync(self):
         pass
 
-    def dose_grid(self, actor, which, out=None):
+    def dose_grid(self, actor, which, out=None, scale=1.0):
         g = np.array(super().dose_grid(actor, which), dtype=np.float64, copy=True)
+        if scale != 1.0:
+            g *= scale
         if out is not None:
             out[...] = g
             return out
         return g
+
+    def uncertainty_grid(self, actor, which, n_events, out=None):
+        """what gate_b200_get_uncertainty evaluates on the device, in numpy (reference algebra utility.py:551-560,
+        dataitems.py:1956-1993)"""
+        from opengate_b200.actors import uncertainty_from_squares
+        v = np.array(TransportOracle.dose_grid(self, actor, which), dtype=np.float64)
+        sq = np.array(TransportOracle.dose_grid(self, actor, which + 1), dtype=np.float64)
+        u = uncertainty_from_squares(v, sq, n_events)
+        if out is not None:
+            out[...] = u
+            return out
+        return u

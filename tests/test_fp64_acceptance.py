@@ -50,21 +50,25 @@ def _body_mask(S, block=1):
     return rho > 0.1
 
 
-def _independent(ga, gb, n, mask=None):
+def _independent(ga, gb, n, mask=None, total_tolerance=0.005):
     out = {}
     for name, v, sq in (("edep", abi.GRID_EDEP, abi.GRID_EDEP_SQ), ("dose", abi.GRID_DOSE, abi.GRID_DOSE_SQ)):
         ua = uncertainty_from_squares(ga[v], ga[sq], n)
         ub = uncertainty_from_squares(gb[v], gb[sq], n)
         out[name] = acceptance.compare_dose(ga[v], ua, gb[v], ub, total_over_selected=(name == "dose"),
-                                            mask=mask if name == "dose" else None)
+                                            mask=mask if name == "dose" else None, total_tolerance=total_tolerance)
     return out
 
 
-def _correlated(ga, gb):
-    """same history ids on both sides: (relative difference of the totals, sum |a - b| / sum a) of edep and dose"""
+def _correlated(ga, gb, mask=None):
+    """same history ids on both sides: (relative difference of the totals, sum |a - b| / sum a) of edep and dose
+    (dose inside `mask`: one history whose branch flipped into an air voxel, dose = e / 1.2e-3 g/cm3, would
+    otherwise outweigh the whole body)"""
     out = {}
     for name, v in (("edep", abi.GRID_EDEP), ("dose", abi.GRID_DOSE)):
         a, b = ga[v], gb[v]
+        if name == "dose" and mask is not None:
+            a, b = a[mask], b[mask]
         out[name] = (abs(a.sum() / b.sum() - 1.0), float(np.abs(a - b).sum() / b.sum()))
     return out
 
@@ -82,11 +86,14 @@ def test_float_oracle_vs_double_oracle_small(name):
     g64b, _ = _run(TransportOracle(S.seed, fp64=True), S, n, n)
     # correlated: the float transport has no bias beyond 2e-4 of the total; histories whose branches flipped move
     # less than 1 % of the deposited energy between voxels
-    for k, (dt, l1) in _correlated(g32, g64).items():
+    for k, (dt, l1) in _correlated(g32, g64, _body_mask(S) if name == "c3" else None).items():
         assert dt < 2e-4 and l1 < 1e-2, (k, dt, l1)
     assert abs(s32["tentative_collisions"] / s64["tentative_collisions"] - 1.0) < 1e-3
     # independent samples through the acceptance metric
-    for k, r in _independent(g32, g64b, n, _body_mask(S) if name == "c3" else None).items():
+    # (2e5 histories of the 6 MV beam on the small slab phantom fix the total deposited energy to about 1 % only --
+    # two float runs over these two ranges differ by 0.8 % as well; the 0.5 % statement is made at 1e7 histories in
+    # the GPU tier)
+    for k, r in _independent(g32, g64b, n, _body_mask(S) if name == "c3" else None, total_tolerance=0.02).items():
         assert r["ok"] and r["voxels_compared"] > 20, (k, r)
 
 
@@ -115,7 +122,7 @@ def test_cuda_float_engine_vs_double_oracle_full_size(cuda_required, name):
     g64, s64 = _run(TransportOracle(S.seed, fp64=True), S, 0, n)            # the same history ids
     g64b, _ = _run(TransportOracle(S.seed, fp64=True), S, n, n)             # an independent sample
     assert sg["histories"] == n == s64["histories"]
-    for k, (dt, l1) in _correlated(ggpu, g64).items():
+    for k, (dt, l1) in _correlated(ggpu, g64, _body_mask(S, 4) if name == "c3" else None).items():
         assert dt < 1e-4 and l1 < 1e-2, (name, k, dt, l1)
     assert abs(sg["tentative_collisions"] / s64["tentative_collisions"] - 1.0) < 2e-4
     for k, r in _independent(ggpu, g64b, n, _body_mask(S, 4) if name == "c3" else None).items():

@@ -81,3 +81,32 @@ def test_script_level_uncertainty_goal_on_the_cuda_engine(cuda_required, tmp_pat
     np.testing.assert_allclose(eg, ec, rtol=1e-10, atol=0)
     u = host_mean_uncertainty(og.get_data("merged", 0).array, og.get_data("merged", 1).array, ng, 5, 0.7)
     assert u <= 0.25
+
+
+def test_device_side_unit_conversion_and_uncertainty_images(cuda_required):
+    """gate_b200_get_dose_grid_scaled / gate_b200_get_uncertainty: the end-of-run algebra of the DoseActor
+    (doseactors.py:685-696, utility.py:551-560, dataitems.py:1956-1993) evaluated on the device gives the bits the
+    numpy expressions give on the host; a page-locked destination (gate_b200_host_register) changes nothing."""
+    from opengate_b200.actors import uncertainty_from_squares
+    from opengate_b200.core import Engine
+    n = 20000
+    S = SMALL["c3"](n)
+    S.dose[0].score_flags = abi.SCORE_EDEP | abi.SCORE_EDEP_SQ | abi.SCORE_DOSE | abi.SCORE_DOSE_SQ
+    eng = Engine(0, S.seed)
+    se, de, _ = S.apply(eng)
+    eng.begin_run()
+    eng.run_source(se[0], 0, n)
+    eng.sync()
+    g = {w: eng.dose_grid(de[0], w) for w in (abi.GRID_EDEP, abi.GRID_EDEP_SQ, abi.GRID_DOSE, abi.GRID_DOSE_SQ)}
+    s = 1.0 / (6.241509074460763e+18 * 1.0e-12 * 7.8 * 7.8 * 7.5)
+    assert np.array_equal(eng.dose_grid(de[0], abi.GRID_DOSE, scale=s), g[abi.GRID_DOSE] * s)
+    assert np.array_equal(eng.dose_grid(de[0], abi.GRID_DOSE_SQ, scale=s * s), g[abi.GRID_DOSE_SQ] * (s * s))
+    for v in (abi.GRID_EDEP, abi.GRID_DOSE):
+        want = uncertainty_from_squares(g[v], g[v + 1], n)
+        assert np.array_equal(eng.uncertainty_grid(de[0], v, n), want)
+    out = np.empty(eng.dose_grid_shape(de[0]), dtype=np.float64)
+    assert eng.pin(out)
+    eng.dose_grid(de[0], abi.GRID_EDEP, out=out)
+    eng.unpin(out)
+    assert np.array_equal(out, g[abi.GRID_EDEP])
+    eng.close()

@@ -423,3 +423,25 @@ def test_output_filename_semantics_follow_the_reference(tmp_path):
     assert dose2.edep.output_filename == "edep_with_uncertainty_from_doseactor_d2_edep.mhd"   # actoroutput.py:488-490
     dose.dose.output_filename = None
     assert dose.dose.output_filename is None
+
+
+def test_lean_outputs_keep_the_squares_on_the_engine_side(tmp_path):
+    """sim.lean_outputs: the squares scored only for an uncertainty image are not brought back in a single-run
+    simulation; the uncertainty image is evaluated by the engine and equals the host algebra of the default path."""
+    imgs = []
+    for lean in (False, True):
+        (tmp_path / str(lean)).mkdir()
+        sim, ct, src, dose, hu = ct_sim(tmp_path / str(lean), n_primaries=3000)
+        sim.lean_outputs = lean
+        dose.dose.active = True
+        dose.dose_uncertainty.active = True
+        dose.edep_uncertainty.active = True
+        sim.run(_backend=OracleBackend)
+        imgs.append((dose.edep.image.array, dose.edep_uncertainty.image.array, dose.dose.image.array, dose.dose_uncertainty.image.array,
+                     dose.user_output["edep_with_uncertainty"].get_data("merged", 1)))
+    a, b = imgs
+    assert a[4] is not None and b[4] is None
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+    assert np.array_equal(a[1], b[1])                                   # same expressions, same bits
+    np.testing.assert_allclose(a[3], b[3], rtol=1e-12, atol=0)          # dose: evaluated before / after the Gy scaling
+    assert (b[1] > 0).any()

@@ -78,8 +78,10 @@ def test_coarse_unaligned_grid_conserves_the_total():
     oa, da = run(Sa, 6000)
     oc, dc = run(Sc, 6000)
     ta, tc = oa.dose_grid(da[-1], abi.GRID_EDEP).sum(), oc.dose_grid(dc[-1], abi.GRID_EDEP).sum()
-    # same histories, same chords; the coarse grid loses only the half voxel at odd borders
-    assert tc == pytest.approx(ta, rel=2e-3)
+    # the same estimator on a coarser, unaligned grid: the totals agree statistically (the two runs share only the
+    # first flight of each history -- the coarse grid draws a random point per chord, which moves every later
+    # random number; batches of 6000 histories scatter by 1 %)
+    assert tc == pytest.approx(ta, rel=3e-2)
 
 
 def test_table_overflow_is_counted_and_conserves_sums():

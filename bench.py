@@ -233,6 +233,7 @@ def main():
     ap.add_argument("--histories", type=int, default=500_000_000, help="histories per step per GPU")
     ap.add_argument("--e2e-histories", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-script-level", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-seconds-per-step", type=float, default=8.0)
     args = ap.parse_args()
@@ -368,6 +369,29 @@ def main():
                                          "tle_steps", "tle_entries", "tle_overflows")},
         }
     eng.close()
+    # the same workload with the reference's DEFAULT hit_type ("random", doseactors.py:84-91; the headline uses
+    # "post"): a second, shorter measurement with its own kernel variant, reported under config.variants
+    if args.config == "c3" and world == 1 and rank == 0:
+        Sv = build_setup("c3_hit_random", H)
+        ev = Engine(local, Sv.seed)
+        ev.set_stream(stream.cuda_stream)
+        sv, _, _ = Sv.apply(ev)
+        ev.begin_run()
+        for k in range(2):
+            flush_buf.fill_(1)
+            ev.run_source(sv[0], k * H, H)
+        ev.sync()
+        ev.begin_run()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for k in range(3):
+            flush_buf.fill_(1)
+            ev.run_source(sv[0], (2 + k) * H, H)
+        b.record(stream)
+        torch.cuda.synchronize()
+        line["config"]["variants"] = {"c3_hit_random": {"value": 3 * H / (a.elapsed_time(b) * 1e-3), "unit": UNIT, "steps": 3, "warmup": 2,
+                                                          "kernel": ev.kernel_name(), "what": "hit_type='random', the reference's default"}}
+        ev.close()
     del flush_buf
     torch.cuda.empty_cache()
 
@@ -377,6 +401,8 @@ def main():
     e2e = measure_e2e(S, He, local, rank, world, torch, dist, steps=max(2, min(args.steps, 3)))
     if rank == 0:
         line["e2e"] = e2e
+        if world == 1 and not args.no_script_level:
+            line["e2e_script"] = measure_script_level(args.config, 2 * H, local)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(S, args.cpu_seconds)
     sys.stdout.flush()
@@ -387,6 +413,61 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def measure_script_level(config, n, local):
+    """`e2e_script`: wall clock of Simulation.run() for the bench workload written against the repo's PUBLIC
+    script-level API (Simulation / add_volume("Image") with the int16 HU image / HounsfieldUnit_to_material /
+    GenericSource / DoseActor dose + edep uncertainty) -- what a GATE user calls.  Everything is inside the timed
+    call: HU -> labels, physics tables, H2D, the histories, Gy conversion, D2H of every image the actor keeps.
+    Config 3 only (the other configs have no script twin here)."""
+    if config != "c3":
+        return None
+    import opengate_b200 as gate
+    from opengate_b200 import image as gimage, setups
+    mm, m, MeV, deg = gate.g4_units.mm, gate.g4_units.m, gate.g4_units.MeV, gate.g4_units.deg
+    hu = setups.synthetic_ct_hu()
+    sim = gate.Simulation()
+    sim.random_seed = 987654321
+    sim.output_dir = "/tmp/gate_b200_bench_script"
+    sim.world.size = [2 * m, 2 * m, 2 * m]
+    ct = sim.add_volume("Image", "ct")
+    ct.image = gimage.Image(hu, (0.9766, 0.9766, 1.0))
+    ct.material = "G4_AIR"
+    ct.voxel_materials, _ = gate.geometry.materials.HounsfieldUnit_to_material(sim, 0.05 * gate.g4_units.g_cm3)
+    sim.physics_manager.set_production_cut("world", "all", 1 * m)
+    sim.physics_manager.set_production_cut("ct", "all", 1 * m)
+    src = sim.add_source("GenericSource", "xray")
+    edges, w = setups.spectrum_120kvp()
+    src.energy.type = "spectrum_histogram"
+    src.energy.spectrum_energy_bin_edges = list(edges * MeV)
+    src.energy.spectrum_weights = list(w)
+    src.position.type = "point"
+    src.position.translation = [-600 * mm, 0, 0]
+    src.direction.type = "iso"
+    src.direction.theta = [0, float(np.degrees(np.arctan(0.95 * 250.0 / 600.0))) * deg]
+    src.position.rotation = np.array([[0.0, 0.0, -1.0], [0.0, 1.0, 0.0], [1.0, 0.0, 0.0]])
+    src.direction_relative_to_attached_volume = True
+    src.number_of_primaries = n
+    dose = sim.add_actor("DoseActor", "dose")
+    dose.attached_to = "ct"
+    dose.size = "like_image_volume"
+    dose.spacing = "like_image_volume"
+    dose.hit_type = "post"
+    dose.dose.active = True
+    dose.edep_uncertainty.active = True
+    dose.write_to_disk = False
+    stats = sim.add_actor("SimulationStatisticsActor", "stats")
+    sim.number_of_gpus = 1
+    t0 = time.perf_counter()
+    sim.run()
+    wall = time.perf_counter() - t0
+    e = dose.edep.image.array
+    assert stats.counts["events"] == n and float(e.sum()) > 0
+    return {"value": n / wall, "unit": UNIT, "wall_s": wall, "histories": n,
+            "statistics_actor_duration_s": stats.counts.get("duration", 0) / gate.g4_units.s,
+            "images_returned": ["edep", "edep_squared", "dose"],
+            "what": "wall clock of Simulation.run() of the public script-level API, 1 GPU, CUDA context warm, nothing cached from an earlier run"}
 
 
 def measure_e2e(S, H, local, rank, world, torch, dist, steps=2):

@@ -1,7 +1,10 @@
 /* GateB200TableExporter.cpp — Geant4 photon cross-sections for the device tables of libgate_b200.
  *
- * NOT built in this repository (needs Geant4 + pybind11: it belongs in core/opengate_core/opengate_lib/ of
- * OpenGATE/opengate and is registered from opengate_core.cpp like the other init_* functions).
+ * Belongs in core/opengate_core/opengate_lib/ of OpenGATE/opengate (registered from opengate_core.cpp like the
+ * other init_* functions) and needs Geant4 there.  In this repository it is compiled and run by the CPU test tier
+ * against the stand-in headers of integration/g4shim (tests/test_g4_exporter_shim.py): the code below only uses
+ * G4NistManager::FindOrBuildElement / FindOrBuildMaterial, G4Material::GetDensity / AddElement and
+ * G4EmCalculator::ComputeCrossSectionPerVolume.
  *
  * Pattern followed: GateMaterialMuHandler::SimulateMaterialTable (GateMaterialMuHandler.cpp:296-549, the loop
  * over processes / models at :373-428) and the G4EmCalculator use of GateDoseActor.cpp:465-470 and

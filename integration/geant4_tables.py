@@ -1,5 +1,6 @@
 """Adaptor between the Geant4 exporter (GateB200TableExporter.cpp, built into opengate_core) and the table
-builder of the B200 engine.  NOT imported by this repository: it needs `opengate_core`.
+builder of the B200 engine.  Needs `opengate_core` in production; the CPU test tier runs it against the exporter compiled with the Geant4
+shim headers of integration/g4shim (a fake G4EmCalculator that answers from registered tables).
 
     from opengate_b200 import physics
     from physics_b200 import geant4_element_xs
@@ -14,8 +15,12 @@ the remaining step of INTEGRATION.md section 3.
 import numpy as np
 
 
-def geant4_element_xs(z, e_mev):
-    import opengate_core as g4  # the reference's pybind11 module, with init_GateB200TableExporter registered
+def geant4_element_xs(z, e_mev, g4=None):
+    """`element_xs` callback of build_photon_tables fed by the exporter.  g4: the module that carries
+    GateB200ExportElementPhotonCrossSections -- `opengate_core` in a GATE installation (the default); the CPU test
+    tier passes the exporter compiled against integration/g4shim (tests/test_g4_exporter_shim.py)."""
+    if g4 is None:
+        import opengate_core as g4  # the reference's pybind11 module, with init_GateB200TableExporter registered
     from opengate_b200 import physics_models as pm
 
     e = np.asarray(e_mev, dtype=np.float64)

@@ -76,6 +76,11 @@ struct gate_b200_engine {
   size_t l2_persist_max = 0, l2_window_max = 0;
   bool l2_persist = false;               // measured on B200: a persisting window for the labels is slower (C3 6.0e8 vs 1.0e9/s)
   size_t l2_limit_set = 0;               // cudaLimitPersistingL2CacheSize this engine applied to ITS device
+  // bounding box (voxel indices, inclusive) of the voxels whose label differs from that of voxel 0 (shell_mat);
+  // has_shell: the box is neither empty nor the whole volume
+  int has_shell = 0, shell_mat = 0;
+  int box_lo[3] = {0, 0, 0}, box_hi[3] = {0, 0, 0};
+  double vol_spacing[3] = {1, 1, 1};
   unsigned long long *d_unc_u = nullptr; // scratch of gate_b200_mean_uncertainty: {max bits, count}
   double *d_unc_s = nullptr;             //                                         sum
 };
@@ -128,25 +133,39 @@ int dev_upload(gate_b200_engine *h, const T **out, const T *src, size_t n) {
   return 0;
 }
 
-// Which labels occur in the volume (bit set, one bit per material) and the first voxel whose label
-// has no material: one pass over the device copy of the label volume.
+// Which labels occur in the volume (bit set, one bit per material), the first voxel whose label has no material,
+// and the bounding box (voxel indices) of the voxels whose label differs from that of voxel 0 (the inner box of
+// the homogeneous shell): one pass over the device copy of the label volume.
 template <typename LabelT>
 __global__ void __launch_bounds__(256) label_scan_kernel(const LabelT *__restrict__ labels, unsigned long long nv, int nmat,
-                                                         unsigned *__restrict__ present, unsigned long long *first_bad) {
+                                                         int nx, int ny, unsigned *__restrict__ present,
+                                                         unsigned long long *first_bad, int *__restrict__ bbox) {
   extern __shared__ unsigned s_present[];
+  __shared__ int s_box[6];
   const int nw = (nmat + 31) >> 5;
   for (int i = threadIdx.x; i < nw; i += blockDim.x) s_present[i] = 0u;
+  if (threadIdx.x < 6) s_box[threadIdx.x] = (threadIdx.x & 1) ? -1 : 0x7fffffff;   // {min, max} per axis
   __syncthreads();
+  const unsigned l0 = (unsigned)labels[0];
   constexpr int kPer = 16 / (int)sizeof(LabelT);          // labels per 16-byte load
   const unsigned long long nvec = nv / kPer;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  int bx0 = 0x7fffffff, bx1 = -1, by0 = 0x7fffffff, by1 = -1, bz0 = 0x7fffffff, bz1 = -1;
   auto see = [&](unsigned l, unsigned long long idx) {
     if (l >= (unsigned)nmat) { atomicMin(first_bad, idx); return; }
     if (!((s_present[l >> 5] >> (l & 31u)) & 1u)) atomicOr(&s_present[l >> 5], 1u << (l & 31u));
+    if (l != l0) {
+      const int x = (int)(idx % (unsigned long long)nx);
+      const unsigned long long r = idx / (unsigned long long)nx;
+      const int y = (int)(r % (unsigned long long)ny), z = (int)(r / (unsigned long long)ny);
+      bx0 = min(bx0, x); bx1 = max(bx1, x); by0 = min(by0, y); by1 = max(by1, y); bz0 = min(bz0, z); bz1 = max(bz1, z);
+    }
   };
   const uint4 *v4 = reinterpret_cast<const uint4 *>(labels);   // cudaMalloc'ed: 256-byte aligned
+  const unsigned pat = sizeof(LabelT) == 1 ? l0 * 0x01010101u : l0 * 0x00010001u;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
     const uint4 v = __ldg(v4 + i);
+    if (v.x == pat && v.y == pat && v.z == pat && v.w == pat) continue;   // sixteen bytes of the shell label (seen at voxel 0)
     const unsigned w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -161,9 +180,18 @@ __global__ void __launch_bounds__(256) label_scan_kernel(const LabelT *__restric
   }
   for (unsigned long long i = nvec * kPer + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride)
     see((unsigned)labels[i], i);
+  if (blockIdx.x == 0 && threadIdx.x == 0) see(l0, 0);          // the skipped vectors: their label is l0
+  if (bx1 >= 0) {
+    atomicMin(&s_box[0], bx0); atomicMax(&s_box[1], bx1); atomicMin(&s_box[2], by0); atomicMax(&s_box[3], by1);
+    atomicMin(&s_box[4], bz0); atomicMax(&s_box[5], bz1);
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < nw; i += blockDim.x)
     if (s_present[i]) atomicOr(&present[i], s_present[i]);
+  if (threadIdx.x < 6 && s_box[1] >= 0) {
+    if (threadIdx.x & 1) atomicMax(&bbox[threadIdx.x], s_box[threadIdx.x]);
+    else atomicMin(&bbox[threadIdx.x], s_box[threadIdx.x]);
+  }
 }
 
 // HU -> label on the device: label = bin_labels[np.digitize(hu, bins)] with sorted bins, i.e. the number
@@ -420,19 +448,26 @@ static int finish_image_volume(gate_b200_engine *h, uint8_t *dl, const void *hos
     const int nw = (P.nmat + 31) / 32;
     unsigned *d_present = nullptr;
     unsigned long long *d_bad = nullptr;
+    int *d_box = nullptr;
     if (int rc = dev_alloc(h, &d_present, (size_t)nw, true)) return rc;
     if (int rc = dev_alloc(h, &d_bad, 1)) return rc;
+    if (int rc = dev_alloc(h, &d_box, 6)) return rc;
     CU(cudaMemsetAsync(d_bad, 0xff, sizeof(unsigned long long), h->stream));
+    int box[6] = {0x7fffffff, -1, 0x7fffffff, -1, 0x7fffffff, -1};
+    CU(cudaMemcpyAsync(d_box, box, sizeof box, cudaMemcpyHostToDevice, h->stream));
     const int blocks = (int)std::min<size_t>((size_t)h->sm_count * 8, (nv + 4095) / 4096);
     if (label_bytes == 1)
-      label_scan_kernel<uint8_t><<<blocks, 256, nw * sizeof(unsigned), h->stream>>>(dl, nv, P.nmat, d_present, d_bad);
+      label_scan_kernel<uint8_t><<<blocks, 256, nw * sizeof(unsigned), h->stream>>>(dl, nv, P.nmat, size[0], size[1], d_present, d_bad, d_box);
     else
-      label_scan_kernel<uint16_t><<<blocks, 256, nw * sizeof(unsigned), h->stream>>>(reinterpret_cast<const uint16_t *>(dl), nv, P.nmat, d_present, d_bad);
+      label_scan_kernel<uint16_t><<<blocks, 256, nw * sizeof(unsigned), h->stream>>>(reinterpret_cast<const uint16_t *>(dl), nv, P.nmat, size[0], size[1], d_present, d_bad, d_box);
     CU(cudaGetLastError());
     std::vector<unsigned> words(nw, 0u);
     unsigned long long bad = ~0ull;
+    uint16_t lab0 = 0;
     CU(cudaMemcpyAsync(words.data(), d_present, nw * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(box, d_box, sizeof box, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(&lab0, dl, (size_t)label_bytes, cudaMemcpyDeviceToHost, h->stream));   // little endian
     CU(cudaStreamSynchronize(h->stream));
     if (bad != ~0ull) {
       const size_t i = (size_t)bad;
@@ -443,6 +478,24 @@ static int finish_image_volume(gate_b200_engine *h, uint8_t *dl, const void *hos
         CU(cudaMemcpy(&v16, dl + i * (size_t)label_bytes, (size_t)label_bytes, cudaMemcpyDeviceToHost));   // little endian
       }
       return fail(h, GATE_B200_EINVAL, "label %d at voxel %zu has no material", (int)v16, i);
+    }
+    // the shell: the voxels outside the bounding box of the labels that differ from the label of voxel 0 (all of
+    // one material); none when the volume is homogeneous or the box is the whole volume
+    h->has_shell = 0;
+    h->shell_mat = (int)lab0;
+    if (box[1] >= 0 && !(box[0] == 0 && box[1] == size[0] - 1 && box[2] == 0 && box[3] == size[1] - 1 && box[4] == 0 && box[5] == size[2] - 1)) {
+      h->has_shell = 1;
+      for (int a = 0; a < 3; ++a) { h->box_lo[a] = box[2 * a]; h->box_hi[a] = box[2 * a + 1]; }
+    }
+    for (int a = 0; a < 3; ++a) h->vol_spacing[a] = spacing[a];
+    // the inner box of the shell in the volume frame (same double expressions as the oracle)
+    P.shell = (h->has_shell && !getenv("GATE_B200_NO_SHELL")) ? 1 : 0;
+    P.shell_mat = h->shell_mat;
+    for (int a = 0; a < 3; ++a) {
+      const double lo = -0.5 * size[a] * spacing[a] + h->box_lo[a] * spacing[a];
+      const double hi = -0.5 * size[a] * spacing[a] + (h->box_hi[a] + 1) * spacing[a];
+      P.tc[a] = P.shell ? (float)(0.5 * (lo + hi)) : 0.0f;
+      P.th[a] = P.shell ? (float)(0.5 * (hi - lo)) : 0.0f;
     }
     for (int m = 0; m < P.nmat; ++m) present[m] = (char)((words[m >> 5] >> (m & 31)) & 1u);
   }

@@ -152,6 +152,11 @@ struct Params {
   float half[3], inv_sp[3], sp[3], hs[3];   // hs = n / 2: voxel coordinate = p * inv_sp + hs
   Affine w2v;
   const void *labels;
+  // The homogeneous shell of the image volume: every voxel outside the box (centre tc, half size th, volume frame)
+  // carries the label shell_mat (the air around a patient).  A Woodcock call that starts out there first crosses
+  // the shell analytically with the optical depth of its first flight (see volume_gather_labels).
+  int shell, shell_mat;
+  float tc[3], th[3];
   int ndose;
   DDose dose[kMaxDose];
   int nphsp;
@@ -279,6 +284,22 @@ __device__ __forceinline__ void snap_to_face(float p[3], const float d[3], const
 
 __device__ __forceinline__ bool inside_box(const float p[3], const float h[3]) {
   return p[0] > -h[0] && p[0] < h[0] && p[1] > -h[1] && p[1] < h[1] && p[2] > -h[2] && p[2] < h[2];
+}
+
+// ray / point against the inner box of the shell (centre P.tc, half size P.th, volume frame)
+__device__ __forceinline__ bool ray_tbox_ax(const Params &P, const float p[3], const float d[3], float &t_in, float &t_out, int &a_in, int &a_out) {
+  const float q[3] = {p[0] - P.tc[0], p[1] - P.tc[1], p[2] - P.tc[2]};
+  return ray_box_ax(q, d, P.th, t_in, t_out, a_in, a_out);
+}
+__device__ __forceinline__ bool inside_tbox(const Params &P, const float p[3]) {
+  const float q[3] = {p[0] - P.tc[0], p[1] - P.tc[1], p[2] - P.tc[2]};
+  return inside_box(q, P.th);
+}
+__device__ __forceinline__ void snap_to_tface(const Params &P, float p[3], const float d[3], int a, bool outward) {
+  float q[3] = {p[0] - P.tc[0], p[1] - P.tc[1], p[2] - P.tc[2]};
+  snap_to_face(q, d, P.th, a, outward);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) p[k] = q[k] + P.tc[k];
 }
 
 __device__ __forceinline__ int lower_bound_f(const float *__restrict__ a, int n, float p) {
@@ -1015,6 +1036,14 @@ __device__ __forceinline__ int phase_world(const Params &P, Smem &S, int slot, i
 // The call is split into three stages (gather labels / gather attenuation / decide) so that one lane
 // can run them for kVWidth slots side by side: kVWidth * kWoodcockK independent gathers in flight per
 // thread, which is what hides the DRAM/L2 latency at 32 warps per SM.
+constexpr unsigned kShellHit = 1u << 8;    // VCall::inb: the call ended with an interaction in the shell
+constexpr unsigned kShellLeft = 1u << 9;   //             the photon leaves the volume through the shell
+// a slot moves along its ray by t (shell crossing at the start of a Woodcock call)
+__device__ __forceinline__ void S_put_point(Smem &S, int slot, float x, float y, float z, float t) {
+  S.px[slot] = x; S.py[slot] = y; S.pz[slot] = z;
+  S.path[slot] = S.path[slot] + t;
+  S.seg[slot] = S.seg[slot] + t;
+}
 struct VCall {
   float s[kWoodcockK];          // flight lengths
   uint32_t racc[kWoodcockK];    // acceptance variates (raw Philox words)
@@ -1027,7 +1056,7 @@ struct VCall {
 };
 
 template <typename LabelT>
-__device__ __forceinline__ void volume_gather_labels(const Params &P, const Smem &S, const float *__restrict__ s_maj,
+__device__ __forceinline__ void volume_gather_labels(const Params &P, Smem &S, const float *__restrict__ s_maj,
                                                      int slot, VCall &c) {
   c.blk = S.blk[slot];
   float a0 = S.px[slot], a1 = S.py[slot], a2 = S.pz[slot];
@@ -1036,16 +1065,72 @@ __device__ __forceinline__ void volume_gather_labels(const Params &P, const Smem
   const float m0 = s_maj[c.ie], m1 = s_maj[c.ie + 1];
   c.maj = __fmaf_rn(c.fe, m1 - m0, m0);
   const float inv_maj = 1.0f / c.maj;
+  c.inb = 0u;
+  // ---- a call that starts in the homogeneous shell (outside the inner box): geometry of the way to the box (or,
+  // if the ray misses it, to the face of the volume); evaluated before the random numbers exist to keep it cheap
+  float sh_mu = 0.0f, sh_tb = 0.0f, sh_lim = -1.0f;   // sh_lim < 0: not in the shell
+  int sh_ax = -1;
+  bool sh_hit = false;
+  if (P.shell) {
+    const float ps[3] = {a0, a1, a2}, dd[3] = {d0, d1, d2};
+    if (!inside_tbox(P, ps)) {
+      sh_mu = tab_mu(P, P.shell_mat, c.ie, c.fe);
+      // slab tests against the inner box (entry) and the volume (exit) with one reciprocal per axis
+      float tmin = -kBig, tmax = kBig, tout = kBig;
+      int ain = -1;
+      bool miss = false;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float q = ps[a] - P.tc[a];
+        if (dd[a] != 0.0f) {
+          const float inv = 1.0f / dd[a];
+          float t1 = (-P.th[a] - q) * inv, t2 = (P.th[a] - q) * inv;
+          if (t1 > t2) { const float w = t1; t1 = t2; t2 = w; }
+          if (t1 > tmin) { tmin = t1; ain = a; }
+          if (t2 < tmax) tmax = t2;
+          const float v1 = (-P.half[a] - ps[a]) * inv, v2 = (P.half[a] - ps[a]) * inv;
+          const float vm = v1 > v2 ? v1 : v2;
+          if (vm < tout) tout = vm;
+        } else if (q < -P.th[a] || q > P.th[a]) {
+          miss = true;
+        }
+      }
+      const float t0 = tmin > 0.0f ? tmin : 0.0f;
+      sh_hit = !miss && tmax > t0;
+      sh_tb = t0;
+      sh_ax = tmin > 0.0f ? ain : -1;
+      sh_lim = sh_hit ? t0 : (tout > 0.0f ? tout : 0.0f);
+    }
+  }
   uint32_t r[2 * kWoodcockK];
   {
     const unsigned long long id = P.first + S.hidx[slot];
     philox_block2((uint32_t)P.seed, (uint32_t)(P.seed >> 32), (uint32_t)id, (uint32_t)(id >> 32), c.blk, r);
   }
   const LabelT *__restrict__ labels = reinterpret_cast<const LabelT *>(P.labels);
-  c.inb = 0u;
+  float tau0 = -d_logf(u32_to_uniform(r[0]));   // optical depth to the first event of the call
+  if (sh_lim >= 0.0f) {
+    // The same optical depth first runs down at the attenuation of the shell material: either it is used up before
+    // the box / the volume face -- a real interaction in the shell, no rejection needed --, or the photon reaches
+    // the box with the remainder, or it leaves the volume.
+    if (tau0 < sh_mu * sh_lim) {
+      const float ts = tau0 / sh_mu;
+      S_put_point(S, slot, a0 + d0 * ts, a1 + d1 * ts, a2 + d2 * ts, ts);
+      c.inb |= kShellHit;
+    } else if (!sh_hit) {
+      c.inb |= kShellLeft;
+    } else {
+      float q[3] = {a0 + d0 * sh_tb, a1 + d1 * sh_tb, a2 + d2 * sh_tb};
+      const float dd[3] = {d0, d1, d2};
+      snap_to_tface(P, q, dd, sh_ax, false);
+      S_put_point(S, slot, q[0], q[1], q[2], sh_tb);
+      a0 = q[0]; a1 = q[1]; a2 = q[2];
+      tau0 = __fmaf_rn(-sh_mu, sh_tb, tau0);
+    }
+  }
 #pragma unroll
   for (int k = 0; k < kWoodcockK; ++k) {
-    c.s[k] = -d_logf(u32_to_uniform(r[2 * k])) * inv_maj;
+    c.s[k] = (k == 0 ? tau0 : -d_logf(u32_to_uniform(r[2 * k]))) * inv_maj;
     c.racc[k] = r[2 * k + 1];
     a0 = __fmaf_rn(d0, c.s[k], a0); a1 = __fmaf_rn(d1, c.s[k], a1); a2 = __fmaf_rn(d2, c.s[k], a2);
     // continuous voxel coordinate: a / spacing + n / 2 in one fused operation
@@ -1083,7 +1168,11 @@ __device__ __forceinline__ int volume_decide(const Params &P, Smem &S, int slot,
   int mat = 0;
   float vsel = 0.0f;
   unsigned tent = 0;
-  bool left = false, hit = false;
+  bool left = (c.inb & kShellLeft) != 0, hit = (c.inb & kShellHit) != 0;
+  if (hit) {                  // interaction in the shell material: the acceptance variate of the first flight selects the process
+    mat = P.shell_mat;
+    vsel = u32_to_uniform(c.racc[0]);
+  }
 #pragma unroll
   for (int k = 0; k < kWoodcockK; ++k) {
     if (hit || left) continue;

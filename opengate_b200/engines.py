@@ -252,19 +252,19 @@ class GpuSimulationEngine:
         return int(np.sum(self._counts)) if self._counts else 0
 
     # ------------------------------------------------------------------------ devices
-    def _init_devices(self):
+    def _init_devices(self, seed):
         sim = self.sim
         if self._backend is not None:
-            self.engines = [self._backend(0, self.setup.seed)]
+            self.engines = [self._backend(0, seed)]
             return
         from .core import Engine
         if self.dist is not None:
             if sim.number_of_gpus not in (None, self.world):
                 warning(f"number_of_gpus={sim.number_of_gpus} ignored: running under torchrun with {self.world} ranks")
-            self.engines = [Engine(self.local_rank, self.setup.seed)]
+            self.engines = [Engine(self.local_rank, seed)]
         else:
             n = int(sim.number_of_gpus or 1)
-            self.engines = [Engine(g, self.setup.seed) for g in range(n)]
+            self.engines = [Engine(g, seed) for g in range(n)]
 
     @property
     def n_shards(self):
@@ -303,8 +303,26 @@ class GpuSimulationEngine:
         t_init = time.perf_counter()
         self._detect_process_group()
         self._share_random_seed()
-        self.build_setup()
-        self._init_devices()
+        # the CUDA context of a process takes about a second to come up: the devices are opened on a worker thread
+        # (ctypes releases the GIL) while this thread turns the simulation into tables and descriptors
+        import threading
+        seed = int(sim.current_random_seed) & (2 ** 64 - 1)
+        opened = {}
+
+        def open_devices():
+            try:
+                self._init_devices(seed)
+            except BaseException as e:   # re-raised on the main thread
+                opened["error"] = e
+
+        th = threading.Thread(target=open_devices, daemon=True)
+        th.start()
+        try:
+            self.build_setup()
+        finally:
+            th.join()
+        if "error" in opened:
+            raise opened["error"]
         self.ids = [self.setup.apply(e) for e in self.engines]
         out = SimulationOutput()
         out.current_random_seed = sim.current_random_seed

@@ -257,14 +257,31 @@ def nist_mu_en_cm2_g(z: int, e_mev):
 _COARSE_N = 160
 
 
-@functools.lru_cache(maxsize=128)
-def _element_models_coarse(z: int):
+def _compute_element_models_coarse(z: int):
     """Compton / Rayleigh / pair on a coarse log grid (they are smooth in E)."""
     e = np.exp(np.linspace(np.log(1e-3), np.log(20.0), _COARSE_N))
     sc, ftr = compton_xs_barn(z, e)
     sr = rayleigh_xs_barn(z, e)
     sp = pair_xs_barn(z, e)
     return e, sc, ftr, sr, sp
+
+
+@functools.lru_cache(maxsize=1)
+def _element_models_file():
+    """data/element_models_coarse.npz (tools/gen_element_models.py): the function above tabulated for Z = 1..100"""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "element_models_coarse.npz")
+    if not os.path.exists(path) or os.environ.get("GATE_B200_NO_MODEL_CACHE"):
+        return None
+    d = np.load(path)
+    return {k: d[k] for k in d.files}
+
+
+@functools.lru_cache(maxsize=128)
+def _element_models_coarse(z: int):
+    d = _element_models_file()
+    if d is not None and f"sc_{z}" in d and len(d["energy_MeV"]) == _COARSE_N:
+        return d["energy_MeV"], d[f"sc_{z}"], d[f"ftr_{z}"], d[f"sr_{z}"], d[f"sp_{z}"]
+    return _compute_element_models_coarse(z)
 
 
 def element_process_xs(z: int, e_mev):

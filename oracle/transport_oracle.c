@@ -256,6 +256,11 @@ struct oracle_engine {
   real_t half[3], inv_sp[3], sp[3], hs[3];
   affine_t w2v;
   void *labels;
+  /* the homogeneous shell: every voxel outside the box (centre tc, half size th, volume frame; the bounding box of
+   * the voxels whose label differs from that of voxel 0) carries the label shell_mat.  A Woodcock call that starts
+   * out there first crosses the shell analytically with the optical depth of its first flight. */
+  int shell, shell_mat;
+  real_t tc[3], th[3];
   /* actors, sources */
   int nsrc; osource_t *src;
   int ndose; odose_t dose[ORACLE_MAX_DOSE];
@@ -351,6 +356,17 @@ static void snap_to_face(real_t p[3], const real_t d[3], const real_t h[3], int 
 
 static int inside_box(const real_t p[3], const real_t h[3]) {
   return p[0] > -h[0] && p[0] < h[0] && p[1] > -h[1] && p[1] < h[1] && p[2] > -h[2] && p[2] < h[2];
+}
+
+/* point against / coordinate snapped to a face of the inner box of the shell (centre tc, half size th) */
+static int inside_tbox(const oracle_engine *g, const real_t p[3]) {
+  const real_t q[3] = {p[0] - g->tc[0], p[1] - g->tc[1], p[2] - g->tc[2]};
+  return inside_box(q, g->th);
+}
+static void snap_to_tface(const oracle_engine *g, real_t p[3], const real_t d[3], int a, int outward) {
+  real_t q[3] = {p[0] - g->tc[0], p[1] - g->tc[1], p[2] - g->tc[2]};
+  snap_to_face(q, d, g->th, a, outward);
+  for (int k = 0; k < 3; ++k) p[k] = q[k] + g->tc[k];
 }
 
 /* ------------------------------------------------------------------ table access */
@@ -1118,8 +1134,72 @@ static void run_photon(hist_t *h, real_t pend_p[3], real_t pend_d[3], int *pend)
       real_t u[2 * WOODCOCK_K];
       rng_begin(&h->rng);
       for (int k = 0; k < 2 * WOODCOCK_K; ++k) u[k] = rng_uniform(&h->rng);
-      for (int k = 0; k < WOODCOCK_K; ++k) {
-        real_t s = -R_LOG(u[2 * k]) * inv_maj;
+      real_t tau0 = -R_LOG(u[0]); /* optical depth to the first event of the call */
+      int shell_done = 0;
+      if (g->shell && !inside_tbox(g, h->p)) {
+        /* The call starts in the homogeneous shell (outside the inner box).  The optical depth of the first flight
+         * first runs down at the attenuation of the shell material along the way to the box (or, if the ray misses
+         * it, to the face of the volume): either it is used up there -- a real interaction in the shell, no
+         * rejection needed, the acceptance variate of the flight selects the process --, or the photon reaches the
+         * box with the remainder, or it leaves the volume.  Slab tests against the box (entry) and the volume (exit)
+         * with one reciprocal per axis. */
+        const real_t mu_s = tab(g->mu, g->ne, g->shell_mat, h->ie, h->fe);
+        real_t tmin = -BIG, tmax = BIG, tout = BIG;
+        int ain = -1, miss = 0;
+        for (int a = 0; a < 3; ++a) {
+          const real_t q = h->p[a] - g->tc[a];
+          if (h->d[a] != 0.0f) {
+            const real_t inv = 1.0f / h->d[a];
+            real_t t1 = (-g->th[a] - q) * inv, t2 = (g->th[a] - q) * inv;
+            if (t1 > t2) { const real_t w = t1; t1 = t2; t2 = w; }
+            if (t1 > tmin) { tmin = t1; ain = a; }
+            if (t2 < tmax) tmax = t2;
+            const real_t v1 = (-g->half[a] - h->p[a]) * inv, v2 = (g->half[a] - h->p[a]) * inv;
+            const real_t vm = v1 > v2 ? v1 : v2;
+            if (vm < tout) tout = vm;
+          } else if (q < -g->th[a] || q > g->th[a]) {
+            miss = 1;
+          }
+        }
+        const real_t t0 = tmin > 0.0f ? tmin : 0.0f;
+        const int hit_box = !miss && tmax > t0;
+        const int ax_in = tmin > 0.0f ? ain : -1;
+        const real_t t_lim = hit_box ? t0 : (tout > 0.0f ? tout : 0.0f);
+        if (tau0 < mu_s * t_lim) {
+          const real_t ts = tau0 / mu_s;
+          for (int a = 0; a < 3; ++a) h->p[a] = h->p[a] + h->d[a] * ts;
+          h->path = h->path + ts;
+          h->seg = h->seg + ts;
+          int proc = select_process(h, g->shell_mat, u[1]);
+          tle_march(h, 0.0f);
+          int ix = (int)R_FMA(h->p[0], g->inv_sp[0], g->hs[0]), iy = (int)R_FMA(h->p[1], g->inv_sp[1], g->hs[1]),
+              iz = (int)R_FMA(h->p[2], g->inv_sp[2], g->hs[2]);
+          alive = interact(h, proc, g->shell_mat, ix, iy, iz, pend_p, pend_d, pend);
+          shell_done = 1;
+        } else if (!hit_box) {
+          /* leaves the volume through the shell: restart from the exit point in the world frame */
+          real_t ti, to;
+          int ai, ao;
+          if (!ray_box_ax(h->p, h->d, g->half, &ti, &to, &ai, &ao)) { to = 0.0f; ao = -1; }
+          tle_march(h, to);
+          for (int a = 0; a < 3; ++a) h->p[a] = h->p[a] + h->d[a] * to;
+          snap_to_face(h->p, h->d, g->half, ao, 1);
+          h->path += to;
+          h->st.steps++;
+          to_world(h);
+          h->in_phantom = 0;
+          shell_done = 1;
+        } else {
+          real_t q[3] = {h->p[0] + h->d[0] * t0, h->p[1] + h->d[1] * t0, h->p[2] + h->d[2] * t0};
+          snap_to_tface(g, q, h->d, ax_in, 0);
+          for (int a = 0; a < 3; ++a) h->p[a] = q[a];
+          h->path = h->path + t0;
+          h->seg = h->seg + t0;
+          tau0 = R_FMA(-mu_s, t0, tau0);
+        }
+      }
+      for (int k = 0; k < WOODCOCK_K && !shell_done; ++k) {
+        real_t s = (k == 0 ? tau0 : -R_LOG(u[2 * k])) * inv_maj;
         real_t q[3] = {R_FMA(h->d[0], s, h->p[0]), R_FMA(h->d[1], s, h->p[1]), R_FMA(h->d[2], s, h->p[2])};
         /* continuous voxel coordinate: q / spacing + n / 2 in one fused operation */
         real_t fx = R_FMA(q[0], g->inv_sp[0], g->hs[0]);
@@ -1328,6 +1408,32 @@ int oracle_set_image_volume(oracle_engine *g, const void *labels, int label_byte
   aff_from_d(&g->w2v, w2v);
   g->has_vol = 1;
   build_majorant(g);
+  {
+    int lo[3] = {size[0], size[1], size[2]}, hi[3] = {-1, -1, -1};
+    const int l0 = label_bytes == 1 ? ((const uint8_t *)g->labels)[0] : ((const uint16_t *)g->labels)[0];
+    size_t i = 0;
+    for (int z = 0; z < size[2]; ++z)
+      for (int y = 0; y < size[1]; ++y)
+        for (int x = 0; x < size[0]; ++x, ++i) {
+          const int m = label_bytes == 1 ? ((const uint8_t *)g->labels)[i] : ((const uint16_t *)g->labels)[i];
+          if (m == l0) continue;
+          if (x < lo[0]) lo[0] = x;
+          if (x > hi[0]) hi[0] = x;
+          if (y < lo[1]) lo[1] = y;
+          if (y > hi[1]) hi[1] = y;
+          if (z < lo[2]) lo[2] = z;
+          if (z > hi[2]) hi[2] = z;
+        }
+    /* the shell exists when that box is neither empty (homogeneous volume) nor the whole volume */
+    g->shell = hi[0] >= 0 && !(lo[0] == 0 && hi[0] == size[0] - 1 && lo[1] == 0 && hi[1] == size[1] - 1 && lo[2] == 0 && hi[2] == size[2] - 1);
+    g->shell_mat = l0;
+    for (int a = 0; a < 3; ++a) {
+      const double l = -0.5 * size[a] * spacing[a] + lo[a] * spacing[a];
+      const double u = -0.5 * size[a] * spacing[a] + (hi[a] + 1) * spacing[a];
+      g->tc[a] = g->shell ? (real_t)(0.5 * (l + u)) : 0.0f;
+      g->th[a] = g->shell ? (real_t)(0.5 * (u - l)) : 0.0f;
+    }
+  }
   return 0;
 }
 

@@ -2,7 +2,7 @@
 # round 2, call a: GPU test tier, ncu captures of the kernel variants the bench times, baseline bench
 mkdir -p gpurun_out
 T=r2a
-( timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/${T}_pytest.log )
+( timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/${T}_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/${T}_pytest.log )
 tail -5 gpurun_out/${T}_pytest.log
 for cfg in c3 c3_hit_random c4; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:transport_kernel -s 1 -c 1 \

@@ -1,0 +1,13 @@
+#!/bin/bash
+# round 2, call c: shell flights: parity, A/B timing
+mkdir -p gpurun_out
+T=r2c
+( timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/${T}_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/${T}_pytest.log )
+tail -15 gpurun_out/${T}_pytest.log
+{
+for lib in "" gpurun_variants/lib_lazy.so gpurun_variants/lib_t768.so gpurun_variants/lib_t1024.so; do
+  echo "== lib=${lib:-default}"
+  for c in c3 c2 c1 c4 c3_hit_random; do env ${lib:+GATE_B200_LIB=$lib} timeout 120 python tools/profile_run.py --config $c --histories 100000000 --launches 2 | cut -c1-24,100-400; done
+done
+} > gpurun_out/${T}_ab.log 2>&1
+cat gpurun_out/${T}_ab.log

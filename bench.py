@@ -481,7 +481,10 @@ def measure_e2e(S, H, local, rank, world, torch, dist, steps=2):
     G = n_active_grids(S)
     nx, ny, nz = desc0(S).size[0], desc0(S).size[1], desc0(S).size[2]
     which = multigpu.active_grids(desc0(S).score_flags)
-    host_out = [torch.empty((nz, ny, nx), dtype=torch.float64, pin_memory=True).numpy() for _ in range(G)] if rank == 0 else []
+    host_out = [torch.empty((nz, ny, nx), dtype=torch.float64, pin_memory=True).numpy() for _ in range(G)] if (rank == 0 and world == 1) else []
+    # N > 1: the result lands in host arrays shared by the ranks of the node; after the all-reduce every rank copies
+    # 1/N of every grid, so the device -> host read uses the host links of all GPUs (multigpu.SharedHostGrids)
+    shared = multigpu.SharedHostGrids(Engine(local, S.seed), [(nz, ny, nx)] * G) if world > 1 else None
     S = copy.copy(S)
     pinned_labels = torch.empty(S.labels.shape, dtype=torch.uint8 if S.labels.dtype == np.uint8 else torch.int16, pin_memory=True)
     lab = pinned_labels.numpy().view(S.labels.dtype)
@@ -513,10 +516,13 @@ def measure_e2e(S, H, local, rank, world, torch, dist, steps=2):
         eng.sync()
         lap("run")
         if world > 1:
-            multigpu.reduce_dose_grids(eng, dids, S, dst=0)
+            multigpu.all_reduce_dose_grids(eng, dids)
             torch.cuda.synchronize()
         lap("reduce")
-        if rank == 0:
+        if world > 1:
+            shared.engine = eng
+            shared.gather(dids[0], which)          # D2H: every rank 1/N of every grid into the shared arrays + barrier
+        else:
             for w, out in zip(which, host_out):   # D2H: every active accumulator grid
                 eng.dose_grid(dids[0], w, out)
         lap("d2h")
@@ -536,11 +542,19 @@ def measure_e2e(S, H, local, rank, world, torch, dist, steps=2):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt = float(tt.item())
+    if shared is not None:
+        e0 = shared.engine
+        shared.engine = Engine(local, S.seed)
+        if rank == 0:
+            assert float(shared.arrays[0].sum()) > 0.0
+        shared.close()
+        shared.engine.close()
     return {"value": world * H * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "histories_per_step_per_gpu": H, "steps": steps,
             "ms_per_step_by_section_rank0": {k: 1e3 * v / steps for k, v in parts.items()},
             "what": "gate_b200 C-ABI from pinned host buffers: create + set_tables + set_image_volume (H2D) + run"
-                    + (" + NCCL reduce to rank 0" if world > 1 else "") + " + get_dose_grid of every grid (D2H) per step"}
+                    + (" + NCCL all-reduce + every rank copies 1/N of every grid into host arrays shared by the ranks" if world > 1
+                       else " + get_dose_grid of every grid (D2H)") + " per step"}
 
 
 if __name__ == "__main__":

@@ -264,6 +264,11 @@ int gate_b200_get_dose_grid(gate_b200_engine *h, int32_t actor_id, int32_t which
  * DoseActor.EndOfRunActionMasterThread (doseactors.py:685-696: dose /= Gy * voxel volume, squares by its square)
  * without a host pass over the image. */
 int gate_b200_get_dose_grid_scaled(gate_b200_engine *h, int32_t actor_id, int32_t which, double scale, double *out);
+/* The voxels [first, first + count) of one accumulator grid (x fastest), scaled: on a multi-GPU node every rank
+ * holds the reduced grids after the all-reduce and copies a DIFFERENT slice into one host array shared by the
+ * ranks, so that the device -> host read of the result uses the host links of all GPUs at once. */
+int gate_b200_get_dose_grid_range(gate_b200_engine *h, int32_t actor_id, int32_t which, double scale,
+                                  uint64_t first, uint64_t count, double *out);
 /* Replaces: the uncertainty item of the reference's data containers (actors/dataitems.py:1956-1993 with
  * utility.py:551-560) evaluated on the device from the value and squared-value accumulators of one run:
  * out = sqrt(clip((S2/n - (S/n)^2) / (n - 1), 0)) / (S/n) where S != 0, else 0; which = GATE_B200_GRID_EDEP or

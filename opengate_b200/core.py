@@ -33,7 +33,7 @@ EXPORTS = [
     "gate_b200_get_dose_grid", "gate_b200_dose_buffers", "gate_b200_set_dose_grid",
     "gate_b200_mean_uncertainty", "gate_b200_phsp_count", "gate_b200_get_phsp",
     "gate_b200_get_stats", "gate_b200_timed_run", "gate_b200_kernel_name",
-    "gate_b200_get_dose_grid_scaled", "gate_b200_get_uncertainty", "gate_b200_host_register", "gate_b200_host_unregister",
+    "gate_b200_get_dose_grid_scaled", "gate_b200_get_dose_grid_range", "gate_b200_get_uncertainty", "gate_b200_host_register", "gate_b200_host_unregister",
 ]
 
 
@@ -96,6 +96,7 @@ def load_library():
     L.gate_b200_get_dose_grid.argtypes = [vp, i32, i32, C.POINTER(C.c_double)]
     L.gate_b200_set_dose_grid.argtypes = [vp, i32, i32, C.POINTER(C.c_double)]
     L.gate_b200_get_dose_grid_scaled.argtypes = [vp, i32, i32, C.c_double, C.POINTER(C.c_double)]
+    L.gate_b200_get_dose_grid_range.argtypes = [vp, i32, i32, C.c_double, u64, u64, C.POINTER(C.c_double)]
     L.gate_b200_get_uncertainty.argtypes = [vp, i32, i32, u64, C.POINTER(C.c_double)]
     L.gate_b200_host_register.argtypes = [vp, u64]
     L.gate_b200_host_unregister.argtypes = [vp]
@@ -249,6 +250,14 @@ class Engine:
         if out is None:
             out = np.empty((nz, ny, nx), dtype=np.float64)
         self._check(self.L.gate_b200_get_dose_grid_scaled(self.h, actor, which, float(scale), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def dose_grid_range(self, actor, which, first, count, out, scale=1.0):
+        """voxels [first, first + count) of one accumulator grid (flat, x fastest) into out[first:first + count] of a
+        flat float64 array `out` that spans the whole grid (e.g. one shared by the ranks of a node)"""
+        flat = out.reshape(-1)
+        ptr = C.cast(flat.ctypes.data + 8 * int(first), C.POINTER(C.c_double))
+        self._check(self.L.gate_b200_get_dose_grid_range(self.h, actor, which, float(scale), C.c_uint64(int(first)), C.c_uint64(int(count)), ptr))
         return out
 
     def uncertainty_grid(self, actor, which, n_events, out=None):

@@ -54,7 +54,7 @@ struct gate_b200_engine {
   bool have_tables = false, have_volume = false;
   Params P;
   std::vector<void *> allocs;           // everything to cudaFree
-  std::vector<float> h_mu;              // host copy for the majorant
+  std::vector<float> h_mu, h_dens;      // host copies for the majorant / the shell rule
   std::vector<DoseActor> dose;
   std::vector<PhspActor> phsp;
   std::vector<SourceRec> src;
@@ -409,6 +409,7 @@ int gate_b200_set_tables(gate_b200_engine *h, const gate_b200_tables *t) {
   if (int rc = dev_upload(h, &P.ray, t->rayl_cum_ff2, nqq)) return rc;
   if (int rc = dev_upload(h, &P.sf, t->compt_sf, nqq)) return rc;
   h->h_mu.assign(t->mu_total_per_mm, t->mu_total_per_mm + n);
+  h->h_dens.assign(t->density_g_cm3, t->density_g_cm3 + P.nmat);
   const double le0 = log(t->e_min_MeV), le1 = log(t->e_max_MeV);
   P.ln_emin = (float)le0;
   P.inv_dlne = (float)((double)(P.ne - 1) / (le1 - le0));
@@ -489,7 +490,10 @@ static int finish_image_volume(gate_b200_engine *h, uint8_t *dl, const void *hos
     }
     for (int a = 0; a < 3; ++a) h->vol_spacing[a] = spacing[a];
     // the inner box of the shell in the volume frame (same double expressions as the oracle)
-    P.shell = (h->has_shell && !getenv("GATE_B200_NO_SHELL")) ? 1 : 0;
+    // only a shell of gas (density < 0.05 g/cm3: the air around a patient) is crossed analytically: in a dense
+    // shell (the water slabs of config 2) the Woodcock steps it replaces are accepted half of the time anyway, and
+    // the extra work at the start of every call that begins out there was measured to cost 11 %
+    P.shell = (h->has_shell && h->h_dens[h->shell_mat] < 0.05f && !getenv("GATE_B200_NO_SHELL")) ? 1 : 0;
     P.shell_mat = h->shell_mat;
     for (int a = 0; a < 3; ++a) {
       const double lo = -0.5 * size[a] * spacing[a] + h->box_lo[a] * spacing[a];
@@ -917,7 +921,8 @@ int gate_b200_run_source(gate_b200_engine *h, int32_t source_id, uint64_t first_
   if (n_histories == 0) return GATE_B200_OK;
   CU(cudaSetDevice(h->device));
   // a slot stores the history index inside its launch in 32 bits: longer requests become several launches
-  const uint64_t kMaxPerLaunch = 1ull << 31;
+  // (and at most 2^24 per persistent CTA: the 32-bit per-CTA event counters of the kernel cannot overflow then)
+  const uint64_t kMaxPerLaunch = std::min<uint64_t>(1ull << 31, (uint64_t)std::max(h->max_ctas, 1) << 24);
   for (uint64_t done = 0; done < n_histories;) {
     const uint64_t k = std::min<uint64_t>(kMaxPerLaunch, n_histories - done);
     if (int rc = launch_histories(h, source_id, first_history + done, k)) return rc;
@@ -970,22 +975,32 @@ static int staging(gate_b200_engine *h, size_t n, double **out) {
   return 0;
 }
 
-int gate_b200_get_dose_grid_scaled(gate_b200_engine *h, int32_t actor_id, int32_t which, double scale, double *out) {
+int gate_b200_get_dose_grid_range(gate_b200_engine *h, int32_t actor_id, int32_t which, double scale, uint64_t first,
+                                  uint64_t count, double *out) {
   if (!h || !out) return GATE_B200_EINVAL;
   double *p; size_t n;
   if (int rc = check_grid(h, actor_id, which, &p, &n)) return rc;
+  if (first > n || count > n - first) return fail(h, GATE_B200_EINVAL, "grid range [%llu, +%llu) exceeds %zu voxels", (unsigned long long)first, (unsigned long long)count, n);
+  if (count == 0) return GATE_B200_OK;
   CU(cudaSetDevice(h->device));
   const size_t stride = which == GATE_B200_GRID_COUNTS ? 1 : (size_t)h->dose[actor_id].dev.gstride;
+  p += (size_t)first * stride;
   if (stride > 1 || scale != 1.0) {
     double *dense;
-    if (int rc = staging(h, n, &dense)) return rc;
-    grid_extract_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(p, n, stride, scale, dense);
+    if (int rc = staging(h, (size_t)count, &dense)) return rc;
+    grid_extract_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(p, (size_t)count, stride, scale, dense);
     CU(cudaGetLastError());
     p = dense;
   }
-  CU(cudaMemcpyAsync(out, p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(out, p, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return GATE_B200_OK;
+}
+
+int gate_b200_get_dose_grid_scaled(gate_b200_engine *h, int32_t actor_id, int32_t which, double scale, double *out) {
+  if (!h) return GATE_B200_EINVAL;
+  if (actor_id < 0 || actor_id >= (int)h->dose.size()) return fail(h, GATE_B200_EINVAL, "unknown dose actor %d", actor_id);
+  return gate_b200_get_dose_grid_range(h, actor_id, which, scale, 0, (uint64_t)h->dose[actor_id].nvox, out);
 }
 
 int gate_b200_get_dose_grid(gate_b200_engine *h, int32_t actor_id, int32_t which, double *out) {

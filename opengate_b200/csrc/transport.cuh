@@ -347,6 +347,11 @@ __device__ __forceinline__ void stat_add64(Smem &S, int idx, unsigned v) {
   const unsigned old = atomicAdd(&S.stats_lo[idx], v);
   if (old + v < old) atomicAdd(&S.stats_hi[idx], 1u);
 }
+// The event counters of one CTA and one launch stay below 2^32 (the host gives a launch at most 2^24 histories per
+// CTA, the per-history counts are a few units): a plain 32-bit add whose result nobody waits for (a fire-and-forget
+// reduction) instead of add + carry.  The counters that can exceed 2^32 per CTA -- tentative collisions, chords
+// of the track-length estimator -- keep the carry.
+__device__ __forceinline__ void stat_add32(Smem &S, int idx, unsigned v) { atomicAdd(&S.stats_lo[idx], v); }
 // opportunistic warp aggregation of a statistics increment (the lanes that arrive together)
 __device__ __forceinline__ void stat_add(Smem &S, int idx, unsigned v) {
   const unsigned act = __activemask();
@@ -361,8 +366,13 @@ __device__ __forceinline__ unsigned stat_reduce_packed(unsigned packed) {
   const unsigned sum = __reduce_add_sync(act, packed);
   return (int)(threadIdx.x & 31u) == __ffs(act) - 1 ? sum : 0u;
 }
+__device__ __forceinline__ void stat_add_small(Smem &S, int idx, unsigned v) {
+  const unsigned act = __activemask();
+  const unsigned sum = __reduce_add_sync(act, v);
+  if ((int)(threadIdx.x & 31u) == __ffs(act) - 1 && sum) stat_add32(S, idx, sum);
+}
 __device__ __forceinline__ void stat_bump(Smem &S, int idx, unsigned v) {
-  if (v) stat_add64(S, idx, v);
+  if (v) stat_add32(S, idx, v);
 }
 // the rare part of a deposit's bookkeeping: coalescing-buffer overflows
 __device__ __forceinline__ void stat_overflow(Smem &S, unsigned over, unsigned flush) {
@@ -1461,7 +1471,7 @@ __device__ __forceinline__ int phase_end(const Params &P, Smem &S, int slot, int
       store_ph(S, slot, g);
     }
   }
-  stat_add(S, S_FLUSH, n_flush);
+  stat_add_small(S, S_FLUSH, n_flush);
   {
     // five 6-bit fields: every count is 0 or 1 per lane
     const unsigned t = stat_reduce_packed(n_abs | (n_hist << 6) | (n_phot << 12) | (n_conv << 18) | (ds.dep << 24));

@@ -90,3 +90,68 @@ def reduce_counters(stats: dict, device, group=None):
     out["edep_total_MeV"] = float(e[0])
     out["kernel_ms"] = float(emax[1])
     return out
+
+
+class SharedHostGrids:
+    """Host arrays shared by the ranks of ONE node (POSIX shared memory), page-locked by every rank: after the
+    all-reduce each rank holds the summed grids and copies a different slice of every grid into the shared array,
+    so the device -> host read of the result runs over the host links of all GPUs at once instead of rank 0's alone
+    (config 3 on 8 GPUs: 1.9 GB, 36 ms through one link).  Rank 0 owns the segment; `arrays[k]` are (z,y,x) float64
+    views, complete on every rank after `gather()`."""
+
+    def __init__(self, engine, shapes, group=None):
+        import numpy as np
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+        self.engine, self.group = engine, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        sizes = [int(np.prod(s)) for s in shapes]
+        total = 8 * sum(sizes)
+        name = [None]
+        if self.rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=max(total, 8))
+            name[0] = self.shm.name
+        dist.broadcast_object_list(name, src=0, group=group)
+        if self.rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+        whole = np.ndarray((sum(sizes),), dtype=np.float64, buffer=self.shm.buf)
+        self.whole = whole
+        self.pinned = bool(engine.pin(whole)) if hasattr(engine, "pin") else False
+        self.arrays, off = [], 0
+        for s, n in zip(shapes, sizes):
+            self.arrays.append(whole[off:off + n].reshape(s))
+            off += n
+        dist.barrier(group=group)
+
+    def gather(self, actor, which_list, scales=None):
+        """every rank copies its slice (split_primaries rule over the voxels) of each grid; barrier; complete arrays"""
+        import torch.distributed as dist
+        for k, w in enumerate(which_list):
+            a = self.arrays[k]
+            first, count = split_primaries(a.size, self.world, self.rank)
+            self.engine.dose_grid_range(actor, w, first, count, a, scale=(scales[k] if scales else 1.0))
+        dist.barrier(group=self.group)
+        return self.arrays
+
+    def close(self):
+        import torch.distributed as dist
+        if self.pinned:
+            self.engine.unpin(self.whole)
+        self.arrays, self.whole = [], None
+        dist.barrier(group=self.group)
+        try:
+            self.shm.close()
+            if self.rank == 0:
+                self.shm.unlink()
+        except Exception:
+            pass
+
+
+def all_reduce_dose_grids(engine, actor_ids, group=None):
+    """Sum the accumulator buffers of the given actors over the ranks, in place, result on EVERY rank (NCCL)."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    for a in actor_ids:
+        for t in buffer_tensors(engine, a):
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)

@@ -1426,6 +1426,8 @@ int oracle_set_image_volume(oracle_engine *g, const void *labels, int label_byte
         }
     /* the shell exists when that box is neither empty (homogeneous volume) nor the whole volume */
     g->shell = hi[0] >= 0 && !(lo[0] == 0 && hi[0] == size[0] - 1 && lo[1] == 0 && hi[1] == size[1] - 1 && lo[2] == 0 && hi[2] == size[2] - 1);
+    /* only a shell of gas (the air around a patient) is crossed this way (device: finish_image_volume) */
+    if (l0 >= g->nmat || !(g->dens[l0] < 0.05f)) g->shell = 0;
     g->shell_mat = l0;
     for (int a = 0; a < 3; ++a) {
       const double l = -0.5 * size[a] * spacing[a] + lo[a] * spacing[a];

@@ -59,6 +59,9 @@ def build_setup(name, histories):
         S.dose[0].hit_type = abi.HIT_RANDOM
         S.name += " hit_type=random"
         return S
+    if name == "c5ct":
+        # config 5 on the CT: the 6 MV spectrum of config 2 into the 512x512x300 synthetic CT (dose + squares)
+        return setups.make_c3(n_primaries=histories, spectrum="6mv")
     if name == "c3small":  # CPU-container debugging only
         return setups.make_c3(nx=128, ny=128, nz=75, spacing=(3.9, 3.9, 4.0), n_primaries=histories)
     raise SystemExit(f"unknown config {name}")
@@ -136,6 +139,10 @@ def measured_traffic_per_history(workload_key, kernel_name):
         return None, f"no ncu capture of workload '{workload_key}'"
     if e.get("kernel") != kernel_name:
         return None, f"capture {e.get('source')} is of '{e.get('kernel')}', launched '{kernel_name}'"
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from ncu_summary import kernel_source_sha
+    if e.get("kernel_source_sha") != kernel_source_sha():
+        return None, f"capture {e.get('source')} is of an older build of '{kernel_name}' (kernel sources changed since)"
     return float(e["dram_bytes_per_history"]), f"{e.get('source')} ({e.get('kernel')}, {e.get('histories_in_capture'):.3g} histories)"
 
 
@@ -231,6 +238,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c3")
     ap.add_argument("--histories", type=int, default=500_000_000, help="histories per step per GPU")
+    ap.add_argument("--total-histories", type=float, default=None,
+                    help="STRONG scaling: this many histories in total over all GPUs and timed steps (config 5: 1e10); "
+                         "histories per step per GPU = total / (gpus * steps)")
     ap.add_argument("--e2e-histories", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-script-level", action="store_true")
@@ -266,6 +276,10 @@ def main():
     from opengate_b200.core import Engine
 
     H = args.histories
+    scaling = "weak"
+    if args.total_histories:
+        H = int(args.total_histories) // (world * args.steps)
+        scaling = "strong"
     S = build_setup(args.config, H)
     eng = Engine(local, S.seed)
     stream = torch.cuda.Stream()          # a real (non-default) stream shared by torch and the engine
@@ -344,8 +358,9 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": S.name, "histories_per_step_per_gpu": H, "seed": S.seed,
+                       "total_histories": (world * H * args.steps if scaling == "strong" else None),
                        "label_dtype": str(S.labels.dtype), "n_materials": len(S.tables.names),
                        "l2": "256 MB L2 flush before every step; accumulator grids "
                              f"({G} x {desc0(S).size[0] * desc0(S).size[1] * desc0(S).size[2] * 8 / 1e6:.0f} MB) exceed L2",
@@ -484,7 +499,7 @@ def measure_e2e(S, H, local, rank, world, torch, dist, steps=2):
     host_out = [torch.empty((nz, ny, nx), dtype=torch.float64, pin_memory=True).numpy() for _ in range(G)] if (rank == 0 and world == 1) else []
     # N > 1: the result lands in host arrays shared by the ranks of the node; after the all-reduce every rank copies
     # 1/N of every grid, so the device -> host read uses the host links of all GPUs (multigpu.SharedHostGrids)
-    shared = multigpu.SharedHostGrids(Engine(local, S.seed), [(nz, ny, nx)] * G) if world > 1 else None
+    shared = multigpu.SharedHostGrids([(nz, ny, nx)] * G) if world > 1 else None
     S = copy.copy(S)
     pinned_labels = torch.empty(S.labels.shape, dtype=torch.uint8 if S.labels.dtype == np.uint8 else torch.int16, pin_memory=True)
     lab = pinned_labels.numpy().view(S.labels.dtype)
@@ -520,8 +535,7 @@ def measure_e2e(S, H, local, rank, world, torch, dist, steps=2):
             torch.cuda.synchronize()
         lap("reduce")
         if world > 1:
-            shared.engine = eng
-            shared.gather(dids[0], which)          # D2H: every rank 1/N of every grid into the shared arrays + barrier
+            shared.gather(eng, dids[0], which)     # D2H: every rank 1/N of every grid into the shared arrays + barrier
         else:
             for w, out in zip(which, host_out):   # D2H: every active accumulator grid
                 eng.dose_grid(dids[0], w, out)
@@ -543,12 +557,9 @@ def measure_e2e(S, H, local, rank, world, torch, dist, steps=2):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt = float(tt.item())
     if shared is not None:
-        e0 = shared.engine
-        shared.engine = Engine(local, S.seed)
         if rank == 0:
             assert float(shared.arrays[0].sum()) > 0.0
         shared.close()
-        shared.engine.close()
     return {"value": world * H * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "histories_per_step_per_gpu": H, "steps": steps,
             "ms_per_step_by_section_rank0": {k: 1e3 * v / steps for k, v in parts.items()},

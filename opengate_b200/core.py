@@ -123,6 +123,15 @@ def release_cached_memory(device=0):
         raise GateB200Error(f"gate_b200_release_cached_memory failed ({rc})")
 
 
+def host_register(array):
+    """page-lock a numpy array in place (gate_b200_host_register); False if the driver refuses"""
+    return load_library().gate_b200_host_register(array.ctypes.data_as(C.c_void_p), C.c_uint64(array.nbytes)) == 0
+
+
+def host_unregister(array):
+    load_library().gate_b200_host_unregister(array.ctypes.data_as(C.c_void_p))
+
+
 class Engine:
     """Object wrapper of one gate_b200_engine handle (one CUDA device)."""
 
@@ -274,10 +283,10 @@ class Engine:
 
     def pin(self, array):
         """page-lock a numpy array in place (gate_b200_host_register); False if the driver refuses"""
-        return self.L.gate_b200_host_register(array.ctypes.data_as(C.c_void_p), C.c_uint64(array.nbytes)) == 0
+        return host_register(array)
 
     def unpin(self, array):
-        self.L.gate_b200_host_unregister(array.ctypes.data_as(C.c_void_p))
+        host_unregister(array)
 
     def set_dose_grid(self, actor, which, array):
         a = np.ascontiguousarray(array, dtype=np.float64)

@@ -99,11 +99,11 @@ class SharedHostGrids:
     (config 3 on 8 GPUs: 1.9 GB, 36 ms through one link).  Rank 0 owns the segment; `arrays[k]` are (z,y,x) float64
     views, complete on every rank after `gather()`."""
 
-    def __init__(self, engine, shapes, group=None):
+    def __init__(self, shapes, group=None, pin=True):
         import numpy as np
         import torch.distributed as dist
         from multiprocessing import shared_memory
-        self.engine, self.group = engine, group
+        self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         sizes = [int(np.prod(s)) for s in shapes]
         total = 8 * sum(sizes)
@@ -114,29 +114,36 @@ class SharedHostGrids:
         dist.broadcast_object_list(name, src=0, group=group)
         if self.rank != 0:
             self.shm = shared_memory.SharedMemory(name=name[0])
-        whole = np.ndarray((sum(sizes),), dtype=np.float64, buffer=self.shm.buf)
-        self.whole = whole
-        self.pinned = bool(engine.pin(whole)) if hasattr(engine, "pin") else False
+        self.whole = np.ndarray((sum(sizes),), dtype=np.float64, buffer=self.shm.buf)
+        self.pinned = False
+        if pin:
+            from . import core
+            self.pinned = bool(core.host_register(self.whole))
         self.arrays, off = [], 0
         for s, n in zip(shapes, sizes):
-            self.arrays.append(whole[off:off + n].reshape(s))
+            self.arrays.append(self.whole[off:off + n].reshape(s))
             off += n
         dist.barrier(group=group)
 
-    def gather(self, actor, which_list, scales=None):
-        """every rank copies its slice (split_primaries rule over the voxels) of each grid; barrier; complete arrays"""
+    def slice_of(self, k):
+        """(first voxel, count) of grid k this rank copies: the split rule of the histories, over the voxels"""
+        return split_primaries(self.arrays[k].size, self.world, self.rank)
+
+    def gather(self, engine, actor, which_list, scales=None):
+        """every rank copies its slice of each grid of `actor` from `engine` (which holds the all-reduced sums)
+        into the shared arrays; barrier; the arrays are complete on every rank"""
         import torch.distributed as dist
         for k, w in enumerate(which_list):
-            a = self.arrays[k]
-            first, count = split_primaries(a.size, self.world, self.rank)
-            self.engine.dose_grid_range(actor, w, first, count, a, scale=(scales[k] if scales else 1.0))
+            first, count = self.slice_of(k)
+            engine.dose_grid_range(actor, w, first, count, self.arrays[k], scale=(scales[k] if scales else 1.0))
         dist.barrier(group=self.group)
         return self.arrays
 
     def close(self):
         import torch.distributed as dist
         if self.pinned:
-            self.engine.unpin(self.whole)
+            from . import core
+            core.host_unregister(self.whole)
         self.arrays, self.whole = [], None
         dist.barrier(group=self.group)
         try:

@@ -241,7 +241,7 @@ def schneider_materials(tol_g_cm3=0.05):
 
 def make_c3(nx=512, ny=512, nz=300, n_primaries=1_000_000_000, seed=987654321,
             flags=abi.SCORE_EDEP | abi.SCORE_EDEP_SQ | abi.SCORE_DOSE, spacing=(0.9766, 0.9766, 1.0),
-            source_distance=600.0, hu=None):
+            source_distance=600.0, hu=None, spectrum="120kvp"):
     """C3: 120 kVp spectrum, point source 600 mm off-axis focused cone, into a synthetic CT
     converted with Schneider (74 materials at 0.05 g/cm3)."""
     if hu is None:
@@ -251,7 +251,7 @@ def make_c3(nx=512, ny=512, nz=300, n_primaries=1_000_000_000, seed=987654321,
     lab16, lut = materials.create_label_array(hu, "G4_AIR", vm)
     names = list(lut.keys())
     mats = [db.find_or_build_material(nm) for nm in names]
-    edges, w = spectrum_120kvp()
+    edges, w = spectrum_6mv() if spectrum == "6mv" else spectrum_120kvp()
     T = physics.build_photon_tables(mats, e_max_mev=edges[-1])
     labels = lab16.astype(np.uint8) if len(names) <= 256 else lab16
     half = np.array([nx * spacing[0], ny * spacing[1], nz * spacing[2]]) / 2
@@ -270,7 +270,8 @@ def make_c3(nx=512, ny=512, nz=300, n_primaries=1_000_000_000, seed=987654321,
     A = dose_world_to_index((nx, ny, nz), spacing)
     d = abi.make_dose_desc((nx, ny, nz), A, flags, abi.HIT_POST)
     wh = tuple(float(max(h + 100.0, source_distance + 100.0)) for h in half)
-    return LowLevelSetup(f"C3 120kVp cone / {nx}x{ny}x{nz} synthetic CT Schneider({len(names)} mat) / DoseActor dose+edep2",
+    title = "C5 6MV cone" if spectrum == "6mv" else "C3 120kVp cone"
+    return LowLevelSetup(f"{title} / {nx}x{ny}x{nz} synthetic CT Schneider({len(names)} mat) / DoseActor dose+edep2",
                          seed, T, wh, names.index("G4_AIR"), labels, tuple(spacing), identity34(), [(s, keep)], [d], [],
                          n_primaries, materials=mats)
 

@@ -162,3 +162,46 @@ def test_engine_under_a_process_group_shares_seed_and_counts(tmp_path):
     assert out.device_stats[0]["histories"] == n0
     np.testing.assert_allclose(edep, dose.edep.image.array, rtol=1e-12, atol=0)
     np.testing.assert_allclose(unc, dose.edep_uncertainty.image.array, rtol=1e-9, atol=0)
+
+
+# ------------------------------------------------------------------------------ shared host arrays of a node
+
+def _shared_worker(rank, world, port, q):
+    sys.path.insert(0, HERE)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class FakeEngine:
+        """holds the 'all-reduced' grids; dose_grid_range as core.Engine implements it"""
+        def __init__(self, grids):
+            self.g = grids
+
+        def dose_grid_range(self, actor, which, first, count, out, scale=1.0):
+            out.reshape(-1)[first:first + count] = self.g[which].reshape(-1)[first:first + count] * scale
+            return out
+
+    shapes = [(5, 7, 3), (5, 7, 3)]
+    grids = {0: np.arange(105, dtype=np.float64).reshape(5, 7, 3), 2: 1000.0 + np.arange(105, dtype=np.float64).reshape(5, 7, 3)}
+    sh = multigpu.SharedHostGrids(shapes, pin=False)
+    arrs = sh.gather(FakeEngine(grids), 0, [0, 2], scales=[1.0, 0.5])
+    ok = np.array_equal(arrs[0], grids[0]) and np.array_equal(arrs[1], grids[2] * 0.5)
+    q.put((rank, bool(ok), sh.slice_of(0)))
+    sh.close()
+    dist.destroy_process_group()
+
+
+def test_shared_host_grids_assemble_the_slices_of_all_ranks():
+    """multigpu.SharedHostGrids: three ranks each copy their slice of two grids into the POSIX shared arrays; every
+    rank then sees the complete arrays; the slices partition the voxels."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 35500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_shared_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(3))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res)
+    assert [s for _, _, s in res] == [(0, 35), (35, 35), (70, 35)]

@@ -40,6 +40,17 @@ RAW = [
 ]
 
 
+def kernel_source_sha():
+    """sha256 of the kernel sources: a capture only describes the kernel built from exactly these files"""
+    import hashlib
+    import os
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "opengate_b200", "csrc")
+    h = hashlib.sha256()
+    for f in ("transport.cuh", "device_math.cuh", "gate_b200.cu", "uncertainty.cuh"):
+        h.update(open(os.path.join(root, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def d_kernel_name(hdr, vals):
     """the instantiation as gate_b200_kernel_name() spells it: 'gb2::transport_kernel<unsigned char, 2>'"""
     import re
@@ -159,7 +170,7 @@ def main():
                     kn = d_kernel_name(hdr, vals)
                     d[a.key] = {"dram_bytes_per_history": (rd + wr) / a.histories, "histories_in_capture": a.histories,
                                 "dram_read_bytes": rd, "dram_write_bytes": wr, "source": os.path.basename(a.out),
-                                "kernel": kn}
+                                "kernel": kn, "kernel_source_sha": kernel_source_sha()}
                     json.dump(d, open(a.traffic_json, "w"), indent=1)
         except Exception:
             pass

@@ -618,12 +618,16 @@ class PhaseSpaceActor(ActorBase):
             f = f"phsp_from_{self.type_name.lower()}_{self.name}.npz"
         return self.simulation.get_output_path(f)
 
-    def store_rows(self, rows, n_absorbed, event_offset=0):
+    def store_rows(self, rows, n_absorbed, event_offset=0, event_time=None):
         """rows: dict of engine columns (KineticEnergy, Position, Direction, Weight, Time, EventID, Flags).
         Builds the requested attribute columns with the reference's types
-        (D = float64, I = int32, 3 = 3 x float64, GateDigiCollection.cpp:240-271)."""
+        (D = float64, I = int32, 3 = 3 x float64, GateDigiCollection.cpp:240-271).
+        event_time: callable(global history ids) -> time of the event in ns (timing.event_times of the source the
+        id belongs to); `GlobalTime` = event time + time of flight (GateDigiAttributeList.cpp: GlobalTime is the
+        post-step global time of the track, which starts at the event time)."""
         n = len(rows["EventID"])
         cols = {}
+        t_event = event_time(rows["EventID"]) if (event_time is not None and "GlobalTime" in self.attributes) else None
         for a in self.attributes:
             if a == "KineticEnergy":
                 cols[a] = rows["KineticEnergy"].astype(np.float64)
@@ -647,7 +651,9 @@ class PhaseSpaceActor(ActorBase):
                     loc = (rows["Position"].astype(np.float64) - np.asarray(t, dtype=np.float64)) @ np.asarray(R, dtype=np.float64)
                 for i, ax in enumerate("XYZ"):
                     cols[f"{a}_{ax}"] = np.ascontiguousarray(loc[:, i])
-            elif a in ("GlobalTime", "LocalTime", "TimeFromBeginOfEvent"):
+            elif a == "GlobalTime":
+                cols[a] = rows["Time"].astype(np.float64) + (t_event if t_event is not None else 0.0)
+            elif a in ("LocalTime", "TimeFromBeginOfEvent"):
                 cols[a] = rows["Time"].astype(np.float64)
             elif a == "ParticleName":
                 cols[a] = np.full(n, "gamma")

@@ -60,6 +60,12 @@ constexpr int kWoodcockK = 4;              // tentative collisions per Woodcock 
 #ifndef GB2_COMPTON_LAZY
 #define GB2_COMPTON_LAZY 0
 #endif
+#ifndef GB2_CLOSE_FUSED
+#define GB2_CLOSE_FUSED 1
+#endif
+#ifndef GB2_PREFETCH_KEYS
+#define GB2_PREFETCH_KEYS 1
+#endif
 #ifndef GB2_SPLIT
 #define GB2_SPLIT 0                        // > 0: that many of the four schedulers' warps prefer the Woodcock queue
 #endif
@@ -562,6 +568,11 @@ template <int kMode = 0>
 __device__ __forceinline__ void flush_buffer(const Params &P, const DepEntry *buf, int nbuf) {
   for (int j = 0; j < nbuf; ++j) grid_add<kMode>(P, ld_dep(buf + j));
 }
+// the same when entry `kj` is held in registers (the deposit that closed the history)
+template <int kMode>
+__device__ __forceinline__ void flush_buffer_keep(const Params &P, const DepEntry *buf, int nbuf, const DepEntry &ken, int kj) {
+  for (int j = 0; j < nbuf; ++j) grid_add<kMode>(P, j == kj ? ken : ld_dep(buf + j));
+}
 
 // ---- per-history table of the TLE actors that score squares: open addressing, Fibonacci hash.
 // A history touches hundreds of voxels along its flights; the event-wise squares need its sum per
@@ -606,13 +617,22 @@ __device__ __forceinline__ void tle_table_add(const Params &P, int gslot, unsign
 }
 
 struct DepStat { unsigned dep, over, flush, tle_ent, tle_over; double edep; };
+struct DepKeys;
+struct DepKeep;
 
 // deposit e (already weighted) at the photon position; in_vol selects whether dose actors see it.
 // e_tle: flight energy of the gamma whose secondaries deposit here (a TLE actor ignores them while that
 // gamma scores by track length, GateTLEDoseActor.cpp:236-243); kBig for a gamma absorbed below the cut.
-template <int kMode>
+// Optional extras of the single-actor kernels (kMode >= 2):
+//  * pk: the keys of the first two buffer entries, loaded by the caller ahead of its own arithmetic (the search of
+//    the buffer is then a register compare for the common histories with at most two voxels);
+//  * keep: the entry this deposit creates or updates is handed back in registers (keep->n = its index) instead of
+//    being stored -- the caller closes the history in the same call and adds it to the grids directly.
+struct DepKeys { int k0, k1; };
+struct DepKeep { DepEntry en; int j; };
+template <int kMode, bool kPre = false, bool kKeep = false>
 __device__ __forceinline__ void deposit(const Params &P, Ph &g, DepEntry *buf, DepStat &ds, float e,
-                                     int m, bool in_vol, float e_tle, int gslot) {
+                                     int m, bool in_vol, float e_tle, int gslot, const DepKeys &pk, DepKeep &keep) {
   ds.edep += (double)e;
   ds.dep++;
   if (!in_vol) return;
@@ -668,13 +688,20 @@ __device__ __forceinline__ void deposit(const Params &P, Ph &g, DepEntry *buf, D
       if (nl != before) tl_st(&P.tle_state[gslot].w, nl);
       continue;
     }
-    int j;
-    for (j = 0; j < nbuf; ++j)
-#if GB2_DEP_L1
-      if (buf[j].key == key) break;
-#else
-      if (__ldcg(&buf[j].key) == key) break;
-#endif
+    int j = 0;
+    if (kMode >= 2 && kPre) {
+      // entries 0 and 1 by their prefetched keys, the rest (rare) by the loop
+      if (nbuf > 0 && pk.k0 == key) j = 0;
+      else if (nbuf > 1 && pk.k1 == key) j = 1;
+      else {
+        for (j = nbuf < 2 ? nbuf : 2; j < nbuf; ++j)
+          if (sc_ld(&buf[j].key) == key) break;
+      }
+    } else {
+      for (j = 0; j < nbuf; ++j)
+        if (sc_ld(&buf[j].key) == key) break;
+    }
+    DepEntry en;
     if (j == nbuf) {
       if (nbuf == kDepBuf) {   // coalescing buffer full: write it out, start again
         flush_buffer<kMode>(P, buf, nbuf);
@@ -683,16 +710,24 @@ __device__ __forceinline__ void deposit(const Params &P, Ph &g, DepEntry *buf, D
         nbuf = 0;
         j = 0;
       }
-      DepEntry z; z.key = key; z.e = e; z.d = dd; z.n = 1;
-      st_dep(buf + j, z);
+      en.key = key; en.e = e; en.d = dd; en.n = 1;
       nbuf++;
     } else {
-      DepEntry en = ld_dep(buf + j);
+      en = ld_dep(buf + j);
       en.e += e; en.d += dd; en.n += 1;
-      st_dep(buf + j, en);
     }
+    if (kMode >= 2 && kKeep) { keep.en = en; keep.j = j; }
+    else st_dep(buf + j, en);
   }
   g.flags = (g.flags & ~F_NBUF) | ((unsigned)nbuf << F_NBUF_SHIFT);
+}
+
+template <int kMode>
+__device__ __forceinline__ void deposit(const Params &P, Ph &g, DepEntry *buf, DepStat &ds, float e,
+                                     int m, bool in_vol, float e_tle, int gslot) {
+  DepKeys pk; pk.k0 = -1; pk.k1 = -1;
+  DepKeep keep;
+  deposit<kMode, false, false>(P, g, buf, ds, e, m, in_vol, e_tle, gslot, pk, keep);
 }
 
 // ------------------------------------------------------------------------------ physics
@@ -1307,6 +1342,15 @@ __device__ __forceinline__ int phase_compton(const Params &P, Smem &S, int slot,
   const float E = S.E[slot];
   const unsigned fm = S.fm[slot];
   const int m = (int)(fm >> F_MAT_SHIFT);
+#if GB2_PREFETCH_KEYS
+  DepKeys pk;
+  {
+    const DepEntry *pb = P.depbuf + (size_t)gslot * kDepBuf;
+    const int nb = (int)((fm & F_NBUF) >> F_NBUF_SHIFT);
+    pk.k0 = nb > 0 ? sc_ld(&pb[0].key) : -1;
+    pk.k1 = nb > 1 ? sc_ld(&pb[1].key) : -1;
+  }
+#endif
   uint32_t r[8];
   const unsigned long long id = P.first + S.hidx[slot];
 #if GB2_COMPTON_LAZY
@@ -1359,7 +1403,14 @@ __device__ __forceinline__ int phase_compton(const Params &P, Smem &S, int slot,
     d_sincos2pi(u32_to_uniform(r[4]), sphi, cphi);
     const float E1 = eps * E;
     const float wgt = hist_weight<kMode>(P, gslot);
+#if GB2_PREFETCH_KEYS
+    {
+      DepKeep nokeep;
+      deposit<kMode, true, false>(P, g, buf, ds, (E - E1) * wgt, m, in_vol, E, gslot, pk, nokeep);
+    }
+#else
     deposit<kMode>(P, g, buf, ds, (E - E1) * wgt, m, in_vol, E, gslot);
+#endif
     rotate_dir(g.d, cost, sint, sphi, cphi);
     g.E = E1;
     g.seg = 0.0f;
@@ -1480,10 +1531,18 @@ __device__ __forceinline__ int phase_end(const Params &P, Smem &S, int slot, int
   int next;
   unsigned n_flush = 0, n_abs = 0, n_hist = 0, n_phot = 0, n_conv = 0;
   DepStat ds; ds.dep = 0; ds.over = 0; ds.flush = 0; ds.tle_ent = 0; ds.tle_over = 0; ds.edep = 0.0;
+  DepKeep keep;
+  keep.j = -1;
   if (g.flags & F_ABSORB) {
     if (g.flags & F_CONV) n_conv = 1; else n_phot = 1;
     rng_begin(g.rng);
-    deposit<kMode>(P, g, P.depbuf + (size_t)gslot * kDepBuf, ds, g.E * hist_weight<kMode>(P, gslot), g.mat, (g.flags & F_INVOL) != 0, g.E, gslot);
+    // the single-actor kernels close the history in this very call unless a second annihilation photon is
+    // pending: the entry of this last deposit goes to the grids from registers, not through the buffer
+    DepKeys nopk; nopk.k0 = -1; nopk.k1 = -1;
+    if (GB2_CLOSE_FUSED && kMode >= 2 && !(g.flags & F_PEND))
+      deposit<kMode, false, true>(P, g, P.depbuf + (size_t)gslot * kDepBuf, ds, g.E * hist_weight<kMode>(P, gslot), g.mat, (g.flags & F_INVOL) != 0, g.E, gslot, nopk, keep);
+    else
+      deposit<kMode>(P, g, P.depbuf + (size_t)gslot * kDepBuf, ds, g.E * hist_weight<kMode>(P, gslot), g.mat, (g.flags & F_INVOL) != 0, g.E, gslot);
     g.flags &= ~(F_ABSORB | F_CONV);
     c_edep += ds.edep;
   }
@@ -1514,7 +1573,10 @@ __device__ __forceinline__ int phase_end(const Params &P, Smem &S, int slot, int
   } else {
     if (g.flags & F_OPEN) {
       const int nbuf = (int)((g.flags & F_NBUF) >> F_NBUF_SHIFT);
-      if (nbuf) flush_buffer<kMode>(P, P.depbuf + (size_t)gslot * kDepBuf, nbuf);
+      if (nbuf) {
+        if (GB2_CLOSE_FUSED && kMode >= 2) flush_buffer_keep<kMode>(P, P.depbuf + (size_t)gslot * kDepBuf, nbuf, keep.en, keep.j);
+        else flush_buffer<kMode>(P, P.depbuf + (size_t)gslot * kDepBuf, nbuf);
+      }
       n_flush = (unsigned)nbuf;
       if (kMode != 2 && kMode != 3 && P.nphsp > 0 && !(g.flags & F_STORED)) n_abs = 1;
     }

@@ -409,6 +409,31 @@ class GpuSimulationEngine:
         for arr in self.__dict__.pop("_pinned", []):
             engine.unpin(arr)
 
+    def _event_time_function(self, run_index, base):
+        """global history id -> event time of run `run_index` (timing.event_times): the ids of a run are dealt to
+        the sources in order, counts[run][source] each, starting at `base`"""
+        from . import timing
+        sim = self.sim
+        interval = sim.run_timing_intervals[run_index]
+        seed = int(sim.current_random_seed) & (2 ** 64 - 1)
+        segs, first = [], base
+        for s, n in zip(self.source_objects, self._counts[run_index]):
+            segs.append((first, first + int(n), s))
+            first += int(n)
+
+        def f(ids):
+            ids = np.asarray(ids, dtype=np.int64)
+            t = np.full(ids.shape, float(interval[0]), dtype=np.float64)
+            for lo, hi, s in segs:
+                m = (ids >= lo) & (ids < hi)
+                if m.any():
+                    ui = s.user_info
+                    t[m] = timing.event_times(seed, ids[m], interval, start_time=ui.start_time, end_time=ui.end_time,
+                                              activity=ui.activity > 0, half_life=ui.half_life)
+            return t
+
+        return f
+
     def _mean_uncertainty(self, actor_index, actor, n_events):
         """GateDoseActor::ComputeMeanUncertainty over the data of ALL shards."""
         if self.n_shards == 1 and hasattr(self.engines[0], "mean_uncertainty"):
@@ -543,7 +568,8 @@ class GpuSimulationEngine:
                 rows = {k: np.concatenate([g[k] for g in gathered]) for k in rows}
             order = np.lexsort((rows["Time"], rows["EventID"]))
             rows = {k: v[order] for k, v in rows.items()}
-            a.store_rows(rows, st["absorbed_events"] if a.store_absorbed_event else 0, event_offset=-base)
+            a.store_rows(rows, st["absorbed_events"] if a.store_absorbed_event else 0, event_offset=-base,
+                         event_time=self._event_time_function(run_index, base))
             if st["phsp_dropped"]:
                 warning(f"PhaseSpaceActor '{a.name}': {st['phsp_dropped']} rows dropped (max_rows too small)")
         return st

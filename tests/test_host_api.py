@@ -445,3 +445,55 @@ def test_lean_outputs_keep_the_squares_on_the_engine_side(tmp_path):
     assert np.array_equal(a[1], b[1])                                   # same expressions, same bits
     np.testing.assert_allclose(a[3], b[3], rtol=1e-12, atol=0)          # dose: evaluated before / after the Gy scaling
     assert (b[1] > 0).any()
+
+
+def test_event_time_stamps_follow_the_source_timing(tmp_path):
+    """GlobalTime of a phase-space row = time of the event + time of flight.  Reference: GateVSource.cpp:55-89: an
+    `activity` source spreads its events over the run interval as a Poisson process (decaying with a half-life),
+    a `number_of_primaries` source emits them at the start of the interval.  Here the time of an event is a pure
+    function of (seed, history id): timing.event_times."""
+    import opengate_b200 as gate
+    from opengate_b200 import timing
+    s_, mm, keV, Bq = gate.g4_units.s, gate.g4_units.mm, gate.g4_units.keV, gate.g4_units.Bq
+    sim, ct, src, dose, hu = ct_sim(tmp_path, n_primaries=0)
+    sim.random_seed = 4242
+    sim.run_timing_intervals = [[2 * s_, 3 * s_]]
+    src.number_of_primaries = 0
+    src.energy.type = "mono"
+    src.energy.mono = 100 * keV
+    src.activity = 20000 * Bq
+    src.half_life = 0.4 * s_
+    plane = sim.add_volume("Box", "plane")
+    plane.size = [900 * mm, 900 * mm, 2 * mm]
+    plane.translation = [0, 0, 350 * mm]
+    ph = sim.add_actor("PhaseSpaceActor", "phsp")
+    ph.attached_to = plane
+    ph.attributes = ["KineticEnergy", "EventID", "GlobalTime", "TimeFromBeginOfEvent"]
+    ph.write_to_disk = False
+    out = sim.run(_backend=OracleBackend)
+    n = out.device_stats[0]["histories"]
+    assert 8500 < n < 10500          # A0 / lambda * (1 - exp(-lambda * 1 s)) = 9500
+    g, tof, ev = ph.data["GlobalTime"], ph.data["TimeFromBeginOfEvent"], ph.data["EventID"]
+    assert len(g) > 2000
+    t_ev = g - tof
+    assert t_ev.min() >= 2 * s_ and t_ev.max() <= 3 * s_ and np.all(tof > 0) and np.all(tof < 1000.0)   # ns of flight
+    # the same function of the id, evaluated directly
+    want = timing.event_times(4242, ev, (2 * s_, 3 * s_), activity=True, half_life=0.4 * s_)
+    np.testing.assert_allclose(t_ev, want, rtol=0, atol=1e-3)
+    # decaying rate: more events early; mean of exp(-lam t) on one second with T1/2 = 0.4 s
+    lam = np.log(2) / 0.4
+    mean = 1 / lam - np.exp(-lam) / (1 - np.exp(-lam))
+    assert abs((t_ev.mean() - 2 * s_) / s_ - mean) < 0.02
+    # a number_of_primaries source: every event at the start of the interval
+    sim2, ct2, src2, dose2, hu2 = ct_sim(tmp_path, n_primaries=3000)
+    sim2.run_timing_intervals = [[5 * s_, 6 * s_]]
+    plane2 = sim2.add_volume("Box", "plane")
+    plane2.size = [900 * mm, 900 * mm, 2 * mm]
+    plane2.translation = [0, 0, 350 * mm]
+    ph2 = sim2.add_actor("PhaseSpaceActor", "phsp")
+    ph2.attached_to = plane2
+    ph2.attributes = ["GlobalTime", "TimeFromBeginOfEvent"]
+    ph2.write_to_disk = False
+    sim2.run(_backend=OracleBackend)
+    assert len(ph2.data["GlobalTime"]) > 100
+    np.testing.assert_allclose(ph2.data["GlobalTime"] - ph2.data["TimeFromBeginOfEvent"], 5 * s_, rtol=0, atol=1e-3)

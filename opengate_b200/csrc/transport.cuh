@@ -66,6 +66,9 @@ constexpr int kWoodcockK = 4;              // tentative collisions per Woodcock 
 #ifndef GB2_PREFETCH_KEYS
 #define GB2_PREFETCH_KEYS 1
 #endif
+#ifndef GB2_PREFETCH_PROB
+#define GB2_PREFETCH_PROB 0                // first n tentative points of a call whose process probabilities are prefetched
+#endif
 #ifndef GB2_SPLIT
 #define GB2_SPLIT 0                        // > 0: that many of the four schedulers' warps prefer the Woodcock queue
 #endif
@@ -1271,11 +1274,22 @@ __device__ __forceinline__ void volume_gather_labels(const Params &P, Smem &S, c
   }
 }
 
+__device__ __forceinline__ void prefetch_l1(const void *p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ void volume_gather_mu(const Params &P, VCall &c) {
   const float2 *__restrict__ murow = P.mu2 + (size_t)c.ie * P.nmat;
 #pragma unroll
   for (int k = 0; k < kWoodcockK; ++k) {
     const float2 v = __ldg(murow + c.lab[k]);
+#if GB2_PREFETCH_PROB
+    // the process probabilities of this material (needed only if the collision is accepted: a third dependent
+    // look-up after label and attenuation) are asked into L1 now, without a register or a wait
+    if (k < GB2_PREFETCH_PROB) {
+      prefetch_l1(P.prob + (size_t)c.ie * P.nmat + c.lab[k]);
+      prefetch_l1(P.prob + (size_t)(c.ie + 1) * P.nmat + c.lab[k]);
+    }
+#endif
     c.mu[k] = __fmaf_rn(c.fe, v.y - v.x, v.x);
   }
 }

@@ -782,7 +782,7 @@ int gate_b200_add_tle_dose_actor(gate_b200_engine *h, const gate_b200_dose_desc 
   if (P.ntle == 0 || emin > P.tle_emin) P.tle_emin = emin;
   if (P.ntle == 0 || D.tle_thr > P.tle_thr_max) P.tle_thr_max = D.tle_thr;
   P.ntle++;
-  const size_t nslots = (size_t)h->max_ctas * kSlots;
+  const size_t nslots = (size_t)h->max_ctas * kTleSlots;   // the TLE kernel works with kTleSlots slots per CTA
   if (!P.tle_state) {
     if (int rc = dev_alloc(h, &P.tle_state, nslots, true)) return rc;
   }

@@ -56,6 +56,17 @@ constexpr int kThreads = GB2_THREADS;
 constexpr int kTleThreads = GB2_TLE_THREADS;
 template <bool kIsTle> constexpr int threads_of() { return kIsTle ? kTleThreads : kThreads; }
 constexpr int kSlots = GB2_SLOTS;          // photon slots per CTA (< 65535: queue cells are 16 bit)
+#ifndef GB2_TLE_SLOTS
+// measured on B200 (C3, TLE with event-wise squares / without, histories/s): 2528 slots 1.795e7 / 6.49e7,
+// 1280 1.827e7 / 6.53e7, 640 1.780e7 / 6.37e7, 320 1.200e7 / 2.82e7: the phase is bound by the dependent chain of a
+// chord, not by the number of histories in flight -- 640 slots (one per thread) need a quarter of the table memory
+#define GB2_TLE_SLOTS 640
+#endif
+// slots a CTA of the track-length-estimator kernel puts to work (the rest of the kSlots stay empty): every history
+// in flight owns a 64 KB table of per-voxel sums there, and the live part of those tables is what that kernel's
+// DRAM traffic is made of
+constexpr int kTleSlots = GB2_TLE_SLOTS < GB2_SLOTS ? GB2_TLE_SLOTS : GB2_SLOTS;
+template <int kMode> constexpr int kActiveSlots = kMode == 1 ? kTleSlots : kSlots;
 constexpr int kWoodcockK = 4;              // tentative collisions per Woodcock call (2 Philox blocks)
 #ifndef GB2_COMPTON_LAZY
 #define GB2_COMPTON_LAZY 0
@@ -184,7 +195,7 @@ struct Params {
   // track-length estimators (dose actors with tle = 1)
   int ntle;
   float tle_emin, tle_thr_max;
-  DepEntry *tle_tab;             // [slots][kTleH] per-history (actor, voxel) sums, only with squares
+  DepEntry *tle_tab;             // [gridDim.x * kTleSlots][kTleH] per-history (actor, voxel) sums, only with squares
   unsigned short *tle_list;      // [slots][kTleMax] occupied table cells in insertion order
   uint4 *tle_state;              // [slots] {t along the flight (-1 new flight, -2 writing the table out),
                                  //          ix | iy << 16 (or next list entry), iz, entries in the table}
@@ -1811,12 +1822,12 @@ __global__ void __launch_bounds__(threads_of<(kMode == 1)>(), GB2_MIN_CTAS) tran
   for (int i = threadIdx.x; i < kSlots; i += blockDim.x) {
     S.fm[i] = 0; S.blk[i] = 0; S.hidx[i] = 0; S.tbin[i] = 0.0f;
 #pragma unroll
-    for (int t = 0; t < Q_COUNT; ++t) S.cell[t][i] = (unsigned short)(t == Q_E ? i : kEmpty);
+    for (int t = 0; t < Q_COUNT; ++t) S.cell[t][i] = (unsigned short)((t == Q_E && i < kActiveSlots<kMode>) ? i : kEmpty);
   }
   if (threadIdx.x < Q_COUNT) {
     S.head[threadIdx.x] = 0;
-    S.tail[threadIdx.x] = threadIdx.x == Q_E ? kSlots : 0;
-    S.avail[threadIdx.x] = threadIdx.x == Q_E ? kSlots : 0;   // every slot starts by asking for a history
+    S.tail[threadIdx.x] = threadIdx.x == Q_E ? kActiveSlots<kMode> : 0;
+    S.avail[threadIdx.x] = threadIdx.x == Q_E ? kActiveSlots<kMode> : 0;   // every slot starts by asking for a history
   }
   if (threadIdx.x < S_COUNT) { S.stats_lo[threadIdx.x] = 0u; S.stats_hi[threadIdx.x] = 0u; }
   if (threadIdx.x == 0) { S.retired = 0; S.edep = 0.0; S.cur = Q_E; S.cur2 = Q_E; }
@@ -1825,7 +1836,7 @@ __global__ void __launch_bounds__(threads_of<(kMode == 1)>(), GB2_MIN_CTAS) tran
   unsigned c_tent = 0;
   double c_edep = 0.0;
   int polls = 0;
-  const int slot_base = blockIdx.x * kSlots;
+  const int slot_base = blockIdx.x * kActiveSlots<kMode>;   // index of slot 0 of this CTA in the per-slot global scratch
 
   for (;;) {
     // ---- claim slots that wait for the same phase (lane 0 negotiates with the queues): up to 32,
@@ -1890,7 +1901,7 @@ __global__ void __launch_bounds__(threads_of<(kMode == 1)>(), GB2_MIN_CTAS) tran
           }
           continue;
         }
-        if (best <= 0 && ld_vol(&S.retired) >= kSlots) { q = -2; break; }
+        if (best <= 0 && ld_vol(&S.retired) >= kActiveSlots<kMode>) { q = -2; break; }
         ++polls;
         __nanosleep(polls < 8 ? 64 : 512);
       }

@@ -20,6 +20,13 @@ cases = {"c1": small_setups.c1(n), "c2": small_setups.c2(n), "c3": small_setups.
 S = small_setups.c3(n)
 S.labels = S.labels.astype(np.uint16)
 cases["c3_u16"] = S
+S = small_setups.c3(n)
+S.dose[0].hit_type = abi.HIT_RANDOM          # kernel variant 3; the variant-2 run is the bench shape
+cases["c3_hit_random"] = S
+S = small_setups.c3(n)
+S.dose[0].hit_type = abi.HIT_POST
+S.dose[0].score_flags = abi.SCORE_EDEP | abi.SCORE_EDEP_SQ | abi.SCORE_DOSE
+cases["c3_bench_shape"] = S
 for name, S in cases.items():
     eng = Engine(0, S.seed)
     se, de, pe = S.apply(eng)
@@ -29,6 +36,13 @@ for name, S in cases.items():
     st = eng.stats()
     for d in de:
         eng.dose_grid(d, abi.GRID_EDEP)
+        eng.dose_grid(d, abi.GRID_EDEP, scale=0.5)
+        nx, ny, nz = eng._dose_sizes[d]
+        out = np.zeros((nz, ny, nx))
+        eng.dose_grid_range(d, abi.GRID_EDEP, 7, nx * ny * nz - 11, out)
+    if name == "c3_bench_shape":
+        eng.uncertainty_grid(de[0], abi.GRID_EDEP, n)
+        eng.mean_uncertainty(de[0], n, 5, 0.7)
     for p in pe:
         eng.phsp(p)
     print(name, st["histories"], st["tentative_collisions"], st["tle_steps"], flush=True)

@@ -62,6 +62,20 @@ public:
     return out;
   }
 
+  /* the same with the end-of-run unit conversion done on the device (doseactors.py:685-696) */
+  py::array_t<double> GetDoseGridScaled(int actor, int which, double scale, std::array<int, 3> size_xyz) {
+    py::array_t<double> out({size_xyz[2], size_xyz[1], size_xyz[0]});
+    Check(gate_b200_get_dose_grid_scaled(h_, actor, which, scale, out.mutable_data()));
+    return out;
+  }
+  /* relative uncertainty image of edep / dose evaluated on the device (dataitems.py:1956-1993) */
+  py::array_t<double> GetUncertainty(int actor, int which, uint64_t n_events, std::array<int, 3> size_xyz) {
+    py::array_t<double> out({size_xyz[2], size_xyz[1], size_xyz[0]});
+    Check(gate_b200_get_uncertainty(h_, actor, which, n_events, out.mutable_data()));
+    return out;
+  }
+  std::string KernelName() { return gate_b200_kernel_name(h_); }
+
   py::dict GetStats() {
     gate_b200_stats s;
     Check(gate_b200_get_stats(h_, &s));
@@ -88,6 +102,9 @@ void init_GateB200Engine(py::module &m) {
       .def("BeginRun", &GateB200Engine::BeginRun)
       .def("RunSource", &GateB200Engine::RunSource, py::call_guard<py::gil_scoped_release>())
       .def("GetDoseGrid", &GateB200Engine::GetDoseGrid)
+      .def("GetDoseGridScaled", &GateB200Engine::GetDoseGridScaled)
+      .def("GetUncertainty", &GateB200Engine::GetUncertainty)
+      .def("KernelName", &GateB200Engine::KernelName)
       .def("GetStats", &GateB200Engine::GetStats)
       .def("GetHandleAddress", [](GateB200Engine &e) { return reinterpret_cast<uintptr_t>(e.handle()); });
   m.def("GateB200AbiVersion", &gate_b200_abi_version);

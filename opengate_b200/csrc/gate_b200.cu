@@ -782,16 +782,7 @@ int gate_b200_add_tle_dose_actor(gate_b200_engine *h, const gate_b200_dose_desc 
   if (P.ntle == 0 || emin > P.tle_emin) P.tle_emin = emin;
   if (P.ntle == 0 || D.tle_thr > P.tle_thr_max) P.tle_thr_max = D.tle_thr;
   P.ntle++;
-  const size_t nslots = (size_t)h->max_ctas * kTleSlots;   // the TLE kernel works with kTleSlots slots per CTA
-  if (!P.tle_state) {
-    if (int rc = dev_alloc(h, &P.tle_state, nslots, true)) return rc;
-  }
-  if ((D.flags & (GATE_B200_SCORE_EDEP_SQ | GATE_B200_SCORE_DOSE_SQ)) && !P.tle_tab) {
-    // per-history tables (event-wise squares): 32 KB per photon slot, empty = key -1
-    if (int rc = dev_alloc(h, &P.tle_tab, nslots * kTleH)) return rc;
-    CU(cudaMemsetAsync(P.tle_tab, 0xff, nslots * kTleH * sizeof(DepEntry), h->stream));
-    if (int rc = dev_alloc(h, &P.tle_list, nslots * kTleMax)) return rc;
-  }
+  // the per-slot scratch of the TLE phase is allocated by the first launch, when the kernel variant is known (tle_prepare)
   P.dose[id] = D;
   if (actor_id) *actor_id = id;
   return GATE_B200_OK;
@@ -845,8 +836,51 @@ int gate_b200_begin_run(gate_b200_engine *h, int32_t /*run_id*/) {
   return GATE_B200_OK;
 }
 
+// Kernel variant of the track-length estimator and its per-slot scratch.  Variant 5 (no per-history tables: the sums of
+// a history per voxel are re-evaluated from its flight records) serves ONE TLE actor that scores event-wise squares on
+// the image grid -- next to any number of analog dose actors; every other combination runs variant 1, whose actors
+// with squares keep a 64 KB table per photon slot.
+static int tle_mode(const Params &P) {
+  if (P.ntle != 1 || getenv("GATE_B200_TLE_TABLE")) return 1;
+  for (int a = 0; a < P.ndose; ++a) {
+    const DDose &D = P.dose[a];
+    if (D.tle) return (D.aligned && (D.flags & (GATE_B200_SCORE_EDEP_SQ | GATE_B200_SCORE_DOSE_SQ)) && P.n[2] <= 65535) ? 5 : 1;
+  }
+  return 1;
+}
+static int tle_prepare(gate_b200_engine *h) {
+  Params &P = h->P;
+  if (P.ntle == 0) return GATE_B200_OK;
+  const size_t nslots = (size_t)h->max_ctas * kTleSlots;   // the TLE kernels work with kTleSlots slots per CTA
+  if (!P.tle_state) {
+    if (int rc = dev_alloc(h, &P.tle_state, nslots, true)) return rc;
+    if (int rc = dev_alloc(h, &P.tle_aux, nslots, true)) return rc;
+  }
+  bool sq = false;
+  for (int a = 0; a < P.ndose; ++a)
+    if (P.dose[a].tle && (P.dose[a].flags & (GATE_B200_SCORE_EDEP_SQ | GATE_B200_SCORE_DOSE_SQ))) { sq = true; P.tle_a = a; }
+  if (tle_mode(P) == 5) {
+    if (!P.tle_rec) {
+      if (int rc = dev_alloc(h, &P.tle_rec, nslots * kTleRecMax * kTleRecW)) return rc;
+    }
+  } else if (sq && !P.tle_tab) {
+    // per-history tables (event-wise squares): 64 KB per photon slot, empty = key -1
+    if (int rc = dev_alloc(h, &P.tle_tab, nslots * kTleH)) return rc;
+    CU(cudaMemsetAsync(P.tle_tab, 0xff, nslots * kTleH * sizeof(DepEntry), h->stream));
+    if (int rc = dev_alloc(h, &P.tle_list, nslots * kTleMax)) return rc;
+  }
+  return GATE_B200_OK;
+}
+
 static int launch_histories(gate_b200_engine *h, int32_t source_id, uint64_t first_history, uint64_t n_histories) {
+  if (int rc = tle_prepare(h)) return rc;
   Params P = h->P;
+  P.label_bytes = h->label_bytes;
+  P.tle_rec_cap = kTleRecMax;
+  if (const char *c = getenv("GATE_B200_TLE_REC_CAP")) {   // tests: reach the record-overflow path with short histories
+    const int v = atoi(c);
+    if (v >= 1 && v <= kTleRecMax) P.tle_rec_cap = v;
+  }
   const int label_bytes = h->label_bytes;
   P.src = h->src[source_id].dev;
   P.first = first_history;
@@ -857,14 +891,16 @@ static int launch_histories(gate_b200_engine *h, int32_t source_id, uint64_t fir
   // or source) with those choices compiled in, 2 for hit_type post, 3 for the other hit types; 4 = one dose actor
   // with phase-space actors; 0 = everything else
   const bool one_dose = P.ntle == 0 && P.ndose == 1 && P.src.ph_b == nullptr && !getenv("GATE_B200_GENERAL_KERNEL");
-  const int mode = P.ntle > 0 ? 1 : !one_dose ? 0 : P.nphsp > 0 ? 4 : (P.dose[0].hit_type == GATE_B200_HIT_POST ? 2 : 3);
+  const int mode = P.ntle > 0 ? tle_mode(P) : !one_dose ? 0 : P.nphsp > 0 ? 4 : (P.dose[0].hit_type == GATE_B200_HIT_POST ? 2 : 3);
   auto kern = transport_kernel<uint8_t, 0>;
   if (label_bytes == 2) {
     kern = mode == 1 ? transport_kernel<uint16_t, 1> : mode == 2 ? transport_kernel<uint16_t, 2>
-         : mode == 3 ? transport_kernel<uint16_t, 3> : mode == 4 ? transport_kernel<uint16_t, 4> : transport_kernel<uint16_t, 0>;
+         : mode == 3 ? transport_kernel<uint16_t, 3> : mode == 4 ? transport_kernel<uint16_t, 4>
+         : mode == 5 ? transport_kernel<uint16_t, 5> : transport_kernel<uint16_t, 0>;
   } else {
     kern = mode == 1 ? transport_kernel<uint8_t, 1> : mode == 2 ? transport_kernel<uint8_t, 2>
-         : mode == 3 ? transport_kernel<uint8_t, 3> : mode == 4 ? transport_kernel<uint8_t, 4> : transport_kernel<uint8_t, 0>;
+         : mode == 3 ? transport_kernel<uint8_t, 3> : mode == 4 ? transport_kernel<uint8_t, 4>
+         : mode == 5 ? transport_kernel<uint8_t, 5> : transport_kernel<uint8_t, 0>;
   }
   {
     char nm[96];

@@ -66,7 +66,11 @@ constexpr int kSlots = GB2_SLOTS;          // photon slots per CTA (< 65535: que
 // in flight owns a 64 KB table of per-voxel sums there, and the live part of those tables is what that kernel's
 // DRAM traffic is made of
 constexpr int kTleSlots = GB2_TLE_SLOTS < GB2_SLOTS ? GB2_TLE_SLOTS : GB2_SLOTS;
-template <int kMode> constexpr int kActiveSlots = kMode == 1 ? kTleSlots : kSlots;
+// kernel variants (template parameter kMode): 1 and 5 carry the track-length-estimator phase (5: the sums of a history per
+// voxel re-evaluated from its flight records instead of kept in a table), 2-4 are the single-dose-actor variants
+__host__ __device__ constexpr bool is_tle(int m) { return m == 1 || m == 5; }
+__host__ __device__ constexpr bool is_one(int m) { return m >= 2 && m <= 4; }
+template <int kMode> constexpr int kActiveSlots = is_tle(kMode) ? kTleSlots : kSlots;
 constexpr int kWoodcockK = 4;              // tentative collisions per Woodcock call (2 Philox blocks)
 #ifndef GB2_COMPTON_LAZY
 #define GB2_COMPTON_LAZY 0
@@ -95,6 +99,8 @@ constexpr int kTleLog2 = 12;
 constexpr int kTleH = 1 << kTleLog2;       // per-history table of (actor, voxel) sums (TLE actor with squares)
 constexpr int kTleMax = 3072;              // entries at which the table is written out (an overflow)
 constexpr int kTleEmpty = -1;
+constexpr int kTleRecMax = 64;             // scored flights + point deposits of one history kept apart (oracle TLE_REC_MAX)
+constexpr int kTleRecW = 4;                // float4 words of one record
 constexpr float kNudge = 1.0e-3f;          // mm pushed across a boundary
 constexpr float kBig = 3.0e38f;
 constexpr float kMc2 = 0.51099891f;
@@ -199,6 +205,13 @@ struct Params {
   unsigned short *tle_list;      // [slots][kTleMax] occupied table cells in insertion order
   uint4 *tle_state;              // [slots] {t along the flight (-1 new flight, -2 writing the table out),
                                  //          ix | iy << 16 (or next list entry), iz, entries in the table}
+  uint2 *tle_aux;                // [slots] {t before which the current flight is written out already, records of the history}
+  // kernel variant 5 (ONE TLE actor with squares, on the image grid; other dose actors analog): no table, the sum a
+  // voxel holds is re-evaluated from the records of the history's scored flights and point deposits
+  int tle_a;                     // index of that actor
+  int tle_rec_cap;               // records a history may hold (<= kTleRecMax; lowered by tests to reach the overflow path)
+  int label_bytes;
+  float4 *tle_rec;               // [slots][kTleRecMax][kTleRecW]
 };
 
 // Shared memory of one CTA: photon slots (structure of arrays), the four ring queues, statistics.
@@ -425,7 +438,7 @@ __device__ __forceinline__ void st_dep(DepEntry *p, const DepEntry &e) {
 // generate_primary), the source's constant otherwise
 template <int kMode>
 __device__ __forceinline__ float hist_weight(const Params &P, int gslot) {
-  if (kMode >= 2) return P.src.weight;
+  if (is_one(kMode)) return P.src.weight;
   return P.src.ph_b ? sc_ld(P.slot_w + gslot) : P.src.weight;
 }
 
@@ -478,6 +491,19 @@ __device__ __forceinline__ void stat_tle_overflow(Smem &S, unsigned over, unsign
   if (__any_sync(__activemask(), over != 0u)) {
     stat_add(S, S_TLE_OVER, over);
     stat_add(S, S_TLE_ENT, ent);
+  }
+}
+// the TLE bookkeeping of a phase's point deposits: variant 1 counts table entries when a table is written out (an
+// overflow), variant 5 when a voxel is touched for the first time by its history
+template <int kMode>
+__device__ __forceinline__ void stat_tle_deposits(Smem &S, unsigned over, unsigned ent) {
+  if (kMode == 5) {
+    if (__any_sync(__activemask(), (over | ent) != 0u)) {
+      stat_add(S, S_TLE_OVER, over);
+      stat_add(S, S_TLE_ENT, ent);
+    }
+  } else {
+    stat_tle_overflow(S, over, ent);
   }
 }
 
@@ -567,7 +593,36 @@ __device__ __forceinline__ void grid_add(const Params &P, const DepEntry &en) {
     e = se; e2 = se2; d = sd; d2 = sd2; n = sn;
   }
   if ((int)lane == leader) {
-    const DDose &D = P.dose[kMode >= 2 ? 0 : a];   // variants 2-4: the one dose actor, fields as immediates
+    const DDose &D = P.dose[is_one(kMode) ? 0 : a];   // variants 2-4: the one dose actor, fields as immediates
+    const size_t o = (size_t)v * (size_t)D.gstride;
+    red_add_f64(D.grid[GATE_B200_GRID_EDEP] + o, e);
+    if (D.flags & GATE_B200_SCORE_EDEP_SQ) red_add_f64(D.grid[GATE_B200_GRID_EDEP_SQ] + o, e2);
+    if (D.flags & GATE_B200_SCORE_DOSE) red_add_f64(D.grid[GATE_B200_GRID_DOSE] + o, d);
+    if (D.flags & GATE_B200_SCORE_DOSE_SQ) red_add_f64(D.grid[GATE_B200_GRID_DOSE_SQ] + o, d2);
+    if ((D.flags & GATE_B200_SCORE_COUNTS) && n != 0.0) red_add_f64(D.grid[GATE_B200_GRID_COUNTS] + v, n);
+  }
+}
+
+// The same for increments given as doubles (kernel variant 5: a voxel's event sum grows from p to p + e and the
+// grids get (p + e) - p and (p + e)^2 - p^2).
+__device__ __forceinline__ void grid_add_vals(const DDose &D, int v, double e, double e2, double d, double d2, double n) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned act = __activemask();
+  const unsigned grp = __match_any_sync(act, v);
+  const int leader = __ffs(grp) - 1;
+  if (grp != (1u << lane)) {
+    double se = 0.0, se2 = 0.0, sd = 0.0, sd2 = 0.0, sn = 0.0;
+    for (unsigned rem = grp; rem; rem &= rem - 1) {
+      const int src = __ffs(rem) - 1;
+      se += __shfl_sync(grp, e, src);
+      se2 += __shfl_sync(grp, e2, src);
+      sd += __shfl_sync(grp, d, src);
+      sd2 += __shfl_sync(grp, d2, src);
+      sn += __shfl_sync(grp, n, src);
+    }
+    e = se; e2 = se2; d = sd; d2 = sd2; n = sn;
+  }
+  if ((int)lane == leader) {
     const size_t o = (size_t)v * (size_t)D.gstride;
     red_add_f64(D.grid[GATE_B200_GRID_EDEP] + o, e);
     if (D.flags & GATE_B200_SCORE_EDEP_SQ) red_add_f64(D.grid[GATE_B200_GRID_EDEP_SQ] + o, e2);
@@ -630,6 +685,113 @@ __device__ __forceinline__ void tle_table_add(const Params &P, int gslot, unsign
   }
 }
 
+// a scored flight or a point deposit is about to add to the history's table: one more record behind its content;
+// the table is written out first when the history has kTleRecMax of them already (oracle tle_record_begin)
+__device__ __forceinline__ void tle_record_begin_tab(const Params &P, int gslot, unsigned &nlist, unsigned &nrec,
+                                                     unsigned &n_ent, unsigned &n_over) {
+  if (nrec >= (unsigned)P.tle_rec_cap) {
+    tle_flush_all(P, gslot, nlist);
+    n_ent += nlist;
+    n_over++;
+    nlist = 0;
+    nrec = 0;
+  }
+  nrec++;
+}
+
+// ---- kernel variant 5: the per-voxel sums of a history WITHOUT a table (oracle tle_fold_*).
+// A straight flight crosses a voxel once, so two contributions of a history to one voxel come from different flights
+// (or point deposits).  The history keeps its scored flights and point deposits as records (64 bytes each, slot
+// scratch); what a voxel holds so far is re-evaluated from them: the chord of an earlier flight through a given
+// voxel has a closed form with exactly the bits the voxel walk produced -- entry = the latest entering-face distance
+// of the axes that moved, exit = the earliest leaving-face distance, every face distance the walk's own expression of
+// the integer face index.  With the previous sum p and the new one p + e the grids get (p + e) - p and
+// (p + e)^2 - p^2: at the end of the history they hold the event's sum and its square (GateDoseActor.cpp:359-381),
+// one 32-byte voxel record touched per chord as in the run without squares, and no table traffic at all
+// (the table variant moved 162 KB of DRAM traffic per history on config 3, this one 27 KB).
+// record: [0] = {start x, y, z, t_end} (point deposit: {e, dose, key, 0}), [1] = {direction x, y, z, 0.1 E w} (point: 0),
+//         [2] = {lo.x | lo.y << 16, lo.z | hi.x << 16, hi.y | hi.z << 16, energy-bin coordinate}: the voxel range walked,
+//         [3] = {t before which the flight's chords are not part of the current sums (table overflow), -, -, -}
+__device__ __forceinline__ float tle_rec_chord(const Params &P, const float4 &A, const float4 &B, const int iv[3],
+                                               const int lo[3], const int hi[3], float &t_in_out) {
+  float t_in = 0.0f, t_out = A.w;
+  const float s[3] = {A.x, A.y, A.z}, d[3] = {B.x, B.y, B.z};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (d[a] == 0.0f) continue;
+    const float inv = 1.0f / d[a];
+    const bool up = d[a] > 0.0f;
+    const float f_in = __fmaf_rn((float)(iv[a] + (up ? 0 : 1)), P.sp[a], -P.half[a]);
+    const float f_out = __fmaf_rn((float)(iv[a] + (up ? 1 : 0)), P.sp[a], -P.half[a]);
+    if (iv[a] != (up ? lo[a] : hi[a])) {   // the walk entered this voxel layer through f_in
+      const float tb = (f_in - s[a]) * inv;
+      if (tb > t_in) t_in = tb;
+    }
+    const float tb = (f_out - s[a]) * inv;
+    if (tb < t_out) t_out = tb;
+  }
+  t_in_out = t_in;
+  return t_out - t_in;
+}
+// sum of the earlier contributions of the history to voxel iv of the TLE actor D; m < 0: label not gathered yet
+// cand: the stored records that can hold the voxel at all (bit r = record r; in record order = chronological order)
+__device__ __forceinline__ bool tle_fold_prev(const Params &P, const DDose &D, int gslot, unsigned long long cand, int key,
+                                              const int iv[3], int m, float &pe, float &pd) {
+  const float4 *rec = P.tle_rec + (size_t)gslot * (kTleRecMax * kTleRecW);
+  bool found = false;
+  float se = 0.0f, sd = 0.0f;
+  for (; cand; cand &= cand - 1ull) {
+    const unsigned r = (unsigned)__ffsll((long long)cand) - 1u;
+    const float4 Cf = tl_ld(rec + kTleRecW * r + 2);
+    const unsigned cx = __float_as_uint(Cf.x), cy = __float_as_uint(Cf.y), cz = __float_as_uint(Cf.z);
+    const int lo[3] = {(int)(cx & 0xffffu), (int)(cx >> 16), (int)(cy & 0xffffu)};
+    const int hi[3] = {(int)(cy >> 16), (int)(cz & 0xffffu), (int)(cz >> 16)};
+    if (iv[0] < lo[0] || iv[0] > hi[0] || iv[1] < lo[1] || iv[1] > hi[1] || iv[2] < lo[2] || iv[2] > hi[2]) continue;
+    const float4 A = tl_ld(rec + kTleRecW * r), B = tl_ld(rec + kTleRecW * r + 1);
+    if (B.x == 0.0f && B.y == 0.0f && B.z == 0.0f) {   // a point deposit
+      if (__float_as_int(A.z) == key) { se += A.x; sd += A.y; found = true; }
+      continue;
+    }
+    float t_in;
+    const float L = tle_rec_chord(P, A, B, iv, lo, hi, t_in);
+    if (!(L > 0.0f) || t_in < tl_ld(rec + kTleRecW * r + 3).x) continue;
+    if (m < 0) {
+      const size_t flat = (size_t)iv[0] + (size_t)P.n[0] * ((size_t)iv[1] + (size_t)P.n[1] * (size_t)iv[2]);
+      m = P.label_bytes == 1 ? (int)__ldg(reinterpret_cast<const uint8_t *>(P.labels) + flat)
+                             : (int)__ldg(reinterpret_cast<const uint16_t *>(P.labels) + flat);
+    }
+    const float rho = __ldg(P.dens + m);
+    int ie; float fe;
+    bin_split(P, Cf.w, ie, fe);
+    const float2 mv = __ldg(D.muen2 + (size_t)ie * P.nmat + m);
+    const float muen = __fmaf_rn(fe, mv.y - mv.x, mv.x);
+    const float e = ((B.w * muen) * L) * rho;
+    se += e; sd += e / rho; found = true;
+  }
+  pe = se; pd = sd;
+  return found;
+}
+// one contribution (chord or point deposit) of the history to voxel iv; tcur: where the current flight stands
+__device__ __forceinline__ void tle_fold_add(const Params &P, const DDose &D, int gslot, unsigned &nrec, unsigned &nlist,
+                                             float &tmin, unsigned long long &cand, int key, const int iv[3], int m, float e,
+                                             float dd, int n, float tcur, unsigned &n_ent, unsigned &n_over) {
+  float pe, pd;
+  if (!tle_fold_prev(P, D, gslot, cand, key, iv, m, pe, pd)) {
+    if (nlist == (unsigned)kTleMax) {   // the table this stands for would be full: forget what was scored so far
+      nrec = 1;
+      cand = 0ull;
+      tmin = tcur;
+      nlist = 0;
+      n_over++;
+    }
+    nlist++;
+    n_ent++;
+  }
+  const float ne = pe + e, nd = pd + dd;
+  const double e0 = (double)pe, e1 = (double)ne, d0 = (double)pd, d1 = (double)nd;
+  grid_add_vals(D, key & 0x0fffffff, e1 - e0, e1 * e1 - e0 * e0, d1 - d0, d1 * d1 - d0 * d0, (double)n);
+}
+
 struct DepStat { unsigned dep, over, flush, tle_ent, tle_over; double edep; };
 struct DepKeys;
 struct DepKeep;
@@ -637,7 +799,7 @@ struct DepKeep;
 // deposit e (already weighted) at the photon position; in_vol selects whether dose actors see it.
 // e_tle: flight energy of the gamma whose secondaries deposit here (a TLE actor ignores them while that
 // gamma scores by track length, GateTLEDoseActor.cpp:236-243); kBig for a gamma absorbed below the cut.
-// Optional extras of the single-actor kernels (kMode >= 2):
+// Optional extras of the single-actor kernels (is_one(kMode)):
 //  * pk: the keys of the first two buffer entries, loaded by the caller ahead of its own arithmetic (the search of
 //    the buffer is then a register compare for the common histories with at most two voxels);
 //  * keep: the entry this deposit creates or updates is handed back in registers (keep->n = its index) instead of
@@ -651,10 +813,10 @@ __device__ __forceinline__ void deposit(const Params &P, Ph &g, DepEntry *buf, D
   ds.dep++;
   if (!in_vol) return;
   int nbuf = (int)((g.flags & F_NBUF) >> F_NBUF_SHIFT);
-  const int ndose = kMode >= 2 ? 1 : P.ndose;
+  const int ndose = is_one(kMode) ? 1 : P.ndose;
   for (int a = 0; a < ndose; ++a) {
-    const DDose &D = P.dose[kMode >= 2 ? 0 : a];
-    if ((kMode == 1) && D.tle && e_tle <= D.tle_thr) continue;
+    const DDose &D = P.dose[is_one(kMode) ? 0 : a];
+    if (is_tle(kMode) && D.tle && e_tle <= D.tle_thr) continue;
     float pos[3] = {g.p[0], g.p[1], g.p[2]};
     if (kMode != 2 && D.hit_type != GATE_B200_HIT_POST) {
       // pre/random/middle between the Geant4 pre and post step points; the Geant4 step starts at
@@ -695,15 +857,36 @@ __device__ __forceinline__ void deposit(const Params &P, Ph &g, DepEntry *buf, D
     int v = (int)fx + D.size[0] * ((int)fy + D.size[1] * (int)fz);
     int key = (int)(((unsigned)a << 28) | (unsigned)v);
     float dd = e / __ldg(P.dens + m);
-    if ((kMode == 1) && D.tle && (D.flags & (GATE_B200_SCORE_EDEP_SQ | GATE_B200_SCORE_DOSE_SQ))) {
-      unsigned nl = tl_ld(&P.tle_state[gslot].w);
-      const unsigned before = nl;
-      tle_table_add(P, gslot, nl, key, e, dd, 1, ds.tle_ent, ds.tle_over);
-      if (nl != before) tl_st(&P.tle_state[gslot].w, nl);
+    if (is_tle(kMode) && D.tle && (D.flags & (GATE_B200_SCORE_EDEP_SQ | GATE_B200_SCORE_DOSE_SQ))) {
+      unsigned nl = tl_ld(&P.tle_state[gslot].w), nr = tl_ld(&P.tle_aux[gslot].y);
+      if (kMode == 5) {
+        // a point deposit is a record of its own: bounding box = its voxel, direction 0
+        if (nr >= (unsigned)P.tle_rec_cap) { nl = 0; nr = 0; ds.tle_over++; }
+        nr++;
+        const int iv[3] = {v % D.size[0], (v / D.size[0]) % D.size[1], v / (D.size[0] * D.size[1])};
+        float tmin = 0.0f;
+        unsigned long long cand = (1ull << (nr - 1u)) - 1ull;   // every stored record
+        tle_fold_add(P, D, gslot, nr, nl, tmin, cand, key, iv, -1, e, dd, 1, 0.0f, ds.tle_ent, ds.tle_over);
+        float4 *rec = P.tle_rec + ((size_t)gslot * kTleRecMax + (nr - 1u)) * kTleRecW;
+        tl_st(rec, make_float4(e, dd, __int_as_float(key), 0.0f));
+        tl_st(rec + 1, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+        tl_st(rec + 2, make_float4(__uint_as_float((unsigned)iv[0] | ((unsigned)iv[1] << 16)), __uint_as_float((unsigned)iv[2] | ((unsigned)iv[0] << 16)),
+                                   __uint_as_float((unsigned)iv[1] | ((unsigned)iv[2] << 16)), 0.0f));
+        tl_st(&P.tle_state[gslot].w, nl);
+        tl_st(P.tle_aux + gslot, make_uint2(0u, nr));
+      } else {
+        const unsigned nl0 = nl, nr0 = nr, over0 = ds.tle_over;
+        tle_record_begin_tab(P, gslot, nl, nr, ds.tle_ent, ds.tle_over);
+        const unsigned over1 = ds.tle_over;
+        tle_table_add(P, gslot, nl, key, e, dd, 1, ds.tle_ent, ds.tle_over);
+        if (ds.tle_over != over1) nr = 1;   // the table was written out while this deposit was scored
+        if (nl != nl0 || ds.tle_over != over0) tl_st(&P.tle_state[gslot].w, nl);
+        if (nr != nr0) tl_st(&P.tle_aux[gslot].y, nr);
+      }
       continue;
     }
     int j = 0;
-    if (kMode >= 2 && kPre) {
+    if (is_one(kMode) && kPre) {
       // entries 0 and 1 by their prefetched keys, the rest (rare) by the loop
       if (nbuf > 0 && pk.k0 == key) j = 0;
       else if (nbuf > 1 && pk.k1 == key) j = 1;
@@ -730,7 +913,7 @@ __device__ __forceinline__ void deposit(const Params &P, Ph &g, DepEntry *buf, D
       en = ld_dep(buf + j);
       en.e += e; en.d += dd; en.n += 1;
     }
-    if (kMode >= 2 && kKeep) { keep.en = en; keep.j = j; }
+    if (is_one(kMode) && kKeep) { keep.en = en; keep.j = j; }
     else st_dep(buf + j, en);
   }
   g.flags = (g.flags & ~F_NBUF) | ((unsigned)nbuf << F_NBUF_SHIFT);
@@ -1348,7 +1531,7 @@ __device__ __forceinline__ int volume_decide(const Params &P, Smem &S, int slot,
     next = route_interaction(P, flags, mat, c.ie, c.fe, vsel);
     S.fm[slot] = flags | ((unsigned)mat << F_MAT_SHIFT);
   }
-  if ((kMode == 1) && next != Q_V && S.E[slot] <= P.tle_thr_max) {
+  if (is_tle(kMode) && next != Q_V && S.E[slot] <= P.tle_thr_max) {
     // the flight has ended (interaction or exit): score its voxel chords first, then carry on
     S.fm[slot] |= (unsigned)(next - 1) << F_NEXT_SHIFT;
     tl_st(&P.tle_state[gslot].x, __float_as_uint(-1.0f));
@@ -1439,7 +1622,7 @@ __device__ __forceinline__ int phase_compton(const Params &P, Smem &S, int slot,
     rotate_dir(g.d, cost, sint, sphi, cphi);
     g.E = E1;
     g.seg = 0.0f;
-    if (E1 < P.e_cut || ((kMode == 1) && in_vol && E1 <= P.tle_emin)) {
+    if (E1 < P.e_cut || (is_tle(kMode) && in_vol && E1 <= P.tle_emin)) {
       deposit<kMode>(P, g, buf, ds, E1 * wgt, m, in_vol, kBig, gslot);
       next = Q_E;
     } else {
@@ -1456,7 +1639,7 @@ __device__ __forceinline__ int phase_compton(const Params &P, Smem &S, int slot,
     stat_bump(S, S_DEP, t >> 8);
   }
   stat_overflow(S, ds.over, ds.flush);
-  if ((kMode == 1)) stat_tle_overflow(S, ds.tle_over, ds.tle_ent);
+  if (is_tle(kMode)) stat_tle_deposits<kMode>(S, ds.tle_over, ds.tle_ent);
   return next;
 }
 
@@ -1541,7 +1724,7 @@ __device__ __forceinline__ int phase_rare(const Params &P, Smem &S, int slot, in
     stat_bump(S, S_DEP, t >> 16);
   }
   stat_overflow(S, ds.over, ds.flush);
-  if ((kMode == 1)) stat_tle_overflow(S, ds.tle_over, ds.tle_ent);
+  if (is_tle(kMode)) stat_tle_deposits<kMode>(S, ds.tle_over, ds.tle_ent);
   return in_vol ? Q_V : Q_W;
 }
 
@@ -1564,7 +1747,7 @@ __device__ __forceinline__ int phase_end(const Params &P, Smem &S, int slot, int
     // the single-actor kernels close the history in this very call unless a second annihilation photon is
     // pending: the entry of this last deposit goes to the grids from registers, not through the buffer
     DepKeys nopk; nopk.k0 = -1; nopk.k1 = -1;
-    if (GB2_CLOSE_FUSED && kMode >= 2 && !(g.flags & F_PEND))
+    if (GB2_CLOSE_FUSED && is_one(kMode) && !(g.flags & F_PEND))
       deposit<kMode, false, true>(P, g, P.depbuf + (size_t)gslot * kDepBuf, ds, g.E * hist_weight<kMode>(P, gslot), g.mat, (g.flags & F_INVOL) != 0, g.E, gslot, nopk, keep);
     else
       deposit<kMode>(P, g, P.depbuf + (size_t)gslot * kDepBuf, ds, g.E * hist_weight<kMode>(P, gslot), g.mat, (g.flags & F_INVOL) != 0, g.E, gslot);
@@ -1588,7 +1771,7 @@ __device__ __forceinline__ int phase_end(const Params &P, Smem &S, int slot, int
     next = locate<kMode>(P, g);
     set_energy(P, S, slot, g);
     store_ph(S, slot, g);
-  } else if ((kMode == 1) && (g.flags & F_OPEN) && P.tle_tab && tl_ld(&P.tle_state[gslot].w) != 0u) {
+  } else if (kMode == 1 && (g.flags & F_OPEN) && P.tle_tab && tl_ld(&P.tle_state[gslot].w) != 0u) {
     // the history's TLE table goes to the grids first: chunked, in the TLE phase; then back here
     tl_st(&P.tle_state[gslot].x, __float_as_uint(-2.0f));
     tl_st(&P.tle_state[gslot].y, 0u);
@@ -1597,9 +1780,13 @@ __device__ __forceinline__ int phase_end(const Params &P, Smem &S, int slot, int
     next = Q_T;
   } else {
     if (g.flags & F_OPEN) {
+      if (kMode == 5) {   // the history's records are forgotten: its sums are in the grids already
+        tl_st(&P.tle_state[gslot].w, 0u);
+        tl_st(P.tle_aux + gslot, make_uint2(0u, 0u));
+      }
       const int nbuf = (int)((g.flags & F_NBUF) >> F_NBUF_SHIFT);
       if (nbuf) {
-        if (GB2_CLOSE_FUSED && kMode >= 2) flush_buffer_keep<kMode>(P, P.depbuf + (size_t)gslot * kDepBuf, nbuf, keep.en, keep.j);
+        if (GB2_CLOSE_FUSED && is_one(kMode)) flush_buffer_keep<kMode>(P, P.depbuf + (size_t)gslot * kDepBuf, nbuf, keep.en, keep.j);
         else flush_buffer<kMode>(P, P.depbuf + (size_t)gslot * kDepBuf, nbuf);
       }
       n_flush = (unsigned)nbuf;
@@ -1649,7 +1836,7 @@ __device__ __forceinline__ int phase_end(const Params &P, Smem &S, int slot, int
     stat_bump(S, S_DEP, t >> 24);
   }
   stat_overflow(S, ds.over, ds.flush);
-  if ((kMode == 1)) stat_tle_overflow(S, ds.tle_over, ds.tle_ent);
+  if (is_tle(kMode)) stat_tle_deposits<kMode>(S, ds.tle_over, ds.tle_ent);
   return next;
 }
 
@@ -1661,7 +1848,7 @@ __device__ __forceinline__ int phase_end(const Params &P, Smem &S, int slot, int
 // distances are always computed from the integer voxel index; a call walks kTleSteps chords and the
 // slot is queued again until the flight is done (lanes never wait for each other's long flights).
 // The same phase writes the per-history table out at the end of a history (tle_state.x == -2).
-template <typename LabelT>
+template <typename LabelT, int kMode>
 __device__ __forceinline__ int phase_tle(const Params &P, Smem &S, int slot, int gslot) {
   const unsigned fm = S.fm[slot];
   uint4 st = tl_ld(P.tle_state + gslot);
@@ -1669,7 +1856,7 @@ __device__ __forceinline__ int phase_tle(const Params &P, Smem &S, int slot, int
   unsigned nlist = st.w;
   unsigned n_steps = 0, n_ent = 0, n_over = 0;
   bool done = false;
-  if (tcur == -2.0f) {
+  if (kMode != 5 && tcur == -2.0f) {
     DepEntry *tab = P.tle_tab + (size_t)gslot * kTleH;
     const unsigned short *list = P.tle_list + (size_t)gslot * kTleMax;
     unsigned j = st.y;
@@ -1682,7 +1869,10 @@ __device__ __forceinline__ int phase_tle(const Params &P, Smem &S, int slot, int
     }
     done = j >= nlist;
     st.y = j;
-    if (done) { st.x = __float_as_uint(-1.0f); st.y = 0u; st.w = 0u; }
+    if (done) {
+      st.x = __float_as_uint(-1.0f); st.y = 0u; st.w = 0u;
+      tl_st(&P.tle_aux[gslot].y, 0u);
+    }
   } else {
     const float p[3] = {S.px[slot], S.py[slot], S.pz[slot]};
     const float d[3] = {S.dx[slot], S.dy[slot], S.dz[slot]};
@@ -1702,6 +1892,13 @@ __device__ __forceinline__ int phase_tle(const Params &P, Smem &S, int slot, int
       s[a] = __fmaf_rn(-d[a], seg, p[a]);
       inv_d[a] = d[a] != 0.0f ? 1.0f / d[a] : 0.0f;
     }
+    // records behind the sums of the history (only where event-wise squares are scored)
+    const bool sq = kMode == 5 || P.tle_tab != nullptr;
+    uint2 aux = make_uint2(0u, 0u);
+    if (sq) aux = tl_ld(P.tle_aux + gslot);
+    unsigned nrec = aux.y;
+    const unsigned nrec0 = nrec;
+    float tmin = __uint_as_float(aux.x);
     if (tcur < 0.0f) {
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
@@ -1711,6 +1908,14 @@ __device__ __forceinline__ int phase_tle(const Params &P, Smem &S, int slot, int
         i[a] = v;
       }
       tcur = 0.0f;
+      // a new scored flight = one more record of the history
+      if (kMode == 5) {
+        if (nrec >= (unsigned)P.tle_rec_cap) { nlist = 0; nrec = 0; n_over++; }
+        nrec++;
+        tmin = 0.0f;
+      } else if (sq) {
+        tle_record_begin_tab(P, gslot, nlist, nrec, n_ent, n_over);
+      }
     } else {
       i[0] = (int)(st.y & 0xffffu); i[1] = (int)(st.y >> 16); i[2] = (int)st.z;
     }
@@ -1722,6 +1927,25 @@ __device__ __forceinline__ int phase_tle(const Params &P, Smem &S, int slot, int
       r.h0 = (uint32_t)id; r.h1 = (uint32_t)(id >> 32); r.blk = S.blk[slot]; r.pos = 4;
     }
     const LabelT *__restrict__ labels = reinterpret_cast<const LabelT *>(P.labels);
+    // variant 5: the stored records whose voxel range meets the voxels this call can reach (kTleSteps steps from the
+    // current voxel, each axis in its direction of travel): the others are not looked at again chord by chord
+    unsigned long long cand = 0ull;
+    if (kMode == 5 && nrec > 1u) {
+      int blo[3], bhi[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        blo[a] = d[a] < 0.0f ? i[a] - kTleSteps : i[a];
+        bhi[a] = d[a] > 0.0f ? i[a] + kTleSteps : i[a];
+      }
+      const float4 *rec = P.tle_rec + (size_t)gslot * (kTleRecMax * kTleRecW);
+      for (unsigned rr = 0; rr + 1u < nrec; ++rr) {
+        const float4 Cf = tl_ld(rec + kTleRecW * rr + 2);
+        const unsigned cx = __float_as_uint(Cf.x), cy = __float_as_uint(Cf.y), cz = __float_as_uint(Cf.z);
+        if ((int)(cx & 0xffffu) <= bhi[0] && (int)(cy >> 16) >= blo[0] && (int)(cx >> 16) <= bhi[1] && (int)(cz & 0xffffu) >= blo[1] &&
+            (int)(cy & 0xffffu) <= bhi[2] && (int)(cz >> 16) >= blo[2])
+          cand |= 1ull << rr;
+      }
+    }
     for (int it = 0; it < kTleSteps; ++it) {
       float tn = kBig;
       int ax = -1;
@@ -1742,6 +1966,16 @@ __device__ __forceinline__ int phase_tle(const Params &P, Smem &S, int slot, int
         const int m = (int)__ldg(labels + flat);
         const float rho = __ldg(P.dens + m);
         n_steps++;
+        if (kMode == 5) {
+          // the one TLE actor, on the image grid: the voxel of the chord is the image voxel
+          const DDose &D = P.dose[P.tle_a];
+          const float2 mv = __ldg(D.muen2 + (size_t)ie * P.nmat + m);
+          const float muen = __fmaf_rn(fe, mv.y - mv.x, mv.x);
+          const float e = ((kE * muen) * L) * rho;
+          const float dd = e / rho;
+          const int key = (int)(((unsigned)P.tle_a << 28) | flat);
+          tle_fold_add(P, D, gslot, nrec, nlist, tmin, cand, key, i, m, e, dd, 0, tcur, n_ent, n_over);
+        } else
         for (int a = 0; a < P.ndose; ++a) {
           const DDose &D = P.dose[a];
           if (!D.tle || !(E <= D.tle_thr)) continue;
@@ -1769,7 +2003,9 @@ __device__ __forceinline__ int phase_tle(const Params &P, Smem &S, int slot, int
           }
           const int key = (int)(((unsigned)a << 28) | (unsigned)v);
           if (D.flags & (GATE_B200_SCORE_EDEP_SQ | GATE_B200_SCORE_DOSE_SQ)) {
+            const unsigned over1 = n_over;
             tle_table_add(P, gslot, nlist, key, e, dd, 0, n_ent, n_over);
+            if (n_over != over1) nrec = 1;   // the table was written out while this flight is being scored
           } else {
             DepEntry z; z.key = key; z.e = e; z.d = dd; z.n = 0;
             grid_add(P, z);
@@ -1782,12 +2018,31 @@ __device__ __forceinline__ int phase_tle(const Params &P, Smem &S, int slot, int
       // selects instead of i[ax]/d[ax]: a run-time index would push the walk state to local memory
       const float dax = ax == 0 ? d[0] : (ax == 1 ? d[1] : d[2]);
       const int stp = dax > 0.0f ? 1 : -1;
-      int iv;
-      if (ax == 0) { i[0] += stp; iv = i[0]; } else if (ax == 1) { i[1] += stp; iv = i[1]; } else { i[2] += stp; iv = i[2]; }
+      const int iv = (ax == 0 ? i[0] : (ax == 1 ? i[1] : i[2])) + stp;
       const int nax = ax == 0 ? P.n[0] : (ax == 1 ? P.n[1] : P.n[2]);
       if (iv < 0 || iv >= nax) { done = true; break; }
+      if (ax == 0) i[0] = iv; else if (ax == 1) i[1] = iv; else i[2] = iv;
     }
     S.blk[slot] = r.blk;
+    if (kMode == 5 && done) {
+      // the flight becomes a record: start, direction, length, energy, the range of voxels it walked
+      int lo[3], hi[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        int v = (int)floorf(__fmaf_rn(s[a], P.inv_sp[a], P.hs[a]));
+        if (v < 0) v = 0;
+        if (v > P.n[a] - 1) v = P.n[a] - 1;
+        lo[a] = v < i[a] ? v : i[a];
+        hi[a] = v < i[a] ? i[a] : v;
+      }
+      float4 *rec = P.tle_rec + ((size_t)gslot * kTleRecMax + (nrec - 1u)) * kTleRecW;
+      tl_st(rec, make_float4(s[0], s[1], s[2], t_end));
+      tl_st(rec + 1, make_float4(d[0], d[1], d[2], kE));
+      tl_st(rec + 2, make_float4(__uint_as_float((unsigned)lo[0] | ((unsigned)lo[1] << 16)), __uint_as_float((unsigned)lo[2] | ((unsigned)hi[0] << 16)),
+                                 __uint_as_float((unsigned)hi[1] | ((unsigned)hi[2] << 16)), S.tbin[slot]));
+      tl_st(rec + 3, make_float4(tmin, 0.0f, 0.0f, 0.0f));
+    }
+    if (sq && (nrec != nrec0 || __float_as_uint(tmin) != aux.x)) tl_st(P.tle_aux + gslot, make_uint2(__float_as_uint(tmin), nrec));
     st.x = __float_as_uint(done ? -1.0f : tcur);
     st.y = (unsigned)i[0] | ((unsigned)i[1] << 16);
     st.z = (unsigned)i[2];
@@ -1811,7 +2066,7 @@ __device__ __forceinline__ int phase_tle(const Params &P, Smem &S, int slot, int
 // reference's default hit_type is random); kMode 4: ONE dose actor with phase-space actors (their loops stay);
 // kMode 0: everything else
 template <typename LabelT, int kMode>
-__global__ void __launch_bounds__(threads_of<(kMode == 1)>(), GB2_MIN_CTAS) transport_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(threads_of<is_tle(kMode)>(), GB2_MIN_CTAS) transport_kernel(const __grid_constant__ Params P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem &S = *reinterpret_cast<Smem *>(smem_raw);
   float *s_maj = reinterpret_cast<float *>(smem_raw + sizeof(Smem));
@@ -1942,7 +2197,7 @@ __global__ void __launch_bounds__(threads_of<(kMode == 1)>(), GB2_MIN_CTAS) tran
       if (q == Q_C) next[0] = phase_compton<kMode>(P, S, slot[0], slot_base + slot[0], c_edep);
       else if (q == Q_E) next[0] = phase_end<kMode>(P, S, slot[0], slot_base + slot[0], c_edep);
       else if (q == Q_W) next[0] = phase_world<kMode>(P, S, slot[0], slot_base + slot[0]);
-      else if ((kMode == 1) && q == Q_T) next[0] = phase_tle<LabelT>(P, S, slot[0], slot_base + slot[0]);
+      else if (is_tle(kMode) && q == Q_T) next[0] = phase_tle<LabelT, kMode>(P, S, slot[0], slot_base + slot[0]);
       else next[0] = phase_rare<kMode>(P, S, slot[0], slot_base + slot[0], c_edep);
     }
     __syncwarp();

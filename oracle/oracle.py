@@ -69,6 +69,10 @@ def lib(fp64=False):
         L.oracle_add_phsp_actor.argtypes = [C.c_void_p, C.POINTER(abi.PhspDesc)]
         L.oracle_begin_run.argtypes = [C.c_void_p]
         L.oracle_run_source.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_int]
+        L.oracle_set_tle_fold.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_set_tle_fold.restype = C.c_int
+        L.oracle_set_tle_rec_cap.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_set_tle_rec_cap.restype = C.c_int
         L.oracle_trace_history.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.POINTER(Trace)]
         L.oracle_dose_grid.restype = C.POINTER(C.c_double)
         L.oracle_dose_grid.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -134,6 +138,18 @@ class TransportOracle:
         self._keep.append(keep)
         self._dose_sizes.append(tuple(desc.size))
         return self.L.oracle_add_tle_dose_actor(self.h, C.byref(desc), C.byref(tle_desc))
+
+    def set_tle_fold(self, on=True):
+        """score the (one, image-aligned, squares) TLE actor by the device's record-fold statement instead of the
+        per-history table: a CPU cross-check of that algorithm (transport_oracle.c tle_fold_*)"""
+        if self.L.oracle_set_tle_fold(self.h, int(on)) != 0:
+            raise ValueError("the record-fold statement needs exactly one TLE actor, with squares, on the image grid")
+
+    def set_tle_rec_cap(self, cap):
+        """records (scored flights + point deposits) a history may hold before its sums are written out: 64 on the
+        device; tests lower it on both sides to reach that overflow path"""
+        if self.L.oracle_set_tle_rec_cap(self.h, int(cap)) != 0:
+            raise ValueError("record cap out of range")
 
     def add_phsp_actor(self, desc):
         return self.L.oracle_add_phsp_actor(self.h, C.byref(desc))

@@ -203,6 +203,8 @@ static real_t rng_uniform(rng_t *r) {
 #define TLE_H 4096     /* per-history table of (actor, voxel) sums of a TLE actor with squares */
 #define TLE_MAX 3072   /* entries at which the table is written out (counted as an overflow) */
 #define TLE_EMPTY (-1)
+#define TLE_REC_MAX 64 /* scored flights + point deposits of one history a TLE actor with squares keeps apart: one more
+                        * writes the table out first (counted as an overflow, like a full table) */
 #define MAX_BLOCKS 4000000u
 #define NUDGE 1.0e-3f
 #define BIG 3.0e38f
@@ -267,12 +269,21 @@ struct oracle_engine {
   int ntle;            /* dose actors that are track-length estimators */
   real_t tle_emin;      /* max energy_min over them */
   real_t tle_thr_max;   /* max threshold over them */
+  int tle_sq;          /* one of them scores event-wise squares (a per-history table exists) */
+  int tle_rec_cap;     /* records a history may hold (TLE_REC_MAX; tests lower it to reach the overflow path) */
+  int tle_fold;        /* test switch (index of the TLE actor + 1): score it by the device's record-fold statement, not the table */
   int nphsp; ophsp_t phsp[ORACLE_MAX_PHSP];
   gate_b200_stats stats;
   char err[256];
 };
 
 typedef struct { int key; real_t e; real_t d; int n; } dep_t;
+/* one scored flight (point = 0) or one point deposit (point = 1) of a history, as the device keeps it (transport.cuh) */
+typedef struct tle_rec {
+  int point;
+  real_t s[3], d[3], t_end, t_min, kE, fe; int ie; int lo[3], hi[3];   /* flight: start, direction, length, energy bin, voxel range */
+  int key; real_t e, dd;                                              /* point deposit */
+} tle_rec;
 
 typedef struct {
   oracle_engine *g;
@@ -287,6 +298,9 @@ typedef struct {
   uint64_t hist;
   dep_t buf[DEP_BUF]; int nbuf;
   dep_t *ttab; uint16_t *tlist; int nlist;   /* TLE table of this history (thread scratch) */
+  int nrec;                                  /* records (scored flights, point deposits) behind the table's content */
+  struct tle_rec *recs;                      /* the records themselves (only used by the fold statement) */
+  real_t fold_tmin;                          /* fold: chords of the current flight before this t are written out already */
   gate_b200_stats st;
   oracle_trace *trace;
 } hist_t;
@@ -436,6 +450,7 @@ static void tle_flush(hist_t *h) {
     h->st.tle_entries++;
   }
   h->nlist = 0;
+  h->nrec = 0;
 }
 static void tle_table_add(hist_t *h, int key, real_t e, real_t d, int n) {
   uint32_t hh = ((uint32_t)key * 2654435761u) >> 20;   /* 32 - log2(TLE_H) */
@@ -445,6 +460,7 @@ static void tle_table_add(hist_t *h, int key, real_t e, real_t d, int n) {
     if (b->key == TLE_EMPTY) {
       if (h->nlist == TLE_MAX) {   /* table full: write it out, start again (squares of this history split) */
         tle_flush(h);
+        h->nrec = 1;               /* the flight / deposit that is being scored goes on in the new table */
         h->st.tle_overflows++;
         hh = ((uint32_t)key * 2654435761u) >> 20;
         b = &h->ttab[hh];
@@ -455,6 +471,111 @@ static void tle_table_add(hist_t *h, int key, real_t e, real_t d, int n) {
     }
     hh = (hh + 1u) & (TLE_H - 1u);
   }
+}
+
+/* ---- the same sums WITHOUT a table (the device's statement for one TLE actor on the image grid, transport.cuh
+ * tle_fold_*; here behind oracle_set_tle_fold as a CPU cross-check of that algorithm against the table above).
+ * A straight flight crosses a voxel once, so two contributions of a history to one voxel come from different
+ * flights (or point deposits).  The history keeps its scored flights and point deposits as RECORDS; the sum a voxel
+ * holds so far is re-evaluated from them: the chord of an earlier flight through a given voxel has a closed form
+ * with exactly the bits the voxel walk produced (entry = the latest entering-face distance of the axes that moved,
+ * exit = the earliest leaving-face distance, each face distance the same expression of the integer face index).
+ * With the previous sum p and the new one p + e of a voxel, the grids get (p + e) - p and (p + e)^2 - p^2: at the end
+ * of the history they hold the sum and the square of the event's total, as GateDoseActor.cpp:359-381 asks. */
+static real_t tle_rec_chord(const oracle_engine *g, const tle_rec *r, const int iv[3], real_t *t_in_out) {
+  real_t t_in = 0.0f, t_out = r->t_end;
+  for (int a = 0; a < 3; ++a) {
+    if (iv[a] < r->lo[a] || iv[a] > r->hi[a]) return -1.0f;
+    if (r->d[a] == 0.0f) continue;
+    const real_t inv = 1.0f / r->d[a];
+    const int up = r->d[a] > 0.0f;
+    const real_t f_in = R_FMA((real_t)(iv[a] + (up ? 0 : 1)), g->sp[a], -g->half[a]);
+    const real_t f_out = R_FMA((real_t)(iv[a] + (up ? 1 : 0)), g->sp[a], -g->half[a]);
+    if (iv[a] != (up ? r->lo[a] : r->hi[a])) {   /* the walk entered this voxel layer through f_in */
+      const real_t tb = (f_in - r->s[a]) * inv;
+      if (tb > t_in) t_in = tb;
+    }
+    const real_t tb = (f_out - r->s[a]) * inv;
+    if (tb < t_out) t_out = tb;
+  }
+  *t_in_out = t_in;
+  return t_out - t_in;
+}
+/* sum of the earlier contributions of this history to voxel v = (iv) of the one TLE actor; m < 0: label not known yet */
+static int tle_fold_prev(hist_t *h, int key, const int iv[3], int m, real_t *pe, real_t *pd) {
+  oracle_engine *g = h->g;
+  const odose_t *D = &g->dose[g->tle_fold - 1];
+  int found = 0;
+  real_t se = 0.0f, sd = 0.0f, rho = 0.0f;
+  const int nst = h->nrec > 0 ? h->nrec - 1 : 0;   /* stored records: all but the one being scored */
+  for (int r = 0; r < nst; ++r) {
+    const tle_rec *R = &h->recs[r];
+    if (R->point) {
+      if (R->key == key) { se += R->e; sd += R->dd; found = 1; }
+      continue;
+    }
+    real_t t_in;
+    const real_t L = tle_rec_chord(g, R, iv, &t_in);
+    if (!(L > 0.0f) || t_in < R->t_min) continue;
+    if (m < 0) {
+      const size_t flat = (size_t)iv[0] + (size_t)g->n[0] * ((size_t)iv[1] + (size_t)g->n[1] * (size_t)iv[2]);
+      m = g->label_bytes == 1 ? (int)((const uint8_t *)g->labels)[flat] : (int)((const uint16_t *)g->labels)[flat];
+    }
+    rho = g->dens[m];
+    const real_t muen = tab(D->muen, g->ne, m, R->ie, R->fe);
+    const real_t e = ((R->kE * muen) * L) * rho;
+    se += e; sd += e / rho; found = 1;
+  }
+  *pe = se; *pd = sd;
+  return found;
+}
+/* one contribution (chord or point deposit) of the history to voxel v; tcur: where the current flight stands */
+static void tle_fold_add(hist_t *h, int key, const int iv[3], int m, real_t e, real_t dd, int n, real_t tcur) {
+  oracle_engine *g = h->g;
+  odose_t *D = &g->dose[g->tle_fold - 1];
+  real_t pe, pd;
+  if (!tle_fold_prev(h, key, iv, m, &pe, &pd)) {
+    if (h->nlist == TLE_MAX) {   /* the table this stands for would be full: forget what was scored so far */
+      h->nrec = 1;
+      h->fold_tmin = tcur;
+      h->nlist = 0;
+      h->st.tle_overflows++;
+    }
+    h->nlist++;
+    h->st.tle_entries++;
+  }
+  const real_t ne = pe + e, nd = pd + dd;
+  const int v = key & 0x0fffffff;
+  const double e0 = (double)pe, e1 = (double)ne, d0 = (double)pd, d1 = (double)nd;
+#pragma omp atomic
+  D->grid[GATE_B200_GRID_EDEP][v] += e1 - e0;
+  if (D->flags & GATE_B200_SCORE_EDEP_SQ) {
+#pragma omp atomic
+    D->grid[GATE_B200_GRID_EDEP_SQ][v] += e1 * e1 - e0 * e0;
+  }
+  if (D->flags & GATE_B200_SCORE_DOSE) {
+#pragma omp atomic
+    D->grid[GATE_B200_GRID_DOSE][v] += d1 - d0;
+  }
+  if (D->flags & GATE_B200_SCORE_DOSE_SQ) {
+#pragma omp atomic
+    D->grid[GATE_B200_GRID_DOSE_SQ][v] += d1 * d1 - d0 * d0;
+  }
+  if ((D->flags & GATE_B200_SCORE_COUNTS) && n) {
+#pragma omp atomic
+    D->grid[GATE_B200_GRID_COUNTS][v] += (double)n;
+  }
+}
+/* a scored flight or a point deposit is about to add to the history's sums: one more record behind them */
+static void tle_record_begin(hist_t *h) {
+  if (!h->g->tle_sq) return;
+  if (h->nrec >= h->g->tle_rec_cap) {
+    if (h->g->tle_fold) { h->nlist = 0; h->nrec = 0; }
+    else tle_flush(h);
+    h->st.tle_overflows++;
+  }
+  h->nrec++;
+  h->fold_tmin = 0.0f;
 }
 
 /* deposit e (already weighted) at the current phantom-frame point, material m.  e_tle: flight energy
@@ -508,7 +629,15 @@ static void deposit(hist_t *h, real_t e, int m, int vix, int viy, int viz, real_
     int key = (int)(((uint32_t)a << 28) | (uint32_t)v);
     real_t dd = e / g->dens[m];
     if (D->tle && (D->flags & (GATE_B200_SCORE_EDEP_SQ | GATE_B200_SCORE_DOSE_SQ))) {
-      tle_table_add(h, key, e, dd, 1);
+      tle_record_begin(h);
+      if (g->tle_fold) {
+        const int iv[3] = {v % D->size[0], (v / D->size[0]) % D->size[1], v / (D->size[0] * D->size[1])};
+        tle_fold_add(h, key, iv, -1, e, dd, 1, 0.0f);
+        tle_rec *R = &h->recs[h->nrec - 1];
+        R->point = 1; R->key = key; R->e = e; R->dd = dd;
+      } else {
+        tle_table_add(h, key, e, dd, 1);
+      }
       continue;
     }
     int j;
@@ -978,6 +1107,8 @@ static void tle_march(hist_t *h, real_t to) {
   }
   const real_t kE = (0.1f * h->E) * h->w;
   real_t tcur = 0.0f;
+  const int i0[3] = {i[0], i[1], i[2]};
+  tle_record_begin(h);
   for (int it = 0;; ++it) {
     if (it % TLE_STEPS == 0) rng_begin(&h->rng);
     real_t tn = BIG;
@@ -1024,7 +1155,8 @@ static void tle_march(hist_t *h, real_t to) {
         }
         const int key = (int)(((uint32_t)a << 28) | (uint32_t)v);
         if (D->flags & (GATE_B200_SCORE_EDEP_SQ | GATE_B200_SCORE_DOSE_SQ)) {
-          tle_table_add(h, key, e, dd, 0);
+          if (g->tle_fold) tle_fold_add(h, key, i, m, e, dd, 0, tcur);
+          else tle_table_add(h, key, e, dd, 0);
         } else {
           dep_t b; b.key = key; b.e = e; b.d = dd; b.n = 0;
           grid_add(g, &b);
@@ -1034,8 +1166,20 @@ static void tle_march(hist_t *h, real_t to) {
     }
     if (last) break;
     if (tnext > tcur) tcur = tnext;
-    i[ax] += h->d[ax] > 0.0f ? 1 : -1;
-    if (i[ax] < 0 || i[ax] >= g->n[ax]) break;
+    const int ni = i[ax] + (h->d[ax] > 0.0f ? 1 : -1);
+    if (ni < 0 || ni >= g->n[ax]) break;
+    i[ax] = ni;
+  }
+  if (g->tle_fold && g->tle_sq) {
+    /* the flight becomes a record: start, direction, length, energy, the range of voxels it walked */
+    tle_rec *R = &h->recs[h->nrec - 1];
+    R->point = 0;
+    for (int a = 0; a < 3; ++a) {
+      R->s[a] = s[a]; R->d[a] = h->d[a];
+      R->lo[a] = i0[a] < i[a] ? i0[a] : i[a];
+      R->hi[a] = i0[a] < i[a] ? i[a] : i0[a];
+    }
+    R->t_end = t_end; R->t_min = h->fold_tmin; R->kE = kE; R->ie = h->ie; R->fe = h->fe;
   }
 }
 
@@ -1241,14 +1385,14 @@ static void run_photon(hist_t *h, real_t pend_p[3], real_t pend_d[3], int *pend)
   }
 }
 
-typedef struct { dep_t *tab; uint16_t *list; } tle_scratch;
+typedef struct { dep_t *tab; uint16_t *list; tle_rec *recs; } tle_scratch;
 
 static void run_history(oracle_engine *g, const osource_t *s, uint64_t hist, gate_b200_stats *acc,
                         oracle_trace *trace, tle_scratch *ts) {
   hist_t h;
   memset(&h, 0, sizeof h);
   h.g = g; h.hist = hist; h.trace = trace;
-  h.ttab = ts->tab; h.tlist = ts->list; h.nlist = 0;
+  h.ttab = ts->tab; h.tlist = ts->list; h.nlist = 0; h.recs = ts->recs; h.nrec = 0;
   if (trace) { trace->n_dep = 0; trace->n_iter = 0; }
   rng_init(&h.rng, g->seed, hist);
   generate_primary(&h, s);
@@ -1300,7 +1444,7 @@ static void run_history(oracle_engine *g, const osource_t *s, uint64_t hist, gat
     run_photon(&h, pend_p, pend_d, &pend2);
   }
   flush_buffer(&h);
-  tle_flush(&h);
+  if (!g->tle_fold) tle_flush(&h);
   if (g->nphsp > 0 && !h.stored) h.st.absorbed_events++;
   /* accumulate */
   acc->histories += h.st.histories; acc->tracks += h.st.tracks; acc->steps += h.st.steps;
@@ -1331,6 +1475,7 @@ oracle_engine *oracle_create(uint64_t seed) {
   oracle_engine *g = (oracle_engine *)calloc(1, sizeof *g);
   g->seed = seed;
   g->wh[0] = g->wh[1] = g->wh[2] = 1.0e6f;
+  g->tle_rec_cap = TLE_REC_MAX;
   return g;
 }
 
@@ -1533,7 +1678,24 @@ int oracle_add_tle_dose_actor(oracle_engine *g, const gate_b200_dose_desc *d, co
   if (g->ntle == 0 || emin > g->tle_emin) g->tle_emin = emin;
   if (g->ntle == 0 || D->tle_thr > g->tle_thr_max) g->tle_thr_max = D->tle_thr;
   g->ntle++;
+  if (D->flags & (GATE_B200_SCORE_EDEP_SQ | GATE_B200_SCORE_DOSE_SQ)) g->tle_sq = 1;
   return id;
+}
+
+/* Test switch: score the TLE actor by the device's record-fold statement (above) instead of the per-history table.
+ * Only for the configuration the device uses it for: ONE dose actor, a TLE actor with squares on the image grid. */
+int oracle_set_tle_rec_cap(oracle_engine *g, int cap) {
+  if (cap < 1 || cap > TLE_REC_MAX) return -1;
+  g->tle_rec_cap = cap;
+  return 0;
+}
+int oracle_set_tle_fold(oracle_engine *g, int on) {
+  g->tle_fold = 0;
+  if (!on) return 0;
+  if (g->ntle != 1 || !g->tle_sq) return -1;
+  for (int a = 0; a < g->ndose; ++a)
+    if (g->dose[a].tle && g->dose[a].aligned) g->tle_fold = a + 1;   /* that actor's index + 1 */
+  return g->tle_fold ? 0 : -1;
 }
 
 int oracle_add_phsp_actor(oracle_engine *g, const gate_b200_phsp_desc *d) {
@@ -1561,9 +1723,10 @@ void oracle_begin_run(oracle_engine *g) {
 static void tle_scratch_init(tle_scratch *ts) {
   ts->tab = (dep_t *)malloc(TLE_H * sizeof(dep_t));
   ts->list = (uint16_t *)malloc(TLE_MAX * sizeof(uint16_t));
+  ts->recs = (tle_rec *)malloc(TLE_REC_MAX * sizeof(tle_rec));
   for (int i = 0; i < TLE_H; ++i) ts->tab[i].key = TLE_EMPTY;
 }
-static void tle_scratch_free(tle_scratch *ts) { free(ts->tab); free(ts->list); }
+static void tle_scratch_free(tle_scratch *ts) { free(ts->tab); free(ts->list); free(ts->recs); }
 
 int oracle_run_source(oracle_engine *g, int source_id, uint64_t first, uint64_t n, int n_threads) {
   const osource_t *s = &g->src[source_id];

@@ -16,13 +16,15 @@ INT_KEYS = ["histories", "tracks", "steps", "tentative_collisions", "n_phot", "n
             "absorbed_events"]
 
 
-def run_both(S, n, first=0):
+def run_both(S, n, first=0, tle_rec_cap=None):
     from opengate_b200.core import Engine
     from oracle.oracle import TransportOracle
     eng = Engine(0, S.seed)
     orc = TransportOracle(S.seed)
     se, de, pe = S.apply(eng)
     so, do, po = S.apply(orc)
+    if tle_rec_cap is not None:   # the engine reads GATE_B200_TLE_REC_CAP at launch (set by the caller)
+        orc.set_tle_rec_cap(tle_rec_cap)
     eng.begin_run()
     orc.begin_run()
     eng.run_source(se[0], first, n)

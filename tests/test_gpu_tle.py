@@ -59,6 +59,29 @@ def test_tle_table_overflow_matches_oracle(cuda_required):
     eng, orc, ids = run_both(S, 300)
     compare_all(eng, orc, S, ids)
     assert eng.stats()["tle_overflows"] > 0
+    assert eng.kernel_name().endswith(", 5>")   # one TLE actor with squares on the image grid: the record variant
+    eng.close()
+
+
+# Two kernel variants score a TLE actor with event-wise squares: 5 (ONE such actor on the image grid: the sums of a
+# history per voxel are re-evaluated from its flight records) and 1 (everything else: a table per history).  The
+# configurations above that qualify run variant 5; here the same ones are forced through variant 1, and both through
+# the record-overflow path (a history may hold 64 records: lowered to 2 on both sides).
+@pytest.mark.parametrize("table", [False, True])
+@pytest.mark.parametrize("cap", [None, 2])
+@pytest.mark.parametrize("mk,kw", [(c3_tle, {}), (c3_tle, {"threshold": 0.06}), (c4_tle, {}), (long_thin, {})])
+def test_tle_variants_and_record_overflow(cuda_required, monkeypatch, mk, kw, cap, table):
+    if table:
+        monkeypatch.setenv("GATE_B200_TLE_TABLE", "1")
+    if cap is not None:
+        monkeypatch.setenv("GATE_B200_TLE_REC_CAP", str(cap))
+    n = 300 if mk is long_thin else 4000
+    S = mk(n, **kw)
+    eng, orc, ids = run_both(S, n, tle_rec_cap=cap)
+    compare_all(eng, orc, S, ids)
+    assert eng.kernel_name().endswith(", 1>" if table else ", 5>")
+    if cap is not None:
+        assert eng.stats()["tle_overflows"] > 0
     eng.close()
 
 

@@ -103,3 +103,45 @@ def test_thread_count_does_not_change_the_result():
     for which in (abi.GRID_EDEP, abi.GRID_EDEP_SQ, abi.GRID_DOSE):
         np.testing.assert_allclose(o1.dose_grid(d1[-1], which), o4.dose_grid(d4[-1], which), rtol=1e-12)
     assert o1.stats()["tle_steps"] == o4.stats()["tle_steps"]
+
+
+@pytest.mark.parametrize("mk,n,cap", [(lambda: c3_tle(6000), 6000, None), (lambda: c3_tle(6000, threshold=0.06), 6000, None),
+                                      (lambda: c4_tle(6000), 6000, None), (lambda: long_thin(200), 200, None),
+                                      (lambda: c3_tle(6000), 6000, 2), (lambda: c3_tle(6000, threshold=0.06), 6000, 1)])
+def test_record_fold_statement_equals_the_table(mk, n, cap):
+    """The device scores ONE TLE actor with squares on the image grid without a per-history table: the sum a voxel
+    holds is re-evaluated from the records of the history's flights (closed form of a voxel chord) and point deposits.
+    The oracle carries that statement behind a switch; it must give the table's sums bit for bit (event sums are
+    float on both sides) and the same squares to the rounding of (p + e)^2 - p^2, overflow paths included."""
+    res = []
+    for fold in (False, True):
+        S = mk()
+        o = TransportOracle(S.seed)
+        sids, dids, _ = S.apply(o)
+        if cap is not None:
+            o.set_tle_rec_cap(cap)
+        if fold:
+            o.set_tle_fold(True)
+        o.begin_run()
+        o.run_source(sids[0], 0, n, 0)
+        res.append((o, dids))
+    (a, d), (b, _) = res
+    sa, sb = a.stats(), b.stats()
+    for k in ("tle_steps", "tle_entries", "tle_overflows", "deposits", "tentative_collisions"):
+        assert sa[k] == sb[k], k
+    if cap is not None or n == 200:
+        assert sa["tle_overflows"] > 0
+    for which in (abi.GRID_EDEP, abi.GRID_DOSE):
+        assert np.array_equal(a.dose_grid(d[-1], which), b.dose_grid(d[-1], which))
+    for which in (abi.GRID_EDEP_SQ, abi.GRID_DOSE_SQ):
+        x, y = a.dose_grid(d[-1], which), b.dose_grid(d[-1], which)
+        assert np.array_equal(x != 0, y != 0)
+        np.testing.assert_allclose(x, y, rtol=1e-14, atol=0)
+
+
+def test_record_fold_needs_one_aligned_tle_actor_with_squares():
+    S = c3_tle(10, coarse=True)
+    o = TransportOracle(S.seed)
+    S.apply(o)
+    with pytest.raises(ValueError):
+        o.set_tle_fold(True)

@@ -1,0 +1,19 @@
+#!/bin/bash
+# round 2: the record variant of the TLE kernel (no per-history tables) -- parity, then A/B against the table variant
+mkdir -p gpurun_out
+T=${1:-r2p}
+( timeout 1200 python -m pytest tests/test_gpu_tle.py tests/test_phsp_source.py -m gpu -q > gpurun_out/${T}_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/${T}_pytest.log )
+tail -5 gpurun_out/${T}_pytest.log
+{
+echo "== table variant (GATE_B200_TLE_TABLE=1)"
+GATE_B200_TLE_TABLE=1 timeout 200 python tools/profile_run.py --config c3tle --histories 4000000 --launches 2 | cut -c1-24,100-400
+for lib in "" gpurun_variants/lib_tle_1280.so; do
+  echo "== record variant lib=${lib:-default}"
+  env ${lib:+GATE_B200_LIB=$lib} timeout 200 python tools/profile_run.py --config c3tle --histories 8000000 --launches 2 | cut -c1-24,100-400
+  env ${lib:+GATE_B200_LIB=$lib} timeout 200 python tools/profile_run.py --config c3tle_nosq --histories 8000000 --launches 2 | cut -c1-24,100-400
+done
+} > gpurun_out/${T}_ab.log 2>&1
+cat gpurun_out/${T}_ab.log | cut -c1-200
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:transport_kernel -s 1 -c 1 \
+    -o gpurun_out/${T}_transport_c3tle -f python tools/profile_run.py --config c3tle --histories 4000000 --launches 1 --warmup 1 > gpurun_out/${T}_ncu_c3tle.log 2>&1
+tail -1 gpurun_out/${T}_ncu_c3tle.log

@@ -27,7 +27,15 @@ S = small_setups.c3(n)
 S.dose[0].hit_type = abi.HIT_POST
 S.dose[0].score_flags = abi.SCORE_EDEP | abi.SCORE_EDEP_SQ | abi.SCORE_DOSE
 cases["c3_bench_shape"] = S
+cases["c3_tle_sq_table"] = tle_setups.c3_tle(n)      # the same actor forced through the table variant (1) of the kernel
+cases["c3_tle_sq_hybrid_cap2"] = tle_setups.c3_tle(n, threshold=0.06)   # record variant: point deposits, record overflows
 for name, S in cases.items():
+    os.environ.pop("GATE_B200_TLE_TABLE", None)
+    os.environ.pop("GATE_B200_TLE_REC_CAP", None)
+    if name.endswith("_table"):
+        os.environ["GATE_B200_TLE_TABLE"] = "1"
+    if name.endswith("_cap2"):
+        os.environ["GATE_B200_TLE_REC_CAP"] = "2"
     eng = Engine(0, S.seed)
     se, de, pe = S.apply(eng)
     eng.begin_run()
@@ -45,5 +53,5 @@ for name, S in cases.items():
         eng.mean_uncertainty(de[0], n, 5, 0.7)
     for p in pe:
         eng.phsp(p)
-    print(name, st["histories"], st["tentative_collisions"], st["tle_steps"], flush=True)
+    print(name, eng.kernel_name(), st["histories"], st["tentative_collisions"], st["tle_steps"], st["tle_overflows"], flush=True)
     eng.close()

@@ -615,7 +615,7 @@ class PhaseSpaceActor(ActorBase):
     def get_output_path(self, which="merged"):
         f = self.output_filename
         if f == "auto":
-            f = f"phsp_from_{self.type_name.lower()}_{self.name}.npz"
+            f = f"phsp_from_{self.type_name.lower()}_{self.name}.root"   # ActorOutputRoot: default suffix root
         return self.simulation.get_output_path(f)
 
     def store_rows(self, rows, n_absorbed, event_offset=0, event_time=None):
@@ -676,16 +676,16 @@ class PhaseSpaceActor(ActorBase):
         path = str(self.get_output_path())
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
         if path.endswith(".root"):
-            try:
-                import uproot  # noqa: F401
-            except ImportError:
-                warning(f"PhaseSpaceActor '{self.name}': uproot is not available, writing {path[:-5]}.npz instead of ROOT")
-                path = path[:-5] + ".npz"
-            else:  # pragma: no cover - only where uproot exists
-                import uproot
-                with uproot.recreate(path) as f:
-                    f[self.name] = self.data
-                return
+            # a flat TTree named after the actor, one branch per column (GateDigiCollectionsRootManager: D -> double,
+            # I -> int, 3 -> name_X / _Y / _Z), written by the package's own ROOT writer (rootio.py)
+            from . import rootio
+            cols = {k: v for k, v in self.data.items() if v.dtype.name in rootio.LEAVES}
+            dropped = [k for k in self.data if k not in cols]
+            if dropped:
+                warning(f"PhaseSpaceActor '{self.name}': string column(s) {dropped} are not written to the ROOT file "
+                        f"(PDGCode carries the particle type)")
+            rootio.write_tree(path, self.name, cols, title=f"PhaseSpaceActor {self.name}")
+            return
         np.savez(path, **self.data)
 
 

@@ -333,21 +333,27 @@ class VoxelSource(GenericSource):
 
 
 def read_phase_space_columns(path, keys):
-    """Columns `keys` (those present) of a phase-space file -> dict of numpy arrays, and the number of
-    entries.  `.root`: first tree of the file through uproot, exactly as the reference reads it
-    (sources/phspsources.py:59-75,153-158); `.npz`: the column archive PhaseSpaceActor writes when
-    uproot is not installed (actors.py)."""
+    """Columns `keys` (those present) of a phase-space file -> dict of numpy arrays, and the names of all columns.
+    `.root`: first tree of the file, branches by name, as the reference reads it through uproot
+    (sources/phspsources.py:59-75,153-158) -- here through the package's own reader of flat TTrees (rootio.py:
+    uncompressed / zlib / lzma, fixed-size leaves), falling back to uproot, where installed, for what that reader
+    does not cover (LZ4 / ZSTD compression, split or jagged branches); `.npz`: a column archive."""
     path = str(path)
     if path.endswith(".npz") or path.endswith(".npy"):
         with np.load(path, allow_pickle=False) as f:
             cols = {k: np.asarray(f[k]) for k in keys if k in f.files}
             avail = list(f.files)
-    else:
+        return cols, avail
+    from . import rootio
+    try:
+        return rootio.read_tree(path, keys=list(keys))
+    except KeyError:
+        fatal(f"PhaseSpaceSourceGenerator: No usable branches in the root file {path}. Aborting.")
+    except ValueError as why:
         try:
             import uproot
         except ImportError:
-            fatal(f"PhaseSpaceSource: reading '{path}' needs the uproot package (as in the reference); "
-                  f"the .npz column archives written by PhaseSpaceActor can be read without it")
+            fatal(f"PhaseSpaceSource: cannot read '{path}': {why}; the uproot package would be needed for this file")
         f = uproot.open(path)
         branches = f.keys()
         if len(branches) == 0:
@@ -355,7 +361,7 @@ def read_phase_space_columns(path, keys):
         tree = f[branches[0]]
         avail = list(tree.keys())
         cols = tree.arrays([k for k in keys if k in avail], library="numpy")
-    return cols, avail
+        return cols, avail
 
 
 class PhaseSpaceSource(SourceBase):

@@ -227,8 +227,13 @@ def test_voxel_source_and_phase_space_plane(tmp_path):
     assert np.all(ph.data["PreDirection_Y"][on_face] > 0)
     assert ph.data["KineticEnergy"].max() == pytest.approx(0.140511, rel=1e-6)
     assert np.all(ph.data["KineticEnergy"] > 0.001) and np.all(ph.data["EventID"] < 6000)
-    # uproot is absent here: ROOT request falls back to npz with the same columns
-    assert os.path.exists(tmp_path / "out" / "plane.npz")
+    # the ROOT file: a flat TTree named after the actor with the same columns, same types (rootio.py)
+    from opengate_b200 import rootio
+    assert rootio.list_trees(tmp_path / "out" / "plane.root") == ["phsp"]
+    cols, avail = rootio.read_tree(tmp_path / "out" / "plane.root")
+    assert avail == list(ph.data)
+    for k, v in ph.data.items():
+        assert cols[k].dtype == v.dtype and np.array_equal(cols[k], v), k
     # emission positions: all inside the hot block of the activity image, in the CT frame (+ translation)
     d = dose.edep.image.array
     assert d.sum() > 0

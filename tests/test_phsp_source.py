@@ -107,7 +107,15 @@ def _plane_sim(tmp_path, backend_n=3000):
     return sim, box, dose
 
 
-def test_script_level_phase_space_actor_file_feeds_phase_space_source(tmp_path):
+def _load_columns(path):
+    if str(path).endswith(".root"):
+        from opengate_b200 import rootio
+        return rootio.read_tree(path)[0]
+    return np.load(path)
+
+
+@pytest.mark.parametrize("plane_file", ["plane.npz", "plane.root"])
+def test_script_level_phase_space_actor_file_feeds_phase_space_source(tmp_path, plane_file):
     """The wire format either side of the path: a PhaseSpaceActor file (local coordinates of its plane)
     replayed by a PhaseSpaceSource attached to the same plane reproduces the stored particles in the world."""
     from scipy.spatial.transform import Rotation
@@ -130,11 +138,11 @@ def test_script_level_phase_space_actor_file_feeds_phase_space_source(tmp_path):
     ph.attached_to = plane
     ph.attributes = ["KineticEnergy", "PrePosition", "PreDirection", "PrePositionLocal", "PreDirectionLocal",
                      "Weight", "PDGCode", "EventID"]
-    ph.output_filename = "plane.npz"
+    ph.output_filename = plane_file
     sim.run(_backend=OracleBackend)
     n_rows = ph.total_number_of_entries
     assert n_rows > 100
-    f = np.load(ph.get_output_path())
+    f = _load_columns(ph.get_output_path())
     # local <-> world relation of the stored columns
     R, t = plane.world_transform()
     loc = np.column_stack([f[f"PrePositionLocal_{a}"] for a in "XYZ"])

@@ -305,6 +305,9 @@ int gate_b200_create(int device_id, uint64_t seed, gate_b200_engine **out) {
   h->sm_count = sm_count;
   lap("device_attributes");
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  if (const char *g = getenv("GATE_B200_L2_FETCH")) {   // experiment: L2 fetch granularity (32 / 64 / 128 bytes) for the random gathers
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+  }
   h->own_stream = true;
   lap("stream_create");
   {

@@ -90,6 +90,15 @@ constexpr int kWoodcockK = 4;              // tentative collisions per Woodcock 
 #ifndef GB2_VWIDTH
 #define GB2_VWIDTH 1
 #endif
+#ifndef GB2_TLE_PREFETCH
+#define GB2_TLE_PREFETCH 1
+#endif
+#ifndef GB2_SPLIT_SHELL
+// Woodcock calls that START in the homogeneous shell of the image volume wait in a queue of their own (the cells of
+// Q_T, which the kernels without the track-length estimator do not use): the shell crossing at the head of such a
+// call (about 300 instructions) then runs with full warps, and the calls that start inside the box carry none of it
+#define GB2_SPLIT_SHELL 1
+#endif
 constexpr int kVWidth = GB2_VWIDTH;        // slots one lane carries through a Woodcock call
 constexpr int kMaxDose = 4;
 constexpr int kMaxPhsp = 4;
@@ -1374,7 +1383,9 @@ struct VCall {
   float fe, maj;
 };
 
-template <typename LabelT>
+// kShell: 0 = the call starts inside the inner box (no shell code at all), 1 = it starts in the shell,
+//         2 = decided at run time (kernels without the separate queue)
+template <typename LabelT, int kShell = 2>
 __device__ __forceinline__ void volume_gather_labels(const Params &P, Smem &S, const float *__restrict__ s_maj,
                                                      int slot, VCall &c) {
   c.blk = S.blk[slot];
@@ -1390,7 +1401,7 @@ __device__ __forceinline__ void volume_gather_labels(const Params &P, Smem &S, c
   float sh_mu = 0.0f, sh_tb = 0.0f, sh_lim = -1.0f;   // sh_lim < 0: not in the shell
   int sh_ax = -1;
   bool sh_hit = false;
-  if (P.shell) {
+  if (kShell != 0 && (kShell == 1 || P.shell)) {
     const float ps[3] = {a0, a1, a2}, dd[3] = {d0, d1, d2};
     if (!inside_tbox(P, ps)) {
       sh_mu = tab_mu(P, P.shell_mat, c.ie, c.fe);
@@ -1428,7 +1439,7 @@ __device__ __forceinline__ void volume_gather_labels(const Params &P, Smem &S, c
   }
   const LabelT *__restrict__ labels = reinterpret_cast<const LabelT *>(P.labels);
   float tau0 = -d_logf(u32_to_uniform(r[0]));   // optical depth to the first event of the call
-  if (sh_lim >= 0.0f) {
+  if (kShell != 0 && sh_lim >= 0.0f) {
     // The same optical depth first runs down at the attenuation of the shell material: either it is used up before
     // the box / the volume face -- a real interaction in the shell, no rejection needed --, or the photon reaches
     // the box with the remainder, or it leaves the volume.
@@ -1468,6 +1479,9 @@ __device__ __forceinline__ void volume_gather_labels(const Params &P, Smem &S, c
   }
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ void prefetch_l1(const void *p) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
@@ -1942,8 +1956,9 @@ __device__ __forceinline__ int phase_tle(const Params &P, Smem &S, int slot, int
         const float4 Cf = tl_ld(rec + kTleRecW * rr + 2);
         const unsigned cx = __float_as_uint(Cf.x), cy = __float_as_uint(Cf.y), cz = __float_as_uint(Cf.z);
         if ((int)(cx & 0xffffu) <= bhi[0] && (int)(cy >> 16) >= blo[0] && (int)(cx >> 16) <= bhi[1] && (int)(cz & 0xffffu) >= blo[1] &&
-            (int)(cy & 0xffffu) <= bhi[2] && (int)(cz >> 16) >= blo[2])
+            (int)(cy & 0xffffu) <= bhi[2] && (int)(cz >> 16) >= blo[2]) {
           cand |= 1ull << rr;
+        }
       }
     }
     for (int it = 0; it < kTleSteps; ++it) {
@@ -1961,6 +1976,20 @@ __device__ __forceinline__ int phase_tle(const Params &P, Smem &S, int slot, int
       const bool last = !(tn < t_end);
       const float tnext = last ? t_end : tn;
       const float L = tnext - tcur;
+#if GB2_TLE_PREFETCH
+      // the label of the NEXT voxel of the walk is asked into L2 before this voxel's label is waited for: the chain
+      // label -> mu_en -> score of a chord then overlaps the DRAM access of its successor
+      if (!last) {
+        const int sx = ax == 0 ? (d[0] > 0.0f ? 1 : -1) : 0, sy = ax == 1 ? (d[1] > 0.0f ? 1 : -1) : 0, sz = ax == 2 ? (d[2] > 0.0f ? 1 : -1) : 0;
+        const int jx = i[0] + sx, jy = i[1] + sy, jz = i[2] + sz;
+        if ((unsigned)jx < (unsigned)P.n[0] && (unsigned)jy < (unsigned)P.n[1] && (unsigned)jz < (unsigned)P.n[2])
+#if GB2_TLE_PREFETCH == 2
+          prefetch_l1(labels + ((unsigned)jx + (unsigned)P.n[0] * ((unsigned)jy + (unsigned)P.n[1] * (unsigned)jz)));
+#else
+          prefetch_l2(labels + ((unsigned)jx + (unsigned)P.n[0] * ((unsigned)jy + (unsigned)P.n[1] * (unsigned)jz)));
+#endif
+      }
+#endif
       if (L > 0.0f) {
         const unsigned flat = (unsigned)i[0] + (unsigned)P.n[0] * ((unsigned)i[1] + (unsigned)P.n[1] * (unsigned)i[2]);
         const int m = (int)__ldg(labels + flat);
@@ -2182,23 +2211,40 @@ __global__ void __launch_bounds__(threads_of<is_tle(kMode)>(), GB2_MIN_CTAS) tra
     __threadfence_block();
 
     // ---- run the phase for all claimed slots
+    constexpr bool kHasVS = GB2_SPLIT_SHELL && kMode == 2;       // measured: +1.3 ... 1.6 % for variant 2, -1 ... -2 % for 3 and 4   // Q_T serves as the queue of the shell-start calls
     if (q == Q_V) {
       VCall vc[kVWidth];
 #pragma unroll
       for (int w = 0; w < kVWidth; ++w)
-        if (slot[w] >= 0) volume_gather_labels<LabelT>(P, S, s_maj, slot[w], vc[w]);
+        if (slot[w] >= 0) volume_gather_labels<LabelT, kHasVS ? 0 : 2>(P, S, s_maj, slot[w], vc[w]);
 #pragma unroll
       for (int w = 0; w < kVWidth; ++w)
         if (slot[w] >= 0) volume_gather_mu(P, vc[w]);
 #pragma unroll
       for (int w = 0; w < kVWidth; ++w)
         if (slot[w] >= 0) next[w] = volume_decide<kMode>(P, S, slot[w], slot_base + slot[w], vc[w], c_tent);
+    } else if (kHasVS && q == Q_T) {
+      if (slot[0] >= 0) {
+        VCall vc;
+        volume_gather_labels<LabelT, 1>(P, S, s_maj, slot[0], vc);
+        volume_gather_mu(P, vc);
+        next[0] = volume_decide<kMode>(P, S, slot[0], slot_base + slot[0], vc, c_tent);
+      }
     } else if (slot[0] >= 0) {
       if (q == Q_C) next[0] = phase_compton<kMode>(P, S, slot[0], slot_base + slot[0], c_edep);
       else if (q == Q_E) next[0] = phase_end<kMode>(P, S, slot[0], slot_base + slot[0], c_edep);
       else if (q == Q_W) next[0] = phase_world<kMode>(P, S, slot[0], slot_base + slot[0]);
       else if (is_tle(kMode) && q == Q_T) next[0] = phase_tle<LabelT, kMode>(P, S, slot[0], slot_base + slot[0]);
       else next[0] = phase_rare<kMode>(P, S, slot[0], slot_base + slot[0], c_edep);
+    }
+    if (kHasVS && P.shell) {
+      // a photon whose next Woodcock call starts outside the inner box waits in the queue of the shell-start calls
+#pragma unroll
+      for (int w = 0; w < kVWidth; ++w)
+        if (next[w] == Q_V) {
+          const float ps[3] = {S.px[slot[w]], S.py[slot[w]], S.pz[slot[w]]};
+          if (!inside_tbox(P, ps)) next[w] = Q_T;
+        }
     }
     __syncwarp();
     __threadfence_block();   // slot state visible before the slot is published again

@@ -91,7 +91,7 @@ constexpr int kWoodcockK = 4;              // tentative collisions per Woodcock 
 #define GB2_VWIDTH 1
 #endif
 #ifndef GB2_TLE_PREFETCH
-#define GB2_TLE_PREFETCH 1
+#define GB2_TLE_PREFETCH 0                // 1 / 2: next-voxel label prefetch to L2 / L1; measured: no effect (the march is bound by the DRAM rate of random sectors)
 #endif
 #ifndef GB2_SPLIT_SHELL
 // Woodcock calls that START in the homogeneous shell of the image volume wait in a queue of their own (the cells of

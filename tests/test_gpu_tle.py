@@ -132,9 +132,11 @@ def test_tle_full_size_c3_properties(cuda_required):
     eng.close()
 
 
-def test_script_level_tle_actor_matches_oracle(cuda_required, tmp_path):
+@pytest.mark.parametrize("like_image", [False, True])
+def test_script_level_tle_actor_matches_oracle(cuda_required, tmp_path, like_image):
     """TLEDoseActor through the drop-in layer: the GATE-style script of the reference's test081 pattern
-    (DoseActor + TLEDoseActor on one voxelised volume) on the CUDA engine and on the oracle back end."""
+    (DoseActor + TLEDoseActor on one voxelised volume) on the CUDA engine and on the oracle back end; with a grid
+    coarser than the image (kernel variant 1: per-history tables) and with the image's own grid (variant 5: records)."""
     import os
     from test_host_api import ct_sim
     from oracle_backend import OracleBackend
@@ -144,8 +146,12 @@ def test_script_level_tle_actor_matches_oracle(cuda_required, tmp_path):
         sim, ct, src, dose, hu = ct_sim(tmp_path / sub, n_primaries=20000)
         tle = sim.add_actor("TLEDoseActor", "tle")
         tle.attached_to = "ct"
-        tle.size = [12, 10, 8]
-        tle.spacing = [20.0, 20.0, 24.0]          # coarser than the image: unaligned grid, hit_type random
+        if like_image:
+            tle.size = "like_image_volume"
+            tle.spacing = "like_image_volume"
+        else:
+            tle.size = [12, 10, 8]
+            tle.spacing = [20.0, 20.0, 24.0]      # coarser than the image: unaligned grid, hit_type random
         tle.dose.active = True
         tle.dose_uncertainty.active = True
         tle.edep_uncertainty.active = True

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, final measurements of the adopted kernels
+# round 2, final measurements of the adopted kernels (r2z: before the TLE record variant; r2y: with it)
 mkdir -p gpurun_out
 T=${1:-r2z}
 ( timeout 2400 python -m pytest tests -m gpu -q > gpurun_out/${T}_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/${T}_pytest.log )
@@ -11,7 +11,7 @@ timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/$
 for cfg in c2 c1 c4 c3_hit_random; do
   timeout 300 python bench.py --config $cfg --no-cpu-baseline > gpurun_out/${T}_bench_${cfg}.json 2> gpurun_out/${T}_bench_${cfg}.err; cut -c1-160 gpurun_out/${T}_bench_${cfg}.json
 done
-timeout 300 python bench.py --config c3tle --histories 4000000 --no-cpu-baseline > gpurun_out/${T}_bench_c3tle.json 2> gpurun_out/${T}_bench_c3tle.err; cut -c1-160 gpurun_out/${T}_bench_c3tle.json
+timeout 300 python bench.py --config c3tle --histories 8000000 --no-cpu-baseline > gpurun_out/${T}_bench_c3tle.json 2> gpurun_out/${T}_bench_c3tle.err; cut -c1-160 gpurun_out/${T}_bench_c3tle.json
 timeout 300 python bench.py --config c3tle_nosq --histories 8000000 --no-cpu-baseline > gpurun_out/${T}_bench_c3tle_nosq.json 2> gpurun_out/${T}_bench_c3tle_nosq.err; cut -c1-160 gpurun_out/${T}_bench_c3tle_nosq.json
 timeout 300 python bench.py --config c2 --steps 4 --total-histories 1e10 --no-cpu-baseline --no-script-level > gpurun_out/${T}_bench_c5_c2_1gpu.json 2> gpurun_out/${T}_bench_c5_c2_1gpu.err; cut -c1-160 gpurun_out/${T}_bench_c5_c2_1gpu.json
 timeout 300 python bench.py --config c5ct --steps 4 --total-histories 1e10 --no-cpu-baseline --no-script-level > gpurun_out/${T}_bench_c5_ct_1gpu.json 2> gpurun_out/${T}_bench_c5_ct_1gpu.err; cut -c1-160 gpurun_out/${T}_bench_c5_ct_1gpu.json
@@ -23,6 +23,6 @@ for cfg in c3 c3_hit_random c4; do
   tail -1 gpurun_out/${T}_ncu_${cfg}.log
 done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:transport_kernel -s 1 -c 1 \
-    -o gpurun_out/${T}_transport_c3tle -f python tools/profile_run.py --config c3tle --histories 2000000 --launches 1 --warmup 1 > gpurun_out/${T}_ncu_c3tle.log 2>&1
+    -o gpurun_out/${T}_transport_c3tle -f python tools/profile_run.py --config c3tle --histories 4000000 --launches 1 --warmup 1 > gpurun_out/${T}_ncu_c3tle.log 2>&1
 tail -1 gpurun_out/${T}_ncu_c3tle.log
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/${T}_smi.txt; nproc >> gpurun_out/${T}_smi.txt

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GATE_B200_ABI_VERSION 4
+#define GATE_B200_ABI_VERSION 5
 
 enum {
   GATE_B200_OK = 0,
@@ -71,7 +71,7 @@ enum { GATE_B200_POS_POINT = 0, GATE_B200_POS_BOX = 1, GATE_B200_POS_SPHERE = 2,
        GATE_B200_POS_DISC = 3, GATE_B200_POS_CYLINDER = 4, GATE_B200_POS_VOXELS = 5,
        GATE_B200_POS_PHSP = 6, GATE_B200_POS_SURFACE_SPHERE = 7 };
 enum { GATE_B200_DIR_ISO = 0, GATE_B200_DIR_MOMENTUM = 1, GATE_B200_DIR_FOCUSED = 2,
-       GATE_B200_DIR_PHSP = 3, GATE_B200_DIR_COS = 4, GATE_B200_DIR_BEAM2D = 5 };
+       GATE_B200_DIR_PHSP = 3, GATE_B200_DIR_COS = 4, GATE_B200_DIR_BEAM2D = 5, GATE_B200_DIR_HISTOGRAM = 6 };
 enum { GATE_B200_ENE_MONO = 0, GATE_B200_ENE_GAUSS = 1, GATE_B200_ENE_RANGE = 2,
        GATE_B200_ENE_SPECTRUM_DISCRETE = 3, GATE_B200_ENE_SPECTRUM_HISTOGRAM = 4,
        GATE_B200_ENE_SPECTRUM_HISTOGRAM_LINEAR = 5, GATE_B200_ENE_CDF = 6, GATE_B200_ENE_PHSP = 7 };
@@ -122,6 +122,19 @@ typedef struct {
    * pos_type SURFACE_SPHERE (points on the sphere of `radius`), are Geant4 G4SPS* algorithms that are
    * not in the reference tree: restated from the published sources. */
   double dir_sigma[2];
+  /* dir_type HISTOGRAM (ABI 5; GateGenericSource.cpp:435-464 -> G4SPSAngDistribution "user", both angles): theta and
+   * phi from user histograms -- bin i between edges[i] and edges[i+1] (rad) holds the probability cdf[i+1] - cdf[i]
+   * (cdf[0] = 0, cdf[n] = 1: the weights are bin contents), the angle is uniform inside its bin (inverse of the
+   * piecewise-linear cumulative, G4PhysicsFreeVector::GetEnergy); momentum = -(sin t cos p, sin t sin p, cos t). */
+  int32_t n_dir_theta, n_dir_phi;                  /* bins */
+  const double *dir_theta_edges, *dir_theta_cdf;   /* [n_dir_theta + 1] */
+  const double *dir_phi_edges, *dir_phi_cdf;       /* [n_dir_phi + 1] */
+  /* position.confine (ABI 5; GateGenericSource.cpp:376-383,223-227 -> G4SPSPosDistribution::ConfineSourceToVolume):
+   * the position is drawn again until it lies inside the box below (a Box volume of the caller's geometry), at most
+   * 100000 times as in Geant4 */
+  int32_t confine;
+  double confine_half_size[3];
+  double world_to_confine[12];
 } gate_b200_source;
 
 /* ---- dose actor -------------------------------------------------------------------------

@@ -10,11 +10,11 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # enums --------------------------------------------------------------------------------
 POS_POINT, POS_BOX, POS_SPHERE, POS_DISC, POS_CYLINDER, POS_VOXELS, POS_PHSP, POS_SURFACE_SPHERE = range(8)
-DIR_ISO, DIR_MOMENTUM, DIR_FOCUSED, DIR_PHSP, DIR_COS, DIR_BEAM2D = range(6)
+DIR_ISO, DIR_MOMENTUM, DIR_FOCUSED, DIR_PHSP, DIR_COS, DIR_BEAM2D, DIR_HISTOGRAM = range(7)
 (ENE_MONO, ENE_GAUSS, ENE_RANGE, ENE_SPECTRUM_DISCRETE, ENE_SPECTRUM_HISTOGRAM,
  ENE_SPECTRUM_HISTOGRAM_LINEAR, ENE_CDF, ENE_PHSP) = range(8)
 HIT_RANDOM, HIT_PRE, HIT_POST, HIT_MIDDLE = range(4)
@@ -58,6 +58,9 @@ class Source(C.Structure):
         ("phsp_dir_x", _fp), ("phsp_dir_y", _fp), ("phsp_dir_z", _fp),
         ("phsp_energy", _fp), ("phsp_weight", _fp),
         ("dir_sigma", C.c_double * 2),
+        ("n_dir_theta", C.c_int32), ("n_dir_phi", C.c_int32),
+        ("dir_theta_edges", _dp), ("dir_theta_cdf", _dp), ("dir_phi_edges", _dp), ("dir_phi_cdf", _dp),
+        ("confine", C.c_int32), ("confine_half_size", C.c_double * 3), ("world_to_confine", C.c_double * 12),
     ]
 
 
@@ -139,9 +142,12 @@ def make_source(pos_type=POS_POINT, half_size=(0, 0, 0), radius=0.0, sigma_x=0.0
                 ene_type=ENE_MONO, mono=0.0, sigma=0.0, e_min=0.0, e_max=0.0,
                 spectrum_energy=None, spectrum_cdf=None, weight=1.0,
                 vox_size=(0, 0, 0), vox_spacing=(1, 1, 1), vox_origin=(0, 0, 0),
-                cdf_z=None, cdf_y=None, cdf_x=None, phsp=None, phsp_entry_start=0, dir_sigma=(0.0, 0.0)):
+                cdf_z=None, cdf_y=None, cdf_x=None, phsp=None, phsp_entry_start=0, dir_sigma=(0.0, 0.0),
+                theta_hist=None, phi_hist=None, confine_half_size=None, world_to_confine=None):
     """Fill a gate_b200_source; returns (struct, keepalive list).
-    phsp: dict of float32 arrays pos_x/y/z, energy and optionally dir_x/y/z, weight (phase-space replay)."""
+    phsp: dict of float32 arrays pos_x/y/z, energy and optionally dir_x/y/z, weight (phase-space replay).
+    theta_hist / phi_hist (dir_type HISTOGRAM): (edges [n+1] rad, weights [n]) of the user angular histograms.
+    confine_half_size / world_to_confine (3x4): box the position is confined to."""
     s = Source()
     keep = []
     s.pos_type = pos_type
@@ -180,6 +186,23 @@ def make_source(pos_type=POS_POINT, half_size=(0, 0, 0), radius=0.0, sigma_x=0.0
         cx = np.ascontiguousarray(cdf_x, dtype=np.float32)
         keep += [cz, cy, cx]
         s.cdf_z, s.cdf_y, s.cdf_x = fptr(cz), fptr(cy), fptr(cx)
+    for name, hist in (("theta", theta_hist), ("phi", phi_hist)):
+        if hist is None:
+            continue
+        edges = np.ascontiguousarray(hist[0], dtype=np.float64)
+        w = np.asarray(hist[1], dtype=np.float64)
+        if len(edges) != len(w) + 1 or len(w) < 1 or np.any(w < 0) or w.sum() <= 0 or np.any(np.diff(edges) < 0):
+            raise ValueError(f"{name} histogram: n weights >= 0 (not all zero) and n + 1 non-decreasing angles are needed")
+        cdf = np.ascontiguousarray(np.concatenate([[0.0], np.cumsum(w) / w.sum()]))
+        cdf[-1] = 1.0
+        keep += [edges, cdf]
+        setattr(s, f"n_dir_{name}", len(w))
+        setattr(s, f"dir_{name}_edges", dptr(edges))
+        setattr(s, f"dir_{name}_cdf", dptr(cdf))
+    if confine_half_size is not None:
+        s.confine = 1
+        s.confine_half_size = (C.c_double * 3)(*[float(x) for x in confine_half_size])
+        s.world_to_confine = (C.c_double * 12)(*np.asarray(world_to_confine, float).reshape(-1))
     if phsp is not None:
         cols = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in phsp.items() if v is not None}
         n = len(cols["pos_x"])

@@ -613,7 +613,7 @@ int gate_b200_add_source(gate_b200_engine *h, const gate_b200_source *s, int32_t
   d.pos_type = s->pos_type; d.dir_type = s->dir_type; d.ene_type = s->ene_type;
   d.dir_relative = s->dir_relative;
   if (d.pos_type < 0 || d.pos_type > GATE_B200_POS_SURFACE_SPHERE) return fail(h, GATE_B200_EINVAL, "bad pos_type %d", d.pos_type);
-  if (d.dir_type < 0 || d.dir_type > GATE_B200_DIR_BEAM2D) return fail(h, GATE_B200_EINVAL, "bad dir_type %d", d.dir_type);
+  if (d.dir_type < 0 || d.dir_type > GATE_B200_DIR_HISTOGRAM) return fail(h, GATE_B200_EINVAL, "bad dir_type %d", d.dir_type);
   if (d.ene_type < 0 || d.ene_type > GATE_B200_ENE_PHSP) return fail(h, GATE_B200_EINVAL, "bad ene_type %d", d.ene_type);
   const bool phsp = d.pos_type == GATE_B200_POS_PHSP;
   if (phsp != (d.ene_type == GATE_B200_ENE_PHSP) || (!phsp && d.dir_type == GATE_B200_DIR_PHSP) ||
@@ -662,6 +662,28 @@ int gate_b200_add_source(gate_b200_engine *h, const gate_b200_source *s, int32_t
     if (int rc = dev_upload(h, &d.cdf_z, s->cdf_z, nz)) return rc;
     if (int rc = dev_upload(h, &d.cdf_y, s->cdf_y, nz * ny)) return rc;
     if (int rc = dev_upload(h, &d.cdf_x, s->cdf_x, nz * ny * nx)) return rc;
+  }
+  if (d.dir_type == GATE_B200_DIR_HISTOGRAM) {
+    if (s->n_dir_theta < 1 || s->n_dir_phi < 1 || !s->dir_theta_edges || !s->dir_theta_cdf || !s->dir_phi_edges || !s->dir_phi_cdf)
+      return fail(h, GATE_B200_EINVAL, "direction histogram: theta and phi edges + cdf are required");
+    const double *src4[4] = {s->dir_theta_edges, s->dir_theta_cdf, s->dir_phi_edges, s->dir_phi_cdf};
+    const float **dst4[4] = {&d.ht_e, &d.ht_c, &d.hp_e, &d.hp_c};
+    for (int k = 0; k < 4; ++k) {
+      const int n = (k < 2 ? s->n_dir_theta : s->n_dir_phi) + 1;
+      std::vector<float> v(n);
+      for (int i = 0; i < n; ++i) v[i] = (float)src4[k][i];
+      if (int rc = dev_upload(h, dst4[k], v.data(), v.size())) return rc;
+    }
+    d.n_ht = s->n_dir_theta; d.n_hp = s->n_dir_phi;
+  }
+  if (s->confine) {
+    if (phsp) return fail(h, GATE_B200_EINVAL, "a phase-space source cannot be confined");
+    d.confine = 1;
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) d.conf.m[3 * r + c] = (float)s->world_to_confine[4 * r + c];
+      d.conf.t[r] = (float)s->world_to_confine[4 * r + 3];
+      d.conf_half[r] = (float)s->confine_half_size[r];
+    }
   }
   if (phsp) {
     const uint64_t n = s->phsp_n_entries;

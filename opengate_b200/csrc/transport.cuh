@@ -138,6 +138,13 @@ struct DSource {
   // phase-space replay: entry e = (ph_start + history id) % ph_n, ph_a[e] = {x, y, z, E}, ph_b[e] = {dx, dy, dz, w}
   const float4 *ph_a, *ph_b;
   unsigned long long ph_n, ph_start;
+  // user angular histograms (dir_type HISTOGRAM): edges and cumulative probabilities, [n + 1] each
+  int n_ht, n_hp;
+  const float *ht_e, *ht_c, *hp_e, *hp_c;
+  // position.confine: the position is drawn again until it lies in this box (world -> box frame, half sizes)
+  int confine;
+  Affine conf;
+  float conf_half[3];
 };
 
 struct DDose {
@@ -1021,6 +1028,10 @@ __device__ __forceinline__ void generate_primary(const Params &P, Ph &g, int gsl
   rng_begin(r);
   float l[3] = {0.0f, 0.0f, 0.0f};
   float4 ea = make_float4(0.0f, 0.0f, 0.0f, 0.0f), eb = ea;
+  // position.confine (G4SPSPosDistribution::GenerateOne with ConfineSourceToVolume): draw again until the point
+  // lies in the confining box, at most 100000 times
+  for (int tries = 0;; ++tries) {
+  l[0] = 0.0f; l[1] = 0.0f; l[2] = 0.0f;
   switch (S.pos_type) {
   case GATE_B200_POS_PHSP: {
     // GatePhaseSpaceSource::GenerateOnePrimary (GatePhaseSpaceSource.cpp:137-166): sequential entries,
@@ -1089,6 +1100,11 @@ __device__ __forceinline__ void generate_primary(const Params &P, Ph &g, int gsl
   } break;
   }
   aff_apply(S.pos, l, g.p);
+  if (!S.confine || tries >= 99999) break;
+  float qc[3];
+  aff_apply(S.conf, g.p, qc);
+  if (inside_box(qc, S.conf_half)) break;
+  }
 
   switch (S.dir_type) {
   case GATE_B200_DIR_ISO: {
@@ -1142,6 +1158,32 @@ __device__ __forceinline__ void generate_primary(const Params &P, Ph &g, int gsl
       const float k = st / th;
       v[0] = -(k * px); v[1] = -(k * py); v[2] = -ct;
     }
+    if (S.dir_relative) rot_apply(S.dir_rot, v, g.d);
+    else { g.d[0] = v[0]; g.d[1] = v[1]; g.d[2] = v[2]; }
+  } break;
+  case GATE_B200_DIR_HISTOGRAM: {
+    // G4SPSAngDistribution::GenerateUserDefFlux, theta and phi from user histograms: the angle is the inverse of the
+    // piecewise-linear cumulative at a uniform variate (uniform inside its bin), momentum = -(sin t cos p, sin t sin p, cos t)
+    float ang[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float *ce = k == 0 ? S.ht_e : S.hp_e;
+      const float *cc = k == 0 ? S.ht_c : S.hp_c;
+      const int nb = k == 0 ? S.n_ht : S.n_hp;
+      const float u = rng_uniform(r);
+      const int b = cdf_index(cc + 1, nb - 1, u);
+      const float c0 = __ldg(cc + b), c1 = __ldg(cc + b + 1), e0 = __ldg(ce + b), e1 = __ldg(ce + b + 1);
+      const float den = c1 - c0;
+      float f = den > 0.0f ? (u - c0) / den : 0.0f;
+      if (f > 1.0f) f = 1.0f;
+      ang[k] = e0 + f * (e1 - e0);
+    }
+    float tt = ang[0] * 0.15915494309189535f, tp = ang[1] * 0.15915494309189535f;
+    tt = tt - floorf(tt); tp = tp - floorf(tp);
+    float st, ct, sp, cp;
+    d_sincos2pi(tt, st, ct);
+    d_sincos2pi(tp, sp, cp);
+    float v[3] = {-st * cp, -st * sp, -ct};
     if (S.dir_relative) rot_apply(S.dir_rot, v, g.d);
     else { g.d[0] = v[0]; g.d[1] = v[1]; g.d[2] = v[2]; }
   } break;

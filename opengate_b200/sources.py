@@ -140,11 +140,30 @@ class GenericSource(SourceBase):
             fatal(f"In {ctx}: size and translation must be 3-vectors")
         if np.asarray(p.rotation).shape != (3, 3):
             fatal(f"In {ctx}: 'rotation' must be convertible to a 3x3 matrix/array, but got: {p.rotation}")
-        if p.confine:
-            fatal(f"In {ctx}: position.confine is not supported by the B200 GPU engine")
-        if d.type not in {"iso", "momentum", "focused", "beam2d", "cos"}:
-            fatal(f"In {ctx}: direction.type '{d.type}' is not supported by the B200 GPU engine "
-                  f"(supported: iso, momentum, focused, beam2d, cos)")
+        if p.confine and p.confine != "None":
+            # generic.py:500-508: a confined point source is almost certainly a mistake
+            if p.type == "point":
+                warning(f"In source {self.name}, confine is used, while position.type is point ... really ?")
+            vols = self.simulation.volume_manager.volumes
+            if p.confine not in vols:
+                fatal(f"In {ctx}: position.confine = '{p.confine}' is not a volume of the simulation")
+            if not hasattr(vols[p.confine], "half_size_mm"):
+                fatal(f"In {ctx}: position.confine needs a Box or Image volume on the B200 GPU engine, "
+                      f"'{p.confine}' is a {vols[p.confine].volume_type}")
+        valid_dir = ["iso", "histogram", "momentum", "focused", "beam2d", "cos"]   # generic.py:160
+        if d.type not in valid_dir:
+            fatal(f"In {ctx}: Cannot find the direction type '{d.type}'. Available types are {valid_dir}")
+        if d.type == "histogram":
+            # generic.py:194-205 / GateGenericSource.cpp:440-458: n weights for n + 1 angles, both histograms
+            for nm in ("theta", "phi"):
+                w, a = getattr(d, f"histogram_{nm}_weights"), getattr(d, f"histogram_{nm}_angles")
+                if len(w) != len(a) - 1 or len(w) < 1:
+                    fatal(f"In {ctx}: histogram_{nm}_weights must have -1 elements than histogram_{nm}_angles")
+                lim = np.pi if nm == "theta" else 2 * np.pi
+                if np.any(np.diff(np.asarray(a, float)) < 0) or np.min(a) < 0 or np.max(a) > lim * (1 + 1e-12):
+                    fatal(f"In {ctx}: histogram_{nm}_angles must increase within [0, {'pi' if nm == 'theta' else '2 pi'}]")
+                if np.any(np.asarray(w, float) < 0) or not np.sum(w) > 0:
+                    fatal(f"In {ctx}: histogram_{nm}_weights must be >= 0 and not all zero")
         if d.angular_acceptance.get("policy") not in (None, "None"):
             fatal(f"In {ctx}: direction.angular_acceptance is not supported by the B200 GPU engine")
         et = "CDF" if e.is_cdf else e.type
@@ -245,6 +264,11 @@ class GenericSource(SourceBase):
             # two Gaussian angular deviations around -z of the source frame (GateGenericSource.cpp:428-433)
             kw.update(dir_type=abi.DIR_BEAM2D, dir_sigma=[float(x) for x in d.sigma], dir_relative=relative,
                       dir_rotation=R_pos)
+        elif d.type == "histogram":
+            # user histograms of theta and phi (GateGenericSource.cpp:435-464): weights are bin contents
+            kw.update(dir_type=abi.DIR_HISTOGRAM, dir_relative=relative, dir_rotation=R_pos,
+                      theta_hist=(np.asarray(d.histogram_theta_angles, float), np.asarray(d.histogram_theta_weights, float)),
+                      phi_hist=(np.asarray(d.histogram_phi_angles, float), np.asarray(d.histogram_phi_weights, float)))
         elif d.type == "momentum":
             m = np.asarray(d.momentum, dtype=np.float64)
             if relative:
@@ -274,6 +298,15 @@ class GenericSource(SourceBase):
             kw.update(ene_type=abi.ENE_SPECTRUM_HISTOGRAM_LINEAR if linear else abi.ENE_SPECTRUM_HISTOGRAM,
                       spectrum_energy=np.asarray(e.spectrum_energy_bin_edges, float), spectrum_cdf=cdf)
         kw["weight"] = 1.0 if self.weight is None or self.weight < 0 else float(self.weight)
+        if p.confine and p.confine != "None":
+            # the confining volume as a box in the world (GateGenericSource.cpp:223-227: ConfineSourceToVolume)
+            cv = self.simulation.volume_manager.volumes[p.confine]
+            Rc, tc = cv.world_transform()
+            w2c = np.zeros((3, 4))
+            w2c[:, :3] = Rc.T
+            w2c[:, 3] = -Rc.T @ tc
+            hs = cv.half_size_mm() if callable(cv.half_size_mm) else cv.half_size_mm
+            kw.update(confine_half_size=[float(x) for x in hs], world_to_confine=w2c)
         return abi.make_source(**kw)
 
 

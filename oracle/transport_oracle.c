@@ -222,6 +222,9 @@ typedef struct {
   real_t sin2_tmin, sin2_tmax, dir_sx, dir_sy;
   real_t mom[3], focus[3];
   float *spec_e, *spec_cdf;   /* as handed to the device */
+  float *ht_e, *ht_c, *hp_e, *hp_c;   /* user angular histograms: edges and cumulative probabilities */
+  affine_t conf;              /* world -> confining box */
+  real_t conf_half[3];
 } osource_t;
 
 typedef struct {
@@ -873,6 +876,10 @@ static void generate_primary(hist_t *h, const osource_t *s) {
   const gate_b200_source *d = &s->d;
   real_t l[3] = {0.0f, 0.0f, 0.0f};
   real_t ed[3] = {0.0f, 0.0f, 1.0f}, eE = 0.0f, ew = 1.0f;   /* phase-space entry */
+  /* position.confine (GateGenericSource.cpp:223-227 -> G4SPSPosDistribution::GenerateOne with a confining volume):
+   * draw again until the point lies in the confining box, at most 100000 times */
+  for (int tries = 0;; ++tries) {
+  l[0] = 0.0f; l[1] = 0.0f; l[2] = 0.0f;
   switch (d->pos_type) {
   case GATE_B200_POS_PHSP: {
     /* GatePhaseSpaceSource::GenerateOnePrimary (GatePhaseSpaceSource.cpp:137-166); entries are read
@@ -941,6 +948,11 @@ static void generate_primary(hist_t *h, const osource_t *s) {
   } break;
   }
   aff_apply(&s->pos, l, h->p);
+  if (!d->confine || tries >= 99999) break;
+  real_t qc[3];
+  aff_apply(&s->conf, h->p, qc);
+  if (inside_box(qc, s->conf_half)) break;
+  }
 
   switch (d->dir_type) {
   case GATE_B200_DIR_ISO: {
@@ -993,6 +1005,33 @@ static void generate_primary(hist_t *h, const osource_t *s) {
       real_t k = st / th;
       v[0] = -(k * px); v[1] = -(k * py); v[2] = -ct;
     }
+    if (d->dir_relative) rot_apply(s->dir_rot, v, h->d);
+    else { h->d[0] = v[0]; h->d[1] = v[1]; h->d[2] = v[2]; }
+  } break;
+  case GATE_B200_DIR_HISTOGRAM: {
+    /* GateGenericSource.cpp:435-464 -> G4SPSAngDistribution::GenerateUserDefFlux with theta and phi histograms: the
+     * angle is the inverse of the piecewise-linear cumulative at a uniform variate (G4PhysicsFreeVector::GetEnergy),
+     * momentum = -(sin t cos p, sin t sin p, cos t) */
+    real_t ang[2];
+    for (int k = 0; k < 2; ++k) {
+      const float *ce = k == 0 ? s->ht_e : s->hp_e;
+      const float *cc = k == 0 ? s->ht_c : s->hp_c;
+      const int nb = k == 0 ? d->n_dir_theta : d->n_dir_phi;
+      const real_t u = rng_uniform(r);
+      int b = 0;
+      while (b < nb - 1 && u >= cc[b + 1]) ++b;   /* first bin whose upper cumulative exceeds u */
+      const real_t c0 = cc[b], c1 = cc[b + 1], e0 = ce[b], e1 = ce[b + 1];
+      const real_t den = c1 - c0;
+      real_t f = den > 0.0f ? (u - c0) / den : 0.0f;
+      if (f > 1.0f) f = 1.0f;
+      ang[k] = e0 + f * (e1 - e0);
+    }
+    real_t tt = ang[0] * 0.15915494309189535f, tp = ang[1] * 0.15915494309189535f;
+    tt = tt - R_FLOOR(tt); tp = tp - R_FLOOR(tp);
+    real_t st, ct, sp, cp;
+    R_SINCOS2PI(tt, &st, &ct);
+    R_SINCOS2PI(tp, &sp, &cp);
+    real_t v[3] = {-st * cp, -st * sp, -ct};
     if (d->dir_relative) rot_apply(s->dir_rot, v, h->d);
     else { h->d[0] = v[0]; h->d[1] = v[1]; h->d[2] = v[2]; }
   } break;
@@ -1612,6 +1651,19 @@ int oracle_add_source(oracle_engine *g, const gate_b200_source *s) {
     o->spec_cdf = (float *)malloc(sizeof(float) * s->n_spectrum);
     for (int i = 0; i < ne; ++i) o->spec_e[i] = (real_t)s->spectrum_energy[i];
     for (int i = 0; i < s->n_spectrum; ++i) o->spec_cdf[i] = (real_t)s->spectrum_cdf[i];
+  }
+  if (s->dir_type == GATE_B200_DIR_HISTOGRAM) {
+    const double *src4[4] = {s->dir_theta_edges, s->dir_theta_cdf, s->dir_phi_edges, s->dir_phi_cdf};
+    float **dst4[4] = {&o->ht_e, &o->ht_c, &o->hp_e, &o->hp_c};
+    for (int k = 0; k < 4; ++k) {
+      const int n = (k < 2 ? s->n_dir_theta : s->n_dir_phi) + 1;
+      *dst4[k] = (float *)malloc(sizeof(float) * n);
+      for (int i = 0; i < n; ++i) (*dst4[k])[i] = (float)src4[k][i];
+    }
+  }
+  if (s->confine) {
+    aff_from_d(&o->conf, s->world_to_confine);
+    for (int a = 0; a < 3; ++a) o->conf_half[a] = (real_t)s->confine_half_size[a];
   }
   return g->nsrc++;
 }

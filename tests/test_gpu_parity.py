@@ -421,6 +421,14 @@ def test_energy_source_types_and_positions(cuda_required):
              dir_rotation=np.array([[1.0, 0.0, 0.0], [0.0, -1.0, 0.0], [0.0, 0.0, -1.0]])),
         dict(pos_type=abi.POS_POINT, ene_type=abi.ENE_MONO, mono=0.3, dir_type=abi.DIR_BEAM2D, dir_sigma=(0.05, 0.2),
              dir_relative=True, dir_rotation=np.array([[1.0, 0.0, 0.0], [0.0, -1.0, 0.0], [0.0, 0.0, -1.0]])),
+        # user angular histograms (a zero-weight bin in theta), pointing at the phantom: -z of the flux frame turned to +z
+        dict(pos_type=abi.POS_POINT, ene_type=abi.ENE_MONO, mono=0.2, dir_type=abi.DIR_HISTOGRAM,
+             theta_hist=([0.0, 0.1, 0.2, 0.5], [1.0, 0.0, 2.0]), phi_hist=([0.5, 1.0, 3.0, 6.0], [0.3, 1.0, 0.2]),
+             dir_relative=True, dir_rotation=np.array([[1.0, 0.0, 0.0], [0.0, -1.0, 0.0], [0.0, 0.0, -1.0]])),
+        # a box source confined to a rotated box that it only partly overlaps (rejection loop in the position sampler)
+        dict(pos_type=abi.POS_BOX, half_size=(30, 30, 10), ene_type=abi.ENE_MONO, mono=0.25, dir_type=abi.DIR_MOMENTUM,
+             momentum=(0.0, 0.1, 1.0), confine_half_size=(12.0, 6.0, 40.0),
+             world_to_confine=np.array([[0.8, 0.6, 0.0, -10.0], [-0.6, 0.8, 0.0, 4.0], [0.0, 0.0, 1.0, 195.0]])),
     ]
     rot = np.array([[0.0, 0.0, -1.0], [0.0, 1.0, 0.0], [1.0, 0.0, 0.0]])
     dirs = [dict(dir_type=abi.DIR_ISO), dict(dir_type=abi.DIR_MOMENTUM, momentum=(0.1, 0.2, 1.0)),

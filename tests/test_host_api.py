@@ -273,8 +273,11 @@ def test_unsupported_configurations_are_fatal(tmp_path):
     with pytest.raises(Exception, match="score_in"):
         sim.run(_backend=OracleBackend)
     dose.score_in = "material"
-    src.direction.type = "histogram"
-    with pytest.raises(Exception, match="direction.type"):
+    src.direction.type = "histogram"            # supported, but needs its histograms (generic.py:194-205)
+    with pytest.raises(Exception, match="histogram_theta_weights"):
+        sim.run(_backend=OracleBackend)
+    src.direction.type = "sideways"
+    with pytest.raises(Exception, match="direction type"):
         sim.run(_backend=OracleBackend)
 
 
@@ -502,3 +505,56 @@ def test_event_time_stamps_follow_the_source_timing(tmp_path):
     sim2.run(_backend=OracleBackend)
     assert len(ph2.data["GlobalTime"]) > 100
     np.testing.assert_allclose(ph2.data["GlobalTime"] - ph2.data["TimeFromBeginOfEvent"], 5 * s_, rtol=0, atol=1e-3)
+
+
+def test_angular_histogram_and_confine_like_the_reference_tests(tmp_path):
+    """direction.type = 'histogram' (reference test010_generic_source_angular_distribution.py: theta 80..100 deg,
+    five phi bins) and position.confine (test010_generic_source_confine.py, here to a Box) through the script API,
+    primaries traced on the oracle."""
+    from oracle.oracle import TransportOracle
+    deg = gate.g4_units.deg
+    sim, ct, src, dose, hu = ct_sim(tmp_path)
+    src.position.type = "point"
+    src.direction.type = "histogram"
+    src.direction.histogram_theta_angles = [80 * deg, 100 * deg]
+    src.direction.histogram_theta_weights = [1]
+    src.direction.histogram_phi_angles = [60 * deg, 70 * deg, 80 * deg, 100 * deg, 110 * deg, 120 * deg]
+    src.direction.histogram_phi_weights = [0.3, 0.5, 1, 0.5, 0.3]
+    stuff = sim.add_volume("Box", "stuff")
+    stuff.size = [20 * mm, 10 * mm, 40 * mm]
+    stuff.translation = [-50 * mm, 5 * mm, -300 * mm]
+    stuff.material = "G4_AIR"
+    src2 = sim.add_source("GenericSource", "confined")
+    src2.particle = "gamma"
+    src2.energy.mono = 0.1 * gate.g4_units.MeV
+    src2.position.type = "box"
+    src2.position.size = [100 * mm, 100 * mm, 100 * mm]
+    src2.position.translation = [-50 * mm, 0, -300 * mm]
+    src2.position.confine = "stuff"
+    src2.direction.type = "momentum"
+    src2.direction.momentum = [0, 0, 1]
+    src2.number_of_primaries = 100
+    for s in (src, src2):
+        s.resolve_and_validate_config(sim.run_timing_intervals)
+    from small_setups import c1
+    S = c1(10)
+    S.sources = [src.to_abi(None), src2.to_abi(None)]
+    orc = TransportOracle(3)
+    so, _, _ = S.apply(orc)
+    d = np.array([orc.trace(so[0], h).d0[:] for h in range(20000)])
+    theta, phi = np.arccos(-d[:, 2]), np.arctan2(-d[:, 1], -d[:, 0]) % (2 * np.pi)
+    assert theta.min() >= 80 * deg - 1e-5 and theta.max() <= 100 * deg + 1e-5
+    assert np.allclose(np.histogram(theta, bins=4, range=(80 * deg, 100 * deg))[0] / len(theta), 0.25, atol=0.012)
+    h = np.histogram(phi, bins=np.array([60, 70, 80, 100, 110, 120]) * deg)[0] / len(phi)
+    assert np.allclose(h, np.array([0.3, 0.5, 1, 0.5, 0.3]) / 2.6, atol=0.012)
+    p = np.array([orc.trace(so[1], h).p0[:] for h in range(5000)])
+    q = p - np.array([-50.0, 5.0, -300.0])
+    assert np.all(np.abs(q) <= np.array([10.0, 5.0, 20.0]) + 1e-4)
+    assert np.allclose(q.std(axis=0), np.array([10.0, 5.0, 20.0]) / np.sqrt(3), rtol=0.05)
+    # validation as the reference: n weights for n + 1 angles; a confine volume that does not exist
+    src.direction.histogram_phi_weights = [1, 2]
+    with pytest.raises(Exception, match="histogram_phi_weights"):
+        src.resolve_and_validate_config(sim.run_timing_intervals)
+    src2.position.confine = "nowhere"
+    with pytest.raises(Exception, match="confine"):
+        src2.resolve_and_validate_config(sim.run_timing_intervals)

@@ -188,6 +188,12 @@ typedef struct {
   uint64_t capacity;              /* rows reserved on the device                          */
 } gate_b200_phsp_desc;
 
+typedef struct {
+  double half_size[3];
+  double world_to_box[12];        /* row-major 3x4: p_box = A*p_world + b                 */
+  int32_t material;               /* index into the tables                                 */
+} gate_b200_region_desc;
+
 /* One stored row (structure of arrays on the device, gathered by gate_b200_get_phsp). */
 typedef struct {
   float *kinetic_energy;          /* [n] MeV                                              */
@@ -261,6 +267,13 @@ int gate_b200_add_dose_actor(gate_b200_engine *h, const gate_b200_dose_desc *d, 
 int gate_b200_add_tle_dose_actor(gate_b200_engine *h, const gate_b200_dose_desc *d,
                                  const gate_b200_tle_desc *t, int32_t *actor_id);
 int gate_b200_add_phsp_actor(gate_b200_engine *h, const gate_b200_phsp_desc *d, int32_t *actor_id);
+
+/* A homogeneous Box of its own material placed in the world (a couch, a detector slab, a collimator plate): what
+ * the reference builds from a BoxVolume with `material` (geometry/volumes.py BoxVolume -> G4Box + G4LogicalVolume,
+ * engines.py:924-933 for the actors of a volume).  Photons travelling in the world are attenuated and scatter in it
+ * with its material's tables; its energy deposits count in the statistics only (dose actors are attached to the image
+ * volume).  At most 4; the boxes must not overlap each other or the image volume (caller's responsibility).  ABI 5. */
+int gate_b200_add_box_region(gate_b200_engine *h, const gate_b200_region_desc *d, int32_t *region_id);
 
 /* Replaces: GateSourceManager::StartMasterThread run loop (GateSourceManager.cpp:198-244):
  * begin_run zeroes the accumulators (BeginOfRunActionMasterThread), run_source enqueues

@@ -79,6 +79,18 @@ class PhspDesc(C.Structure):
                 ("steps_to_store", C.c_int32), ("capacity", C.c_uint64)]
 
 
+class RegionDesc(C.Structure):
+    _fields_ = [("half_size", C.c_double * 3), ("world_to_box", C.c_double * 12), ("material", C.c_int32)]
+
+
+def make_region_desc(half_size, world_to_box12, material):
+    d = RegionDesc()
+    d.half_size = (C.c_double * 3)(*[float(x) for x in half_size])
+    d.world_to_box = (C.c_double * 12)(*np.asarray(world_to_box12, float).reshape(-1))
+    d.material = int(material)
+    return d
+
+
 class PhspColumns(C.Structure):
     _fields_ = [("kinetic_energy", _fp), ("position", _fp), ("direction", _fp), ("weight", _fp),
                 ("time_ns", _fp), ("event_id", C.POINTER(C.c_int64)), ("flags", C.POINTER(C.c_int32))]

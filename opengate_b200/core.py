@@ -29,7 +29,7 @@ EXPORTS = [
     "gate_b200_abi_version", "gate_b200_create", "gate_b200_destroy", "gate_b200_release_cached_memory", "gate_b200_last_error",
     "gate_b200_set_stream", "gate_b200_set_tables", "gate_b200_set_world",
     "gate_b200_set_image_volume", "gate_b200_set_image_volume_hu", "gate_b200_add_source", "gate_b200_add_dose_actor",
-    "gate_b200_add_tle_dose_actor", "gate_b200_add_phsp_actor", "gate_b200_begin_run", "gate_b200_run_source", "gate_b200_sync",
+    "gate_b200_add_tle_dose_actor", "gate_b200_add_phsp_actor", "gate_b200_add_box_region", "gate_b200_begin_run", "gate_b200_run_source", "gate_b200_sync",
     "gate_b200_get_dose_grid", "gate_b200_dose_buffers", "gate_b200_set_dose_grid",
     "gate_b200_mean_uncertainty", "gate_b200_phsp_count", "gate_b200_get_phsp",
     "gate_b200_get_stats", "gate_b200_timed_run", "gate_b200_kernel_name",
@@ -90,6 +90,7 @@ def load_library():
     L.gate_b200_add_dose_actor.argtypes = [vp, C.POINTER(abi.DoseDesc), C.POINTER(i32)]
     L.gate_b200_add_tle_dose_actor.argtypes = [vp, C.POINTER(abi.DoseDesc), C.POINTER(abi.TleDesc), C.POINTER(i32)]
     L.gate_b200_add_phsp_actor.argtypes = [vp, C.POINTER(abi.PhspDesc), C.POINTER(i32)]
+    L.gate_b200_add_box_region.argtypes = [vp, C.POINTER(abi.RegionDesc), C.POINTER(i32)]
     L.gate_b200_begin_run.argtypes = [vp, i32]
     L.gate_b200_run_source.argtypes = [vp, i32, u64, u64]
     L.gate_b200_sync.argtypes = [vp]
@@ -236,6 +237,12 @@ class Engine:
         aid = C.c_int32(-1)
         self._check(self.L.gate_b200_add_phsp_actor(self.h, C.byref(desc), C.byref(aid)))
         return aid.value
+
+    def add_box_region(self, desc):
+        """a homogeneous Box of its own material in the world (gate_b200_add_box_region)"""
+        rid = C.c_int32(-1)
+        self._check(self.L.gate_b200_add_box_region(self.h, C.byref(desc), C.byref(rid)))
+        return rid.value
 
     # run -----------------------------------------------------------------------------
     def begin_run(self, run_id=0):

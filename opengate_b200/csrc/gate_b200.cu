@@ -843,6 +843,23 @@ int gate_b200_add_phsp_actor(gate_b200_engine *h, const gate_b200_phsp_desc *d, 
   return GATE_B200_OK;
 }
 
+int gate_b200_add_box_region(gate_b200_engine *h, const gate_b200_region_desc *d, int32_t *region_id) {
+  if (!h || !d) return GATE_B200_EINVAL;
+  Params &P = h->P;
+  if (P.nreg >= kMaxReg) return fail(h, GATE_B200_EINVAL, "at most %d box regions", kMaxReg);
+  if (!h->have_tables) return fail(h, GATE_B200_ESTATE, "add_box_region before set_tables");
+  if (d->material < 0 || d->material >= P.nmat) return fail(h, GATE_B200_EINVAL, "box region: material %d is not in the tables", d->material);
+  for (int a = 0; a < 3; ++a)
+    if (!(d->half_size[a] > 0.0)) return fail(h, GATE_B200_EINVAL, "box region: half sizes must be positive");
+  DRegion &R = P.reg[P.nreg];
+  for (int a = 0; a < 3; ++a) R.half[a] = (float)d->half_size[a];
+  affine_from_double(R.w2b, d->world_to_box);
+  R.mat = d->material;
+  if (region_id) *region_id = P.nreg;
+  P.nreg++;
+  return GATE_B200_OK;
+}
+
 int gate_b200_begin_run(gate_b200_engine *h, int32_t /*run_id*/) {
   if (!h) return GATE_B200_EINVAL;
   CU(cudaSetDevice(h->device));
@@ -916,7 +933,8 @@ static int launch_histories(gate_b200_engine *h, int32_t source_id, uint64_t fir
   // kernel variant: 1 = with the TLE phase; 2 / 3 = the common dose run (one dose actor, no phase-space actor
   // or source) with those choices compiled in, 2 for hit_type post, 3 for the other hit types; 4 = one dose actor
   // with phase-space actors; 0 = everything else
-  const bool one_dose = P.ntle == 0 && P.ndose == 1 && P.src.ph_b == nullptr && !getenv("GATE_B200_GENERAL_KERNEL");
+  const bool one_dose = P.ntle == 0 && P.ndose == 1 && P.nreg == 0 && P.src.ph_b == nullptr && !P.src.confine && P.src.dir_type != GATE_B200_DIR_HISTOGRAM &&
+                        !getenv("GATE_B200_GENERAL_KERNEL");
   const int mode = P.ntle > 0 ? tle_mode(P) : !one_dose ? 0 : P.nphsp > 0 ? 4 : (P.dose[0].hit_type == GATE_B200_HIT_POST ? 2 : 3);
   auto kern = transport_kernel<uint8_t, 0>;
   if (label_bytes == 2) {

@@ -102,6 +102,7 @@ constexpr int kWoodcockK = 4;              // tentative collisions per Woodcock 
 constexpr int kVWidth = GB2_VWIDTH;        // slots one lane carries through a Woodcock call
 constexpr int kMaxDose = 4;
 constexpr int kMaxPhsp = 4;
+constexpr int kMaxReg = 4;                // homogeneous Box regions of their own material in the world
 constexpr int kDepBuf = 32;                // per-history coalescing buffer entries
 constexpr int kTleSteps = 16;              // voxel chords (or table entries) per call of the TLE phase
 constexpr int kTleLog2 = 12;
@@ -174,6 +175,12 @@ struct DPhsp {
   unsigned long long *n_rows, *n_dropped;
 };
 
+struct DRegion {
+  float half[3];
+  Affine w2b;
+  int mat;
+};
+
 struct DepEntry { int key; float e; float d; int n; };   // one (voxel, history) partial sum
 
 // indices into the statistics array (unsigned long long)
@@ -206,6 +213,8 @@ struct Params {
   DDose dose[kMaxDose];
   int nphsp;
   DPhsp phsp[kMaxPhsp];
+  int nreg;                      // Box regions (general kernel variants only: 0, 1, 5)
+  DRegion reg[kMaxReg];
   DSource src;
   unsigned long long first, count;
   unsigned long long *next;      // history counter of this launch
@@ -1022,15 +1031,9 @@ __device__ __forceinline__ int cdf_index(const float *__restrict__ cdf, int last
   return lo;
 }
 
-__device__ __forceinline__ void generate_primary(const Params &P, Ph &g, int gslot) {
-  const DSource &S = P.src;
-  Rng &r = g.rng;
-  rng_begin(r);
-  float l[3] = {0.0f, 0.0f, 0.0f};
-  float4 ea = make_float4(0.0f, 0.0f, 0.0f, 0.0f), eb = ea;
-  // position.confine (G4SPSPosDistribution::GenerateOne with ConfineSourceToVolume): draw again until the point
-  // lies in the confining box, at most 100000 times
-  for (int tries = 0;; ++tries) {
+// position of a primary in the frame of its source (the position samplers of GateGenericSource::InitializePosition /
+// G4SPSPosDistribution, the voxel sampler, the entry of a phase-space file)
+__device__ __forceinline__ void sample_position(const Params &P, const DSource &S, Rng &r, float l[3], float4 &ea, float4 &eb, int gslot) {
   l[0] = 0.0f; l[1] = 0.0f; l[2] = 0.0f;
   switch (S.pos_type) {
   case GATE_B200_POS_PHSP: {
@@ -1099,11 +1102,30 @@ __device__ __forceinline__ void generate_primary(const Params &P, Ph &g, int gsl
     l[2] += (rng_uniform(r) - 0.5f) * S.vox_sp[2];
   } break;
   }
+}
+
+// kMode: the single-dose-actor kernel variants (2-4) are launched for sources without position.confine and without
+// angular histograms only and carry neither piece of code (measured: the presence of the confine loop alone cost
+// config 3 0.8 %)
+template <int kMode>
+__device__ __forceinline__ void generate_primary(const Params &P, Ph &g, int gslot) {
+  const DSource &S = P.src;
+  Rng &r = g.rng;
+  rng_begin(r);
+  float l[3];
+  float4 ea = make_float4(0.0f, 0.0f, 0.0f, 0.0f), eb = ea;
+  sample_position(P, S, r, l, ea, eb, gslot);
   aff_apply(S.pos, l, g.p);
-  if (!S.confine || tries >= 99999) break;
-  float qc[3];
-  aff_apply(S.conf, g.p, qc);
-  if (inside_box(qc, S.conf_half)) break;
+  if (!is_one(kMode) && S.confine) {
+    // position.confine (G4SPSPosDistribution::GenerateOne with ConfineSourceToVolume): draw again until the point
+    // lies in the confining box, at most 100000 draws in all
+    for (int tries = 1; tries < 100000; ++tries) {
+      float qc[3];
+      aff_apply(S.conf, g.p, qc);
+      if (inside_box(qc, S.conf_half)) break;
+      sample_position(P, S, r, l, ea, eb, gslot);
+      aff_apply(S.pos, l, g.p);
+    }
   }
 
   switch (S.dir_type) {
@@ -1161,7 +1183,7 @@ __device__ __forceinline__ void generate_primary(const Params &P, Ph &g, int gsl
     if (S.dir_relative) rot_apply(S.dir_rot, v, g.d);
     else { g.d[0] = v[0]; g.d[1] = v[1]; g.d[2] = v[2]; }
   } break;
-  case GATE_B200_DIR_HISTOGRAM: {
+  case GATE_B200_DIR_HISTOGRAM: if (!is_one(kMode)) {
     // G4SPSAngDistribution::GenerateUserDefFlux, theta and phi from user histograms: the angle is the inverse of the
     // piecewise-linear cumulative at a uniform variate (uniform inside its bin), momentum = -(sin t cos p, sin t sin p, cos t)
     float ang[2];
@@ -1329,10 +1351,19 @@ __device__ __forceinline__ int phase_world(const Params &P, Smem &S, int slot, i
     n_esc = 1;
     next = Q_E;
   } else {
-    int ev = 0;   // 0 interact, 1 leave world, 2 enter volume, 3+2k enter plane k, 4+2k leave plane k
-    float mu = tab_mu(P, P.world_mat, g.ie, g.fe);
+    int ev = 0;   // 0 interact, 1 leave world, 2 enter volume, 3+2k enter plane k, 4+2k leave plane k, 11 cross the face of a Box region
+    // the medium of this flight: the Box region the photon is in, else the world material
+    const int nreg = is_one(kMode) ? 0 : P.nreg;
+    int cur = -1, mat_here = P.world_mat;
+    for (int k = 0; k < nreg; ++k) {
+      float pb[3];
+      aff_apply(P.reg[k].w2b, g.p, pb);
+      if (cur < 0 && inside_box(pb, P.reg[k].half)) { cur = k; mat_here = P.reg[k].mat; }
+    }
+    float mu = tab_mu(P, mat_here, g.ie, g.fe);
     float t_best = -d_logf(rng_uniform(g.rng)) / mu;
     if (t_exit < t_best) { t_best = t_exit; ev = 1; }
+
     int ax_in = -1;
     if (P.has_vol) {
       float pl[3], dl[3], ti, to;
@@ -1353,6 +1384,17 @@ __device__ __forceinline__ int phase_world(const Params &P, Smem &S, int slot, i
         if (to < t_best) { t_best = to; ev = 4 + 2 * k; }
       } else if (ti < t_best) { t_best = ti; ev = 3 + 2 * k; }
     }
+    // faces of the Box regions, after the planes: a Box that is both (a detector slab with a phase-space actor) reports
+    // the crossing as the plane's event, the medium follows from the position at the next call
+    for (int k = 0; k < nreg; ++k) {
+      float pb[3], db[3], ti, to;
+      aff_apply(P.reg[k].w2b, g.p, pb);
+      rot_apply(P.reg[k].w2b.m, g.d, db);
+      if (!ray_box(pb, db, P.reg[k].half, ti, to)) continue;
+      if (k == cur) {
+        if (to < t_best) { t_best = to; ev = 11; }
+      } else if (ti < t_best) { t_best = ti; ev = 11; }
+    }
     float step = (ev >= 3) ? t_best + kNudge : t_best;
     if (ev == 1) {
       n_esc = 1;
@@ -1363,10 +1405,13 @@ __device__ __forceinline__ int phase_world(const Params &P, Smem &S, int slot, i
       for (int a = 0; a < 3; ++a) g.p[a] = g.p[a] + g.d[a] * step;
       g.path += step;
       if (ev == 0) {
-        // real interaction in the world material
+        // real interaction in the world material (or in the material of the Box region the photon is in)
         g.flags &= ~F_INVOL;
-        g.mat = P.world_mat;
+        g.mat = mat_here;
         next = route_interaction(P, g.flags, g.mat, g.ie, g.fe, rng_uniform(g.rng));
+      } else if (ev == 11) {
+        n_steps++;
+        next = Q_W;       // the next flight starts on the other side of the face, in the other medium
       } else if (ev == 2) {
         n_steps++;
         to_volume(P, g);
@@ -1864,7 +1909,7 @@ __device__ __forceinline__ int phase_end(const Params &P, Smem &S, int slot, int
       rng_init(g.rng, P.seed, P.first + idx, 0u);
       g.flags = F_OPEN;
       g.mat = 0;
-      generate_primary(P, g, gslot);
+      generate_primary<kMode>(P, g, gslot);
       g.path = 0.0f; g.seg = 0.0f;
       n_hist = 1;
       next = locate<kMode>(P, g);

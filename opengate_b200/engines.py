@@ -56,6 +56,34 @@ def invert_rigid(R, t):
     return Ri, -Ri @ np.asarray(t, dtype=np.float64)
 
 
+def _half_size(v):
+    h = v.half_size_mm() if callable(v.half_size_mm) else v.half_size_mm
+    return np.asarray(h, dtype=np.float64)
+
+
+def _boxes_overlap(a, b):
+    """separating-axis test of two placed boxes (15 axes): True when they share volume"""
+    Ra, ta = a.world_transform()
+    Rb, tb = b.world_transform()
+    ha, hb = _half_size(a), _half_size(b)
+    R = Ra.T @ Rb
+    t = Ra.T @ (tb - ta)
+    A = np.abs(R) + 1e-12
+    for i in range(3):
+        if abs(t[i]) > ha[i] + hb @ A[i]:
+            return False
+    for j in range(3):
+        if abs(t @ R[:, j]) > ha @ A[:, j] + hb[j]:
+            return False
+    for i in range(3):
+        for j in range(3):
+            ra = ha[(i + 1) % 3] * A[(i + 2) % 3, j] + ha[(i + 2) % 3] * A[(i + 1) % 3, j]
+            rb = hb[(j + 1) % 3] * A[i, (j + 2) % 3] + hb[(j + 2) % 3] * A[i, (j + 1) % 3]
+            if abs(t[(i + 2) % 3] * R[(i + 1) % 3, j] - t[(i + 1) % 3] * R[(i + 2) % 3, j]) > ra + rb:
+                return False
+    return True
+
+
 def affine34(R, t):
     A = np.zeros((3, 4))
     A[:, :3] = R
@@ -106,21 +134,45 @@ class GpuSimulationEngine:
             fatal("The B200 GPU engine supports one ImageVolume per simulation")
         if images:
             phantom = images[0]
+        # Boxes: the one a dose actor is attached to (or, without an Image volume, the first one of another material)
+        # is the phantom; every other Box of a material of its own is a homogeneous region of the world (a couch, a
+        # detector slab -- photons are attenuated and scatter there, nothing is scored); Boxes of the world
+        # material only carry phase-space actors
+        self.region_volumes = []
         for v in vols:
             if v is phantom:
                 continue
             if v.volume_type != "BoxVolume":
                 fatal(f"Volume '{v.name}' of type {v.volume_type} is not supported by the B200 GPU engine")
-            if v.name in dose_targets or (v.material != world_mat and v.name not in phsp_targets):
+            if v.name in dose_targets:
                 if phantom is not None:
-                    fatal(f"Volume '{v.name}' ({v.material}) is a second material region besides '{phantom.name}': "
-                          f"the B200 GPU engine transports photons through the world and ONE phantom volume")
+                    fatal(f"DoseActor attached to '{v.name}' besides the phantom '{phantom.name}': on the B200 GPU engine "
+                          f"dose actors are attached to ONE phantom volume")
                 phantom = v
-            elif v.material != world_mat:
-                fatal(f"Box '{v.name}' holding a PhaseSpaceActor must be made of the world material "
-                      f"('{world_mat}') on the B200 GPU engine (it is a scoring plane, not a material region)")
+        for v in vols:
+            if v is phantom or v.material == world_mat:
+                continue
+            if phantom is None and v.name not in phsp_targets:
+                phantom = v
+                continue
+            self.region_volumes.append(v)
         if phantom is None:
             fatal("No phantom volume: add an Image volume (or a Box with a DoseActor attached)")
+        if len(self.region_volumes) > 4:
+            fatal(f"The B200 GPU engine supports at most 4 Box volumes of their own material besides the phantom "
+                  f"({[v.name for v in self.region_volumes]})")
+        for v in self.region_volumes:
+            m = v.mother_volume
+            while m is not None and m.name != __world_name__:
+                if m.material != world_mat:
+                    fatal(f"Box '{v.name}' must be placed in the world (or in mothers made of the world material) "
+                          f"on the B200 GPU engine: nested material regions are not supported")
+                m = m.mother_volume
+            others = [phantom] + [w for w in self.region_volumes if w is not v]
+            for w in others:
+                if _boxes_overlap(v, w):
+                    fatal(f"Box '{v.name}' overlaps volume '{w.name}': material regions must be disjoint "
+                          f"on the B200 GPU engine")
         for t in dose_targets:
             if t != phantom.name:
                 fatal(f"DoseActor attached to '{t}': on the B200 GPU engine dose actors must be attached to the "
@@ -170,6 +222,9 @@ class GpuSimulationEngine:
         names = list(lut.keys())
         if world.material not in lut:
             names.append(world.material)
+        for v in self.region_volumes:
+            if v.material not in names:
+                names.append(v.material)
         world_label = names.index(world.material)
         label_bytes = 1 if len(names) <= 256 else 2
         labels = None if labels16 is None else labels16.astype(np.uint8 if label_bytes == 1 else np.uint16)
@@ -237,6 +292,10 @@ class GpuSimulationEngine:
             labels=None if labels is None else np.ascontiguousarray(labels), spacing=spacing,
             world_to_volume=w2v, sources=src_structs, dose=dose_desc, phsp=phsp_desc, n_primaries=int(n_total),
             materials=mats, hu=hu, hu_bins=hu_bins, hu_bin_labels=hu_bin_labels, label_bytes=label_bytes)
+        for v in self.region_volumes:
+            Rb, tb = v.world_transform()
+            Rbi, tbi = invert_rigid(Rb, tb)
+            self.setup.regions.append(abi.make_region_desc(_half_size(v), affine34(Rbi, tbi), names.index(v.material)))
         # TLE dose actors come after the plain ones in the engine's actor id space
         for size, A, flags, hit, thr, emin, database in tle_desc:
             self.setup.add_tle_actor(size, A, flags, hit_type=hit, threshold=thr, energy_min=emin, database=database)

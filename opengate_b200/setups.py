@@ -124,6 +124,7 @@ class LowLevelSetup:
     hu_bins: list = None
     hu_bin_labels: list = None
     label_bytes: int = 1
+    regions: list = field(default_factory=list)       # RegionDesc: homogeneous Boxes of their own material in the world
 
     def label_array(self):
         """(z,y,x) label volume; made on the host from the HU image when it was not given."""
@@ -140,6 +141,8 @@ class LowLevelSetup:
                                     self.label_bytes)
         else:
             eng.set_image_volume(self.label_array(), self.spacing, self.world_to_volume)
+        for r in self.regions:
+            eng.add_box_region(r)
         sids = [eng.add_source(s, keep) for s, keep in self.sources]
         dids = [eng.add_dose_actor(d) for d in self.dose]
         dids += [eng.add_tle_dose_actor(d, t, keep) for d, t, keep in self.tle]

@@ -67,6 +67,7 @@ def lib(fp64=False):
         L.oracle_add_dose_actor.argtypes = [C.c_void_p, C.POINTER(abi.DoseDesc)]
         L.oracle_add_tle_dose_actor.argtypes = [C.c_void_p, C.POINTER(abi.DoseDesc), C.POINTER(abi.TleDesc)]
         L.oracle_add_phsp_actor.argtypes = [C.c_void_p, C.POINTER(abi.PhspDesc)]
+        L.oracle_add_box_region.argtypes = [C.c_void_p, C.POINTER(abi.RegionDesc)]
         L.oracle_begin_run.argtypes = [C.c_void_p]
         L.oracle_run_source.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_int]
         L.oracle_set_tle_fold.argtypes = [C.c_void_p, C.c_int]
@@ -153,6 +154,12 @@ class TransportOracle:
 
     def add_phsp_actor(self, desc):
         return self.L.oracle_add_phsp_actor(self.h, C.byref(desc))
+
+    def add_box_region(self, desc):
+        r = self.L.oracle_add_box_region(self.h, C.byref(desc))
+        if r < 0:
+            raise ValueError("box region refused (more than 4, or a material outside the tables)")
+        return r
 
     def begin_run(self):
         self.L.oracle_begin_run(self.h)

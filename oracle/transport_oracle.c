@@ -276,6 +276,7 @@ struct oracle_engine {
   int tle_rec_cap;     /* records a history may hold (TLE_REC_MAX; tests lower it to reach the overflow path) */
   int tle_fold;        /* test switch (index of the TLE actor + 1): score it by the device's record-fold statement, not the table */
   int nphsp; ophsp_t phsp[ORACLE_MAX_PHSP];
+  int nreg; struct { real_t half[3]; affine_t w2b; int mat; } reg[4];   /* homogeneous Box regions in the world */
   gate_b200_stats stats;
   char err[256];
 };
@@ -1260,10 +1261,18 @@ static void run_photon(hist_t *h, real_t pend_p[3], real_t pend_d[3], int *pend)
         h->st.escaped++;
         return;
       }
-      int ev = 0; /* 0 interact, 1 leave world, 2 enter phantom, 3+2k enter plane k, 4+2k leave plane k */
-      real_t mu = tab(g->mu, g->ne, g->world_mat, h->ie, h->fe);
+      int ev = 0; /* 0 interact, 1 leave world, 2 enter phantom, 3+2k enter plane k, 4+2k leave plane k, 11 cross the face of a Box region */
+      /* the medium of this flight: the Box region the photon is in (BoxVolume with its own material), else the world */
+      int cur = -1, mat_here = g->world_mat;
+      for (int k = 0; k < g->nreg; ++k) {
+        real_t pb[3];
+        aff_apply(&g->reg[k].w2b, h->p, pb);
+        if (cur < 0 && inside_box(pb, g->reg[k].half)) { cur = k; mat_here = g->reg[k].mat; }
+      }
+      real_t mu = tab(g->mu, g->ne, mat_here, h->ie, h->fe);
       real_t t_best = -R_LOG(rng_uniform(&h->rng)) / mu;
       if (t_exit < t_best) { t_best = t_exit; ev = 1; }
+
       int ax_in = -1;
       if (g->has_vol) {
         real_t pl[3], dl[3], ti, to;
@@ -1284,13 +1293,25 @@ static void run_photon(hist_t *h, real_t pend_p[3], real_t pend_d[3], int *pend)
           if (to < t_best) { t_best = to; ev = 4 + 2 * k; }
         } else if (ti < t_best) { t_best = ti; ev = 3 + 2 * k; }
       }
+      /* faces of the Box regions, after the planes (a Box that is both reports the crossing as the plane's event) */
+      for (int k = 0; k < g->nreg; ++k) {
+        real_t pb[3], db[3], ti, to;
+        aff_apply(&g->reg[k].w2b, h->p, pb);
+        rot_apply(g->reg[k].w2b.m, h->d, db);
+        if (!ray_box(pb, db, g->reg[k].half, &ti, &to)) continue;
+        if (k == cur) {
+          if (to < t_best) { t_best = to; ev = 11; }
+        } else if (ti < t_best) { t_best = ti; ev = 11; }
+      }
       real_t step = (ev >= 3) ? t_best + NUDGE : t_best;
       if (ev == 1) { h->st.escaped++; h->path += t_best; return; }
       for (int a = 0; a < 3; ++a) h->p[a] = h->p[a] + h->d[a] * step;
       h->path += step;
       if (ev == 0) {
-        int proc = select_process(h, g->world_mat, rng_uniform(&h->rng));
-        alive = interact(h, proc, g->world_mat, 0, 0, 0, pend_p, pend_d, pend);
+        int proc = select_process(h, mat_here, rng_uniform(&h->rng));
+        alive = interact(h, proc, mat_here, 0, 0, 0, pend_p, pend_d, pend);
+      } else if (ev == 11) {
+        h->st.steps++;   /* the next flight starts on the other side of the face, in the other medium */
       } else if (ev == 2) {
         h->st.steps++;
         to_phantom(h);
@@ -1748,6 +1769,14 @@ int oracle_set_tle_fold(oracle_engine *g, int on) {
   for (int a = 0; a < g->ndose; ++a)
     if (g->dose[a].tle && g->dose[a].aligned) g->tle_fold = a + 1;   /* that actor's index + 1 */
   return g->tle_fold ? 0 : -1;
+}
+
+int oracle_add_box_region(oracle_engine *g, const gate_b200_region_desc *d) {
+  if (g->nreg >= 4 || d->material < 0 || d->material >= g->nmat) return -1;
+  for (int a = 0; a < 3; ++a) g->reg[g->nreg].half[a] = (real_t)d->half_size[a];
+  aff_from_d(&g->reg[g->nreg].w2b, d->world_to_box);
+  g->reg[g->nreg].mat = d->material;
+  return g->nreg++;
 }
 
 int oracle_add_phsp_actor(oracle_engine *g, const gate_b200_phsp_desc *d) {

@@ -40,6 +40,7 @@ int oracle_add_dose_actor(oracle_engine *g, const gate_b200_dose_desc *d);
 int oracle_add_tle_dose_actor(oracle_engine *g, const gate_b200_dose_desc *d, const gate_b200_tle_desc *t);
 int oracle_set_tle_fold(oracle_engine *g, int on);
 int oracle_set_tle_rec_cap(oracle_engine *g, int cap);
+int oracle_add_box_region(oracle_engine *g, const gate_b200_region_desc *d);
 int oracle_add_phsp_actor(oracle_engine *g, const gate_b200_phsp_desc *d);
 void oracle_begin_run(oracle_engine *g);
 int oracle_run_source(oracle_engine *g, int source_id, uint64_t first, uint64_t n, int n_threads);

@@ -597,3 +597,17 @@ def test_ten_billion_histories_launch_splitting_and_64_bit_counters(cuda_require
     assert g.sum() <= st["edep_total_MeV"] * (1 + 1e-9)          # the grid misses what is deposited outside it
     assert g.sum() > 0.5 * st["edep_total_MeV"]
     eng.close()
+
+
+@pytest.mark.parametrize("kw", [dict(thickness=40.0, tilt_deg=0.0), dict(thickness=25.0, tilt_deg=30.0),
+                                dict(thickness=30.0, tilt_deg=-15.0, energy=0.08)])
+def test_box_regions_match_oracle(cuda_required, kw):
+    """a homogeneous Box of its own material in the world (couch / detector slab), scoring planes before and behind:
+    counters, phase-space rows and grids as the oracle (general kernel variant)"""
+    from region_setups import slab_in_front
+    n = 6000
+    S = slab_in_front(n, **kw)
+    eng, orc, ids = run_both(S, n)
+    compare(eng, orc, S, ids)
+    assert eng.kernel_name().endswith(", 0>") and eng.stats()["phsp_dropped"] == 0
+    eng.close()

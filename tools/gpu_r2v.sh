@@ -1,11 +1,14 @@
 #!/bin/bash
 mkdir -p gpurun_out
 T=${1:-r2v}
+( timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -q > gpurun_out/${T}_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/${T}_pytest.log )
+tail -4 gpurun_out/${T}_pytest.log
+timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_run.py 3000 > gpurun_out/${T}_sanitizer_memcheck.log 2>&1; tail -3 gpurun_out/${T}_sanitizer_memcheck.log
 {
 for rep in 1 2; do
 for lib in "" gpurun_variants/lib_prev_abi4.so; do
   echo "== lib=${lib:-default}"
-  for c in c3 c2 c1; do env ${lib:+GATE_B200_LIB=$lib} timeout 120 python tools/profile_run.py --config $c --histories 100000000 --launches 2 | cut -c1-24,100-400; done
+  for c in c3 c2 c1 c4; do env ${lib:+GATE_B200_LIB=$lib} timeout 120 python tools/profile_run.py --config $c --histories 100000000 --launches 2 | cut -c1-24,100-400; done
 done
 done
 } > gpurun_out/${T}_ab.log 2>&1

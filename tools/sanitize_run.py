@@ -27,6 +27,8 @@ S = small_setups.c3(n)
 S.dose[0].hit_type = abi.HIT_POST
 S.dose[0].score_flags = abi.SCORE_EDEP | abi.SCORE_EDEP_SQ | abi.SCORE_DOSE
 cases["c3_bench_shape"] = S
+import region_setups  # noqa: E402
+cases["box_region"] = region_setups.slab_in_front(n, 25.0, 30.0)
 cases["c3_tle_sq_table"] = tle_setups.c3_tle(n)      # the same actor forced through the table variant (1) of the kernel
 cases["c3_tle_sq_hybrid_cap2"] = tle_setups.c3_tle(n, threshold=0.06)   # record variant: point deposits, record overflows
 for name, S in cases.items():

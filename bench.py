@@ -51,9 +51,10 @@ def build_setup(name, histories):
         return S
     if name == "c3_hit_random":
         # config 3 with the reference's DEFAULT hit_type ("random": a point between the pre- and post-step
-        # points of the Geant4 step).  For a dose grid equal to the image grid the voxel is the same as with
-        # "post" (a Geant4 step never leaves its voxel); the bench uses "post", this variant measures the cost
-        # of emulating the default.
+        # points of the Geant4 step).  A Geant4 step never leaves its voxel, so on a dose grid equal to the image
+        # grid that point lies in the voxel of the interaction: engine and oracle score it like "post" (no
+        # emulation, no random number; the kernel variant of the main line); grids of their own keep the
+        # hit-point emulation (kernel variant 3).  This variant shows that the default costs nothing here.
         from opengate_b200 import abi
         S = setups.make_c3(n_primaries=histories)
         S.dose[0].hit_type = abi.HIT_RANDOM

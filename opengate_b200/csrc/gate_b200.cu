@@ -750,6 +750,21 @@ int gate_b200_add_dose_actor(gate_b200_engine *h, const gate_b200_dose_desc *d, 
     }
   }
   affine_from_double(D.v2i, comp);
+  // the grid is the image grid when volume point -> index is p / spacing + n / 2 - 1 / 2 on the image's own
+  // lattice (same test as the oracle's grid_is_image_grid): the voxel of a TLE chord is then the image voxel, and
+  // the point a hit type picks on a Geant4 step (which never leaves its voxel) cannot change the voxel scored
+  {
+    const Params &P = h->P;
+    D.aligned = 1;
+    for (int a = 0; a < 3; ++a) {
+      if (D.size[a] != P.n[a]) D.aligned = 0;
+      for (int c = 0; c < 3; ++c) {
+        const double wnt = a == c ? 1.0 / (double)P.sp[a] : 0.0;
+        if (fabs((double)D.v2i.m[3 * a + c] - wnt) > 1.0e-6 * (1.0 / (double)P.sp[a])) D.aligned = 0;
+      }
+      if (fabs((double)D.v2i.t[a] - (0.5 * (double)P.n[a] - 0.5)) > 1.0e-4) D.aligned = 0;
+    }
+  }
   const int want[5] = {GATE_B200_SCORE_EDEP, GATE_B200_SCORE_EDEP_SQ, GATE_B200_SCORE_DOSE,
                        GATE_B200_SCORE_DOSE_SQ, GATE_B200_SCORE_COUNTS};
   // one 32-byte record per voxel for the four sums (a deposit touches one DRAM sector instead of
@@ -792,17 +807,6 @@ int gate_b200_add_tle_dose_actor(gate_b200_engine *h, const gate_b200_dose_desc 
         m2[(size_t)ie * P.nmat + m] = make_float2(t->mu_en_over_rho[(size_t)m * P.ne + ie], t->mu_en_over_rho[(size_t)m * P.ne + ie1]);
     }
     if (int rc = dev_upload(h, &D.muen2, m2.data(), n)) return rc;
-  }
-  // the grid is the image grid when volume point -> index is p / spacing + n / 2 - 1 / 2 on the image's own
-  // lattice (same test as the oracle's grid_is_image_grid): the voxel of a chord is then the image voxel
-  D.aligned = 1;
-  for (int a = 0; a < 3; ++a) {
-    if (D.size[a] != P.n[a]) D.aligned = 0;
-    for (int c = 0; c < 3; ++c) {
-      const double want = a == c ? 1.0 / (double)P.sp[a] : 0.0;
-      if (fabs((double)D.v2i.m[3 * a + c] - want) > 1.0e-6 * (1.0 / (double)P.sp[a])) D.aligned = 0;
-    }
-    if (fabs((double)D.v2i.t[a] - (0.5 * (double)P.n[a] - 0.5)) > 1.0e-4) D.aligned = 0;
   }
   const float emin = (float)t->energy_min_MeV;
   if (P.ntle == 0 || emin > P.tle_emin) P.tle_emin = emin;
@@ -935,7 +939,10 @@ static int launch_histories(gate_b200_engine *h, int32_t source_id, uint64_t fir
   // with phase-space actors; 0 = everything else
   const bool one_dose = P.ntle == 0 && P.ndose == 1 && P.nreg == 0 && P.src.ph_b == nullptr && !P.src.confine && P.src.dir_type != GATE_B200_DIR_HISTOGRAM &&
                         !getenv("GATE_B200_GENERAL_KERNEL");
-  const int mode = P.ntle > 0 ? tle_mode(P) : !one_dose ? 0 : P.nphsp > 0 ? 4 : (P.dose[0].hit_type == GATE_B200_HIT_POST ? 2 : 3);
+  // hit_type random / middle on the image's own grid score the voxel of the interaction, like post (hit_point_is_post)
+  const bool post = P.ndose > 0 && (P.dose[0].hit_type == GATE_B200_HIT_POST ||
+                                    (P.dose[0].aligned && P.dose[0].hit_type != GATE_B200_HIT_PRE));
+  const int mode = P.ntle > 0 ? tle_mode(P) : !one_dose ? 0 : P.nphsp > 0 ? 4 : (post ? 2 : 3);
   auto kern = transport_kernel<uint8_t, 0>;
   if (label_bytes == 2) {
     kern = mode == 1 ? transport_kernel<uint16_t, 1> : mode == 2 ? transport_kernel<uint16_t, 2>

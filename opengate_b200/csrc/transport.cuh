@@ -843,7 +843,11 @@ __device__ __forceinline__ void deposit(const Params &P, Ph &g, DepEntry *buf, D
     const DDose &D = P.dose[is_one(kMode) ? 0 : a];
     if (is_tle(kMode) && D.tle && e_tle <= D.tle_thr) continue;
     float pos[3] = {g.p[0], g.p[1], g.p[2]};
-    if (kMode != 2 && D.hit_type != GATE_B200_HIT_POST) {
+    // A Geant4 step inside the nested-parameterised image never leaves its voxel: when the dose grid IS the image grid,
+    // any point strictly between the pre- and the post-step point (hit_type random, middle) lies in the voxel of the
+    // interaction, so the emulation below -- and the random number of "random" -- is not needed; "pre" keeps it (a
+    // pre-step point ON a voxel face is the reference's own ambiguity)
+    if (kMode != 2 && D.hit_type != GATE_B200_HIT_POST && !(D.aligned && D.hit_type != GATE_B200_HIT_PRE)) {
       // pre/random/middle between the Geant4 pre and post step points; the Geant4 step starts at
       // the voxel entry or at the previous interaction (GateDoseActor.cpp:144-178)
       // the image voxel of the interaction point, by the SAME expression that gathered its label in the Woodcock

@@ -598,7 +598,11 @@ static void deposit(hist_t *h, real_t e, int m, int vix, int viy, int viz, real_
     odose_t *D = &g->dose[a];
     if (D->tle && e_tle <= D->tle_thr) continue;
     real_t pos[3] = {h->p[0], h->p[1], h->p[2]};
-    if (D->hit_type != GATE_B200_HIT_POST) {
+    /* A Geant4 step inside the nested-parameterised image never leaves its voxel: when the dose grid IS the image
+     * grid, any point strictly between the pre- and the post-step point (hit_type random, middle) lies in the voxel
+     * of the interaction: no emulation, no random number; "pre" keeps it (a pre-step point ON a voxel face is the
+     * reference's own ambiguity) */
+    if (D->hit_type != GATE_B200_HIT_POST && !(D->aligned && D->hit_type != GATE_B200_HIT_PRE)) {
       /* GateDoseActor.cpp:144-178: pre/random/middle between the Geant4 pre and post step
        * points; the Geant4 step starts at the voxel entry or at the previous interaction */
       real_t back = h->seg;
@@ -1689,6 +1693,7 @@ int oracle_add_source(oracle_engine *g, const gate_b200_source *s) {
   return g->nsrc++;
 }
 
+static int grid_is_image_grid(const oracle_engine *g, const odose_t *D);
 int oracle_add_dose_actor(oracle_engine *g, const gate_b200_dose_desc *d) {
   if (g->ndose >= ORACLE_MAX_DOSE) return -1;
   odose_t *D = &g->dose[g->ndose];
@@ -1717,6 +1722,7 @@ int oracle_add_dose_actor(oracle_engine *g, const gate_b200_dose_desc *d) {
     }
   }
   aff_from_d(&D->v2i, comp);
+  D->aligned = grid_is_image_grid(g, D);
   size_t nv = (size_t)D->size[0] * D->size[1] * D->size[2];
   const int want[5] = {GATE_B200_SCORE_EDEP, GATE_B200_SCORE_EDEP_SQ, GATE_B200_SCORE_DOSE,
                        GATE_B200_SCORE_DOSE_SQ, GATE_B200_SCORE_COUNTS};

@@ -611,3 +611,24 @@ def test_box_regions_match_oracle(cuda_required, kw):
     compare(eng, orc, S, ids)
     assert eng.kernel_name().endswith(", 0>") and eng.stats()["phsp_dropped"] == 0
     eng.close()
+
+
+@pytest.mark.parametrize("hit,variant", [(abi.HIT_RANDOM, 2), (abi.HIT_MIDDLE, 2), (abi.HIT_PRE, 3)])
+def test_hit_type_on_the_image_grid(cuda_required, hit, variant):
+    """On a dose grid that is the image grid a point between the pre- and the post-step point of a Geant4 step lies
+    in the voxel of the interaction: random and middle are scored like post (same kernel variant, identical grids),
+    pre keeps the hit-point emulation."""
+    n = 8000
+    S = SMALL["c3"](n)
+    S.dose[0].hit_type = hit
+    eng, orc, ids = run_both(S, n)
+    compare(eng, orc, S, ids)
+    assert eng.kernel_name().endswith(f", {variant}>")
+    if variant == 2:
+        P = SMALL["c3"](n)
+        P.dose[0].hit_type = abi.HIT_POST
+        e2, o2, i2 = run_both(P, n)
+        for which in (abi.GRID_EDEP, abi.GRID_DOSE, abi.GRID_COUNTS):
+            assert np.array_equal(orc.dose_grid(ids[1][0], which), o2.dose_grid(i2[1][0], which))
+        e2.close()
+    eng.close()

@@ -21,8 +21,12 @@ S = small_setups.c3(n)
 S.labels = S.labels.astype(np.uint16)
 cases["c3_u16"] = S
 S = small_setups.c3(n)
-S.dose[0].hit_type = abi.HIT_RANDOM          # kernel variant 3; the variant-2 run is the bench shape
+S.dose[0].hit_type = abi.HIT_RANDOM          # on the image's own grid: scored like post, kernel variant 2
 cases["c3_hit_random"] = S
+cases["c1_hit_random"] = small_setups.c1(n, hit_type=abi.HIT_RANDOM)   # a grid of its own: hit-point emulation, variant 3
+S = small_setups.c3(n)
+S.dose[0].hit_type = abi.HIT_PRE             # pre-step points keep the emulation on any grid: variant 3
+cases["c3_hit_pre"] = S
 S = small_setups.c3(n)
 S.dose[0].hit_type = abi.HIT_POST
 S.dose[0].score_flags = abi.SCORE_EDEP | abi.SCORE_EDEP_SQ | abi.SCORE_DOSE

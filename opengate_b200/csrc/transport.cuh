@@ -90,6 +90,17 @@ constexpr int kWoodcockK = 4;              // tentative collisions per Woodcock 
 #ifndef GB2_VWIDTH
 #define GB2_VWIDTH 1
 #endif
+#ifndef GB2_CHAIN
+// Phase chaining: when at least GB2_CHAIN_MIN lanes of a warp leave a single-slot phase for the world phase or the
+// end-of-photon phase, the warp runs that phase for them at once instead of sending them through the queues (up to
+// GB2_CHAIN times in a row).  The typical chain of a history that leaves the volume -- world (exit, escape) -> end
+// (close the history, next primary) -> world (first flight to the volume) -- then costs one visit of the scheduler
+// instead of three.  Every phase call still starts on a fresh Philox block: the histories do not change.
+#define GB2_CHAIN 0                       // measured (profiles/r2x6_ab_phase_chaining.log): 2 or 3 links cost 2.6 ... 5.6 %
+#endif
+#ifndef GB2_CHAIN_MIN
+#define GB2_CHAIN_MIN 16
+#endif
 #ifndef GB2_TLE_PREFETCH
 #define GB2_TLE_PREFETCH 0                // 1 / 2: next-voxel label prefetch to L2 / L1; measured: no effect (the march is bound by the DRAM rate of random sectors)
 #endif
@@ -2321,12 +2332,29 @@ __global__ void __launch_bounds__(threads_of<is_tle(kMode)>(), GB2_MIN_CTAS) tra
         volume_gather_mu(P, vc);
         next[0] = volume_decide<kMode>(P, S, slot[0], slot_base + slot[0], vc, c_tent);
       }
-    } else if (slot[0] >= 0) {
-      if (q == Q_C) next[0] = phase_compton<kMode>(P, S, slot[0], slot_base + slot[0], c_edep);
-      else if (q == Q_E) next[0] = phase_end<kMode>(P, S, slot[0], slot_base + slot[0], c_edep);
-      else if (q == Q_W) next[0] = phase_world<kMode>(P, S, slot[0], slot_base + slot[0]);
-      else if (is_tle(kMode) && q == Q_T) next[0] = phase_tle<LabelT, kMode>(P, S, slot[0], slot_base + slot[0]);
-      else next[0] = phase_rare<kMode>(P, S, slot[0], slot_base + slot[0], c_edep);
+    } else {
+      // single-slot phases, with chaining (GB2_CHAIN): each phase function is inlined ONCE, the chain loops back here
+      int qq = q;
+      bool active = slot[0] >= 0;
+      for (int chain = 0;; ++chain) {
+        if (active) {
+          if (qq == Q_C) next[0] = phase_compton<kMode>(P, S, slot[0], slot_base + slot[0], c_edep);
+          else if (qq == Q_E) next[0] = phase_end<kMode>(P, S, slot[0], slot_base + slot[0], c_edep);
+          else if (qq == Q_W) next[0] = phase_world<kMode>(P, S, slot[0], slot_base + slot[0]);
+          else if (is_tle(kMode) && qq == Q_T) next[0] = phase_tle<LabelT, kMode>(P, S, slot[0], slot_base + slot[0]);
+          else next[0] = phase_rare<kMode>(P, S, slot[0], slot_base + slot[0], c_edep);
+        }
+        if (chain >= GB2_CHAIN) break;
+        __syncwarp();
+        const int nx = slot[0] >= 0 ? next[0] : -3;
+        const int nE = __popc(__ballot_sync(FULL, nx == Q_E)), nW = __popc(__ballot_sync(FULL, nx == Q_W));
+        int qn = -1;
+        if (nE >= GB2_CHAIN_MIN && nE >= nW) qn = Q_E;
+        else if (nW >= GB2_CHAIN_MIN) qn = Q_W;
+        if (qn < 0) break;                      // warp-uniform
+        qq = qn;
+        active = nx == qn;
+      }
     }
     if (kHasVS && P.shell) {
       // a photon whose next Woodcock call starts outside the inner box waits in the queue of the shell-start calls

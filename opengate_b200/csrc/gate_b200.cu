@@ -134,6 +134,21 @@ int dev_upload(gate_b200_engine *h, const T **out, const T *src, size_t n) {
   return 0;
 }
 
+// class volume of the Woodcock phase: 2 bits per voxel, four voxels per byte (x fastest, flat index >> 2)
+template <typename LabelT>
+__global__ void __launch_bounds__(256) class_pack_kernel(const LabelT *__restrict__ labels, unsigned long long nv,
+                                                         const unsigned char *__restrict__ cls_of, unsigned char *__restrict__ out) {
+  const unsigned long long nb = (nv + 3ull) / 4ull;
+  for (unsigned long long b = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; b < nb; b += (unsigned long long)gridDim.x * blockDim.x) {
+    unsigned v = 0;
+    for (int j = 0; j < 4; ++j) {
+      const unsigned long long i = 4ull * b + j;
+      if (i < nv) v |= (unsigned)cls_of[labels[i]] << (2 * j);
+    }
+    out[b] = (unsigned char)v;
+  }
+}
+
 // Which labels occur in the volume (bit set, one bit per material), the first voxel whose label has no material,
 // and the bounding box (voxel indices) of the voxels whose label differs from that of voxel 0 (the inner box of
 // the homogeneous shell): one pass over the device copy of the label volume.
@@ -515,6 +530,46 @@ static int finish_image_volume(gate_b200_engine *h, uint8_t *dl, const void *hos
     maj[i] = mx;
   }
   CU(cudaMemcpyAsync(h->d_maj, maj.data(), maj.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  // ---- the class volume (Params::cls): the materials present in four classes; at most four present -> class = material
+  P.cls = nullptr;
+  P.cmax = nullptr;
+  if (GB2_CLASSVOL) {
+    std::vector<unsigned char> cls_of(P.nmat, 0);
+    std::vector<int> pres;
+    for (int m = 0; m < P.nmat; ++m) if (present[m]) pres.push_back(m);
+    P.cls_exact = pres.size() <= 4 ? 1 : 0;
+    for (int k = 0; k < 4; ++k) P.cls_mat[k] = pres.empty() ? 0 : pres[std::min<size_t>(k, pres.size() - 1)];
+    if (P.cls_exact) {
+      for (size_t k = 0; k < pres.size(); ++k) cls_of[pres[k]] = (unsigned char)k;
+    } else {
+      // by density: gas, lung-like, soft tissue, denser (Schneider materials of a CT: a class spans a few percent of
+      // attenuation except the last one)
+      for (int m : pres) {
+        const float rho = h->h_dens[m];
+        cls_of[m] = rho < 0.05f ? 0 : (rho < 0.6f ? 1 : (rho < 1.12f ? 2 : 3));
+      }
+    }
+    std::vector<float4> cmax(P.ne, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int i = 0; i < P.ne; ++i) {
+      float mx[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int m : pres) mx[cls_of[m]] = std::max(mx[cls_of[m]], h->h_mu[(size_t)m * P.ne + i]);
+      cmax[i] = make_float4(mx[0], mx[1], mx[2], mx[3]);
+    }
+    const unsigned char *d_cls_of = nullptr;
+    unsigned char *d_cls = nullptr;
+    const float4 *d_cmax = nullptr;
+    if (int rc = dev_upload(h, &d_cls_of, cls_of.data(), cls_of.size())) return rc;
+    if (int rc = dev_upload(h, &d_cmax, cmax.data(), cmax.size())) return rc;
+    if (int rc = dev_alloc(h, &d_cls, (nv + 3) / 4)) return rc;
+    const int blocks = (int)std::min<size_t>((size_t)h->sm_count * 8, ((nv + 3) / 4 + 255) / 256);
+    if (label_bytes == 1)
+      class_pack_kernel<uint8_t><<<blocks, 256, 0, h->stream>>>(dl, nv, d_cls_of, d_cls);
+    else
+      class_pack_kernel<uint16_t><<<blocks, 256, 0, h->stream>>>(reinterpret_cast<const uint16_t *>(dl), nv, d_cls_of, d_cls);
+    CU(cudaGetLastError());
+    P.cls = d_cls;
+    P.cmax = d_cmax;
+  }
   CU(cudaStreamSynchronize(h->stream));
   h->d_labels = dl;
   P.labels = dl;

@@ -90,6 +90,9 @@ constexpr int kWoodcockK = 4;              // tentative collisions per Woodcock 
 #ifndef GB2_VWIDTH
 #define GB2_VWIDTH 1
 #endif
+#ifndef GB2_CLASSVOL
+#define GB2_CLASSVOL 0                    // 1: Woodcock phase with early rejection by a 2-bit material-class volume (Params::cls); measured: -7 %
+#endif
 #ifndef GB2_CHAIN
 // Phase chaining: when at least GB2_CHAIN_MIN lanes of a warp leave a single-slot phase for the world phase or the
 // end-of-photon phase, the warp runs that phase for them at once instead of sending them through the queues (up to
@@ -215,6 +218,16 @@ struct Params {
   float half[3], inv_sp[3], sp[3], hs[3];   // hs = n / 2: voxel coordinate = p * inv_sp + hs
   Affine w2v;
   const void *labels;
+  // Material CLASS volume: 2 bits per voxel (4 voxels per byte, x fastest), the materials present in the volume sorted
+  // into four classes by density; cmax[ie] = the largest attenuation coefficient of each class at energy node ie.
+  // A tentative collision whose acceptance variate exceeds the bound of its voxel's class is rejected whatever the
+  // material is -- the same decision the exact test takes -- and needs neither the label nor the attenuation
+  // look-up; only the others (every accepted collision among them) gather the label.  With at most four materials
+  // present the class IS the material (cls_exact) and the label volume is not read by the Woodcock phase at all.
+  const unsigned char *cls;
+  const float4 *cmax;            // [ne]
+  int cls_exact;
+  int cls_mat[4];
   // The homogeneous shell of the image volume: every voxel outside the box (centre tc, half size th, volume frame)
   // carries the label shell_mat (the air around a patient).  A Woodcock call that starts out there first crosses
   // the shell analytically with the optical depth of its first flight (see volume_gather_labels).
@@ -1577,7 +1590,12 @@ __device__ __forceinline__ void volume_gather_labels(const Params &P, Smem &S, c
       flat = (unsigned)ix + (unsigned)P.n[0] * ((unsigned)iy + (unsigned)P.n[1] * (unsigned)iz);
       c.inb |= 1u << k;
     }
+#if GB2_CLASSVOL
+    c.lab[k] = (int)__ldg(P.cls + (flat >> 2));   // the byte of four class codes
+    c.mu[k] = __uint_as_float(flat);              // parked until volume_gather_mu needs it
+#else
     c.lab[k] = (int)__ldg(labels + flat);
+#endif
   }
 }
 
@@ -1587,8 +1605,42 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
 __device__ __forceinline__ void prefetch_l1(const void *p) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
+template <typename LabelT>
 __device__ __forceinline__ void volume_gather_mu(const Params &P, VCall &c) {
   const float2 *__restrict__ murow = P.mu2 + (size_t)c.ie * P.nmat;
+#if GB2_CLASSVOL
+  {
+    // class bounds at the photon's energy, a hair above the interpolated maxima (the interpolation of the maxima
+    // bounds the interpolated coefficient of every material of the class up to rounding: 1e-6 covers it)
+    const float4 q0 = __ldg(P.cmax + c.ie), q1 = __ldg(P.cmax + c.ie + 1);
+    const float cm0 = __fmaf_rn(c.fe, q1.x - q0.x, q0.x) * 1.000001f, cm1 = __fmaf_rn(c.fe, q1.y - q0.y, q0.y) * 1.000001f;
+    const float cm2 = __fmaf_rn(c.fe, q1.z - q0.z, q0.z) * 1.000001f, cm3 = __fmaf_rn(c.fe, q1.w - q0.w, q0.w) * 1.000001f;
+    const LabelT *__restrict__ labels = reinterpret_cast<const LabelT *>(P.labels);
+#pragma unroll
+    for (int k = 0; k < kWoodcockK; ++k) {
+      const unsigned flat = __float_as_uint(c.mu[k]);
+      const int cl = (c.lab[k] >> ((flat & 3u) * 2u)) & 3;
+      const float bound = cl == 0 ? cm0 : (cl == 1 ? cm1 : (cl == 2 ? cm2 : cm3));
+      const float t = u32_to_uniform(c.racc[k]) * c.maj;          // the acceptance variate of volume_decide
+      const bool need = ((c.inb >> k) & 1u) && t <= bound;
+      int lab = -1;
+      if (need) {
+        if (P.cls_exact) lab = cl == 0 ? P.cls_mat[0] : (cl == 1 ? P.cls_mat[1] : (cl == 2 ? P.cls_mat[2] : P.cls_mat[3]));
+        else lab = (int)__ldg(labels + flat);
+      }
+      c.lab[k] = lab;
+    }
+#pragma unroll
+    for (int k = 0; k < kWoodcockK; ++k) {
+      float mu = 0.0f;   // a sure rejection: t <= 0 never holds
+      if (c.lab[k] >= 0) {
+        const float2 v = __ldg(murow + c.lab[k]);
+        mu = __fmaf_rn(c.fe, v.y - v.x, v.x);
+      }
+      c.mu[k] = mu;
+    }
+  }
+#else
 #pragma unroll
   for (int k = 0; k < kWoodcockK; ++k) {
     const float2 v = __ldg(murow + c.lab[k]);
@@ -1602,6 +1654,7 @@ __device__ __forceinline__ void volume_gather_mu(const Params &P, VCall &c) {
 #endif
     c.mu[k] = __fmaf_rn(c.fe, v.y - v.x, v.x);
   }
+#endif
 }
 
 template <int kMode>
@@ -2321,7 +2374,7 @@ __global__ void __launch_bounds__(threads_of<is_tle(kMode)>(), GB2_MIN_CTAS) tra
         if (slot[w] >= 0) volume_gather_labels<LabelT, kHasVS ? 0 : 2>(P, S, s_maj, slot[w], vc[w]);
 #pragma unroll
       for (int w = 0; w < kVWidth; ++w)
-        if (slot[w] >= 0) volume_gather_mu(P, vc[w]);
+        if (slot[w] >= 0) volume_gather_mu<LabelT>(P, vc[w]);
 #pragma unroll
       for (int w = 0; w < kVWidth; ++w)
         if (slot[w] >= 0) next[w] = volume_decide<kMode>(P, S, slot[w], slot_base + slot[w], vc[w], c_tent);
@@ -2329,7 +2382,7 @@ __global__ void __launch_bounds__(threads_of<is_tle(kMode)>(), GB2_MIN_CTAS) tra
       if (slot[0] >= 0) {
         VCall vc;
         volume_gather_labels<LabelT, 1>(P, S, s_maj, slot[0], vc);
-        volume_gather_mu(P, vc);
+        volume_gather_mu<LabelT>(P, vc);
         next[0] = volume_decide<kMode>(P, S, slot[0], slot_base + slot[0], vc, c_tent);
       }
     } else {

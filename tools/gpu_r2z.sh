@@ -21,8 +21,15 @@ for cfg in c3 c3_hit_random c4; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:transport_kernel -s 1 -c 1 \
       -o gpurun_out/${T}_transport_${cfg} -f python tools/profile_run.py --config $cfg --histories 100000000 --launches 1 --warmup 1 > gpurun_out/${T}_ncu_${cfg}.log 2>&1
   tail -1 gpurun_out/${T}_ncu_${cfg}.log
+  # summarised on the box: the four reports together exceed what gpurun brings back
+  python tools/ncu_summary.py gpurun_out/${T}_transport_${cfg}.ncu-rep gpurun_out/${T}_transport_${cfg}_ncu.md --histories 1e8 \
+      --title "${T} ${cfg} (kernel of the bench line, 1e8 histories)" --traffic-json gpurun_out/${T}_traffic.json --key ${cfg} > /dev/null
+  [ "$cfg" = c3 ] || rm -f gpurun_out/${T}_transport_${cfg}.ncu-rep
 done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:transport_kernel -s 1 -c 1 \
     -o gpurun_out/${T}_transport_c3tle -f python tools/profile_run.py --config c3tle --histories 4000000 --launches 1 --warmup 1 > gpurun_out/${T}_ncu_c3tle.log 2>&1
 tail -1 gpurun_out/${T}_ncu_c3tle.log
+python tools/ncu_summary.py gpurun_out/${T}_transport_c3tle.ncu-rep gpurun_out/${T}_transport_c3tle_ncu.md --histories 4e6 \
+    --title "${T} c3tle (TLE with squares, record variant, 4e6 histories)" --traffic-json gpurun_out/${T}_traffic.json --key c3tle > /dev/null
+rm -f gpurun_out/${T}_transport_c3tle.ncu-rep
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/${T}_smi.txt; nproc >> gpurun_out/${T}_smi.txt

@@ -74,3 +74,37 @@ def test_script_level_couch_under_the_ct(tmp_path):
     couch.translation = [0, 0, 0]                  # now inside the CT
     with pytest.raises(Exception, match="overlaps"):
         sim.run(_backend=OracleBackend)
+
+
+def test_detector_slab_with_phase_space_actor(tmp_path):
+    """a Box of its own material that also carries a PhaseSpaceActor: scoring plane AND material region (the crossing
+    is reported as the plane's event; the medium follows from the position)"""
+    from test_host_api import ct_sim
+    from oracle_backend import OracleBackend
+    res = {}
+    for mat in ("G4_AIR", "G4_WATER"):
+        sim, ct, src, dose, hu = ct_sim(tmp_path / mat, n_primaries=4000)
+        slab = sim.add_volume("Box", "detector")
+        slab.size = [400 * mm, 400 * mm, 40 * mm]
+        slab.translation = [0, 0, -250 * mm]
+        slab.material = mat
+        ph = sim.add_actor("PhaseSpaceActor", "phsp")
+        ph.attached_to = slab
+        ph.attributes = ["KineticEnergy", "PrePosition", "PreDirection", "EventID"]
+        ph.steps_to_store = "entering exiting"
+        ph.max_rows = 40000                      # entering + exiting + what the CT scatters back
+        ph.output_filename = "det.npz"
+        sim.run(_backend=OracleBackend)
+        res[mat] = (ph, dose.edep.image.array.sum())
+    (pa, ea), (pw, ew) = res["G4_AIR"], res["G4_WATER"]
+    # every primary enters the slab from below in both cases; fewer leave it unscattered when it is made of water
+    for ph in (pa, pw):
+        z = ph.data["PrePosition_Z"]
+        first = (np.abs(z + 270.0) < 0.1) & (ph.data["PreDirection_Z"] > 0.999999)
+        assert 3975 <= first.sum() <= 4000        # a few interact in the 130 mm of air on the way
+    def straight_out(ph):
+        z = ph.data["PrePosition_Z"]
+        return ((np.abs(z + 230.0) < 0.1) & (ph.data["PreDirection_Z"] > 0.999999)).sum()
+    assert straight_out(pa) > 3980
+    assert 0.3 * 4000 < straight_out(pw) < 0.6 * 4000      # 40 mm of water at 40 ... 120 keV
+    assert ew < 0.75 * ea

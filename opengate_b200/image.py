@@ -68,7 +68,7 @@ def create_3d_image(size, spacing, origin=None, pixel_type="float", allocate=Tru
 
 
 def read_image(path):
-    """Read .mhd/.mha (uncompressed) or .npy."""
+    """Read .mhd/.mha (raw or zlib-compressed element data, local or in a separate .raw / .zraw file) or .npy."""
     path = str(path)
     if path.endswith(".npy"):
         return Image(np.load(path))
@@ -89,8 +89,7 @@ def read_image(path):
             if k == "ElementDataFile":
                 offset = f.tell()
                 break
-    if hdr.get("CompressedData", "False") == "True":
-        fatal("Compressed MetaImage is not supported")
+    compressed = hdr.get("CompressedData", "False") == "True"   # ITK: the element data as ONE zlib stream (.zraw)
     ndim = int(hdr.get("NDims", 3))
     dims = [int(x) for x in hdr["DimSize"].split()]
     if ndim != 3:
@@ -102,10 +101,21 @@ def read_image(path):
     if hdr["ElementDataFile"] == "LOCAL":
         with open(path, "rb") as f:
             f.seek(offset)
-            data = np.frombuffer(f.read(n * dt.itemsize), dtype=dt)
+            blob = f.read() if compressed else f.read(n * dt.itemsize)
     else:
         raw = os.path.join(os.path.dirname(path), hdr["ElementDataFile"])
-        data = np.fromfile(raw, dtype=dt, count=n)
+        with open(raw, "rb") as f:
+            blob = f.read() if compressed else f.read(n * dt.itemsize)
+    if compressed:
+        import zlib
+        csize = int(hdr.get("CompressedDataSize", len(blob)))
+        try:
+            blob = zlib.decompress(blob[:csize])
+        except zlib.error as why:
+            fatal(f"Cannot decompress the element data of {path}: {why}")
+    if len(blob) < n * dt.itemsize:
+        fatal(f"{path}: element data hold {len(blob)} bytes, the header asks for {n * dt.itemsize}")
+    data = np.frombuffer(blob, dtype=dt, count=n)
     arr = data.reshape(dims[2], dims[1], dims[0]).astype(dt.newbyteorder("="), copy=False)
     spacing = [float(x) for x in hdr.get("ElementSpacing", "1 1 1").split()]
     origin = [float(x) for x in hdr.get("Offset", hdr.get("Position", "0 0 0")).split()]
@@ -115,8 +125,9 @@ def read_image(path):
     return Image(arr, spacing, origin, direction)
 
 
-def write_image(img, path):
-    """Write .mhd + .raw (or .mha with local data), or .npy."""
+def write_image(img, path, compressed=False):
+    """Write .mhd + .raw (or .mha with local data), or .npy; compressed: element data as one zlib stream
+    (.mhd + .zraw, CompressedData = True, as ITK's MetaImageIO writes it)."""
     path = str(path)
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
     if path.endswith(".npy"):
@@ -126,12 +137,17 @@ def write_image(img, path):
     if arr.dtype not in _NP_TO_MET:
         fatal(f"Cannot write dtype {arr.dtype} as MetaImage")
     local = path.endswith(".mha")
-    raw_name = "LOCAL" if local else os.path.basename(path)[:-4] + ".raw"
+    raw_name = "LOCAL" if local else os.path.basename(path)[:-4] + (".zraw" if compressed else ".raw")
+    payload = arr.tobytes()
+    if compressed:
+        import zlib
+        payload = zlib.compress(payload, 2)
     nx, ny, nz = img.size
     tm = img.direction.T.reshape(-1)
     hdr = (
         "ObjectType = Image\nNDims = 3\nBinaryData = True\nBinaryDataByteOrderMSB = False\n"
-        "CompressedData = False\n"
+        f"CompressedData = {'True' if compressed else 'False'}\n"
+        + (f"CompressedDataSize = {len(payload)}\n" if compressed else "") +
         f"TransformMatrix = {' '.join(repr(float(x)) for x in tm)}\n"
         f"Offset = {' '.join(repr(float(x)) for x in img.origin)}\n"
         "CenterOfRotation = 0 0 0\nAnatomicalOrientation = RAI\n"
@@ -143,9 +159,10 @@ def write_image(img, path):
     with open(path, "wb") as f:
         f.write(hdr.encode("latin-1"))
         if local:
-            f.write(arr.tobytes())
+            f.write(payload)
     if not local:
-        arr.tofile(os.path.join(os.path.dirname(os.path.abspath(path)), raw_name))
+        with open(os.path.join(os.path.dirname(os.path.abspath(path)), raw_name), "wb") as f:
+            f.write(payload)
 
 
 def compute_image_3D_CDF(image_or_array):

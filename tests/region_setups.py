@@ -4,7 +4,7 @@ import numpy as np
 from opengate_b200 import abi, setups
 
 
-def slab_in_front(n=20000, thickness=40.0, tilt_deg=0.0, energy=0.2, material=0, planes=True):
+def slab_in_front(n=20000, thickness=40.0, tilt_deg=0.0, energy=0.2, material=0, planes=True, slab_is_plane=False):
     """c1's water box and pencil beam (source moved back to z = -400 mm); a slab of `material` (0 = water, 1 = air)
     across the beam at z = -300 mm, tilted about x; two thin scoring planes of world material before and behind it."""
     S = setups.make_c1(n_primaries=n, grid=(50, 50, 50), spacing_mm=6.0, energy=energy,
@@ -19,6 +19,9 @@ def slab_in_front(n=20000, thickness=40.0, tilt_deg=0.0, energy=0.2, material=0,
     w2b[:, :3] = R.T
     w2b[:, 3] = -R.T @ t
     S.regions = [abi.make_region_desc((150.0, 150.0, thickness / 2), w2b, material)]
+    if slab_is_plane:
+        # the slab itself carries a phase-space actor (entering + exiting): region and scoring plane at once
+        S.phsp.append(abi.make_phsp_desc((150.0, 150.0, thickness / 2), w2b, abi.PHSP_ENTERING | abi.PHSP_EXITING, 8 * n + 16))
     if planes:
         for z in (-390.0, -200.0):
             B = np.zeros((3, 4))

@@ -558,3 +558,19 @@ def test_angular_histogram_and_confine_like_the_reference_tests(tmp_path):
     src2.position.confine = "nowhere"
     with pytest.raises(Exception, match="confine"):
         src2.resolve_and_validate_config(sim.run_timing_intervals)
+
+
+def test_compressed_metaimage_round_trip(tmp_path):
+    """CT images often come as .mhd + .zraw (ITK MetaImageIO: the element data as one zlib stream): read and written"""
+    a = np.random.default_rng(3).integers(-1000, 2000, (6, 8, 10)).astype(np.int16)
+    img = gimage.Image(a, (0.5, 0.6, 0.7), (1.0, 2.0, 3.0))
+    for name in ("ct.mhd", "ct.mha"):
+        gimage.write_image(img, tmp_path / name, compressed=True)
+        assert "CompressedData = True" in open(tmp_path / name, "rb").read(400).decode("latin-1")
+        r = gimage.read_image(tmp_path / name)
+        assert r.array.dtype == a.dtype and np.array_equal(r.array, a)
+        assert np.allclose(r.spacing, img.spacing) and np.allclose(r.origin, img.origin)
+    assert (tmp_path / "ct.zraw").exists()
+    (tmp_path / "ct.zraw").write_bytes(b"not zlib")
+    with pytest.raises(Exception, match="decompress"):
+        gimage.read_image(tmp_path / "ct.mhd")

@@ -92,3 +92,26 @@ def test_rejects_what_it_cannot_write(tmp_path):
     (tmp_path / "n.root").write_bytes(b"nope" * 100)
     with pytest.raises(ValueError):
         rootio.read_tree(tmp_path / "n.root")
+
+
+def test_cross_check_with_uproot_where_installed(tmp_path):
+    """The one check this image cannot run (no ROOT, no uproot): files of the own writer opened by uproot and uproot's
+    files opened by the own reader.  Runs wherever uproot is installed."""
+    uproot = pytest.importorskip("uproot")
+    cols = columns(3000)
+    cols.pop("flag")                      # uproot writes bool branches with its own leaf conventions: numbers only here
+    path = tmp_path / "ours.root"
+    rootio.write_tree(path, "PhaseSpace", cols, compression=1, basket_entries=1000)
+    with uproot.open(path) as f:
+        t = f["PhaseSpace"]
+        assert t.num_entries == 3000 and set(t.keys()) == set(cols)
+        got = t.arrays(library="np")
+        for k, v in cols.items():
+            assert np.array_equal(got[k], v), k
+    theirs = tmp_path / "theirs.root"
+    with uproot.recreate(theirs, compression=uproot.ZLIB(1)) as f:
+        f["PhaseSpace"] = cols
+    out, avail = rootio.read_tree(theirs)
+    assert set(avail) == set(cols)
+    for k, v in cols.items():
+        assert np.array_equal(out[k], v), k

@@ -62,7 +62,8 @@ def _half_size(v):
 
 
 def _boxes_overlap(a, b):
-    """separating-axis test of two placed boxes (15 axes): True when they share volume"""
+    """separating-axis test of two placed boxes (15 axes): True when they share volume (boxes that merely touch,
+    e.g. a couch under the image volume, do not: 1e-6 mm of slack)"""
     Ra, ta = a.world_transform()
     Rb, tb = b.world_transform()
     ha, hb = _half_size(a), _half_size(b)
@@ -70,16 +71,16 @@ def _boxes_overlap(a, b):
     t = Ra.T @ (tb - ta)
     A = np.abs(R) + 1e-12
     for i in range(3):
-        if abs(t[i]) > ha[i] + hb @ A[i]:
+        if abs(t[i]) > ha[i] + hb @ A[i] - 1e-6:
             return False
     for j in range(3):
-        if abs(t @ R[:, j]) > ha @ A[:, j] + hb[j]:
+        if abs(t @ R[:, j]) > ha @ A[:, j] + hb[j] - 1e-6:
             return False
     for i in range(3):
         for j in range(3):
             ra = ha[(i + 1) % 3] * A[(i + 2) % 3, j] + ha[(i + 2) % 3] * A[(i + 1) % 3, j]
             rb = hb[(j + 1) % 3] * A[i, (j + 2) % 3] + hb[(j + 2) % 3] * A[i, (j + 1) % 3]
-            if abs(t[(i + 2) % 3] * R[(i + 1) % 3, j] - t[(i + 1) % 3] * R[(i + 2) % 3, j]) > ra + rb:
+            if abs(t[(i + 2) % 3] * R[(i + 1) % 3, j] - t[(i + 1) % 3] * R[(i + 2) % 3, j]) > ra + rb + 1e-9:
                 return False
     return True
 

@@ -4,7 +4,7 @@ import numpy as np
 from opengate_b200 import abi, setups
 
 
-def slab_in_front(n=20000, thickness=40.0, tilt_deg=0.0, energy=0.2, material=0, planes=True, slab_is_plane=False):
+def slab_in_front(n=20000, thickness=40.0, tilt_deg=0.0, energy=0.2, material=0, planes=True, slab_is_plane=False, touching=False):
     """c1's water box and pencil beam (source moved back to z = -400 mm); a slab of `material` (0 = water, 1 = air)
     across the beam at z = -300 mm, tilted about x; two thin scoring planes of world material before and behind it."""
     S = setups.make_c1(n_primaries=n, grid=(50, 50, 50), spacing_mm=6.0, energy=energy,
@@ -14,7 +14,8 @@ def slab_in_front(n=20000, thickness=40.0, tilt_deg=0.0, energy=0.2, material=0,
     S.sources = [(s, keep)]
     c, sn = np.cos(np.radians(tilt_deg)), np.sin(np.radians(tilt_deg))
     R = np.array([[1.0, 0.0, 0.0], [0.0, c, -sn], [0.0, sn, c]])      # box -> world
-    t = np.array([0.0, 0.0, -300.0])
+    # touching: the slab lies flat on the -z face of the water box (z = -150 mm), like a couch under a phantom
+    t = np.array([0.0, 0.0, -150.0 - thickness / 2 if touching else -300.0])
     w2b = np.zeros((3, 4))
     w2b[:, :3] = R.T
     w2b[:, 3] = -R.T @ t

@@ -108,3 +108,20 @@ def test_detector_slab_with_phase_space_actor(tmp_path):
     assert straight_out(pa) > 3980
     assert 0.3 * 4000 < straight_out(pw) < 0.6 * 4000      # 40 mm of water at 40 ... 120 keV
     assert ew < 0.75 * ea
+
+
+def test_couch_touching_the_phantom():
+    """a slab that lies flat on the face of the phantom (its exit face IS the entry face of the image volume)"""
+    n = 20000
+    S = slab_in_front(n, 30.0, 0.0, energy=0.1, touching=True)
+    o, (sids, dids, pids) = run(S, n)
+    R = slab_in_front(n, 30.0, 0.0, energy=0.1, touching=True)
+    R.regions = []
+    r, (_, rd, _) = run(R, n)
+    a, b = o.dose_grid(dids[0], abi.GRID_EDEP), r.dose_grid(rd[0], abi.GRID_EDEP)
+    T = S.tables
+    ie = np.searchsorted(T.energy, 0.1) - 1
+    # the primary fluence that reaches the water box is attenuated by 30 mm of water; scatter from the couch adds some
+    att = np.exp(-T.mu_total[0, ie] * 30.0)
+    assert att * 0.98 < a.sum() / b.sum() < att * 1.35
+    assert o.stats()["histories"] == n and o.stats()["escaped"] > 0

@@ -601,7 +601,8 @@ def test_ten_billion_histories_launch_splitting_and_64_bit_counters(cuda_require
 
 @pytest.mark.parametrize("kw", [dict(thickness=40.0, tilt_deg=0.0), dict(thickness=25.0, tilt_deg=30.0),
                                 dict(thickness=30.0, tilt_deg=-15.0, energy=0.08),
-                                dict(thickness=25.0, tilt_deg=20.0, energy=0.1, slab_is_plane=True)])
+                                dict(thickness=25.0, tilt_deg=20.0, energy=0.1, slab_is_plane=True),
+                                dict(thickness=30.0, energy=0.1, touching=True)])
 def test_box_regions_match_oracle(cuda_required, kw):
     """a homogeneous Box of its own material in the world (couch / detector slab), scoring planes before and behind:
     counters, phase-space rows and grids as the oracle (general kernel variant)"""

@@ -679,12 +679,7 @@ class PhaseSpaceActor(ActorBase):
             # a flat TTree named after the actor, one branch per column (GateDigiCollectionsRootManager: D -> double,
             # I -> int, 3 -> name_X / _Y / _Z), written by the package's own ROOT writer (rootio.py)
             from . import rootio
-            cols = {k: v for k, v in self.data.items() if v.dtype.name in rootio.LEAVES}
-            dropped = [k for k in self.data if k not in cols]
-            if dropped:
-                warning(f"PhaseSpaceActor '{self.name}': string column(s) {dropped} are not written to the ROOT file "
-                        f"(PDGCode carries the particle type)")
-            rootio.write_tree(path, self.name, cols, title=f"PhaseSpaceActor {self.name}")
+            rootio.write_tree(path, self.name, self.data, title=f"PhaseSpaceActor {self.name}")
             return
         np.savez(path, **self.data)
 

@@ -11,8 +11,8 @@ this module states the container itself, from the published description of the f
     [file header, 100 bytes][top directory record][basket records ...][TTree record][StreamerInfo record]
     [keys list][free-segments record]
 
-* `write_tree(path, name, columns)`: float64 / float32 / int32 / int64 / int16 / int8 / bool columns -> one branch and
-  one leaf each, data in basket records of at most `BASKET_ENTRIES` entries, optionally zlib-compressed ("ZL"
+* `write_tree(path, name, columns)`: float64 / float32 / int32 / int64 / int16 / int8 / bool / string columns -> one
+  branch and one leaf each (strings: `TLeafC` with an entry-offset table per basket), data in basket records of at most `BASKET_ENTRIES` entries, optionally zlib-compressed ("ZL"
   blocks).  Files beyond 2 GB switch to the 64-bit seek layout (header version + 1000000, key version + 1000).
   Class versions are the ones ROOT 6.14 ... 6.3x compile in (a StreamerInfo list is present but empty).
 * `read_tree(path, name=None, keys=None)`: the same subset back -- any uncompressed, zlib- or lzma-compressed flat
@@ -189,8 +189,10 @@ def write_tree(path, tree_name, columns, title="", compression=0, basket_entries
         a = np.asarray(v)
         if a.ndim != 1:
             raise ValueError(f"branch '{k}': only one number per entry (got shape {a.shape})")
-        if a.dtype.name not in LEAVES:
-            raise ValueError(f"branch '{k}': dtype {a.dtype} has no ROOT leaf here ({sorted(LEAVES)})")
+        if a.dtype.kind in "US":
+            a = np.char.encode(a, "utf-8") if a.dtype.kind == "U" else a     # -> bytes: a TLeafC branch
+        elif a.dtype.name not in LEAVES:
+            raise ValueError(f"branch '{k}': dtype {a.dtype} has no ROOT leaf here ({sorted(LEAVES)} or strings)")
         if n is None:
             n = a.shape[0]
         if a.shape[0] != n:
@@ -214,20 +216,44 @@ def write_tree(path, tree_name, columns, title="", compression=0, basket_entries
         # ---- baskets: one TKey record each, class TBasket, name = branch, title = tree
         branches = []
         for k, a in cols.items():
-            cls, suffix, size, _ = LEAVES[a.dtype.name]
-            be = a.astype(LEAF_DTYPE[cls], copy=False) if cls != "TLeafO" else a
+            strings = a.dtype.kind == "S"
+            if strings:
+                # TLeafC: every entry is one length byte (255 + int32 for longer strings) and the characters; the
+                # basket ends with the table of entry offsets (TBasket::WriteBuffer: count, fKeylen + offset of each
+                # entry, one spare word), fLast pointing at that table
+                cls, suffix, size, uns = "TLeafC", "C", 1, False
+                maxlen = max((len(x) for x in a), default=0)
+            else:
+                cls, suffix, size, uns = LEAVES[a.dtype.name]
+                be = a.astype(LEAF_DTYPE[cls], copy=False) if cls != "TLeafO" else a
             keylen = _key_length("TBasket", k, tree_name, big) + 2 + 4 + 4 + 4 + 4 + 1
-            info = {"name": k, "cls": cls, "title": f"{k}/{suffix}", "size": size, "unsigned": LEAVES[a.dtype.name][3],
-                    "seek": [], "nbytes": [], "first": [], "tot": 0, "zip": 0}
+            info = {"name": k, "cls": cls, "title": f"{k}/{suffix}", "size": size, "unsigned": uns,
+                    "seek": [], "nbytes": [], "first": [], "tot": 0, "zip": 0,
+                    "flen": (maxlen + 1) if strings else 1, "offset_len": 1000 if strings else 0}
             for e0 in range(0, n, basket_entries):
                 e1 = min(n, e0 + basket_entries)
-                data = be[e0:e1].tobytes()
-                z = _compress(data, compression) if compression else data
+                tail = b""
+                if strings:
+                    parts, offs, pos = [], [], 0
+                    for x in a[e0:e1]:
+                        x = bytes(x)
+                        offs.append(pos)
+                        enc = (bytes([len(x)]) if len(x) < 255 else b"\xff" + struct.pack(">i", len(x))) + x
+                        parts.append(enc)
+                        pos += len(enc)
+                    data = b"".join(parts)
+                else:
+                    data = be[e0:e1].tobytes()
                 pos = f.tell()
                 kbig = big or pos > START_BIG
                 kl = keylen + (8 if kbig and not big else 0)
+                last = kl + len(data)
+                if strings:
+                    tail = struct.pack(f">i{e1 - e0 + 1}i", e1 - e0 + 1, *[kl + o for o in offs], 0)
+                    data += tail
+                z = _compress(data, compression) if compression else data
                 hdr = _key_header(kl + len(z), len(data), kl, pos, 100, "TBasket", k, tree_name, now, cycle=0, big=kbig)
-                hdr += struct.pack(">hiiiib", 3, 32000, size, e1 - e0, kl + len(data), 0)
+                hdr += struct.pack(">hiiiib", 3, 32000, 1000 if strings else size, e1 - e0, last, 0)
                 assert len(hdr) == kl
                 f.write(hdr)
                 f.write(z)
@@ -260,9 +286,12 @@ def write_tree(path, tree_name, columns, title="", compression=0, basket_entries
                 p1 = b.begin(1)                                       # TLeafX
                 p2 = b.begin(2)                                       # TLeaf
                 b.tnamed(info["name"], info["name"])
-                b.add("iii??I", 1, info["size"], 0, False, info["unsigned"], 0)   # fLen fLenType fOffset fIsRange fIsUnsigned fLeafCount
+                b.add("iii??I", info["flen"], info["size"], 0, False, info["unsigned"], 0)   # fLen fLenType fOffset fIsRange fIsUnsigned fLeafCount
                 b.end(p2)
-                b.raw(struct.pack(LEAF_MINMAX[info["cls"]], 0, 0))
+                if info["cls"] == "TLeafC":
+                    b.add("ii", 0, info["flen"])                      # fMinimum, fMaximum (longest string + 1)
+                else:
+                    b.raw(struct.pack(LEAF_MINMAX[info["cls"]], 0, 0))
                 b.end(p1)
 
             def payload(b):
@@ -271,7 +300,7 @@ def write_tree(path, tree_name, columns, title="", compression=0, basket_entries
                 p1 = b.begin(13)                                      # TBranch
                 b.tnamed(info["name"], info["title"])
                 p2 = b.begin(2); b.add("hh", 0, 1001); b.end(p2)      # TAttFill
-                b.add("iiiiq", fcompress, 32000, 0, nb, n)            # fCompress fBasketSize fEntryOffsetLen fWriteBasket fEntryNumber
+                b.add("iiiiq", fcompress, 32000, info["offset_len"], nb, n)   # fCompress fBasketSize fEntryOffsetLen fWriteBasket fEntryNumber
                 b.iofeatures()
                 b.add("iiiqqqq", 0, maxb, 0, n, 0, info["tot"], info["zip"])   # fOffset fMaxBaskets fSplitLevel fEntries fFirstEntry fTotBytes fZipBytes
                 b.objarray([])                                        # fBranches
@@ -481,10 +510,36 @@ def _read_branch(c, cname, ref, classes):
     c.tstring()
     if sub:
         raise ValueError(f"branch '{name}' has sub-branches: not a flat tree")
-    if len(leaves) != 1 or not isinstance(leaves[0], dict) or leaves[0]["count"] != 0 or leaves[0]["class"] not in LEAF_DTYPE:
+    if len(leaves) != 1 or not isinstance(leaves[0], dict) or leaves[0]["count"] != 0 or \
+            (leaves[0]["class"] not in LEAF_DTYPE and leaves[0]["class"] != "TLeafC"):
         raise ValueError(f"branch '{name}': only one fixed-size leaf per branch is supported")
     return {"name": name, "title": title, "leaf": leaves[0], "n_baskets": write_basket, "entries": entries,
             "basket_bytes": arrays[0], "basket_entry": arrays[1], "basket_seek": arrays[2]}
+
+
+def _read_strings(f, b, entries):
+    """a TLeafC branch: the entries of a basket lie between the offsets of its table (after fLast), each one a length
+    byte (255 + int32 for long strings) and the characters"""
+    vals = []
+    for i in range(b["n_baskets"]):
+        f.seek(int(b["basket_seek"][i]))
+        raw = f.read(int(b["basket_bytes"][i]))
+        bc = _Cur(raw)
+        bk = _read_key(bc)
+        _bver, _bufsize, _nevsize, nev, last = bc.get("hiiii")
+        data = _decompress(raw[bk["keylen"]:], bk["objlen"])
+        border = last - bk["keylen"]
+        table = np.frombuffer(data, ">i4", offset=border)
+        offs = (table[1:1 + nev].astype(np.int64) - bk["keylen"]).tolist() + [border]
+        for j in range(nev):
+            s = data[offs[j]:offs[j + 1]]
+            k = 1
+            if s[:1] == b"\xff":
+                k = 5
+            vals.append(bytes(s[k:]).decode("utf-8", "replace"))
+    if len(vals) != entries:
+        raise ValueError(f"branch '{b['name']}': {len(vals)} entries read, tree has {entries}")
+    return np.array(vals, dtype=str) if vals else np.zeros(0, dtype="U1")
 
 
 def list_trees(path):
@@ -555,6 +610,9 @@ def read_tree(path, name=None, keys=None):
             if keys is not None and b["name"] not in keys:
                 continue
             leaf = b["leaf"]
+            if leaf["class"] == "TLeafC":
+                out[b["name"]] = _read_strings(f, b, entries)
+                continue
             if leaf["class"] not in LEAF_DTYPE:
                 raise ValueError(f"branch '{b['name']}': leaf class {leaf['class']} is not supported")
             dt = np.dtype(LEAF_DTYPE[leaf["class"]])

@@ -574,3 +574,22 @@ def test_compressed_metaimage_round_trip(tmp_path):
     (tmp_path / "ct.zraw").write_bytes(b"not zlib")
     with pytest.raises(Exception, match="decompress"):
         gimage.read_image(tmp_path / "ct.mhd")
+
+
+def test_particle_name_column_reaches_the_root_file(tmp_path):
+    """ParticleName (a string attribute, `S` column of the reference's digi collections) is written as a TLeafC branch"""
+    from opengate_b200 import rootio
+    sim, ct, src, dose, hu = ct_sim(tmp_path, n_primaries=500)
+    plane = sim.add_volume("Box", "plane")
+    plane.size = [400 * mm, 400 * mm, 2 * mm]
+    plane.translation = [0, 0, -300 * mm]
+    plane.material = "G4_AIR"
+    ph = sim.add_actor("PhaseSpaceActor", "phsp")
+    ph.attached_to = plane
+    ph.attributes = ["KineticEnergy", "ParticleName", "PDGCode", "EventID"]
+    ph.output_filename = "names.root"
+    sim.run(_backend=OracleBackend)
+    cols, avail = rootio.read_tree(tmp_path / "out" / "names.root")
+    assert avail == ["KineticEnergy", "ParticleName", "PDGCode", "EventID"]
+    assert len(cols["ParticleName"]) == ph.total_number_of_entries >= 490
+    assert set(cols["ParticleName"].tolist()) == {"gamma"} and set(cols["PDGCode"].tolist()) == {22}

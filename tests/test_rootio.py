@@ -16,6 +16,7 @@ def columns(n, seed=0):
         "PrePosition_X": r.normal(size=n), "PrePosition_Y": r.normal(size=n), "PrePosition_Z": r.normal(size=n),
         "big": r.integers(-2**62, 2**62, n), "PDGCode": np.full(n, 22, np.int32), "flag": r.integers(0, 2, n).astype(bool),
         "s16": r.integers(-30000, 30000, n).astype(np.int16), "u8": r.integers(0, 255, n).astype(np.uint8),
+        "ParticleName": np.array(["gamma", "e-", "", "x" * 300])[r.integers(0, 4, n)] if n else np.zeros(0, dtype="U5"),
     }
 
 
@@ -29,7 +30,7 @@ def test_round_trip(tmp_path, n, compression, basket, big):
     out, avail = rootio.read_tree(path)
     assert avail == list(cols)
     for k, v in cols.items():
-        assert out[k].dtype == v.dtype and np.array_equal(out[k], v), k
+        assert (out[k].dtype == v.dtype or v.dtype.kind == "U") and np.array_equal(out[k], v), k
     sub, _ = rootio.read_tree(path, "PhaseSpace", keys=["Weight", "big", "nope"])
     assert list(sub) == ["Weight", "big"]
     with pytest.raises(KeyError):
@@ -88,7 +89,7 @@ def test_rejects_what_it_cannot_write(tmp_path):
     with pytest.raises(ValueError):
         rootio.write_tree(tmp_path / "a.root", "T", {"x": np.zeros(3), "y": np.zeros(4)})
     with pytest.raises(ValueError):
-        rootio.write_tree(tmp_path / "a.root", "T", {"x": np.array(["a", "b"])})
+        rootio.write_tree(tmp_path / "a.root", "T", {"x": np.array([1 + 2j, 3j])})
     (tmp_path / "n.root").write_bytes(b"nope" * 100)
     with pytest.raises(ValueError):
         rootio.read_tree(tmp_path / "n.root")
@@ -99,7 +100,8 @@ def test_cross_check_with_uproot_where_installed(tmp_path):
     files opened by the own reader.  Runs wherever uproot is installed."""
     uproot = pytest.importorskip("uproot")
     cols = columns(3000)
-    cols.pop("flag")                      # uproot writes bool branches with its own leaf conventions: numbers only here
+    cols.pop("flag")                      # uproot writes bool and string branches with its own conventions: numbers only
+    names = cols.pop("ParticleName")
     path = tmp_path / "ours.root"
     rootio.write_tree(path, "PhaseSpace", cols, compression=1, basket_entries=1000)
     with uproot.open(path) as f:
@@ -108,6 +110,10 @@ def test_cross_check_with_uproot_where_installed(tmp_path):
         got = t.arrays(library="np")
         for k, v in cols.items():
             assert np.array_equal(got[k], v), k
+    with_names = tmp_path / "names.root"
+    rootio.write_tree(with_names, "PhaseSpace", {"ParticleName": names, "x": cols["KineticEnergy"]})
+    with uproot.open(with_names) as f:
+        assert f["PhaseSpace"]["ParticleName"].array(library="np").tolist() == names.tolist()
     theirs = tmp_path / "theirs.root"
     with uproot.recreate(theirs, compression=uproot.ZLIB(1)) as f:
         f["PhaseSpace"] = cols

@@ -447,7 +447,10 @@ class GpuSimulationEngine:
         jobs = [(i, key) for i, a in enumerate(self.dose_actors) for key, _, _, _ in a.fetch_plan(single_run)]
         if not jobs:
             return
-        pool = ThreadPoolExecutor(max_workers=min(len(jobs), 4))
+        # ONE worker: gate_b200_host_register touches the pages of an array from several threads itself (0.09 s for a
+        # 0.6 GB image on the GPU box); three arrays registered side by side contend for the same cores and locks and
+        # took 0.35 ... 0.65 s instead of 3 x 0.09 s one after the other (tools/probe_pin.py)
+        pool = ThreadPoolExecutor(max_workers=1)
 
         def make(i):
             arr = np.empty(e.dose_grid_shape(self.ids[0][1][i]), dtype=np.float64)

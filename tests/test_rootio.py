@@ -121,3 +121,36 @@ def test_cross_check_with_uproot_where_installed(tmp_path):
     assert set(avail) == set(cols)
     for k, v in cols.items():
         assert np.array_equal(out[k], v), k
+
+
+def test_round_trip_property(tmp_path):
+    """random schemas: any mix of the supported column types, lengths, basket sizes, compression and layouts"""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    dtypes = ["float64", "float32", "int64", "int32", "int16", "int8", "uint8", "uint16", "uint32", "bool", "str"]
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(st.lists(st.sampled_from(dtypes), min_size=1, max_size=6), st.integers(0, 400), st.integers(1, 300),
+           st.sampled_from([0, 1, 9]), st.booleans(), st.integers(0, 2**31 - 1))
+    def check(kinds, n, basket, comp, big, seed):
+        r = np.random.default_rng(seed)
+        cols = {}
+        for i, k in enumerate(kinds):
+            if k == "str":
+                words = np.array(["", "gamma", "e+", "γ", "y" * 260])
+                cols[f"b{i}"] = words[r.integers(0, len(words), n)] if n else np.zeros(0, dtype="U1")
+            elif k == "bool":
+                cols[f"b{i}"] = r.integers(0, 2, n).astype(bool)
+            elif k.startswith("float"):
+                cols[f"b{i}"] = r.normal(size=n).astype(k)
+            else:
+                info = np.iinfo(k)
+                cols[f"b{i}"] = r.integers(info.min, info.max, n, dtype=k, endpoint=True)
+        path = tmp_path / "p.root"
+        rootio.write_tree(path, "t", cols, compression=comp, basket_entries=basket, big=big)
+        out, avail = rootio.read_tree(path)
+        assert avail == list(cols)
+        for name, v in cols.items():
+            assert np.array_equal(out[name], v), (name, kinds)
+            assert out[name].dtype == v.dtype or v.dtype.kind == "U"
+
+    check()
